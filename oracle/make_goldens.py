@@ -1,0 +1,145 @@
+#!/usr/bin/env python
+"""Generate tests/golden/ref_*.npz by running the REFERENCE's own functions (imported from
+/root/reference behind oracle/ref_stub, see oracle/ref_runner.py) on small seeded inputs.
+TEST INFRASTRUCTURE ONLY; run in the build container, outputs are committed:
+
+    python oracle/make_goldens.py
+
+Every file is self-contained: inputs (CSR of the training graph, features or a feature
+spec, links, num_hops, K, flow, strategy) and the reference's outputs in canonical order
+(operators x0..xK row-stacked, row_ptr, the global id of every output row, and for PoS
+flows the node / hop / induced-edge lists of every link from the reference's
+k_hop_subgraph).  The `union` strategy has no golden: the reference raises for it
+(tuned_SIGN.py:243).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.join(HERE, '..')
+sys.path.insert(0, ROOT)
+
+from oracle import ref_runner as rr          # noqa: E402
+from s3grl_b200 import datasets as ds        # noqa: E402
+
+OUT = os.path.join(ROOT, 'tests', 'golden')
+
+
+def features_from_spec(spec, A, num_nodes):
+    """Feature matrices are rebuilt from a spec where storing them would bloat the fixture."""
+    kind = spec.split(':')[0]
+    if kind == 'cora':
+        _, _, X = ds.load_graph('cora')
+        return ds.normalize_features(X)
+    if kind == 'degree':
+        return ds.normalize_features(ds.degree_one_hot(A, int(spec.split(':')[1])))
+    if kind == 'synthetic':
+        _, F, density, seed = spec.split(':')
+        return ds.synthetic_features(num_nodes, int(F), float(density), int(seed))
+    raise ValueError(spec)
+
+
+def _graph_dump(links, h, A):
+    node_ptr, edge_ptr, nodes, hops, edges = [0], [0], [], [], []
+    for i in range(links.shape[1]):
+        cn, hp, ed = rr.ref_k_hop(int(links[0, i]), int(links[1, i]), h, A)
+        nodes.append(cn)
+        hops.append(hp)
+        edges.append(ed)
+        node_ptr.append(node_ptr[-1] + cn.size)
+        edge_ptr.append(edge_ptr[-1] + ed.shape[0])
+    return dict(node_ptr=np.asarray(node_ptr, np.int64), edge_ptr=np.asarray(edge_ptr, np.int64),
+                nodes=np.concatenate(nodes).astype(np.int32), hops=np.concatenate(hops).astype(np.int8),
+                edges=np.concatenate(edges, 0).astype(np.int32))
+
+
+def make_case(name, A, links, flow, K, num_hops=0, strategy=None, X=None, x_spec=None):
+    A = A.tocsr()
+    A.sort_indices()
+    N = A.shape[0]
+    feats = X if X is not None else features_from_spec(x_spec, A, N)
+    links = np.ascontiguousarray(links, dtype=np.int64)
+    if flow == 'pos':
+        r = rr.ref_pos(links, num_hops, A, feats, K, strategy)
+        extra = _graph_dump(links, num_hops, A)
+        extra['row_gid'] = r['row_gid']
+    elif flow == 'sop':
+        r = rr.ref_sop(links, A, feats, K)
+        extra = {}
+    else:
+        raise ValueError(flow)
+    out = dict(indptr=A.indptr.astype(np.int64), indices=A.indices.astype(np.int32),
+               adata=A.data.astype(np.int64), num_nodes=np.int64(N), links=links,
+               num_hops=np.int64(num_hops), K=np.int64(K), flow=np.str_(flow),
+               strategy=np.str_(strategy or ''), row_ptr=r['row_ptr'], **extra)
+    if X is not None:
+        out['X'] = np.asarray(X, np.float32)
+    else:
+        out['x_spec'] = np.str_(x_spec)
+    for k, x in enumerate(r['xs']):
+        out[f'x{k}'] = x.astype(np.float32)
+    path = os.path.join(OUT, f'ref_{name}.npz')
+    np.savez_compressed(path, **out)
+    print(f"{name}: L={links.shape[1]} R={int(r['row_ptr'][-1])} F'={r['xs'][0].shape[1]} "
+          f"-> {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def tiny_graphs():
+    """Hand graphs for the edge cases of SURVEY.md A.6: isolated endpoints, n == 2, an
+    endpoint whose only neighbour is the other endpoint, pendant paths, a hub, two components."""
+    E = [(0, 1), (1, 2), (2, 3), (3, 4), (4, 5),          # path 0..5
+         (6, 7), (6, 8), (7, 8), (8, 9),                  # triangle + pendant
+         (10, 11), (10, 12), (10, 13), (10, 14), (10, 15), (11, 12),   # hub 10
+         (16, 17),                                        # lone edge
+         (5, 6)]                                          # bridge
+    N = 21                                                # 18, 19, 20 isolated
+    e = np.asarray([(min(a, b), max(a, b)) for a, b in E], dtype=np.int64)
+    A = ds.adjacency(e, N)
+    links = np.asarray([(0, 1), (1, 0), (0, 5), (2, 4), (6, 7), (7, 9), (10, 11), (11, 12), (13, 14),
+                        (16, 17), (18, 19), (18, 0), (3, 20), (10, 8), (5, 6), (12, 15), (17, 4)]).T
+    rng = np.random.default_rng(7)
+    X = rng.random((N, 5), dtype=np.float32)
+    return A, links, X
+
+
+def sample_links(splits, count, seed):
+    links = ds.all_links(splits)
+    pick = np.sort(np.random.default_rng(seed).choice(links.shape[1], count, replace=False))
+    return links[:, pick]
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    A, links, X = tiny_graphs()
+    for h in (1, 2, 3):
+        make_case(f'tiny_pos_h{h}', A, links, 'pos', 3, h, None, X=X)
+    make_case('tiny_posplus_h2', A, links, 'pos', 3, 2, 'intersection', X=X)
+    make_case('tiny_sop', A, links, 'sop', 3, X=X)
+
+    edges, N, _ = ds.load_graph('cora')
+    A, splits = ds.split_links(edges, N, seed=1)
+    make_case('cora_pos_fullF', A, sample_links(splits, 20, 0), 'pos', 3, 3, None, x_spec='cora')
+    make_case('cora_pos', A, sample_links(splits, 160, 1), 'pos', 3, 3, None, x_spec='synthetic:24:0.3:5')
+    make_case('cora_posplus', A, sample_links(splits, 160, 2), 'pos', 3, 3, 'intersection',
+              x_spec='synthetic:24:0.3:5')
+
+    edges, N, _ = ds.load_graph('usair')
+    A, splits = ds.split_links(edges, N, seed=1)
+    make_case('usair_sop_degree', A, sample_links(splits, 12, 0), 'sop', 3, x_spec='degree:1024')
+    make_case('usair_sop', A, sample_links(splits, 160, 1), 'sop', 3, x_spec='synthetic:16:0.5:6')
+    make_case('usair_posplus', A, sample_links(splits, 120, 2), 'pos', 3, 2, 'intersection',
+              x_spec='synthetic:16:0.5:6')
+
+    edges, N, _ = ds.load_graph('yeast')
+    A, splits = ds.split_links(edges, N, seed=1)
+    make_case('yeast_pos_k5', A, sample_links(splits, 100, 3), 'pos', 5, 2, None, x_spec='synthetic:32:0.5:8')
+
+    edges, N, _ = ds.load_graph('power')
+    A, splits = ds.split_links(edges, N, seed=1)
+    make_case('power_pos_k5', A, sample_links(splits, 100, 4), 'pos', 5, 2, None, x_spec='synthetic:8:1.0:9')
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,149 @@
+"""Run the REAL reference functions (imported, unmodified, from /root/reference behind the
+stand-ins in oracle/ref_stub) and canonicalise their outputs.  TEST INFRASTRUCTURE ONLY and
+build-container only: /root/reference does not exist on the GPU box, so nothing under
+`-m gpu`, smoke() or bench.py may import this module.  Used by oracle/make_goldens.py and by
+tests/test_oracle_vs_reference.py (skipped when the reference is absent).
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REFERENCE = os.environ.get('S3GRL_REFERENCE', '/root/reference')
+
+
+def available():
+    return os.path.isfile(os.path.join(REFERENCE, 'tuned_SIGN.py'))
+
+
+_mods = None
+
+
+def load_reference():
+    """-> (utils, tuned_SIGN) modules of the reference."""
+    global _mods
+    if _mods is None:
+        if not available():
+            raise RuntimeError(f"reference not found at {REFERENCE}")
+        for p in (REFERENCE, os.path.join(_HERE, 'ref_stub')):
+            if p not in sys.path:
+                sys.path.insert(0, p)
+        import tqdm as _tqdm_mod  # silence the reference's progress bars
+        import tuned_SIGN
+        import utils
+        quiet = lambda it=None, *a, **k: it  # noqa: E731
+        tuned_SIGN.tqdm = quiet
+        utils.tqdm = quiet
+        _mods = (utils, tuned_SIGN)
+    return _mods
+
+
+@contextlib.contextmanager
+def _quiet():
+    with contextlib.redirect_stdout(io.StringIO()):
+        yield
+
+
+def ref_k_hop(src, dst, num_hops, A):
+    """Reference k_hop_subgraph (utils.py:47-85) -> canonical
+    (nodes int64 [n], hops int32 [n], edges int64 [m,2] of GLOBAL ids sorted by canonical
+    (local row, local col)).  Edges are the non-zero entries `ssp.find` returns
+    (tuned_SIGN.py:153), i.e. after the target-link mask."""
+    import scipy.sparse as ssp
+    utils, _ = load_reference()
+    nodes, sub, dists, _, _ = utils.k_hop_subgraph(src, dst, num_hops, A)
+    nodes = np.asarray(nodes, dtype=np.int64)
+    dists = np.asarray(dists, dtype=np.int32)
+    order = np.concatenate([[0, 1], 2 + np.lexsort((nodes[2:], dists[2:]))]).astype(np.int64)
+    rank = np.empty_like(order)
+    rank[order] = np.arange(order.size)
+    u, v, _ = ssp.find(sub)
+    lu, lv = rank[u], rank[v]
+    eo = np.lexsort((lv, lu))
+    cn = nodes[order]
+    edges = np.stack([cn[lu[eo]], cn[lv[eo]]], axis=1) if eo.size else np.zeros((0, 2), np.int64)
+    return cn, dists[order], edges
+
+
+def _sign_kwargs(K, strategy):
+    return {'sign_k': K, 'use_feature': True, 'sign_type': 'PoS', 'optimize_sign': True,
+            'k_heuristic': 0 if strategy is None else 1, 'k_node_set_strategy': strategy}
+
+
+def ref_pos(links, num_hops, A, X, K, strategy=None):
+    """get_PoS_prepped_ds / get_PoS_Plus_prepped_ds (tuned_SIGN.py:137-262) through
+    extract_enclosing_subgraphs (utils.py:446-496) -> dict(xs, row_ptr, row_gid) with the rows
+    of every link put in canonical order: row 0 = src, row 1 = dst, extra rows by ascending
+    global id (== ascending canonical local id, all extra rows being hop-1 nodes)."""
+    utils, tuned = load_reference()
+    link_index = torch.as_tensor(np.asarray(links), dtype=torch.long)
+    x = torch.as_tensor(np.asarray(X), dtype=torch.float32)
+    with _quiet():
+        data_list = utils.extract_enclosing_subgraphs(
+            link_index, A, x, 1, num_hops, 'zo', 1.0, None, False, None, None,
+            _sign_kwargs(K, strategy), powers_of_A=[], data=None)
+    xs = [[] for _ in range(K + 1)]
+    row_ptr, row_gid = [0], []
+    for i, d in enumerate(data_list):
+        src, dst = int(links[0][i]), int(links[1][i])
+        s = d['x'].shape[0]
+        gids = [src, dst]
+        if strategy is not None:
+            # recover which node each extra row is: same calls, same (deterministic) set order
+            nodes, sub, _, _, _ = utils.k_hop_subgraph(src, dst, num_hops, A)
+            if strategy == 'intersection':
+                sel = utils.neighbors({0}, sub).intersection(utils.neighbors({1}, sub))
+            else:
+                sel = utils.neighbors({0}, sub).union(utils.neighbors({1}, sub))
+            gids += [int(nodes[j]) for j in list(sel)]
+        assert len(gids) == s
+        gids = np.asarray(gids, dtype=np.int64)
+        order = np.concatenate([[0, 1], 2 + np.argsort(gids[2:], kind='stable')]).astype(np.int64)
+        row_gid.append(gids[order])
+        keys = ['x'] + [f'x{k}' for k in range(1, K + 1)]
+        for k, key in enumerate(keys):
+            xs[k].append(d[key].numpy().astype(np.float32)[order])
+        row_ptr.append(row_ptr[-1] + s)
+    F1 = x.shape[1] + 1
+    xs = [np.concatenate(v, 0) if v else np.zeros((0, F1), np.float32) for v in xs]
+    return dict(xs=xs, row_ptr=np.asarray(row_ptr, np.int64),
+                row_gid=np.concatenate(row_gid) if row_gid else np.zeros(0, np.int64))
+
+
+def ref_sop_powers(A, K):
+    """Global normalised powers exactly as SEALDataset.process builds them
+    (sgrl_link_pred.py:161-178; that file cannot be imported without real PyG, so its ten
+    lines of SparseTensor calls are issued here against the same stand-in)."""
+    load_reference()
+    from torch_sparse import SparseTensor
+    coo = A.tocoo()
+    # edge_index holds one column per stored edge; multiplicity -> repeated columns
+    rep = np.asarray(coo.data, dtype=np.int64)
+    row = torch.as_tensor(np.repeat(coo.row, rep), dtype=torch.long)
+    col = torch.as_tensor(np.repeat(coo.col, rep), dtype=torch.long)
+    adj_t = SparseTensor(row=row, col=col, sparse_sizes=A.shape)
+    deg = adj_t.sum(dim=1).to(torch.float)
+    dis = deg.pow(-0.5)
+    dis[dis == float('inf')] = 0
+    adj_t = dis.view(-1, 1) * adj_t * dis.view(1, -1)
+    powers = [adj_t]
+    for _ in range(2, K + 1):
+        powers += [adj_t @ powers[-1]]
+    return powers
+
+
+def ref_sop(links, A, X, K):
+    """get_SoP_prepped_ds (tuned_SIGN.py:49-134) -> dict(xs, row_ptr)."""
+    utils, tuned = load_reference()
+    link_index = torch.as_tensor(np.asarray(links), dtype=torch.long)
+    x = torch.as_tensor(np.asarray(X), dtype=torch.float32)
+    powers = ref_sop_powers(A, K)
+    with _quiet():
+        data_list = tuned.OptimizedSignOperations.get_SoP_prepped_ds(powers, link_index, A, x, 1)
+    keys = ['x'] + [f'x{k}' for k in range(1, K + 1)]
+    xs = [np.concatenate([np.asarray(d[key], dtype=np.float32) for d in data_list], 0) for key in keys]
+    return dict(xs=xs, row_ptr=np.arange(len(data_list) + 1, dtype=np.int64) * 2)

@@ -1,0 +1,43 @@
+"""`Data`: attribute bag with item access, as the reference uses it
+(tuned_SIGN.py:117-131, :182-185: ``Data(x=..., y=...)`` then ``data[f'x{k}'] = ...``)."""
+
+
+class Data:
+    def __init__(self, **kwargs):
+        self.__dict__['_store'] = dict(kwargs)
+
+    def __getattr__(self, key):
+        store = self.__dict__['_store']
+        if key in store:
+            return store[key]
+        if key in ('x', 'y', 'edge_index', 'edge_weight', 'edge_attr', 'pos'):
+            return None
+        raise AttributeError(key)
+
+    def __setattr__(self, key, value):
+        self.__dict__['_store'][key] = value
+
+    def __getitem__(self, key):
+        return self.__dict__['_store'][key]
+
+    def __setitem__(self, key, value):
+        self.__dict__['_store'][key] = value
+
+    def __delitem__(self, key):
+        del self.__dict__['_store'][key]
+
+    def __contains__(self, key):
+        return key in self.__dict__['_store']
+
+    def pop(self, key):
+        return self.__dict__['_store'].pop(key)
+
+    def keys(self):
+        return list(self.__dict__['_store'].keys())
+
+    @property
+    def num_nodes(self):
+        st = self.__dict__['_store']
+        if 'num_nodes' in st:
+            return st['num_nodes']
+        return st['x'].shape[0]

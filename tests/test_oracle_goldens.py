@@ -1,0 +1,60 @@
+"""The oracle (oracle/s3grl_oracle.py) against the reference's own outputs committed under
+tests/golden/ — this is what pins the oracle (the reference has no tests)."""
+import numpy as np
+import pytest
+
+from golden_util import Case, assert_features_close, case_names
+from oracle import s3grl_oracle as orc
+
+
+@pytest.mark.parametrize('name', case_names('pos'))
+def test_pos_flows_match_reference(name):
+    c = Case(name)
+    out = orc.pos_precompute(c.links, c.num_hops, c.A, c.X, c.K, c.strategy, keep_graphs=True)
+    assert np.array_equal(out['row_ptr'], c.row_ptr)
+    for k in range(c.K + 1):
+        assert_features_close(out['xs'][k], c.xs[k], what=f'{name} x{k}')
+    # index parity: node lists, hop labels, induced + masked edge lists, bit-exact
+    for i, g in enumerate(out['graphs']):
+        a, b = c.node_ptr[i], c.node_ptr[i + 1]
+        assert np.array_equal(g['nodes'], c.nodes[a:b]), f'{name} link {i} nodes'
+        assert np.array_equal(g['hops'], c.hops[a:b]), f'{name} link {i} hops'
+        rows = np.repeat(np.arange(g['nodes'].size), np.diff(g['lrowptr']))
+        e = np.stack([g['nodes'][rows], g['nodes'][g['lcol']]], 1)
+        assert np.array_equal(e, c.edges[c.edge_ptr[i]:c.edge_ptr[i + 1]]), f'{name} link {i} edges'
+        assert np.array_equal(g['nodes'][g['sel']], c.row_gid[c.row_ptr[i]:c.row_ptr[i + 1]])
+
+
+@pytest.mark.parametrize('name', case_names('sop'))
+def test_sop_matches_reference(name):
+    c = Case(name)
+    out = orc.sop_precompute(c.links, c.A, c.X, c.K)
+    assert np.array_equal(out['row_ptr'], c.row_ptr)
+    for k in range(c.K + 1):
+        assert_features_close(out['xs'][k], c.xs[k], what=f'{name} x{k}')
+
+
+def test_union_rule_is_superset_of_intersection():
+    c = Case('usair_posplus')
+    inter = orc.pos_precompute(c.links[:, :20], c.num_hops, c.A, c.X, c.K, 'intersection', keep_graphs=True)
+    union = orc.pos_precompute(c.links[:, :20], c.num_hops, c.A, c.X, c.K, 'union', keep_graphs=True)
+    for gi, gu in zip(inter['graphs'], union['graphs']):
+        assert set(gi['sel']) <= set(gu['sel'])
+        assert list(gu['sel'][:2]) == [0, 1] and np.all(np.diff(gu['sel'][2:]) > 0)
+        # rows 0,1 do not depend on the strategy
+        for k in range(c.K + 1):
+            assert np.array_equal(gi['xs'][k][:2], gu['xs'][k][:2])
+
+
+def test_src_equals_dst_rejected():
+    c = Case('tiny_pos_h1')
+    with pytest.raises(ValueError):
+        orc.k_hop_subgraph(3, 3, 2, c.A)
+
+
+def test_float64_oracle_agrees():
+    c = Case('cora_pos')
+    a = orc.pos_precompute(c.links[:, :30], c.num_hops, c.A, c.X, c.K)
+    b = orc.pos_precompute(c.links[:, :30], c.num_hops, c.A, c.X, c.K, dtype=np.float64)
+    for k in range(c.K + 1):
+        assert_features_close(a['xs'][k], b['xs'][k], what=f'x{k}')
