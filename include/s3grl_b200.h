@@ -1,0 +1,166 @@
+/*
+ * s3grl_b200.h — C ABI of the B200-native S3GRL precompute library (libs3grl_b200.so).
+ *
+ * The reference (venomouscyanide/S3GRL) has no FFI layer: its hot path is the Python
+ * call  extract_enclosing_subgraphs(link_index, A, x, y, num_hops, ..., sign_kwargs,
+ * powers_of_A, data)  (reference utils.py:446-449) and beneath it the three static methods
+ * OptimizedSignOperations.get_PoS_prepped_ds / get_PoS_Plus_prepped_ds / get_SoP_prepped_ds
+ * (reference tuned_SIGN.py:137, :192, :49).  This header is what a binding for that path
+ * binds instead: plain pointers and sizes, no torch types, every pointer a DEVICE pointer
+ * owned by the caller, every call asynchronous on the given cudaStream_t (passed as void*).
+ * The library allocates nothing: scratch comes from a caller-supplied arena.
+ *
+ * One precompute call over a batch of B "records" is three stages (north_star kernels 1-3):
+ *
+ *   s3_extract  : per record, h-hop frontier expansion over the device-resident CSR, dedup,
+ *                 canonical renumbering, induced + target-masked local CSR, row selection.
+ *                 replaces reference utils.py:33-85 (neighbors, k_hop_subgraph BFS branch),
+ *                 the ssp.find at tuned_SIGN.py:153/:208 and the CCN row selection
+ *                 tuned_SIGN.py:228-238.
+ *   s3_plan     : row_ptr / work-item lists from the per-record selected-row counts
+ *                 (the slices PyG's collate would record, sgrl_link_pred.py:204).
+ *   s3_diffuse  : per work item, S = D^-1/2 A_sub D^-1/2 and the K row vectors e_sel^T S^k
+ *                 replaces tuned_SIGN.py:155-175 (normalise, SpGEMM powers, row select)
+ *                 and, in SoP flow, sgrl_link_pred.py:161-178 + tuned_SIGN.py:60-86, :106-113.
+ *   s3_gather   : per work item, x_k[sel] = (e_sel^T S^k) [label | X_sub] for k = 0..K written
+ *                 straight into the K+1 row-stacked operator matrices the SIGNNet models
+ *                 consume (tuned_SIGN.py:177-187, :94-133; layout models.py:372).
+ *
+ * A "record" is one target link (PoS / PoS Plus: two seeds, target edge masked, induced
+ * degrees) or one link endpoint (SoP: one seed, K-hop ball, global degrees; record 2i is
+ * the source of link i, 2i+1 its destination).
+ *
+ * Canonical order (bit-exact contract): local node ids are [seeds..., then ascending
+ * (hop, global id)]; row j of the local CSR lists j's neighbours in ascending GLOBAL id;
+ * extra selected rows ascend by local id.
+ */
+#ifndef S3GRL_B200_H
+#define S3GRL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S3_VERSION 100
+
+/* return codes (the reference raises Python exceptions; see INTEGRATION.md for the mapping) */
+#define S3_OK 0
+#define S3_ERR_INVALID_ARG 1     /* null pointer, negative size, unsupported K / hops        */
+#define S3_ERR_UNSUPPORTED 2     /* graph too large for the selected extraction tier        */
+#define S3_ERR_CUDA 3            /* a CUDA runtime call failed; see s3_last_cuda_error()     */
+#define S3_ERR_NOT_IMPLEMENTED 4 /* unknown strategy / flow (reference: NotImplementedError) */
+
+/* flows (reference sign_type) and row-selection strategies (reference k_node_set_strategy) */
+#define S3_FLOW_POS 0
+#define S3_FLOW_SOP 1
+#define S3_STRATEGY_NONE 0          /* PoS: rows [0,1]              tuned_SIGN.py:173     */
+#define S3_STRATEGY_INTERSECTION 1  /* PoS Plus, common neighbours  tuned_SIGN.py:232-233 */
+#define S3_STRATEGY_UNION 2         /* PoS Plus, union minus {0,1}  tuned_SIGN.py:230-231 */
+
+#define S3_MAX_HOPS 8
+#define S3_MAX_K 15
+
+/* per-record status written by s3_extract into cnt[S3_CNT_STATUS] */
+#define S3_REC_OK 0
+#define S3_REC_ARENA_OVERFLOW 1  /* arena too small: re-run the batch with a larger arena            */
+#define S3_REC_BAD_LINK 2        /* node id out of range or src == dst               */
+
+/* per-record int64 offsets (in 4-byte words from the arena base), off[rec*S3_NOFF + i] */
+#define S3_OFF_NODES 0   /* int32 global ids, n                                   */
+#define S3_OFF_ROWPTR 1  /* int32 local CSR row pointer, n+1                      */
+#define S3_OFF_LCOL 2    /* int32 local column ids, m                             */
+#define S3_OFF_SEL 3     /* int32 extra selected local ids, s - num_seeds         */
+#define S3_OFF_F32 4     /* float scratch of the record's work items              */
+#define S3_NOFF 5
+
+/* per-record int32 counts, cnt[rec*S3_NCNT + i] */
+#define S3_CNT_N 0        /* subgraph nodes                                       */
+#define S3_CNT_M 1        /* directed induced edges after masking                 */
+#define S3_CNT_S 2        /* selected rows                                        */
+#define S3_CNT_STATUS 3
+#define S3_CNT_PARTNER 4  /* SoP: local id of the other endpoint in the ball, or -1 */
+#define S3_CNT_HOP0 5     /* S3_CNT_HOP0 + l = number of nodes at hop l, l = 0..S3_MAX_HOPS */
+#define S3_NCNT 16
+
+/* int64 counters[S3_NCTR]; the caller zeroes them before s3_extract */
+#define S3_CTR_CURSOR 0    /* arena words requested so far (may exceed the capacity)      */
+#define S3_CTR_ERRORS 1    /* number of records whose status != S3_REC_OK                 */
+#define S3_CTR_ROWS 2      /* total selected rows   (written by s3_plan)                  */
+#define S3_CTR_ITEMS 3     /* total work items      (written by s3_plan)                  */
+#define S3_CTR_MAX_N 4     /* largest subgraph in the batch                               */
+#define S3_CTR_SUM_N 5     /* sum of n  (roofline accounting: 4*F*sum_n feature bytes)    */
+#define S3_CTR_SUM_D 6     /* sum over subgraph nodes of their global degree (4*D bytes)  */
+#define S3_NCTR 8
+
+/* Device-resident graph: CSR of the training graph (both directions stored, columns
+ * ascending and unique per row — what scipy's csr_matrix gives the reference at
+ * sgrl_link_pred.py:111-114; stored values are not needed, tuned_SIGN.py:153 drops them)
+ * and the feature matrix, rows padded to a multiple of 4 floats for 128-bit loads. */
+typedef struct s3_graph {
+    const int64_t* indptr;  /* [num_nodes + 1]                              */
+    const int32_t* indices; /* [indptr[num_nodes]]                          */
+    const float* x;         /* [num_nodes, ldx] row-major, 16-byte aligned  */
+    int64_t num_nodes;
+    int64_t num_feat;       /* F                                            */
+    int64_t ldx;            /* row stride in floats, multiple of 4, >= F    */
+} s3_graph;
+
+/* One batch of records and its scratch. */
+typedef struct s3_batch {
+    const int64_t* link_src; /* [num_links] device                                         */
+    const int64_t* link_dst; /* [num_links] device                                         */
+    int64_t num_links;
+    int32_t flow;            /* S3_FLOW_*                                                   */
+    int32_t strategy;        /* S3_STRATEGY_* (PoS flow only)                               */
+    int32_t num_hops;        /* PoS: h.  SoP: ignored (the ball radius is sign_k)           */
+    int32_t sign_k;          /* K operators beyond x                                        */
+    int32_t* arena;          /* scratch, 16-byte aligned                                    */
+    int64_t arena_words;     /* capacity in 4-byte words                                    */
+    int64_t* off;            /* [num_records * S3_NOFF]                                     */
+    int32_t* cnt;            /* [num_records * S3_NCNT]                                     */
+    int64_t* counters;       /* [S3_NCTR]                                                   */
+    /* The next three may be NULL when every record has exactly num_seeds selected rows
+     * (PoS with S3_STRATEGY_NONE, SoP): then record r is work item r and owns output rows
+     * [r*num_seeds, (r+1)*num_seeds). */
+    int64_t* row_ptr;        /* [num_records + 1] output-row offset of each record          */
+    int64_t* item_ptr;       /* [num_records + 1] first work item of each record            */
+    int32_t* item_rec;       /* [total items] record of each work item                      */
+} s3_batch;
+
+int s3_version(void);
+const char* s3_error_string(int code);
+const char* s3_last_cuda_error(void);
+
+/* records in a batch: num_links (PoS) or 2*num_links (SoP) */
+int64_t s3_num_records(const s3_batch* b);
+/* upper bound of work items s3_plan can produce is not known before extract; after
+ * s3_plan + a stream sync the exact numbers are counters[S3_CTR_ROWS] / [S3_CTR_ITEMS]. */
+
+/* dynamic shared memory the bitmap extraction tier needs for this graph, or -1 if the
+ * graph is too large for it (then S3_ERR_UNSUPPORTED from s3_extract). */
+int64_t s3_extract_smem_bytes(int64_t num_nodes, int32_t radius);
+
+int s3_extract(const s3_graph* g, const s3_batch* b, void* stream);
+/* s3_plan: exclusive scans -> row_ptr, item_ptr, counters[S3_CTR_ROWS|ITEMS]. The caller then
+ * synchronises the stream, reads the two totals, allocates item_rec and the outputs, and calls
+ * s3_plan_items to fill item_rec. */
+int s3_plan(const s3_batch* b, void* stream);
+int s3_plan_items(const s3_batch* b, void* stream);
+int s3_diffuse(const s3_graph* g, const s3_batch* b, int64_t num_items, void* stream);
+
+/* out: HOST array of sign_k+1 device pointers; out[k], k = 0..sign_k to the operator matrices, [*, ldo] row-major
+ * float32; record r's rows land at row_base + row_ptr[r] .. ; column 0 is the label /
+ * self-return column, columns 1..F the features (reference tuned_SIGN.py:177-187). */
+int s3_gather(const s3_graph* g, const s3_batch* b, int64_t num_items,
+              float* const* out, int64_t ldo, int64_t row_base, void* stream);
+
+/* Optional dumps for parity checks: canonical global-id edge list of every record,
+ * edges[e] = (global row, global col), e in [edge_ptr[r], edge_ptr[r+1]). */
+int s3_dump_edges(const s3_batch* b, const int64_t* edge_ptr, int32_t* edges_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S3GRL_B200_H */

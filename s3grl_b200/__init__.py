@@ -1,0 +1,15 @@
+"""s3grl_b200 — B200-native (sm_100a) precompute hot path of S3GRL.
+
+Public surface (mirrors the reference for this path):
+    extract_enclosing_subgraphs            reference utils.py:446
+    OptimizedSignOperations                reference tuned_SIGN.py:47
+    DeviceGraph, precompute                tensor-level API beneath them
+The compute lives in lib/libs3grl_b200.so (include/s3grl_b200.h); build it with
+`python -m s3grl_b200.build`.  Importing the package does not need a GPU; calling it does.
+"""
+__version__ = '0.1.0'
+
+from .data import Data, PrecomputedList  # noqa: F401
+from .engine import DeviceGraph, PrecomputeResult, algorithmic_bytes, precompute  # noqa: F401
+from .tuned_sign import OptimizedSignOperations  # noqa: F401
+from .utils import extract_enclosing_subgraphs  # noqa: F401

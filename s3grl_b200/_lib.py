@@ -1,0 +1,85 @@
+"""ctypes binding of libs3grl_b200.so (include/s3grl_b200.h).  There is no fallback: if the
+library cannot be loaded, or a call fails, the product path raises."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'lib', 'libs3grl_b200.so')
+
+# constants mirrored from the header
+S3_OK, S3_ERR_INVALID_ARG, S3_ERR_UNSUPPORTED, S3_ERR_CUDA, S3_ERR_NOT_IMPLEMENTED = 0, 1, 2, 3, 4
+FLOW_POS, FLOW_SOP = 0, 1
+STRATEGY_NONE, STRATEGY_INTERSECTION, STRATEGY_UNION = 0, 1, 2
+MAX_HOPS, MAX_K = 8, 15
+REC_OK, REC_ARENA_OVERFLOW, REC_BAD_LINK = 0, 1, 2
+OFF_NODES, OFF_ROWPTR, OFF_LCOL, OFF_SEL, OFF_F32, NOFF = 0, 1, 2, 3, 4, 5
+CNT_N, CNT_M, CNT_S, CNT_STATUS, CNT_PARTNER, CNT_HOP0, NCNT = 0, 1, 2, 3, 4, 5, 16
+CTR_CURSOR, CTR_ERRORS, CTR_ROWS, CTR_ITEMS, CTR_MAX_N, CTR_SUM_N, CTR_SUM_D, NCTR = 0, 1, 2, 3, 4, 5, 6, 8
+
+EXPORTS = ['s3_version', 's3_error_string', 's3_last_cuda_error', 's3_num_records', 's3_extract_smem_bytes',
+           's3_extract', 's3_plan', 's3_plan_items', 's3_diffuse', 's3_gather', 's3_dump_edges']
+
+
+class Graph(C.Structure):
+    _fields_ = [('indptr', C.c_void_p), ('indices', C.c_void_p), ('x', C.c_void_p),
+                ('num_nodes', C.c_int64), ('num_feat', C.c_int64), ('ldx', C.c_int64)]
+
+
+class Batch(C.Structure):
+    _fields_ = [('link_src', C.c_void_p), ('link_dst', C.c_void_p), ('num_links', C.c_int64),
+                ('flow', C.c_int32), ('strategy', C.c_int32), ('num_hops', C.c_int32), ('sign_k', C.c_int32),
+                ('arena', C.c_void_p), ('arena_words', C.c_int64),
+                ('off', C.c_void_p), ('cnt', C.c_void_p), ('counters', C.c_void_p),
+                ('row_ptr', C.c_void_p), ('item_ptr', C.c_void_p), ('item_rec', C.c_void_p)]
+
+
+class S3Error(RuntimeError):
+    def __init__(self, code, where, detail=''):
+        self.code = code
+        super().__init__(f"{where}: {detail}" if detail else where)
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library once. Raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m s3grl_b200.build` "
+                "(the precompute path has no CPU or PyTorch fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.s3_version.restype = C.c_int
+        L.s3_error_string.restype = C.c_char_p
+        L.s3_error_string.argtypes = [C.c_int]
+        L.s3_last_cuda_error.restype = C.c_char_p
+        L.s3_num_records.restype = C.c_int64
+        L.s3_num_records.argtypes = [C.POINTER(Batch)]
+        L.s3_extract_smem_bytes.restype = C.c_int64
+        L.s3_extract_smem_bytes.argtypes = [C.c_int64, C.c_int32]
+        L.s3_extract.argtypes = [C.POINTER(Graph), C.POINTER(Batch), C.c_void_p]
+        L.s3_plan.argtypes = [C.POINTER(Batch), C.c_void_p]
+        L.s3_plan_items.argtypes = [C.POINTER(Batch), C.c_void_p]
+        L.s3_diffuse.argtypes = [C.POINTER(Graph), C.POINTER(Batch), C.c_int64, C.c_void_p]
+        L.s3_gather.argtypes = [C.POINTER(Graph), C.POINTER(Batch), C.c_int64, C.POINTER(C.c_void_p),
+                                C.c_int64, C.c_int64, C.c_void_p]
+        L.s3_dump_edges.argtypes = [C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p]
+        for fn in ('s3_extract', 's3_plan', 's3_plan_items', 's3_diffuse', 's3_gather', 's3_dump_edges'):
+            getattr(L, fn).restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def check(code, where):
+    """Map a C return code to the exception the reference would raise at the same point."""
+    if code == S3_OK:
+        return
+    L = lib()
+    msg = L.s3_error_string(code).decode()
+    if code == S3_ERR_NOT_IMPLEMENTED:
+        raise NotImplementedError(f"{where}: {msg}")      # reference tuned_SIGN.py:235, utils.py:553
+    if code == S3_ERR_CUDA:
+        raise S3Error(code, where, f"{msg}: {L.s3_last_cuda_error().decode()}")
+    raise S3Error(code, where, msg)

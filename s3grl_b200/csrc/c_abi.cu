@@ -1,0 +1,133 @@
+// extern "C" boundary of libs3grl_b200.so — see include/s3grl_b200.h for the contract and the
+// reference interfaces each entry point replaces.
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace {
+thread_local char g_cuda_err[256] = "";
+
+int cuda_fail(cudaError_t e) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+    return S3_ERR_CUDA;
+}
+
+bool gather_cols_supported(int nw) {
+    return (nw >= 2 && nw <= 8) || nw == 10 || nw == 12 || nw == 14 || nw == 16;
+}
+
+int check_batch(const s3_batch* b) {
+    if (!b || b->num_links < 0) return S3_ERR_INVALID_ARG;
+    if (b->flow != S3_FLOW_POS && b->flow != S3_FLOW_SOP) return S3_ERR_NOT_IMPLEMENTED;
+    if (b->flow == S3_FLOW_POS && (b->strategy < S3_STRATEGY_NONE || b->strategy > S3_STRATEGY_UNION))
+        return S3_ERR_NOT_IMPLEMENTED;  // reference: NotImplementedError(f"check strat {strat}"), tuned_SIGN.py:235
+    if (b->sign_k < 1 || b->sign_k > S3_MAX_K) return S3_ERR_INVALID_ARG;
+    if (!gather_cols_supported(s3::weight_cols(b->flow, b->sign_k))) return S3_ERR_INVALID_ARG;
+    const int radius = b->flow == S3_FLOW_POS ? b->num_hops : b->sign_k;
+    if (radius < 0 || radius > S3_MAX_HOPS) return S3_ERR_INVALID_ARG;
+    if (b->num_links > 0 && (!b->link_src || !b->link_dst || !b->arena || !b->off || !b->cnt || !b->counters))
+        return S3_ERR_INVALID_ARG;
+    if (b->arena_words < 0 || (reinterpret_cast<uintptr_t>(b->arena) & 15)) return S3_ERR_INVALID_ARG;
+    return S3_OK;
+}
+
+int check_graph(const s3_graph* g, bool need_x) {
+    if (!g || !g->indptr || !g->indices || g->num_nodes <= 0 || g->num_nodes > INT32_MAX) return S3_ERR_INVALID_ARG;
+    if (need_x) {
+        if (!g->x || g->num_feat <= 0 || g->ldx < g->num_feat || (g->ldx & 3)) return S3_ERR_INVALID_ARG;
+        if (reinterpret_cast<uintptr_t>(g->x) & 15) return S3_ERR_INVALID_ARG;
+    }
+    return S3_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int s3_version(void) { return S3_VERSION; }
+
+const char* s3_error_string(int code) {
+    switch (code) {
+        case S3_OK: return "ok";
+        case S3_ERR_INVALID_ARG: return "invalid argument";
+        case S3_ERR_UNSUPPORTED: return "graph too large for the bitmap extraction tier";
+        case S3_ERR_CUDA: return "CUDA error";
+        case S3_ERR_NOT_IMPLEMENTED: return "unknown flow or strategy";
+        default: return "unknown error code";
+    }
+}
+
+const char* s3_last_cuda_error(void) { return g_cuda_err; }
+
+int64_t s3_num_records(const s3_batch* b) { return b->flow == S3_FLOW_SOP ? 2 * b->num_links : b->num_links; }
+
+int64_t s3_extract_smem_bytes(int64_t num_nodes, int32_t radius) {
+    if (num_nodes <= 0 || radius < 0 || radius > S3_MAX_HOPS) return -1;
+    const int64_t W = (num_nodes + 31) / 32;
+    const int64_t bytes = (1 + 2 * (int64_t)radius) * W * 4;
+    return bytes <= s3::kMaxSmemBytes ? bytes : -1;
+}
+
+int s3_extract(const s3_graph* g, const s3_batch* b, void* stream) {
+    int rc = check_graph(g, false);
+    if (rc != S3_OK) return rc;
+    rc = check_batch(b);
+    if (rc != S3_OK) return rc;
+    const int radius = b->flow == S3_FLOW_POS ? b->num_hops : b->sign_k;
+    if (s3_extract_smem_bytes(g->num_nodes, radius) < 0) return S3_ERR_UNSUPPORTED;
+    cudaError_t e = s3::launch_extract_bitmap(*g, *b, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? S3_OK : cuda_fail(e);
+}
+
+int s3_plan(const s3_batch* b, void* stream) {
+    int rc = check_batch(b);
+    if (rc != S3_OK) return rc;
+    if (!b->row_ptr || !b->item_ptr) return S3_ERR_INVALID_ARG;
+    cudaError_t e = s3::launch_plan(*b, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? S3_OK : cuda_fail(e);
+}
+
+int s3_plan_items(const s3_batch* b, void* stream) {
+    int rc = check_batch(b);
+    if (rc != S3_OK) return rc;
+    if (!b->item_ptr || !b->item_rec) return S3_ERR_INVALID_ARG;
+    cudaError_t e = s3::launch_plan_items(*b, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? S3_OK : cuda_fail(e);
+}
+
+int s3_diffuse(const s3_graph* g, const s3_batch* b, int64_t num_items, void* stream) {
+    int rc = check_graph(g, false);
+    if (rc != S3_OK) return rc;
+    rc = check_batch(b);
+    if (rc != S3_OK) return rc;
+    if (num_items < 0) return S3_ERR_INVALID_ARG;
+    cudaError_t e = s3::launch_diffuse(*g, *b, num_items, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? S3_OK : cuda_fail(e);
+}
+
+int s3_gather(const s3_graph* g, const s3_batch* b, int64_t num_items, float* const* out, int64_t ldo, int64_t row_base,
+              void* stream) {
+    int rc = check_graph(g, true);
+    if (rc != S3_OK) return rc;
+    rc = check_batch(b);
+    if (rc != S3_OK) return rc;
+    if (num_items < 0 || !out || ldo < g->num_feat + 1 || row_base < 0) return S3_ERR_INVALID_ARG;
+    s3::OutPtrs o;
+    memset(&o, 0, sizeof(o));
+    for (int k = 0; k <= b->sign_k; ++k) {
+        if (!out[k]) return S3_ERR_INVALID_ARG;
+        o.p[k] = out[k];
+    }
+    cudaError_t e = s3::launch_gather(*g, *b, num_items, o, ldo, row_base, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? S3_OK : cuda_fail(e);
+}
+
+int s3_dump_edges(const s3_batch* b, const int64_t* edge_ptr, int32_t* edges_out, void* stream) {
+    int rc = check_batch(b);
+    if (rc != S3_OK) return rc;
+    if (!edge_ptr || !edges_out) return S3_ERR_INVALID_ARG;
+    cudaError_t e = s3::launch_dump_edges(*b, edge_ptr, edges_out, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? S3_OK : cuda_fail(e);
+}
+
+}  // extern "C"

@@ -1,0 +1,69 @@
+// Shared device helpers and launch declarations for libs3grl_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/s3grl_b200.h"
+
+namespace s3 {
+
+constexpr int kExtractThreads = 256;
+constexpr int kDiffuseThreads = 256;
+constexpr int kGatherThreads = 128;
+constexpr int kMaxSmemBytes = 200 * 1024;  // bitmap tier budget (227 KB is the hardware limit)
+
+// selected rows a work item carries; (K+1)*kSC weight columns per subgraph node
+__host__ __device__ inline int sel_chunk(int flow) { return flow == S3_FLOW_SOP ? 1 : 2; }
+__host__ __device__ inline int num_seeds(int flow) { return flow == S3_FLOW_SOP ? 1 : 2; }
+__host__ __device__ inline int weight_cols(int flow, int K) { return (K + 1) * sel_chunk(flow); }
+__host__ __device__ inline int weight_stride(int flow, int K) { return (weight_cols(flow, K) + 3) & ~3; }
+// float words of one work item's scratch: [labels NWP][weights n*NWP][z ping n*SC][z pong n*SC]
+__host__ __device__ inline int64_t item_words(int flow, int K, int64_t n) {
+    const int64_t nwp = weight_stride(flow, K), sc = sel_chunk(flow);
+    return (nwp + n * nwp + 2 * n * sc + 3) & ~int64_t(3);
+}
+
+// ---- block-wide exclusive scan of one int per thread (blockDim.x <= 1024, multiple of 32) ----
+// `warp_sums` is caller-provided shared scratch of 33 ints. Returns the exclusive prefix of
+// `v`; *total (same for all threads) is the block sum. Contains two __syncthreads().
+__device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int s = lane < nw ? warp_sums[lane] : 0;
+        int si = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, si, d);
+            if (lane >= d) si += t;
+        }
+        if (lane < nw) warp_sums[lane] = si - s;  // exclusive warp offsets
+        if (lane == 31) warp_sums[32] = si;
+    }
+    __syncthreads();
+    *total = warp_sums[32];
+    const int out = warp_sums[wid] + inc - v;
+    return out;
+}
+
+struct OutPtrs {
+    float* p[S3_MAX_K + 1];
+};
+
+// launchers (defined in the .cu files, called from c_abi.cu)
+cudaError_t launch_extract_bitmap(const s3_graph& g, const s3_batch& b, cudaStream_t st);
+cudaError_t launch_plan(const s3_batch& b, cudaStream_t st);
+cudaError_t launch_plan_items(const s3_batch& b, cudaStream_t st);
+cudaError_t launch_diffuse(const s3_graph& g, const s3_batch& b, int64_t num_items, cudaStream_t st);
+cudaError_t launch_gather(const s3_graph& g, const s3_batch& b, int64_t num_items, const OutPtrs& out,
+                          int64_t ldo, int64_t row_base, cudaStream_t st);
+cudaError_t launch_dump_edges(const s3_batch& b, const int64_t* edge_ptr, int32_t* edges_out, cudaStream_t st);
+
+}  // namespace s3

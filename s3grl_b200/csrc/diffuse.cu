@@ -1,0 +1,151 @@
+// Kernel 2 — per-subgraph diffusion weights: the K row vectors e_sel^T S^k, S = D^-1/2 A_sub D^-1/2.
+//
+// Replaces reference tuned_SIGN.py:155-161 (degree normalisation), :168-170 (S^2..S^K by
+// SpGEMM) and :173-175 (keep the selected rows); in SoP flow sgrl_link_pred.py:161-178
+// (global normalised powers) and tuned_SIGN.py:60-86, :106-113 (rows of the endpoints, partner
+// entry zeroed, self-return weight).
+//
+// The reference forms whole n x n powers and keeps 2 (+CCN) rows. Only those rows are needed:
+// with w_0 = e_sel and z_k = w_k D^-1/2,
+//      t_j = sum_{i in N(j)} z_{k-1}[i],   w_k[j] = dis_j t_j,   z_k[j] = dis_j^2 t_j
+// (A_sub symmetric), i.e. K segmented CSR SpMV sweeps per selected row instead of K-1 SpGEMMs.
+// Sums run over the local CSR row in its stored order, so results do not depend on scheduling.
+//
+// One CTA per work item (= up to SC selected rows of one record). Output per item, in the
+// record's float scratch:  labels[NWP] | weights[n][NWP] | z ping | z pong,  weight column
+// q = k*SC + c for operator k (k = 0 is the one-hot selecting x itself) and selected row c.
+#include "common.cuh"
+
+namespace s3 {
+namespace {
+
+struct DiffuseParams {
+    const int64_t* __restrict__ indptr;  // SoP: global degrees
+    int32_t* arena;
+    const int64_t* __restrict__ off;
+    const int32_t* __restrict__ cnt;
+    const int64_t* __restrict__ item_ptr;  // may be null (one item per record)
+    const int32_t* __restrict__ item_rec;  // may be null
+    int flow, sign_k;
+};
+
+template <int SC>
+__global__ void __launch_bounds__(kDiffuseThreads) diffuse_kernel(DiffuseParams p) {
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int64_t item = blockIdx.x;
+    const int64_t rec = p.item_rec ? p.item_rec[item] : item;
+    const int32_t* cnt = p.cnt + rec * S3_NCNT;
+    if (cnt[S3_CNT_STATUS] != S3_REC_OK) return;
+    const int chunk = p.item_ptr ? (int)(item - p.item_ptr[rec]) : 0;
+    const int n = cnt[S3_CNT_N], s = cnt[S3_CNT_S];
+    const int K = p.sign_k, nseed = num_seeds(p.flow);
+    const int NW = (K + 1) * SC, NWP = (NW + 3) & ~3;
+    const int64_t* off = p.off + rec * S3_NOFF;
+    const int32_t* nodes = p.arena + off[S3_OFF_NODES];
+    const int32_t* rowptr = p.arena + off[S3_OFF_ROWPTR];
+    const int32_t* lcol = p.arena + off[S3_OFF_LCOL];
+    const int32_t* sel = p.arena + off[S3_OFF_SEL];
+    float* item_f = reinterpret_cast<float*>(p.arena + off[S3_OFF_F32]) + (int64_t)chunk * item_words(p.flow, K, n);
+    float* lab = item_f;
+    float* wgt = item_f + NWP;
+    float* zA = wgt + (int64_t)n * NWP;
+    float* zB = zA + (int64_t)n * SC;
+
+    // selected local rows of this item
+    int r[SC];
+#pragma unroll
+    for (int c = 0; c < SC; ++c) {
+        const int i = chunk * SC + c;
+        r[c] = i >= s ? -1 : (i < nseed ? i : sel[i - nseed]);
+    }
+
+    // k = 0: one-hot weights, z_0 = e_sel D^-1/2
+    for (int j = tid; j < n; j += T) {
+        int deg;
+        if (p.flow == S3_FLOW_SOP) {
+            const int g = nodes[j];
+            deg = (int)(p.indptr[g + 1] - p.indptr[g]);  // global degree (sgrl_link_pred.py:165-168)
+        } else {
+            deg = rowptr[j + 1] - rowptr[j];  // induced, masked degree (tuned_SIGN.py:158)
+        }
+        const float dis = deg > 0 ? 1.0f / sqrtf((float)deg) : 0.0f;  // inf -> 0 (tuned_SIGN.py:159-160)
+        float* wj = wgt + (int64_t)j * NWP;
+        for (int q = SC; q < NWP; ++q) wj[q] = 0.0f;
+#pragma unroll
+        for (int c = 0; c < SC; ++c) {
+            const float one = (j == r[c]) ? 1.0f : 0.0f;
+            wj[c] = one;
+            zA[(int64_t)j * SC + c] = one * dis;
+        }
+    }
+    __syncthreads();
+
+    float* zprev = zA;
+    float* znext = zB;
+    for (int k = 1; k <= K; ++k) {
+        for (int j = tid; j < n; j += T) {
+            const int e0 = rowptr[j], e1 = rowptr[j + 1];
+            int deg;
+            if (p.flow == S3_FLOW_SOP) {
+                const int g = nodes[j];
+                deg = (int)(p.indptr[g + 1] - p.indptr[g]);
+            } else {
+                deg = e1 - e0;
+            }
+            const float dis = deg > 0 ? 1.0f / sqrtf((float)deg) : 0.0f;
+            float t[SC];
+#pragma unroll
+            for (int c = 0; c < SC; ++c) t[c] = 0.0f;
+            for (int e = e0; e < e1; ++e) {
+                const int i = lcol[e];
+#pragma unroll
+                for (int c = 0; c < SC; ++c) t[c] += zprev[(int64_t)i * SC + c];
+            }
+#pragma unroll
+            for (int c = 0; c < SC; ++c) {
+                const float w = dis * t[c];
+                wgt[(int64_t)j * NWP + k * SC + c] = w;
+                znext[(int64_t)j * SC + c] = dis * w;
+            }
+        }
+        __syncthreads();
+        float* tmp = zprev;
+        zprev = znext;
+        znext = tmp;
+    }
+
+    // label / self-return column of every operator, then (SoP) drop the partner's weight
+    if (p.flow == S3_FLOW_POS) {
+        // x_k[sel, 0] = sum_j w_k[j] * label_j, label = 1 on local 0 and 1 (tuned_SIGN.py:177)
+        for (int q = tid; q < NWP; q += T) lab[q] = q < NW ? wgt[q] + wgt[NWP + q] : 0.0f;
+    } else {
+        // x_k[., 0] = A^k[u,u] (tuned_SIGN.py:106-113); x[., 0] = 1 (tuned_SIGN.py:119-124)
+        for (int q = tid; q < NWP; q += T) lab[q] = q < NW ? wgt[q] : 0.0f;
+        __syncthreads();
+        const int partner = cnt[S3_CNT_PARTNER];
+        if (partner >= 0)  // r_u[v] = 0 (tuned_SIGN.py:73-76); k = 0 is already 0 there
+            for (int q = SC + tid; q < NW; q += T) wgt[(int64_t)partner * NWP + q] = 0.0f;
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_diffuse(const s3_graph& g, const s3_batch& b, int64_t num_items, cudaStream_t st) {
+    if (num_items == 0) return cudaSuccess;
+    DiffuseParams p;
+    p.indptr = g.indptr;
+    p.arena = b.arena;
+    p.off = b.off;
+    p.cnt = b.cnt;
+    p.item_ptr = b.item_rec ? b.item_ptr : nullptr;
+    p.item_rec = b.item_rec;
+    p.flow = b.flow;
+    p.sign_k = b.sign_k;
+    if (sel_chunk(b.flow) == 1)
+        diffuse_kernel<1><<<(unsigned)num_items, kDiffuseThreads, 0, st>>>(p);
+    else
+        diffuse_kernel<2><<<(unsigned)num_items, kDiffuseThreads, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace s3

@@ -1,0 +1,103 @@
+// Plan: output-row offsets and work-item lists from the per-record selected-row counts —
+// the `slices` PyG's collate records for x, x1..xK (reference sgrl_link_pred.py:204,
+// SURVEY.md §8a row 10b) — plus the canonical edge-list dump used by the parity tests.
+#include "common.cuh"
+
+namespace s3 {
+namespace {
+
+// Single CTA: exclusive scans of s (rows) and ceil(s / SC) (items) over all records.
+__global__ void __launch_bounds__(1024) plan_scan_kernel(const int32_t* __restrict__ cnt, int64_t num_records, int sc,
+                                                         int64_t* __restrict__ row_ptr, int64_t* __restrict__ item_ptr,
+                                                         unsigned long long* counters) {
+    __shared__ long long s_rows[1024], s_items[1024];
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int64_t per = (num_records + T - 1) / T;
+    const int64_t r0 = min(num_records, (int64_t)tid * per), r1 = min(num_records, r0 + per);
+    long long rows = 0, items = 0;
+    for (int64_t r = r0; r < r1; ++r) {
+        const int s = cnt[r * S3_NCNT + S3_CNT_S];
+        rows += s;
+        items += (s + sc - 1) / sc;
+    }
+    s_rows[tid] = rows;
+    s_items[tid] = items;
+    __syncthreads();
+    // Hillis-Steele over 1024 partials (tiny; runs once per batch)
+    for (int d = 1; d < T; d <<= 1) {
+        long long a = 0, b = 0;
+        if (tid >= d) {
+            a = s_rows[tid - d];
+            b = s_items[tid - d];
+        }
+        __syncthreads();
+        s_rows[tid] += a;
+        s_items[tid] += b;
+        __syncthreads();
+    }
+    long long row_run = s_rows[tid] - rows, item_run = s_items[tid] - items;
+    for (int64_t r = r0; r < r1; ++r) {
+        const int s = cnt[r * S3_NCNT + S3_CNT_S];
+        row_ptr[r] = row_run;
+        item_ptr[r] = item_run;
+        row_run += s;
+        item_run += (s + sc - 1) / sc;
+    }
+    if (tid == T - 1) {
+        row_ptr[num_records] = s_rows[tid];
+        item_ptr[num_records] = s_items[tid];
+        counters[S3_CTR_ROWS] = (unsigned long long)s_rows[tid];
+        counters[S3_CTR_ITEMS] = (unsigned long long)s_items[tid];
+    }
+}
+
+__global__ void plan_items_kernel(const int64_t* __restrict__ item_ptr, int64_t num_records, int32_t* __restrict__ item_rec) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= num_records) return;
+    for (int64_t i = item_ptr[r]; i < item_ptr[r + 1]; ++i) item_rec[i] = (int32_t)r;
+}
+
+// edges_out[2*e], edges_out[2*e+1] = global (row, col) of local edge e, in local CSR order.
+__global__ void dump_edges_kernel(const int32_t* __restrict__ arena, const int64_t* __restrict__ off,
+                                  const int32_t* __restrict__ cnt, const int64_t* __restrict__ edge_ptr,
+                                  int32_t* __restrict__ edges_out) {
+    const int64_t rec = blockIdx.x;
+    if (cnt[rec * S3_NCNT + S3_CNT_STATUS] != S3_REC_OK) return;
+    const int n = cnt[rec * S3_NCNT + S3_CNT_N];
+    const int32_t* nodes = arena + off[rec * S3_NOFF + S3_OFF_NODES];
+    const int32_t* rowptr = arena + off[rec * S3_NOFF + S3_OFF_ROWPTR];
+    const int32_t* lcol = arena + off[rec * S3_NOFF + S3_OFF_LCOL];
+    int32_t* out = edges_out + 2 * edge_ptr[rec];
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const int g = nodes[j];
+        for (int e = rowptr[j]; e < rowptr[j + 1]; ++e) {
+            out[2 * (int64_t)e] = g;
+            out[2 * (int64_t)e + 1] = nodes[lcol[e]];
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_plan(const s3_batch& b, cudaStream_t st) {
+    const int64_t R = s3_num_records(&b);
+    plan_scan_kernel<<<1, 1024, 0, st>>>(b.cnt, R, sel_chunk(b.flow), b.row_ptr, b.item_ptr,
+                                         reinterpret_cast<unsigned long long*>(b.counters));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_plan_items(const s3_batch& b, cudaStream_t st) {
+    const int64_t R = s3_num_records(&b);
+    if (R == 0) return cudaSuccess;
+    plan_items_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(b.item_ptr, R, b.item_rec);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dump_edges(const s3_batch& b, const int64_t* edge_ptr, int32_t* edges_out, cudaStream_t st) {
+    const int64_t R = s3_num_records(&b);
+    if (R == 0) return cudaSuccess;
+    dump_edges_kernel<<<(unsigned)R, 128, 0, st>>>(b.arena, b.off, b.cnt, edge_ptr, edges_out);
+    return cudaGetLastError();
+}
+
+}  // namespace s3

@@ -1,0 +1,263 @@
+"""Host orchestration of the CUDA precompute path (tensor-level API).
+
+`DeviceGraph` uploads the training graph once (what the reference rebuilds per split at
+sgrl_link_pred.py:107-114 as a SciPy CSR) and `precompute` runs a whole
+get_PoS_prepped_ds / get_PoS_Plus_prepped_ds / get_SoP_prepped_ds call
+(reference tuned_SIGN.py:137, :192, :49) on the GPU in batches of records:
+
+    s3_extract -> [s3_plan -> sync -> s3_plan_items] -> s3_diffuse -> s3_gather
+
+PyTorch is used for device memory, streams and (in parallel.py) torch.distributed only; all
+compute is in libs3grl_b200.so.  There is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as ssp
+import torch
+
+from . import _lib as L
+
+_STRATEGY = {None: L.STRATEGY_NONE, '': L.STRATEGY_NONE, 'intersection': L.STRATEGY_INTERSECTION,
+             'union': L.STRATEGY_UNION}
+_FLOW = {'PoS': L.FLOW_POS, 'SoP': L.FLOW_SOP}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class DeviceGraph:
+    """CSR + features resident in HBM.
+
+    A : scipy sparse matrix N x N (any values; only the pattern is used by PoS,
+        tuned_SIGN.py:153).  Must be structurally symmetric — the reference's training graphs
+        always are (both directions of every edge, sgrl_link_pred.py:849-859).
+    x : [N, F] float32 array / tensor (rows are padded to a multiple of 4 floats on device so
+        every feature row is read with 128-bit loads).
+    """
+
+    def __init__(self, A, x, device='cuda', check_symmetric=True):
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise RuntimeError("s3grl_b200 needs a CUDA device: there is no CPU path")
+        L.lib()  # fail early and loudly if the extension is missing
+        A = ssp.csr_matrix(A)
+        A.sum_duplicates()
+        A.sort_indices()
+        if A.shape[0] != A.shape[1]:
+            raise ValueError("A must be square")
+        if check_symmetric and A.nnz and ((A != 0) != (A.T != 0)).nnz != 0:
+            raise NotImplementedError("directed / structurally asymmetric graphs are not supported "
+                                      "(reference flag `directed`, utils.py:58-63, is out of scope)")
+        self.num_nodes = int(A.shape[0])
+        self.nnz = int(A.nnz)
+        self.has_multi_edges = bool(A.nnz and A.data.max() > 1)
+        self.indptr = torch.from_numpy(A.indptr.astype(np.int64)).to(self.device)
+        self.indices = torch.from_numpy(A.indices.astype(np.int32)).to(self.device)
+        x = torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x, dtype=torch.float32)
+        if x.dim() != 2 or x.shape[0] != self.num_nodes:
+            raise ValueError(f"x must be [N={self.num_nodes}, F], got {tuple(x.shape)}")
+        self.num_feat = int(x.shape[1])
+        self.ldx = (self.num_feat + 3) // 4 * 4
+        self.x = torch.zeros((self.num_nodes, self.ldx), dtype=torch.float32, device=self.device)
+        self.x[:, :self.num_feat].copy_(x, non_blocking=True)
+        self.h2d_bytes = self.indptr.numel() * 8 + self.indices.numel() * 4 + x.numel() * 4
+        self._c = L.Graph(_ptr(self.indptr), _ptr(self.indices), _ptr(self.x), self.num_nodes, self.num_feat,
+                          self.ldx)
+        self._arena = None
+
+    # scratch arena (int32 words), grown on demand and kept across calls
+    def arena(self, words):
+        if self._arena is None or self._arena.numel() < words:
+            self._arena = None
+            self._arena = torch.empty(int(words), dtype=torch.int32, device=self.device)
+        return self._arena
+
+
+class PrecomputeResult:
+    """Collated outputs of one precompute call:
+    xs[k] is the row-stacked operator matrix x_k, [R, F+1]; row_ptr[i]..row_ptr[i+1] are the
+    rows of link i (row 0 = src, row 1 = dst, then CCN rows ascending local id)."""
+
+    def __init__(self, xs, row_ptr, stats, graphs=None):
+        self.xs, self.row_ptr, self.stats, self.graphs = xs, row_ptr, stats, graphs
+
+
+def _records_per_link(flow):
+    return 2 if flow == L.FLOW_SOP else 1
+
+
+def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_records=8192,
+               out=None, return_graphs=False, arena_words=None, stream=None):
+    """Run the hot path for `links` ([2, L] int64, host or device) on `graph`.
+
+    Returns PrecomputeResult with device tensors.  `out`, if given, is a list of K+1
+    preallocated [>=R, F+1] float32 device tensors (fixed-row flows only).
+    Raises ValueError for invalid links (out of range, src == dst), NotImplementedError for an
+    unknown strategy (as reference tuned_SIGN.py:235)."""
+    lib = L.lib()
+    if flow not in _FLOW:
+        raise NotImplementedError(f"sign_type {flow!r}: no matching configuration (reference utils.py:553)")
+    if strategy not in _STRATEGY:
+        raise NotImplementedError(f"check strat {strategy}")   # reference tuned_SIGN.py:235
+    cflow = _FLOW[flow]
+    cstrat = _STRATEGY[strategy] if cflow == L.FLOW_POS else L.STRATEGY_NONE
+    if cflow == L.FLOW_SOP and graph.has_multi_edges:
+        raise NotImplementedError("SoP on a multigraph (duplicate edges) is not supported")
+    dev = graph.device
+    links = torch.as_tensor(links)
+    if links.dim() != 2 or links.shape[0] != 2:
+        raise ValueError("links must be [2, L]")
+    links = links.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
+    Lk = int(links.shape[1])
+    K = int(sign_k)
+    F1 = graph.num_feat + 1
+    rpl = _records_per_link(cflow)
+    nseed = 1 if cflow == L.FLOW_SOP else 2
+    fixed_rows = cstrat == L.STRATEGY_NONE
+    st = stream if stream is not None else torch.cuda.current_stream(dev)
+    st_ptr = C.c_void_p(st.cuda_stream)
+
+    with torch.cuda.device(dev), torch.cuda.stream(st):
+        if fixed_rows:
+            R = 2 * Lk
+            if out is None:
+                out = [torch.empty((R, F1), dtype=torch.float32, device=dev) for _ in range(K + 1)]
+            else:
+                assert len(out) == K + 1 and all(o.shape[0] >= R and o.shape[1] == F1 and o.is_contiguous() for o in out)
+            out_ptrs = (C.c_void_p * (K + 1))(*[o.data_ptr() for o in out])
+        batch_links = max(1, int(batch_records) // rpl)
+        nb = (Lk + batch_links - 1) // batch_links
+        counters = torch.zeros((max(nb, 1), L.NCTR), dtype=torch.int64, device=dev)
+        words = int(arena_words) if arena_words else max(1 << 24, graph._arena.numel() if graph._arena is not None else 0)
+        stats = dict(records=Lk * rpl, links=Lk, sum_n=0, sum_d=0, max_n=0, rows=0, retries=0, batches=nb)
+        pieces, row_counts, graphs = [], [], ([] if return_graphs else None)
+
+        def make_batch(b0, b1, arena, off, cnt, ctr, row_ptr=None, item_ptr=None, item_rec=None):
+            return L.Batch(_ptr(links[0, b0:b1]), _ptr(links[1, b0:b1]), b1 - b0, cflow, cstrat, int(num_hops), K,
+                           _ptr(arena), arena.numel(), _ptr(off), _ptr(cnt), _ptr(ctr),
+                           _ptr(row_ptr), _ptr(item_ptr), _ptr(item_rec))
+
+        def run_batch(bi, arena):
+            """Enqueue one batch; returns (cnt, off, pending) where pending finishes Plus flows."""
+            b0, b1 = bi * batch_links, min(Lk, (bi + 1) * batch_links)
+            nrec = (b1 - b0) * rpl
+            off = torch.empty((nrec, L.NOFF), dtype=torch.int64, device=dev)
+            cnt = torch.empty((nrec, L.NCNT), dtype=torch.int32, device=dev)
+            ctr = counters[bi]
+            ctr.zero_()
+            if fixed_rows:
+                batch = make_batch(b0, b1, arena, off, cnt, ctr)
+                L.check(lib.s3_extract(C.byref(graph._c), C.byref(batch), st_ptr), 's3_extract')
+                L.check(lib.s3_diffuse(C.byref(graph._c), C.byref(batch), nrec, st_ptr), 's3_diffuse')
+                L.check(lib.s3_gather(C.byref(graph._c), C.byref(batch), nrec, out_ptrs, F1, b0 * rpl * nseed, st_ptr),
+                        's3_gather')
+                return cnt, off, None
+            row_ptr = torch.empty(nrec + 1, dtype=torch.int64, device=dev)
+            item_ptr = torch.empty(nrec + 1, dtype=torch.int64, device=dev)
+            batch = make_batch(b0, b1, arena, off, cnt, ctr, row_ptr, item_ptr)
+            L.check(lib.s3_extract(C.byref(graph._c), C.byref(batch), st_ptr), 's3_extract')
+            L.check(lib.s3_plan(C.byref(batch), st_ptr), 's3_plan')
+            c = ctr.cpu()                                  # sync: rows / items / errors of this batch
+            if int(c[L.CTR_ERRORS]) != 0:
+                return cnt, off, 'retry'
+            rows, items = int(c[L.CTR_ROWS]), int(c[L.CTR_ITEMS])
+            item_rec = torch.empty(max(items, 1), dtype=torch.int32, device=dev)
+            xs_b = [torch.empty((rows, F1), dtype=torch.float32, device=dev) for _ in range(K + 1)]
+            batch = make_batch(b0, b1, arena, off, cnt, ctr, row_ptr, item_ptr, item_rec)
+            ptrs = (C.c_void_p * (K + 1))(*[o.data_ptr() for o in xs_b])
+            L.check(lib.s3_plan_items(C.byref(batch), st_ptr), 's3_plan_items')
+            L.check(lib.s3_diffuse(C.byref(graph._c), C.byref(batch), items, st_ptr), 's3_diffuse')
+            L.check(lib.s3_gather(C.byref(graph._c), C.byref(batch), items, ptrs, F1, 0, st_ptr), 's3_gather')
+            pieces.append(xs_b)
+            row_counts.append(row_ptr[1:] - row_ptr[:-1])
+            return cnt, off, None
+
+        def check_and_account(bi, cnt):
+            c = counters[bi].cpu()
+            if int(c[L.CTR_ERRORS]) != 0:
+                status = cnt[:, L.CNT_STATUS]
+                if bool((status == L.REC_BAD_LINK).any()):
+                    bad = int(torch.nonzero(status == L.REC_BAD_LINK)[0]) // rpl + bi * batch_links
+                    raise ValueError(f"invalid target link at position {bad}: node id out of range or src == dst")
+                return False
+            stats['sum_n'] += int(c[L.CTR_SUM_N])
+            stats['sum_d'] += int(c[L.CTR_SUM_D])
+            stats['max_n'] = max(stats['max_n'], int(c[L.CTR_MAX_N]))
+            return True
+
+        def dump(bi, cnt, off, arena):
+            cn, of, ar = cnt.cpu().numpy(), off.cpu().numpy(), arena.cpu().numpy()
+            for r in range(cn.shape[0]):
+                n, m, s = int(cn[r, L.CNT_N]), int(cn[r, L.CNT_M]), int(cn[r, L.CNT_S])
+                nodes = ar[of[r, L.OFF_NODES]:of[r, L.OFF_NODES] + n].astype(np.int64)
+                rowptr = ar[of[r, L.OFF_ROWPTR]:of[r, L.OFF_ROWPTR] + n + 1].astype(np.int64)
+                lcol = ar[of[r, L.OFF_LCOL]:of[r, L.OFF_LCOL] + m].copy()
+                sel = np.concatenate([np.arange(nseed), ar[of[r, L.OFF_SEL]:of[r, L.OFF_SEL] + s - nseed]]).astype(np.int32)
+                hop_cnt = cn[r, L.CNT_HOP0:L.CNT_HOP0 + L.MAX_HOPS + 1]
+                hops = np.repeat(np.arange(L.MAX_HOPS + 1), hop_cnt).astype(np.int32)
+                graphs.append(dict(nodes=nodes, hops=hops, lrowptr=rowptr, lcol=lcol, sel=sel,
+                                   partner=int(cn[r, L.CNT_PARTNER])))
+
+        def grow():
+            nonlocal words
+            stats['retries'] += 1
+            words = int(words * 2)
+            free, _ = torch.cuda.mem_get_info(dev)
+            have = graph._arena.numel() * 4 if graph._arena is not None else 0
+            if words * 4 > free + have:
+                raise MemoryError("scratch arena does not fit in device memory; lower batch_records")
+
+        if fixed_rows:
+            # Enqueue every batch without a host sync, validate at the end; a batch whose arena
+            # overflowed is re-run (its output rows are simply rewritten) with a larger arena.
+            todo = list(range(nb))
+            while todo:
+                arena = graph.arena(words)
+                metas = []
+                for bi in todo:
+                    cnt, off, _ = run_batch(bi, arena)
+                    if return_graphs:   # the arena is recycled by the next batch: dump now
+                        st.synchronize()
+                        if check_and_account(bi, cnt):
+                            dump(bi, cnt, off, arena)
+                            continue
+                    metas.append((bi, cnt))
+                st.synchronize()
+                todo = [bi for bi, cnt in metas if not (False if return_graphs else check_and_account(bi, cnt))]
+                if todo:
+                    if return_graphs and graphs:
+                        raise RuntimeError("arena overflow while dumping graphs: pass a larger arena_words")
+                    grow()
+        else:
+            # Row counts are data dependent: one host sync per batch (inside run_batch).
+            for bi in range(nb):
+                while True:
+                    arena = graph.arena(words)
+                    cnt, off, pending = run_batch(bi, arena)
+                    st.synchronize()
+                    if pending is None and check_and_account(bi, cnt):
+                        if return_graphs:
+                            dump(bi, cnt, off, arena)
+                        break
+                    check_and_account(bi, cnt)      # raises on bad links
+                    grow()
+
+        if fixed_rows:
+            xs = [o[:2 * Lk] for o in out]
+            row_ptr = torch.arange(Lk + 1, dtype=torch.int64, device=dev) * 2
+            stats['rows'] = 2 * Lk
+        else:
+            xs = [torch.cat([p[k] for p in pieces], 0) if pieces else torch.empty((0, F1), device=dev) for k in range(K + 1)]
+            counts = torch.cat(row_counts) if row_counts else torch.zeros(0, dtype=torch.int64, device=dev)
+            row_ptr = torch.zeros(Lk + 1, dtype=torch.int64, device=dev)
+            torch.cumsum(counts, 0, out=row_ptr[1:])
+            stats['rows'] = int(xs[0].shape[0])
+    return PrecomputeResult(xs, row_ptr, stats, graphs)
+
+
+def algorithmic_bytes(stats, num_feat, sign_k):
+    """SURVEY.md §8d:  sum over links of 4·D + 8·n + 4·F·n + 4·s·(K+1)·(F+1)."""
+    return (4 * stats['sum_d'] + 8 * stats['sum_n'] + 4 * num_feat * stats['sum_n']
+            + 4 * stats['rows'] * (sign_k + 1) * (num_feat + 1))

@@ -1,0 +1,84 @@
+"""Drop-in mirror of the reference's `OptimizedSignOperations` (tuned_SIGN.py:47-262): same
+static-method names, argument order and meaning, same exceptions; the work is done by the
+CUDA path (s3grl_b200.engine.precompute).  Results come back as a `PrecomputedList`
+(a sequence of Data with keys x, y, x1..xK) on `S3GRL_OUTPUT_DEVICE` ('cpu' by default, as the
+reference returns CPU tensors; 'cuda' keeps them in HBM for a GPU-resident loader).
+"""
+import os
+
+import torch
+
+from .data import PrecomputedList
+from .engine import DeviceGraph, precompute
+
+_graph_cache = {}
+
+
+def device_graph(A, x, device=None):
+    """Upload (A, x) once per (matrix, feature) pair; the reference re-uses one A and x across
+    the positive and negative call of a split (sgrl_link_pred.py:193-203)."""
+    device = device or os.environ.get('S3GRL_DEVICE', 'cuda')
+    key = (id(A), id(x), str(device))
+    hit = _graph_cache.get(key)
+    if hit is not None and hit[0] is A and hit[1] is x:
+        return hit[2]
+    g = DeviceGraph(A, x.detach().cpu() if torch.is_tensor(x) else x, device=device)
+    _graph_cache.clear()          # keep one graph resident
+    _graph_cache[key] = (A, x, g)
+    return g
+
+
+def _finish(res, y):
+    out_dev = os.environ.get('S3GRL_OUTPUT_DEVICE', 'cpu')
+    xs, row_ptr = res.xs, res.row_ptr
+    if out_dev == 'cpu':
+        host = [torch.empty(x.shape, dtype=x.dtype, pin_memory=True) for x in xs]
+        for h, x in zip(host, xs):
+            h.copy_(x, non_blocking=True)
+        row_ptr = row_ptr.cpu()       # synchronises the stream: the copies above are complete
+        torch.cuda.current_stream(xs[0].device).synchronize()
+        xs = host
+    return PrecomputedList(xs, row_ptr, y, res.stats)
+
+
+def _reject_unsupported(ratio_per_hop, max_nodes_per_hop, directed, rw_kwargs):
+    if rw_kwargs:
+        raise NotImplementedError("ScaLed random-walk subgraphs (rw_kwargs) are out of scope (SURVEY.md §8f)")
+    if directed:
+        raise NotImplementedError("directed BFS is out of scope")
+    if (ratio_per_hop is not None and ratio_per_hop < 1.0) or max_nodes_per_hop is not None:
+        raise NotImplementedError("per-hop random down-sampling has no reproducible reference "
+                                  "(random.sample on a set, utils.py:66-70) and is not supported")
+
+
+class OptimizedSignOperations:
+    @staticmethod
+    def get_SoP_prepped_ds(powers_of_A, link_index, A, x, y):
+        """reference tuned_SIGN.py:49.  `powers_of_A` only supplies K = len(powers_of_A): the
+        rows Â^k[u,:] are recomputed on the GPU from A by K-hop row propagation instead of
+        being read out of global SpGEMM powers (sgrl_link_pred.py:161-178)."""
+        K = len(powers_of_A) if not isinstance(powers_of_A, int) else powers_of_A
+        g = device_graph(A, x)
+        return _finish(precompute(g, link_index, 0, K, flow='SoP'), y)
+
+    @staticmethod
+    def get_PoS_prepped_ds(link_index, num_hops, A, ratio_per_hop, max_nodes_per_hop, directed, A_csc, x, y,
+                           sign_kwargs, rw_kwargs):
+        """reference tuned_SIGN.py:137-189."""
+        _reject_unsupported(ratio_per_hop, max_nodes_per_hop, directed, rw_kwargs)
+        assert x is not None                       # reference tuned_SIGN.py:166
+        g = device_graph(A, x)
+        return _finish(precompute(g, link_index, num_hops, sign_kwargs['sign_k'], flow='PoS'), y)
+
+    @staticmethod
+    def get_PoS_Plus_prepped_ds(link_index, num_hops, A, ratio_per_hop, max_nodes_per_hop, directed, A_csc, x, y,
+                                sign_kwargs, rw_kwargs):
+        """reference tuned_SIGN.py:192-262.  `union` follows the paper semantics
+        sel = [0,1] + sorted((N(0) ∪ N(1)) − {0,1}) (the reference raises for it)."""
+        _reject_unsupported(ratio_per_hop, max_nodes_per_hop, directed, rw_kwargs)
+        assert x is not None                       # reference tuned_SIGN.py:221
+        strat = sign_kwargs['k_node_set_strategy']
+        if strat not in ('union', 'intersection'):
+            raise NotImplementedError(f"check strat {strat}")      # reference tuned_SIGN.py:235
+        g = device_graph(A, x)
+        return _finish(precompute(g, link_index, num_hops, sign_kwargs['sign_k'], flow='PoS', strategy=strat), y)

@@ -1,0 +1,40 @@
+"""Drop-in mirror of the reference's dispatcher `extract_enclosing_subgraphs`
+(utils.py:446-496): same signature, same branch order on `sign_kwargs` / `powers_of_A`."""
+import torch
+
+from .data import PrecomputedList
+from .tuned_sign import OptimizedSignOperations
+
+
+def extract_enclosing_subgraphs(link_index, A, x, y, num_hops, node_label='drnl',
+                                ratio_per_hop=1.0, max_nodes_per_hop=None,
+                                directed=False, A_csc=None, rw_kwargs=None, sign_kwargs=None, powers_of_A=None,
+                                data=None):
+    if not sign_kwargs:
+        raise NotImplementedError("only the SIGN flows (sign_kwargs) are on the accelerated path; "
+                                  "SEAL / DRNL subgraph datasets are out of scope (SURVEY.md §2)")
+    if powers_of_A and sign_kwargs['optimize_sign'] and sign_kwargs['sign_type'] == 'hybrid':
+        # reference utils.py:454-480: PoS x, x1..xK then SoP x2..xK appended as x{K+1}..x{2K-1}
+        sign_k = sign_kwargs['sign_k']
+        sup = OptimizedSignOperations.get_PoS_prepped_ds(link_index, num_hops, A, ratio_per_hop,
+                                                         max_nodes_per_hop, directed, A_csc, x, y,
+                                                         sign_kwargs, rw_kwargs)
+        if sign_k == 1:
+            return sup
+        sop = OptimizedSignOperations.get_SoP_prepped_ds(powers_of_A, link_index, A, x, y)
+        return PrecomputedList(sup.xs + [t.to(sup.xs[0].device) for t in sop.xs[2:sign_k + 1]], sup.row_ptr, sup.y)
+    elif powers_of_A and sign_kwargs['optimize_sign']:
+        return OptimizedSignOperations.get_SoP_prepped_ds(powers_of_A, link_index, A, x, y)
+    elif not powers_of_A and sign_kwargs['optimize_sign'] and not sign_kwargs['k_heuristic']:
+        return OptimizedSignOperations.get_PoS_prepped_ds(link_index, num_hops, A, ratio_per_hop,
+                                                          max_nodes_per_hop, directed, A_csc, x, y,
+                                                          sign_kwargs, rw_kwargs)
+    elif not powers_of_A and sign_kwargs['optimize_sign'] and sign_kwargs['k_heuristic']:
+        return OptimizedSignOperations.get_PoS_Plus_prepped_ds(link_index, num_hops, A, ratio_per_hop,
+                                                               max_nodes_per_hop, directed, A_csc, x, y,
+                                                               sign_kwargs, rw_kwargs)
+    elif not sign_kwargs['optimize_sign']:
+        raise NotImplementedError("the non-optimised SIGN+SEAL flow (optimize_sign=False, utils.py:497-550) "
+                                  "is not on the accelerated path; no paper config uses it")
+    else:
+        raise NotImplementedError("No matching configuration for model data prep found. Please check code.")

@@ -1,0 +1,90 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports every function
+include/s3grl_b200.h declares, constants agree with the header, and argument validation that
+needs no GPU behaves (no compute calls here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from s3grl_b200 import _lib as L
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
+HEADER = os.path.join(ROOT, 'include', 's3grl_b200.h')
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from s3grl_b200.build import build
+    build()
+    return L.lib()
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(s3_[a-z_0-9]+)\s*\(', src)))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    names = _declared_functions()
+    assert set(names) == set(L.EXPORTS)
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_constants_match_header():
+    src = open(HEADER).read()
+    defs = dict(re.findall(r'#define\s+(S3_[A-Z_0-9]+)\s+(-?\d+)', src))
+    pairs = {'S3_FLOW_POS': L.FLOW_POS, 'S3_FLOW_SOP': L.FLOW_SOP, 'S3_STRATEGY_UNION': L.STRATEGY_UNION,
+             'S3_STRATEGY_INTERSECTION': L.STRATEGY_INTERSECTION, 'S3_MAX_HOPS': L.MAX_HOPS, 'S3_MAX_K': L.MAX_K,
+             'S3_NOFF': L.NOFF, 'S3_NCNT': L.NCNT, 'S3_NCTR': L.NCTR, 'S3_OFF_F32': L.OFF_F32,
+             'S3_CNT_HOP0': L.CNT_HOP0, 'S3_CNT_PARTNER': L.CNT_PARTNER, 'S3_CTR_SUM_D': L.CTR_SUM_D,
+             'S3_CTR_ITEMS': L.CTR_ITEMS, 'S3_REC_BAD_LINK': L.REC_BAD_LINK, 'S3_ERR_NOT_IMPLEMENTED': L.S3_ERR_NOT_IMPLEMENTED}
+    for k, v in pairs.items():
+        assert int(defs[k]) == v, k
+    assert ctypes.sizeof(L.Graph) == 48 and ctypes.sizeof(L.Batch) == 104
+
+
+def test_version_and_error_strings(lib):
+    assert lib.s3_version() == 100
+    assert lib.s3_error_string(0) == b'ok'
+    assert b'strategy' in lib.s3_error_string(L.S3_ERR_NOT_IMPLEMENTED)
+
+
+def test_smem_sizing(lib):
+    # PubMed, h=3: (1 + 2*3) * ceil(19717/32) * 4 bytes
+    assert lib.s3_extract_smem_bytes(19717, 3) == 7 * 617 * 4
+    assert lib.s3_extract_smem_bytes(10_000_000, 1) == -1     # needs the hash tier
+    assert lib.s3_extract_smem_bytes(100, 9) == -1
+
+
+def test_argument_validation_without_gpu(lib):
+    g = L.Graph(0, 0, 0, 10, 4, 4)
+    b = L.Batch()
+    assert lib.s3_extract(ctypes.byref(g), ctypes.byref(b), None) == L.S3_ERR_INVALID_ARG      # null graph arrays
+    g = L.Graph(16, 16, 16, 10, 4, 4)
+    b.flow, b.strategy, b.sign_k, b.num_hops = 7, 0, 3, 2
+    assert lib.s3_extract(ctypes.byref(g), ctypes.byref(b), None) == L.S3_ERR_NOT_IMPLEMENTED  # unknown flow
+    b.flow, b.strategy = L.FLOW_POS, 9
+    assert lib.s3_extract(ctypes.byref(g), ctypes.byref(b), None) == L.S3_ERR_NOT_IMPLEMENTED  # unknown strategy
+    b.strategy, b.sign_k = 0, 0
+    assert lib.s3_extract(ctypes.byref(g), ctypes.byref(b), None) == L.S3_ERR_INVALID_ARG      # K < 1
+    b.sign_k, b.num_hops = 3, 99
+    assert lib.s3_extract(ctypes.byref(g), ctypes.byref(b), None) == L.S3_ERR_INVALID_ARG      # too many hops
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(L, '_lib', None)
+    monkeypatch.setattr(L, 'LIB_PATH', str(tmp_path / 'nope.so'))
+    with pytest.raises(RuntimeError, match='no CPU or PyTorch fallback'):
+        L.lib()
+
+
+def test_product_package_does_not_import_oracle():
+    pkg = os.path.join(ROOT, 's3grl_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', src, flags=re.M), f

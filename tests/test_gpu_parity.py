@@ -1,0 +1,244 @@
+"""Parity tests proper (run on the B200 box): the CUDA path, called through the C ABI, against
+(a) the reference's own outputs committed under tests/golden/ and (b) the oracle on seeded
+inputs.  Indices (node lists, hop labels, induced + masked edge lists, selected rows) must be
+bit-exact; features within 1e-5 of max|ref| per tensor (north_star tolerance)."""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import Case, assert_features_close, case_names
+from oracle import s3grl_oracle as orc
+from s3grl_b200 import DeviceGraph, datasets as ds, precompute
+
+pytestmark = pytest.mark.gpu
+
+
+def _graph_edges(g):
+    rows = np.repeat(np.arange(g['nodes'].size), np.diff(g['lrowptr']))
+    e = np.stack([g['nodes'][rows], g['nodes'][g['lcol']]], 1)
+    return e
+
+
+def _check_indices(got, ref, what):
+    assert np.array_equal(got['nodes'], ref['nodes']), f'{what}: nodes'
+    assert np.array_equal(got['hops'], ref['hops']), f'{what}: hops'
+    assert np.array_equal(got['lrowptr'], ref['lrowptr']), f'{what}: rowptr'
+    # the CUDA path lists a row's columns in ascending GLOBAL id, the oracle in ascending local
+    # id: same set, compare after canonical (row, global col) ordering
+    ge, re_ = _graph_edges(got), _graph_edges(ref)
+    assert ge.shape == re_.shape, f'{what}: edge count'
+    if ge.size:
+        ge = ge[np.lexsort((ge[:, 1], ge[:, 0]))]
+        re_ = re_[np.lexsort((re_[:, 1], re_[:, 0]))]
+        assert np.array_equal(ge, re_), f'{what}: edges'
+    assert np.array_equal(got['sel'], ref['sel']), f'{what}: selected rows'
+
+
+@pytest.mark.parametrize('name', case_names('pos'))
+def test_pos_against_reference_goldens(name):
+    c = Case(name)
+    g = DeviceGraph(c.A, c.X)
+    res = precompute(g, c.links, c.num_hops, c.K, 'PoS', c.strategy, return_graphs=True)
+    assert np.array_equal(res.row_ptr.cpu().numpy(), c.row_ptr)
+    for k in range(c.K + 1):
+        assert_features_close(res.xs[k].cpu().numpy(), c.xs[k], what=f'{name} x{k}')
+    assert np.array_equal(res.xs[0].cpu().numpy(), c.xs[0]), 'x (operator 0) must be an exact copy'
+    for i, gr in enumerate(res.graphs):
+        a, b = c.node_ptr[i], c.node_ptr[i + 1]
+        assert np.array_equal(gr['nodes'], c.nodes[a:b]), f'{name} link {i}: nodes vs reference'
+        assert np.array_equal(gr['hops'], c.hops[a:b]), f'{name} link {i}: hops vs reference'
+        e = _graph_edges(gr)
+        ref_e = c.edges[c.edge_ptr[i]:c.edge_ptr[i + 1]].astype(np.int64)
+        assert e.shape == ref_e.shape
+        if e.size:
+            e = e[np.lexsort((e[:, 1], e[:, 0]))]
+            ref_e = ref_e[np.lexsort((ref_e[:, 1], ref_e[:, 0]))]
+            assert np.array_equal(e, ref_e), f'{name} link {i}: edges vs reference'
+        assert np.array_equal(gr['nodes'][gr['sel']], c.row_gid[c.row_ptr[i]:c.row_ptr[i + 1]])
+
+
+@pytest.mark.parametrize('name', case_names('sop'))
+def test_sop_against_reference_goldens(name):
+    c = Case(name)
+    g = DeviceGraph(c.A, c.X)
+    res = precompute(g, c.links, 0, c.K, 'SoP')
+    assert np.array_equal(res.row_ptr.cpu().numpy(), c.row_ptr)
+    for k in range(c.K + 1):
+        assert_features_close(res.xs[k].cpu().numpy(), c.xs[k], what=f'{name} x{k}')
+
+
+def _random_graph(rng, N, E):
+    u = rng.integers(0, N, E)
+    v = rng.integers(0, N, E)
+    keep = u != v
+    e = np.unique(np.stack([np.minimum(u, v)[keep], np.maximum(u, v)[keep]], 1), axis=0)
+    return ds.adjacency(e, N)
+
+
+@pytest.mark.parametrize('seed,N,E,F,h,K,strategy', [
+    (0, 60, 90, 7, 2, 3, None), (1, 200, 500, 33, 3, 3, 'intersection'), (2, 200, 900, 12, 2, 3, 'union'),
+    (3, 1000, 1500, 130, 3, 2, None), (4, 333, 2000, 5, 1, 5, 'union'), (5, 97, 300, 64, 2, 4, 'intersection'),
+    (6, 50, 40, 1, 3, 1, None), (7, 3000, 9000, 260, 2, 3, None), (8, 40, 500, 9, 2, 7, None),
+])
+def test_pos_against_oracle_random_graphs(seed, N, E, F, h, K, strategy):
+    rng = np.random.default_rng(seed)
+    A = _random_graph(rng, N, E)
+    X = rng.random((N, F), dtype=np.float32)
+    links = rng.integers(0, N, (2, 64))
+    links = links[:, links[0] != links[1]]
+    ref = orc.pos_precompute(links, h, A, X, K, strategy, keep_graphs=True)
+    res = precompute(DeviceGraph(A, X), links, h, K, 'PoS', strategy, return_graphs=True)
+    assert np.array_equal(res.row_ptr.cpu().numpy(), ref['row_ptr'])
+    for i, (g, r) in enumerate(zip(res.graphs, ref['graphs'])):
+        _check_indices(g, r, f'link {i}')
+    for k in range(K + 1):
+        assert_features_close(res.xs[k].cpu().numpy(), ref['xs'][k], what=f'x{k}')
+
+
+@pytest.mark.parametrize('seed,N,E,F,K', [(0, 80, 150, 6, 3), (1, 500, 1200, 40, 2), (2, 120, 900, 129, 3), (3, 64, 100, 3, 5)])
+def test_sop_against_oracle_random_graphs(seed, N, E, F, K):
+    rng = np.random.default_rng(100 + seed)
+    A = _random_graph(rng, N, E)
+    X = rng.random((N, F), dtype=np.float32)
+    links = rng.integers(0, N, (2, 48))
+    links = links[:, links[0] != links[1]]
+    ref = orc.sop_precompute(links, A, X, K)
+    res = precompute(DeviceGraph(A, X), links, 0, K, 'SoP')
+    for k in range(K + 1):
+        assert_features_close(res.xs[k].cpu().numpy(), ref['xs'][k], what=f'x{k}')
+
+
+def test_batching_and_arena_growth_do_not_change_results():
+    """Per-link results must not depend on batch composition (SURVEY.md §7 determinism): one
+    big batch, many small batches and a run that starts with a far-too-small arena (forcing the
+    overflow/retry path) are bit-identical."""
+    c = Case('cora_posplus')
+    for strategy in (None, 'intersection'):
+        g = DeviceGraph(c.A, c.X)
+        a = precompute(g, c.links, c.num_hops, c.K, 'PoS', strategy, batch_records=8192)
+        b = precompute(g, c.links, c.num_hops, c.K, 'PoS', strategy, batch_records=7)
+        g2 = DeviceGraph(c.A, c.X)
+        d = precompute(g2, c.links, c.num_hops, c.K, 'PoS', strategy, batch_records=64, arena_words=4096)
+        assert d.stats['retries'] > 0
+        for k in range(c.K + 1):
+            assert torch.equal(a.xs[k], b.xs[k]) and torch.equal(a.xs[k], d.xs[k])
+        assert torch.equal(a.row_ptr, b.row_ptr) and torch.equal(a.row_ptr, d.row_ptr)
+
+
+def test_invalid_links_and_strategy_raise():
+    c = Case('tiny_pos_h2')
+    g = DeviceGraph(c.A, c.X)
+    with pytest.raises(ValueError):
+        precompute(g, np.array([[0, 3], [1, 3]]), 2, 3)            # src == dst
+    with pytest.raises(ValueError):
+        precompute(g, np.array([[0], [c.N]]), 2, 3)                # out of range
+    with pytest.raises(NotImplementedError):
+        precompute(g, c.links, 2, 3, 'PoS', 'both')                # reference: check strat
+    res = precompute(g, np.zeros((2, 0), dtype=np.int64), 2, 3)    # empty call
+    assert res.xs[0].shape == (0, c.X.shape[1] + 1) and res.row_ptr.tolist() == [0]
+
+
+def test_reference_interface_mirror():
+    """The drop-in boundary: same call the reference's SEALDataset.process makes
+    (sgrl_link_pred.py:195-203), returning a sequence of Data with x, y, x1..xK."""
+    from s3grl_b200 import extract_enclosing_subgraphs
+    c = Case('cora_posplus')
+    x = torch.from_numpy(c.X)
+    link_index = torch.from_numpy(c.links[:, :40])
+    sign_kwargs = dict(sign_k=c.K, use_feature=True, sign_type='PoS', optimize_sign=True, k_heuristic=1,
+                       k_node_set_strategy='intersection')
+    pos = extract_enclosing_subgraphs(link_index, c.A, x, 1, c.num_hops, 'zo', 1.0, None, False, None, None,
+                                      sign_kwargs, powers_of_A=[], data=None)
+    neg = extract_enclosing_subgraphs(link_index, c.A, x, 0, c.num_hops, 'zo', 1.0, None, False, None, None,
+                                      sign_kwargs, powers_of_A=[], data=None)
+    both = pos + neg
+    assert len(pos) == 40 and len(both) == 80
+    d = both[3]
+    a, b = c.row_ptr[3], c.row_ptr[4]
+    assert d.y == 1 and both[43].y == 0 and not d.x.is_cuda
+    for k, key in enumerate(['x', 'x1', 'x2', 'x3']):
+        assert_features_close(d[key].numpy(), c.xs[k][a:b], what=key)
+    data, slices = both.collate()
+    assert data.x.shape[0] == 2 * c.row_ptr[40] and slices['x2'].shape[0] == 81 and data.y.tolist() == [1] * 40 + [0] * 40
+    # hybrid (utils.py:454-480): K PoS operators + SoP x2..xK
+    sign_kwargs.update(sign_type='hybrid', k_heuristic=0)
+    hyb = extract_enclosing_subgraphs(link_index, c.A, x, 1, c.num_hops, 'zo', 1.0, None, False, None, None,
+                                      sign_kwargs, powers_of_A=[1, 2, 3], data=None)
+    ref = orc.hybrid_precompute(c.links[:, :40], c.num_hops, c.A, c.X, c.K)
+    assert len(hyb.xs) == 2 * c.K
+    for k in range(2 * c.K):
+        assert_features_close(hyb.xs[k].numpy(), ref['xs'][k], what=f'hybrid x{k}')
+
+
+def test_dump_edges_entry_point():
+    """s3_dump_edges returns the canonical global-id edge list of every record."""
+    import ctypes as C
+    from s3grl_b200 import _lib as L
+    c = Case('tiny_pos_h2')
+    g = DeviceGraph(c.A, c.X)
+    dev = g.device
+    links = torch.from_numpy(c.links).to(dev)
+    nrec = c.L
+    arena = torch.empty(1 << 20, dtype=torch.int32, device=dev)
+    off = torch.empty((nrec, L.NOFF), dtype=torch.int64, device=dev)
+    cnt = torch.empty((nrec, L.NCNT), dtype=torch.int32, device=dev)
+    ctr = torch.zeros(L.NCTR, dtype=torch.int64, device=dev)
+    b = L.Batch(links[0].data_ptr(), links[1].data_ptr(), nrec, L.FLOW_POS, 0, 2, 3, arena.data_ptr(), arena.numel(),
+                off.data_ptr(), cnt.data_ptr(), ctr.data_ptr(), None, None, None)
+    lib = L.lib()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    L.check(lib.s3_extract(C.byref(g._c), C.byref(b), st), 'extract')
+    m = cnt[:, L.CNT_M].to(torch.int64)
+    edge_ptr = torch.zeros(nrec + 1, dtype=torch.int64, device=dev)
+    edge_ptr[1:] = torch.cumsum(m, 0)
+    edges = torch.empty((int(edge_ptr[-1]), 2), dtype=torch.int32, device=dev)
+    L.check(lib.s3_dump_edges(C.byref(b), C.c_void_p(edge_ptr.data_ptr()), C.c_void_p(edges.data_ptr()), st), 'dump')
+    got = edges.cpu().numpy()
+    ep = edge_ptr.cpu().numpy()
+    assert np.array_equal(ep, c.edge_ptr)
+    for i in range(nrec):
+        e, r = got[ep[i]:ep[i + 1]], c.edges[ep[i]:ep[i + 1]]
+        if e.size:
+            assert np.array_equal(e[np.lexsort((e[:, 1], e[:, 0]))], r[np.lexsort((r[:, 1], r[:, 0]))])
+
+
+def test_pubmed_full_size_sample_and_properties():
+    """BASELINE config 3 at full size: PubMed training graph, F = 500, h = 3, K = 3.  A seeded
+    sample of links is checked against the oracle; the full run is checked through
+    size-independent properties: x rows are exact copies of [1 | X[u]], operator rows are
+    non-negative with row sums <= label + 1 (S is sub-stochastic up to D^1/2 scaling ... so only
+    finiteness and the label-column identity are asserted), and link (u,v) equals link (v,u)
+    with its two rows swapped."""
+    edges, N, _ = ds.load_graph('pubmed')
+    A, splits = ds.split_links(edges, N, seed=1)
+    X = ds.synthetic_features(N, 500, 0.1, 0)
+    links = ds.all_links(splits)
+    g = DeviceGraph(A, X)
+    res = precompute(g, links, 3, 3)
+    assert res.xs[0].shape == (2 * links.shape[1], 501)
+    x0 = res.xs[0].cpu().numpy()
+    assert np.array_equal(x0[:, 0], np.ones(x0.shape[0], np.float32))
+    assert np.array_equal(x0[0::2, 1:], X[links[0]]) and np.array_equal(x0[1::2, 1:], X[links[1]])
+    for k in range(1, 4):
+        assert bool(torch.isfinite(res.xs[k]).all()) and float(res.xs[k].min()) >= 0.0
+    # symmetry: train positives hold both directions of every edge
+    rng = np.random.default_rng(0)
+    pick = rng.choice(links.shape[1], 300, replace=False)
+    sub = links[:, pick]
+    fwd = precompute(g, sub, 3, 3)
+    rev = precompute(g, sub[::-1].copy(), 3, 3)
+    for k in range(4):
+        a = fwd.xs[k].view(-1, 2, 501)
+        b = rev.xs[k].view(-1, 2, 501).flip(1)
+        assert_features_close(a.cpu().numpy(), b.cpu().numpy(), tol=2e-6, what=f'swap x{k}')
+    # oracle on a sample
+    ref = orc.pos_precompute(sub[:, :48], 3, A, X, 3, keep_graphs=True)
+    got = precompute(g, sub[:, :48], 3, 3, return_graphs=True)
+    for i, (gg, r) in enumerate(zip(got.graphs, ref['graphs'])):
+        _check_indices(gg, r, f'pubmed link {i}')
+    for k in range(4):
+        assert_features_close(got.xs[k].cpu().numpy(), ref['xs'][k], what=f'pubmed x{k}')
+    # and the sampled rows of the full run are the same bits as the sampled run
+    for k in range(4):
+        full = res.xs[k].view(-1, 2, 501)[torch.from_numpy(pick).to(res.xs[k].device)]
+        assert torch.equal(full, fwd.xs[k].view(-1, 2, 501))
