@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Benchmark of the precompute hot path (BASELINE.json metric: precomputed target links/s,
+extract + diffuse + select, PubMed PoS r=3).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+
+One "step" = one pass of the hot path over the whole link list of the workload (what the
+three SEALDataset.process calls of a run precompute: train/valid/test positives+negatives,
+reference sgrl_link_pred.py:193-204).  Prints ONE JSON line on rank 0.
+
+* value      : links/s with CSR, X, links and the output buffers resident in HBM.
+* e2e        : the same metric through the reference-facing call
+               s3grl_b200.extract_enclosing_subgraphs(link_index, A, x, ...) with HOST inputs
+               (SciPy CSR, CPU tensors) and HOST outputs: graph + link H2D and the D2H of all
+               K+1 operator matrices are inside the timed region.
+* roofline   : dominant kernel (gather) — algorithmic bytes / CUDA-event time vs measured HBM peak.
+* cpu_baseline / --impl reference : the oracle port (oracle/s3grl_oracle.py — the reference
+               itself is Python and cannot travel to the GPU box) on all host cores.
+
+Multi-GPU (torchrun, one rank per GPU): weak scaling — every rank precomputes a full-size
+shard (the workload's link list in a rank-specific order) against its replica of the graph;
+no data-path collective. The NCCL allgather of the joint rows that training would need is
+timed separately and reported under "allgather".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "precomputed target links/sec (extract+diffuse+pool), PubMed PoS r=3"
+UNIT = "links/s"
+
+
+# ----------------------------------------------------------------------------------------
+# workloads (host side, seeded; no file outside the repo is read)
+# ----------------------------------------------------------------------------------------
+def build_workload(name):
+    from s3grl_b200 import datasets as ds
+    if name in ('pubmed_pos', 'pubmed_posplus_union', 'pubmed_posplus_intersection'):
+        edges, N, _ = ds.load_graph('pubmed')
+        A, splits = ds.split_links(edges, N, seed=1)
+        X = ds.synthetic_features(N, 500, 0.1, 0)
+        links = ds.all_links(splits)
+        strategy = {'pubmed_pos': None, 'pubmed_posplus_union': 'union',
+                    'pubmed_posplus_intersection': 'intersection'}[name]
+        desc = (f"PubMed graph (tests/golden/graphs/pubmed.npz, N={N}, train nnz={A.nnz}), synthetic X F=500 "
+                f"~10% nnz row-normalised seed 0 (real ind.pubmed.allx absent from the reference checkout), 85/5/10 "
+                f"split seed 1, all {links.shape[1]} links of the 3 splits, PoS"
+                f"{' Plus ' + strategy if strategy else ''} num_hops=3 sign_k=3")
+        return dict(A=A, X=X, links=links, num_hops=3, K=3, flow='PoS', strategy=strategy, desc=desc)
+    if name == 'cora_pos':
+        edges, N, X = ds.load_graph('cora')
+        A, splits = ds.split_links(edges, N, seed=1)
+        X = ds.normalize_features(X)
+        links = ds.all_links(splits)
+        return dict(A=A, X=X, links=links, num_hops=3, K=3, flow='PoS', strategy=None,
+                    desc=f"Cora (real X F=1433), all {links.shape[1]} links, PoS num_hops=3 sign_k=3")
+    raise SystemExit(f"unknown workload {name}")
+
+
+# ----------------------------------------------------------------------------------------
+# CPU baseline: the oracle port on all host cores (bounded sample)
+# ----------------------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_init(w):
+    os.environ['OMP_NUM_THREADS'] = '1'
+    _W.update(w)
+
+
+def _cpu_chunk(cols):
+    from oracle import s3grl_oracle as orc
+    w = _W
+    out = orc.pos_precompute(w['links'][:, cols], w['num_hops'], w['A'], w['X'], w['K'], w['strategy'])
+    return int(out['row_ptr'][-1])
+
+
+def cpu_pass(w, sample_cols, procs):
+    """One pass of the oracle over the sampled links with `procs` processes -> seconds."""
+    import multiprocessing as mp
+    chunks = [c for c in np.array_split(sample_cols, procs * 4) if c.size]
+    ctx = mp.get_context('fork')
+    with ctx.Pool(procs, initializer=_cpu_init, initargs=(w,)) as pool:
+        pool.map(_cpu_chunk, [chunks[0][:1]] * procs)      # start-up outside the timing
+        t0 = time.perf_counter()
+        pool.map(_cpu_chunk, chunks)
+        return time.perf_counter() - t0
+
+
+def cpu_sample(w, per_core):
+    procs = os.cpu_count() or 1
+    n = min(w['links'].shape[1], max(procs, per_core * procs))
+    cols = np.sort(np.random.default_rng(123).choice(w['links'].shape[1], n, replace=False))
+    return cols, procs
+
+
+def run_reference_arm(args, w, rank, world):
+    if rank != 0:
+        return
+    cols, procs = cpu_sample(w, args.cpu_links_per_core)
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_pass(w, cols[:procs * 2], procs)
+    t = sum(cpu_pass(w, cols, procs) for _ in range(args.steps))
+    value = cols.size * args.steps / t
+    sample = (f"{cols.size} links sampled uniformly (seed 123) from the workload's {w['links'].shape[1]}, "
+              f"per step; links are independent, so links/s extrapolates linearly")
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1000 * t / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload=w['desc'], links_per_step=int(cols.size)),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=procs, kind="port", sample=sample),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                note="oracle port (NumPy/SciPy restatement of reference utils.py:47-85 + tuned_SIGN.py:137-262, "
+                     "validated against the reference in tests/golden) in a fork pool over all host cores; the "
+                     "reference itself is single-threaded Python and cannot be shipped to the GPU box")
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                       '-lms', '100', '-i', str(index)], stdout=subprocess.PIPE,
+                                      stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.p.terminate()
+        out = self.p.communicate()[0]
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in out.strip().splitlines():
+            f = [t.strip() for t in line.split(',')]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except Exception:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        busy = [s for s in sm if s >= 0.5 * max(sm)]
+        return dict(sm_mhz=float(np.median(busy)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+# ----------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='pubmed_pos')
+    ap.add_argument('--batch-records', type=int, default=8192)
+    ap.add_argument('--cpu-links-per-core', type=int, default=400)
+    ap.add_argument('--e2e-steps', type=int, default=None)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    w = build_workload(args.workload)
+
+    if args.impl == 'reference':
+        run_reference_arm(args, w, rank, world)
+        return
+
+    # CPU baseline first: the fork pool must not inherit an initialised CUDA context
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cols, procs = cpu_sample(w, args.cpu_links_per_core)
+        t = cpu_pass(w, cols, procs)
+        cpu = dict(value=cols.size / t, unit=UNIT, cores=procs, kind="port",
+                   sample=f"{cols.size} links sampled uniformly (seed 123) of {w['links'].shape[1]}, one pass, "
+                          f"{t:.1f} s; oracle port in a {procs}-process fork pool")
+
+    import torch
+    import torch.distributed as dist
+    from s3grl_b200 import DeviceGraph, algorithmic_bytes, precompute
+    from s3grl_b200 import tuned_sign
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    links_host = w['links']
+    if world > 1:   # weak scaling: same link set per rank, rank-specific order
+        links_host = links_host[:, np.random.default_rng(1000 + rank).permutation(links_host.shape[1])]
+    Lk = links_host.shape[1]
+    K, F = w['K'], w['X'].shape[1]
+    g = DeviceGraph(w['A'], w['X'], device=dev)
+    links_dev = torch.from_numpy(np.ascontiguousarray(links_host)).to(dev)
+    fixed = w['strategy'] is None
+    out = [torch.empty((2 * Lk, F + 1), dtype=torch.float32, device=dev) for _ in range(K + 1)] if fixed else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step(profile=None):
+        flush.zero_()               # L2 flush between steps
+        return precompute(g, links_dev, w['num_hops'], K, w['flow'], w['strategy'],
+                          batch_records=args.batch_records, out=out, profile=profile)
+
+    for _ in range(max(args.warmup, 3)):
+        res = step()
+    barrier()
+    vis = [v for v in os.environ.get('CUDA_VISIBLE_DEVICES', '').split(',') if v.strip()]
+    clocks = ClockSampler(vis[local_rank] if local_rank < len(vis) else local_rank)
+    profile = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    launches = 0
+    for _ in range(args.steps):
+        res = step(profile)
+        launches += res.stats['launches'] + 1           # + the flush memset
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * Lk * args.steps / (ms_max / 1e3)
+
+    # per-kernel times from the events recorded on the launching stream during the timed steps
+    stage_ms = {}
+    for stage, bi, a, b in profile:
+        stage_ms.setdefault(stage, []).append(a.elapsed_time(b))
+    nb = res.stats['batches']
+    gather_ms = float(np.sum(stage_ms.get('gather', [0.0])))
+    gather_launches = len(stage_ms.get('gather', []))
+    st = res.stats
+    gather_bytes_step = 4 * F * st['sum_n'] + 4 * st['rows'] * (K + 1) * (F + 1)
+    path_bytes_step = algorithmic_bytes(st, F, K)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if 'hbm_gbs' in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    achieved = gather_bytes_step * args.steps / (gather_ms / 1e3) / 1e9 if gather_ms > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(args.workload)
+    except Exception:
+        pass
+    roofline = dict(bound="hbm", kernel="gather_kernel<8,3>" if F > 1024 else "gather_kernel", achieved=achieved, peak=peak,
+                    unit="GB/s", frac=achieved / peak, traffic=traffic, peak_source=peak_src,
+                    bytes_per_launch=gather_bytes_step / max(nb, 1), launches_timed=gather_launches,
+                    avg_launch_ms=gather_ms / max(gather_launches, 1),
+                    share_of_step={k: float(np.sum(v)) / ms for k, v in stage_ms.items()},
+                    path=dict(achieved=path_bytes_step * args.steps / (ms / 1e3) / 1e9,
+                              frac=path_bytes_step * args.steps / (ms / 1e3) / 1e9 / peak,
+                              bytes_per_link=path_bytes_step / Lk,
+                              note="whole path: SURVEY 8d bytes/link over the full step time"))
+
+    # ---- allgather of the joint rows (what training on N GPUs needs), timed separately ----
+    allgather = None
+    if world > 1 and fixed:
+        from s3grl_b200.parallel import allgather_rows
+        shard = [o[:2 * (Lk // world)] for o in out]
+        rp = torch.arange(Lk // world + 1, device=dev, dtype=torch.int64) * 2
+        allgather_rows(shard, rp)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        full, _ = allgather_rows(shard, rp)
+        a1.record()
+        barrier()
+        ag = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(ag, op=dist.ReduceOp.MAX)
+        nbytes = sum(f.numel() * 4 for f in full)
+        allgather = dict(ms=float(ag.item()), bytes_per_rank_out=nbytes, busbw_GBps=nbytes * (world - 1) / world / (float(ag.item()) / 1e3) / 1e9,
+                         note="NCCL all_gather_into_tensor of one step's joint rows (strong-scaling shard size: links/N per rank)")
+        del full
+
+    # ---- end to end through the reference-facing call, host buffers in, host buffers out ----
+    e2e = None
+    if not args.no_e2e:
+        from s3grl_b200 import extract_enclosing_subgraphs
+        x_host = torch.from_numpy(w['X']).pin_memory()
+        link_index = torch.from_numpy(np.ascontiguousarray(links_host)).pin_memory()
+        sign_kwargs = dict(sign_k=K, use_feature=True, sign_type=w['flow'], optimize_sign=True,
+                           k_heuristic=0 if fixed else 1, k_node_set_strategy=w['strategy'])
+        os.environ['S3GRL_DEVICE'] = str(dev)
+        os.environ['S3GRL_OUTPUT_DEVICE'] = 'cpu'
+        del out, res
+        torch.cuda.empty_cache()
+
+        def e2e_step():
+            tuned_sign._graph_cache.clear()       # the graph upload is part of every step
+            lst = extract_enclosing_subgraphs(link_index, w['A'], x_host, 1, w['num_hops'], 'zo', 1.0, None, False,
+                                              None, None, sign_kwargs, powers_of_A=[], data=None)
+            d2h = sum(x.numel() * 4 for x in lst.xs) + lst.row_ptr.numel() * 8
+            chk = float(lst.xs[-1][0, 0])        # touch the host result
+            return d2h, chk
+        for _ in range(2):
+            e2e_step()
+        n_e2e = args.e2e_steps or max(2, min(args.steps, 3))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            d2h, _ = e2e_step()
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        h2d = g.h2d_bytes + link_index.numel() * 8
+        e2e = dict(value=world * Lk * n_e2e / float(tt.item()), unit=UNIT, h2d_bytes_per_step=int(h2d),
+                   d2h_bytes_per_step=int(d2h), steps=n_e2e, ms_per_step=1000 * float(tt.item()) / n_e2e,
+                   api="s3grl_b200.extract_enclosing_subgraphs(link_index, A, x, y, num_hops, ..., sign_kwargs) "
+                       "-> host tensors (S3GRL_OUTPUT_DEVICE=cpu)")
+
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                    ms_per_step=ms_max / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="f32", data="synthetic",
+                    config=dict(workload=w['desc'], links_per_step_per_gpu=Lk, batch_records=args.batch_records,
+                                l2="flushed between steps (256 MiB memset); within a step X (39 MB) is L2-resident by nature of the workload",
+                                parallelism=f"links sharded x{world}, graph replicated, no data-path collective"),
+                    clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu)
+        if allgather:
+            line['allgather'] = allgather
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

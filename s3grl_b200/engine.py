@@ -89,11 +89,13 @@ def _records_per_link(flow):
 
 
 def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_records=8192,
-               out=None, return_graphs=False, arena_words=None, stream=None):
+               out=None, return_graphs=False, arena_words=None, stream=None, profile=None):
     """Run the hot path for `links` ([2, L] int64, host or device) on `graph`.
 
     Returns PrecomputeResult with device tensors.  `out`, if given, is a list of K+1
-    preallocated [>=R, F+1] float32 device tensors (fixed-row flows only).
+    preallocated [>=R, F+1] float32 device tensors (fixed-row flows only).  `profile`, if a
+    list, receives (stage, batch, start_event, end_event) for every kernel launch group so the
+    caller can time each kernel on the launching stream with CUDA events.
     Raises ValueError for invalid links (out of range, src == dst), NotImplementedError for an
     unknown strategy (as reference tuned_SIGN.py:235)."""
     lib = L.lib()
@@ -131,13 +133,23 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
         nb = (Lk + batch_links - 1) // batch_links
         counters = torch.zeros((max(nb, 1), L.NCTR), dtype=torch.int64, device=dev)
         words = int(arena_words) if arena_words else max(1 << 24, graph._arena.numel() if graph._arena is not None else 0)
-        stats = dict(records=Lk * rpl, links=Lk, sum_n=0, sum_d=0, max_n=0, rows=0, retries=0, batches=nb)
+        stats = dict(records=Lk * rpl, links=Lk, sum_n=0, sum_d=0, max_n=0, rows=0, retries=0, batches=nb, launches=0)
         pieces, row_counts, graphs = [], [], ([] if return_graphs else None)
 
         def make_batch(b0, b1, arena, off, cnt, ctr, row_ptr=None, item_ptr=None, item_rec=None):
             return L.Batch(_ptr(links[0, b0:b1]), _ptr(links[1, b0:b1]), b1 - b0, cflow, cstrat, int(num_hops), K,
                            _ptr(arena), arena.numel(), _ptr(off), _ptr(cnt), _ptr(ctr),
                            _ptr(row_ptr), _ptr(item_ptr), _ptr(item_rec))
+
+        def timed(stage, bi, fn):
+            if profile is None:
+                return fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            r = fn()
+            e1.record(st)
+            profile.append((stage, bi, e0, e1))
+            return r
 
         def run_batch(bi, arena):
             """Enqueue one batch; returns (cnt, off, pending) where pending finishes Plus flows."""
@@ -149,16 +161,18 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
             ctr.zero_()
             if fixed_rows:
                 batch = make_batch(b0, b1, arena, off, cnt, ctr)
-                L.check(lib.s3_extract(C.byref(graph._c), C.byref(batch), st_ptr), 's3_extract')
-                L.check(lib.s3_diffuse(C.byref(graph._c), C.byref(batch), nrec, st_ptr), 's3_diffuse')
-                L.check(lib.s3_gather(C.byref(graph._c), C.byref(batch), nrec, out_ptrs, F1, b0 * rpl * nseed, st_ptr),
-                        's3_gather')
+                timed('extract', bi, lambda: L.check(lib.s3_extract(C.byref(graph._c), C.byref(batch), st_ptr), 's3_extract'))
+                timed('diffuse', bi, lambda: L.check(lib.s3_diffuse(C.byref(graph._c), C.byref(batch), nrec, st_ptr), 's3_diffuse'))
+                timed('gather', bi, lambda: L.check(
+                    lib.s3_gather(C.byref(graph._c), C.byref(batch), nrec, out_ptrs, F1, b0 * rpl * nseed, st_ptr), 's3_gather'))
+                stats['launches'] += 3
                 return cnt, off, None
             row_ptr = torch.empty(nrec + 1, dtype=torch.int64, device=dev)
             item_ptr = torch.empty(nrec + 1, dtype=torch.int64, device=dev)
             batch = make_batch(b0, b1, arena, off, cnt, ctr, row_ptr, item_ptr)
-            L.check(lib.s3_extract(C.byref(graph._c), C.byref(batch), st_ptr), 's3_extract')
+            timed('extract', bi, lambda: L.check(lib.s3_extract(C.byref(graph._c), C.byref(batch), st_ptr), 's3_extract'))
             L.check(lib.s3_plan(C.byref(batch), st_ptr), 's3_plan')
+            stats['launches'] += 2
             c = ctr.cpu()                                  # sync: rows / items / errors of this batch
             if int(c[L.CTR_ERRORS]) != 0:
                 return cnt, off, 'retry'
@@ -168,8 +182,9 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
             batch = make_batch(b0, b1, arena, off, cnt, ctr, row_ptr, item_ptr, item_rec)
             ptrs = (C.c_void_p * (K + 1))(*[o.data_ptr() for o in xs_b])
             L.check(lib.s3_plan_items(C.byref(batch), st_ptr), 's3_plan_items')
-            L.check(lib.s3_diffuse(C.byref(graph._c), C.byref(batch), items, st_ptr), 's3_diffuse')
-            L.check(lib.s3_gather(C.byref(graph._c), C.byref(batch), items, ptrs, F1, 0, st_ptr), 's3_gather')
+            timed('diffuse', bi, lambda: L.check(lib.s3_diffuse(C.byref(graph._c), C.byref(batch), items, st_ptr), 's3_diffuse'))
+            timed('gather', bi, lambda: L.check(lib.s3_gather(C.byref(graph._c), C.byref(batch), items, ptrs, F1, 0, st_ptr), 's3_gather'))
+            stats['launches'] += 3
             pieces.append(xs_b)
             row_counts.append(row_ptr[1:] - row_ptr[:-1])
             return cnt, off, None
