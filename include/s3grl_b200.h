@@ -60,7 +60,7 @@ extern "C" {
 #define S3_STRATEGY_UNION 2         /* PoS Plus, union minus {0,1}  tuned_SIGN.py:230-231 */
 
 #define S3_MAX_HOPS 8
-#define S3_MAX_K 15
+#define S3_MAX_K 7
 
 /* per-record status written by s3_extract into cnt[S3_CNT_STATUS] */
 #define S3_REC_OK 0

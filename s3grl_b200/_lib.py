@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(HERE, 'lib', 'libs3grl_b200.so')
 S3_OK, S3_ERR_INVALID_ARG, S3_ERR_UNSUPPORTED, S3_ERR_CUDA, S3_ERR_NOT_IMPLEMENTED = 0, 1, 2, 3, 4
 FLOW_POS, FLOW_SOP = 0, 1
 STRATEGY_NONE, STRATEGY_INTERSECTION, STRATEGY_UNION = 0, 1, 2
-MAX_HOPS, MAX_K = 8, 15
+MAX_HOPS, MAX_K = 8, 7
 REC_OK, REC_ARENA_OVERFLOW, REC_BAD_LINK = 0, 1, 2
 OFF_NODES, OFF_ROWPTR, OFF_LCOL, OFF_SEL, OFF_F32, NOFF = 0, 1, 2, 3, 4, 5
 CNT_N, CNT_M, CNT_S, CNT_STATUS, CNT_PARTNER, CNT_HOP0, NCNT = 0, 1, 2, 3, 4, 5, 16

@@ -13,17 +13,12 @@ int cuda_fail(cudaError_t e) {
     return S3_ERR_CUDA;
 }
 
-bool gather_cols_supported(int nw) {
-    return (nw >= 2 && nw <= 8) || nw == 10 || nw == 12 || nw == 14 || nw == 16;
-}
-
 int check_batch(const s3_batch* b) {
     if (!b || b->num_links < 0) return S3_ERR_INVALID_ARG;
     if (b->flow != S3_FLOW_POS && b->flow != S3_FLOW_SOP) return S3_ERR_NOT_IMPLEMENTED;
     if (b->flow == S3_FLOW_POS && (b->strategy < S3_STRATEGY_NONE || b->strategy > S3_STRATEGY_UNION))
         return S3_ERR_NOT_IMPLEMENTED;  // reference: NotImplementedError(f"check strat {strat}"), tuned_SIGN.py:235
     if (b->sign_k < 1 || b->sign_k > S3_MAX_K) return S3_ERR_INVALID_ARG;
-    if (!gather_cols_supported(s3::weight_cols(b->flow, b->sign_k))) return S3_ERR_INVALID_ARG;
     const int radius = b->flow == S3_FLOW_POS ? b->num_hops : b->sign_k;
     if (radius < 0 || radius > S3_MAX_HOPS) return S3_ERR_INVALID_ARG;
     if (b->num_links > 0 && (!b->link_src || !b->link_dst || !b->arena || !b->off || !b->cnt || !b->counters))

@@ -9,10 +9,16 @@
 //      out_k[row(c), 0]     = label weight computed by kernel 2
 // Every subgraph node's feature row is read exactly ONCE (4*F*n bytes, the dominant term of
 // the roofline in SURVEY.md §8d) with 128-bit loads; NW = (K+1)*SC accumulator rows live in
-// registers; weights and node ids are staged through shared memory in tiles. The sum over j
-// runs in canonical node order within each row group, groups are combined in fixed order, so
-// results are independent of scheduling, batch composition and GPU count.
+// registers; weights and node ids are staged through shared memory in tiles.
 //
+// Structural sparsity: a k-step walk cannot reach a node more than k hops away, so a node at
+// hop l of the canonical (hop-major) order has w_k = 0 for k < l (k < l-1 when the selected
+// rows are hop-1 CCN nodes). The node list is walked hop range by hop range with the inner
+// loop specialised on the first live operator, which removes ~2/3 of the FMAs and weight
+// loads on 3-hop subgraphs (most nodes sit on the outermost hop) and skips nodes beyond hop K.
+//
+// The sum over j runs in canonical node order within each row group and groups are combined
+// in fixed order, so results are independent of scheduling, batch composition and GPU count.
 // HBM/L2-bound streaming gather: no tensor cores (M = NW <= 16 rows, fp32 required by the
 // 1e-5 tolerance).
 #include "common.cuh"
@@ -21,6 +27,7 @@ namespace s3 {
 namespace {
 
 constexpr int kTile = 64;  // nodes staged per tile
+constexpr int kU = 4;      // nodes in flight per row group
 
 struct GatherParams {
     const float* __restrict__ x;
@@ -32,17 +39,109 @@ struct GatherParams {
     const int64_t* __restrict__ row_ptr;   // may be null: row = rec * num_seeds
     const int64_t* __restrict__ item_ptr;  // may be null
     const int32_t* __restrict__ item_rec;  // may be null
-    int flow, sign_k, sc, tpr;             // tpr = threads per feature row (32/64/128)
+    int flow, sign_k, tpr;                 // tpr = threads per feature row (32/64/128)
     OutPtrs out;
     int64_t ldo, row_base;
 };
 
-template <int NW, int C>
+template <int C>
+struct GatherCtx {
+    const int32_t* __restrict__ nodes;
+    const float4* __restrict__ wgt4;
+    const float4* __restrict__ x4;
+    int64_t ldx4;
+    int col[C];
+    bool colok[C];
+    float* s_w;
+    int* s_gid;
+    int tid, grp, G;
+};
+
+// Accumulate nodes [lo, hi) of the record; only operators k >= KMIN carry weight there.
+template <int K1, int SC, int C, int KMIN>
+__device__ __forceinline__ void accumulate_range(float4 (&acc)[K1 * SC][C], int lo, int hi, const GatherCtx<C>& cx) {
+    constexpr int NW = K1 * SC, NWP = (NW + 3) & ~3, Q0 = KMIN * SC;
+    const int32_t* __restrict__ nodes = cx.nodes;
+    const float4* __restrict__ wgt4 = cx.wgt4;
+    const float4* __restrict__ x4 = cx.x4;
+    const int64_t ldx4 = cx.ldx4;
+    float* s_w = cx.s_w;
+    int* s_gid = cx.s_gid;
+    const int tid = cx.tid, grp = cx.grp, G = cx.G;
+    const int (&col)[C] = cx.col;
+    const bool (&colok)[C] = cx.colok;
+    for (int base = lo; base < hi; base += kTile) {
+        const int tn = min(kTile, hi - base);
+        __syncthreads();
+        if (tid < tn) s_gid[tid] = nodes[base + tid];
+        {
+            const float4* src = wgt4 + (int64_t)base * (NWP / 4);
+            float4* dst = reinterpret_cast<float4*>(s_w);
+            for (int i = tid; i < tn * (NWP / 4); i += kGatherThreads) dst[i] = src[i];
+        }
+        __syncthreads();
+
+        for (int t0 = grp; t0 < tn; t0 += kU * G) {
+            float4 xv[kU][C];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int t = t0 + u * G;
+                const bool ok = t < tn;
+                const int64_t rowoff = ok ? (int64_t)s_gid[t] * ldx4 : 0;
+#pragma unroll
+                for (int i = 0; i < C; ++i)
+                    xv[u][i] = (ok && colok[i]) ? __ldg(x4 + rowoff + col[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int t = min(t0 + u * G, tn - 1);  // out-of-range slots carry x = 0
+                const float* wrow = s_w + t * NWP;
+                float w[NW];
+                if (SC == 2) {
+#pragma unroll
+                    for (int k = KMIN; k < K1; ++k) {
+                        const float2 v = reinterpret_cast<const float2*>(wrow)[k];
+                        w[2 * k] = v.x;
+                        w[2 * k + 1] = v.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = Q0; q < NW; ++q) w[q] = wrow[q];
+                }
+#pragma unroll
+                for (int q = Q0; q < NW; ++q)
+#pragma unroll
+                    for (int i = 0; i < C; ++i) {
+                        acc[q][i].x = fmaf(w[q], xv[u][i].x, acc[q][i].x);
+                        acc[q][i].y = fmaf(w[q], xv[u][i].y, acc[q][i].y);
+                        acc[q][i].z = fmaf(w[q], xv[u][i].z, acc[q][i].z);
+                        acc[q][i].w = fmaf(w[q], xv[u][i].w, acc[q][i].w);
+                    }
+            }
+        }
+    }
+}
+
+template <int K1, int SC, int C, int KMIN>
+struct RangeDispatch {
+    __device__ __forceinline__ static void run(int kmin, float4 (&acc)[K1 * SC][C], int lo, int hi, const GatherCtx<C>& cx) {
+        if (kmin == KMIN)
+            accumulate_range<K1, SC, C, KMIN>(acc, lo, hi, cx);
+        else
+            RangeDispatch<K1, SC, C, KMIN + 1>::run(kmin, acc, lo, hi, cx);
+    }
+};
+template <int K1, int SC, int C>
+struct RangeDispatch<K1, SC, C, K1> {
+    __device__ __forceinline__ static void run(int, float4 (&)[K1 * SC][C], int, int, const GatherCtx<C>&) {}
+};
+
+template <int K1, int SC, int C>
 __global__ void __launch_bounds__(kGatherThreads) gather_kernel(GatherParams p) {
-    constexpr int NWP = (NW + 3) & ~3;
+    constexpr int NW = K1 * SC, NWP = (NW + 3) & ~3;
     extern __shared__ float4 smem4[];
-    float* s_w = reinterpret_cast<float*>(smem4);                 // [kTile][NWP]
-    int* s_gid = reinterpret_cast<int*>(s_w + kTile * NWP);       // [kTile]
+    float* s_w = reinterpret_cast<float*>(smem4);            // [kTile][NWP]
+    int* s_gid = reinterpret_cast<int*>(s_w + kTile * NWP);  // [kTile]
 
     const int tid = threadIdx.x;
     const int64_t item = blockIdx.x;
@@ -60,13 +159,23 @@ __global__ void __launch_bounds__(kGatherThreads) gather_kernel(GatherParams p) 
 
     const int tpr = p.tpr, G = kGatherThreads / tpr;
     const int grp = tid / tpr, lane = tid - grp * tpr;
-    int col[C];
-    bool colok[C];
+    GatherCtx<C> cx;
+    int (&col)[C] = cx.col;
+    bool (&colok)[C] = cx.colok;
 #pragma unroll
     for (int i = 0; i < C; ++i) {
         col[i] = (blockIdx.y * C + i) * tpr + lane;
         colok[i] = col[i] < p.F4;
     }
+    cx.nodes = nodes;
+    cx.wgt4 = wgt4;
+    cx.x4 = reinterpret_cast<const float4*>(p.x);
+    cx.ldx4 = p.ldx >> 2;
+    cx.s_w = s_w;
+    cx.s_gid = s_gid;
+    cx.tid = tid;
+    cx.grp = grp;
+    cx.G = G;
 
     float4 acc[NW][C];
 #pragma unroll
@@ -74,61 +183,21 @@ __global__ void __launch_bounds__(kGatherThreads) gather_kernel(GatherParams p) 
 #pragma unroll
         for (int i = 0; i < C; ++i) acc[q][i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-    const float4* __restrict__ x4 = reinterpret_cast<const float4*>(p.x);
-    const int64_t ldx4 = p.ldx >> 2;
-
-    for (int base = 0; base < n; base += kTile) {
-        const int tn = min(kTile, n - base);
-        __syncthreads();
-        if (tid < tn) s_gid[tid] = nodes[base + tid];
-        {
-            const float4* src = wgt4 + (int64_t)base * (NWP / 4);
-            float4* dst = reinterpret_cast<float4*>(s_w);
-            for (int i = tid; i < tn * (NWP / 4); i += kGatherThreads) dst[i] = src[i];
-        }
-        __syncthreads();
-
-        constexpr int U = 4;
-        for (int t0 = grp; t0 < tn; t0 += U * G) {
-            float4 xv[U][C];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int t = t0 + u * G;
-                const bool ok = t < tn;
-                const int64_t rowoff = ok ? (int64_t)s_gid[t] * ldx4 : 0;
-#pragma unroll
-                for (int i = 0; i < C; ++i)
-                    xv[u][i] = (ok && colok[i]) ? __ldg(x4 + rowoff + col[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int t = min(t0 + u * G, tn - 1);  // out-of-range slots carry x = 0
-                const float* wrow = s_w + t * NWP;
-                float w[NWP];
-#pragma unroll
-                for (int q4 = 0; q4 < NWP / 4; ++q4) {
-                    const float4 v = reinterpret_cast<const float4*>(wrow)[q4];
-                    w[4 * q4] = v.x;
-                    w[4 * q4 + 1] = v.y;
-                    w[4 * q4 + 2] = v.z;
-                    w[4 * q4 + 3] = v.w;
-                }
-#pragma unroll
-                for (int q = 0; q < NW; ++q)
-#pragma unroll
-                    for (int i = 0; i < C; ++i) {
-                        acc[q][i].x = fmaf(w[q], xv[u][i].x, acc[q][i].x);
-                        acc[q][i].y = fmaf(w[q], xv[u][i].y, acc[q][i].y);
-                        acc[q][i].z = fmaf(w[q], xv[u][i].z, acc[q][i].z);
-                        acc[q][i].w = fmaf(w[q], xv[u][i].w, acc[q][i].w);
-                    }
-            }
-        }
+    // hop ranges of the canonical node order; selected rows of chunk 0 are the seeds, those of
+    // later chunks are hop-1 nodes (one hop closer to everything: kmin shifts down by one)
+    const int shift = chunk == 0 ? 0 : 1;
+    int lo = 0;
+    for (int l = 0; l <= S3_MAX_HOPS && lo < n; ++l) {
+        const int hi = lo + cnt[S3_CNT_HOP0 + l];
+        const int kmin = max(0, l - shift);
+        if (kmin >= K1) break;  // farther than K hops: no operator reaches these nodes
+        if (hi > lo)
+            RangeDispatch<K1, SC, C, 0>::run(kmin, acc, lo, hi, cx);
+        lo = hi;
     }
 
     // combine the G row groups in fixed order (group 0 accumulates groups 1..G-1)
     if (G > 1) {
-        static_assert(C == 1 || true, "");
         float4* red = smem4;  // [(G-1)][NW][C][tpr]
         __syncthreads();
         if (grp > 0) {
@@ -154,12 +223,11 @@ __global__ void __launch_bounds__(kGatherThreads) gather_kernel(GatherParams p) 
     }
     if (grp != 0) return;
 
-    const int sc = p.sc;
-    const int64_t row0 = p.row_base + (p.row_ptr ? p.row_ptr[rec] : rec * (int64_t)num_seeds(p.flow)) + (int64_t)chunk * sc;
+    const int64_t row0 = p.row_base + (p.row_ptr ? p.row_ptr[rec] : rec * (int64_t)num_seeds(p.flow)) + (int64_t)chunk * SC;
 #pragma unroll
     for (int q = 0; q < NW; ++q) {
-        const int k = q / sc, c = q - k * sc;
-        if (chunk * sc + c >= s) continue;
+        const int k = q / SC, c = q - k * SC;
+        if (chunk * SC + c >= s) continue;
         float* orow = p.out.p[k] + (row0 + c) * p.ldo;
         if (blockIdx.y == 0 && lane == 0) orow[0] = lab[q];
 #pragma unroll
@@ -175,22 +243,36 @@ __global__ void __launch_bounds__(kGatherThreads) gather_kernel(GatherParams p) 
     }
 }
 
-template <int NW, int C>
+template <int K1, int SC, int C>
 cudaError_t launch_one(const GatherParams& p, dim3 grid, size_t smem, cudaStream_t st) {
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(gather_kernel<NW, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(gather_kernel<K1, SC, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    gather_kernel<NW, C><<<grid, kGatherThreads, smem, st>>>(p);
+    gather_kernel<K1, SC, C><<<grid, kGatherThreads, smem, st>>>(p);
     return cudaGetLastError();
 }
 
-template <int NW>
+template <int K1, int SC>
 cudaError_t launch_c(const GatherParams& p, int C, dim3 grid, size_t smem, cudaStream_t st) {
     switch (C) {
-        case 1: return launch_one<NW, 1>(p, grid, smem, st);
-        case 2: return launch_one<NW, 2>(p, grid, smem, st);
-        default: return launch_one<NW, 3>(p, grid, smem, st);
+        case 1: return launch_one<K1, SC, 1>(p, grid, smem, st);
+        case 2: return launch_one<K1, SC, 2>(p, grid, smem, st);
+        default: return launch_one<K1, SC, 3>(p, grid, smem, st);
+    }
+}
+
+template <int SC>
+cudaError_t launch_k(const GatherParams& p, int K1, int C, dim3 grid, size_t smem, cudaStream_t st) {
+    switch (K1) {
+        case 2: return launch_c<2, SC>(p, C, grid, smem, st);
+        case 3: return launch_c<3, SC>(p, C, grid, smem, st);
+        case 4: return launch_c<4, SC>(p, C, grid, smem, st);
+        case 5: return launch_c<5, SC>(p, C, grid, smem, st);
+        case 6: return launch_c<6, SC>(p, C, grid, smem, st);
+        case 7: return launch_c<7, SC>(p, C, grid, smem, st);
+        case 8: return launch_c<8, SC>(p, C, grid, smem, st);
+        default: return cudaErrorInvalidValue;
     }
 }
 
@@ -212,7 +294,6 @@ cudaError_t launch_gather(const s3_graph& g, const s3_batch& b, int64_t num_item
     p.item_rec = b.item_rec;
     p.flow = b.flow;
     p.sign_k = b.sign_k;
-    p.sc = sel_chunk(b.flow);
     p.out = out;
     p.ldo = ldo;
     p.row_base = row_base;
@@ -226,6 +307,7 @@ cudaError_t launch_gather(const s3_graph& g, const s3_batch& b, int64_t num_item
     else { C = 3; tpr = 128; }
     p.tpr = tpr;
     const int colchunks = (F4 + tpr * C - 1) / (tpr * C);
+    const int sc = sel_chunk(b.flow);
     const int NW = weight_cols(b.flow, b.sign_k);
     const int NWP = (NW + 3) & ~3;
     const int G = kGatherThreads / tpr;
@@ -233,20 +315,7 @@ cudaError_t launch_gather(const s3_graph& g, const s3_batch& b, int64_t num_item
     const size_t red_bytes = (size_t)(G - 1) * NW * C * tpr * 16;
     const size_t smem = tile_bytes > red_bytes ? tile_bytes : red_bytes;
     dim3 grid((unsigned)num_items, (unsigned)colchunks);
-    switch (NW) {
-        case 2: return launch_c<2>(p, C, grid, smem, st);
-        case 3: return launch_c<3>(p, C, grid, smem, st);
-        case 4: return launch_c<4>(p, C, grid, smem, st);
-        case 5: return launch_c<5>(p, C, grid, smem, st);
-        case 6: return launch_c<6>(p, C, grid, smem, st);
-        case 7: return launch_c<7>(p, C, grid, smem, st);
-        case 8: return launch_c<8>(p, C, grid, smem, st);
-        case 10: return launch_c<10>(p, C, grid, smem, st);
-        case 12: return launch_c<12>(p, C, grid, smem, st);
-        case 14: return launch_c<14>(p, C, grid, smem, st);
-        case 16: return launch_c<16>(p, C, grid, smem, st);
-        default: return cudaErrorInvalidValue;
-    }
+    return sc == 2 ? launch_k<2>(p, b.sign_k + 1, C, grid, smem, st) : launch_k<1>(p, b.sign_k + 1, C, grid, smem, st);
 }
 
 }  // namespace s3

@@ -132,7 +132,13 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
         batch_links = max(1, int(batch_records) // rpl)
         nb = (Lk + batch_links - 1) // batch_links
         counters = torch.zeros((max(nb, 1), L.NCTR), dtype=torch.int64, device=dev)
-        words = int(arena_words) if arena_words else max(1 << 24, graph._arena.numel() if graph._arena is not None else 0)
+        if arena_words:
+            words = int(arena_words)
+        else:   # ~128 KiB of scratch per record to start with (PubMed h=3 averages ~100 KiB), grown on overflow
+            free, _ = torch.cuda.mem_get_info(dev)
+            words = max(1 << 22, min(int(batch_records) * 32768, free // 16))
+            if graph._arena is not None:
+                words = max(words, graph._arena.numel())
         stats = dict(records=Lk * rpl, links=Lk, sum_n=0, sum_d=0, max_n=0, rows=0, retries=0, batches=nb, launches=0)
         pieces, row_counts, graphs = [], [], ([] if return_graphs else None)
 
