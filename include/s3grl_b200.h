@@ -51,6 +51,7 @@ extern "C" {
 #define S3_ERR_UNSUPPORTED 2     /* graph too large for the selected extraction tier        */
 #define S3_ERR_CUDA 3            /* a CUDA runtime call failed; see s3_last_cuda_error()     */
 #define S3_ERR_NOT_IMPLEMENTED 4 /* unknown strategy / flow (reference: NotImplementedError) */
+#define S3_ERR_WORKSPACE 5       /* arena smaller than s3_min_arena_words(): nothing was launched */
 
 /* flows (reference sign_type) and row-selection strategies (reference k_node_set_strategy) */
 #define S3_FLOW_POS 0
@@ -68,12 +69,15 @@ extern "C" {
 #define S3_REC_BAD_LINK 2        /* node id out of range or src == dst               */
 
 /* per-record int64 offsets (in 4-byte words from the arena base), off[rec*S3_NOFF + i] */
+/* The local CSR is padded: row j occupies lcol[rowptr[j] .. rowptr[j] + rowlen[j]), where    */
+/* rowptr is the prefix sum of the nodes' GLOBAL degrees (rowptr[n] = D).                      */
 #define S3_OFF_NODES 0   /* int32 global ids, n                                   */
-#define S3_OFF_ROWPTR 1  /* int32 local CSR row pointer, n+1                      */
-#define S3_OFF_LCOL 2    /* int32 local column ids, m                             */
-#define S3_OFF_SEL 3     /* int32 extra selected local ids, s - num_seeds         */
-#define S3_OFF_F32 4     /* float scratch of the record's work items              */
-#define S3_NOFF 5
+#define S3_OFF_ROWPTR 1  /* int32 row starts into lcol, n+1                       */
+#define S3_OFF_ROWLEN 2  /* int32 induced + masked degree of every row, n         */
+#define S3_OFF_LCOL 3    /* int32 local column ids, D slots of which m are used   */
+#define S3_OFF_SEL 4     /* int32 extra selected local ids, s - num_seeds         */
+#define S3_OFF_F32 5     /* float scratch of the record's work items              */
+#define S3_NOFF 6
 
 /* per-record int32 counts, cnt[rec*S3_NCNT + i] */
 #define S3_CNT_N 0        /* subgraph nodes                                       */
@@ -92,6 +96,7 @@ extern "C" {
 #define S3_CTR_MAX_N 4     /* largest subgraph in the batch                               */
 #define S3_CTR_SUM_N 5     /* sum of n  (roofline accounting: 4*F*sum_n feature bytes)    */
 #define S3_CTR_SUM_D 6     /* sum over subgraph nodes of their global degree (4*D bytes)  */
+#define S3_CTR_WORK 7      /* work-queue head of the persistent extraction CTAs           */
 #define S3_NCTR 8
 
 /* Device-resident graph: CSR of the training graph (both directions stored, columns
@@ -137,6 +142,10 @@ const char* s3_last_cuda_error(void);
 int64_t s3_num_records(const s3_batch* b);
 /* upper bound of work items s3_plan can produce is not known before extract; after
  * s3_plan + a stream sync the exact numbers are counters[S3_CTR_ROWS] / [S3_CTR_ITEMS]. */
+
+/* smallest arena s3_extract accepts for this graph (per-CTA node slabs live at its head);
+ * a useful arena is much larger: roughly 14*n + D + 12*n*ceil(s/2) words per record. */
+int64_t s3_min_arena_words(int64_t num_nodes);
 
 /* dynamic shared memory the bitmap extraction tier needs for this graph, or -1 if the
  * graph is too large for it (then S3_ERR_UNSUPPORTED from s3_extract). */

@@ -7,16 +7,17 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'lib', 'libs3grl_b200.so')
 
 # constants mirrored from the header
-S3_OK, S3_ERR_INVALID_ARG, S3_ERR_UNSUPPORTED, S3_ERR_CUDA, S3_ERR_NOT_IMPLEMENTED = 0, 1, 2, 3, 4
+S3_OK, S3_ERR_INVALID_ARG, S3_ERR_UNSUPPORTED, S3_ERR_CUDA, S3_ERR_NOT_IMPLEMENTED, S3_ERR_WORKSPACE = 0, 1, 2, 3, 4, 5
 FLOW_POS, FLOW_SOP = 0, 1
 STRATEGY_NONE, STRATEGY_INTERSECTION, STRATEGY_UNION = 0, 1, 2
 MAX_HOPS, MAX_K = 8, 7
 REC_OK, REC_ARENA_OVERFLOW, REC_BAD_LINK = 0, 1, 2
-OFF_NODES, OFF_ROWPTR, OFF_LCOL, OFF_SEL, OFF_F32, NOFF = 0, 1, 2, 3, 4, 5
+OFF_NODES, OFF_ROWPTR, OFF_ROWLEN, OFF_LCOL, OFF_SEL, OFF_F32, NOFF = 0, 1, 2, 3, 4, 5, 6
 CNT_N, CNT_M, CNT_S, CNT_STATUS, CNT_PARTNER, CNT_HOP0, NCNT = 0, 1, 2, 3, 4, 5, 16
-CTR_CURSOR, CTR_ERRORS, CTR_ROWS, CTR_ITEMS, CTR_MAX_N, CTR_SUM_N, CTR_SUM_D, NCTR = 0, 1, 2, 3, 4, 5, 6, 8
+CTR_CURSOR, CTR_ERRORS, CTR_ROWS, CTR_ITEMS, CTR_MAX_N, CTR_SUM_N, CTR_SUM_D, CTR_WORK, NCTR = 0, 1, 2, 3, 4, 5, 6, 7, 8
 
 EXPORTS = ['s3_version', 's3_error_string', 's3_last_cuda_error', 's3_num_records', 's3_extract_smem_bytes',
+           's3_min_arena_words',
            's3_extract', 's3_plan', 's3_plan_items', 's3_diffuse', 's3_gather', 's3_dump_edges']
 
 
@@ -57,6 +58,8 @@ def lib():
         L.s3_last_cuda_error.restype = C.c_char_p
         L.s3_num_records.restype = C.c_int64
         L.s3_num_records.argtypes = [C.POINTER(Batch)]
+        L.s3_min_arena_words.restype = C.c_int64
+        L.s3_min_arena_words.argtypes = [C.c_int64]
         L.s3_extract_smem_bytes.restype = C.c_int64
         L.s3_extract_smem_bytes.argtypes = [C.c_int64, C.c_int32]
         L.s3_extract.argtypes = [C.POINTER(Graph), C.POINTER(Batch), C.c_void_p]

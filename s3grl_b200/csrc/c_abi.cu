@@ -48,6 +48,7 @@ const char* s3_error_string(int code) {
         case S3_ERR_UNSUPPORTED: return "graph too large for the bitmap extraction tier";
         case S3_ERR_CUDA: return "CUDA error";
         case S3_ERR_NOT_IMPLEMENTED: return "unknown flow or strategy";
+        case S3_ERR_WORKSPACE: return "arena smaller than s3_min_arena_words()";
         default: return "unknown error code";
     }
 }
@@ -55,6 +56,8 @@ const char* s3_error_string(int code) {
 const char* s3_last_cuda_error(void) { return g_cuda_err; }
 
 int64_t s3_num_records(const s3_batch* b) { return b->flow == S3_FLOW_SOP ? 2 * b->num_links : b->num_links; }
+
+int64_t s3_min_arena_words(int64_t num_nodes) { return 2 * ((2 * num_nodes + 31) & ~int64_t(31)); }
 
 int64_t s3_extract_smem_bytes(int64_t num_nodes, int32_t radius) {
     if (num_nodes <= 0 || radius < 0 || radius > S3_MAX_HOPS) return -1;
@@ -70,8 +73,10 @@ int s3_extract(const s3_graph* g, const s3_batch* b, void* stream) {
     if (rc != S3_OK) return rc;
     const int radius = b->flow == S3_FLOW_POS ? b->num_hops : b->sign_k;
     if (s3_extract_smem_bytes(g->num_nodes, radius) < 0) return S3_ERR_UNSUPPORTED;
-    cudaError_t e = s3::launch_extract_bitmap(*g, *b, static_cast<cudaStream_t>(stream));
-    return e == cudaSuccess ? S3_OK : cuda_fail(e);
+    int launch_rc = S3_OK;
+    cudaError_t e = s3::launch_extract_bitmap(*g, *b, static_cast<cudaStream_t>(stream), &launch_rc);
+    if (e != cudaSuccess) return cuda_fail(e);
+    return launch_rc;
 }
 
 int s3_plan(const s3_batch* b, void* stream) {

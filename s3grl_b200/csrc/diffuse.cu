@@ -9,15 +9,22 @@
 // with w_0 = e_sel and z_k = w_k D^-1/2,
 //      t_j = sum_{i in N(j)} z_{k-1}[i],   w_k[j] = dis_j t_j,   z_k[j] = dis_j^2 t_j
 // (A_sub symmetric), i.e. K segmented CSR SpMV sweeps per selected row instead of K-1 SpGEMMs.
-// Sums run over the local CSR row in its stored order, so results do not depend on scheduling.
+// A k-step walk cannot leave the k-hop ball of the selected rows, so sweep k only visits the
+// nodes of hops <= k (+1 when the selected rows are hop-1 CCN nodes) of the hop-major node
+// order; everything beyond is an exact zero that kernel 3 never reads.
 //
-// One CTA per work item (= up to SC selected rows of one record). Output per item, in the
-// record's float scratch:  labels[NWP] | weights[n][NWP] | z ping | z pong,  weight column
-// q = k*SC + c for operator k (k = 0 is the one-hot selecting x itself) and selected row c.
+// One CTA per work item (= up to SC selected rows of one record), one 8-lane group per node:
+// lanes stride the node's local row, partial sums are combined by a fixed shuffle tree, so
+// results do not depend on scheduling. z ping-pong buffers live in shared memory when the
+// subgraph fits, else in the item's global scratch. Output per item, in the record's float
+// scratch:  labels[NWP] | weights[n][NWP] | z ping | z pong,  weight column q = k*SC + c for
+// operator k (k = 0 is the one-hot selecting x itself) and selected row c.
 #include "common.cuh"
 
 namespace s3 {
 namespace {
+
+constexpr int kZCap = 4096;  // floats per shared z buffer (2 buffers: 32 KB)
 
 struct DiffuseParams {
     const int64_t* __restrict__ indptr;  // SoP: global degrees
@@ -31,7 +38,10 @@ struct DiffuseParams {
 
 template <int SC>
 __global__ void __launch_bounds__(kDiffuseThreads) diffuse_kernel(DiffuseParams p) {
-    const int tid = threadIdx.x, T = blockDim.x;
+    __shared__ float s_z[2][kZCap];
+    const int tid = threadIdx.x, T = kDiffuseThreads;
+    const int l8 = tid & 7, grp = tid >> 3;
+    constexpr int NG = kDiffuseThreads / 8;
     const int64_t item = blockIdx.x;
     const int64_t rec = p.item_rec ? p.item_rec[item] : item;
     const int32_t* cnt = p.cnt + rec * S3_NCNT;
@@ -43,13 +53,15 @@ __global__ void __launch_bounds__(kDiffuseThreads) diffuse_kernel(DiffuseParams 
     const int64_t* off = p.off + rec * S3_NOFF;
     const int32_t* nodes = p.arena + off[S3_OFF_NODES];
     const int32_t* rowptr = p.arena + off[S3_OFF_ROWPTR];
+    const int32_t* rowlen = p.arena + off[S3_OFF_ROWLEN];
     const int32_t* lcol = p.arena + off[S3_OFF_LCOL];
     const int32_t* sel = p.arena + off[S3_OFF_SEL];
     float* item_f = reinterpret_cast<float*>(p.arena + off[S3_OFF_F32]) + (int64_t)chunk * item_words(p.flow, K, n);
     float* lab = item_f;
     float* wgt = item_f + NWP;
-    float* zA = wgt + (int64_t)n * NWP;
-    float* zB = zA + (int64_t)n * SC;
+    const bool z_shared = (int64_t)n * SC <= kZCap;
+    float* zA = z_shared ? s_z[0] : wgt + (int64_t)n * NWP;
+    float* zB = z_shared ? s_z[1] : wgt + (int64_t)n * NWP + (int64_t)n * SC;
 
     // selected local rows of this item
     int r[SC];
@@ -58,24 +70,49 @@ __global__ void __launch_bounds__(kDiffuseThreads) diffuse_kernel(DiffuseParams 
         const int i = chunk * SC + c;
         r[c] = i >= s ? -1 : (i < nseed ? i : sel[i - nseed]);
     }
-
-    // k = 0: one-hot weights, z_0 = e_sel D^-1/2
-    for (int j = tid; j < n; j += T) {
-        int deg;
-        if (p.flow == S3_FLOW_SOP) {
-            const int g = nodes[j];
-            deg = (int)(p.indptr[g + 1] - p.indptr[g]);  // global degree (sgrl_link_pred.py:165-168)
-        } else {
-            deg = rowptr[j + 1] - rowptr[j];  // induced, masked degree (tuned_SIGN.py:158)
+    // reach[k] = number of leading nodes (hop-major order) a k-step walk from the selected rows
+    // can touch: hops <= k for seed rows, hops <= k+1 for hop-1 (CCN) rows
+    const int shift = chunk == 0 ? 0 : 1;
+    int hop_end[S3_MAX_HOPS + 2];
+    {
+        int acc = 0;
+#pragma unroll
+        for (int l = 0; l <= S3_MAX_HOPS; ++l) {
+            acc += cnt[S3_CNT_HOP0 + l];
+            hop_end[l] = acc;
         }
-        const float dis = deg > 0 ? 1.0f / sqrtf((float)deg) : 0.0f;  // inf -> 0 (tuned_SIGN.py:159-160)
-        float* wj = wgt + (int64_t)j * NWP;
-        for (int q = SC; q < NWP; ++q) wj[q] = 0.0f;
+        hop_end[S3_MAX_HOPS + 1] = acc;
+    }
+    auto reach = [&](int k) { return hop_end[min(k + shift, S3_MAX_HOPS + 1)]; };
+
+    // k = 0: one-hot weights on the reachable prefix, z_0 = e_sel D^-1/2 on ALL nodes (both
+    // buffers must be zero beyond what later sweeps overwrite)
+    const int n0 = reach(0);
+    for (int j = tid; j < n; j += T) {
+        float zv[SC];
+#pragma unroll
+        for (int c = 0; c < SC; ++c) zv[c] = 0.0f;
+        if (j < n0) {
+            int deg;
+            if (p.flow == S3_FLOW_SOP) {
+                const int g = nodes[j];
+                deg = (int)(p.indptr[g + 1] - p.indptr[g]);  // global degree (sgrl_link_pred.py:165-168)
+            } else {
+                deg = rowlen[j];  // induced, masked degree (tuned_SIGN.py:158)
+            }
+            const float dis = deg > 0 ? 1.0f / sqrtf((float)deg) : 0.0f;  // inf -> 0 (tuned_SIGN.py:159-160)
+            float* wj = wgt + (int64_t)j * NWP;
+#pragma unroll
+            for (int c = 0; c < SC; ++c) {
+                const float one = (j == r[c]) ? 1.0f : 0.0f;
+                wj[c] = one;
+                zv[c] = one * dis;
+            }
+        }
 #pragma unroll
         for (int c = 0; c < SC; ++c) {
-            const float one = (j == r[c]) ? 1.0f : 0.0f;
-            wj[c] = one;
-            zA[(int64_t)j * SC + c] = one * dis;
+            zA[(int64_t)j * SC + c] = zv[c];
+            zB[(int64_t)j * SC + c] = 0.0f;
         }
     }
     __syncthreads();
@@ -83,29 +120,42 @@ __global__ void __launch_bounds__(kDiffuseThreads) diffuse_kernel(DiffuseParams 
     float* zprev = zA;
     float* znext = zB;
     for (int k = 1; k <= K; ++k) {
-        for (int j = tid; j < n; j += T) {
-            const int e0 = rowptr[j], e1 = rowptr[j + 1];
-            int deg;
-            if (p.flow == S3_FLOW_SOP) {
-                const int g = nodes[j];
-                deg = (int)(p.indptr[g + 1] - p.indptr[g]);
-            } else {
-                deg = e1 - e0;
+        const int nk = reach(k);
+        for (int jb = 0; jb < nk; jb += NG) {
+            const int j = jb + grp;
+            const bool valid = j < nk;
+            int e0 = 0, len = 0;
+            if (valid) {
+                e0 = rowptr[j];
+                len = rowlen[j];
             }
-            const float dis = deg > 0 ? 1.0f / sqrtf((float)deg) : 0.0f;
             float t[SC];
 #pragma unroll
             for (int c = 0; c < SC; ++c) t[c] = 0.0f;
-            for (int e = e0; e < e1; ++e) {
-                const int i = lcol[e];
+            for (int e = l8; e < len; e += 8) {
+                const int i = lcol[e0 + e];
 #pragma unroll
                 for (int c = 0; c < SC; ++c) t[c] += zprev[(int64_t)i * SC + c];
             }
 #pragma unroll
             for (int c = 0; c < SC; ++c) {
-                const float w = dis * t[c];
-                wgt[(int64_t)j * NWP + k * SC + c] = w;
-                znext[(int64_t)j * SC + c] = dis * w;
+                t[c] += __shfl_xor_sync(0xffffffffu, t[c], 4);
+                t[c] += __shfl_xor_sync(0xffffffffu, t[c], 2);
+                t[c] += __shfl_xor_sync(0xffffffffu, t[c], 1);
+            }
+            if (valid && l8 == 0) {
+                int deg = len;
+                if (p.flow == S3_FLOW_SOP) {
+                    const int g = nodes[j];
+                    deg = (int)(p.indptr[g + 1] - p.indptr[g]);
+                }
+                const float dis = deg > 0 ? 1.0f / sqrtf((float)deg) : 0.0f;
+#pragma unroll
+                for (int c = 0; c < SC; ++c) {
+                    const float w = dis * t[c];
+                    wgt[(int64_t)j * NWP + k * SC + c] = w;
+                    znext[(int64_t)j * SC + c] = dis * w;
+                }
             }
         }
         __syncthreads();
@@ -116,14 +166,23 @@ __global__ void __launch_bounds__(kDiffuseThreads) diffuse_kernel(DiffuseParams 
 
     // label / self-return column of every operator, then (SoP) drop the partner's weight
     if (p.flow == S3_FLOW_POS) {
-        // x_k[sel, 0] = sum_j w_k[j] * label_j, label = 1 on local 0 and 1 (tuned_SIGN.py:177)
-        for (int q = tid; q < NWP; q += T) lab[q] = q < NW ? wgt[q] + wgt[NWP + q] : 0.0f;
+        // x_k[sel, 0] = sum_j w_k[j] * label_j, label = 1 on local 0 and 1 (tuned_SIGN.py:177).
+        // Weights of operator k exist on the first reach(k) nodes only.
+        for (int q = tid; q < NWP; q += T) {
+            float v = 0.0f;
+            if (q < NW) {
+                const int nk = reach(q / SC);
+                if (nk > 0) v += wgt[q];
+                if (nk > 1) v += wgt[NWP + q];
+            }
+            lab[q] = v;
+        }
     } else {
         // x_k[., 0] = A^k[u,u] (tuned_SIGN.py:106-113); x[., 0] = 1 (tuned_SIGN.py:119-124)
         for (int q = tid; q < NWP; q += T) lab[q] = q < NW ? wgt[q] : 0.0f;
         __syncthreads();
         const int partner = cnt[S3_CNT_PARTNER];
-        if (partner >= 0)  // r_u[v] = 0 (tuned_SIGN.py:73-76); k = 0 is already 0 there
+        if (partner >= 0)  // r_u[v] = 0 (tuned_SIGN.py:73-76); columns k < hop(partner) are never read
             for (int q = SC + tid; q < NW; q += T) wgt[(int64_t)partner * NWP + q] = 0.0f;
     }
 }

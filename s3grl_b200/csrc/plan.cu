@@ -66,14 +66,34 @@ __global__ void dump_edges_kernel(const int32_t* __restrict__ arena, const int64
     const int n = cnt[rec * S3_NCNT + S3_CNT_N];
     const int32_t* nodes = arena + off[rec * S3_NOFF + S3_OFF_NODES];
     const int32_t* rowptr = arena + off[rec * S3_NOFF + S3_OFF_ROWPTR];
+    const int32_t* rowlen = arena + off[rec * S3_NOFF + S3_OFF_ROWLEN];
     const int32_t* lcol = arena + off[rec * S3_NOFF + S3_OFF_LCOL];
     int32_t* out = edges_out + 2 * edge_ptr[rec];
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-        const int g = nodes[j];
-        for (int e = rowptr[j]; e < rowptr[j + 1]; ++e) {
-            out[2 * (int64_t)e] = g;
-            out[2 * (int64_t)e + 1] = nodes[lcol[e]];
+    // compact position of row j = sum of rowlen[0..j): serial prefix by one thread per tile
+    __shared__ int s_run;
+    __shared__ int s_pos[128];
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int j = base + threadIdx.x;
+        if (threadIdx.x == 0) {
+            int run = s_run;
+            for (int t = 0; t < (int)blockDim.x && base + t < n; ++t) {
+                s_pos[t] = run;
+                run += rowlen[base + t];
+            }
+            s_run = run;
         }
+        __syncthreads();
+        if (j < n) {
+            const int g = nodes[j];
+            const int pos = s_pos[threadIdx.x];
+            for (int e = 0; e < rowlen[j]; ++e) {
+                out[2 * (int64_t)(pos + e)] = g;
+                out[2 * (int64_t)(pos + e) + 1] = nodes[lcol[rowptr[j] + e]];
+            }
+        }
+        __syncthreads();
     }
 }
 

@@ -139,6 +139,7 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
             words = max(1 << 22, min(int(batch_records) * 32768, free // 16))
             if graph._arena is not None:
                 words = max(words, graph._arena.numel())
+        words = max(words, 4 * int(lib.s3_min_arena_words(graph.num_nodes)))
         stats = dict(records=Lk * rpl, links=Lk, sum_n=0, sum_d=0, max_n=0, rows=0, retries=0, batches=nb, launches=0)
         pieces, row_counts, graphs = [], [], ([] if return_graphs else None)
 
@@ -213,8 +214,14 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
             for r in range(cn.shape[0]):
                 n, m, s = int(cn[r, L.CNT_N]), int(cn[r, L.CNT_M]), int(cn[r, L.CNT_S])
                 nodes = ar[of[r, L.OFF_NODES]:of[r, L.OFF_NODES] + n].astype(np.int64)
-                rowptr = ar[of[r, L.OFF_ROWPTR]:of[r, L.OFF_ROWPTR] + n + 1].astype(np.int64)
-                lcol = ar[of[r, L.OFF_LCOL]:of[r, L.OFF_LCOL] + m].copy()
+                rstart = ar[of[r, L.OFF_ROWPTR]:of[r, L.OFF_ROWPTR] + n + 1].astype(np.int64)
+                rlen = ar[of[r, L.OFF_ROWLEN]:of[r, L.OFF_ROWLEN] + n].astype(np.int64)
+                padded = ar[of[r, L.OFF_LCOL]:of[r, L.OFF_LCOL] + int(rstart[n])]
+                rowptr = np.zeros(n + 1, dtype=np.int64)      # compact the padded CSR
+                np.cumsum(rlen, out=rowptr[1:])
+                assert int(rowptr[n]) == m
+                take = np.repeat(rstart[:n] - rowptr[:n], rlen) + np.arange(m)
+                lcol = padded[take].copy()
                 sel = np.concatenate([np.arange(nseed), ar[of[r, L.OFF_SEL]:of[r, L.OFF_SEL] + s - nseed]]).astype(np.int32)
                 hop_cnt = cn[r, L.CNT_HOP0:L.CNT_HOP0 + L.MAX_HOPS + 1]
                 hops = np.repeat(np.arange(L.MAX_HOPS + 1), hop_cnt).astype(np.int32)
