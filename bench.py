@@ -239,9 +239,11 @@ def main():
     barrier()
     e0.record()
     launches = 0
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
         res = step(profile)
         launches += res.stats['launches'] + 1           # + the flush memset
+    host_enqueue_ms = res.stats.get('host_enqueue_ms')
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -350,7 +352,8 @@ def main():
                     config=dict(workload=w['desc'], links_per_step_per_gpu=Lk, batch_records=args.batch_records,
                                 l2="flushed between steps (256 MiB memset); within a step X (39 MB) is L2-resident by nature of the workload",
                                 parallelism=f"links sharded x{world}, graph replicated, no data-path collective"),
-                    clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu)
+                    clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu,
+                    host_enqueue_ms_per_step=host_enqueue_ms)
         if allgather:
             line['allgather'] = allgather
         print(json.dumps(line))

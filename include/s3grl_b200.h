@@ -69,8 +69,10 @@ extern "C" {
 #define S3_REC_BAD_LINK 2        /* node id out of range or src == dst               */
 
 /* per-record int64 offsets (in 4-byte words from the arena base), off[rec*S3_NOFF + i] */
-/* The local CSR is padded: row j occupies lcol[rowptr[j] .. rowptr[j] + rowlen[j]), where    */
-/* rowptr is the prefix sum of the nodes' GLOBAL degrees (rowptr[n] = D).                      */
+/* The local CSR is padded: row j owns the slots lcol[rowptr[j] .. rowptr[j+1]), one per entry */
+/* of the node's GLOBAL adjacency list in its order (rowptr = prefix sum of global degrees,    */
+/* rowptr[n] = D); a slot holds the neighbour's local id, or -1 when the neighbour is outside  */
+/* the subgraph or the entry is the masked target link. rowlen[j] counts the non-holes.        */
 #define S3_OFF_NODES 0   /* int32 global ids, n                                   */
 #define S3_OFF_ROWPTR 1  /* int32 row starts into lcol, n+1                       */
 #define S3_OFF_ROWLEN 2  /* int32 induced + masked degree of every row, n         */
@@ -110,6 +112,7 @@ typedef struct s3_graph {
     int64_t num_nodes;
     int64_t num_feat;       /* F                                            */
     int64_t ldx;            /* row stride in floats, multiple of 4, >= F    */
+    int64_t num_edges;      /* indptr[num_nodes]; < 2^32 for the bitmap tier */
 } s3_graph;
 
 /* One batch of records and its scratch. */

@@ -23,7 +23,7 @@ EXPORTS = ['s3_version', 's3_error_string', 's3_last_cuda_error', 's3_num_record
 
 class Graph(C.Structure):
     _fields_ = [('indptr', C.c_void_p), ('indices', C.c_void_p), ('x', C.c_void_p),
-                ('num_nodes', C.c_int64), ('num_feat', C.c_int64), ('ldx', C.c_int64)]
+                ('num_nodes', C.c_int64), ('num_feat', C.c_int64), ('ldx', C.c_int64), ('num_edges', C.c_int64)]
 
 
 class Batch(C.Structure):

@@ -29,6 +29,7 @@ int check_batch(const s3_batch* b) {
 
 int check_graph(const s3_graph* g, bool need_x) {
     if (!g || !g->indptr || !g->indices || g->num_nodes <= 0 || g->num_nodes > INT32_MAX) return S3_ERR_INVALID_ARG;
+    if (g->num_edges < 0) return S3_ERR_INVALID_ARG;
     if (need_x) {
         if (!g->x || g->num_feat <= 0 || g->ldx < g->num_feat || (g->ldx & 3)) return S3_ERR_INVALID_ARG;
         if (reinterpret_cast<uintptr_t>(g->x) & 15) return S3_ERR_INVALID_ARG;
@@ -57,7 +58,7 @@ const char* s3_last_cuda_error(void) { return g_cuda_err; }
 
 int64_t s3_num_records(const s3_batch* b) { return b->flow == S3_FLOW_SOP ? 2 * b->num_links : b->num_links; }
 
-int64_t s3_min_arena_words(int64_t num_nodes) { return 2 * ((2 * num_nodes + 31) & ~int64_t(31)); }
+int64_t s3_min_arena_words(int64_t num_nodes) { return 2 * ((3 * num_nodes + 31) & ~int64_t(31)); }
 
 int64_t s3_extract_smem_bytes(int64_t num_nodes, int32_t radius) {
     if (num_nodes <= 0 || radius < 0 || radius > S3_MAX_HOPS) return -1;
@@ -72,7 +73,7 @@ int s3_extract(const s3_graph* g, const s3_batch* b, void* stream) {
     rc = check_batch(b);
     if (rc != S3_OK) return rc;
     const int radius = b->flow == S3_FLOW_POS ? b->num_hops : b->sign_k;
-    if (s3_extract_smem_bytes(g->num_nodes, radius) < 0) return S3_ERR_UNSUPPORTED;
+    if (s3_extract_smem_bytes(g->num_nodes, radius) < 0 || g->num_edges >= (int64_t(1) << 32)) return S3_ERR_UNSUPPORTED;
     int launch_rc = S3_OK;
     cudaError_t e = s3::launch_extract_bitmap(*g, *b, static_cast<cudaStream_t>(stream), &launch_rc);
     if (e != cudaSuccess) return cuda_fail(e);

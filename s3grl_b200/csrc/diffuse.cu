@@ -124,18 +124,20 @@ __global__ void __launch_bounds__(kDiffuseThreads) diffuse_kernel(DiffuseParams 
         for (int jb = 0; jb < nk; jb += NG) {
             const int j = jb + grp;
             const bool valid = j < nk;
-            int e0 = 0, len = 0;
+            int e0 = 0, e1 = 0;
             if (valid) {
                 e0 = rowptr[j];
-                len = rowlen[j];
+                e1 = rowptr[j + 1];
             }
             float t[SC];
 #pragma unroll
             for (int c = 0; c < SC; ++c) t[c] = 0.0f;
-            for (int e = l8; e < len; e += 8) {
-                const int i = lcol[e0 + e];
+            for (int e = e0 + l8; e < e1; e += 8) {
+                const int i = lcol[e];  // -1: neighbour outside the subgraph / masked target link
+                if (i >= 0) {
 #pragma unroll
-                for (int c = 0; c < SC; ++c) t[c] += zprev[(int64_t)i * SC + c];
+                    for (int c = 0; c < SC; ++c) t[c] += zprev[(int64_t)i * SC + c];
+                }
             }
 #pragma unroll
             for (int c = 0; c < SC; ++c) {
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(kDiffuseThreads) diffuse_kernel(DiffuseParams 
                 t[c] += __shfl_xor_sync(0xffffffffu, t[c], 1);
             }
             if (valid && l8 == 0) {
-                int deg = len;
+                int deg = rowlen[j];
                 if (p.flow == S3_FLOW_SOP) {
                     const int g = nodes[j];
                     deg = (int)(p.indptr[g + 1] - p.indptr[g]);

@@ -10,11 +10,13 @@
 // exclusive popcount prefix per level. A level bitmap enumerated in word order IS the level
 // sorted by global id, so the canonical order [seeds, then (hop, global id) ascending] needs no
 // sort, and  local_id(g) = level_base + prefix[word(g)] + popc(bits below g)  needs no hash.
-// Each CTA owns a slab [nodes N | degrees N] at the head of the arena for the growing node
-// list; adjacency lists are scanned by 8-lane groups (one 32-byte sector per step), twice in
-// total: once to expand the frontier, once to emit local column ids with a ballot-ordered
-// compaction. The local CSR is "padded": row j starts at the prefix sum of GLOBAL degrees
-// (known without scanning) and carries its own length, which removes the count pass.
+// Each CTA owns a slab [nodes N | degrees N | adjacency offsets N] at the head of the arena for the growing node
+// list. Adjacency lists are scanned twice in total: once by 8-lane groups to expand the
+// frontier, once EDGE-PARALLEL to emit local column ids: the local CSR is "padded" — row j
+// owns deg_G(j) slots starting at the prefix sum of GLOBAL degrees (known without scanning),
+// slot t of the subgraph maps to its row by a binary search of that prefix in shared memory,
+// and a neighbour outside the subgraph (or the masked target link) leaves a -1 hole. Every
+// lane does useful work whatever the degree distribution; no count pass, no compaction.
 // Results go to a bump-allocated arena in global memory (one atomicAdd per allocation);
 // placement depends on scheduling, contents do not.
 #include "common.cuh"
@@ -33,27 +35,31 @@ struct ExtractParams {
     int W;  // bitmap words
     int32_t* arena;
     int64_t arena_words;
-    int64_t slab_stride;  // words per CTA slab (2 * N rounded up), slabs sit at the arena head
+    int64_t slab_stride;  // words per CTA slab (3 * N rounded up), slabs sit at the arena head
     int64_t slab_words;   // gridDim.x * slab_stride: bump allocations start here
     int64_t* off;
     int32_t* cnt;
     unsigned long long* counters;
 };
 
+constexpr int kRowCap = 3072;  // rows whose (start, adjacency offset) pairs are cached in shared memory
+
 __device__ __forceinline__ bool test_bit(const uint32_t* bm, int g) { return (bm[g >> 5] >> (g & 31)) & 1u; }
 
 // local id of global node g, which must be in the subgraph
 __device__ __forceinline__ int local_id(int g, int s0, int s1, int nseed, const uint32_t* Lb, const uint32_t* pre,
                                         const int* lvl_base, int nlev, int W) {
-    if (g == s0) return 0;
-    if (nseed == 2 && g == s1) return 1;
-    const int w = g >> 5;
-    const uint32_t below = (1u << (g & 31)) - 1u;
-    for (int l = 0; l < nlev; ++l) {
+    const int w = g >> 5, b = g & 31;
+    const uint32_t below = (1u << b) - 1u;
+    int lid = -1;
+    for (int l = 0; l < nlev; ++l) {  // block-uniform trip count, no early exit: no divergence
         const uint32_t bits = Lb[l * W + w];
-        if ((bits >> (g & 31)) & 1u) return lvl_base[l] + (int)pre[l * W + w] + __popc(bits & below);
+        const int cand = lvl_base[l] + (int)pre[l * W + w] + __popc(bits & below);
+        lid = ((bits >> b) & 1u) ? cand : lid;
     }
-    return -1;  // unreachable for members of V
+    if (nseed == 2 && g == s1) lid = 1;
+    if (g == s0) lid = 0;
+    return lid;
 }
 
 __global__ void __launch_bounds__(kExtractThreads) extract_bitmap_kernel(ExtractParams p) {
@@ -69,14 +75,16 @@ __global__ void __launch_bounds__(kExtractThreads) extract_bitmap_kernel(Extract
     __shared__ long long s_rec;
     __shared__ unsigned long long s_sumdeg;
     __shared__ int s_m;
+    __shared__ int s_rowptr[kRowCap + 1];        // row starts of the current record when n <= kRowCap
+    __shared__ uint32_t s_estart[kRowCap];       // indptr[node] of every row
 
     int32_t* slab_nodes = p.arena + (int64_t)blockIdx.x * p.slab_stride;
     int32_t* slab_deg = slab_nodes + p.num_nodes;
+    uint32_t* slab_estart = reinterpret_cast<uint32_t*>(slab_deg + p.num_nodes);
     const int nseed = num_seeds(p.flow);
     const bool mask_target = p.flow == S3_FLOW_POS;
     const int lane = tid & 31, l8 = tid & 7, grp = tid >> 3;  // 8-lane groups
     constexpr int NG = kExtractThreads / 8;
-    const int grp_in_warp = (tid >> 3) & 3;
 
     for (;;) {
         __syncthreads();
@@ -116,12 +124,14 @@ __global__ void __launch_bounds__(kExtractThreads) extract_bitmap_kernel(Extract
             slab_nodes[0] = s0;
             const int d0 = (int)(p.indptr[s0 + 1] - p.indptr[s0]);
             slab_deg[0] = d0;
+            slab_estart[0] = (uint32_t)p.indptr[s0];
             my_deg += d0;
             if (nseed == 2) {
                 V[s1 >> 5] |= 1u << (s1 & 31);
                 slab_nodes[1] = s1;
                 const int d1 = (int)(p.indptr[s1 + 1] - p.indptr[s1]);
                 slab_deg[1] = d1;
+                slab_estart[1] = (uint32_t)p.indptr[s1];
                 my_deg += d1;
             }
             s_lvl_cnt[0] = nseed;
@@ -138,8 +148,7 @@ __global__ void __launch_bounds__(kExtractThreads) extract_bitmap_kernel(Extract
             uint32_t* cur = Lb + (size_t)l * W;
             // frontier = slab_nodes[flo, n): one 8-lane group per node, 32 B of column ids per step
             for (int j = flo + grp; j < n; j += NG) {
-                const int g = slab_nodes[j];
-                const int64_t e0 = p.indptr[g], e1 = e0 + slab_deg[j];
+                const int64_t e0 = slab_estart[j], e1 = e0 + slab_deg[j];
                 for (int64_t e = e0 + l8; e < e1; e += 8) {
                     const int c = p.indices[e];
                     if (!test_bit(V, c)) atomicOr(&cur[c >> 5], 1u << (c & 31));
@@ -166,9 +175,11 @@ __global__ void __launch_bounds__(kExtractThreads) extract_bitmap_kernel(Extract
                     const int bit = __ffs(bb) - 1;
                     bb &= bb - 1;
                     const int g = w * 32 + bit;
-                    const int d = (int)(p.indptr[g + 1] - p.indptr[g]);
+                    const int64_t ge0 = p.indptr[g];
+                    const int d = (int)(p.indptr[g + 1] - ge0);
                     slab_nodes[r] = g;
                     slab_deg[r] = d;
+                    slab_estart[r] = (uint32_t)ge0;
                     my_deg += d;
                     ++r;
                 }
@@ -210,6 +221,7 @@ __global__ void __launch_bounds__(kExtractThreads) extract_bitmap_kernel(Extract
         int s = nseed, partner_local = -1;
         if (!overflow) {
             // node list + exclusive scan of global degrees, tile by tile
+            const bool cached = n <= kRowCap;
             int running = 0;
             for (int base = 0; base < n; base += T) {
                 const int j = base + tid;
@@ -219,45 +231,49 @@ __global__ void __launch_bounds__(kExtractThreads) extract_bitmap_kernel(Extract
                 if (j < n) {
                     nodes[j] = slab_nodes[j];
                     rowptr[j] = running + ex;
+                    rowlen[j] = 0;
+                    if (cached) {
+                        s_rowptr[j] = running + ex;
+                        s_estart[j] = slab_estart[j];
+                    }
                 }
                 running += tile_total;
                 __syncthreads();  // s_scan is reused by the next tile
             }
-            if (tid == 0) rowptr[n] = running;
+            if (tid == 0) {
+                rowptr[n] = running;
+                if (cached) s_rowptr[n] = running;
+            }
             __syncthreads();
 
-            // ---------------- fill: local column ids, ascending global id per row ----------------
+            // ---------------- fill: one lane per adjacency slot of the subgraph ----------------
+            const int* rp = cached ? s_rowptr : rowptr;
+            const uint32_t* es = cached ? s_estart : slab_estart;
             int my_m = 0;
-            for (int jb = 0; jb < n; jb += NG) {
-                const int j = jb + grp;
-                const bool valid = j < n;
-                int g = 0, len = 0, rs = 0;
-                int64_t e0 = 0;
-                if (valid) {
-                    g = slab_nodes[j];
-                    len = slab_deg[j];
-                    e0 = p.indptr[g];
-                    rs = rowptr[j];
+            const int Di = (int)D;
+            for (int slot0 = (tid >> 5) * 32; slot0 < Di; slot0 += T) {
+                const int slot = slot0 + lane;
+                const bool ok = slot < Di;
+                int lo = 0, hi = n;  // rp[lo] <= slot < rp[hi]; picks the last of equal starts (degree-0 rows)
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (rp[mid] <= slot) lo = mid; else hi = mid;
                 }
-                int iters = (len + 7) >> 3;
-                iters = max(iters, __shfl_xor_sync(0xffffffffu, iters, 8));
-                iters = max(iters, __shfl_xor_sync(0xffffffffu, iters, 16));
-                int kept = 0;
-                for (int it = 0; it < iters; ++it) {
-                    const int idx = it * 8 + l8;
-                    const bool ok = valid && idx < len;
-                    const int c = ok ? p.indices[e0 + idx] : 0;
-                    bool in = ok && test_bit(V, c);
-                    if (in && mask_target && ((j == 0 && c == s1) || (j == 1 && c == s0))) in = false;  // utils.py:79-80
-                    const unsigned ball = __ballot_sync(0xffffffffu, in);
-                    const unsigned gb = (ball >> (grp_in_warp * 8)) & 0xffu;
-                    if (in) lcol[rs + kept + __popc(gb & ((1u << l8) - 1u))] = local_id(c, s0, s1, nseed, Lb, pre, s_lvl_base, nlev, W);
-                    kept += __popc(gb);
+                const int j = lo;
+                int lid = -1;
+                bool in = false;
+                if (ok) {
+                    const int c = p.indices[(int64_t)es[j] + (slot - rp[j])];
+                    in = test_bit(V, c);
+                    if (mask_target && ((j == 0 && c == s1) || (j == 1 && c == s0))) in = false;  // utils.py:79-80
+                    if (in) lid = local_id(c, s0, s1, nseed, Lb, pre, s_lvl_base, nlev, W);
+                    lcol[slot] = lid;
                 }
-                if (valid && l8 == 0) {
-                    rowlen[j] = kept;
-                    my_m += kept;
-                }
+                // induced degree: one integer atomic per (row, warp step)
+                const unsigned seg = __match_any_sync(0xffffffffu, ok ? j : -1 - lane);
+                const int kept = __popc(__ballot_sync(0xffffffffu, in) & seg);
+                if (ok && kept && (__ffs(seg) - 1) == lane) atomicAdd(&rowlen[j], kept);
+                my_m += in ? 1 : 0;
             }
             for (int d = 16; d > 0; d >>= 1) my_m += __shfl_down_sync(0xffffffffu, my_m, d);
             if (lane == 0 && my_m) atomicAdd(&s_m, my_m);
@@ -278,12 +294,12 @@ __global__ void __launch_bounds__(kExtractThreads) extract_bitmap_kernel(Extract
                     F1[w] = 0u;
                 }
                 __syncthreads();
-                for (int e = tid; e < rowlen[0]; e += T) {
-                    const int c = lcol[rowptr[0] + e] - 2;
+                for (int e = rowptr[0] + tid; e < rowptr[1]; e += T) {
+                    const int c = lcol[e] - 2;  // holes are -1, seeds 0/1: both excluded
                     if (c >= 0) atomicOr(&F0[c >> 5], 1u << (c & 31));
                 }
-                for (int e = tid; e < rowlen[1]; e += T) {
-                    const int c = lcol[rowptr[1] + e] - 2;
+                for (int e = rowptr[1] + tid; e < rowptr[2]; e += T) {
+                    const int c = lcol[e] - 2;
                     if (c >= 0) atomicOr(&F1[c >> 5], 1u << (c & 31));
                 }
                 __syncthreads();
@@ -369,14 +385,22 @@ cudaError_t launch_extract_bitmap(const s3_graph& g, const s3_batch& b, cudaStre
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    int dev = 0, sms = 0, occ = 0;
+    // device queries are slow host calls: cache them per (device, smem) pair
+    static int c_dev = -1, c_sms = 0, c_occ = 0;
+    static size_t c_smem = 0;
+    int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, extract_bitmap_kernel, kExtractThreads, smem);
-    if (e != cudaSuccess) return e;
-    p.slab_stride = (2 * g.num_nodes + 31) & ~int64_t(31);
+    if (dev != c_dev || smem != c_smem) {
+        e = cudaDeviceGetAttribute(&c_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c_occ, extract_bitmap_kernel, kExtractThreads, smem);
+        if (e != cudaSuccess) return e;
+        c_dev = dev;
+        c_smem = smem;
+    }
+    const int sms = c_sms, occ = c_occ;
+    p.slab_stride = (3 * g.num_nodes + 31) & ~int64_t(31);
     int64_t grid = (int64_t)sms * (occ > 0 ? occ : 1);
     if (grid > p.num_records) grid = p.num_records;
     const int64_t fit = (b.arena_words / 2) / p.slab_stride;  // slabs may take at most half of the arena

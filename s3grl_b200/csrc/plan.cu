@@ -88,9 +88,13 @@ __global__ void dump_edges_kernel(const int32_t* __restrict__ arena, const int64
         if (j < n) {
             const int g = nodes[j];
             const int pos = s_pos[threadIdx.x];
-            for (int e = 0; e < rowlen[j]; ++e) {
-                out[2 * (int64_t)(pos + e)] = g;
-                out[2 * (int64_t)(pos + e) + 1] = nodes[lcol[rowptr[j] + e]];
+            int k = 0;
+            for (int e = rowptr[j]; e < rowptr[j + 1]; ++e) {
+                const int c = lcol[e];
+                if (c < 0) continue;  // hole of the padded CSR
+                out[2 * (int64_t)(pos + k)] = g;
+                out[2 * (int64_t)(pos + k) + 1] = nodes[c];
+                ++k;
             }
         }
         __syncthreads();

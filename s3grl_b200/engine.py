@@ -11,6 +11,7 @@ PyTorch is used for device memory, streams and (in parallel.py) torch.distribute
 compute is in libs3grl_b200.so.  There is no CPU fallback.
 """
 import ctypes as C
+import time
 
 import numpy as np
 import scipy.sparse as ssp
@@ -64,7 +65,7 @@ class DeviceGraph:
         self.x[:, :self.num_feat].copy_(x, non_blocking=True)
         self.h2d_bytes = self.indptr.numel() * 8 + self.indices.numel() * 4 + x.numel() * 4
         self._c = L.Graph(_ptr(self.indptr), _ptr(self.indices), _ptr(self.x), self.num_nodes, self.num_feat,
-                          self.ldx)
+                          self.ldx, self.nnz)
         self._arena = None
 
     # scratch arena (int32 words), grown on demand and kept across calls
@@ -196,8 +197,8 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
             row_counts.append(row_ptr[1:] - row_ptr[:-1])
             return cnt, off, None
 
-        def check_and_account(bi, cnt):
-            c = counters[bi].cpu()
+        def check_and_account(bi, cnt, host_counters=None):
+            c = counters[bi].cpu() if host_counters is None else host_counters[bi]
             if int(c[L.CTR_ERRORS]) != 0:
                 status = cnt[:, L.CNT_STATUS]
                 if bool((status == L.REC_BAD_LINK).any()):
@@ -217,11 +218,11 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
                 rstart = ar[of[r, L.OFF_ROWPTR]:of[r, L.OFF_ROWPTR] + n + 1].astype(np.int64)
                 rlen = ar[of[r, L.OFF_ROWLEN]:of[r, L.OFF_ROWLEN] + n].astype(np.int64)
                 padded = ar[of[r, L.OFF_LCOL]:of[r, L.OFF_LCOL] + int(rstart[n])]
-                rowptr = np.zeros(n + 1, dtype=np.int64)      # compact the padded CSR
+                rowptr = np.zeros(n + 1, dtype=np.int64)      # compact the padded CSR (holes are -1)
                 np.cumsum(rlen, out=rowptr[1:])
-                assert int(rowptr[n]) == m
-                take = np.repeat(rstart[:n] - rowptr[:n], rlen) + np.arange(m)
-                lcol = padded[take].copy()
+                lcol = padded[padded >= 0].copy()
+                owner = np.repeat(np.arange(n), np.diff(rstart))[padded >= 0]
+                assert int(rowptr[n]) == m == lcol.size and np.array_equal(np.bincount(owner, minlength=n), rlen)
                 sel = np.concatenate([np.arange(nseed), ar[of[r, L.OFF_SEL]:of[r, L.OFF_SEL] + s - nseed]]).astype(np.int32)
                 hop_cnt = cn[r, L.CNT_HOP0:L.CNT_HOP0 + L.MAX_HOPS + 1]
                 hops = np.repeat(np.arange(L.MAX_HOPS + 1), hop_cnt).astype(np.int32)
@@ -244,6 +245,7 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
             while todo:
                 arena = graph.arena(words)
                 metas = []
+                t_enq = time.perf_counter()
                 for bi in todo:
                     cnt, off, _ = run_batch(bi, arena)
                     if return_graphs:   # the arena is recycled by the next batch: dump now
@@ -252,8 +254,10 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
                             dump(bi, cnt, off, arena)
                             continue
                     metas.append((bi, cnt))
+                stats['host_enqueue_ms'] = 1000 * (time.perf_counter() - t_enq)
                 st.synchronize()
-                todo = [bi for bi, cnt in metas if not (False if return_graphs else check_and_account(bi, cnt))]
+                hc = counters.cpu()       # one D2H for every batch's counters
+                todo = [bi for bi, cnt in metas if not (False if return_graphs else check_and_account(bi, cnt, hc))]
                 if todo:
                     if return_graphs and graphs:
                         raise RuntimeError("arena overflow while dumping graphs: pass a larger arena_words")
