@@ -134,6 +134,8 @@ class ClockSampler:
 
     def __init__(self, index):
         self.p = None
+        if os.environ.get('S3GRL_BENCH_NO_CLOCKS'):
+            return
         try:
             self.p = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
                                        '-lms', '100', '-i', str(index)], stdout=subprocess.PIPE,
@@ -179,6 +181,7 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--overlap', action='store_true', help='two-stream front/back overlap (measured slower on PubMed: L2 contention)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -227,7 +230,7 @@ def main():
     def step(profile=None):
         flush.zero_()               # L2 flush between steps
         return precompute(g, links_dev, w['num_hops'], K, w['flow'], w['strategy'],
-                          batch_records=args.batch_records, out=out, profile=profile)
+                          batch_records=args.batch_records, out=out, profile=profile, overlap=args.overlap)
 
     for _ in range(max(args.warmup, 3)):
         res = step()

@@ -13,13 +13,16 @@
  * One precompute call over a batch of B "records" is three stages (north_star kernels 1-3):
  *
  *   s3_extract  : per record, h-hop frontier expansion over the device-resident CSR, dedup,
- *                 canonical renumbering, induced + target-masked local CSR, row selection.
+ *                 canonical renumbering, induced + target-masked local CSR, row selection,
+ *                 AND the diffusion weights of the record's first work item (the rows of the
+ *                 two targets) — the "front" kernel.
  *                 replaces reference utils.py:33-85 (neighbors, k_hop_subgraph BFS branch),
- *                 the ssp.find at tuned_SIGN.py:153/:208 and the CCN row selection
- *                 tuned_SIGN.py:228-238.
+ *                 the ssp.find at tuned_SIGN.py:153/:208, the CCN row selection
+ *                 tuned_SIGN.py:228-238 and tuned_SIGN.py:155-175 for rows [0,1].
  *   s3_plan     : row_ptr / work-item lists from the per-record selected-row counts
  *                 (the slices PyG's collate would record, sgrl_link_pred.py:204).
- *   s3_diffuse  : per work item, S = D^-1/2 A_sub D^-1/2 and the K row vectors e_sel^T S^k
+ *   s3_diffuse  : per LATER work item (PoS Plus CCN rows; a no-op otherwise),
+ *                 S = D^-1/2 A_sub D^-1/2 and the K row vectors e_sel^T S^k
  *                 replaces tuned_SIGN.py:155-175 (normalise, SpGEMM powers, row select)
  *                 and, in SoP flow, sgrl_link_pred.py:161-178 + tuned_SIGN.py:60-86, :106-113.
  *   s3_gather   : per work item, x_k[sel] = (e_sel^T S^k) [label | X_sub] for k = 0..K written
@@ -69,6 +72,7 @@ extern "C" {
 #define S3_REC_BAD_LINK 2        /* node id out of range or src == dst               */
 
 /* per-record int64 offsets (in 4-byte words from the arena base), off[rec*S3_NOFF + i] */
+/* Only rows j < cnt[S3_CNT_NSTORE] are stored (see s3_extract).                                */
 /* The local CSR is padded: row j owns the slots lcol[rowptr[j] .. rowptr[j+1]), one per entry */
 /* of the node's GLOBAL adjacency list in its order (rowptr = prefix sum of global degrees,    */
 /* rowptr[n] = D); a slot holds the neighbour's local id, or -1 when the neighbour is outside  */
@@ -83,11 +87,12 @@ extern "C" {
 
 /* per-record int32 counts, cnt[rec*S3_NCNT + i] */
 #define S3_CNT_N 0        /* subgraph nodes                                       */
-#define S3_CNT_M 1        /* directed induced edges after masking                 */
+#define S3_CNT_M 1        /* directed induced edges after masking, over the STORED rows */
 #define S3_CNT_S 2        /* selected rows                                        */
 #define S3_CNT_STATUS 3
 #define S3_CNT_PARTNER 4  /* SoP: local id of the other endpoint in the ball, or -1 */
 #define S3_CNT_HOP0 5     /* S3_CNT_HOP0 + l = number of nodes at hop l, l = 0..S3_MAX_HOPS */
+#define S3_CNT_NSTORE 14  /* rows kept in the padded CSR: hops <= K-1, or all n with S3_BATCH_STORE_ALL_ROWS */
 #define S3_NCNT 16
 
 /* int64 counters[S3_NCTR]; the caller zeroes them before s3_extract */
@@ -115,6 +120,10 @@ typedef struct s3_graph {
     int64_t num_edges;      /* indptr[num_nodes]; < 2^32 for the bitmap tier */
 } s3_graph;
 
+/* s3_batch.flags: keep every row of the induced adjacency (parity dumps). Without it rows of
+ * hop == K are streamed once and never stored (PoS Plus always stores all rows). */
+#define S3_BATCH_STORE_ALL_ROWS 1
+
 /* One batch of records and its scratch. */
 typedef struct s3_batch {
     const int64_t* link_src; /* [num_links] device                                         */
@@ -124,6 +133,8 @@ typedef struct s3_batch {
     int32_t strategy;        /* S3_STRATEGY_* (PoS flow only)                               */
     int32_t num_hops;        /* PoS: h.  SoP: ignored (the ball radius is sign_k)           */
     int32_t sign_k;          /* K operators beyond x                                        */
+    int32_t flags;           /* S3_BATCH_* bits                                             */
+    int32_t reserved;
     int32_t* arena;          /* scratch, 16-byte aligned                                    */
     int64_t arena_words;     /* capacity in 4-byte words                                    */
     int64_t* off;            /* [num_records * S3_NOFF]                                     */

@@ -13,7 +13,8 @@ STRATEGY_NONE, STRATEGY_INTERSECTION, STRATEGY_UNION = 0, 1, 2
 MAX_HOPS, MAX_K = 8, 7
 REC_OK, REC_ARENA_OVERFLOW, REC_BAD_LINK = 0, 1, 2
 OFF_NODES, OFF_ROWPTR, OFF_ROWLEN, OFF_LCOL, OFF_SEL, OFF_F32, NOFF = 0, 1, 2, 3, 4, 5, 6
-CNT_N, CNT_M, CNT_S, CNT_STATUS, CNT_PARTNER, CNT_HOP0, NCNT = 0, 1, 2, 3, 4, 5, 16
+CNT_N, CNT_M, CNT_S, CNT_STATUS, CNT_PARTNER, CNT_HOP0, CNT_NSTORE, NCNT = 0, 1, 2, 3, 4, 5, 14, 16
+BATCH_STORE_ALL_ROWS = 1
 CTR_CURSOR, CTR_ERRORS, CTR_ROWS, CTR_ITEMS, CTR_MAX_N, CTR_SUM_N, CTR_SUM_D, CTR_WORK, NCTR = 0, 1, 2, 3, 4, 5, 6, 7, 8
 
 EXPORTS = ['s3_version', 's3_error_string', 's3_last_cuda_error', 's3_num_records', 's3_extract_smem_bytes',
@@ -29,6 +30,7 @@ class Graph(C.Structure):
 class Batch(C.Structure):
     _fields_ = [('link_src', C.c_void_p), ('link_dst', C.c_void_p), ('num_links', C.c_int64),
                 ('flow', C.c_int32), ('strategy', C.c_int32), ('num_hops', C.c_int32), ('sign_k', C.c_int32),
+                ('flags', C.c_int32), ('reserved', C.c_int32),
                 ('arena', C.c_void_p), ('arena_words', C.c_int64),
                 ('off', C.c_void_p), ('cnt', C.c_void_p), ('counters', C.c_void_p),
                 ('row_ptr', C.c_void_p), ('item_ptr', C.c_void_p), ('item_rec', C.c_void_p)]

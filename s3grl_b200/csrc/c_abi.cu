@@ -58,7 +58,7 @@ const char* s3_last_cuda_error(void) { return g_cuda_err; }
 
 int64_t s3_num_records(const s3_batch* b) { return b->flow == S3_FLOW_SOP ? 2 * b->num_links : b->num_links; }
 
-int64_t s3_min_arena_words(int64_t num_nodes) { return 2 * ((3 * num_nodes + 31) & ~int64_t(31)); }
+int64_t s3_min_arena_words(int64_t num_nodes) { return 2 * ((4 * num_nodes + 1 + 31) & ~int64_t(31)); }
 
 int64_t s3_extract_smem_bytes(int64_t num_nodes, int32_t radius) {
     if (num_nodes <= 0 || radius < 0 || radius > S3_MAX_HOPS) return -1;

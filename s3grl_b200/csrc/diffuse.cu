@@ -13,6 +13,9 @@
 // nodes of hops <= k (+1 when the selected rows are hop-1 CCN nodes) of the hop-major node
 // order; everything beyond is an exact zero that kernel 3 never reads.
 //
+// Work item 0 of every record (the rows of the two targets) is diffused inside the front
+// kernel (extract.cu); this kernel handles the later items — PoS Plus CCN rows — over the fully
+// stored padded CSR.
 // One CTA per work item (= up to SC selected rows of one record), one 8-lane group per node:
 // lanes stride the node's local row, partial sums are combined by a fixed shuffle tree, so
 // results do not depend on scheduling. z ping-pong buffers live in shared memory when the
@@ -47,6 +50,7 @@ __global__ void __launch_bounds__(kDiffuseThreads) diffuse_kernel(DiffuseParams 
     const int32_t* cnt = p.cnt + rec * S3_NCNT;
     if (cnt[S3_CNT_STATUS] != S3_REC_OK) return;
     const int chunk = p.item_ptr ? (int)(item - p.item_ptr[rec]) : 0;
+    if (chunk == 0) return;  // work item 0 was diffused by the front kernel (extract.cu)
     const int n = cnt[S3_CNT_N], s = cnt[S3_CNT_S];
     const int K = p.sign_k, nseed = num_seeds(p.flow);
     const int NW = (K + 1) * SC, NWP = (NW + 3) & ~3;

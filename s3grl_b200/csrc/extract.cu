@@ -1,24 +1,40 @@
-// Kernel 1 — enclosing-subgraph extraction, bitmap tier (graphs whose node-id bitmaps fit in
-// shared memory: every dataset bundled with the reference; N up to a few hundred thousand).
+// Kernel 1 — "front" kernel, bitmap tier: enclosing-subgraph extraction FUSED with the diffusion
+// sweeps of the record's first work item (graphs whose node-id bitmaps fit in shared memory:
+// every dataset bundled with the reference; N up to a few hundred thousand).
 //
 // Replaces, per record: reference utils.py:33-44 (neighbors), utils.py:53-74 (BFS),
 // utils.py:76 (A[nodes,:][:,nodes]), utils.py:79-80 (target-link mask), the ssp.find at
-// tuned_SIGN.py:153/:208 and the PoS-Plus row selection tuned_SIGN.py:228-238.
+// tuned_SIGN.py:153/:208, the PoS-Plus row selection tuned_SIGN.py:228-238, and for the rows of
+// the two targets tuned_SIGN.py:155-175 (normalise, powers, row select) — in SoP flow
+// sgrl_link_pred.py:161-178 + tuned_SIGN.py:60-86, :106-113.
 //
 // Persistent CTAs (one wave, grid = SMs x resident CTAs) pull records from an atomic work
 // counter. Shared memory holds a visited bitmap V, one bitmap per hop level and a per-word
 // exclusive popcount prefix per level. A level bitmap enumerated in word order IS the level
 // sorted by global id, so the canonical order [seeds, then (hop, global id) ascending] needs no
 // sort, and  local_id(g) = level_base + prefix[word(g)] + popc(bits below g)  needs no hash.
-// Each CTA owns a slab [nodes N | degrees N | adjacency offsets N] at the head of the arena for the growing node
-// list. Adjacency lists are scanned twice in total: once by 8-lane groups to expand the
-// frontier, once EDGE-PARALLEL to emit local column ids: the local CSR is "padded" — row j
-// owns deg_G(j) slots starting at the prefix sum of GLOBAL degrees (known without scanning),
-// slot t of the subgraph maps to its row by a binary search of that prefix in shared memory,
-// and a neighbour outside the subgraph (or the masked target link) leaves a -1 hole. Every
-// lane does useful work whatever the degree distribution; no count pass, no compaction.
+// Each CTA owns a slab [nodes | degrees | adjacency offsets | row starts] at the head of the
+// arena for the growing node list.
+//
+// Which rows of the induced adjacency are ever needed?  With w_0 = e_sel, z_k = w_k D^-1/2:
+//      t_j = sum_{i in N(j)} z_{k-1}[i],   w_k[j] = dis_j t_j,   z_k[j] = dis_j^2 t_j
+// and a k-step walk stays inside the k-hop ball, sweep k touches rows of hop <= k and reads z
+// only on hop <= k-1. Rows of hop <= K-1 are read by several sweeps: they are STORED, as a
+// padded CSR (row j owns deg_G(j) slots at the prefix sum of global degrees; a neighbour
+// outside the subgraph or the masked target link leaves a -1 hole), filled edge-parallel, one
+// lane per slot. Rows of hop == K are read exactly once, by the last sweep: they are STREAMED
+// — their adjacency is scanned once by 8-lane groups, accumulating z_{K-1} of the inner
+// neighbours and the induced degree on the fly — and never stored. Nodes beyond hop K get no
+// weight at all. On a 3-hop PubMed subgraph (n ~ 930, of which ~770 on hop 3) this stores
+// ~2 k of ~9 k adjacency slots and removes the largest sweep. When later work items (PoS Plus
+// CCN rows) or a parity dump need every row, S3_BATCH_STORE_ALL_ROWS stores them all and the
+// stand-alone diffuse kernel (diffuse.cu) handles the remaining items.
+//
 // Results go to a bump-allocated arena in global memory (one atomicAdd per allocation);
-// placement depends on scheduling, contents do not.
+// placement depends on scheduling, contents do not. Sums run in fixed order (row slots by
+// lane, fixed shuffle tree), so results are independent of scheduling.
+#include <climits>
+
 #include "common.cuh"
 
 namespace s3 {
@@ -31,28 +47,30 @@ struct ExtractParams {
     const int64_t* __restrict__ link_src;
     const int64_t* __restrict__ link_dst;
     int64_t num_records;
-    int flow, strategy, radius, sign_k;
+    int flow, strategy, radius, sign_k, store_all;
     int W;  // bitmap words
     int32_t* arena;
     int64_t arena_words;
-    int64_t slab_stride;  // words per CTA slab (3 * N rounded up), slabs sit at the arena head
+    int64_t slab_stride;  // words per CTA slab, slabs sit at the arena head
     int64_t slab_words;   // gridDim.x * slab_stride: bump allocations start here
     int64_t* off;
     int32_t* cnt;
     unsigned long long* counters;
 };
 
-constexpr int kRowCap = 3072;  // rows whose (start, adjacency offset) pairs are cached in shared memory
+constexpr int kRowCap = 2560;  // rows whose (start, adjacency offset) are cached in shared memory
+constexpr int kZCap = 2048;    // floats per shared z buffer
 
 __device__ __forceinline__ bool test_bit(const uint32_t* bm, int g) { return (bm[g >> 5] >> (g & 31)) & 1u; }
 
-// local id of global node g, which must be in the subgraph
+// local id of global node g if it sits on one of the first `levels` hop levels (or is a seed),
+// else -1. Block-uniform trip count, no early exit: no divergence.
 __device__ __forceinline__ int local_id(int g, int s0, int s1, int nseed, const uint32_t* Lb, const uint32_t* pre,
-                                        const int* lvl_base, int nlev, int W) {
+                                        const int* lvl_base, int levels, int W) {
     const int w = g >> 5, b = g & 31;
     const uint32_t below = (1u << b) - 1u;
     int lid = -1;
-    for (int l = 0; l < nlev; ++l) {  // block-uniform trip count, no early exit: no divergence
+    for (int l = 0; l < levels; ++l) {
         const uint32_t bits = Lb[l * W + w];
         const int cand = lvl_base[l] + (int)pre[l * W + w] + __popc(bits & below);
         lid = ((bits >> b) & 1u) ? cand : lid;
@@ -62,29 +80,34 @@ __device__ __forceinline__ int local_id(int g, int s0, int s1, int nseed, const 
     return lid;
 }
 
-__global__ void __launch_bounds__(kExtractThreads) extract_bitmap_kernel(ExtractParams p) {
+template <int SC>  // selected rows of the first work item == number of seeds: 2 (PoS), 1 (SoP)
+__global__ void __launch_bounds__(kExtractThreads, 4) front_kernel(ExtractParams p) {
     extern __shared__ uint32_t sm[];
-    const int W = p.W, h = p.radius, T = kExtractThreads, tid = threadIdx.x;
+    const int W = p.W, h = p.radius, T = kExtractThreads, tid = threadIdx.x, K = p.sign_k;
+    constexpr int nseed = SC;
     uint32_t* V = sm;
     uint32_t* Lb = V + W;                // [h][W]
     uint32_t* pre = Lb + (size_t)h * W;  // [h][W]
     __shared__ int s_scan[33];
     __shared__ int s_lvl_base[S3_MAX_HOPS + 2];
     __shared__ int s_lvl_cnt[S3_MAX_HOPS + 1];
+    __shared__ int s_hop_end[S3_MAX_HOPS + 2];
     __shared__ long long s_base;
     __shared__ long long s_rec;
     __shared__ unsigned long long s_sumdeg;
     __shared__ int s_m;
-    __shared__ int s_rowptr[kRowCap + 1];        // row starts of the current record when n <= kRowCap
-    __shared__ uint32_t s_estart[kRowCap];       // indptr[node] of every row
+    __shared__ int s_rowptr[kRowCap + 1];   // row starts of the current record when n_rows <= kRowCap
+    __shared__ uint32_t s_estart[kRowCap];  // indptr[node] of every row
+    __shared__ float s_z[2][kZCap];
 
     int32_t* slab_nodes = p.arena + (int64_t)blockIdx.x * p.slab_stride;
     int32_t* slab_deg = slab_nodes + p.num_nodes;
     uint32_t* slab_estart = reinterpret_cast<uint32_t*>(slab_deg + p.num_nodes);
-    const int nseed = num_seeds(p.flow);
-    const bool mask_target = p.flow == S3_FLOW_POS;
+    int32_t* slab_rp = slab_deg + 2 * p.num_nodes;  // [N + 1]
+    const bool pos_flow = p.flow == S3_FLOW_POS;
     const int lane = tid & 31, l8 = tid & 7, grp = tid >> 3;  // 8-lane groups
     constexpr int NG = kExtractThreads / 8;
+    const int NW = (K + 1) * SC, NWP = (NW + 3) & ~3;
 
     for (;;) {
         __syncthreads();
@@ -94,7 +117,7 @@ __global__ void __launch_bounds__(kExtractThreads) extract_bitmap_kernel(Extract
         if (rec >= p.num_records) break;
 
         int64_t a, b;
-        if (p.flow == S3_FLOW_POS) {
+        if (pos_flow) {
             a = p.link_src[rec];
             b = p.link_dst[rec];
         } else {
@@ -195,43 +218,35 @@ __global__ void __launch_bounds__(kExtractThreads) extract_bitmap_kernel(Extract
             nlev = l + 1;
             __syncthreads();
         }
-        // D = sum of global degrees (block reduction)
+        // D = sum of global degrees (block reduction); hop_end[l] = nodes of hop <= l
         for (int d = 16; d > 0; d >>= 1) my_deg += __shfl_down_sync(0xffffffffu, my_deg, d);
         if (lane == 0 && my_deg) atomicAdd(&s_sumdeg, my_deg);
         __syncthreads();
-        const int64_t D = (int64_t)s_sumdeg;
-
-        // ---------------- allocation 1: every integer array of the record ----------------
-        int sel_bound = 0;
-        if (p.strategy != S3_STRATEGY_NONE) {
-            const int d0 = slab_deg[0], d1 = slab_deg[1];
-            sel_bound = p.strategy == S3_STRATEGY_INTERSECTION ? min(d0, d1) : d0 + d1;
+        if (tid == 0) {
+            int acc = 0;
+            for (int l = 0; l <= S3_MAX_HOPS + 1; ++l) {
+                if (l <= nlev) acc += s_lvl_cnt[l];
+                s_hop_end[l] = acc;
+            }
         }
-        const int64_t words1 = ((int64_t)n + (n + 1) + n + D + sel_bound + 31) & ~int64_t(31);
-        if (tid == 0) s_base = (long long)atomicAdd(&p.counters[S3_CTR_CURSOR], (unsigned long long)words1);
         __syncthreads();
-        const int64_t base1 = p.slab_words + s_base;
-        bool overflow = base1 + words1 > p.arena_words;
-        int32_t* nodes = p.arena + base1;
-        int32_t* rowptr = nodes + n;       // [n+1] row starts (prefix of global degrees)
-        int32_t* rowlen = rowptr + n + 1;  // [n]   induced, masked degree
-        int32_t* lcol = rowlen + n;        // [D]   padded local column ids
-        int32_t* sel = lcol + D;
+        const int64_t D = (int64_t)s_sumdeg;
+        const int n_reach = s_hop_end[min(K, S3_MAX_HOPS + 1)];  // nodes that get any weight
+        const int nz = s_hop_end[min(K - 1, S3_MAX_HOPS + 1)];   // support of z_k, k <= K-1
+        const int n_store = p.store_all ? n : nz;                // rows kept in the padded CSR
+        const int n_rows = max(n_store, n_reach);                // rows whose start is needed
+        const bool cached = n_rows <= kRowCap;
 
-        int s = nseed, partner_local = -1;
-        if (!overflow) {
-            // node list + exclusive scan of global degrees, tile by tile
-            const bool cached = n <= kRowCap;
+        // ---------------- row starts: exclusive scan of global degrees, tile by tile ----------------
+        {
             int running = 0;
-            for (int base = 0; base < n; base += T) {
+            for (int base = 0; base < n_rows; base += T) {
                 const int j = base + tid;
-                const int d = j < n ? slab_deg[j] : 0;
+                const int d = j < n_rows ? slab_deg[j] : 0;
                 int tile_total;
                 const int ex = block_exclusive_scan(d, s_scan, &tile_total);
-                if (j < n) {
-                    nodes[j] = slab_nodes[j];
-                    rowptr[j] = running + ex;
-                    rowlen[j] = 0;
+                if (j < n_rows) {
+                    slab_rp[j] = running + ex;
                     if (cached) {
                         s_rowptr[j] = running + ex;
                         s_estart[j] = slab_estart[j];
@@ -241,31 +256,74 @@ __global__ void __launch_bounds__(kExtractThreads) extract_bitmap_kernel(Extract
                 __syncthreads();  // s_scan is reused by the next tile
             }
             if (tid == 0) {
-                rowptr[n] = running;
-                if (cached) s_rowptr[n] = running;
+                slab_rp[n_rows] = running;
+                if (cached) s_rowptr[n_rows] = running;
+            }
+            __syncthreads();
+        }
+        const int* rp = cached ? s_rowptr : slab_rp;
+        const uint32_t* es = cached ? s_estart : slab_estart;
+        const int Ds = rp[n_store];  // slots of the stored rows
+
+        // ---------------- allocation 1: every integer array of the record ----------------
+        int sel_bound = 0;
+        if (p.strategy != S3_STRATEGY_NONE) {
+            const int d0 = slab_deg[0], d1 = slab_deg[1];
+            sel_bound = p.strategy == S3_STRATEGY_INTERSECTION ? min(d0, d1) : d0 + d1;
+        }
+        const int64_t words1 = ((int64_t)n + (n_store + 1) + n_store + Ds + sel_bound + 31) & ~int64_t(31);
+        if (tid == 0) s_base = (long long)atomicAdd(&p.counters[S3_CTR_CURSOR], (unsigned long long)words1);
+        __syncthreads();
+        const int64_t base1 = p.slab_words + s_base;
+        bool overflow = base1 + words1 > p.arena_words;
+        int32_t* nodes = p.arena + base1;
+        int32_t* rowptr = nodes + n;             // [n_store+1] row starts (prefix of global degrees)
+        int32_t* rowlen = rowptr + n_store + 1;  // [n_store]   induced, masked degree
+        int32_t* lcol = rowlen + n_store;        // [Ds]        padded local column ids, -1 = hole
+        int32_t* sel = lcol + Ds;
+
+        int s = nseed, partner_local = -1;
+        int64_t base3 = 0;
+        if (!overflow) {
+            for (int j = tid; j < n; j += T) nodes[j] = slab_nodes[j];
+            for (int j = tid; j <= n_store; j += T) {
+                rowptr[j] = rp[j];
+                if (j < n_store) rowlen[j] = 0;
             }
             __syncthreads();
 
-            // ---------------- fill: one lane per adjacency slot of the subgraph ----------------
-            const int* rp = cached ? s_rowptr : rowptr;
-            const uint32_t* es = cached ? s_estart : slab_estart;
+            // ---------------- fill: one lane per adjacency slot of the stored rows ----------------
+            // Each warp streams a contiguous chunk of slots, 32 per step. The row of a step's first
+            // slot is carried from the previous step (one binary search per chunk); the other lanes
+            // find theirs from a 32-bit mask of the row starts inside the step's window (rows 2..
+            // own >= 1 slot, so at most 32 rows start in 32 slots).
             int my_m = 0;
-            const int Di = (int)D;
-            for (int slot0 = (tid >> 5) * 32; slot0 < Di; slot0 += T) {
-                const int slot = slot0 + lane;
-                const bool ok = slot < Di;
-                int lo = 0, hi = n;  // rp[lo] <= slot < rp[hi]; picks the last of equal starts (degree-0 rows)
+            const int chunk_slots = (((Ds + (T >> 5) - 1) / (T >> 5)) + 31) & ~31;
+            const int c_lo = (tid >> 5) * chunk_slots, c_hi = min(Ds, c_lo + chunk_slots);
+            int jb = 0;
+            if (c_lo < c_hi) {
+                int lo = 0, hi = n_store;  // rp[lo] <= c_lo < rp[hi]; picks the last of equal starts
                 while (hi - lo > 1) {
                     const int mid = (lo + hi) >> 1;
-                    if (rp[mid] <= slot) lo = mid; else hi = mid;
+                    if (rp[mid] <= c_lo) lo = mid; else hi = mid;
                 }
-                const int j = lo;
+                jb = lo;
+            }
+            for (int slot0 = c_lo; slot0 < c_hi; slot0 += 32) {
+                const int slot = slot0 + lane;
+                const bool ok = slot < c_hi;
+                const int r = jb + 1 + lane;
+                const int pos = (r <= n_store ? rp[r] : INT_MAX) - slot0;  // start of row r relative to the window
+                const unsigned heads = __reduce_or_sync(0xffffffffu, (pos >= 0 && pos < 32) ? (1u << pos) : 0u);
+                int j = jb + __popc(heads & (0xffffffffu >> (31 - lane)));
+                if (j + 1 < n_store && rp[j + 1] <= slot) ++j;  // a degree-0 seed (row 1) shares its start with row 2
+                jb = __shfl_sync(0xffffffffu, j, 31);
                 int lid = -1;
                 bool in = false;
                 if (ok) {
                     const int c = p.indices[(int64_t)es[j] + (slot - rp[j])];
                     in = test_bit(V, c);
-                    if (mask_target && ((j == 0 && c == s1) || (j == 1 && c == s0))) in = false;  // utils.py:79-80
+                    if (pos_flow && ((j == 0 && c == s1) || (j == 1 && c == s0))) in = false;  // utils.py:79-80
                     if (in) lid = local_id(c, s0, s1, nseed, Lb, pre, s_lvl_base, nlev, W);
                     lcol[slot] = lid;
                 }
@@ -277,22 +335,20 @@ __global__ void __launch_bounds__(kExtractThreads) extract_bitmap_kernel(Extract
             }
             for (int d = 16; d > 0; d >>= 1) my_m += __shfl_down_sync(0xffffffffu, my_m, d);
             if (lane == 0 && my_m) atomicAdd(&s_m, my_m);
-            if (p.flow == S3_FLOW_SOP && test_bit(V, s1)) partner_local = local_id(s1, s0, s1, nseed, Lb, pre, s_lvl_base, nlev, W);
+            if (!pos_flow && test_bit(V, s1)) partner_local = local_id(s1, s0, s1, nseed, Lb, pre, s_lvl_base, nlev, W);
             __syncthreads();
 
             // ---------------- row selection (PoS Plus): tuned_SIGN.py:228-238 ----------------
             // Neighbours of local 0 / 1 are hop-1 nodes, local ids [2, 2 + cnt1). Two flag bitmaps
-            // over that range (re-using V and the level-1 bitmap, both dead now) give the
-            // intersection or union in ascending local id.
+            // over that range (carved from the z scratch, or the dead row-start slab when huge)
+            // give the intersection or union in ascending local id.
             if (p.strategy != S3_STRATEGY_NONE) {
                 const int cnt1 = nlev > 0 ? s_lvl_cnt[1] : 0;
                 const int FW = (cnt1 + 31) >> 5;
-                uint32_t* F0 = V;
-                uint32_t* F1 = Lb;
-                for (int w = tid; w < FW; w += T) {
-                    F0[w] = 0u;
-                    F1[w] = 0u;
-                }
+                const bool fshared = 2 * FW <= 2 * kZCap;
+                uint32_t* F0 = fshared ? reinterpret_cast<uint32_t*>(&s_z[0][0]) : reinterpret_cast<uint32_t*>(slab_nodes);
+                uint32_t* F1 = F0 + FW;
+                for (int w = tid; w < 2 * FW; w += T) F0[w] = 0u;
                 __syncthreads();
                 for (int e = rowptr[0] + tid; e < rowptr[1]; e += T) {
                     const int c = lcol[e] - 2;  // holes are -1, seeds 0/1: both excluded
@@ -319,28 +375,154 @@ __global__ void __launch_bounds__(kExtractThreads) extract_bitmap_kernel(Extract
                     }
                 }
                 s = nseed + extra;
+                __syncthreads();
             }
-        }
 
-        // ---------------- allocation 2: float scratch of the record's work items ----------------
-        const int sc = sel_chunk(p.flow);
-        const int items = (s + sc - 1) / sc;
-        const int64_t words3 = ((int64_t)items * item_words(p.flow, p.sign_k, n) + 31) & ~int64_t(31);
-        int64_t base3 = 0;
-        if (!overflow) {
-            __syncthreads();
+            // ---------------- allocation 2: float scratch of the record's work items ----------------
+            const int items = (s + SC - 1) / SC;
+            const int64_t words3 = ((int64_t)items * item_words(p.flow, K, n) + 31) & ~int64_t(31);
             if (tid == 0) s_base = (long long)atomicAdd(&p.counters[S3_CTR_CURSOR], (unsigned long long)words3);
             __syncthreads();
             base3 = p.slab_words + s_base;
             overflow = base3 + words3 > p.arena_words;
         }
 
+        // ---------------- diffusion of work item 0 (selected rows = the seeds) ----------------
+        if (!overflow) {
+            float* item_f = reinterpret_cast<float*>(p.arena + base3);
+            float* lab = item_f;
+            float* wgt = item_f + NWP;
+            const bool z_shared = nz * SC <= kZCap;
+            float* zprev = z_shared ? s_z[0] : wgt + (int64_t)n * NWP;
+            float* znext = z_shared ? s_z[1] : wgt + (int64_t)n * NWP + (int64_t)n * SC;
+
+            // k = 0: one-hot rows of the seeds; z_0 = e_sel D^-1/2 on the support, z buffers zeroed
+            for (int j = tid; j < nz; j += T) {
+#pragma unroll
+                for (int c = 0; c < SC; ++c) {
+                    float zv = 0.0f;
+                    if (j == c) {
+                        const int deg = pos_flow ? rowlen[j] : slab_deg[j];  // tuned_SIGN.py:158 / sgrl_link_pred.py:165
+                        zv = deg > 0 ? 1.0f / sqrtf((float)deg) : 0.0f;     // inf -> 0 (tuned_SIGN.py:159-160)
+                    }
+                    zprev[j * SC + c] = zv;
+                    znext[j * SC + c] = 0.0f;
+                }
+            }
+            for (int i = tid; i < nseed * NWP; i += T) {
+                const int j = i / NWP, q = i - j * NWP;
+                wgt[i] = (q < SC && q == j) ? 1.0f : 0.0f;
+            }
+            __syncthreads();
+
+            for (int k = 1; k <= K; ++k) {
+                // stored rows reached by a k-step walk
+                const int nk = min(s_hop_end[min(k, S3_MAX_HOPS + 1)], n_store);
+                for (int jb0 = 0; jb0 < nk; jb0 += NG) {
+                    const int j = jb0 + grp;
+                    const bool valid = j < nk;
+                    int e0 = 0, e1 = 0;
+                    if (valid) {
+                        e0 = rp[j];
+                        e1 = rp[j + 1];
+                    }
+                    float t[SC];
+#pragma unroll
+                    for (int c = 0; c < SC; ++c) t[c] = 0.0f;
+                    for (int e = e0 + l8; e < e1; e += 8) {
+                        const int i = lcol[e];  // -1: hole; >= nz: z is an exact zero there
+                        if (i >= 0 && i < nz) {
+#pragma unroll
+                            for (int c = 0; c < SC; ++c) t[c] += zprev[i * SC + c];
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < SC; ++c) {
+                        t[c] += __shfl_xor_sync(0xffffffffu, t[c], 4);
+                        t[c] += __shfl_xor_sync(0xffffffffu, t[c], 2);
+                        t[c] += __shfl_xor_sync(0xffffffffu, t[c], 1);
+                    }
+                    if (valid && l8 == 0) {
+                        const int deg = pos_flow ? rowlen[j] : slab_deg[j];
+                        const float dis = deg > 0 ? 1.0f / sqrtf((float)deg) : 0.0f;
+#pragma unroll
+                        for (int c = 0; c < SC; ++c) {
+                            const float w = dis * t[c];
+                            wgt[(int64_t)j * NWP + k * SC + c] = w;
+                            if (j < nz) znext[j * SC + c] = dis * w;
+                        }
+                    }
+                }
+                if (k == K) {
+                    // streamed rows: hop-K nodes, read once, never stored
+                    const int inner_levels = min(K - 1, nlev);
+                    for (int jb0 = n_store; jb0 < n_reach; jb0 += NG) {
+                        const int j = jb0 + grp;
+                        const bool valid = j < n_reach;
+                        int64_t e0 = 0;
+                        int len = 0;
+                        if (valid) {
+                            e0 = es[j];
+                            len = rp[j + 1] - rp[j];
+                        }
+                        float t[SC];
+#pragma unroll
+                        for (int c = 0; c < SC; ++c) t[c] = 0.0f;
+                        int cntv = 0;
+                        for (int idx = l8; idx < len; idx += 8) {
+                            const int c_ = p.indices[e0 + idx];
+                            if (test_bit(V, c_)) {
+                                ++cntv;
+                                const int i = local_id(c_, s0, s1, nseed, Lb, pre, s_lvl_base, inner_levels, W);
+                                if (i >= 0) {  // hop <= K-1: the only nodes where z_{K-1} lives
+#pragma unroll
+                                    for (int c = 0; c < SC; ++c) t[c] += zprev[i * SC + c];
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int c = 0; c < SC; ++c) {
+                            t[c] += __shfl_xor_sync(0xffffffffu, t[c], 4);
+                            t[c] += __shfl_xor_sync(0xffffffffu, t[c], 2);
+                            t[c] += __shfl_xor_sync(0xffffffffu, t[c], 1);
+                        }
+                        cntv += __shfl_xor_sync(0xffffffffu, cntv, 4);
+                        cntv += __shfl_xor_sync(0xffffffffu, cntv, 2);
+                        cntv += __shfl_xor_sync(0xffffffffu, cntv, 1);
+                        if (valid && l8 == 0) {
+                            const int deg = pos_flow ? cntv : len;
+                            const float dis = deg > 0 ? 1.0f / sqrtf((float)deg) : 0.0f;
+#pragma unroll
+                            for (int c = 0; c < SC; ++c) wgt[(int64_t)j * NWP + K * SC + c] = dis * t[c];
+                        }
+                    }
+                }
+                __syncthreads();
+                float* tmp = zprev;
+                zprev = znext;
+                znext = tmp;
+            }
+
+            // label / self-return column of every operator, then (SoP) drop the partner's weight
+            if (pos_flow) {
+                // x_k[sel, 0] = sum_j w_k[j] * label_j, label = 1 on local 0 and 1 (tuned_SIGN.py:177)
+                for (int q = tid; q < NWP; q += T) lab[q] = q < NW ? wgt[q] + wgt[NWP + q] : 0.0f;
+            } else {
+                // x_k[., 0] = A^k[u,u] (tuned_SIGN.py:106-113); x[., 0] = 1 (tuned_SIGN.py:119-124)
+                for (int q = tid; q < NWP; q += T) lab[q] = q < NW ? wgt[q] : 0.0f;
+                __syncthreads();
+                if (partner_local >= 0 && partner_local < n_reach)  // r_u[v] = 0 (tuned_SIGN.py:73-76)
+                    for (int q = SC + tid; q < NW; q += T) wgt[(int64_t)partner_local * NWP + q] = 0.0f;
+            }
+        }
+
+        __syncthreads();
         if (tid == 0) {
             off[S3_OFF_NODES] = base1;
             off[S3_OFF_ROWPTR] = base1 + n;
-            off[S3_OFF_ROWLEN] = base1 + n + n + 1;
-            off[S3_OFF_LCOL] = base1 + 3 * (int64_t)n + 1;
-            off[S3_OFF_SEL] = base1 + 3 * (int64_t)n + 1 + D;
+            off[S3_OFF_ROWLEN] = base1 + n + n_store + 1;
+            off[S3_OFF_LCOL] = base1 + n + 2 * (int64_t)n_store + 1;
+            off[S3_OFF_SEL] = base1 + n + 2 * (int64_t)n_store + 1 + Ds;
             off[S3_OFF_F32] = base3;
             cnt[S3_CNT_N] = n;
             cnt[S3_CNT_M] = s_m;
@@ -348,12 +530,51 @@ __global__ void __launch_bounds__(kExtractThreads) extract_bitmap_kernel(Extract
             cnt[S3_CNT_STATUS] = overflow ? S3_REC_ARENA_OVERFLOW : S3_REC_OK;
             cnt[S3_CNT_PARTNER] = partner_local;
             for (int l = 0; l <= S3_MAX_HOPS; ++l) cnt[S3_CNT_HOP0 + l] = (l <= nlev) ? s_lvl_cnt[l] : 0;
+            cnt[S3_CNT_NSTORE] = n_store;
+            cnt[S3_CNT_NSTORE + 1] = 0;
             if (overflow) atomicAdd(&p.counters[S3_CTR_ERRORS], 1ull);
             atomicMax(&p.counters[S3_CTR_MAX_N], (unsigned long long)n);
             atomicAdd(&p.counters[S3_CTR_SUM_N], (unsigned long long)n);
             atomicAdd(&p.counters[S3_CTR_SUM_D], (unsigned long long)D);
         }
     }
+}
+
+template <int SC>
+cudaError_t launch_front(ExtractParams& p, const s3_graph& g, const s3_batch& b, cudaStream_t st, int* rc_out) {
+    const size_t smem = (size_t)s3_extract_smem_bytes(g.num_nodes, p.radius);
+    static size_t configured = 0;
+    if (smem > configured) {  // static (37 KB) + dynamic shared memory may exceed the 48 KB default limit
+        cudaError_t e = cudaFuncSetAttribute(front_kernel<SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    // device queries are slow host calls: cache them per (device, smem) pair
+    static int c_dev = -1, c_sms = 0, c_occ = 0;
+    static size_t c_smem = 0;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev != c_dev || smem != c_smem) {
+        e = cudaDeviceGetAttribute(&c_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c_occ, front_kernel<SC>, kExtractThreads, smem);
+        if (e != cudaSuccess) return e;
+        c_dev = dev;
+        c_smem = smem;
+    }
+    p.slab_stride = (4 * g.num_nodes + 1 + 31) & ~int64_t(31);
+    int64_t grid = (int64_t)c_sms * (c_occ > 0 ? c_occ : 1);
+    if (grid > p.num_records) grid = p.num_records;
+    const int64_t fit = (b.arena_words / 2) / p.slab_stride;  // slabs may take at most half of the arena
+    if (grid > fit) grid = fit;
+    if (grid < 1) {
+        *rc_out = S3_ERR_WORKSPACE;
+        return cudaSuccess;
+    }
+    p.slab_words = grid * p.slab_stride;
+    front_kernel<SC><<<(unsigned)grid, kExtractThreads, smem, st>>>(p);
+    return cudaGetLastError();
 }
 
 }  // namespace
@@ -371,6 +592,7 @@ cudaError_t launch_extract_bitmap(const s3_graph& g, const s3_batch& b, cudaStre
     p.strategy = b.flow == S3_FLOW_POS ? b.strategy : S3_STRATEGY_NONE;
     p.radius = b.flow == S3_FLOW_POS ? b.num_hops : b.sign_k;
     p.sign_k = b.sign_k;
+    p.store_all = (p.strategy != S3_STRATEGY_NONE) || (b.flags & S3_BATCH_STORE_ALL_ROWS);
     p.W = (int)((g.num_nodes + 31) / 32);
     p.arena = b.arena;
     p.arena_words = b.arena_words;
@@ -378,40 +600,7 @@ cudaError_t launch_extract_bitmap(const s3_graph& g, const s3_batch& b, cudaStre
     p.cnt = b.cnt;
     p.counters = reinterpret_cast<unsigned long long*>(b.counters);
     if (p.num_records == 0) return cudaSuccess;
-    const size_t smem = (size_t)s3_extract_smem_bytes(g.num_nodes, p.radius);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(extract_bitmap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
-    // device queries are slow host calls: cache them per (device, smem) pair
-    static int c_dev = -1, c_sms = 0, c_occ = 0;
-    static size_t c_smem = 0;
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    if (dev != c_dev || smem != c_smem) {
-        e = cudaDeviceGetAttribute(&c_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c_occ, extract_bitmap_kernel, kExtractThreads, smem);
-        if (e != cudaSuccess) return e;
-        c_dev = dev;
-        c_smem = smem;
-    }
-    const int sms = c_sms, occ = c_occ;
-    p.slab_stride = (3 * g.num_nodes + 31) & ~int64_t(31);
-    int64_t grid = (int64_t)sms * (occ > 0 ? occ : 1);
-    if (grid > p.num_records) grid = p.num_records;
-    const int64_t fit = (b.arena_words / 2) / p.slab_stride;  // slabs may take at most half of the arena
-    if (grid > fit) grid = fit;
-    if (grid < 1) {
-        *rc_out = S3_ERR_WORKSPACE;
-        return cudaSuccess;
-    }
-    p.slab_words = grid * p.slab_stride;
-    extract_bitmap_kernel<<<(unsigned)grid, kExtractThreads, smem, st>>>(p);
-    return cudaGetLastError();
+    return b.flow == S3_FLOW_POS ? launch_front<2>(p, g, b, st, rc_out) : launch_front<1>(p, g, b, st, rc_out);
 }
 
 }  // namespace s3

@@ -63,7 +63,7 @@ __global__ void dump_edges_kernel(const int32_t* __restrict__ arena, const int64
                                   int32_t* __restrict__ edges_out) {
     const int64_t rec = blockIdx.x;
     if (cnt[rec * S3_NCNT + S3_CNT_STATUS] != S3_REC_OK) return;
-    const int n = cnt[rec * S3_NCNT + S3_CNT_N];
+    const int n = cnt[rec * S3_NCNT + S3_CNT_NSTORE];  // == cnt[S3_CNT_N] with S3_BATCH_STORE_ALL_ROWS
     const int32_t* nodes = arena + off[rec * S3_NOFF + S3_OFF_NODES];
     const int32_t* rowptr = arena + off[rec * S3_NOFF + S3_OFF_ROWPTR];
     const int32_t* rowlen = arena + off[rec * S3_NOFF + S3_OFF_ROWLEN];

@@ -67,13 +67,24 @@ class DeviceGraph:
         self._c = L.Graph(_ptr(self.indptr), _ptr(self.indices), _ptr(self.x), self.num_nodes, self.num_feat,
                           self.ldx, self.nnz)
         self._arena = None
+        self._arena2 = None
+        self._streams = None
 
-    # scratch arena (int32 words), grown on demand and kept across calls
-    def arena(self, words):
-        if self._arena is None or self._arena.numel() < words:
-            self._arena = None
-            self._arena = torch.empty(int(words), dtype=torch.int32, device=self.device)
-        return self._arena
+    # scratch arenas (int32 words), grown on demand and kept across calls; the second one is
+    # only allocated by the overlapped (two-stream, double-buffered) schedule
+    def arena(self, words, slot=0):
+        name = '_arena' if slot == 0 else '_arena2'
+        cur = getattr(self, name)
+        if cur is None or cur.numel() < words:
+            setattr(self, name, None)
+            cur = torch.empty(int(words), dtype=torch.int32, device=self.device)
+            setattr(self, name, cur)
+        return cur
+
+    def streams(self):
+        if self._streams is None:
+            self._streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        return self._streams
 
 
 class PrecomputeResult:
@@ -90,13 +101,15 @@ def _records_per_link(flow):
 
 
 def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_records=8192,
-               out=None, return_graphs=False, arena_words=None, stream=None, profile=None):
+               out=None, return_graphs=False, arena_words=None, stream=None, profile=None, overlap=False):
     """Run the hot path for `links` ([2, L] int64, host or device) on `graph`.
 
     Returns PrecomputeResult with device tensors.  `out`, if given, is a list of K+1
     preallocated [>=R, F+1] float32 device tensors (fixed-row flows only).  `profile`, if a
     list, receives (stage, batch, start_event, end_event) for every kernel launch group so the
-    caller can time each kernel on the launching stream with CUDA events.
+    caller can time each kernel on the launching stream with CUDA events.  `overlap` (fixed-row
+    flows) runs extract+diffuse of batch i+1 on one stream while gather of batch i runs on
+    another, with two arenas: the latency-bound front half hides under the bandwidth-bound gather.
     Raises ValueError for invalid links (out of range, src == dst), NotImplementedError for an
     unknown strategy (as reference tuned_SIGN.py:235)."""
     lib = L.lib()
@@ -146,18 +159,57 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
 
         def make_batch(b0, b1, arena, off, cnt, ctr, row_ptr=None, item_ptr=None, item_rec=None):
             return L.Batch(_ptr(links[0, b0:b1]), _ptr(links[1, b0:b1]), b1 - b0, cflow, cstrat, int(num_hops), K,
-                           _ptr(arena), arena.numel(), _ptr(off), _ptr(cnt), _ptr(ctr),
+                           L.BATCH_STORE_ALL_ROWS if return_graphs else 0, 0, _ptr(arena), arena.numel(), _ptr(off), _ptr(cnt), _ptr(ctr),
                            _ptr(row_ptr), _ptr(item_ptr), _ptr(item_rec))
 
-        def timed(stage, bi, fn):
+        def timed(stage, bi, fn, on=None):
             if profile is None:
                 return fn()
+            on = st if on is None else on
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(st)
+            e0.record(on)
             r = fn()
-            e1.record(st)
+            e1.record(on)
             profile.append((stage, bi, e0, e1))
             return r
+
+        def run_fixed_overlapped(todo, words):
+            """Two streams, two arenas: front (extract, diffuse) of batch i+1 overlaps back (gather)
+            of batch i.  Returns [(bi, cnt)] for validation after the caller's sync."""
+            sF, sB = graph.streams()
+            arenas = (graph.arena(words, 0), graph.arena(words, 1))
+            nrecs = [(min(Lk, (bi + 1) * batch_links) - bi * batch_links) * rpl for bi in todo]
+            off_all = torch.empty((sum(nrecs), L.NOFF), dtype=torch.int64, device=dev)
+            cnt_all = torch.empty((sum(nrecs), L.NCNT), dtype=torch.int32, device=dev)
+            counters[torch.as_tensor(todo, device=dev)] = 0
+            start = torch.cuda.Event()
+            start.record(st)
+            sF.wait_event(start)
+            sB.wait_event(start)
+            pF, pB = C.c_void_p(sF.cuda_stream), C.c_void_p(sB.cuda_stream)
+            metas, back_done, r0 = [], [], 0
+            for idx, bi in enumerate(todo):
+                b0, b1 = bi * batch_links, min(Lk, (bi + 1) * batch_links)
+                nrec = nrecs[idx]
+                off, cnt = off_all[r0:r0 + nrec], cnt_all[r0:r0 + nrec]
+                r0 += nrec
+                batch = make_batch(b0, b1, arenas[idx % 2], off, cnt, counters[bi])
+                if idx >= 2:
+                    sF.wait_event(back_done[idx - 2])          # this arena is free again
+                timed('extract', bi, lambda: L.check(lib.s3_extract(C.byref(graph._c), C.byref(batch), pF), 's3_extract'), sF)
+                fd = torch.cuda.Event()
+                fd.record(sF)
+                sB.wait_event(fd)
+                timed('gather', bi, lambda: L.check(
+                    lib.s3_gather(C.byref(graph._c), C.byref(batch), nrec, out_ptrs, F1, b0 * rpl * nseed, pB), 's3_gather'), sB)
+                bd = torch.cuda.Event()
+                bd.record(sB)
+                back_done.append(bd)
+                stats['launches'] += 2
+                metas.append((bi, cnt))
+            if back_done:
+                st.wait_event(back_done[-1])
+            return metas, (off_all, cnt_all)
 
         def run_batch(bi, arena):
             """Enqueue one batch; returns (cnt, off, pending) where pending finishes Plus flows."""
@@ -170,10 +222,9 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
             if fixed_rows:
                 batch = make_batch(b0, b1, arena, off, cnt, ctr)
                 timed('extract', bi, lambda: L.check(lib.s3_extract(C.byref(graph._c), C.byref(batch), st_ptr), 's3_extract'))
-                timed('diffuse', bi, lambda: L.check(lib.s3_diffuse(C.byref(graph._c), C.byref(batch), nrec, st_ptr), 's3_diffuse'))
                 timed('gather', bi, lambda: L.check(
                     lib.s3_gather(C.byref(graph._c), C.byref(batch), nrec, out_ptrs, F1, b0 * rpl * nseed, st_ptr), 's3_gather'))
-                stats['launches'] += 3
+                stats['launches'] += 2
                 return cnt, off, None
             row_ptr = torch.empty(nrec + 1, dtype=torch.int64, device=dev)
             item_ptr = torch.empty(nrec + 1, dtype=torch.int64, device=dev)
@@ -214,6 +265,7 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
             cn, of, ar = cnt.cpu().numpy(), off.cpu().numpy(), arena.cpu().numpy()
             for r in range(cn.shape[0]):
                 n, m, s = int(cn[r, L.CNT_N]), int(cn[r, L.CNT_M]), int(cn[r, L.CNT_S])
+                assert int(cn[r, L.CNT_NSTORE]) == n
                 nodes = ar[of[r, L.OFF_NODES]:of[r, L.OFF_NODES] + n].astype(np.int64)
                 rstart = ar[of[r, L.OFF_ROWPTR]:of[r, L.OFF_ROWPTR] + n + 1].astype(np.int64)
                 rlen = ar[of[r, L.OFF_ROWLEN]:of[r, L.OFF_ROWLEN] + n].astype(np.int64)
@@ -242,18 +294,22 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
             # Enqueue every batch without a host sync, validate at the end; a batch whose arena
             # overflowed is re-run (its output rows are simply rewritten) with a larger arena.
             todo = list(range(nb))
+            use_overlap = bool(overlap) and not return_graphs and nb > 1
             while todo:
-                arena = graph.arena(words)
                 metas = []
                 t_enq = time.perf_counter()
-                for bi in todo:
-                    cnt, off, _ = run_batch(bi, arena)
-                    if return_graphs:   # the arena is recycled by the next batch: dump now
-                        st.synchronize()
-                        if check_and_account(bi, cnt):
-                            dump(bi, cnt, off, arena)
-                            continue
-                    metas.append((bi, cnt))
+                if use_overlap:
+                    metas, keep_alive = run_fixed_overlapped(todo, words)
+                else:
+                    arena = graph.arena(words)
+                    for bi in todo:
+                        cnt, off, _ = run_batch(bi, arena)
+                        if return_graphs:   # the arena is recycled by the next batch: dump now
+                            st.synchronize()
+                            if check_and_account(bi, cnt):
+                                dump(bi, cnt, off, arena)
+                                continue
+                        metas.append((bi, cnt))
                 stats['host_enqueue_ms'] = 1000 * (time.perf_counter() - t_enq)
                 st.synchronize()
                 hc = counters.cpu()       # one D2H for every batch's counters

@@ -183,7 +183,8 @@ def test_dump_edges_entry_point():
     off = torch.empty((nrec, L.NOFF), dtype=torch.int64, device=dev)
     cnt = torch.empty((nrec, L.NCNT), dtype=torch.int32, device=dev)
     ctr = torch.zeros(L.NCTR, dtype=torch.int64, device=dev)
-    b = L.Batch(links[0].data_ptr(), links[1].data_ptr(), nrec, L.FLOW_POS, 0, 2, 3, arena.data_ptr(), arena.numel(),
+    b = L.Batch(links[0].data_ptr(), links[1].data_ptr(), nrec, L.FLOW_POS, 0, 2, 3, L.BATCH_STORE_ALL_ROWS, 0,
+                arena.data_ptr(), arena.numel(),
                 off.data_ptr(), cnt.data_ptr(), ctr.data_ptr(), None, None, None)
     lib = L.lib()
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
