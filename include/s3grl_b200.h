@@ -93,6 +93,7 @@ extern "C" {
 #define S3_CNT_PARTNER 4  /* SoP: local id of the other endpoint in the ball, or -1 */
 #define S3_CNT_HOP0 5     /* S3_CNT_HOP0 + l = number of nodes at hop l, l = 0..S3_MAX_HOPS */
 #define S3_CNT_NSTORE 14  /* rows kept in the padded CSR: hops <= K-1, or all n with S3_BATCH_STORE_ALL_ROWS */
+#define S3_CNT_CLASSPOS 15 /* arrival index of the record inside its size class           */
 #define S3_NCNT 16
 
 /* int64 counters[S3_NCTR]; the caller zeroes them before s3_extract */
@@ -104,7 +105,8 @@ extern "C" {
 #define S3_CTR_SUM_N 5     /* sum of n  (roofline accounting: 4*F*sum_n feature bytes)    */
 #define S3_CTR_SUM_D 6     /* sum over subgraph nodes of their global degree (4*D bytes)  */
 #define S3_CTR_WORK 7      /* work-queue head of the persistent extraction CTAs           */
-#define S3_NCTR 8
+#define S3_CTR_CLASS0 16   /* + c: records whose n has floor(log2 n) == c (size classes)  */
+#define S3_NCTR 48
 
 /* Device-resident graph: CSR of the training graph (both directions stored, columns
  * ascending and unique per row — what scipy's csr_matrix gives the reference at
@@ -146,6 +148,10 @@ typedef struct s3_batch {
     int64_t* row_ptr;        /* [num_records + 1] output-row offset of each record          */
     int64_t* item_ptr;       /* [num_records + 1] first work item of each record            */
     int32_t* item_rec;       /* [total items] record of each work item                      */
+    /* Optional [num_records]: s3_extract fills it with the records in descending size class
+     * (largest subgraphs first) and s3_gather schedules its CTAs in that order, which trims the
+     * tail of the launch. Results do not depend on it. Used only when item_rec is NULL. */
+    int32_t* order;
 } s3_batch;
 
 int s3_version(void);

@@ -15,7 +15,7 @@ REC_OK, REC_ARENA_OVERFLOW, REC_BAD_LINK = 0, 1, 2
 OFF_NODES, OFF_ROWPTR, OFF_ROWLEN, OFF_LCOL, OFF_SEL, OFF_F32, NOFF = 0, 1, 2, 3, 4, 5, 6
 CNT_N, CNT_M, CNT_S, CNT_STATUS, CNT_PARTNER, CNT_HOP0, CNT_NSTORE, NCNT = 0, 1, 2, 3, 4, 5, 14, 16
 BATCH_STORE_ALL_ROWS = 1
-CTR_CURSOR, CTR_ERRORS, CTR_ROWS, CTR_ITEMS, CTR_MAX_N, CTR_SUM_N, CTR_SUM_D, CTR_WORK, NCTR = 0, 1, 2, 3, 4, 5, 6, 7, 8
+CTR_CURSOR, CTR_ERRORS, CTR_ROWS, CTR_ITEMS, CTR_MAX_N, CTR_SUM_N, CTR_SUM_D, CTR_WORK, NCTR = 0, 1, 2, 3, 4, 5, 6, 7, 48
 
 EXPORTS = ['s3_version', 's3_error_string', 's3_last_cuda_error', 's3_num_records', 's3_extract_smem_bytes',
            's3_min_arena_words',
@@ -33,7 +33,7 @@ class Batch(C.Structure):
                 ('flags', C.c_int32), ('reserved', C.c_int32),
                 ('arena', C.c_void_p), ('arena_words', C.c_int64),
                 ('off', C.c_void_p), ('cnt', C.c_void_p), ('counters', C.c_void_p),
-                ('row_ptr', C.c_void_p), ('item_ptr', C.c_void_p), ('item_rec', C.c_void_p)]
+                ('row_ptr', C.c_void_p), ('item_ptr', C.c_void_p), ('item_rec', C.c_void_p), ('order', C.c_void_p)]
 
 
 class S3Error(RuntimeError):

@@ -531,13 +531,35 @@ __global__ void __launch_bounds__(kExtractThreads, 4) front_kernel(ExtractParams
             cnt[S3_CNT_PARTNER] = partner_local;
             for (int l = 0; l <= S3_MAX_HOPS; ++l) cnt[S3_CNT_HOP0 + l] = (l <= nlev) ? s_lvl_cnt[l] : 0;
             cnt[S3_CNT_NSTORE] = n_store;
-            cnt[S3_CNT_NSTORE + 1] = 0;
+            // size class for the largest-first schedule of kernel 3
+            cnt[S3_CNT_CLASSPOS] = (int)atomicAdd(&p.counters[S3_CTR_CLASS0 + (31 - __clz(n))], 1ull);
             if (overflow) atomicAdd(&p.counters[S3_CTR_ERRORS], 1ull);
             atomicMax(&p.counters[S3_CTR_MAX_N], (unsigned long long)n);
             atomicAdd(&p.counters[S3_CTR_SUM_N], (unsigned long long)n);
             atomicAdd(&p.counters[S3_CTR_SUM_D], (unsigned long long)D);
         }
     }
+}
+
+// order[] = records sorted by descending size class (counting sort over the class counters the
+// front kernel filled; arrival order inside a class is scheduling dependent, results are not).
+__global__ void order_kernel(const int32_t* __restrict__ cnt, const unsigned long long* __restrict__ counters,
+                             int64_t num_records, int32_t* __restrict__ order) {
+    __shared__ int s_off[32];
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int c = 31; c >= 0; --c) {
+            s_off[c] = acc;
+            acc += (int)counters[S3_CTR_CLASS0 + c];
+        }
+    }
+    __syncthreads();
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= num_records) return;
+    const int32_t* c = cnt + r * S3_NCNT;
+    if (c[S3_CNT_STATUS] == S3_REC_BAD_LINK) return;  // not classed; its slot stays -1
+    const int n = c[S3_CNT_N];
+    order[s_off[31 - __clz(n)] + c[S3_CNT_CLASSPOS]] = (int32_t)r;
 }
 
 template <int SC>
@@ -574,6 +596,11 @@ cudaError_t launch_front(ExtractParams& p, const s3_graph& g, const s3_batch& b,
     }
     p.slab_words = grid * p.slab_stride;
     front_kernel<SC><<<(unsigned)grid, kExtractThreads, smem, st>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess || !b.order) return e;
+    e = cudaMemsetAsync(b.order, 0xff, (size_t)p.num_records * 4, st);  // -1: skipped by kernel 3
+    if (e != cudaSuccess) return e;
+    order_kernel<<<(unsigned)((p.num_records + 255) / 256), 256, 0, st>>>(p.cnt, p.counters, p.num_records, b.order);
     return cudaGetLastError();
 }
 

@@ -39,6 +39,7 @@ struct GatherParams {
     const int64_t* __restrict__ row_ptr;   // may be null: row = rec * num_seeds
     const int64_t* __restrict__ item_ptr;  // may be null
     const int32_t* __restrict__ item_rec;  // may be null
+    const int32_t* __restrict__ order;     // may be null: largest-first schedule (fixed-row flows)
     int flow, sign_k, tpr;                 // tpr = threads per feature row (32/64/128)
     OutPtrs out;
     int64_t ldo, row_base;
@@ -144,7 +145,8 @@ __global__ void __launch_bounds__(kGatherThreads) gather_kernel(GatherParams p) 
     int* s_gid = reinterpret_cast<int*>(s_w + kTile * NWP);  // [kTile]
 
     const int tid = threadIdx.x;
-    const int64_t item = blockIdx.x;
+    const int64_t item = p.order ? (int64_t)p.order[blockIdx.x] : (int64_t)blockIdx.x;
+    if (item < 0) return;  // slot of an invalid record
     const int64_t rec = p.item_rec ? p.item_rec[item] : item;
     const int32_t* cnt = p.cnt + rec * S3_NCNT;
     if (cnt[S3_CNT_STATUS] != S3_REC_OK) return;
@@ -292,6 +294,7 @@ cudaError_t launch_gather(const s3_graph& g, const s3_batch& b, int64_t num_item
     p.row_ptr = b.row_ptr;
     p.item_ptr = b.item_rec ? b.item_ptr : nullptr;
     p.item_rec = b.item_rec;
+    p.order = b.item_rec ? nullptr : b.order;
     p.flow = b.flow;
     p.sign_k = b.sign_k;
     p.out = out;

@@ -94,14 +94,22 @@ class PrecomputeResult:
 
     def __init__(self, xs, row_ptr, stats, graphs=None):
         self.xs, self.row_ptr, self.stats, self.graphs = xs, row_ptr, stats, graphs
+        self._finalize = None
+
+    def finalize(self):
+        """Complete a deferred call: sync, validate, re-run overflowed batches. Idempotent."""
+        if self._finalize is not None:
+            fn, self._finalize = self._finalize, None
+            fn()
+        return self
 
 
 def _records_per_link(flow):
     return 2 if flow == L.FLOW_SOP else 1
 
 
-def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_records=8192,
-               out=None, return_graphs=False, arena_words=None, stream=None, profile=None, overlap=False):
+def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_records=32768,
+               out=None, return_graphs=False, arena_words=None, stream=None, profile=None, overlap=False, defer=False):
     """Run the hot path for `links` ([2, L] int64, host or device) on `graph`.
 
     Returns PrecomputeResult with device tensors.  `out`, if given, is a list of K+1
@@ -110,6 +118,9 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
     caller can time each kernel on the launching stream with CUDA events.  `overlap` (fixed-row
     flows) runs extract+diffuse of batch i+1 on one stream while gather of batch i runs on
     another, with two arenas: the latency-bound front half hides under the bandwidth-bound gather.
+    `defer` (fixed-row flows) returns right after enqueueing; the caller must call
+    `result.finalize()` (stream sync + validation + re-run of overflowed batches) before using
+    the outputs.  It lets several calls be queued back to back without a host round trip.
     Raises ValueError for invalid links (out of range, src == dst), NotImplementedError for an
     unknown strategy (as reference tuned_SIGN.py:235)."""
     lib = L.lib()
@@ -150,17 +161,17 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
             words = int(arena_words)
         else:   # ~128 KiB of scratch per record to start with (PubMed h=3 averages ~100 KiB), grown on overflow
             free, _ = torch.cuda.mem_get_info(dev)
-            words = max(1 << 22, min(int(batch_records) * 32768, free // 16))
+            words = max(1 << 22, min(min(int(batch_records), Lk * rpl) * 32768, free // 16))
             if graph._arena is not None:
                 words = max(words, graph._arena.numel())
         words = max(words, 4 * int(lib.s3_min_arena_words(graph.num_nodes)))
         stats = dict(records=Lk * rpl, links=Lk, sum_n=0, sum_d=0, max_n=0, rows=0, retries=0, batches=nb, launches=0)
         pieces, row_counts, graphs = [], [], ([] if return_graphs else None)
 
-        def make_batch(b0, b1, arena, off, cnt, ctr, row_ptr=None, item_ptr=None, item_rec=None):
+        def make_batch(b0, b1, arena, off, cnt, ctr, row_ptr=None, item_ptr=None, item_rec=None, order=None):
             return L.Batch(_ptr(links[0, b0:b1]), _ptr(links[1, b0:b1]), b1 - b0, cflow, cstrat, int(num_hops), K,
                            L.BATCH_STORE_ALL_ROWS if return_graphs else 0, 0, _ptr(arena), arena.numel(), _ptr(off), _ptr(cnt), _ptr(ctr),
-                           _ptr(row_ptr), _ptr(item_ptr), _ptr(item_rec))
+                           _ptr(row_ptr), _ptr(item_ptr), _ptr(item_rec), _ptr(order))
 
         def timed(stage, bi, fn, on=None):
             if profile is None:
@@ -181,6 +192,7 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
             nrecs = [(min(Lk, (bi + 1) * batch_links) - bi * batch_links) * rpl for bi in todo]
             off_all = torch.empty((sum(nrecs), L.NOFF), dtype=torch.int64, device=dev)
             cnt_all = torch.empty((sum(nrecs), L.NCNT), dtype=torch.int32, device=dev)
+            order_all = torch.empty(sum(nrecs), dtype=torch.int32, device=dev)
             counters[torch.as_tensor(todo, device=dev)] = 0
             start = torch.cuda.Event()
             start.record(st)
@@ -193,7 +205,8 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
                 nrec = nrecs[idx]
                 off, cnt = off_all[r0:r0 + nrec], cnt_all[r0:r0 + nrec]
                 r0 += nrec
-                batch = make_batch(b0, b1, arenas[idx % 2], off, cnt, counters[bi])
+                order = order_all[r0 - nrec:r0]
+                batch = make_batch(b0, b1, arenas[idx % 2], off, cnt, counters[bi], order=order)
                 if idx >= 2:
                     sF.wait_event(back_done[idx - 2])          # this arena is free again
                 timed('extract', bi, lambda: L.check(lib.s3_extract(C.byref(graph._c), C.byref(batch), pF), 's3_extract'), sF)
@@ -209,7 +222,7 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
                 metas.append((bi, cnt))
             if back_done:
                 st.wait_event(back_done[-1])
-            return metas, (off_all, cnt_all)
+            return metas, (off_all, cnt_all, order_all)
 
         def run_batch(bi, arena):
             """Enqueue one batch; returns (cnt, off, pending) where pending finishes Plus flows."""
@@ -220,7 +233,8 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
             ctr = counters[bi]
             ctr.zero_()
             if fixed_rows:
-                batch = make_batch(b0, b1, arena, off, cnt, ctr)
+                order = torch.empty(nrec, dtype=torch.int32, device=dev)
+                batch = make_batch(b0, b1, arena, off, cnt, ctr, order=order)
                 timed('extract', bi, lambda: L.check(lib.s3_extract(C.byref(graph._c), C.byref(batch), st_ptr), 's3_extract'))
                 timed('gather', bi, lambda: L.check(
                     lib.s3_gather(C.byref(graph._c), C.byref(batch), nrec, out_ptrs, F1, b0 * rpl * nseed, st_ptr), 's3_gather'))
@@ -293,14 +307,14 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
         if fixed_rows:
             # Enqueue every batch without a host sync, validate at the end; a batch whose arena
             # overflowed is re-run (its output rows are simply rewritten) with a larger arena.
-            todo = list(range(nb))
             use_overlap = bool(overlap) and not return_graphs and nb > 1
-            while todo:
-                metas = []
+
+            def enqueue(todo):
                 t_enq = time.perf_counter()
                 if use_overlap:
-                    metas, keep_alive = run_fixed_overlapped(todo, words)
+                    metas, keep = run_fixed_overlapped(todo, words)
                 else:
+                    metas, keep = [], None
                     arena = graph.arena(words)
                     for bi in todo:
                         cnt, off, _ = run_batch(bi, arena)
@@ -311,13 +325,28 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
                                 continue
                         metas.append((bi, cnt))
                 stats['host_enqueue_ms'] = 1000 * (time.perf_counter() - t_enq)
-                st.synchronize()
+                return metas, keep
+
+            def settle(metas):
+                """After a stream sync: account finished batches, return the ones to re-run."""
                 hc = counters.cpu()       # one D2H for every batch's counters
-                todo = [bi for bi, cnt in metas if not (False if return_graphs else check_and_account(bi, cnt, hc))]
-                if todo:
-                    if return_graphs and graphs:
-                        raise RuntimeError("arena overflow while dumping graphs: pass a larger arena_words")
-                    grow()
+                return [bi for bi, cnt in metas if not (False if return_graphs else check_and_account(bi, cnt, hc))]
+
+            def finalize(metas):
+                with torch.cuda.device(dev), torch.cuda.stream(st):
+                    st.synchronize()
+                    todo = settle(metas)
+                    while todo:
+                        if return_graphs and graphs:
+                            raise RuntimeError("arena overflow while dumping graphs: pass a larger arena_words")
+                        grow()
+                        metas, _keep = enqueue(todo)
+                        st.synchronize()
+                        todo = settle(metas)
+
+            metas0, keep0 = enqueue(list(range(nb)))
+            if not defer:
+                finalize(metas0)
         else:
             # Row counts are data dependent: one host sync per batch (inside run_batch).
             for bi in range(nb):
@@ -342,7 +371,11 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
             row_ptr = torch.zeros(Lk + 1, dtype=torch.int64, device=dev)
             torch.cumsum(counts, 0, out=row_ptr[1:])
             stats['rows'] = int(xs[0].shape[0])
-    return PrecomputeResult(xs, row_ptr, stats, graphs)
+    result = PrecomputeResult(xs, row_ptr, stats, graphs)
+    if fixed_rows and defer:
+        result._finalize = lambda: finalize(metas0)
+        result._keep = keep0
+    return result
 
 
 def algorithmic_bytes(stats, num_feat, sign_k):

@@ -185,7 +185,7 @@ def test_dump_edges_entry_point():
     ctr = torch.zeros(L.NCTR, dtype=torch.int64, device=dev)
     b = L.Batch(links[0].data_ptr(), links[1].data_ptr(), nrec, L.FLOW_POS, 0, 2, 3, L.BATCH_STORE_ALL_ROWS, 0,
                 arena.data_ptr(), arena.numel(),
-                off.data_ptr(), cnt.data_ptr(), ctr.data_ptr(), None, None, None)
+                off.data_ptr(), cnt.data_ptr(), ctr.data_ptr(), None, None, None, None)
     lib = L.lib()
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     L.check(lib.s3_extract(C.byref(g._c), C.byref(b), st), 'extract')
