@@ -109,7 +109,7 @@ def _records_per_link(flow):
 
 
 def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_records=32768,
-               out=None, return_graphs=False, arena_words=None, stream=None, profile=None, overlap=False, defer=False):
+               out=None, return_graphs=False, arena_words=None, stream=None, profile=None, overlap=False, defer=False, host_out=None):
     """Run the hot path for `links` ([2, L] int64, host or device) on `graph`.
 
     Returns PrecomputeResult with device tensors.  `out`, if given, is a list of K+1
@@ -118,6 +118,9 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
     caller can time each kernel on the launching stream with CUDA events.  `overlap` (fixed-row
     flows) runs extract+diffuse of batch i+1 on one stream while gather of batch i runs on
     another, with two arenas: the latency-bound front half hides under the bandwidth-bound gather.
+    `host_out` (fixed-row flows): K+1 pinned host tensors [>=R, F+1]; every batch's rows are
+    copied device->host on a side stream as soon as its gather finishes, so the D2H of batch i
+    overlaps the kernels of batch i+1 (the reference returns CPU tensors).
     `defer` (fixed-row flows) returns right after enqueueing; the caller must call
     `result.finalize()` (stream sync + validation + re-run of overflowed batches) before using
     the outputs.  It lets several calls be queued back to back without a host round trip.
@@ -147,6 +150,14 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
     st_ptr = C.c_void_p(st.cuda_stream)
 
     with torch.cuda.device(dev), torch.cuda.stream(st):
+        copy_stream = None
+        if host_out is not None:
+            if not fixed_rows or overlap:
+                raise ValueError("host_out needs a fixed-row flow without overlap")
+            copy_stream = graph.streams()[1]
+            ready = torch.cuda.Event()
+            ready.record(st)
+            copy_stream.wait_event(ready)
         if fixed_rows:
             R = 2 * Lk
             if out is None:
@@ -239,6 +250,14 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
                 timed('gather', bi, lambda: L.check(
                     lib.s3_gather(C.byref(graph._c), C.byref(batch), nrec, out_ptrs, F1, b0 * rpl * nseed, st_ptr), 's3_gather'))
                 stats['launches'] += 2
+                if host_out is not None:      # pipelined D2H of this batch's rows
+                    r0, r1 = b0 * rpl * nseed, b1 * rpl * nseed
+                    done = torch.cuda.Event()
+                    done.record(st)
+                    copy_stream.wait_event(done)
+                    with torch.cuda.stream(copy_stream):
+                        for k in range(K + 1):
+                            host_out[k][r0:r1].copy_(out[k][r0:r1], non_blocking=True)
                 return cnt, off, None
             row_ptr = torch.empty(nrec + 1, dtype=torch.int64, device=dev)
             item_ptr = torch.empty(nrec + 1, dtype=torch.int64, device=dev)
@@ -335,6 +354,8 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
             def finalize(metas):
                 with torch.cuda.device(dev), torch.cuda.stream(st):
                     st.synchronize()
+                    if copy_stream is not None:
+                        copy_stream.synchronize()
                     todo = settle(metas)
                     while todo:
                         if return_graphs and graphs:
@@ -342,6 +363,8 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
                         grow()
                         metas, _keep = enqueue(todo)
                         st.synchronize()
+                        if copy_stream is not None:
+                            copy_stream.synchronize()
                         todo = settle(metas)
 
             metas0, keep0 = enqueue(list(range(nb)))

@@ -28,9 +28,19 @@ def device_graph(A, x, device=None):
     return g
 
 
-def _finish(res, y):
+def _host_buffers(num_links, num_feat, K):
+    """Pinned host outputs for a fixed-row flow (2 rows per link), or None when the operator
+    matrices are to stay in HBM."""
+    if os.environ.get('S3GRL_OUTPUT_DEVICE', 'cpu') != 'cpu':
+        return None
+    return [torch.empty((2 * num_links, num_feat + 1), dtype=torch.float32, pin_memory=True) for _ in range(K + 1)]
+
+
+def _finish(res, y, host=None):
     out_dev = os.environ.get('S3GRL_OUTPUT_DEVICE', 'cpu')
     xs, row_ptr = res.xs, res.row_ptr
+    if host is not None:          # already copied batch by batch, overlapped with the kernels
+        return PrecomputedList(host, row_ptr.cpu(), y, res.stats)
     if out_dev == 'cpu':
         host = [torch.empty(x.shape, dtype=x.dtype, pin_memory=True) for x in xs]
         for h, x in zip(host, xs):
@@ -59,7 +69,8 @@ class OptimizedSignOperations:
         being read out of global SpGEMM powers (sgrl_link_pred.py:161-178)."""
         K = len(powers_of_A) if not isinstance(powers_of_A, int) else powers_of_A
         g = device_graph(A, x)
-        return _finish(precompute(g, link_index, 0, K, flow='SoP'), y)
+        host = _host_buffers(int(link_index.shape[1]), g.num_feat, K)
+        return _finish(precompute(g, link_index, 0, K, flow='SoP', host_out=host), y, host)
 
     @staticmethod
     def get_PoS_prepped_ds(link_index, num_hops, A, ratio_per_hop, max_nodes_per_hop, directed, A_csc, x, y,
@@ -68,7 +79,8 @@ class OptimizedSignOperations:
         _reject_unsupported(ratio_per_hop, max_nodes_per_hop, directed, rw_kwargs)
         assert x is not None                       # reference tuned_SIGN.py:166
         g = device_graph(A, x)
-        return _finish(precompute(g, link_index, num_hops, sign_kwargs['sign_k'], flow='PoS'), y)
+        host = _host_buffers(int(link_index.shape[1]), g.num_feat, sign_kwargs['sign_k'])
+        return _finish(precompute(g, link_index, num_hops, sign_kwargs['sign_k'], flow='PoS', host_out=host), y, host)
 
     @staticmethod
     def get_PoS_Plus_prepped_ds(link_index, num_hops, A, ratio_per_hop, max_nodes_per_hop, directed, A_csc, x, y,
