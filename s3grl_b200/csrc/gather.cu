@@ -9,7 +9,9 @@
 //      out_k[row(c), 0]     = label weight computed by kernel 2
 // Every subgraph node's feature row is read exactly ONCE (4*F*n bytes, the dominant term of
 // the roofline in SURVEY.md §8d) with 128-bit loads; NW = (K+1)*SC accumulator rows live in
-// registers; weights and node ids are staged through shared memory in tiles.
+// registers; weights and row offsets are staged through shared memory in tiles. Feature rows are
+// padded by the host (DeviceGraph) so that every lane owns a valid 16-byte column: the inner
+// loop is LDS(offset) + LDG.128 + LDS(weights) + FFMAs, with no predicates or 64-bit index math.
 //
 // Structural sparsity: a k-step walk cannot reach a node more than k hops away, so a node at
 // hop l of the canonical (hop-major) order has w_k = 0 for k < l (k < l-1 when the selected
@@ -49,66 +51,63 @@ template <int C>
 struct GatherCtx {
     const int32_t* __restrict__ nodes;
     const float4* __restrict__ wgt4;
-    const float4* __restrict__ x4;
-    int64_t ldx4;
-    int col[C];
+    const float4* xcol[C];  // x + this lane's float4 column(s)
+    uint32_t ldx4;
     bool colok[C];
     float* s_w;
-    int* s_gid;
+    uint32_t* s_off;  // float4 index of every staged node's feature row
     int tid, grp, G;
 };
 
+template <int K1, int SC, int KMIN>
+__device__ __forceinline__ void load_weights(float (&w)[K1 * SC], const float* wrow) {
+    if (SC == 2) {
+#pragma unroll
+        for (int k = KMIN; k < K1; ++k) {
+            const float2 v = reinterpret_cast<const float2*>(wrow)[k];
+            w[2 * k] = v.x;
+            w[2 * k + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int q = KMIN * SC; q < K1 * SC; ++q) w[q] = wrow[q];
+    }
+}
+
 // Accumulate nodes [lo, hi) of the record; only operators k >= KMIN carry weight there.
-template <int K1, int SC, int C, int KMIN>
+// FULL: every lane owns a valid column (rows are padded), so the loads carry no predicates.
+template <int K1, int SC, int C, int KMIN, bool FULL>
 __device__ __forceinline__ void accumulate_range(float4 (&acc)[K1 * SC][C], int lo, int hi, const GatherCtx<C>& cx) {
     constexpr int NW = K1 * SC, NWP = (NW + 3) & ~3, Q0 = KMIN * SC;
-    const int32_t* __restrict__ nodes = cx.nodes;
-    const float4* __restrict__ wgt4 = cx.wgt4;
-    const float4* __restrict__ x4 = cx.x4;
-    const int64_t ldx4 = cx.ldx4;
     float* s_w = cx.s_w;
-    int* s_gid = cx.s_gid;
+    uint32_t* s_off = cx.s_off;
     const int tid = cx.tid, grp = cx.grp, G = cx.G;
-    const int (&col)[C] = cx.col;
-    const bool (&colok)[C] = cx.colok;
     for (int base = lo; base < hi; base += kTile) {
         const int tn = min(kTile, hi - base);
         __syncthreads();
-        if (tid < tn) s_gid[tid] = nodes[base + tid];
+        if (tid < tn) s_off[tid] = (uint32_t)cx.nodes[base + tid] * cx.ldx4;
         {
-            const float4* src = wgt4 + (int64_t)base * (NWP / 4);
+            const float4* src = cx.wgt4 + (int64_t)base * (NWP / 4);
             float4* dst = reinterpret_cast<float4*>(s_w);
             for (int i = tid; i < tn * (NWP / 4); i += kGatherThreads) dst[i] = src[i];
         }
         __syncthreads();
 
-        for (int t0 = grp; t0 < tn; t0 += kU * G) {
+        int t = grp;
+        // main loop: kU rows in flight per row group, no bounds checks
+        for (; t + (kU - 1) * G < tn; t += kU * G) {
             float4 xv[kU][C];
 #pragma unroll
             for (int u = 0; u < kU; ++u) {
-                const int t = t0 + u * G;
-                const bool ok = t < tn;
-                const int64_t rowoff = ok ? (int64_t)s_gid[t] * ldx4 : 0;
+                const uint32_t o = s_off[t + u * G];
 #pragma unroll
                 for (int i = 0; i < C; ++i)
-                    xv[u][i] = (ok && colok[i]) ? __ldg(x4 + rowoff + col[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    xv[u][i] = (FULL || cx.colok[i]) ? __ldg(cx.xcol[i] + o) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int u = 0; u < kU; ++u) {
-                const int t = min(t0 + u * G, tn - 1);  // out-of-range slots carry x = 0
-                const float* wrow = s_w + t * NWP;
                 float w[NW];
-                if (SC == 2) {
-#pragma unroll
-                    for (int k = KMIN; k < K1; ++k) {
-                        const float2 v = reinterpret_cast<const float2*>(wrow)[k];
-                        w[2 * k] = v.x;
-                        w[2 * k + 1] = v.y;
-                    }
-                } else {
-#pragma unroll
-                    for (int q = Q0; q < NW; ++q) w[q] = wrow[q];
-                }
+                load_weights<K1, SC, KMIN>(w, s_w + (t + u * G) * NWP);
 #pragma unroll
                 for (int q = Q0; q < NW; ++q)
 #pragma unroll
@@ -120,29 +119,48 @@ __device__ __forceinline__ void accumulate_range(float4 (&acc)[K1 * SC][C], int 
                     }
             }
         }
+        // tail of the tile, one row at a time (same order of accumulation: ascending node index)
+        for (; t < tn; t += G) {
+            const uint32_t o = s_off[t];
+            float4 xv[C];
+#pragma unroll
+            for (int i = 0; i < C; ++i)
+                xv[i] = (FULL || cx.colok[i]) ? __ldg(cx.xcol[i] + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float w[NW];
+            load_weights<K1, SC, KMIN>(w, s_w + t * NWP);
+#pragma unroll
+            for (int q = Q0; q < NW; ++q)
+#pragma unroll
+                for (int i = 0; i < C; ++i) {
+                    acc[q][i].x = fmaf(w[q], xv[i].x, acc[q][i].x);
+                    acc[q][i].y = fmaf(w[q], xv[i].y, acc[q][i].y);
+                    acc[q][i].z = fmaf(w[q], xv[i].z, acc[q][i].z);
+                    acc[q][i].w = fmaf(w[q], xv[i].w, acc[q][i].w);
+                }
+        }
     }
 }
 
-template <int K1, int SC, int C, int KMIN>
+template <int K1, int SC, int C, int KMIN, bool FULL>
 struct RangeDispatch {
     __device__ __forceinline__ static void run(int kmin, float4 (&acc)[K1 * SC][C], int lo, int hi, const GatherCtx<C>& cx) {
         if (kmin == KMIN)
-            accumulate_range<K1, SC, C, KMIN>(acc, lo, hi, cx);
+            accumulate_range<K1, SC, C, KMIN, FULL>(acc, lo, hi, cx);
         else
-            RangeDispatch<K1, SC, C, KMIN + 1>::run(kmin, acc, lo, hi, cx);
+            RangeDispatch<K1, SC, C, KMIN + 1, FULL>::run(kmin, acc, lo, hi, cx);
     }
 };
-template <int K1, int SC, int C>
-struct RangeDispatch<K1, SC, C, K1> {
+template <int K1, int SC, int C, bool FULL>
+struct RangeDispatch<K1, SC, C, K1, FULL> {
     __device__ __forceinline__ static void run(int, float4 (&)[K1 * SC][C], int, int, const GatherCtx<C>&) {}
 };
 
-template <int K1, int SC, int C>
+template <int K1, int SC, int C, bool FULL>
 __global__ void __launch_bounds__(kGatherThreads) gather_kernel(GatherParams p) {
     constexpr int NW = K1 * SC, NWP = (NW + 3) & ~3;
     extern __shared__ float4 smem4[];
-    float* s_w = reinterpret_cast<float*>(smem4);            // [kTile][NWP]
-    int* s_gid = reinterpret_cast<int*>(s_w + kTile * NWP);  // [kTile]
+    float* s_w = reinterpret_cast<float*>(smem4);                        // [kTile][NWP]
+    uint32_t* s_off = reinterpret_cast<uint32_t*>(s_w + kTile * NWP);    // [kTile]
 
     const int tid = threadIdx.x;
     const int64_t item = p.order ? (int64_t)p.order[blockIdx.x] : (int64_t)blockIdx.x;
@@ -162,19 +180,19 @@ __global__ void __launch_bounds__(kGatherThreads) gather_kernel(GatherParams p) 
     const int tpr = p.tpr, G = kGatherThreads / tpr;
     const int grp = tid / tpr, lane = tid - grp * tpr;
     GatherCtx<C> cx;
-    int (&col)[C] = cx.col;
+    int col[C];
     bool (&colok)[C] = cx.colok;
 #pragma unroll
     for (int i = 0; i < C; ++i) {
         col[i] = (blockIdx.y * C + i) * tpr + lane;
         colok[i] = col[i] < p.F4;
+        cx.xcol[i] = reinterpret_cast<const float4*>(p.x) + (colok[i] ? col[i] : 0);
     }
     cx.nodes = nodes;
     cx.wgt4 = wgt4;
-    cx.x4 = reinterpret_cast<const float4*>(p.x);
-    cx.ldx4 = p.ldx >> 2;
+    cx.ldx4 = (uint32_t)(p.ldx >> 2);
     cx.s_w = s_w;
-    cx.s_gid = s_gid;
+    cx.s_off = s_off;
     cx.tid = tid;
     cx.grp = grp;
     cx.G = G;
@@ -194,7 +212,7 @@ __global__ void __launch_bounds__(kGatherThreads) gather_kernel(GatherParams p) 
         const int kmin = max(0, l - shift);
         if (kmin >= K1) break;  // farther than K hops: no operator reaches these nodes
         if (hi > lo)
-            RangeDispatch<K1, SC, C, 0>::run(kmin, acc, lo, hi, cx);
+            RangeDispatch<K1, SC, C, 0, FULL>::run(kmin, acc, lo, hi, cx);
         lo = hi;
     }
 
@@ -245,14 +263,20 @@ __global__ void __launch_bounds__(kGatherThreads) gather_kernel(GatherParams p) 
     }
 }
 
-template <int K1, int SC, int C>
-cudaError_t launch_one(const GatherParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+template <int K1, int SC, int C, bool FULL>
+cudaError_t launch_full(const GatherParams& p, dim3 grid, size_t smem, cudaStream_t st) {
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(gather_kernel<K1, SC, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(gather_kernel<K1, SC, C, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    gather_kernel<K1, SC, C><<<grid, kGatherThreads, smem, st>>>(p);
+    gather_kernel<K1, SC, C, FULL><<<grid, kGatherThreads, smem, st>>>(p);
     return cudaGetLastError();
+}
+
+template <int K1, int SC, int C>
+cudaError_t launch_one(const GatherParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+    const bool full = p.F4 % (p.tpr * C) == 0;  // every lane of every column chunk owns a valid column
+    return full ? launch_full<K1, SC, C, true>(p, grid, smem, st) : launch_full<K1, SC, C, false>(p, grid, smem, st);
 }
 
 template <int K1, int SC>
@@ -283,6 +307,7 @@ cudaError_t launch_k(const GatherParams& p, int K1, int C, dim3 grid, size_t sme
 cudaError_t launch_gather(const s3_graph& g, const s3_batch& b, int64_t num_items, const OutPtrs& out, int64_t ldo,
                           int64_t row_base, cudaStream_t st) {
     if (num_items == 0) return cudaSuccess;
+    if (g.num_nodes * (g.ldx / 4) >= (int64_t(1) << 32)) return cudaErrorInvalidValue;  // 32-bit row offsets
     GatherParams p;
     p.x = g.x;
     p.ldx = g.ldx;

@@ -60,7 +60,7 @@ class DeviceGraph:
         if x.dim() != 2 or x.shape[0] != self.num_nodes:
             raise ValueError(f"x must be [N={self.num_nodes}, F], got {tuple(x.shape)}")
         self.num_feat = int(x.shape[1])
-        self.ldx = (self.num_feat + 3) // 4 * 4
+        self.ldx = self.padded_row_stride(self.num_feat)
         self.x = torch.zeros((self.num_nodes, self.ldx), dtype=torch.float32, device=self.device)
         self.x[:, :self.num_feat].copy_(x, non_blocking=True)
         self.h2d_bytes = self.indptr.numel() * 8 + self.indices.numel() * 4 + x.numel() * 4
@@ -69,6 +69,22 @@ class DeviceGraph:
         self._arena = None
         self._arena2 = None
         self._streams = None
+
+    @staticmethod
+    def padded_row_stride(F):
+        """Row stride (floats) that gives every lane of kernel 3 a valid 16-byte column and starts
+        every row on a 128-byte line: the kernel's (threads per row) x (columns per thread) tiling
+        — 32/64/128 lanes x 1..3 float4 — mirrored here (gather.cu, launch_gather)."""
+        f4 = (F + 3) // 4
+        if f4 <= 32:
+            return 128
+        if f4 <= 64:
+            return 256
+        if f4 <= 128:
+            return 512
+        if f4 <= 256:
+            return 1024
+        return (f4 + 383) // 384 * 384 * 4
 
     # scratch arenas (int32 words), grown on demand and kept across calls; the second one is
     # only allocated by the overlapped (two-stream, double-buffered) schedule
