@@ -454,8 +454,13 @@ __global__ void __launch_bounds__(kExtractThreads, 4) front_kernel(ExtractParams
                     }
                 }
                 if (k == K) {
-                    // streamed rows: hop-K nodes, read once, never stored
-                    const int inner_levels = min(K - 1, nlev);
+                    // streamed rows: hop-K nodes, read once, never stored. Their neighbours sit on
+                    // hops K-1, K, K+1 and z_{K-1} lives on hop K-1 only: ONE level bitmap (or, for
+                    // K = 1, the seed ids) decides whether a neighbour contributes.
+                    const int zl = K - 2;  // level index of hop K-1 (levels are hops 1..h); -1: the seeds
+                    const uint32_t* Lz = Lb + (size_t)max(zl, 0) * W;
+                    const uint32_t* Pz = pre + (size_t)max(zl, 0) * W;
+                    const int zbase = zl >= 0 ? s_lvl_base[zl] : 0;
                     for (int jb0 = n_store; jb0 < n_reach; jb0 += NG) {
                         const int j = jb0 + grp;
                         const bool valid = j < n_reach;
@@ -471,13 +476,18 @@ __global__ void __launch_bounds__(kExtractThreads, 4) front_kernel(ExtractParams
                         int cntv = 0;
                         for (int idx = l8; idx < len; idx += 8) {
                             const int c_ = p.indices[e0 + idx];
-                            if (test_bit(V, c_)) {
-                                ++cntv;
-                                const int i = local_id(c_, s0, s1, nseed, Lb, pre, s_lvl_base, inner_levels, W);
-                                if (i >= 0) {  // hop <= K-1: the only nodes where z_{K-1} lives
+                            const int w = c_ >> 5, b = c_ & 31;
+                            cntv += (V[w] >> b) & 1u;
+                            int i = -1;
+                            if (zl >= 0) {
+                                const uint32_t bits = Lz[w];
+                                if ((bits >> b) & 1u) i = zbase + (int)Pz[w] + __popc(bits & ((1u << b) - 1u));
+                            } else {
+                                i = c_ == s0 ? 0 : ((nseed == 2 && c_ == s1) ? 1 : -1);
+                            }
+                            if (i >= 0) {
 #pragma unroll
-                                    for (int c = 0; c < SC; ++c) t[c] += zprev[i * SC + c];
-                                }
+                                for (int c = 0; c < SC; ++c) t[c] += zprev[i * SC + c];
                             }
                         }
 #pragma unroll
