@@ -34,7 +34,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "precomputed target links/sec (extract+diffuse+pool), PubMed PoS r=3"
+METRIC = "precomputed target links/sec (extract+diffuse+pool), PubMed PoS r=3"   # default workload; see config.workload
 UNIT = "links/s"
 
 
@@ -55,6 +55,22 @@ def build_workload(name):
                 f"split seed 1, all {links.shape[1]} links of the 3 splits, PoS"
                 f"{' Plus ' + strategy if strategy else ''} num_hops=3 sign_k=3")
         return dict(A=A, X=X, links=links, num_hops=3, K=3, flow='PoS', strategy=strategy, desc=desc)
+    if name == 'usair_sop':          # BASELINE config 2
+        edges, N, _ = ds.load_graph('usair')
+        A, splits = ds.split_links(edges, N, seed=1)
+        X = ds.normalize_features(ds.degree_one_hot(A, 1024))
+        links = ds.all_links(splits)
+        return dict(A=A, X=X, links=links, num_hops=0, K=3, flow='SoP', strategy=None,
+                    desc=f"USAir (N={N}), init_features=degree one-hot F=1025, all {links.shape[1]} links, SoP sign_k=3")
+    if name in ('yeast_pos_k5', 'power_pos_k5', 'router_pos_k5'):      # BASELINE config 4
+        gname = name.split('_')[0]
+        edges, N, _ = ds.load_graph(gname)
+        A, splits = ds.split_links(edges, N, seed=1)
+        X = ds.synthetic_features(N, 256, 1.0, 0)
+        links = ds.all_links(splits)
+        return dict(A=A, X=X, links=links, num_hops=2, K=5, flow='PoS', strategy=None,
+                    desc=f"{gname} SEAL graph (N={N}), synthetic X F=256 row-normalised seed 0, all {links.shape[1]} links, "
+                         f"PoS num_hops=2 sign_k=5")
     if name == 'cora_pos':
         edges, N, X = ds.load_graph('cora')
         A, splits = ds.split_links(edges, N, seed=1)
@@ -79,7 +95,12 @@ def _cpu_init(w):
 def _cpu_chunk(cols):
     from oracle import s3grl_oracle as orc
     w = _W
-    out = orc.pos_precompute(w['links'][:, cols], w['num_hops'], w['A'], w['X'], w['K'], w['strategy'])
+    if w['flow'] == 'SoP':
+        if 'sop_powers' not in w:       # the reference builds the global powers once per split
+            w['sop_powers'] = orc.sop_powers(w['A'], w['K'])
+        out = orc.sop_precompute(w['links'][:, cols], w['A'], w['X'], w['K'], powers=w['sop_powers'])
+    else:
+        out = orc.pos_precompute(w['links'][:, cols], w['num_hops'], w['A'], w['X'], w['K'], w['strategy'])
     return int(out['row_ptr'][-1])
 
 

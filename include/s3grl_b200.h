@@ -120,11 +120,15 @@ typedef struct s3_graph {
     int64_t num_feat;       /* F                                            */
     int64_t ldx;            /* row stride in floats, multiple of 4, >= F    */
     int64_t num_edges;      /* indptr[num_nodes]; < 2^32 for the bitmap tier */
+    int64_t max_degree;     /* largest row of the CSR (sizes the sorted tier's slabs) */
 } s3_graph;
 
 /* s3_batch.flags: keep every row of the induced adjacency (parity dumps). Without it rows of
  * hop == K are streamed once and never stored (PoS Plus always stores all rows). */
 #define S3_BATCH_STORE_ALL_ROWS 1
+/* Use the sorted-set extraction tier even when the bitmap tier would fit (tests). The sorted
+ * tier serves graphs of any size but only PoS with num_hops == 1 and S3_STRATEGY_NONE. */
+#define S3_BATCH_FORCE_SORTED_TIER 2
 
 /* One batch of records and its scratch. */
 typedef struct s3_batch {
@@ -163,9 +167,12 @@ int64_t s3_num_records(const s3_batch* b);
 /* upper bound of work items s3_plan can produce is not known before extract; after
  * s3_plan + a stream sync the exact numbers are counters[S3_CTR_ROWS] / [S3_CTR_ITEMS]. */
 
-/* smallest arena s3_extract accepts for this graph (per-CTA node slabs live at its head);
- * a useful arena is much larger: roughly 14*n + D + 12*n*ceil(s/2) words per record. */
-int64_t s3_min_arena_words(int64_t num_nodes);
+/* smallest arena s3_extract accepts for this graph (per-CTA slabs live at its head); a useful
+ * arena is much larger: roughly 14*n + D_store + 12*n*ceil(s/2) words per record. */
+int64_t s3_min_arena_words(const s3_graph* g, const s3_batch* b);
+
+/* 0: shared-memory bitmap tier, 1: sorted-set tier, -1: unsupported combination. */
+int s3_extract_tier(const s3_graph* g, const s3_batch* b);
 
 /* dynamic shared memory the bitmap extraction tier needs for this graph, or -1 if the
  * graph is too large for it (then S3_ERR_UNSUPPORTED from s3_extract). */

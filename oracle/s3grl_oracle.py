@@ -234,6 +234,21 @@ def hybrid_precompute(links, num_hops, A, X, K, dtype=np.float32):
     return dict(xs=pos['xs'] + sop['xs'][2:], row_ptr=pos['row_ptr'])
 
 
+def sign_all_rows(src, dst, num_hops, A, X, K, dtype=np.float32):
+    """The NON-optimised flow (utils.py:497-550 + TunedSIGN.__call__, tuned_SIGN.py:18-23 — PyG's
+    SIGN transform on the whole subgraph): x_k = S x_{k-1} for ALL n rows with the zero-one label
+    column.  No paper config uses it; it is restated because it is an independent route to the same
+    numbers: its rows 0 and 1 must equal the optimised PoS flow's output."""
+    nodes, hops, lrowptr, lcol = k_hop_subgraph(src, dst, num_hops, A)
+    S, _ = normalized_subgraph(lrowptr, lcol, dtype)
+    label = np.zeros((nodes.size, 1), dtype=dtype)
+    label[:2] = 1
+    xs = [np.hstack([label, np.asarray(X[nodes], dtype=dtype)])]
+    for _ in range(K):
+        xs.append(np.asarray(S @ xs[-1], dtype=dtype))
+    return xs
+
+
 def joint_matrix(xs):
     """models.py:372 — feature-wise concat of the operators, [R, (K+1)(F+1)]."""
     return np.concatenate(xs, axis=-1)

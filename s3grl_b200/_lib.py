@@ -14,17 +14,18 @@ MAX_HOPS, MAX_K = 8, 7
 REC_OK, REC_ARENA_OVERFLOW, REC_BAD_LINK = 0, 1, 2
 OFF_NODES, OFF_ROWPTR, OFF_ROWLEN, OFF_LCOL, OFF_SEL, OFF_F32, NOFF = 0, 1, 2, 3, 4, 5, 6
 CNT_N, CNT_M, CNT_S, CNT_STATUS, CNT_PARTNER, CNT_HOP0, CNT_NSTORE, NCNT = 0, 1, 2, 3, 4, 5, 14, 16
-BATCH_STORE_ALL_ROWS = 1
+BATCH_STORE_ALL_ROWS, BATCH_FORCE_SORTED_TIER = 1, 2
 CTR_CURSOR, CTR_ERRORS, CTR_ROWS, CTR_ITEMS, CTR_MAX_N, CTR_SUM_N, CTR_SUM_D, CTR_WORK, NCTR = 0, 1, 2, 3, 4, 5, 6, 7, 48
 
 EXPORTS = ['s3_version', 's3_error_string', 's3_last_cuda_error', 's3_num_records', 's3_extract_smem_bytes',
-           's3_min_arena_words',
+           's3_min_arena_words', 's3_extract_tier',
            's3_extract', 's3_plan', 's3_plan_items', 's3_diffuse', 's3_gather', 's3_dump_edges']
 
 
 class Graph(C.Structure):
     _fields_ = [('indptr', C.c_void_p), ('indices', C.c_void_p), ('x', C.c_void_p),
-                ('num_nodes', C.c_int64), ('num_feat', C.c_int64), ('ldx', C.c_int64), ('num_edges', C.c_int64)]
+                ('num_nodes', C.c_int64), ('num_feat', C.c_int64), ('ldx', C.c_int64), ('num_edges', C.c_int64),
+                ('max_degree', C.c_int64)]
 
 
 class Batch(C.Structure):
@@ -61,7 +62,9 @@ def lib():
         L.s3_num_records.restype = C.c_int64
         L.s3_num_records.argtypes = [C.POINTER(Batch)]
         L.s3_min_arena_words.restype = C.c_int64
-        L.s3_min_arena_words.argtypes = [C.c_int64]
+        L.s3_min_arena_words.argtypes = [C.POINTER(Graph), C.POINTER(Batch)]
+        L.s3_extract_tier.restype = C.c_int
+        L.s3_extract_tier.argtypes = [C.POINTER(Graph), C.POINTER(Batch)]
         L.s3_extract_smem_bytes.restype = C.c_int64
         L.s3_extract_smem_bytes.argtypes = [C.c_int64, C.c_int32]
         L.s3_extract.argtypes = [C.POINTER(Graph), C.POINTER(Batch), C.c_void_p]

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, 'csrc')
 BUILD = os.path.join(HERE, '..', 'build')
 LIB_DIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIB_DIR, 'libs3grl_b200.so')
-SOURCES = ['extract.cu', 'plan.cu', 'diffuse.cu', 'gather.cu', 'c_abi.cu']
+SOURCES = ['extract.cu', 'extract_sorted.cu', 'plan.cu', 'diffuse.cu', 'gather.cu', 'c_abi.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 

@@ -29,7 +29,7 @@ int check_batch(const s3_batch* b) {
 
 int check_graph(const s3_graph* g, bool need_x) {
     if (!g || !g->indptr || !g->indices || g->num_nodes <= 0 || g->num_nodes > INT32_MAX) return S3_ERR_INVALID_ARG;
-    if (g->num_edges < 0) return S3_ERR_INVALID_ARG;
+    if (g->num_edges < 0 || g->max_degree < 0) return S3_ERR_INVALID_ARG;
     if (need_x) {
         if (!g->x || g->num_feat <= 0 || g->ldx < g->num_feat || (g->ldx & 3)) return S3_ERR_INVALID_ARG;
         if (reinterpret_cast<uintptr_t>(g->x) & 15) return S3_ERR_INVALID_ARG;
@@ -46,7 +46,7 @@ const char* s3_error_string(int code) {
     switch (code) {
         case S3_OK: return "ok";
         case S3_ERR_INVALID_ARG: return "invalid argument";
-        case S3_ERR_UNSUPPORTED: return "graph too large for the bitmap extraction tier";
+        case S3_ERR_UNSUPPORTED: return "graph too large for the bitmap tier and the request is not PoS / num_hops 1 / no CCN (sorted tier)";
         case S3_ERR_CUDA: return "CUDA error";
         case S3_ERR_NOT_IMPLEMENTED: return "unknown flow or strategy";
         case S3_ERR_WORKSPACE: return "arena smaller than s3_min_arena_words()";
@@ -58,7 +58,19 @@ const char* s3_last_cuda_error(void) { return g_cuda_err; }
 
 int64_t s3_num_records(const s3_batch* b) { return b->flow == S3_FLOW_SOP ? 2 * b->num_links : b->num_links; }
 
-int64_t s3_min_arena_words(int64_t num_nodes) { return 2 * ((4 * num_nodes + 1 + 31) & ~int64_t(31)); }
+int s3_extract_tier(const s3_graph* g, const s3_batch* b) {
+    if (!g || !b) return -1;
+    const int radius = b->flow == S3_FLOW_POS ? b->num_hops : b->sign_k;
+    const bool bitmap_ok = s3_extract_smem_bytes(g->num_nodes, radius) >= 0 && g->num_edges < (int64_t(1) << 32);
+    const bool sorted_ok = b->flow == S3_FLOW_POS && b->num_hops == 1 && b->strategy == S3_STRATEGY_NONE;
+    if (sorted_ok && ((b->flags & S3_BATCH_FORCE_SORTED_TIER) || !bitmap_ok)) return 1;
+    return bitmap_ok ? 0 : -1;
+}
+
+int64_t s3_min_arena_words(const s3_graph* g, const s3_batch* b) {
+    if (s3_extract_tier(g, b) == 1) return 2 * ((2 * (g->max_degree + 1) + 31) & ~int64_t(31));
+    return 2 * ((4 * g->num_nodes + 1 + 31) & ~int64_t(31));
+}
 
 int64_t s3_extract_smem_bytes(int64_t num_nodes, int32_t radius) {
     if (num_nodes <= 0 || radius < 0 || radius > S3_MAX_HOPS) return -1;
@@ -72,10 +84,11 @@ int s3_extract(const s3_graph* g, const s3_batch* b, void* stream) {
     if (rc != S3_OK) return rc;
     rc = check_batch(b);
     if (rc != S3_OK) return rc;
-    const int radius = b->flow == S3_FLOW_POS ? b->num_hops : b->sign_k;
-    if (s3_extract_smem_bytes(g->num_nodes, radius) < 0 || g->num_edges >= (int64_t(1) << 32)) return S3_ERR_UNSUPPORTED;
+    const int tier = s3_extract_tier(g, b);
+    if (tier < 0) return S3_ERR_UNSUPPORTED;
     int launch_rc = S3_OK;
-    cudaError_t e = s3::launch_extract_bitmap(*g, *b, static_cast<cudaStream_t>(stream), &launch_rc);
+    cudaError_t e = tier == 1 ? s3::launch_extract_sorted(*g, *b, static_cast<cudaStream_t>(stream), &launch_rc)
+                              : s3::launch_extract_bitmap(*g, *b, static_cast<cudaStream_t>(stream), &launch_rc);
     if (e != cudaSuccess) return cuda_fail(e);
     return launch_rc;
 }

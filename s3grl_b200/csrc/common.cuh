@@ -59,6 +59,8 @@ struct OutPtrs {
 
 // launchers (defined in the .cu files, called from c_abi.cu)
 cudaError_t launch_extract_bitmap(const s3_graph& g, const s3_batch& b, cudaStream_t st, int* rc_out);
+cudaError_t launch_extract_sorted(const s3_graph& g, const s3_batch& b, cudaStream_t st, int* rc_out);
+cudaError_t launch_order(const s3_batch& b, int64_t num_records, cudaStream_t st);
 cudaError_t launch_plan(const s3_batch& b, cudaStream_t st);
 cudaError_t launch_plan_items(const s3_batch& b, cudaStream_t st);
 cudaError_t launch_diffuse(const s3_graph& g, const s3_batch& b, int64_t num_items, cudaStream_t st);

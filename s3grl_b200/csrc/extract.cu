@@ -572,6 +572,18 @@ __global__ void order_kernel(const int32_t* __restrict__ cnt, const unsigned lon
     order[s_off[31 - __clz(n)] + c[S3_CNT_CLASSPOS]] = (int32_t)r;
 }
 
+}  // namespace
+
+cudaError_t launch_order(const s3_batch& b, int64_t num_records, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(b.order, 0xff, (size_t)num_records * 4, st);  // -1: skipped by kernel 3
+    if (e != cudaSuccess) return e;
+    order_kernel<<<(unsigned)((num_records + 255) / 256), 256, 0, st>>>(
+        b.cnt, reinterpret_cast<const unsigned long long*>(b.counters), num_records, b.order);
+    return cudaGetLastError();
+}
+
+namespace {
+
 template <int SC>
 cudaError_t launch_front(ExtractParams& p, const s3_graph& g, const s3_batch& b, cudaStream_t st, int* rc_out) {
     const size_t smem = (size_t)s3_extract_smem_bytes(g.num_nodes, p.radius);
@@ -608,10 +620,7 @@ cudaError_t launch_front(ExtractParams& p, const s3_graph& g, const s3_batch& b,
     front_kernel<SC><<<(unsigned)grid, kExtractThreads, smem, st>>>(p);
     e = cudaGetLastError();
     if (e != cudaSuccess || !b.order) return e;
-    e = cudaMemsetAsync(b.order, 0xff, (size_t)p.num_records * 4, st);  // -1: skipped by kernel 3
-    if (e != cudaSuccess) return e;
-    order_kernel<<<(unsigned)((p.num_records + 255) / 256), 256, 0, st>>>(p.cnt, p.counters, p.num_records, b.order);
-    return cudaGetLastError();
+    return launch_order(b, p.num_records, st);
 }
 
 }  // namespace

@@ -1,0 +1,405 @@
+// Kernel 1, sorted-set tier — the front kernel for graphs too large for shared-memory bitmaps
+// (N up to 2^31: the 10 M-node R-MAT configuration), one-hop enclosing subgraphs.
+//
+// Replaces the same reference lines as extract.cu (utils.py:33-85, tuned_SIGN.py:153-175 for the
+// rows of the two targets). With num_hops = 1 the subgraph of link (u, v) is
+//      S = {u, v} ∪ N(u) ∪ N(v)
+// and both adjacency lists are already sorted, so the canonical order [u, v, ascending id] comes
+// out of a parallel MERGE — exclusive prefix sums of "keep" flags over N(u) and N(v) plus one
+// binary search per element give every node its final position; no hash table, no sort.
+// Membership / local-id lookups afterwards are binary searches in that sorted node list
+// (shared memory when it fits).
+//
+// The induced adjacency N(g_j) ∩ S of row j is computed by whichever side is cheaper:
+//   (i)  stream N(g_j) and look every entry up in S          deg_j · log n
+//   (ii) look every node of S up in N(g_j)                    n · log deg_j   (hub rows)
+// one warp per row, exact count -> block scan -> fill (ballot-ordered), so the local CSR is
+// dense and the arena only holds the m real edges. All K sweeps then run over that CSR
+// (num_hops = 1 < K: every row is read by every sweep), 8-lane group per row, z in shared
+// memory when the subgraph fits.
+//
+// Larger radii on graphs of this size are rejected (S3_ERR_UNSUPPORTED): a 2-hop ball of an
+// R-MAT hub is most of the graph, and the reference itself only handles it with random caps.
+#include <climits>
+
+#include "common.cuh"
+
+namespace s3 {
+namespace {
+
+struct SortedParams {
+    const int64_t* __restrict__ indptr;
+    const int32_t* __restrict__ indices;
+    int64_t num_nodes;
+    const int64_t* __restrict__ link_src;
+    const int64_t* __restrict__ link_dst;
+    int64_t num_records;
+    int sign_k;
+    int32_t* arena;
+    int64_t arena_words;
+    int64_t slab_stride;  // words per CTA slab: prefix arrays of both adjacency lists
+    int64_t slab_words;
+    int64_t* off;
+    int32_t* cnt;
+    unsigned long long* counters;
+};
+
+constexpr int kNodeCap = 6144;  // nodes cached in shared memory (24 KB)
+constexpr int kZCapS = 2048;    // floats per shared z buffer
+
+// number of elements of the ascending array a[0..n) that are < x
+__device__ __forceinline__ int lower_bound(const int32_t* __restrict__ a, int n, int x) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] < x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ bool contains(const int32_t* __restrict__ a, int n, int x) {
+    const int p = lower_bound(a, n, x);
+    return p < n && a[p] == x;
+}
+
+// local id of global node c in [u, v, sorted rest...] or -1
+__device__ __forceinline__ int lookup(const int32_t* nodes, int n, int u, int v, int c) {
+    if (c == u) return 0;
+    if (c == v) return 1;
+    const int p = lower_bound(nodes + 2, n - 2, c);
+    return (p < n - 2 && nodes[2 + p] == c) ? 2 + p : -1;
+}
+
+__global__ void __launch_bounds__(kExtractThreads, 3) front_sorted_kernel(SortedParams p) {
+    const int T = kExtractThreads, tid = threadIdx.x, K = p.sign_k;
+    constexpr int SC = 2;
+    const int lane = tid & 31, wid = tid >> 5, l8 = tid & 7, grp = tid >> 3;
+    constexpr int NG = kExtractThreads / 8, NWARP = kExtractThreads / 32;
+    const int NW = (K + 1) * SC, NWP = (NW + 3) & ~3;
+    __shared__ int s_scan[33];
+    __shared__ long long s_base;
+    __shared__ long long s_rec;
+    __shared__ int s_nodes[kNodeCap];
+    __shared__ float s_z[2][kZCapS];
+
+    int32_t* PA = p.arena + (int64_t)blockIdx.x * p.slab_stride;  // [du + 1]
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_rec = (long long)atomicAdd(&p.counters[S3_CTR_WORK], 1ull);
+        __syncthreads();
+        const int64_t rec = s_rec;
+        if (rec >= p.num_records) break;
+        const int64_t a64 = p.link_src[rec], b64 = p.link_dst[rec];
+        int32_t* cnt = p.cnt + rec * S3_NCNT;
+        int64_t* off = p.off + rec * S3_NOFF;
+        if (a64 < 0 || b64 < 0 || a64 >= p.num_nodes || b64 >= p.num_nodes || a64 == b64) {
+            if (tid == 0) {
+                for (int i = 0; i < S3_NCNT; ++i) cnt[i] = 0;
+                for (int i = 0; i < S3_NOFF; ++i) off[i] = 0;
+                cnt[S3_CNT_STATUS] = S3_REC_BAD_LINK;
+                cnt[S3_CNT_PARTNER] = -1;
+                atomicAdd(&p.counters[S3_CTR_ERRORS], 1ull);
+            }
+            continue;
+        }
+        const int u = (int)a64, v = (int)b64;
+        const int64_t eu0 = p.indptr[u], ev0 = p.indptr[v];
+        const int du = (int)(p.indptr[u + 1] - eu0), dv = (int)(p.indptr[v + 1] - ev0);
+        const int32_t* __restrict__ A = p.indices + eu0;
+        const int32_t* __restrict__ B = p.indices + ev0;
+        int32_t* PB = PA + du + 1;  // [dv + 1]
+
+        // ---- keep flags and their exclusive prefix sums: A minus {u,v}; B minus {u,v} minus A ----
+        int nA = 0, nB = 0;
+        for (int base = 0; base < du; base += T) {
+            const int i = base + tid;
+            int f = 0;
+            if (i < du) {
+                const int x = A[i];
+                f = (x != u && x != v) ? 1 : 0;
+            }
+            int tot;
+            const int ex = block_exclusive_scan(f, s_scan, &tot);
+            if (i < du) PA[i] = nA + ex;
+            nA += tot;
+            __syncthreads();
+        }
+        for (int base = 0; base < dv; base += T) {
+            const int k = base + tid;
+            int f = 0;
+            if (k < dv) {
+                const int y = B[k];
+                f = (y != u && y != v && !contains(A, du, y)) ? 1 : 0;
+            }
+            int tot;
+            const int ex = block_exclusive_scan(f, s_scan, &tot);
+            if (k < dv) PB[k] = nB + ex;
+            nB += tot;
+            __syncthreads();
+        }
+        if (tid == 0) {
+            PA[du] = nA;
+            PB[dv] = nB;
+        }
+        const int n = 2 + nA + nB;
+
+        // ---- allocation 1a: nodes | rowptr | rowlen ----
+        const int64_t words1 = (3 * (int64_t)n + 1 + 31) & ~int64_t(31);
+        __syncthreads();
+        if (tid == 0) s_base = (long long)atomicAdd(&p.counters[S3_CTR_CURSOR], (unsigned long long)words1);
+        __syncthreads();
+        const int64_t base1 = p.slab_words + s_base;
+        bool overflow = base1 + words1 > p.arena_words;
+        int32_t* nodes_g = p.arena + base1;
+        int32_t* rowptr = nodes_g + n;
+        int32_t* rowlen = rowptr + n + 1;
+        int64_t base2 = 0, base3 = 0;
+        int m = 0;
+        unsigned long long my_deg = 0;
+
+        if (!overflow) {
+            // ---- merge into the canonical order ----
+            if (tid == 0) {
+                nodes_g[0] = u;
+                nodes_g[1] = v;
+            }
+            for (int i = tid; i < du; i += T) {
+                const int x = A[i];
+                if (x != u && x != v) nodes_g[2 + PA[i] + PB[lower_bound(B, dv, x)]] = x;
+            }
+            for (int k = tid; k < dv; k += T) {
+                if (PB[k + 1] != PB[k]) {  // kept
+                    const int y = B[k];
+                    nodes_g[2 + PB[k] + PA[lower_bound(A, du, y)]] = y;
+                }
+            }
+            __syncthreads();
+            const bool cached = n <= kNodeCap;
+            if (cached)
+                for (int j = tid; j < n; j += T) s_nodes[j] = nodes_g[j];
+            __syncthreads();
+            const int32_t* nodes = cached ? s_nodes : nodes_g;
+
+            // ---- count pass: |N(g_j) ∩ S| minus the masked target link, one warp per row ----
+            for (int j = wid; j < n; j += NWARP) {
+                const int g = nodes[j];
+                const int64_t e0 = p.indptr[g];
+                const int d = (int)(p.indptr[g + 1] - e0);
+                if (lane == 0) my_deg += (unsigned long long)d;
+                const int32_t* __restrict__ Nj = p.indices + e0;
+                const bool by_nodes = (int64_t)n * (32 - __clz(d | 1)) * 2 < d;  // (ii) for hub rows
+                int c_row = 0;
+                if (!by_nodes) {
+                    for (int e = lane; e < ((d + 31) & ~31); e += 32) {
+                        int lid = -1;
+                        if (e < d) lid = lookup(nodes, n, u, v, Nj[e]);
+                        const bool ok = lid >= 0 && !((j == 0 && lid == 1) || (j == 1 && lid == 0));  // utils.py:79-80
+                        c_row += __popc(__ballot_sync(0xffffffffu, ok));
+                    }
+                } else {
+                    for (int t = lane; t < ((n + 31) & ~31); t += 32) {
+                        bool ok = false;
+                        if (t < n) ok = contains(Nj, d, nodes[t]) && !((j == 0 && t == 1) || (j == 1 && t == 0));
+                        c_row += __popc(__ballot_sync(0xffffffffu, ok));
+                    }
+                }
+                if (lane == 0) rowlen[j] = c_row;
+            }
+            __syncthreads();
+            // ---- row starts: exclusive scan of rowlen ----
+            for (int base = 0; base < n; base += T) {
+                const int j = base + tid;
+                const int d = j < n ? rowlen[j] : 0;
+                int tot;
+                const int ex = block_exclusive_scan(d, s_scan, &tot);
+                if (j < n) rowptr[j] = m + ex;
+                m += tot;
+                __syncthreads();
+            }
+            if (tid == 0) rowptr[n] = m;
+
+            // ---- allocation 1b: lcol[m];  allocation 2: float scratch of the work item ----
+            const int64_t words2 = ((int64_t)m + 31) & ~int64_t(31);
+            const int64_t words3 = (item_words(S3_FLOW_POS, K, n) + 31) & ~int64_t(31);
+            if (tid == 0) s_base = (long long)atomicAdd(&p.counters[S3_CTR_CURSOR], (unsigned long long)(words2 + words3));
+            __syncthreads();
+            base2 = p.slab_words + s_base;
+            base3 = base2 + words2;
+            overflow = base3 + words3 > p.arena_words;
+
+            if (!overflow) {
+                int32_t* lcol = p.arena + base2;
+                // ---- fill pass: same intersections, ballot-ordered ----
+                for (int j = wid; j < n; j += NWARP) {
+                    const int g = nodes[j];
+                    const int64_t e0 = p.indptr[g];
+                    const int d = (int)(p.indptr[g + 1] - e0);
+                    const int32_t* __restrict__ Nj = p.indices + e0;
+                    const bool by_nodes = (int64_t)n * (32 - __clz(d | 1)) * 2 < d;
+                    int outp = rowptr[j];
+                    if (!by_nodes) {
+                        for (int e = lane; e < ((d + 31) & ~31); e += 32) {
+                            int lid = -1;
+                            if (e < d) lid = lookup(nodes, n, u, v, Nj[e]);
+                            const bool ok = lid >= 0 && !((j == 0 && lid == 1) || (j == 1 && lid == 0));
+                            const unsigned ball = __ballot_sync(0xffffffffu, ok);
+                            if (ok) lcol[outp + __popc(ball & ((1u << lane) - 1u))] = lid;
+                            outp += __popc(ball);
+                        }
+                    } else {
+                        for (int t = lane; t < ((n + 31) & ~31); t += 32) {
+                            bool ok = false;
+                            if (t < n) ok = contains(Nj, d, nodes[t]) && !((j == 0 && t == 1) || (j == 1 && t == 0));
+                            const unsigned ball = __ballot_sync(0xffffffffu, ok);
+                            if (ok) lcol[outp + __popc(ball & ((1u << lane) - 1u))] = t;
+                            outp += __popc(ball);
+                        }
+                    }
+                }
+                __syncthreads();
+
+                // ---- diffusion of the target rows: K sweeps over every row (num_hops = 1 <= K) ----
+                float* item_f = reinterpret_cast<float*>(p.arena + base3);
+                float* lab = item_f;
+                float* wgt = item_f + NWP;
+                const bool z_shared = n * SC <= kZCapS;
+                float* zprev = z_shared ? s_z[0] : wgt + (int64_t)n * NWP;
+                float* znext = z_shared ? s_z[1] : wgt + (int64_t)n * NWP + (int64_t)n * SC;
+                for (int j = tid; j < n; j += T) {
+#pragma unroll
+                    for (int c = 0; c < SC; ++c) {
+                        float zv = 0.0f;
+                        if (j == c) {
+                            const int deg = rowlen[j];
+                            zv = deg > 0 ? 1.0f / sqrtf((float)deg) : 0.0f;
+                        }
+                        zprev[(int64_t)j * SC + c] = zv;
+                        znext[(int64_t)j * SC + c] = 0.0f;
+                    }
+                }
+                for (int i = tid; i < 2 * NWP; i += T) {
+                    const int j = i / NWP, q = i - j * NWP;
+                    wgt[i] = (q < SC && q == j) ? 1.0f : 0.0f;
+                }
+                __syncthreads();
+                for (int k = 1; k <= K; ++k) {
+                    const int nk = n;  // hop <= 1 <= k: every row
+                    for (int jb0 = 0; jb0 < nk; jb0 += NG) {
+                        const int j = jb0 + grp;
+                        const bool valid = j < nk;
+                        int e0 = 0, e1 = 0;
+                        if (valid) {
+                            e0 = rowptr[j];
+                            e1 = e0 + rowlen[j];
+                        }
+                        float t[SC];
+#pragma unroll
+                        for (int c = 0; c < SC; ++c) t[c] = 0.0f;
+                        for (int e = e0 + l8; e < e1; e += 8) {
+                            const int i = lcol[e];
+#pragma unroll
+                            for (int c = 0; c < SC; ++c) t[c] += zprev[(int64_t)i * SC + c];
+                        }
+#pragma unroll
+                        for (int c = 0; c < SC; ++c) {
+                            t[c] += __shfl_xor_sync(0xffffffffu, t[c], 4);
+                            t[c] += __shfl_xor_sync(0xffffffffu, t[c], 2);
+                            t[c] += __shfl_xor_sync(0xffffffffu, t[c], 1);
+                        }
+                        if (valid && l8 == 0) {
+                            const int deg = e1 - e0;
+                            const float dis = deg > 0 ? 1.0f / sqrtf((float)deg) : 0.0f;
+#pragma unroll
+                            for (int c = 0; c < SC; ++c) {
+                                const float w = dis * t[c];
+                                wgt[(int64_t)j * NWP + k * SC + c] = w;
+                                znext[(int64_t)j * SC + c] = dis * w;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    float* tmp = zprev;
+                    zprev = znext;
+                    znext = tmp;
+                }
+                for (int q = tid; q < NWP; q += T) lab[q] = q < NW ? wgt[q] + wgt[NWP + q] : 0.0f;
+            }
+        }
+
+        for (int d = 16; d > 0; d >>= 1) my_deg += __shfl_down_sync(0xffffffffu, my_deg, d);
+        if (lane == 0 && my_deg) atomicAdd(&p.counters[S3_CTR_SUM_D], my_deg);
+        __syncthreads();
+        if (tid == 0) {
+            off[S3_OFF_NODES] = base1;
+            off[S3_OFF_ROWPTR] = base1 + n;
+            off[S3_OFF_ROWLEN] = base1 + 2 * (int64_t)n + 1;
+            off[S3_OFF_LCOL] = base2;
+            off[S3_OFF_SEL] = base2;
+            off[S3_OFF_F32] = base3;
+            for (int i = 0; i < S3_NCNT; ++i) cnt[i] = 0;
+            cnt[S3_CNT_N] = n;
+            cnt[S3_CNT_M] = m;
+            cnt[S3_CNT_S] = overflow ? 0 : 2;
+            cnt[S3_CNT_STATUS] = overflow ? S3_REC_ARENA_OVERFLOW : S3_REC_OK;
+            cnt[S3_CNT_PARTNER] = -1;
+            cnt[S3_CNT_HOP0] = 2;
+            cnt[S3_CNT_HOP0 + 1] = n - 2;
+            cnt[S3_CNT_NSTORE] = n;
+            cnt[S3_CNT_CLASSPOS] = (int)atomicAdd(&p.counters[S3_CTR_CLASS0 + (31 - __clz(n))], 1ull);
+            if (overflow) atomicAdd(&p.counters[S3_CTR_ERRORS], 1ull);
+            atomicMax(&p.counters[S3_CTR_MAX_N], (unsigned long long)n);
+            atomicAdd(&p.counters[S3_CTR_SUM_N], (unsigned long long)n);
+        }
+    }
+}
+
+}  // namespace
+
+// defined in extract.cu
+cudaError_t launch_order(const s3_batch& b, int64_t num_records, cudaStream_t st);
+
+cudaError_t launch_extract_sorted(const s3_graph& g, const s3_batch& b, cudaStream_t st, int* rc_out) {
+    *rc_out = S3_OK;
+    SortedParams p;
+    p.indptr = g.indptr;
+    p.indices = g.indices;
+    p.num_nodes = g.num_nodes;
+    p.link_src = b.link_src;
+    p.link_dst = b.link_dst;
+    p.num_records = b.num_links;
+    p.sign_k = b.sign_k;
+    p.arena = b.arena;
+    p.arena_words = b.arena_words;
+    p.off = b.off;
+    p.cnt = b.cnt;
+    p.counters = reinterpret_cast<unsigned long long*>(b.counters);
+    if (p.num_records == 0) return cudaSuccess;
+    static int c_dev = -1, c_sms = 0, c_occ = 0;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev != c_dev) {
+        e = cudaDeviceGetAttribute(&c_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c_occ, front_sorted_kernel, kExtractThreads, 0);
+        if (e != cudaSuccess) return e;
+        c_dev = dev;
+    }
+    p.slab_stride = (2 * (g.max_degree + 1) + 31) & ~int64_t(31);
+    int64_t grid = (int64_t)c_sms * (c_occ > 0 ? c_occ : 1);
+    if (grid > p.num_records) grid = p.num_records;
+    const int64_t fit = (b.arena_words / 2) / p.slab_stride;
+    if (grid > fit) grid = fit;
+    if (grid < 1) {
+        *rc_out = S3_ERR_WORKSPACE;
+        return cudaSuccess;
+    }
+    p.slab_words = grid * p.slab_stride;
+    front_sorted_kernel<<<(unsigned)grid, kExtractThreads, 0, st>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess || !b.order) return e;
+    return launch_order(b, p.num_records, st);
+}
+
+}  // namespace s3

@@ -54,6 +54,7 @@ class DeviceGraph:
         self.num_nodes = int(A.shape[0])
         self.nnz = int(A.nnz)
         self.has_multi_edges = bool(A.nnz and A.data.max() > 1)
+        self.max_degree = int(np.diff(A.indptr).max()) if A.shape[0] else 0
         self.indptr = torch.from_numpy(A.indptr.astype(np.int64)).to(self.device)
         self.indices = torch.from_numpy(A.indices.astype(np.int32)).to(self.device)
         x = torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x, dtype=torch.float32)
@@ -65,7 +66,7 @@ class DeviceGraph:
         self.x[:, :self.num_feat].copy_(x, non_blocking=True)
         self.h2d_bytes = self.indptr.numel() * 8 + self.indices.numel() * 4 + x.numel() * 4
         self._c = L.Graph(_ptr(self.indptr), _ptr(self.indices), _ptr(self.x), self.num_nodes, self.num_feat,
-                          self.ldx, self.nnz)
+                          self.ldx, self.nnz, self.max_degree)
         self._arena = None
         self._arena2 = None
         self._streams = None
@@ -125,7 +126,7 @@ def _records_per_link(flow):
 
 
 def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_records=32768,
-               out=None, return_graphs=False, arena_words=None, stream=None, profile=None, overlap=False, defer=False, host_out=None):
+               out=None, return_graphs=False, arena_words=None, stream=None, profile=None, overlap=False, defer=False, host_out=None, force_sorted_tier=False):
     """Run the hot path for `links` ([2, L] int64, host or device) on `graph`.
 
     Returns PrecomputeResult with device tensors.  `out`, if given, is a list of K+1
@@ -191,13 +192,18 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
             words = max(1 << 22, min(min(int(batch_records), Lk * rpl) * 32768, free // 16))
             if graph._arena is not None:
                 words = max(words, graph._arena.numel())
-        words = max(words, 4 * int(lib.s3_min_arena_words(graph.num_nodes)))
+        batch_flags = (L.BATCH_STORE_ALL_ROWS if return_graphs else 0) | (L.BATCH_FORCE_SORTED_TIER if force_sorted_tier else 0)
+        probe = L.Batch(None, None, 0, cflow, cstrat, int(num_hops), K, batch_flags, 0, None, 0, None, None, None, None, None,
+                        None, None)
+        if lib.s3_extract_tier(C.byref(graph._c), C.byref(probe)) < 0:
+            L.check(L.S3_ERR_UNSUPPORTED, 's3_extract')
+        words = max(words, 4 * int(lib.s3_min_arena_words(C.byref(graph._c), C.byref(probe))))
         stats = dict(records=Lk * rpl, links=Lk, sum_n=0, sum_d=0, max_n=0, rows=0, retries=0, batches=nb, launches=0)
         pieces, row_counts, graphs = [], [], ([] if return_graphs else None)
 
         def make_batch(b0, b1, arena, off, cnt, ctr, row_ptr=None, item_ptr=None, item_rec=None, order=None):
             return L.Batch(_ptr(links[0, b0:b1]), _ptr(links[1, b0:b1]), b1 - b0, cflow, cstrat, int(num_hops), K,
-                           L.BATCH_STORE_ALL_ROWS if return_graphs else 0, 0, _ptr(arena), arena.numel(), _ptr(off), _ptr(cnt), _ptr(ctr),
+                           batch_flags, 0, _ptr(arena), arena.numel(), _ptr(off), _ptr(cnt), _ptr(ctr),
                            _ptr(row_ptr), _ptr(item_ptr), _ptr(item_rec), _ptr(order))
 
         def timed(stage, bi, fn, on=None):

@@ -43,7 +43,7 @@ def test_constants_match_header():
              'S3_CTR_ITEMS': L.CTR_ITEMS, 'S3_REC_BAD_LINK': L.REC_BAD_LINK, 'S3_ERR_NOT_IMPLEMENTED': L.S3_ERR_NOT_IMPLEMENTED}
     for k, v in pairs.items():
         assert int(defs[k]) == v, k
-    assert ctypes.sizeof(L.Graph) == 56 and ctypes.sizeof(L.Batch) == 120
+    assert ctypes.sizeof(L.Graph) == 64 and ctypes.sizeof(L.Batch) == 120
 
 
 def test_version_and_error_strings(lib):
@@ -60,10 +60,10 @@ def test_smem_sizing(lib):
 
 
 def test_argument_validation_without_gpu(lib):
-    g = L.Graph(0, 0, 0, 10, 4, 4, 20)
+    g = L.Graph(0, 0, 0, 10, 4, 4, 20, 5)
     b = L.Batch()
     assert lib.s3_extract(ctypes.byref(g), ctypes.byref(b), None) == L.S3_ERR_INVALID_ARG      # null graph arrays
-    g = L.Graph(16, 16, 16, 10, 4, 4, 20)
+    g = L.Graph(16, 16, 16, 10, 4, 4, 20, 5)
     b.flow, b.strategy, b.sign_k, b.num_hops = 7, 0, 3, 2
     assert lib.s3_extract(ctypes.byref(g), ctypes.byref(b), None) == L.S3_ERR_NOT_IMPLEMENTED  # unknown flow
     b.flow, b.strategy = L.FLOW_POS, 9

@@ -243,3 +243,61 @@ def test_pubmed_full_size_sample_and_properties():
     for k in range(4):
         full = res.xs[k].view(-1, 2, 501)[torch.from_numpy(pick).to(res.xs[k].device)]
         assert torch.equal(full, fwd.xs[k].view(-1, 2, 501))
+
+
+@pytest.mark.parametrize('seed,N,E,F,K', [(0, 300, 900, 9, 3), (1, 2000, 30000, 33, 3), (2, 500, 6000, 128, 5), (3, 64, 80, 4, 1)])
+def test_sorted_tier_against_oracle(seed, N, E, F, K):
+    """The large-graph extraction tier (sorted merge, num_hops = 1), forced on small graphs so the
+    oracle can check it: bit-exact indices, features within tolerance, and bit-identical to the
+    bitmap tier's operators is NOT required (different summation order) but both must agree."""
+    rng = np.random.default_rng(200 + seed)
+    A = _random_graph(rng, N, E)
+    hub = int(np.argmax(np.diff(A.indptr)))
+    X = rng.random((N, F), dtype=np.float32)
+    links = rng.integers(0, N, (2, 60))
+    links[0, :6] = hub                       # hub rows exercise the search-in-adjacency side
+    links = links[:, links[0] != links[1]]
+    ref = orc.pos_precompute(links, 1, A, X, K, None, keep_graphs=True)
+    g = DeviceGraph(A, X)
+    res = precompute(g, links, 1, K, 'PoS', None, return_graphs=True, force_sorted_tier=True)
+    for i, (gg, r) in enumerate(zip(res.graphs, ref['graphs'])):
+        _check_indices(gg, r, f'link {i}')
+    for k in range(K + 1):
+        assert_features_close(res.xs[k].cpu().numpy(), ref['xs'][k], what=f'x{k}')
+    bitmap = precompute(g, links, 1, K, 'PoS', None)
+    for k in range(K + 1):
+        assert_features_close(res.xs[k].cpu().numpy(), bitmap.xs[k].cpu().numpy(), tol=2e-6, what=f'tiers x{k}')
+
+
+def test_sorted_tier_on_reference_golden():
+    c = Case('tiny_pos_h1')
+    res = precompute(DeviceGraph(c.A, c.X), c.links, 1, c.K, 'PoS', None, force_sorted_tier=True)
+    for k in range(c.K + 1):
+        assert_features_close(res.xs[k].cpu().numpy(), c.xs[k], what=f'x{k}')
+
+
+def test_rmat_large_graph_uses_sorted_tier():
+    """A graph beyond the bitmap tier (1 M nodes): R-MAT, hub links included, against the oracle."""
+    import ctypes as C
+    from s3grl_b200 import _lib as L
+    edges = ds.rmat_edges(20, 1_000_000, seed=42)
+    N = 1 << 20
+    A = ds.adjacency(edges, N)
+    X = ds.synthetic_features(N, 16, 1.0, 43)
+    rng = np.random.default_rng(44)
+    deg = np.diff(A.indptr)
+    hubs = np.argsort(deg)[-1:]              # one hub link (n ~ 9 000): the oracle needs seconds for it
+    pos = edges[rng.choice(edges.shape[0], 30, replace=False)].T
+    neg = rng.integers(0, N, (2, 30))
+    hub_links = np.stack([hubs, A.indices[A.indptr[hubs]]])     # each hub with its first neighbour
+    links = np.concatenate([pos, neg[:, neg[0] != neg[1]], hub_links], axis=1)
+    g = DeviceGraph(A, X, check_symmetric=False)
+    probe = L.Batch(None, None, 0, L.FLOW_POS, 0, 1, 3, 0, 0, None, 0, None, None, None, None, None, None, None)
+    assert L.lib().s3_extract_tier(C.byref(g._c), C.byref(probe)) == 1
+    res = precompute(g, links, 1, 3)
+    ref = orc.pos_precompute(links, 1, A, X, 3, None, keep_graphs=True)
+    assert res.stats['max_n'] == max(gr['nodes'].size for gr in ref['graphs']) > 1000
+    for k in range(4):
+        assert_features_close(res.xs[k].cpu().numpy(), ref['xs'][k], what=f'rmat x{k}')
+    with pytest.raises(Exception):
+        precompute(g, links[:, :4], 2, 3)        # 2 hops on a graph of this size: unsupported

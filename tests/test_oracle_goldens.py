@@ -58,3 +58,17 @@ def test_float64_oracle_agrees():
     b = orc.pos_precompute(c.links[:, :30], c.num_hops, c.A, c.X, c.K, dtype=np.float64)
     for k in range(c.K + 1):
         assert_features_close(a['xs'][k], b['xs'][k], what=f'x{k}')
+
+
+def test_non_optimised_flow_is_an_independent_cross_check():
+    """Flow 9 (SIGN on every row, SpMM chain) and flow 6 (SpGEMM powers then 2 rows) are two
+    algebraically different routes; rows 0,1 must agree."""
+    c = Case('cora_pos')
+    for i in range(12):
+        src, dst = int(c.links[0, i]), int(c.links[1, i])
+        full = orc.sign_all_rows(src, dst, c.num_hops, c.A, c.X, c.K)
+        opt = orc.pos_link(src, dst, c.num_hops, c.A, c.X, c.K)
+        for k in range(c.K + 1):
+            assert_features_close(full[k][:2], opt['xs'][k], what=f'link {i} x{k}')
+            a, b = c.row_ptr[i], c.row_ptr[i + 1]
+            assert_features_close(full[k][:2], c.xs[k][a:b], what=f'link {i} x{k} vs reference golden')
