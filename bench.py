@@ -38,6 +38,10 @@ METRIC = "precomputed target links/sec (extract+diffuse+pool), PubMed PoS r=3"  
 UNIT = "links/s"
 
 
+def metric_name(workload):
+    return METRIC if workload == 'pubmed_pos' else f"precomputed target links/sec (extract+diffuse+pool), {workload}"
+
+
 # ----------------------------------------------------------------------------------------
 # workloads (host side, seeded; no file outside the repo is read)
 # ----------------------------------------------------------------------------------------
@@ -79,6 +83,48 @@ def build_workload(name):
         return dict(A=A, X=X, links=links, num_hops=3, K=3, flow='PoS', strategy=None,
                     desc=f"Cora (real X F=1433), all {links.shape[1]} links, PoS num_hops=3 sign_k=3")
     raise SystemExit(f"unknown workload {name}")
+
+
+def build_rmat_workload(args, dev):
+    """BASELINE config 5: R-MAT (0.57, 0.19, 0.19, 0.05), ids reduced mod N, symmetrised,
+    de-duplicated; F = 128 row-normalised features; half the targets are edges, half random pairs;
+    num_hops = 1, sign_k = 3.  Built on the GPU.  Targets are restricted to endpoints of degree <=
+    --rmat-degree-cap: the exact one-hop subgraph of a hub link has 10^4..10^5 nodes and ~10^8
+    adjacency entries to intersect (the reference only copes with such graphs through random
+    per-hop caps, which have no reproducible semantics), see DESIGN.md §6."""
+    import torch
+    from s3grl_b200 import DeviceGraph, datasets as ds
+    N, E, Lk, cap = args.rmat_nodes, args.rmat_edges, args.rmat_links, args.rmat_degree_cap
+    scale = int(np.ceil(np.log2(N)))
+    indptr, indices = ds.rmat_csr_torch(scale, E, N, seed=42, device=dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(43)
+    X = torch.rand((N, 128), device=dev, generator=gen)
+    X /= X.sum(1, keepdim=True)
+    deg = indptr[1:] - indptr[:-1]
+    gen.manual_seed(44)
+    nnz = indices.numel()
+    # positives: uniformly sampled stored entries (u, v) with both degrees <= cap
+    pos = torch.empty((2, 0), dtype=torch.int64, device=dev)
+    while pos.shape[1] < Lk // 2:
+        e = torch.randint(0, nnz, (Lk,), device=dev, generator=gen)
+        u = torch.searchsorted(indptr, e, right=True) - 1
+        v = indices[e].to(torch.int64)
+        ok = (deg[u] <= cap) & (deg[v] <= cap)
+        pos = torch.cat([pos, torch.stack([u[ok], v[ok]])], 1)
+    neg = torch.empty((2, 0), dtype=torch.int64, device=dev)
+    while neg.shape[1] < Lk - Lk // 2:
+        u = torch.randint(0, N, (Lk,), device=dev, generator=gen)
+        v = torch.randint(0, N, (Lk,), device=dev, generator=gen)
+        ok = (u != v) & (deg[u] <= cap) & (deg[v] <= cap)
+        neg = torch.cat([neg, torch.stack([u[ok], v[ok]])], 1)
+    links = torch.cat([pos[:, :Lk // 2], neg[:, :Lk - Lk // 2]], 1).contiguous()
+    g = DeviceGraph.from_device_csr(indptr, indices, X)
+    desc = (f"synthetic R-MAT (0.57,0.19,0.19,0.05) scale {scale}, N={N}, {E} edge samples -> nnz={nnz}, max degree "
+            f"{g.max_degree}; X F=128 uniform row-normalised; {Lk} targets (half edges, half random pairs) with endpoint "
+            f"degree <= {cap}; PoS num_hops=1 sign_k=3; graph and targets generated on the GPU (seeds 42/43/44)")
+    return dict(graph=g, links_dev=links, links=links.cpu().numpy(), num_hops=1, K=3, flow='PoS', strategy=None, desc=desc,
+                A=None, X=None)
 
 
 # ----------------------------------------------------------------------------------------
@@ -133,7 +179,7 @@ def run_reference_arm(args, w, rank, world):
     value = cols.size * args.steps / t
     sample = (f"{cols.size} links sampled uniformly (seed 123) from the workload's {w['links'].shape[1]}, "
               f"per step; links are independent, so links/s extrapolates linearly")
-    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+    line = dict(metric=metric_name(args.workload), value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1000 * t / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32", data="synthetic", impl="reference",
                 config=dict(workload=w['desc'], links_per_step=int(cols.size)),
@@ -202,20 +248,30 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--rmat-nodes', type=int, default=10_000_000)
+    ap.add_argument('--rmat-edges', type=int, default=200_000_000)
+    ap.add_argument('--rmat-links', type=int, default=4_000_000)
+    ap.add_argument('--rmat-degree-cap', type=int, default=512)
     ap.add_argument('--overlap', action='store_true', help='two-stream front/back overlap (measured slower on PubMed: L2 contention)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
-    w = build_workload(args.workload)
+    is_rmat = args.workload == 'rmat'
+    w = None if is_rmat else build_workload(args.workload)
 
     if args.impl == 'reference':
+        if is_rmat:
+            if rank == 0:
+                print(json.dumps(dict(impl="reference", unavailable="the rmat workload is generated on the GPU; run the "
+                                      "default PubMed workload for the reference arm")))
+            return
         run_reference_arm(args, w, rank, world)
         return
 
     # CPU baseline first: the fork pool must not inherit an initialised CUDA context
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not is_rmat:
         cols, procs = cpu_sample(w, args.cpu_links_per_core)
         t = cpu_pass(w, cols, procs)
         cpu = dict(value=cols.size / t, unit=UNIT, cores=procs, kind="port",
@@ -237,13 +293,31 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    if is_rmat:
+        w = build_rmat_workload(args, dev)
+        args.no_e2e = True          # the host-facing call would re-upload a 7 GB graph every step
     links_host = w['links']
     if world > 1:   # weak scaling: same link set per rank, rank-specific order
         links_host = links_host[:, np.random.default_rng(1000 + rank).permutation(links_host.shape[1])]
     Lk = links_host.shape[1]
-    K, F = w['K'], w['X'].shape[1]
-    g = DeviceGraph(w['A'], w['X'], device=dev)
+    K = w['K']
+    g = w['graph'] if is_rmat else DeviceGraph(w['A'], w['X'], device=dev)
+    F = g.num_feat
     links_dev = torch.from_numpy(np.ascontiguousarray(links_host)).to(dev)
+    if is_rmat and not args.no_cpu_baseline and rank == 0 and world == 1:
+        # single-process oracle on a small sample (the fork pool cannot be used once CUDA is up)
+        import scipy.sparse as ssp
+        from oracle import s3grl_oracle as orc
+        A_host = ssp.csr_matrix((np.ones(g.nnz, np.int8), g.indices.cpu().numpy(), g.indptr.cpu().numpy()),
+                                shape=(g.num_nodes, g.num_nodes))
+        X_host = g.x[:, :F].cpu().numpy()
+        cols = np.random.default_rng(123).choice(Lk, min(Lk, 200), replace=False)
+        t0 = time.perf_counter()
+        orc.pos_precompute(links_host[:, cols], 1, A_host, X_host, K)
+        dt = time.perf_counter() - t0
+        cpu = dict(value=cols.size / dt, unit=UNIT, cores=1, kind="port",
+                   sample=f"{cols.size} links sampled uniformly (seed 123), one pass, {dt:.1f} s; single-process oracle port")
+        del A_host, X_host
     fixed = w['strategy'] is None
     out = [torch.empty((2 * Lk, F + 1), dtype=torch.float32, device=dev) for _ in range(K + 1)] if fixed else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
@@ -380,11 +454,12 @@ def main():
                        "-> host tensors (S3GRL_OUTPUT_DEVICE=cpu)")
 
     if rank == 0:
-        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+        line = dict(metric=metric_name(args.workload), value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=ms_max / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="f32", data="synthetic",
                     config=dict(workload=w['desc'], links_per_step_per_gpu=Lk, batch_records=args.batch_records,
-                                l2="flushed between steps (256 MiB memset); within a step X (39 MB) is L2-resident by nature of the workload",
+                                l2="flushed between steps (256 MiB memset); PubMed's X (39 MB) is L2-resident within a step by "
+                                   "nature of the workload, the R-MAT X (5 GB) is not",
                                 parallelism=f"links sharded x{world}, graph replicated, no data-path collective"),
                     clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu,
                     host_enqueue_ms_per_step=host_enqueue_ms,

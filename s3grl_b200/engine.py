@@ -87,6 +87,34 @@ class DeviceGraph:
             return 1024
         return (f4 + 383) // 384 * 384 * 4
 
+    @classmethod
+    def from_device_csr(cls, indptr, indices, x):
+        """Wrap a CSR that already lives on the GPU (int64 indptr, int32 indices with ascending unique
+        columns, symmetric pattern — not checked) and features [N, F] on the same device."""
+        self = cls.__new__(cls)
+        self.device = indptr.device
+        L.lib()
+        self.num_nodes = int(indptr.numel() - 1)
+        self.nnz = int(indices.numel())
+        self.has_multi_edges = False
+        self.max_degree = int((indptr[1:] - indptr[:-1]).max()) if self.num_nodes else 0
+        self.indptr = indptr.to(torch.int64).contiguous()
+        self.indices = indices.to(torch.int32).contiguous()
+        self.num_feat = int(x.shape[1])
+        self.ldx = cls.padded_row_stride(self.num_feat)
+        if x.shape[1] == self.ldx and x.is_contiguous() and x.dtype == torch.float32:
+            self.x = x
+        else:
+            self.x = torch.zeros((self.num_nodes, self.ldx), dtype=torch.float32, device=self.device)
+            self.x[:, :self.num_feat].copy_(x)
+        self.h2d_bytes = 0
+        self._c = L.Graph(_ptr(self.indptr), _ptr(self.indices), _ptr(self.x), self.num_nodes, self.num_feat,
+                          self.ldx, self.nnz, self.max_degree)
+        self._arena = None
+        self._arena2 = None
+        self._streams = None
+        return self
+
     # scratch arenas (int32 words), grown on demand and kept across calls; the second one is
     # only allocated by the overlapped (two-stream, double-buffered) schedule
     def arena(self, words, slot=0):
