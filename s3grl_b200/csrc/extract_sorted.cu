@@ -34,7 +34,7 @@ struct SortedParams {
     const int64_t* __restrict__ link_src;
     const int64_t* __restrict__ link_dst;
     int64_t num_records;
-    int sign_k;
+    int sign_k, store_all;
     int32_t* arena;
     int64_t arena_words;
     int64_t slab_stride;  // words per CTA slab: prefix arrays of both adjacency lists
@@ -44,8 +44,10 @@ struct SortedParams {
     unsigned long long* counters;
 };
 
-constexpr int kNodeCap = 6144;  // nodes cached in shared memory (24 KB)
-constexpr int kZCapS = 2048;    // floats per shared z buffer
+constexpr int kNodeCap = 2048;  // nodes cached in shared memory (8 KB)
+constexpr int kZCapS = 2048;    // floats per shared z buffer (2 buffers; also scratch for the big-node list)
+constexpr int kBitCap = 2048;   // subgraphs up to this many nodes use the n x n bit-matrix path
+constexpr int kMCapS = 3072;    // bit-matrix words kept in shared memory (n <= 313), else in the arena
 
 // number of elements of the ascending array a[0..n) that are < x
 __device__ __forceinline__ int lower_bound(const int32_t* __restrict__ a, int n, int x) {
@@ -70,6 +72,227 @@ __device__ __forceinline__ int lookup(const int32_t* nodes, int n, int u, int v,
     return (p < n - 2 && nodes[2 + p] == c) ? 2 + p : -1;
 }
 
+
+// ---- bit-matrix path (n <= kBitCap) ---------------------------------------------------------
+// The induced adjacency is an n x n symmetric bit matrix M. Every unordered pair is decided ONCE
+// and both bits are set:
+//   * a "small" node j (deg_G <= 2n) streams its adjacency list and looks every entry up in S;
+//   * a pair of "big" nodes is decided by one binary search of the one in the adjacency list of
+//     the other (the shorter list) — flat over all threads of the CTA, no per-row imbalance.
+// The K sweeps then run straight over the bit rows (ascending local id: the canonical order), so
+// no CSR is materialised unless a dump asks for it.
+struct BitCtx {
+    const int32_t* nodes;  // shared
+    int n, u, v;
+    int* s_deg;            // [kBitCap] shared
+    uint32_t* s_M;         // [kMCapS] shared
+    float* s_z;            // [2 * kZCapS] shared
+    int* s_scan;
+    long long* s_base;
+};
+
+__device__ __forceinline__ bool bitmatrix_record(const SortedParams& p, const BitCtx& cx, int32_t* rowptr, int32_t* rowlen,
+                                                 int& m_out, int64_t& base2, int64_t& base3, unsigned long long& my_deg) {
+    constexpr int SC = 2;
+    const int T = kExtractThreads, tid = threadIdx.x, K = p.sign_k;
+    const int lane = tid & 31, wid = tid >> 5, l8 = tid & 7, grp = tid >> 3;
+    constexpr int NG = kExtractThreads / 8, NWARP = kExtractThreads / 32;
+    const int NW = (K + 1) * SC, NWP = (NW + 3) & ~3;
+    const int n = cx.n, u = cx.u, v = cx.v;
+    const int32_t* nodes = cx.nodes;
+    const int nw = (n + 31) >> 5;
+    const int mwords = n * nw;
+    const bool m_shared = mwords <= kMCapS;
+
+    // allocation: [bit matrix, when it does not fit in shared memory] [float scratch of the work item]
+    const int64_t wordsM = m_shared ? 0 : (((int64_t)mwords + 31) & ~int64_t(31));
+    const int64_t wordsF = (item_words(S3_FLOW_POS, K, n) + 31) & ~int64_t(31);
+    __syncthreads();
+    if (tid == 0) *cx.s_base = (long long)atomicAdd(&p.counters[S3_CTR_CURSOR], (unsigned long long)(wordsM + wordsF));
+    __syncthreads();
+    const int64_t baseM = p.slab_words + *cx.s_base;
+    base3 = baseM + wordsM;
+    if (base3 + wordsF > p.arena_words) return true;  // overflow
+    uint32_t* M = m_shared ? cx.s_M : reinterpret_cast<uint32_t*>(p.arena + baseM);
+    for (int i = tid; i < mwords; i += T) M[i] = 0u;
+
+    // global degrees; list of big nodes (scratch: the z buffers, not live yet)
+    int* s_big = reinterpret_cast<int*>(cx.s_z);
+    const int tau = 2 * n;
+    int nb = 0;
+    for (int base = 0; base < n; base += T) {
+        const int j = base + tid;
+        int d = 0, big = 0;
+        if (j < n) {
+            const int g = nodes[j];
+            d = (int)(p.indptr[g + 1] - p.indptr[g]);
+            cx.s_deg[j] = d;
+            my_deg += (unsigned long long)d;
+            big = d > tau ? 1 : 0;
+        }
+        int tot;
+        const int ex = block_exclusive_scan(big, cx.s_scan, &tot);
+        if (big) s_big[nb + ex] = j;
+        nb += tot;
+        __syncthreads();
+    }
+
+    // phase A: small rows stream their adjacency list
+    for (int j = wid; j < n; j += NWARP) {
+        const int d = cx.s_deg[j];
+        if (d > tau) continue;
+        const int32_t* __restrict__ Nj = p.indices + p.indptr[nodes[j]];
+        for (int e = lane; e < d; e += 32) {
+            const int lid = lookup(nodes, n, u, v, Nj[e]);
+            if (lid >= 0) {
+                atomicOr(&M[j * nw + (lid >> 5)], 1u << (lid & 31));
+                atomicOr(&M[lid * nw + (j >> 5)], 1u << (j & 31));
+            }
+        }
+    }
+    // phase B: big-big pairs, one binary search each, in the shorter of the two lists
+    for (int q = tid; q < nb * nb; q += T) {
+        const int ia = q / nb, ib = q - ia * nb;
+        if (ia >= ib) continue;
+        int ja = s_big[ia], jb = s_big[ib];
+        if (cx.s_deg[ja] > cx.s_deg[jb]) {
+            const int t = ja;
+            ja = jb;
+            jb = t;
+        }
+        const int ga = nodes[ja];  // search g_b in N(g_a), the shorter list
+        if (contains(p.indices + p.indptr[ga], cx.s_deg[ja], nodes[jb])) {
+            atomicOr(&M[ja * nw + (jb >> 5)], 1u << (jb & 31));
+            atomicOr(&M[jb * nw + (ja >> 5)], 1u << (ja & 31));
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {  // mask the target link (utils.py:79-80)
+        M[0 * nw + 0] &= ~2u;
+        M[1 * nw + 0] &= ~1u;
+    }
+    __syncthreads();
+    // induced degrees
+    int my_m = 0;
+    for (int j = tid; j < n; j += T) {
+        int c = 0;
+        for (int w = 0; w < nw; ++w) c += __popc(M[j * nw + w]);
+        cx.s_deg[j] = c;
+        my_m += c;
+    }
+    __syncthreads();
+
+    // optional CSR for dumps: rowlen, rowptr, lcol (ascending local id)
+    base2 = base3;
+    m_out = 0;
+    if (p.store_all) {
+        int m = 0;
+        for (int base = 0; base < n; base += T) {
+            const int j = base + tid;
+            const int d = j < n ? cx.s_deg[j] : 0;
+            int tot;
+            const int ex = block_exclusive_scan(d, cx.s_scan, &tot);
+            if (j < n) {
+                rowptr[j] = m + ex;
+                rowlen[j] = d;
+            }
+            m += tot;
+            __syncthreads();
+        }
+        if (tid == 0) rowptr[n] = m;
+        m_out = m;
+        const int64_t wordsC = ((int64_t)m + 31) & ~int64_t(31);
+        if (tid == 0) *cx.s_base = (long long)atomicAdd(&p.counters[S3_CTR_CURSOR], (unsigned long long)wordsC);
+        __syncthreads();
+        base2 = p.slab_words + *cx.s_base;
+        if (base2 + wordsC > p.arena_words) return true;
+        int32_t* lcol = p.arena + base2;
+        for (int j = tid; j < n; j += T) {  // one thread per row: dumps are not on the hot path
+            int o = rowptr[j];
+            for (int w = 0; w < nw; ++w) {
+                uint32_t bits = M[j * nw + w];
+                while (bits) {
+                    const int b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    lcol[o++] = w * 32 + b;
+                }
+            }
+        }
+        __syncthreads();
+    } else {
+        for (int d = 16; d > 0; d >>= 1) my_m += __shfl_down_sync(0xffffffffu, my_m, d);
+        m_out = 0;  // not reduced across the block: CNT_M is exact only for dumps
+    }
+
+    // ---- diffusion of the target rows over the bit rows ----
+    float* item_f = reinterpret_cast<float*>(p.arena + base3);
+    float* lab = item_f;
+    float* wgt = item_f + NWP;
+    const bool z_shared = n * SC <= kZCapS;
+    float* zprev = z_shared ? cx.s_z : wgt + (int64_t)n * NWP;
+    float* znext = z_shared ? cx.s_z + kZCapS : wgt + (int64_t)n * NWP + (int64_t)n * SC;
+    __syncthreads();  // s_big (aliasing the z buffers) is dead
+    for (int j = tid; j < n; j += T) {
+#pragma unroll
+        for (int c = 0; c < SC; ++c) {
+            float zv = 0.0f;
+            if (j == c) {
+                const int deg = cx.s_deg[j];
+                zv = deg > 0 ? 1.0f / sqrtf((float)deg) : 0.0f;
+            }
+            zprev[(int64_t)j * SC + c] = zv;
+            znext[(int64_t)j * SC + c] = 0.0f;
+        }
+    }
+    for (int i = tid; i < 2 * NWP; i += T) {
+        const int j = i / NWP, q = i - j * NWP;
+        wgt[i] = (q < SC && q == j) ? 1.0f : 0.0f;
+    }
+    __syncthreads();
+    for (int k = 1; k <= K; ++k) {
+        for (int jb0 = 0; jb0 < n; jb0 += NG) {
+            const int j = jb0 + grp;
+            const bool valid = j < n;
+            float t[SC];
+#pragma unroll
+            for (int c = 0; c < SC; ++c) t[c] = 0.0f;
+            if (valid) {
+                for (int w = l8; w < nw; w += 8) {
+                    uint32_t bits = M[j * nw + w];
+                    while (bits) {
+                        const int i = w * 32 + __ffs(bits) - 1;
+                        bits &= bits - 1;
+#pragma unroll
+                        for (int c = 0; c < SC; ++c) t[c] += zprev[(int64_t)i * SC + c];
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < SC; ++c) {
+                t[c] += __shfl_xor_sync(0xffffffffu, t[c], 4);
+                t[c] += __shfl_xor_sync(0xffffffffu, t[c], 2);
+                t[c] += __shfl_xor_sync(0xffffffffu, t[c], 1);
+            }
+            if (valid && l8 == 0) {
+                const int deg = cx.s_deg[j];
+                const float dis = deg > 0 ? 1.0f / sqrtf((float)deg) : 0.0f;
+#pragma unroll
+                for (int c = 0; c < SC; ++c) {
+                    const float w = dis * t[c];
+                    wgt[(int64_t)j * NWP + k * SC + c] = w;
+                    znext[(int64_t)j * SC + c] = dis * w;
+                }
+            }
+        }
+        __syncthreads();
+        float* tmp = zprev;
+        zprev = znext;
+        znext = tmp;
+    }
+    for (int q = tid; q < NWP; q += T) lab[q] = q < NW ? wgt[q] + wgt[NWP + q] : 0.0f;
+    return false;
+}
+
 __global__ void __launch_bounds__(kExtractThreads, 3) front_sorted_kernel(SortedParams p) {
     const int T = kExtractThreads, tid = threadIdx.x, K = p.sign_k;
     constexpr int SC = 2;
@@ -81,6 +304,8 @@ __global__ void __launch_bounds__(kExtractThreads, 3) front_sorted_kernel(Sorted
     __shared__ long long s_rec;
     __shared__ int s_nodes[kNodeCap];
     __shared__ float s_z[2][kZCapS];
+    __shared__ int s_deg[kBitCap];
+    __shared__ uint32_t s_M[kMCapS];
 
     int32_t* PA = p.arena + (int64_t)blockIdx.x * p.slab_stride;  // [du + 1]
 
@@ -181,6 +406,20 @@ __global__ void __launch_bounds__(kExtractThreads, 3) front_sorted_kernel(Sorted
             __syncthreads();
             const int32_t* nodes = cached ? s_nodes : nodes_g;
 
+            if (n <= kBitCap) {
+                BitCtx cx;
+                cx.nodes = s_nodes;
+                cx.n = n;
+                cx.u = u;
+                cx.v = v;
+                cx.s_deg = s_deg;
+                cx.s_M = s_M;
+                cx.s_z = &s_z[0][0];
+                cx.s_scan = s_scan;
+                cx.s_base = &s_base;
+                overflow = bitmatrix_record(p, cx, rowptr, rowlen, m, base2, base3, my_deg);
+            } else {
+            // ======== large subgraphs: per-row intersections, exact count -> scan -> fill ========
             // ---- count pass: |N(g_j) ∩ S| minus the masked target link, one warp per row ----
             for (int j = wid; j < n; j += NWARP) {
                 const int g = nodes[j];
@@ -325,6 +564,7 @@ __global__ void __launch_bounds__(kExtractThreads, 3) front_sorted_kernel(Sorted
                 }
                 for (int q = tid; q < NWP; q += T) lab[q] = q < NW ? wgt[q] + wgt[NWP + q] : 0.0f;
             }
+            }  // per-row path
         }
 
         for (int d = 16; d > 0; d >>= 1) my_deg += __shfl_down_sync(0xffffffffu, my_deg, d);
@@ -345,7 +585,7 @@ __global__ void __launch_bounds__(kExtractThreads, 3) front_sorted_kernel(Sorted
             cnt[S3_CNT_PARTNER] = -1;
             cnt[S3_CNT_HOP0] = 2;
             cnt[S3_CNT_HOP0 + 1] = n - 2;
-            cnt[S3_CNT_NSTORE] = n;
+            cnt[S3_CNT_NSTORE] = (n <= kBitCap && !p.store_all) ? 0 : n;  // bit-matrix records keep no CSR
             cnt[S3_CNT_CLASSPOS] = (int)atomicAdd(&p.counters[S3_CTR_CLASS0 + (31 - __clz(n))], 1ull);
             if (overflow) atomicAdd(&p.counters[S3_CTR_ERRORS], 1ull);
             atomicMax(&p.counters[S3_CTR_MAX_N], (unsigned long long)n);
@@ -369,6 +609,7 @@ cudaError_t launch_extract_sorted(const s3_graph& g, const s3_batch& b, cudaStre
     p.link_dst = b.link_dst;
     p.num_records = b.num_links;
     p.sign_k = b.sign_k;
+    p.store_all = (b.flags & S3_BATCH_STORE_ALL_ROWS) ? 1 : 0;
     p.arena = b.arena;
     p.arena_words = b.arena_words;
     p.off = b.off;
