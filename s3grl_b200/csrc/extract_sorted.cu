@@ -293,7 +293,7 @@ __device__ __forceinline__ bool bitmatrix_record(const SortedParams& p, const Bi
     return false;
 }
 
-__global__ void __launch_bounds__(kExtractThreads, 3) front_sorted_kernel(SortedParams p) {
+__global__ void __launch_bounds__(kExtractThreads, 4) front_sorted_kernel(SortedParams p) {
     const int T = kExtractThreads, tid = threadIdx.x, K = p.sign_k;
     constexpr int SC = 2;
     const int lane = tid & 31, wid = tid >> 5, l8 = tid & 7, grp = tid >> 3;
