@@ -210,6 +210,10 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
             else:
                 assert len(out) == K + 1 and all(o.shape[0] >= R and o.shape[1] == F1 and o.is_contiguous() for o in out)
             out_ptrs = (C.c_void_p * (K + 1))(*[o.data_ptr() for o in out])
+        if not fixed_rows:
+            # data-dependent row counts: every batch ends in a host sync and keeps its own output
+            # pieces, and CCN work items multiply the float scratch — smaller batches
+            batch_records = min(int(batch_records), 4096)
         batch_links = max(1, int(batch_records) // rpl)
         nb = (Lk + batch_links - 1) // batch_links
         counters = torch.zeros((max(nb, 1), L.NCTR), dtype=torch.int64, device=dev)
@@ -368,9 +372,10 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
             nonlocal words
             stats['retries'] += 1
             words = int(words * 2)
+            graph._arena = graph._arena2 = None       # hand the old arenas back to the driver first
+            torch.cuda.empty_cache()
             free, _ = torch.cuda.mem_get_info(dev)
-            have = graph._arena.numel() * 4 if graph._arena is not None else 0
-            if words * 4 > free + have:
+            if words * 4 > free:
                 raise MemoryError("scratch arena does not fit in device memory; lower batch_records")
 
         if fixed_rows:

@@ -301,3 +301,37 @@ def test_rmat_large_graph_uses_sorted_tier():
         assert_features_close(res.xs[k].cpu().numpy(), ref['xs'][k], what=f'rmat x{k}')
     with pytest.raises(Exception):
         precompute(g, links[:, :4], 2, 3)        # 2 hops on a graph of this size: unsupported
+
+
+def test_schedules_are_bit_identical():
+    """Synchronous, deferred, two-stream overlapped and host-pipelined runs give the same bits."""
+    c = Case('cora_pos')
+    g = DeviceGraph(c.A, c.X)
+    base = precompute(g, c.links, c.num_hops, c.K, batch_records=40)
+    deferred = precompute(g, c.links, c.num_hops, c.K, batch_records=40, defer=True).finalize()
+    overlapped = precompute(g, c.links, c.num_hops, c.K, batch_records=40, overlap=True)
+    host = [torch.empty((2 * c.L, c.X.shape[1] + 1), dtype=torch.float32, pin_memory=True) for _ in range(c.K + 1)]
+    piped = precompute(g, c.links, c.num_hops, c.K, batch_records=40, host_out=host)
+    for k in range(c.K + 1):
+        assert torch.equal(base.xs[k], deferred.xs[k]) and torch.equal(base.xs[k], overlapped.xs[k])
+        assert torch.equal(base.xs[k].cpu(), host[k]) and torch.equal(piped.xs[k], base.xs[k])
+    assert deferred.stats['sum_n'] == base.stats['sum_n'] > 0
+
+
+def test_sop_and_k5_through_reference_interface():
+    """get_SoP_prepped_ds mirror on host tensors, and K = 5 / num_hops = 2 (BASELINE config 4)."""
+    from s3grl_b200 import OptimizedSignOperations as Ops
+    c = Case('usair_sop')
+    out = Ops.get_SoP_prepped_ds([None] * c.K, torch.from_numpy(c.links), c.A, torch.from_numpy(c.X), 1)
+    assert len(out) == c.L and not out.xs[0].is_cuda
+    for k in range(c.K + 1):
+        assert_features_close(out.xs[k].numpy(), c.xs[k], what=f'sop x{k}')
+    c = Case('yeast_pos_k5')
+    kw = dict(sign_k=5, use_feature=True, sign_type='PoS', optimize_sign=True, k_heuristic=0, k_node_set_strategy=None)
+    out = Ops.get_PoS_prepped_ds(torch.from_numpy(c.links), 2, c.A, 1.0, None, False, None, torch.from_numpy(c.X), 0, kw, None)
+    for k in range(6):
+        assert_features_close(out.xs[k].numpy(), c.xs[k], what=f'yeast x{k}')
+    with pytest.raises(NotImplementedError):
+        Ops.get_PoS_prepped_ds(torch.from_numpy(c.links), 2, c.A, 0.5, None, False, None, torch.from_numpy(c.X), 0, kw, None)
+    with pytest.raises(NotImplementedError):
+        Ops.get_PoS_prepped_ds(torch.from_numpy(c.links), 2, c.A, 1.0, 50, False, None, torch.from_numpy(c.X), 0, kw, None)
