@@ -58,8 +58,8 @@ struct ExtractParams {
     unsigned long long* counters;
 };
 
-constexpr int kRowCap = 2560;  // rows whose (start, adjacency offset) are cached in shared memory
-constexpr int kZCap = 2048;    // floats per shared z buffer
+constexpr int kRowCap = 1536;  // rows whose (start, adjacency offset) are cached in shared memory
+constexpr int kZCap = 1024;    // floats per shared z buffer
 
 __device__ __forceinline__ bool test_bit(const uint32_t* bm, int g) { return (bm[g >> 5] >> (g & 31)) & 1u; }
 
@@ -81,7 +81,7 @@ __device__ __forceinline__ int local_id(int g, int s0, int s1, int nseed, const 
 }
 
 template <int SC>  // selected rows of the first work item == number of seeds: 2 (PoS), 1 (SoP)
-__global__ void __launch_bounds__(kExtractThreads, 4) front_kernel(ExtractParams p) {
+__global__ void __launch_bounds__(kExtractThreads, 5) front_kernel(ExtractParams p) {
     extern __shared__ uint32_t sm[];
     const int W = p.W, h = p.radius, T = kExtractThreads, tid = threadIdx.x, K = p.sign_k;
     constexpr int nseed = SC;

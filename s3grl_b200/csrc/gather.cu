@@ -155,8 +155,12 @@ struct RangeDispatch<K1, SC, C, K1, FULL> {
     __device__ __forceinline__ static void run(int, float4 (&)[K1 * SC][C], int, int, const GatherCtx<C>&) {}
 };
 
+// Occupancy target by accumulator footprint (K1*SC*C float4 per thread): the kernel is latency /
+// L2-throughput bound, and 8 CTAs of 4 warps per SM stream 16 TB/s where 5 CTAs streamed 12 TB/s.
+constexpr int gather_min_blocks(int acc4) { return acc4 <= 8 ? 8 : acc4 <= 12 ? 6 : acc4 <= 16 ? 5 : acc4 <= 24 ? 3 : 2; }
+
 template <int K1, int SC, int C, bool FULL>
-__global__ void __launch_bounds__(kGatherThreads) gather_kernel(GatherParams p) {
+__global__ void __launch_bounds__(kGatherThreads, gather_min_blocks(K1 * SC * C)) gather_kernel(GatherParams p) {
     constexpr int NW = K1 * SC, NWP = (NW + 3) & ~3;
     extern __shared__ float4 smem4[];
     float* s_w = reinterpret_cast<float*>(smem4);                        // [kTile][NWP]
