@@ -21,7 +21,7 @@
  *                 tuned_SIGN.py:228-238 and tuned_SIGN.py:155-175 for rows [0,1].
  *   s3_plan     : row_ptr / work-item lists from the per-record selected-row counts
  *                 (the slices PyG's collate would record, sgrl_link_pred.py:204).
- *   s3_diffuse  : per LATER work item (PoS Plus CCN rows; a no-op otherwise),
+ *   s3_diffuse  : per CCN work item (PoS Plus: up to 8 extra selected rows of a record),
  *                 S = D^-1/2 A_sub D^-1/2 and the K row vectors e_sel^T S^k
  *                 replaces tuned_SIGN.py:155-175 (normalise, SpGEMM powers, row select)
  *                 and, in SoP flow, sgrl_link_pred.py:161-178 + tuned_SIGN.py:60-86, :106-113.
@@ -100,7 +100,7 @@ extern "C" {
 #define S3_CTR_CURSOR 0    /* arena words requested so far (may exceed the capacity)      */
 #define S3_CTR_ERRORS 1    /* number of records whose status != S3_REC_OK                 */
 #define S3_CTR_ROWS 2      /* total selected rows   (written by s3_plan)                  */
-#define S3_CTR_ITEMS 3     /* total work items      (written by s3_plan)                  */
+#define S3_CTR_ITEMS 3     /* total CCN work items: 8 extra selected rows each (s3_plan)  */
 #define S3_CTR_MAX_N 4     /* largest subgraph in the batch                               */
 #define S3_CTR_SUM_N 5     /* sum of n  (roofline accounting: 4*F*sum_n feature bytes)    */
 #define S3_CTR_SUM_D 6     /* sum over subgraph nodes of their global degree (4*D bytes)  */
@@ -150,11 +150,11 @@ typedef struct s3_batch {
      * (PoS with S3_STRATEGY_NONE, SoP): then record r is work item r and owns output rows
      * [r*num_seeds, (r+1)*num_seeds). */
     int64_t* row_ptr;        /* [num_records + 1] output-row offset of each record          */
-    int64_t* item_ptr;       /* [num_records + 1] first work item of each record            */
-    int32_t* item_rec;       /* [total items] record of each work item                      */
+    int64_t* item_ptr;       /* [num_records + 1] first CCN work item of each record        */
+    int32_t* item_rec;       /* [total CCN items] record of each CCN work item              */
     /* Optional [num_records]: s3_extract fills it with the records in descending size class
      * (largest subgraphs first) and s3_gather schedules its CTAs in that order, which trims the
-     * tail of the launch. Results do not depend on it. Used only when item_rec is NULL. */
+     * tail of the launch. Results do not depend on it. */
     int32_t* order;
 } s3_batch;
 
@@ -186,11 +186,16 @@ int s3_plan(const s3_batch* b, void* stream);
 int s3_plan_items(const s3_batch* b, void* stream);
 int s3_diffuse(const s3_graph* g, const s3_batch* b, int64_t num_items, void* stream);
 
-/* out: HOST array of sign_k+1 device pointers; out[k], k = 0..sign_k to the operator matrices, [*, ldo] row-major
+/* s3_gather writes the rows of the records themselves (row 0 = src, row 1 = dst; SoP: one row per
+ * record), one CTA per record; s3_gather_ccn writes the CCN rows of PoS Plus, one CTA per CCN
+ * work item (s3_plan / s3_plan_items).
+ * out: HOST array of sign_k+1 device pointers; out[k], k = 0..sign_k to the operator matrices, [*, ldo] row-major
  * float32; record r's rows land at row_base + row_ptr[r] .. ; column 0 is the label /
  * self-return column, columns 1..F the features (reference tuned_SIGN.py:177-187). */
-int s3_gather(const s3_graph* g, const s3_batch* b, int64_t num_items,
+int s3_gather(const s3_graph* g, const s3_batch* b, int64_t num_records,
               float* const* out, int64_t ldo, int64_t row_base, void* stream);
+int s3_gather_ccn(const s3_graph* g, const s3_batch* b, int64_t num_items,
+                  float* const* out, int64_t ldo, int64_t row_base, void* stream);
 
 /* Optional dumps for parity checks: canonical global-id edge list of every record,
  * edges[e] = (global row, global col), e in [edge_ptr[r], edge_ptr[r+1]). */

@@ -15,7 +15,9 @@ CSRC = os.path.join(HERE, 'csrc')
 BUILD = os.path.join(HERE, '..', 'build')
 LIB_DIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIB_DIR, 'libs3grl_b200.so')
-SOURCES = ['extract.cu', 'extract_sorted.cu', 'plan.cu', 'diffuse.cu', 'gather.cu', 'c_abi.cu']
+SOURCES = ['extract.cu', 'extract_sorted.cu', 'plan.cu', 'diffuse.cu', 'gather.cu', 'gather_sc1_lo.cu', 'gather_sc1_mid.cu',
+           'gather_sc1_hi.cu', 'gather_sc2_lo.cu', 'gather_sc2_mid.cu', 'gather_sc2_hi.cu', 'gather_sc8_k2.cu', 'gather_sc8_k3.cu',
+           'gather_sc8_k4.cu', 'gather_sc8_k5.cu', 'gather_sc8_k6.cu', 'c_abi.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 
@@ -53,7 +55,7 @@ def build(force=False, verbose=False):
             raise RuntimeError(f"nvcc failed on {src}:\n{r.stderr[-4000:]}")
         return obj
 
-    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     cmd = [nvcc, '-shared', '-o', LIB, *objs, '-gencode', 'arch=compute_100a,code=sm_100a']
     r = subprocess.run(cmd, capture_output=True, text=True)

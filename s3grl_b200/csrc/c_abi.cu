@@ -119,8 +119,8 @@ int s3_diffuse(const s3_graph* g, const s3_batch* b, int64_t num_items, void* st
     return e == cudaSuccess ? S3_OK : cuda_fail(e);
 }
 
-int s3_gather(const s3_graph* g, const s3_batch* b, int64_t num_items, float* const* out, int64_t ldo, int64_t row_base,
-              void* stream) {
+static int gather_impl(const s3_graph* g, const s3_batch* b, int64_t num_items, float* const* out, int64_t ldo,
+                       int64_t row_base, int ccn, void* stream) {
     int rc = check_graph(g, true);
     if (rc != S3_OK) return rc;
     rc = check_batch(b);
@@ -132,8 +132,18 @@ int s3_gather(const s3_graph* g, const s3_batch* b, int64_t num_items, float* co
         if (!out[k]) return S3_ERR_INVALID_ARG;
         o.p[k] = out[k];
     }
-    cudaError_t e = s3::launch_gather(*g, *b, num_items, o, ldo, row_base, static_cast<cudaStream_t>(stream));
+    cudaError_t e = s3::launch_gather(*g, *b, num_items, o, ldo, row_base, ccn != 0, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? S3_OK : cuda_fail(e);
+}
+
+int s3_gather(const s3_graph* g, const s3_batch* b, int64_t num_records, float* const* out, int64_t ldo, int64_t row_base,
+              void* stream) {
+    return gather_impl(g, b, num_records, out, ldo, row_base, 0, stream);
+}
+
+int s3_gather_ccn(const s3_graph* g, const s3_batch* b, int64_t num_items, float* const* out, int64_t ldo, int64_t row_base,
+                  void* stream) {
+    return gather_impl(g, b, num_items, out, ldo, row_base, 1, stream);
 }
 
 int s3_dump_edges(const s3_batch* b, const int64_t* edge_ptr, int32_t* edges_out, void* stream) {

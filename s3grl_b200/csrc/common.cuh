@@ -53,6 +53,17 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int* 
     return out;
 }
 
+// PoS Plus: the CCN rows (selected rows beyond the seeds) are processed kCcnRows at a time as
+// extra work items of the record; their scratch follows the record's own item.
+// Intersections are small (mean 0.4 rows on PubMed): 2 rows per item; unions are large (mean 20):
+// 8 rows per item, so that the subgraph's features are re-read 4x less often.
+__host__ __device__ inline int ccn_rows(int strategy) { return strategy == S3_STRATEGY_UNION ? 8 : 2; }
+__host__ __device__ inline int ccn_items(int s, int nseed, int cr) { return s > nseed ? (s - nseed + cr - 1) / cr : 0; }
+__host__ __device__ inline int64_t ccn_item_words(int K, int64_t n, int cr) {
+    const int64_t nwp = ((int64_t)(K + 1) * cr + 3) & ~int64_t(3);
+    return (nwp + n * nwp + 2 * n * cr + 3) & ~int64_t(3);
+}
+
 struct OutPtrs {
     float* p[S3_MAX_K + 1];
 };
@@ -65,7 +76,7 @@ cudaError_t launch_plan(const s3_batch& b, cudaStream_t st);
 cudaError_t launch_plan_items(const s3_batch& b, cudaStream_t st);
 cudaError_t launch_diffuse(const s3_graph& g, const s3_batch& b, int64_t num_items, cudaStream_t st);
 cudaError_t launch_gather(const s3_graph& g, const s3_batch& b, int64_t num_items, const OutPtrs& out,
-                          int64_t ldo, int64_t row_base, cudaStream_t st);
+                          int64_t ldo, int64_t row_base, bool ccn, cudaStream_t st);
 cudaError_t launch_dump_edges(const s3_batch& b, const int64_t* edge_ptr, int32_t* edges_out, cudaStream_t st);
 
 }  // namespace s3

@@ -13,10 +13,10 @@
 // nodes of hops <= k (+1 when the selected rows are hop-1 CCN nodes) of the hop-major node
 // order; everything beyond is an exact zero that kernel 3 never reads.
 //
-// Work item 0 of every record (the rows of the two targets) is diffused inside the front
-// kernel (extract.cu); this kernel handles the later items — PoS Plus CCN rows — over the fully
+// The rows of the two targets are diffused inside the front kernel (extract.cu); this kernel
+// handles the PoS Plus CCN rows — extra work items of up to 8 selected rows each — over the fully
 // stored padded CSR.
-// One CTA per work item (= up to SC selected rows of one record), one 8-lane group per node:
+// One CTA per CCN work item, one 8-lane group per node:
 // lanes stride the node's local row, partial sums are combined by a fixed shuffle tree, so
 // results do not depend on scheduling. z ping-pong buffers live in shared memory when the
 // subgraph fits, else in the item's global scratch. Output per item, in the record's float
@@ -27,7 +27,7 @@
 namespace s3 {
 namespace {
 
-constexpr int kZCap = 4096;  // floats per shared z buffer (2 buffers: 32 KB)
+constexpr int kZCap = 4096;  // floats per shared z buffer (2 buffers: 32 KB): n <= 2048 with 2 rows, 512 with 8
 
 struct DiffuseParams {
     const int64_t* __restrict__ indptr;  // SoP: global degrees
@@ -49,8 +49,7 @@ __global__ void __launch_bounds__(kDiffuseThreads) diffuse_kernel(DiffuseParams 
     const int64_t rec = p.item_rec ? p.item_rec[item] : item;
     const int32_t* cnt = p.cnt + rec * S3_NCNT;
     if (cnt[S3_CNT_STATUS] != S3_REC_OK) return;
-    const int chunk = p.item_ptr ? (int)(item - p.item_ptr[rec]) : 0;
-    if (chunk == 0) return;  // work item 0 was diffused by the front kernel (extract.cu)
+    const int chunk = (int)(item - p.item_ptr[rec]);  // CCN chunk: selected rows nseed + chunk*8 ...
     const int n = cnt[S3_CNT_N], s = cnt[S3_CNT_S];
     const int K = p.sign_k, nseed = num_seeds(p.flow);
     const int NW = (K + 1) * SC, NWP = (NW + 3) & ~3;
@@ -60,7 +59,8 @@ __global__ void __launch_bounds__(kDiffuseThreads) diffuse_kernel(DiffuseParams 
     const int32_t* rowlen = p.arena + off[S3_OFF_ROWLEN];
     const int32_t* lcol = p.arena + off[S3_OFF_LCOL];
     const int32_t* sel = p.arena + off[S3_OFF_SEL];
-    float* item_f = reinterpret_cast<float*>(p.arena + off[S3_OFF_F32]) + (int64_t)chunk * item_words(p.flow, K, n);
+    float* item_f = reinterpret_cast<float*>(p.arena + off[S3_OFF_F32]) + item_words(p.flow, K, n) +
+                    (int64_t)chunk * ccn_item_words(K, n, SC);
     float* lab = item_f;
     float* wgt = item_f + NWP;
     const bool z_shared = (int64_t)n * SC <= kZCap;
@@ -71,12 +71,12 @@ __global__ void __launch_bounds__(kDiffuseThreads) diffuse_kernel(DiffuseParams 
     int r[SC];
 #pragma unroll
     for (int c = 0; c < SC; ++c) {
-        const int i = chunk * SC + c;
-        r[c] = i >= s ? -1 : (i < nseed ? i : sel[i - nseed]);
+        const int i = nseed + chunk * SC + c;
+        r[c] = i >= s ? -1 : sel[i - nseed];
     }
     // reach[k] = number of leading nodes (hop-major order) a k-step walk from the selected rows
     // can touch: hops <= k for seed rows, hops <= k+1 for hop-1 (CCN) rows
-    const int shift = chunk == 0 ? 0 : 1;
+    const int shift = 1;  // CCN rows are hop-1 nodes
     int hop_end[S3_MAX_HOPS + 2];
     {
         int acc = 0;
@@ -202,12 +202,13 @@ cudaError_t launch_diffuse(const s3_graph& g, const s3_batch& b, int64_t num_ite
     p.arena = b.arena;
     p.off = b.off;
     p.cnt = b.cnt;
-    p.item_ptr = b.item_rec ? b.item_ptr : nullptr;
+    if (!b.item_rec || !b.item_ptr) return cudaErrorInvalidValue;  // CCN items need the plan
+    p.item_ptr = b.item_ptr;
     p.item_rec = b.item_rec;
     p.flow = b.flow;
     p.sign_k = b.sign_k;
-    if (sel_chunk(b.flow) == 1)
-        diffuse_kernel<1><<<(unsigned)num_items, kDiffuseThreads, 0, st>>>(p);
+    if (ccn_rows(b.strategy) == 8)
+        diffuse_kernel<8><<<(unsigned)num_items, kDiffuseThreads, 0, st>>>(p);
     else
         diffuse_kernel<2><<<(unsigned)num_items, kDiffuseThreads, 0, st>>>(p);
     return cudaGetLastError();

@@ -379,8 +379,7 @@ __global__ void __launch_bounds__(kExtractThreads, 5) front_kernel(ExtractParams
             }
 
             // ---------------- allocation 2: float scratch of the record's work items ----------------
-            const int items = (s + SC - 1) / SC;
-            const int64_t words3 = ((int64_t)items * item_words(p.flow, K, n) + 31) & ~int64_t(31);
+            const int64_t words3 = (item_words(p.flow, K, n) + (int64_t)ccn_items(s, nseed, ccn_rows(p.strategy)) * ccn_item_words(K, n, ccn_rows(p.strategy)) + 31) & ~int64_t(31);
             if (tid == 0) s_base = (long long)atomicAdd(&p.counters[S3_CTR_CURSOR], (unsigned long long)words3);
             __syncthreads();
             base3 = p.slab_words + s_base;

@@ -1,0 +1,341 @@
+// Kernel 3 — fused row-select + weighted feature gather, writing the operator matrices.
+//
+// Replaces reference tuned_SIGN.py:177-187 / :240-260 (subg_x = [label | X_sub];
+// x = subg_x[sel]; x_k = P_k[sel] @ subg_x) and, in SoP flow, tuned_SIGN.py:94-133
+// (g = rows @ X, prepend the self-return weight, pack x / x1..xK).
+//
+// For one work item (up to SC selected rows of one record) and all K+1 operators at once:
+//      out_k[row(c), 1 + f] = sum_j  w[j][k*SC + c] * X[node_j][f]      (k = 0 is the one-hot: x itself)
+//      out_k[row(c), 0]     = label weight computed by kernel 2
+// Every subgraph node's feature row is read exactly ONCE (4*F*n bytes, the dominant term of
+// the roofline in SURVEY.md §8d) with 128-bit loads; NW = (K+1)*SC accumulator rows live in
+// registers; weights and row offsets are staged through shared memory in tiles. Feature rows are
+// padded by the host (DeviceGraph) so that every lane owns a valid 16-byte column: the inner
+// loop is LDS(offset) + LDG.128 + LDS(weights) + FFMAs, with no predicates or 64-bit index math.
+//
+// Structural sparsity: a k-step walk cannot reach a node more than k hops away, so a node at
+// hop l of the canonical (hop-major) order has w_k = 0 for k < l (k < l-1 when the selected
+// rows are hop-1 CCN nodes). The node list is walked hop range by hop range with the inner
+// loop specialised on the first live operator, which removes ~2/3 of the FMAs and weight
+// loads on 3-hop subgraphs (most nodes sit on the outermost hop) and skips nodes beyond hop K.
+//
+// The sum over j runs in canonical node order within each row group and groups are combined
+// in fixed order, so results are independent of scheduling, batch composition and GPU count.
+// HBM/L2-bound streaming gather: no tensor cores (M = NW <= 16 rows, fp32 required by the
+// 1e-5 tolerance).
+
+#pragma once
+#include "common.cuh"
+
+namespace s3 {
+
+struct GatherParams {
+    const float* __restrict__ x;
+    int64_t ldx;
+    int F, F4;  // features, float4 columns per row (ldx / 4)
+    const int32_t* __restrict__ arena;
+    const int64_t* __restrict__ off;
+    const int32_t* __restrict__ cnt;
+    const int64_t* __restrict__ row_ptr;   // may be null: row = rec * num_seeds
+    const int64_t* __restrict__ item_ptr;  // may be null
+    const int32_t* __restrict__ item_rec;  // may be null
+    const int32_t* __restrict__ order;     // may be null: largest-first schedule of the records
+    int flow, sign_k, tpr;                 // tpr = threads per feature row (32/64/128)
+    int ccn;                               // 1: CCN work items (item_rec/item_ptr), 0: the records' own rows
+    OutPtrs out;
+    int64_t ldo, row_base;
+};
+// per-(SC, K1 range) translation units, so that the ~130 instantiations compile in parallel
+#define S3_DECL_GATHER_TU(name) \
+    cudaError_t name(const GatherParams& p, int K1, int C, dim3 grid, size_t smem, cudaStream_t st)
+S3_DECL_GATHER_TU(launch_gather_sc1_lo);
+S3_DECL_GATHER_TU(launch_gather_sc1_mid);
+S3_DECL_GATHER_TU(launch_gather_sc1_hi);
+S3_DECL_GATHER_TU(launch_gather_sc2_lo);
+S3_DECL_GATHER_TU(launch_gather_sc2_mid);
+S3_DECL_GATHER_TU(launch_gather_sc2_hi);
+cudaError_t launch_gather_sc8_k2(const GatherParams& p, int C, dim3 grid, size_t smem, cudaStream_t st);
+cudaError_t launch_gather_sc8_k3(const GatherParams& p, int C, dim3 grid, size_t smem, cudaStream_t st);
+cudaError_t launch_gather_sc8_k4(const GatherParams& p, int C, dim3 grid, size_t smem, cudaStream_t st);
+cudaError_t launch_gather_sc8_k5(const GatherParams& p, int C, dim3 grid, size_t smem, cudaStream_t st);
+cudaError_t launch_gather_sc8_k6(const GatherParams& p, int C, dim3 grid, size_t smem, cudaStream_t st);
+
+namespace {
+
+
+constexpr int kTile = 64;  // nodes staged per tile
+constexpr int kU = 4;      // nodes in flight per row group
+
+
+template <int C>
+struct GatherCtx {
+    const int32_t* __restrict__ nodes;
+    const float4* __restrict__ wgt4;
+    const float4* xcol[C];  // x + this lane's float4 column(s)
+    uint32_t ldx4;
+    bool colok[C];
+    float* s_w;
+    uint32_t* s_off;  // float4 index of every staged node's feature row
+    int tid, grp, G;
+};
+
+template <int K1, int SC, int KMIN>
+__device__ __forceinline__ void load_weights(float (&w)[K1 * SC], const float* wrow) {
+    if (SC == 2) {
+#pragma unroll
+        for (int k = KMIN; k < K1; ++k) {
+            const float2 v = reinterpret_cast<const float2*>(wrow)[k];
+            w[2 * k] = v.x;
+            w[2 * k + 1] = v.y;
+        }
+    } else if (SC % 4 == 0) {
+#pragma unroll
+        for (int q4 = KMIN * SC / 4; q4 < K1 * SC / 4; ++q4) {
+            const float4 v = reinterpret_cast<const float4*>(wrow)[q4];
+            w[4 * q4] = v.x;
+            w[4 * q4 + 1] = v.y;
+            w[4 * q4 + 2] = v.z;
+            w[4 * q4 + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int q = KMIN * SC; q < K1 * SC; ++q) w[q] = wrow[q];
+    }
+}
+
+// Accumulate nodes [lo, hi) of the record; only operators k >= KMIN carry weight there.
+// FULL: every lane owns a valid column (rows are padded), so the loads carry no predicates.
+template <int K1, int SC, int C, int KMIN, bool FULL>
+__device__ __forceinline__ void accumulate_range(float4 (&acc)[K1 * SC][C], int lo, int hi, const GatherCtx<C>& cx) {
+    constexpr int NW = K1 * SC, NWP = (NW + 3) & ~3, Q0 = KMIN * SC;
+    float* s_w = cx.s_w;
+    uint32_t* s_off = cx.s_off;
+    const int tid = cx.tid, grp = cx.grp, G = cx.G;
+    for (int base = lo; base < hi; base += kTile) {
+        const int tn = min(kTile, hi - base);
+        __syncthreads();
+        if (tid < tn) s_off[tid] = (uint32_t)cx.nodes[base + tid] * cx.ldx4;
+        {
+            const float4* src = cx.wgt4 + (int64_t)base * (NWP / 4);
+            float4* dst = reinterpret_cast<float4*>(s_w);
+            for (int i = tid; i < tn * (NWP / 4); i += kGatherThreads) dst[i] = src[i];
+        }
+        __syncthreads();
+
+        int t = grp;
+        // main loop: kU rows in flight per row group, no bounds checks
+        for (; t + (kU - 1) * G < tn; t += kU * G) {
+            float4 xv[kU][C];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const uint32_t o = s_off[t + u * G];
+#pragma unroll
+                for (int i = 0; i < C; ++i)
+                    xv[u][i] = (FULL || cx.colok[i]) ? __ldg(cx.xcol[i] + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                float w[NW];
+                load_weights<K1, SC, KMIN>(w, s_w + (t + u * G) * NWP);
+#pragma unroll
+                for (int q = Q0; q < NW; ++q)
+#pragma unroll
+                    for (int i = 0; i < C; ++i) {
+                        acc[q][i].x = fmaf(w[q], xv[u][i].x, acc[q][i].x);
+                        acc[q][i].y = fmaf(w[q], xv[u][i].y, acc[q][i].y);
+                        acc[q][i].z = fmaf(w[q], xv[u][i].z, acc[q][i].z);
+                        acc[q][i].w = fmaf(w[q], xv[u][i].w, acc[q][i].w);
+                    }
+            }
+        }
+        // tail of the tile, one row at a time (same order of accumulation: ascending node index)
+        for (; t < tn; t += G) {
+            const uint32_t o = s_off[t];
+            float4 xv[C];
+#pragma unroll
+            for (int i = 0; i < C; ++i)
+                xv[i] = (FULL || cx.colok[i]) ? __ldg(cx.xcol[i] + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float w[NW];
+            load_weights<K1, SC, KMIN>(w, s_w + t * NWP);
+#pragma unroll
+            for (int q = Q0; q < NW; ++q)
+#pragma unroll
+                for (int i = 0; i < C; ++i) {
+                    acc[q][i].x = fmaf(w[q], xv[i].x, acc[q][i].x);
+                    acc[q][i].y = fmaf(w[q], xv[i].y, acc[q][i].y);
+                    acc[q][i].z = fmaf(w[q], xv[i].z, acc[q][i].z);
+                    acc[q][i].w = fmaf(w[q], xv[i].w, acc[q][i].w);
+                }
+        }
+    }
+}
+
+template <int K1, int SC, int C, int KMIN, bool FULL>
+struct RangeDispatch {
+    __device__ __forceinline__ static void run(int kmin, float4 (&acc)[K1 * SC][C], int lo, int hi, const GatherCtx<C>& cx) {
+        if (kmin == KMIN)
+            accumulate_range<K1, SC, C, KMIN, FULL>(acc, lo, hi, cx);
+        else
+            RangeDispatch<K1, SC, C, KMIN + 1, FULL>::run(kmin, acc, lo, hi, cx);
+    }
+};
+template <int K1, int SC, int C, bool FULL>
+struct RangeDispatch<K1, SC, C, K1, FULL> {
+    __device__ __forceinline__ static void run(int, float4 (&)[K1 * SC][C], int, int, const GatherCtx<C>&) {}
+};
+
+// Occupancy target by accumulator footprint (K1*SC*C float4 per thread): the kernel is latency /
+// L2-throughput bound, and 8 CTAs of 4 warps per SM stream 16 TB/s where 5 CTAs streamed 12 TB/s.
+constexpr int gather_min_blocks(int acc4) { return acc4 <= 8 ? 8 : acc4 <= 12 ? 6 : acc4 <= 16 ? 5 : acc4 <= 24 ? 3 : 2; }
+
+template <int K1, int SC, int C, bool FULL>
+__global__ void __launch_bounds__(kGatherThreads, gather_min_blocks(K1 * SC * C)) gather_kernel(GatherParams p) {
+    constexpr int NW = K1 * SC, NWP = (NW + 3) & ~3;
+    extern __shared__ float4 smem4[];
+    float* s_w = reinterpret_cast<float*>(smem4);                        // [kTile][NWP]
+    uint32_t* s_off = reinterpret_cast<uint32_t*>(s_w + kTile * NWP);    // [kTile]
+
+    const int tid = threadIdx.x;
+    // record mode: one CTA per record (largest first when an order is given), its seed rows;
+    // CCN mode: one CTA per CCN work item = up to SC extra selected rows of a record
+    int64_t rec;
+    int chunk = 0;
+    if (p.ccn) {
+        const int64_t item = blockIdx.x;
+        rec = p.item_rec[item];
+        chunk = (int)(item - p.item_ptr[rec]);
+    } else {
+        rec = p.order ? (int64_t)p.order[blockIdx.x] : (int64_t)blockIdx.x;
+        if (rec < 0) return;  // slot of an invalid record
+    }
+    const int32_t* cnt = p.cnt + rec * S3_NCNT;
+    if (cnt[S3_CNT_STATUS] != S3_REC_OK) return;
+    const int n = cnt[S3_CNT_N], s = cnt[S3_CNT_S];
+    const int nseed = num_seeds(p.flow);
+    const int64_t* off = p.off + rec * S3_NOFF;
+    const int32_t* nodes = p.arena + off[S3_OFF_NODES];
+    const float* item_f = reinterpret_cast<const float*>(p.arena + off[S3_OFF_F32]) +
+                          (p.ccn ? item_words(p.flow, p.sign_k, n) + (int64_t)chunk * ccn_item_words(p.sign_k, n, SC) : 0);
+    const float* lab = item_f;
+    const float4* wgt4 = reinterpret_cast<const float4*>(item_f + NWP);
+
+    const int tpr = p.tpr, G = kGatherThreads / tpr;
+    const int grp = tid / tpr, lane = tid - grp * tpr;
+    GatherCtx<C> cx;
+    int col[C];
+    bool (&colok)[C] = cx.colok;
+#pragma unroll
+    for (int i = 0; i < C; ++i) {
+        col[i] = (blockIdx.y * C + i) * tpr + lane;
+        colok[i] = col[i] < p.F4;
+        cx.xcol[i] = reinterpret_cast<const float4*>(p.x) + (colok[i] ? col[i] : 0);
+    }
+    cx.nodes = nodes;
+    cx.wgt4 = wgt4;
+    cx.ldx4 = (uint32_t)(p.ldx >> 2);
+    cx.s_w = s_w;
+    cx.s_off = s_off;
+    cx.tid = tid;
+    cx.grp = grp;
+    cx.G = G;
+
+    float4 acc[NW][C];
+#pragma unroll
+    for (int q = 0; q < NW; ++q)
+#pragma unroll
+        for (int i = 0; i < C; ++i) acc[q][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    // hop ranges of the canonical node order; the records' own rows are the seeds, CCN rows are
+    // hop-1 nodes (one hop closer to everything: kmin shifts down by one)
+    const int shift = p.ccn ? 1 : 0;
+    int lo = 0;
+    for (int l = 0; l <= S3_MAX_HOPS && lo < n; ++l) {
+        const int hi = lo + cnt[S3_CNT_HOP0 + l];
+        const int kmin = max(0, l - shift);
+        if (kmin >= K1) break;  // farther than K hops: no operator reaches these nodes
+        if (hi > lo)
+            RangeDispatch<K1, SC, C, 0, FULL>::run(kmin, acc, lo, hi, cx);
+        lo = hi;
+    }
+
+    // combine the G row groups in fixed order (group 0 accumulates groups 1..G-1)
+    if (G > 1) {
+        float4* red = smem4;  // [(G-1)][NW][C][tpr]
+        __syncthreads();
+        if (grp > 0) {
+#pragma unroll
+            for (int q = 0; q < NW; ++q)
+#pragma unroll
+                for (int i = 0; i < C; ++i) red[(((grp - 1) * NW + q) * C + i) * tpr + lane] = acc[q][i];
+        }
+        __syncthreads();
+        if (grp == 0) {
+            for (int g = 1; g < G; ++g)
+#pragma unroll
+                for (int q = 0; q < NW; ++q)
+#pragma unroll
+                    for (int i = 0; i < C; ++i) {
+                        const float4 v = red[(((g - 1) * NW + q) * C + i) * tpr + lane];
+                        acc[q][i].x += v.x;
+                        acc[q][i].y += v.y;
+                        acc[q][i].z += v.z;
+                        acc[q][i].w += v.w;
+                    }
+        }
+    }
+    if (grp != 0) return;
+
+    const int first_sel = p.ccn ? nseed + chunk * SC : 0;  // index of this item's first selected row
+    const int64_t row0 = p.row_base + (p.row_ptr ? p.row_ptr[rec] : rec * (int64_t)nseed) + first_sel;
+#pragma unroll
+    for (int q = 0; q < NW; ++q) {
+        const int k = q / SC, c = q - k * SC;
+        if (first_sel + c >= s) continue;
+        float* orow = p.out.p[k] + (row0 + c) * p.ldo;
+        if (blockIdx.y == 0 && lane == 0) orow[0] = lab[q];
+#pragma unroll
+        for (int i = 0; i < C; ++i) {
+            if (!colok[i]) continue;
+            const int f = 4 * col[i];
+            float* o = orow + 1 + f;
+            if (f + 0 < p.F) o[0] = acc[q][i].x;
+            if (f + 1 < p.F) o[1] = acc[q][i].y;
+            if (f + 2 < p.F) o[2] = acc[q][i].z;
+            if (f + 3 < p.F) o[3] = acc[q][i].w;
+        }
+    }
+}
+
+template <int K1, int SC, int C, bool FULL>
+cudaError_t launch_full(const GatherParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(gather_kernel<K1, SC, C, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    gather_kernel<K1, SC, C, FULL><<<grid, kGatherThreads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <int K1, int SC, int C>
+cudaError_t launch_one(const GatherParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+    const bool full = p.F4 % (p.tpr * C) == 0;  // every lane of every column chunk owns a valid column
+    return full ? launch_full<K1, SC, C, true>(p, grid, smem, st) : launch_full<K1, SC, C, false>(p, grid, smem, st);
+}
+
+template <int K1, int SC>
+cudaError_t launch_c(const GatherParams& p, int C, dim3 grid, size_t smem, cudaStream_t st) {
+    if (SC == 8) return C == 1 ? launch_one<K1, SC, 1>(p, grid, smem, st) : cudaErrorInvalidValue;  // 8-row items: 1 column/thread
+    switch (C) {
+        case 1: return launch_one<K1, SC, 1>(p, grid, smem, st);
+        case 2: return launch_one<K1, SC, 2>(p, grid, smem, st);
+        default: return launch_one<K1, SC, 3>(p, grid, smem, st);
+    }
+}
+
+template <int SC, int K1>
+cudaError_t launch_k1(const GatherParams& p, int C, dim3 grid, size_t smem, cudaStream_t st) {
+    return launch_c<K1, SC>(p, C, grid, smem, st);
+}
+
+}  // namespace
+}  // namespace s3

@@ -6,8 +6,8 @@
 namespace s3 {
 namespace {
 
-// Single CTA: exclusive scans of s (rows) and ceil(s / SC) (items) over all records.
-__global__ void __launch_bounds__(1024) plan_scan_kernel(const int32_t* __restrict__ cnt, int64_t num_records, int sc,
+// Single CTA: exclusive scans of s (rows) and of the CCN work items ceil((s - seeds) / 8) over all records.
+__global__ void __launch_bounds__(1024) plan_scan_kernel(const int32_t* __restrict__ cnt, int64_t num_records, int nseed, int cr,
                                                          int64_t* __restrict__ row_ptr, int64_t* __restrict__ item_ptr,
                                                          unsigned long long* counters) {
     __shared__ long long s_rows[1024], s_items[1024];
@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(1024) plan_scan_kernel(const int32_t* __restri
     for (int64_t r = r0; r < r1; ++r) {
         const int s = cnt[r * S3_NCNT + S3_CNT_S];
         rows += s;
-        items += (s + sc - 1) / sc;
+        items += ccn_items(s, nseed, cr);
     }
     s_rows[tid] = rows;
     s_items[tid] = items;
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(1024) plan_scan_kernel(const int32_t* __restri
         row_ptr[r] = row_run;
         item_ptr[r] = item_run;
         row_run += s;
-        item_run += (s + sc - 1) / sc;
+        item_run += ccn_items(s, nseed, cr);
     }
     if (tid == T - 1) {
         row_ptr[num_records] = s_rows[tid];
@@ -105,7 +105,7 @@ __global__ void dump_edges_kernel(const int32_t* __restrict__ arena, const int64
 
 cudaError_t launch_plan(const s3_batch& b, cudaStream_t st) {
     const int64_t R = s3_num_records(&b);
-    plan_scan_kernel<<<1, 1024, 0, st>>>(b.cnt, R, sel_chunk(b.flow), b.row_ptr, b.item_ptr,
+    plan_scan_kernel<<<1, 1024, 0, st>>>(b.cnt, R, num_seeds(b.flow), ccn_rows(b.strategy), b.row_ptr, b.item_ptr,
                                          reinterpret_cast<unsigned long long*>(b.counters));
     return cudaGetLastError();
 }

@@ -213,7 +213,7 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
         if not fixed_rows:
             # data-dependent row counts: every batch ends in a host sync and keeps its own output
             # pieces, and CCN work items multiply the float scratch — smaller batches
-            batch_records = min(int(batch_records), 4096)
+            batch_records = min(int(batch_records), 4096 if cstrat == L.STRATEGY_UNION else 16384)
         batch_links = max(1, int(batch_records) // rpl)
         nb = (Lk + batch_links - 1) // batch_links
         counters = torch.zeros((max(nb, 1), L.NCTR), dtype=torch.int64, device=dev)
@@ -315,7 +315,8 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
                 return cnt, off, None
             row_ptr = torch.empty(nrec + 1, dtype=torch.int64, device=dev)
             item_ptr = torch.empty(nrec + 1, dtype=torch.int64, device=dev)
-            batch = make_batch(b0, b1, arena, off, cnt, ctr, row_ptr, item_ptr)
+            order = torch.empty(nrec, dtype=torch.int32, device=dev)
+            batch = make_batch(b0, b1, arena, off, cnt, ctr, row_ptr, item_ptr, order=order)
             timed('extract', bi, lambda: L.check(lib.s3_extract(C.byref(graph._c), C.byref(batch), st_ptr), 's3_extract'))
             L.check(lib.s3_plan(C.byref(batch), st_ptr), 's3_plan')
             stats['launches'] += 2
@@ -325,12 +326,16 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
             rows, items = int(c[L.CTR_ROWS]), int(c[L.CTR_ITEMS])
             item_rec = torch.empty(max(items, 1), dtype=torch.int32, device=dev)
             xs_b = [torch.empty((rows, F1), dtype=torch.float32, device=dev) for _ in range(K + 1)]
-            batch = make_batch(b0, b1, arena, off, cnt, ctr, row_ptr, item_ptr, item_rec)
+            batch = make_batch(b0, b1, arena, off, cnt, ctr, row_ptr, item_ptr, item_rec, order)
             ptrs = (C.c_void_p * (K + 1))(*[o.data_ptr() for o in xs_b])
-            L.check(lib.s3_plan_items(C.byref(batch), st_ptr), 's3_plan_items')
-            timed('diffuse', bi, lambda: L.check(lib.s3_diffuse(C.byref(graph._c), C.byref(batch), items, st_ptr), 's3_diffuse'))
-            timed('gather', bi, lambda: L.check(lib.s3_gather(C.byref(graph._c), C.byref(batch), items, ptrs, F1, 0, st_ptr), 's3_gather'))
-            stats['launches'] += 3
+            timed('gather', bi, lambda: L.check(lib.s3_gather(C.byref(graph._c), C.byref(batch), nrec, ptrs, F1, 0, st_ptr), 's3_gather'))
+            stats['launches'] += 1
+            if items:       # CCN rows: extra work items of up to 8 selected rows each
+                L.check(lib.s3_plan_items(C.byref(batch), st_ptr), 's3_plan_items')
+                timed('diffuse', bi, lambda: L.check(lib.s3_diffuse(C.byref(graph._c), C.byref(batch), items, st_ptr), 's3_diffuse'))
+                timed('gather_ccn', bi, lambda: L.check(
+                    lib.s3_gather_ccn(C.byref(graph._c), C.byref(batch), items, ptrs, F1, 0, st_ptr), 's3_gather_ccn'))
+                stats['launches'] += 3
             pieces.append(xs_b)
             row_counts.append(row_ptr[1:] - row_ptr[:-1])
             return cnt, off, None
