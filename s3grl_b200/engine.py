@@ -149,316 +149,345 @@ class PrecomputeResult:
         return self
 
 
-def _records_per_link(flow):
-    return 2 if flow == L.FLOW_SOP else 1
+class _Call:
+    """One precompute call: validated arguments, per-call device state and the batch schedule.
 
+    Fixed-row flows (PoS, SoP: every record owns `num_seeds` output rows) enqueue all batches
+    without a host sync, validate once at the end and re-run batches whose arena overflowed.
+    PoS Plus has data-dependent row counts: every batch ends in a host sync (rows / CCN items),
+    owns its output pieces, and the pieces are concatenated at the end."""
 
-def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_records=32768,
-               out=None, return_graphs=False, arena_words=None, stream=None, profile=None, overlap=False, defer=False, host_out=None, force_sorted_tier=False):
-    """Run the hot path for `links` ([2, L] int64, host or device) on `graph`.
-
-    Returns PrecomputeResult with device tensors.  `out`, if given, is a list of K+1
-    preallocated [>=R, F+1] float32 device tensors (fixed-row flows only).  `profile`, if a
-    list, receives (stage, batch, start_event, end_event) for every kernel launch group so the
-    caller can time each kernel on the launching stream with CUDA events.  `overlap` (fixed-row
-    flows) runs extract+diffuse of batch i+1 on one stream while gather of batch i runs on
-    another, with two arenas: the latency-bound front half hides under the bandwidth-bound gather.
-    `host_out` (fixed-row flows): K+1 pinned host tensors [>=R, F+1]; every batch's rows are
-    copied device->host on a side stream as soon as its gather finishes, so the D2H of batch i
-    overlaps the kernels of batch i+1 (the reference returns CPU tensors).
-    `defer` (fixed-row flows) returns right after enqueueing; the caller must call
-    `result.finalize()` (stream sync + validation + re-run of overflowed batches) before using
-    the outputs.  It lets several calls be queued back to back without a host round trip.
-    Raises ValueError for invalid links (out of range, src == dst), NotImplementedError for an
-    unknown strategy (as reference tuned_SIGN.py:235)."""
-    lib = L.lib()
-    if flow not in _FLOW:
-        raise NotImplementedError(f"sign_type {flow!r}: no matching configuration (reference utils.py:553)")
-    if strategy not in _STRATEGY:
-        raise NotImplementedError(f"check strat {strategy}")   # reference tuned_SIGN.py:235
-    cflow = _FLOW[flow]
-    cstrat = _STRATEGY[strategy] if cflow == L.FLOW_POS else L.STRATEGY_NONE
-    if cflow == L.FLOW_SOP and graph.has_multi_edges:
-        raise NotImplementedError("SoP on a multigraph (duplicate edges) is not supported")
-    dev = graph.device
-    links = torch.as_tensor(links)
-    if links.dim() != 2 or links.shape[0] != 2:
-        raise ValueError("links must be [2, L]")
-    links = links.to(device=dev, dtype=torch.int64, non_blocking=True).contiguous()
-    Lk = int(links.shape[1])
-    K = int(sign_k)
-    F1 = graph.num_feat + 1
-    rpl = _records_per_link(cflow)
-    nseed = 1 if cflow == L.FLOW_SOP else 2
-    fixed_rows = cstrat == L.STRATEGY_NONE
-    st = stream if stream is not None else torch.cuda.current_stream(dev)
-    st_ptr = C.c_void_p(st.cuda_stream)
-
-    with torch.cuda.device(dev), torch.cuda.stream(st):
-        copy_stream = None
-        if host_out is not None:
-            if not fixed_rows or overlap:
-                raise ValueError("host_out needs a fixed-row flow without overlap")
-            copy_stream = graph.streams()[1]
-            ready = torch.cuda.Event()
-            ready.record(st)
-            copy_stream.wait_event(ready)
-        if fixed_rows:
-            R = 2 * Lk
-            if out is None:
-                out = [torch.empty((R, F1), dtype=torch.float32, device=dev) for _ in range(K + 1)]
-            else:
-                assert len(out) == K + 1 and all(o.shape[0] >= R and o.shape[1] == F1 and o.is_contiguous() for o in out)
-            out_ptrs = (C.c_void_p * (K + 1))(*[o.data_ptr() for o in out])
-        if not fixed_rows:
-            # data-dependent row counts: every batch ends in a host sync and keeps its own output
-            # pieces, and CCN work items multiply the float scratch — smaller batches
-            batch_records = min(int(batch_records), 4096 if cstrat == L.STRATEGY_UNION else 16384)
-        batch_links = max(1, int(batch_records) // rpl)
-        nb = (Lk + batch_links - 1) // batch_links
-        counters = torch.zeros((max(nb, 1), L.NCTR), dtype=torch.int64, device=dev)
+    def __init__(self, graph, links, num_hops, sign_k, flow, strategy, batch_records, out, return_graphs,
+                 arena_words, stream, profile, overlap, host_out, force_sorted_tier):
+        self.lib = L.lib()
+        if flow not in _FLOW:
+            raise NotImplementedError(f"sign_type {flow!r}: no matching configuration (reference utils.py:553)")
+        if strategy not in _STRATEGY:
+            raise NotImplementedError(f"check strat {strategy}")   # reference tuned_SIGN.py:235
+        self.graph, self.dev = graph, graph.device
+        self.flow = _FLOW[flow]
+        self.strategy = _STRATEGY[strategy] if self.flow == L.FLOW_POS else L.STRATEGY_NONE
+        if self.flow == L.FLOW_SOP and graph.has_multi_edges:
+            raise NotImplementedError("SoP on a multigraph (duplicate edges) is not supported")
+        links = torch.as_tensor(links)
+        if links.dim() != 2 or links.shape[0] != 2:
+            raise ValueError("links must be [2, L]")
+        self.links = links.to(device=self.dev, dtype=torch.int64, non_blocking=True).contiguous()
+        self.num_links = int(self.links.shape[1])
+        self.num_hops, self.K = int(num_hops), int(sign_k)
+        self.F1 = graph.num_feat + 1
+        self.rpl = 2 if self.flow == L.FLOW_SOP else 1          # records per link
+        self.nseed = 1 if self.flow == L.FLOW_SOP else 2        # output rows per record (fixed-row flows)
+        self.fixed_rows = self.strategy == L.STRATEGY_NONE
+        self.return_graphs, self.profile = bool(return_graphs), profile
+        self.stream = stream if stream is not None else torch.cuda.current_stream(self.dev)
+        self.stream_ptr = C.c_void_p(self.stream.cuda_stream)
+        self.host_out, self.copy_stream = host_out, None
+        if host_out is not None and (not self.fixed_rows or overlap):
+            raise ValueError("host_out needs a fixed-row flow without overlap")
+        if not self.fixed_rows:
+            # every batch keeps its own output pieces and CCN work items multiply the float scratch
+            batch_records = min(int(batch_records), 4096 if self.strategy == L.STRATEGY_UNION else 16384)
+        self.batch_links = max(1, int(batch_records) // self.rpl)
+        self.num_batches = (self.num_links + self.batch_links - 1) // self.batch_links
+        self.overlap = bool(overlap) and self.fixed_rows and not self.return_graphs and self.num_batches > 1
+        self.flags = ((L.BATCH_STORE_ALL_ROWS if self.return_graphs else 0)
+                      | (L.BATCH_FORCE_SORTED_TIER if force_sorted_tier else 0))
+        probe = self.make_batch(0, 0, None, None, None, None)
+        if self.lib.s3_extract_tier(C.byref(graph._c), C.byref(probe)) < 0:
+            L.check(L.S3_ERR_UNSUPPORTED, 's3_extract')
         if arena_words:
             words = int(arena_words)
-        else:   # ~128 KiB of scratch per record to start with (PubMed h=3 averages ~100 KiB), grown on overflow
-            free, _ = torch.cuda.mem_get_info(dev)
-            words = max(1 << 22, min(min(int(batch_records), Lk * rpl) * 32768, free // 16))
+        else:   # ~128 KiB of scratch per record to start with (PubMed h=3 averages ~60 KiB), grown on overflow
+            free, _ = torch.cuda.mem_get_info(self.dev)
+            words = max(1 << 22, min(min(int(batch_records), self.num_links * self.rpl) * 32768, free // 16))
             if graph._arena is not None:
                 words = max(words, graph._arena.numel())
-        batch_flags = (L.BATCH_STORE_ALL_ROWS if return_graphs else 0) | (L.BATCH_FORCE_SORTED_TIER if force_sorted_tier else 0)
-        probe = L.Batch(None, None, 0, cflow, cstrat, int(num_hops), K, batch_flags, 0, None, 0, None, None, None, None, None,
-                        None, None)
-        if lib.s3_extract_tier(C.byref(graph._c), C.byref(probe)) < 0:
-            L.check(L.S3_ERR_UNSUPPORTED, 's3_extract')
-        words = max(words, 4 * int(lib.s3_min_arena_words(C.byref(graph._c), C.byref(probe))))
-        stats = dict(records=Lk * rpl, links=Lk, sum_n=0, sum_d=0, max_n=0, rows=0, retries=0, batches=nb, launches=0)
-        pieces, row_counts, graphs = [], [], ([] if return_graphs else None)
+        self.words = max(words, 4 * int(self.lib.s3_min_arena_words(C.byref(graph._c), C.byref(probe))))
+        self.out, self.out_ptrs = out, None
+        self.stats = dict(records=self.num_links * self.rpl, links=self.num_links, sum_n=0, sum_d=0, max_n=0, rows=0,
+                          retries=0, batches=self.num_batches, launches=0)
+        self.pieces, self.row_counts = [], []
+        self.graphs = [] if self.return_graphs else None
+        self.counters = None
 
-        def make_batch(b0, b1, arena, off, cnt, ctr, row_ptr=None, item_ptr=None, item_rec=None, order=None):
-            return L.Batch(_ptr(links[0, b0:b1]), _ptr(links[1, b0:b1]), b1 - b0, cflow, cstrat, int(num_hops), K,
-                           batch_flags, 0, _ptr(arena), arena.numel(), _ptr(off), _ptr(cnt), _ptr(ctr),
-                           _ptr(row_ptr), _ptr(item_ptr), _ptr(item_rec), _ptr(order))
+    # ------------------------------------------------------------------ helpers
+    def bounds(self, bi):
+        b0 = bi * self.batch_links
+        return b0, min(self.num_links, b0 + self.batch_links)
 
-        def timed(stage, bi, fn, on=None):
-            if profile is None:
-                return fn()
-            on = st if on is None else on
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(on)
-            r = fn()
-            e1.record(on)
-            profile.append((stage, bi, e0, e1))
-            return r
+    def make_batch(self, b0, b1, arena, off, cnt, ctr, row_ptr=None, item_ptr=None, item_rec=None, order=None):
+        src = self.links[0, b0:b1] if b1 > b0 else None
+        dst = self.links[1, b0:b1] if b1 > b0 else None
+        return L.Batch(_ptr(src), _ptr(dst), b1 - b0, self.flow, self.strategy, self.num_hops, self.K, self.flags, 0,
+                       _ptr(arena), arena.numel() if arena is not None else 0, _ptr(off), _ptr(cnt), _ptr(ctr),
+                       _ptr(row_ptr), _ptr(item_ptr), _ptr(item_rec), _ptr(order))
 
-        def run_fixed_overlapped(todo, words):
-            """Two streams, two arenas: front (extract, diffuse) of batch i+1 overlaps back (gather)
-            of batch i.  Returns [(bi, cnt)] for validation after the caller's sync."""
-            sF, sB = graph.streams()
-            arenas = (graph.arena(words, 0), graph.arena(words, 1))
-            nrecs = [(min(Lk, (bi + 1) * batch_links) - bi * batch_links) * rpl for bi in todo]
-            off_all = torch.empty((sum(nrecs), L.NOFF), dtype=torch.int64, device=dev)
-            cnt_all = torch.empty((sum(nrecs), L.NCNT), dtype=torch.int32, device=dev)
-            order_all = torch.empty(sum(nrecs), dtype=torch.int32, device=dev)
-            counters[torch.as_tensor(todo, device=dev)] = 0
-            start = torch.cuda.Event()
-            start.record(st)
-            sF.wait_event(start)
-            sB.wait_event(start)
-            pF, pB = C.c_void_p(sF.cuda_stream), C.c_void_p(sB.cuda_stream)
-            metas, back_done, r0 = [], [], 0
-            for idx, bi in enumerate(todo):
-                b0, b1 = bi * batch_links, min(Lk, (bi + 1) * batch_links)
-                nrec = nrecs[idx]
-                off, cnt = off_all[r0:r0 + nrec], cnt_all[r0:r0 + nrec]
-                r0 += nrec
-                order = order_all[r0 - nrec:r0]
-                batch = make_batch(b0, b1, arenas[idx % 2], off, cnt, counters[bi], order=order)
-                if idx >= 2:
-                    sF.wait_event(back_done[idx - 2])          # this arena is free again
-                timed('extract', bi, lambda: L.check(lib.s3_extract(C.byref(graph._c), C.byref(batch), pF), 's3_extract'), sF)
-                fd = torch.cuda.Event()
-                fd.record(sF)
-                sB.wait_event(fd)
-                timed('gather', bi, lambda: L.check(
-                    lib.s3_gather(C.byref(graph._c), C.byref(batch), nrec, out_ptrs, F1, b0 * rpl * nseed, pB), 's3_gather'), sB)
-                bd = torch.cuda.Event()
-                bd.record(sB)
-                back_done.append(bd)
-                stats['launches'] += 2
+    def launch(self, stage, bi, fn_name, *args, on=None):
+        """Call one C entry point; with `profile`, bracket it with CUDA events on its stream."""
+        fn = getattr(self.lib, fn_name)
+        if self.profile is None:
+            return L.check(fn(*args), fn_name)
+        on = self.stream if on is None else on
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(on)
+        L.check(fn(*args), fn_name)
+        e1.record(on)
+        self.profile.append((stage, bi, e0, e1))
+
+    def grow(self):
+        self.stats['retries'] += 1
+        self.words = int(self.words * 2)
+        self.graph._arena = self.graph._arena2 = None       # hand the old arenas back to the driver first
+        torch.cuda.empty_cache()
+        free, _ = torch.cuda.mem_get_info(self.dev)
+        if self.words * 4 > free:
+            raise MemoryError("scratch arena does not fit in device memory; lower batch_records")
+
+    def account(self, bi, cnt, host_counters=None):
+        """True if batch `bi` finished cleanly (and add its counters to the stats); False if its arena
+        overflowed; raises ValueError for invalid links."""
+        c = self.counters[bi].cpu() if host_counters is None else host_counters[bi]
+        if int(c[L.CTR_ERRORS]) != 0:
+            status = cnt[:, L.CNT_STATUS]
+            if bool((status == L.REC_BAD_LINK).any()):
+                bad = int(torch.nonzero(status == L.REC_BAD_LINK)[0]) // self.rpl + bi * self.batch_links
+                raise ValueError(f"invalid target link at position {bad}: node id out of range or src == dst")
+            return False
+        self.stats['sum_n'] += int(c[L.CTR_SUM_N])
+        self.stats['sum_d'] += int(c[L.CTR_SUM_D])
+        self.stats['max_n'] = max(self.stats['max_n'], int(c[L.CTR_MAX_N]))
+        return True
+
+    def dump(self, cnt, off, arena):
+        """Parity dump of one batch (S3_BATCH_STORE_ALL_ROWS): canonical nodes, hops, compact local CSR."""
+        cn, of, ar = cnt.cpu().numpy(), off.cpu().numpy(), arena.cpu().numpy()
+        for r in range(cn.shape[0]):
+            n, m, s = int(cn[r, L.CNT_N]), int(cn[r, L.CNT_M]), int(cn[r, L.CNT_S])
+            assert int(cn[r, L.CNT_NSTORE]) == n
+            nodes = ar[of[r, L.OFF_NODES]:of[r, L.OFF_NODES] + n].astype(np.int64)
+            rstart = ar[of[r, L.OFF_ROWPTR]:of[r, L.OFF_ROWPTR] + n + 1].astype(np.int64)
+            rlen = ar[of[r, L.OFF_ROWLEN]:of[r, L.OFF_ROWLEN] + n].astype(np.int64)
+            padded = ar[of[r, L.OFF_LCOL]:of[r, L.OFF_LCOL] + int(rstart[n])]
+            rowptr = np.zeros(n + 1, dtype=np.int64)      # compact the padded CSR (holes are -1)
+            np.cumsum(rlen, out=rowptr[1:])
+            lcol = padded[padded >= 0].copy()
+            owner = np.repeat(np.arange(n), np.diff(rstart))[padded >= 0]
+            assert int(rowptr[n]) == m == lcol.size and np.array_equal(np.bincount(owner, minlength=n), rlen)
+            sel = np.concatenate([np.arange(self.nseed),
+                                  ar[of[r, L.OFF_SEL]:of[r, L.OFF_SEL] + s - self.nseed]]).astype(np.int32)
+            hop_cnt = cn[r, L.CNT_HOP0:L.CNT_HOP0 + L.MAX_HOPS + 1]
+            hops = np.repeat(np.arange(L.MAX_HOPS + 1), hop_cnt).astype(np.int32)
+            self.graphs.append(dict(nodes=nodes, hops=hops, lrowptr=rowptr, lcol=lcol, sel=sel,
+                                    partner=int(cn[r, L.CNT_PARTNER])))
+
+    def meta(self, nrec):
+        off = torch.empty((nrec, L.NOFF), dtype=torch.int64, device=self.dev)
+        cnt = torch.empty((nrec, L.NCNT), dtype=torch.int32, device=self.dev)
+        order = torch.empty(nrec, dtype=torch.int32, device=self.dev)
+        return off, cnt, order
+
+    # ------------------------------------------------------------------ fixed-row flows
+    def enqueue_fixed_batch(self, bi, arena):
+        g, st = C.byref(self.graph._c), self.stream_ptr
+        b0, b1 = self.bounds(bi)
+        nrec = (b1 - b0) * self.rpl
+        off, cnt, order = self.meta(nrec)
+        self.counters[bi].zero_()
+        batch = self.make_batch(b0, b1, arena, off, cnt, self.counters[bi], order=order)
+        row_base = b0 * self.rpl * self.nseed
+        self.launch('extract', bi, 's3_extract', g, C.byref(batch), st)
+        self.launch('gather', bi, 's3_gather', g, C.byref(batch), nrec, self.out_ptrs, self.F1, row_base, st)
+        self.stats['launches'] += 2
+        if self.host_out is not None:      # pipelined D2H of this batch's rows
+            r0, r1 = row_base, b1 * self.rpl * self.nseed
+            done = torch.cuda.Event()
+            done.record(self.stream)
+            self.copy_stream.wait_event(done)
+            with torch.cuda.stream(self.copy_stream):
+                for k in range(self.K + 1):
+                    self.host_out[k][r0:r1].copy_(self.out[k][r0:r1], non_blocking=True)
+        return off, cnt
+
+    def enqueue_fixed_overlapped(self, todo):
+        """Two streams, two arenas: the front kernel of batch i+1 overlaps the gather of batch i."""
+        g = C.byref(self.graph._c)
+        sF, sB = self.graph.streams()
+        arenas = (self.graph.arena(self.words, 0), self.graph.arena(self.words, 1))
+        self.counters[torch.as_tensor(todo, device=self.dev)] = 0
+        start = torch.cuda.Event()
+        start.record(self.stream)
+        sF.wait_event(start)
+        sB.wait_event(start)
+        pF, pB = C.c_void_p(sF.cuda_stream), C.c_void_p(sB.cuda_stream)
+        metas, keep, back_done = [], [], []
+        for idx, bi in enumerate(todo):
+            b0, b1 = self.bounds(bi)
+            nrec = (b1 - b0) * self.rpl
+            off, cnt, order = self.meta(nrec)
+            keep.append((off, cnt, order))          # allocated on self.stream, used on sF / sB: keep alive
+            batch = self.make_batch(b0, b1, arenas[idx % 2], off, cnt, self.counters[bi], order=order)
+            if idx >= 2:
+                sF.wait_event(back_done[idx - 2])   # this arena is free again
+            self.launch('extract', bi, 's3_extract', g, C.byref(batch), pF, on=sF)
+            front_done = torch.cuda.Event()
+            front_done.record(sF)
+            sB.wait_event(front_done)
+            self.launch('gather', bi, 's3_gather', g, C.byref(batch), nrec, self.out_ptrs, self.F1,
+                        b0 * self.rpl * self.nseed, pB, on=sB)
+            done = torch.cuda.Event()
+            done.record(sB)
+            back_done.append(done)
+            self.stats['launches'] += 2
+            metas.append((bi, cnt))
+        if back_done:
+            self.stream.wait_event(back_done[-1])
+        return metas, keep
+
+    def enqueue_fixed(self, todo):
+        t0 = time.perf_counter()
+        if self.overlap:
+            metas, keep = self.enqueue_fixed_overlapped(todo)
+        else:
+            metas, keep = [], None
+            arena = self.graph.arena(self.words)
+            for bi in todo:
+                off, cnt = self.enqueue_fixed_batch(bi, arena)
+                if self.return_graphs:       # the arena is recycled by the next batch: dump now
+                    self.stream.synchronize()
+                    if self.account(bi, cnt):
+                        self.dump(cnt, off, arena)
+                        continue
                 metas.append((bi, cnt))
-            if back_done:
-                st.wait_event(back_done[-1])
-            return metas, (off_all, cnt_all, order_all)
+        self.stats['host_enqueue_ms'] = 1000 * (time.perf_counter() - t0)
+        return metas, keep
 
-        def run_batch(bi, arena):
-            """Enqueue one batch; returns (cnt, off, pending) where pending finishes Plus flows."""
-            b0, b1 = bi * batch_links, min(Lk, (bi + 1) * batch_links)
-            nrec = (b1 - b0) * rpl
-            off = torch.empty((nrec, L.NOFF), dtype=torch.int64, device=dev)
-            cnt = torch.empty((nrec, L.NCNT), dtype=torch.int32, device=dev)
-            ctr = counters[bi]
-            ctr.zero_()
-            if fixed_rows:
-                order = torch.empty(nrec, dtype=torch.int32, device=dev)
-                batch = make_batch(b0, b1, arena, off, cnt, ctr, order=order)
-                timed('extract', bi, lambda: L.check(lib.s3_extract(C.byref(graph._c), C.byref(batch), st_ptr), 's3_extract'))
-                timed('gather', bi, lambda: L.check(
-                    lib.s3_gather(C.byref(graph._c), C.byref(batch), nrec, out_ptrs, F1, b0 * rpl * nseed, st_ptr), 's3_gather'))
-                stats['launches'] += 2
-                if host_out is not None:      # pipelined D2H of this batch's rows
-                    r0, r1 = b0 * rpl * nseed, b1 * rpl * nseed
-                    done = torch.cuda.Event()
-                    done.record(st)
-                    copy_stream.wait_event(done)
-                    with torch.cuda.stream(copy_stream):
-                        for k in range(K + 1):
-                            host_out[k][r0:r1].copy_(out[k][r0:r1], non_blocking=True)
-                return cnt, off, None
-            row_ptr = torch.empty(nrec + 1, dtype=torch.int64, device=dev)
-            item_ptr = torch.empty(nrec + 1, dtype=torch.int64, device=dev)
-            order = torch.empty(nrec, dtype=torch.int32, device=dev)
-            batch = make_batch(b0, b1, arena, off, cnt, ctr, row_ptr, item_ptr, order=order)
-            timed('extract', bi, lambda: L.check(lib.s3_extract(C.byref(graph._c), C.byref(batch), st_ptr), 's3_extract'))
-            L.check(lib.s3_plan(C.byref(batch), st_ptr), 's3_plan')
-            stats['launches'] += 2
-            c = ctr.cpu()                                  # sync: rows / items / errors of this batch
-            if int(c[L.CTR_ERRORS]) != 0:
-                return cnt, off, 'retry'
-            rows, items = int(c[L.CTR_ROWS]), int(c[L.CTR_ITEMS])
-            item_rec = torch.empty(max(items, 1), dtype=torch.int32, device=dev)
-            xs_b = [torch.empty((rows, F1), dtype=torch.float32, device=dev) for _ in range(K + 1)]
-            batch = make_batch(b0, b1, arena, off, cnt, ctr, row_ptr, item_ptr, item_rec, order)
-            ptrs = (C.c_void_p * (K + 1))(*[o.data_ptr() for o in xs_b])
-            timed('gather', bi, lambda: L.check(lib.s3_gather(C.byref(graph._c), C.byref(batch), nrec, ptrs, F1, 0, st_ptr), 's3_gather'))
-            stats['launches'] += 1
-            if items:       # CCN rows: extra work items of up to 8 selected rows each
-                L.check(lib.s3_plan_items(C.byref(batch), st_ptr), 's3_plan_items')
-                timed('diffuse', bi, lambda: L.check(lib.s3_diffuse(C.byref(graph._c), C.byref(batch), items, st_ptr), 's3_diffuse'))
-                timed('gather_ccn', bi, lambda: L.check(
-                    lib.s3_gather_ccn(C.byref(graph._c), C.byref(batch), items, ptrs, F1, 0, st_ptr), 's3_gather_ccn'))
-                stats['launches'] += 3
-            pieces.append(xs_b)
-            row_counts.append(row_ptr[1:] - row_ptr[:-1])
-            return cnt, off, None
+    def sync(self):
+        self.stream.synchronize()
+        if self.copy_stream is not None:
+            self.copy_stream.synchronize()
 
-        def check_and_account(bi, cnt, host_counters=None):
-            c = counters[bi].cpu() if host_counters is None else host_counters[bi]
-            if int(c[L.CTR_ERRORS]) != 0:
-                status = cnt[:, L.CNT_STATUS]
-                if bool((status == L.REC_BAD_LINK).any()):
-                    bad = int(torch.nonzero(status == L.REC_BAD_LINK)[0]) // rpl + bi * batch_links
-                    raise ValueError(f"invalid target link at position {bad}: node id out of range or src == dst")
-                return False
-            stats['sum_n'] += int(c[L.CTR_SUM_N])
-            stats['sum_d'] += int(c[L.CTR_SUM_D])
-            stats['max_n'] = max(stats['max_n'], int(c[L.CTR_MAX_N]))
-            return True
+    def finalize_fixed(self, metas):
+        """Stream sync, validation, re-run of overflowed batches with a larger arena."""
+        with torch.cuda.device(self.dev), torch.cuda.stream(self.stream):
+            while True:
+                self.sync()
+                host_counters = self.counters.cpu()       # one D2H for every batch's counters
+                todo = [bi for bi, cnt in metas if not self.account(bi, cnt, host_counters)]
+                if not todo:
+                    return
+                if self.return_graphs and self.graphs:
+                    raise RuntimeError("arena overflow while dumping graphs: pass a larger arena_words")
+                self.grow()
+                metas, _keep = self.enqueue_fixed(todo)
 
-        def dump(bi, cnt, off, arena):
-            cn, of, ar = cnt.cpu().numpy(), off.cpu().numpy(), arena.cpu().numpy()
-            for r in range(cn.shape[0]):
-                n, m, s = int(cn[r, L.CNT_N]), int(cn[r, L.CNT_M]), int(cn[r, L.CNT_S])
-                assert int(cn[r, L.CNT_NSTORE]) == n
-                nodes = ar[of[r, L.OFF_NODES]:of[r, L.OFF_NODES] + n].astype(np.int64)
-                rstart = ar[of[r, L.OFF_ROWPTR]:of[r, L.OFF_ROWPTR] + n + 1].astype(np.int64)
-                rlen = ar[of[r, L.OFF_ROWLEN]:of[r, L.OFF_ROWLEN] + n].astype(np.int64)
-                padded = ar[of[r, L.OFF_LCOL]:of[r, L.OFF_LCOL] + int(rstart[n])]
-                rowptr = np.zeros(n + 1, dtype=np.int64)      # compact the padded CSR (holes are -1)
-                np.cumsum(rlen, out=rowptr[1:])
-                lcol = padded[padded >= 0].copy()
-                owner = np.repeat(np.arange(n), np.diff(rstart))[padded >= 0]
-                assert int(rowptr[n]) == m == lcol.size and np.array_equal(np.bincount(owner, minlength=n), rlen)
-                sel = np.concatenate([np.arange(nseed), ar[of[r, L.OFF_SEL]:of[r, L.OFF_SEL] + s - nseed]]).astype(np.int32)
-                hop_cnt = cn[r, L.CNT_HOP0:L.CNT_HOP0 + L.MAX_HOPS + 1]
-                hops = np.repeat(np.arange(L.MAX_HOPS + 1), hop_cnt).astype(np.int32)
-                graphs.append(dict(nodes=nodes, hops=hops, lrowptr=rowptr, lcol=lcol, sel=sel,
-                                   partner=int(cn[r, L.CNT_PARTNER])))
+    # ------------------------------------------------------------------ PoS Plus (data-dependent rows)
+    def run_variable_batch(self, bi, arena):
+        """front -> plan -> host sync (rows, CCN items) -> gather [-> plan_items -> diffuse -> gather_ccn].
+        Returns (off, cnt, ok); not ok means the arena overflowed."""
+        g, st = C.byref(self.graph._c), self.stream_ptr
+        b0, b1 = self.bounds(bi)
+        nrec = (b1 - b0) * self.rpl
+        off, cnt, order = self.meta(nrec)
+        row_ptr = torch.empty(nrec + 1, dtype=torch.int64, device=self.dev)
+        item_ptr = torch.empty(nrec + 1, dtype=torch.int64, device=self.dev)
+        ctr = self.counters[bi]
+        ctr.zero_()
+        batch = self.make_batch(b0, b1, arena, off, cnt, ctr, row_ptr, item_ptr, order=order)
+        self.launch('extract', bi, 's3_extract', g, C.byref(batch), st)
+        L.check(self.lib.s3_plan(C.byref(batch), st), 's3_plan')
+        self.stats['launches'] += 2
+        c = ctr.cpu()                                  # sync: rows / items / errors of this batch
+        if int(c[L.CTR_ERRORS]) != 0:
+            return off, cnt, False
+        rows, items = int(c[L.CTR_ROWS]), int(c[L.CTR_ITEMS])
+        item_rec = torch.empty(max(items, 1), dtype=torch.int32, device=self.dev)
+        xs = [torch.empty((rows, self.F1), dtype=torch.float32, device=self.dev) for _ in range(self.K + 1)]
+        ptrs = (C.c_void_p * (self.K + 1))(*[o.data_ptr() for o in xs])
+        batch = self.make_batch(b0, b1, arena, off, cnt, ctr, row_ptr, item_ptr, item_rec, order)
+        self.launch('gather', bi, 's3_gather', g, C.byref(batch), nrec, ptrs, self.F1, 0, st)
+        self.stats['launches'] += 1
+        if items:       # CCN rows: extra work items of 2 (intersection) or 8 (union) selected rows each
+            L.check(self.lib.s3_plan_items(C.byref(batch), st), 's3_plan_items')
+            self.launch('diffuse', bi, 's3_diffuse', g, C.byref(batch), items, st)
+            self.launch('gather_ccn', bi, 's3_gather_ccn', g, C.byref(batch), items, ptrs, self.F1, 0, st)
+            self.stats['launches'] += 3
+        self.pieces.append(xs)
+        self.row_counts.append(row_ptr[1:] - row_ptr[:-1])
+        return off, cnt, True
 
-        def grow():
-            nonlocal words
-            stats['retries'] += 1
-            words = int(words * 2)
-            graph._arena = graph._arena2 = None       # hand the old arenas back to the driver first
-            torch.cuda.empty_cache()
-            free, _ = torch.cuda.mem_get_info(dev)
-            if words * 4 > free:
-                raise MemoryError("scratch arena does not fit in device memory; lower batch_records")
+    def run_variable(self):
+        for bi in range(self.num_batches):
+            while True:
+                arena = self.graph.arena(self.words)
+                off, cnt, ok = self.run_variable_batch(bi, arena)
+                self.stream.synchronize()
+                if ok and self.account(bi, cnt):
+                    if self.return_graphs:
+                        self.dump(cnt, off, arena)
+                    break
+                self.account(bi, cnt)      # raises on bad links
+                self.grow()
 
-        if fixed_rows:
-            # Enqueue every batch without a host sync, validate at the end; a batch whose arena
-            # overflowed is re-run (its output rows are simply rewritten) with a larger arena.
-            use_overlap = bool(overlap) and not return_graphs and nb > 1
-
-            def enqueue(todo):
-                t_enq = time.perf_counter()
-                if use_overlap:
-                    metas, keep = run_fixed_overlapped(todo, words)
-                else:
-                    metas, keep = [], None
-                    arena = graph.arena(words)
-                    for bi in todo:
-                        cnt, off, _ = run_batch(bi, arena)
-                        if return_graphs:   # the arena is recycled by the next batch: dump now
-                            st.synchronize()
-                            if check_and_account(bi, cnt):
-                                dump(bi, cnt, off, arena)
-                                continue
-                        metas.append((bi, cnt))
-                stats['host_enqueue_ms'] = 1000 * (time.perf_counter() - t_enq)
-                return metas, keep
-
-            def settle(metas):
-                """After a stream sync: account finished batches, return the ones to re-run."""
-                hc = counters.cpu()       # one D2H for every batch's counters
-                return [bi for bi, cnt in metas if not (False if return_graphs else check_and_account(bi, cnt, hc))]
-
-            def finalize(metas):
-                with torch.cuda.device(dev), torch.cuda.stream(st):
-                    st.synchronize()
-                    if copy_stream is not None:
-                        copy_stream.synchronize()
-                    todo = settle(metas)
-                    while todo:
-                        if return_graphs and graphs:
-                            raise RuntimeError("arena overflow while dumping graphs: pass a larger arena_words")
-                        grow()
-                        metas, _keep = enqueue(todo)
-                        st.synchronize()
-                        if copy_stream is not None:
-                            copy_stream.synchronize()
-                        todo = settle(metas)
-
-            metas0, keep0 = enqueue(list(range(nb)))
-            if not defer:
-                finalize(metas0)
-        else:
-            # Row counts are data dependent: one host sync per batch (inside run_batch).
-            for bi in range(nb):
-                while True:
-                    arena = graph.arena(words)
-                    cnt, off, pending = run_batch(bi, arena)
-                    st.synchronize()
-                    if pending is None and check_and_account(bi, cnt):
-                        if return_graphs:
-                            dump(bi, cnt, off, arena)
-                        break
-                    check_and_account(bi, cnt)      # raises on bad links
-                    grow()
-
-        if fixed_rows:
-            xs = [o[:2 * Lk] for o in out]
-            row_ptr = torch.arange(Lk + 1, dtype=torch.int64, device=dev) * 2
-            stats['rows'] = 2 * Lk
-        else:
-            xs = [torch.cat([p[k] for p in pieces], 0) if pieces else torch.empty((0, F1), device=dev) for k in range(K + 1)]
-            counts = torch.cat(row_counts) if row_counts else torch.zeros(0, dtype=torch.int64, device=dev)
+    # ------------------------------------------------------------------ driver
+    def run(self, defer):
+        dev, K, F1, Lk = self.dev, self.K, self.F1, self.num_links
+        with torch.cuda.device(dev), torch.cuda.stream(self.stream):
+            self.counters = torch.zeros((max(self.num_batches, 1), L.NCTR), dtype=torch.int64, device=dev)
+            if self.host_out is not None:
+                self.copy_stream = self.graph.streams()[1]
+                ready = torch.cuda.Event()
+                ready.record(self.stream)
+                self.copy_stream.wait_event(ready)
+            if self.fixed_rows:
+                R = 2 * Lk
+                if self.out is None:
+                    self.out = [torch.empty((R, F1), dtype=torch.float32, device=dev) for _ in range(K + 1)]
+                elif not (len(self.out) == K + 1 and all(o.shape[0] >= R and o.shape[1] == F1 and o.is_contiguous()
+                                                         for o in self.out)):
+                    raise ValueError("out must be K+1 contiguous [>= 2L, F+1] float32 tensors")
+                self.out_ptrs = (C.c_void_p * (K + 1))(*[o.data_ptr() for o in self.out])
+                metas, keep = self.enqueue_fixed(list(range(self.num_batches)))
+                xs = [o[:R] for o in self.out]
+                row_ptr = torch.arange(Lk + 1, dtype=torch.int64, device=dev) * 2
+                self.stats['rows'] = R
+                result = PrecomputeResult(xs, row_ptr, self.stats, self.graphs)
+                result._keep = keep
+                result._finalize = lambda: self.finalize_fixed(metas)
+                return result if defer else result.finalize()
+            self.run_variable()
+            xs = [torch.cat([p[k] for p in self.pieces], 0) if self.pieces else torch.empty((0, F1), device=dev)
+                  for k in range(K + 1)]
+            counts = torch.cat(self.row_counts) if self.row_counts else torch.zeros(0, dtype=torch.int64, device=dev)
             row_ptr = torch.zeros(Lk + 1, dtype=torch.int64, device=dev)
             torch.cumsum(counts, 0, out=row_ptr[1:])
-            stats['rows'] = int(xs[0].shape[0])
-    result = PrecomputeResult(xs, row_ptr, stats, graphs)
-    if fixed_rows and defer:
-        result._finalize = lambda: finalize(metas0)
-        result._keep = keep0
-    return result
+            self.stats['rows'] = int(xs[0].shape[0])
+            return PrecomputeResult(xs, row_ptr, self.stats, self.graphs)
+
+
+def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_records=32768, out=None,
+               return_graphs=False, arena_words=None, stream=None, profile=None, overlap=False, defer=False,
+               host_out=None, force_sorted_tier=False):
+    """Run the hot path for `links` ([2, L] int64, host or device) on `graph`; returns a
+    PrecomputeResult with device tensors.
+
+    out            K+1 preallocated [>= 2L, F+1] float32 device tensors (fixed-row flows only).
+    profile        a list that receives (stage, batch, start_event, end_event) for every kernel launch,
+                   so the caller can time each kernel on its launching stream with CUDA events.
+    overlap        (fixed-row flows) front kernel of batch i+1 on one stream while the gather of batch i
+                   runs on another, with two arenas.  Measured gain on PubMed: ~1.5 %; off by default.
+    host_out       (fixed-row flows) K+1 pinned host tensors [>= 2L, F+1]: every batch's rows are copied
+                   device->host on a side stream as soon as its gather finishes, so the D2H of batch i
+                   overlaps the kernels of batch i+1 (the reference returns CPU tensors).
+    defer          (fixed-row flows) return right after enqueueing; the caller must call
+                   `result.finalize()` (stream sync + validation + re-run of overflowed batches) before
+                   using the outputs.  Lets several calls be queued back to back.
+    return_graphs  also return every record's canonical nodes / hops / local CSR (parity tests).
+    Raises ValueError for invalid links (out of range, src == dst), NotImplementedError for an unknown
+    strategy (as reference tuned_SIGN.py:235) or an unsupported combination."""
+    call = _Call(graph, links, num_hops, sign_k, flow, strategy, batch_records, out, return_graphs, arena_words,
+                 stream, profile, overlap, host_out, force_sorted_tier)
+    return call.run(defer)
 
 
 def algorithmic_bytes(stats, num_feat, sign_k):
