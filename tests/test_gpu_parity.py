@@ -67,10 +67,10 @@ def test_sop_against_reference_goldens(name):
         assert_features_close(res.xs[k].cpu().numpy(), c.xs[k], what=f'{name} x{k}')
 
 
-def _random_graph(rng, N, E):
+def _random_graph(rng, N, E, self_loops=False):
     u = rng.integers(0, N, E)
     v = rng.integers(0, N, E)
-    keep = u != v
+    keep = (u != v) | self_loops
     e = np.unique(np.stack([np.minimum(u, v)[keep], np.maximum(u, v)[keep]], 1), axis=0)
     return ds.adjacency(e, N)
 
@@ -79,6 +79,8 @@ def _random_graph(rng, N, E):
     (0, 60, 90, 7, 2, 3, None), (1, 200, 500, 33, 3, 3, 'intersection'), (2, 200, 900, 12, 2, 3, 'union'),
     (3, 1000, 1500, 130, 3, 2, None), (4, 333, 2000, 5, 1, 5, 'union'), (5, 97, 300, 64, 2, 4, 'intersection'),
     (6, 50, 40, 1, 3, 1, None), (7, 3000, 9000, 260, 2, 3, None), (8, 40, 500, 9, 2, 7, None),
+    (9, 400, 450, 6, 5, 2, None), (10, 300, 400, 10, 4, 6, 'intersection'), (11, 150, 200, 3, 8, 3, None),
+    (12, 5000, 6000, 20, 3, 3, 'union'),
 ])
 def test_pos_against_oracle_random_graphs(seed, N, E, F, h, K, strategy):
     rng = np.random.default_rng(seed)
@@ -335,3 +337,28 @@ def test_sop_and_k5_through_reference_interface():
         Ops.get_PoS_prepped_ds(torch.from_numpy(c.links), 2, c.A, 0.5, None, False, None, torch.from_numpy(c.X), 0, kw, None)
     with pytest.raises(NotImplementedError):
         Ops.get_PoS_prepped_ds(torch.from_numpy(c.links), 2, c.A, 1.0, 50, False, None, torch.from_numpy(c.X), 0, kw, None)
+
+
+def test_self_loops_follow_the_reference_semantics():
+    """A[nodes,:][:,nodes] keeps diagonal entries (utils.py:76): a self loop is an edge (j, j) of the
+    induced subgraph, counts in the degree and carries weight.  Both tiers, against the oracle."""
+    rng = np.random.default_rng(77)
+    u = rng.integers(0, 120, 400)
+    v = rng.integers(0, 120, 400)
+    v[:60] = u[:60]                                   # 60 self loops
+    row, col = np.r_[u, v], np.r_[v, u]
+    import scipy.sparse as ssp
+    A = ssp.csr_matrix((np.ones(row.size, np.int64), (row, col)), shape=(120, 120))
+    A.sum_duplicates()
+    A.data[:] = 1
+    X = rng.random((120, 11), dtype=np.float32)
+    links = rng.integers(0, 120, (2, 50))
+    links = links[:, links[0] != links[1]]
+    g = DeviceGraph(A, X)
+    for h, K, kw in ((2, 3, {}), (1, 3, {}), (1, 3, dict(force_sorted_tier=True)), (3, 2, {})):
+        ref = orc.pos_precompute(links, h, A, X, K, None, keep_graphs=True)
+        res = precompute(g, links, h, K, return_graphs=True, **kw)
+        for i, (gg, r) in enumerate(zip(res.graphs, ref['graphs'])):
+            _check_indices(gg, r, f'h={h} link {i}')
+        for k in range(K + 1):
+            assert_features_close(res.xs[k].cpu().numpy(), ref['xs'][k], what=f'h={h} x{k}')
