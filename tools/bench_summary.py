@@ -1,3 +1,5 @@
+import signal
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
