@@ -243,7 +243,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='pubmed_pos')
-    ap.add_argument('--batch-records', type=int, default=32768)
+    ap.add_argument('--batch-records', type=int, default=None)
     ap.add_argument('--cpu-links-per-core', type=int, default=400)
     ap.add_argument('--e2e-steps', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -457,7 +457,7 @@ def main():
         line = dict(metric=metric_name(args.workload), value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=ms_max / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="f32", data="synthetic",
-                    config=dict(workload=w['desc'], links_per_step_per_gpu=Lk, batch_records=args.batch_records,
+                    config=dict(workload=w['desc'], links_per_step_per_gpu=Lk, batch_records=args.batch_records or "auto (32768 for fixed-row flows)",
                                 l2="flushed between steps (256 MiB memset); PubMed's X (39 MB) is L2-resident within a step by "
                                    "nature of the workload, the R-MAT X (5 GB) is not",
                                 parallelism=f"links sharded x{world}, graph replicated, no data-path collective"),

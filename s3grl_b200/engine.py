@@ -185,9 +185,13 @@ class _Call:
         self.host_out, self.copy_stream = host_out, None
         if host_out is not None and (not self.fixed_rows or overlap):
             raise ValueError("host_out needs a fixed-row flow without overlap")
-        if not self.fixed_rows:
-            # every batch keeps its own output pieces and CCN work items multiply the float scratch
-            batch_records = min(int(batch_records), 4096 if self.strategy == L.STRATEGY_UNION else 16384)
+        if batch_records is None:
+            # fixed rows: 32 Ki records amortise the launch tails.  PoS Plus ends every batch with a host
+            # sync, so intersection (small scratch) takes everything in as few batches as memory allows;
+            # union multiplies the float scratch by the CCN work items and stays small.
+            free, _ = torch.cuda.mem_get_info(self.dev)
+            batch_records = {L.STRATEGY_NONE: 32768, L.STRATEGY_INTERSECTION: 262144, L.STRATEGY_UNION: 8192}[self.strategy]
+            batch_records = max(1024, min(batch_records, int(free // 3 // (32768 * 4))))
         self.batch_links = max(1, int(batch_records) // self.rpl)
         self.num_batches = (self.num_links + self.batch_links - 1) // self.batch_links
         self.overlap = bool(overlap) and self.fixed_rows and not self.return_graphs and self.num_batches > 1
@@ -465,12 +469,14 @@ class _Call:
             return PrecomputeResult(xs, row_ptr, self.stats, self.graphs)
 
 
-def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_records=32768, out=None,
+def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_records=None, out=None,
                return_graphs=False, arena_words=None, stream=None, profile=None, overlap=False, defer=False,
                host_out=None, force_sorted_tier=False):
     """Run the hot path for `links` ([2, L] int64, host or device) on `graph`; returns a
     PrecomputeResult with device tensors.
 
+    batch_records  records per batch (default: 32768 for fixed-row flows, as many as memory allows for
+                   PoS Plus intersection, 8192 for union).
     out            K+1 preallocated [>= 2L, F+1] float32 device tensors (fixed-row flows only).
     profile        a list that receives (stage, batch, start_event, end_event) for every kernel launch,
                    so the caller can time each kernel on its launching stream with CUDA events.
