@@ -302,7 +302,7 @@ class _Call:
         row_base = b0 * self.rpl * self.nseed
         self.launch('extract', bi, 's3_extract', g, C.byref(batch), st)
         self.launch('gather', bi, 's3_gather', g, C.byref(batch), nrec, self.out_ptrs, self.F1, row_base, st)
-        self.stats['launches'] += 2
+        self.stats['launches'] += 3         # front kernel, order kernel, gather kernel
         if self.host_out is not None:      # pipelined D2H of this batch's rows
             r0, r1 = row_base, b1 * self.rpl * self.nseed
             done = torch.cuda.Event()
@@ -342,7 +342,7 @@ class _Call:
             done = torch.cuda.Event()
             done.record(sB)
             back_done.append(done)
-            self.stats['launches'] += 2
+            self.stats['launches'] += 3
             metas.append((bi, cnt))
         if back_done:
             self.stream.wait_event(back_done[-1])
@@ -400,7 +400,7 @@ class _Call:
         batch = self.make_batch(b0, b1, arena, off, cnt, ctr, row_ptr, item_ptr, order=order)
         self.launch('extract', bi, 's3_extract', g, C.byref(batch), st)
         L.check(self.lib.s3_plan(C.byref(batch), st), 's3_plan')
-        self.stats['launches'] += 2
+        self.stats['launches'] += 3         # front kernel, order kernel, plan scan
         c = ctr.cpu()                                  # sync: rows / items / errors of this batch
         if int(c[L.CTR_ERRORS]) != 0:
             return off, cnt, False
