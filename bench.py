@@ -47,6 +47,14 @@ def metric_name(workload):
 # ----------------------------------------------------------------------------------------
 def build_workload(name):
     from s3grl_b200 import datasets as ds
+    if name == 'pubmed_scaled':      # ScaLed random-walk subgraphs, configs/paper/scaled.json (m=3, M=20)
+        edges, N, _ = ds.load_graph('pubmed')
+        A, splits = ds.split_links(edges, N, seed=1)
+        X = ds.synthetic_features(N, 500, 0.1, 0)
+        links = ds.all_links(splits)
+        return dict(A=A, X=X, links=links, num_hops=0, K=3, flow='PoS', strategy=None, walk=dict(m=3, M=20, seed=0),
+                    desc=f"PubMed graph, synthetic X F=500, all {links.shape[1]} links, ScaLed random-walk subgraphs "
+                         f"m=3 M=20 (walks sampled inside every step), PoS sign_k=3")
     if name in ('pubmed_pos', 'pubmed_posplus_union', 'pubmed_posplus_intersection'):
         edges, N, _ = ds.load_graph('pubmed')
         A, splits = ds.split_links(edges, N, seed=1)
@@ -141,7 +149,11 @@ def _cpu_init(w):
 def _cpu_chunk(cols):
     from oracle import s3grl_oracle as orc
     w = _W
-    if w['flow'] == 'SoP':
+    if w.get('walk'):
+        sub = w['links'][:, cols]
+        sets = orc.random_walk_sets(w['A'], sub.reshape(-1), w['walk']['m'], w['walk']['M'], w['walk']['seed'])
+        out = orc.scaled_pos_precompute(sub, sets, w['A'], w['X'], w['K'])
+    elif w['flow'] == 'SoP':
         if 'sop_powers' not in w:       # the reference builds the global powers once per split
             w['sop_powers'] = orc.sop_powers(w['A'], w['K'])
         out = orc.sop_precompute(w['links'][:, cols], w['A'], w['X'], w['K'], powers=w['sop_powers'])
@@ -326,7 +338,7 @@ def main():
         flush.zero_()               # L2 flush between steps
         return precompute(g, links_dev, w['num_hops'], K, w['flow'], w['strategy'],
                           batch_records=args.batch_records, out=out, profile=profile, overlap=args.overlap,
-                          defer=defer and fixed)
+                          defer=defer and fixed, walk=w.get('walk'))
 
     # the sampler starts before the warm-up so that nvidia-smi's own start-up (driver queries)
     # is over when the timed region begins
@@ -430,8 +442,10 @@ def main():
 
         def e2e_step():
             tuned_sign._graph_cache.clear()       # the graph upload is part of every step
+            rw_kwargs = dict(rw_m=w['walk']['m'], rw_M=w['walk']['M'], seed=w['walk']['seed'], sign=True) if w.get('walk') else None
             lst = extract_enclosing_subgraphs(link_index, w['A'], x_host, 1, w['num_hops'], 'zo', 1.0, None, False,
-                                              None, None, sign_kwargs, powers_of_A=[], data=None)
+                                              None, rw_kwargs, sign_kwargs, powers_of_A=[] if w['flow'] == 'PoS' else [None] * K,
+                                              data=None)
             d2h = sum(x.numel() * 4 for x in lst.xs) + lst.row_ptr.numel() * 8
             chk = float(lst.xs[-1][0, 0])        # touch the host result
             return d2h, chk

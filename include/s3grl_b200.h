@@ -156,6 +156,16 @@ typedef struct s3_batch {
      * (largest subgraphs first) and s3_gather schedules its CTAs in that order, which trims the
      * tail of the launch. Results do not depend on it. */
     int32_t* order;
+    /* ScaLed random-walk subgraphs (reference utils.py:86-150): when walk_sets is not NULL the
+     * subgraph of link i is {src, dst} ∪ set[link_src_set[i]] ∪ set[link_dst_set[i]] instead of an
+     * h-hop ball; sets come from s3_walk_sets (or from the caller). PoS, S3_STRATEGY_NONE only;
+     * num_hops is ignored (the reference passes 0). */
+    const int32_t* walk_sets;     /* [num_sets, walk_cap] ascending unique node ids          */
+    const int32_t* walk_counts;   /* [num_sets]                                              */
+    const int64_t* link_src_set;  /* [num_links] row of walk_sets of every link's source     */
+    const int64_t* link_dst_set;  /* [num_links] ... destination                             */
+    int32_t walk_cap;
+    int32_t reserved2;
 } s3_batch;
 
 int s3_version(void);
@@ -196,6 +206,13 @@ int s3_gather(const s3_graph* g, const s3_batch* b, int64_t num_records,
               float* const* out, int64_t ldo, int64_t row_base, void* stream);
 int s3_gather_ccn(const s3_graph* g, const s3_batch* b, int64_t num_items,
                   float* const* out, int64_t ldo, int64_t row_base, void* stream);
+
+/* ScaLed: sorted node sets of rw_M uniform random walks of length rw_m from every
+ * start node — replaces reference utils.py:425-443 (create_rw_cache). sets is [num_starts, cap]
+ * with cap >= 1 + rw_M*rw_m (a set can not be larger); counts[i] receives the size of set i.
+ * Counter-based RNG: set i depends only on (seed, starts[i]). */
+int s3_walk_sets(const s3_graph* g, const int64_t* starts, int64_t num_starts, int32_t rw_m, int32_t rw_M,
+                 uint64_t seed, int32_t cap, int32_t* sets, int32_t* counts, void* stream);
 
 /* Optional dumps for parity checks: canonical global-id edge list of every record,
  * edges[e] = (global row, global col), e in [edge_ptr[r], edge_ptr[r+1]). */

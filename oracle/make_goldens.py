@@ -86,6 +86,34 @@ def make_case(name, A, links, flow, K, num_hops=0, strategy=None, X=None, x_spec
           f"-> {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def make_scaled_case(name, A, links, K, x_spec, rw_m=3, rw_M=20, seed=5):
+    """ScaLed (configs/paper/scaled.json: m = 3, M = 20, num_hops = 0): the walk sets are drawn here
+    with NumPy and stored in the fixture — the reference's own sampler (torch_cluster.random_walk) is
+    not available — and the REFERENCE code turns them into subgraphs and operators."""
+    from oracle import s3grl_oracle as orc
+    A = A.tocsr()
+    A.sort_indices()
+    N = A.shape[0]
+    feats = features_from_spec(x_spec, A, N)
+    links = np.ascontiguousarray(links, dtype=np.int64)
+    sets = orc.random_walk_sets(A, links.reshape(-1), rw_m, rw_M, seed)
+    r = rr.ref_scaled_pos(links, A, feats, K, sets)
+    keys = np.array(sorted(sets), dtype=np.int64)
+    cap = max(v.size for v in sets.values())
+    table = np.full((keys.size, cap), -1, dtype=np.int32)
+    for i, k in enumerate(keys):
+        table[i, :sets[int(k)].size] = sets[int(k)]
+    out = dict(indptr=A.indptr.astype(np.int64), indices=A.indices.astype(np.int32), adata=A.data.astype(np.int64),
+               num_nodes=np.int64(N), links=links, num_hops=np.int64(0), K=np.int64(K), flow=np.str_('scaled'),
+               strategy=np.str_(''), row_ptr=r['row_ptr'], x_spec=np.str_(x_spec), set_nodes=keys, set_table=table,
+               rw_m=np.int64(rw_m), rw_M=np.int64(rw_M))
+    for k, x in enumerate(r['xs']):
+        out[f'x{k}'] = x.astype(np.float32)
+    path = os.path.join(OUT, f'ref_{name}.npz')
+    np.savez_compressed(path, **out)
+    print(f"{name}: L={links.shape[1]} sets={keys.size} cap={cap} -> {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 def tiny_graphs():
     """Hand graphs for the edge cases of SURVEY.md A.6: isolated endpoints, n == 2, an
     endpoint whose only neighbour is the other endpoint, pendant paths, a hub, two components."""
@@ -124,6 +152,8 @@ def main():
     make_case('cora_pos', A, sample_links(splits, 160, 1), 'pos', 3, 3, None, x_spec='synthetic:24:0.3:5')
     make_case('cora_posplus', A, sample_links(splits, 160, 2), 'pos', 3, 3, 'intersection',
               x_spec='synthetic:24:0.3:5')
+
+    make_scaled_case('cora_scaled', A, sample_links(splits, 120, 6), 3, 'synthetic:24:0.3:5')
 
     edges, N, _ = ds.load_graph('usair')
     A, splits = ds.split_links(edges, N, seed=1)

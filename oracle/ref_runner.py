@@ -147,3 +147,24 @@ def ref_sop(links, A, X, K):
     keys = ['x'] + [f'x{k}' for k in range(1, K + 1)]
     xs = [np.concatenate([np.asarray(d[key], dtype=np.float32) for d in data_list], 0) for key in keys]
     return dict(xs=xs, row_ptr=np.arange(len(data_list) + 1, dtype=np.int64) * 2)
+
+
+def ref_scaled_pos(links, A, X, K, sets):
+    """ScaLed through the reference's own code: get_PoS_prepped_ds with rw_kwargs carrying a walk
+    cache (utils.py:94-105 picks cached_pos_rws for y = 1) -> dict(xs, row_ptr).  `sets` is
+    {node: array}; the walks themselves are an input (the reference draws them with
+    torch_cluster.random_walk, which is not available here)."""
+    utils, tuned = load_reference()
+    from torch_geometric.data import Data
+    link_index = torch.as_tensor(np.asarray(links), dtype=torch.long)
+    x = torch.as_tensor(np.asarray(X), dtype=torch.float32)
+    cache = {int(k): torch.as_tensor(v, dtype=torch.long) for k, v in sets.items()}
+    data = Data(x=x, num_nodes=A.shape[0])
+    rw_kwargs = dict(rw_m=3, rw_M=20, sparse_adj=None, edge_index=None, device='cpu', data=data, node_label='zo',
+                     cached_pos_rws=cache, cached_neg_rws=cache, sign=True)
+    with _quiet():
+        data_list = tuned.OptimizedSignOperations.get_PoS_prepped_ds(
+            link_index, 0, A, 1.0, None, False, None, x, 1, _sign_kwargs(K, None), rw_kwargs)
+    keys = ['x'] + [f'x{k}' for k in range(1, K + 1)]
+    xs = [np.concatenate([np.asarray(d[key], dtype=np.float32) for d in data_list], 0) for key in keys]
+    return dict(xs=xs, row_ptr=np.arange(len(data_list) + 1, dtype=np.int64) * 2)

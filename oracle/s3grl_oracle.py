@@ -16,6 +16,7 @@ node order so results can be compared bit-exactly on indices:
   sgrl_link_pred.py:161-178 SoP global powers `sop_powers`
   tuned_SIGN.py:49-134  get_SoP_prepped_ds    `sop_link`
   utils.py:454-480 hybrid                     `hybrid_precompute`
+  utils.py:86-150, :425-443 ScaLed walks      `random_walk_sets`, `scaled_pos_link`
   models.py:372    joint matrix layout        `joint_matrix`
 
 Pinning (see tests/test_oracle_vs_reference.py, oracle/make_goldens.py): the reference has
@@ -86,6 +87,14 @@ def k_hop_subgraph(src, dst, num_hops, A):
         hops.append(np.full(fringe.size, dist, dtype=np.int32))
     nodes = np.concatenate(nodes)
     hops = np.concatenate(hops)
+    lrowptr, lcol = _induced_masked(nodes, A)
+    return nodes, hops, lrowptr, lcol
+
+
+def _induced_masked(nodes, A):
+    """utils.py:76-80 — A[nodes,:][:,nodes] with the target link (0,1)/(1,0) removed, as a local CSR
+    with ascending columns (pattern only)."""
+    indptr, indices = A.indptr, A.indices
     n = nodes.size
     local = np.full(A.shape[0], -1, dtype=np.int64)
     local[nodes] = np.arange(n)
@@ -101,7 +110,7 @@ def k_hop_subgraph(src, dst, num_hops, A):
         cols.append(c)
         lrowptr[i + 1] = lrowptr[i] + c.size
     lcol = np.concatenate(cols).astype(np.int32) if cols else np.empty(0, np.int32)
-    return nodes, hops, lrowptr, lcol
+    return lrowptr, lcol
 
 
 def select_rows(lrowptr, lcol, strategy):
@@ -153,6 +162,59 @@ def pos_link(src, dst, num_hops, A, X, K, strategy=None, dtype=np.float32):
             P = (S @ P).astype(dtype)               # powers by SpGEMM, tuned_SIGN.py:168-170
         xs.append(np.asarray(P[sel] @ subg_x, dtype=dtype))
     return dict(nodes=nodes, hops=hops, lrowptr=lrowptr, lcol=lcol, sel=sel, xs=xs)
+
+
+def random_walk_sets(A, starts, rw_m, rw_M, seed=0):
+    """utils.py:425-443 (create_rw_cache): for every start node the sorted set of nodes visited by
+    rw_M uniform random walks of length rw_m (torch_cluster.random_walk, p = q = 1; a node without
+    neighbours stays put).  NumPy RNG: same distribution as the reference and as the CUDA kernel,
+    not the same stream.  Returns {node: int64 array}."""
+    rng = np.random.default_rng(seed)
+    indptr, indices = A.indptr, A.indices
+    out = {}
+    for s in np.unique(np.asarray(starts)):
+        seen = {int(s)}
+        for _ in range(rw_M):
+            cur = int(s)
+            for _ in range(rw_m):
+                d = indptr[cur + 1] - indptr[cur]
+                if d > 0:
+                    cur = int(indices[indptr[cur] + rng.integers(0, d)])
+                seen.add(cur)
+        out[int(s)] = np.array(sorted(seen), dtype=np.int64)
+    return out
+
+
+def scaled_pos_link(src, dst, sets, A, X, K, dtype=np.float32):
+    """ScaLed + optimised PoS (utils.py:94-150 with rw_kwargs['sign'], then tuned_SIGN.py:153-187):
+    nodes = [src, dst] + ascending(set(src) ∪ set(dst) − {src, dst}); induced, masked subgraph; the
+    usual diffusion with rows [0, 1]."""
+    rest = np.union1d(sets[int(src)], sets[int(dst)])
+    rest = rest[(rest != src) & (rest != dst)]
+    nodes = np.concatenate([[src, dst], rest]).astype(np.int64)
+    lrowptr, lcol = _induced_masked(nodes, A)
+    S, _ = normalized_subgraph(lrowptr, lcol, dtype)
+    label = np.zeros((nodes.size, 1), dtype=dtype)
+    label[:2] = 1
+    subg_x = np.hstack([label, np.asarray(X[nodes], dtype=dtype)])
+    xs = [subg_x[:2]]
+    P = S
+    for k in range(1, K + 1):
+        if k > 1:
+            P = (S @ P).astype(dtype)
+        xs.append(np.asarray(P[:2] @ subg_x, dtype=dtype))
+    hops = np.r_[0, 0, np.ones(nodes.size - 2, dtype=np.int32)].astype(np.int32)
+    return dict(nodes=nodes, hops=hops, lrowptr=lrowptr, lcol=lcol, sel=np.array([0, 1], np.int32), xs=xs)
+
+
+def scaled_pos_precompute(links, sets, A, X, K, dtype=np.float32, keep_graphs=False):
+    links = np.asarray(links)
+    per = [scaled_pos_link(int(links[0, i]), int(links[1, i]), sets, A, X, K, dtype) for i in range(links.shape[1])]
+    xs = [np.concatenate([p['xs'][k] for p in per], 0) for k in range(K + 1)]
+    out = dict(xs=xs, row_ptr=np.arange(links.shape[1] + 1, dtype=np.int64) * 2)
+    if keep_graphs:
+        out['graphs'] = per
+    return out
 
 
 def pos_precompute(links, num_hops, A, X, K, strategy=None, dtype=np.float32, keep_graphs=False):

@@ -19,7 +19,7 @@ CTR_CURSOR, CTR_ERRORS, CTR_ROWS, CTR_ITEMS, CTR_MAX_N, CTR_SUM_N, CTR_SUM_D, CT
 
 EXPORTS = ['s3_version', 's3_error_string', 's3_last_cuda_error', 's3_num_records', 's3_extract_smem_bytes',
            's3_min_arena_words', 's3_extract_tier',
-           's3_extract', 's3_plan', 's3_plan_items', 's3_diffuse', 's3_gather', 's3_gather_ccn', 's3_dump_edges']
+           's3_extract', 's3_plan', 's3_plan_items', 's3_diffuse', 's3_gather', 's3_gather_ccn', 's3_walk_sets', 's3_dump_edges']
 
 
 class Graph(C.Structure):
@@ -34,7 +34,9 @@ class Batch(C.Structure):
                 ('flags', C.c_int32), ('reserved', C.c_int32),
                 ('arena', C.c_void_p), ('arena_words', C.c_int64),
                 ('off', C.c_void_p), ('cnt', C.c_void_p), ('counters', C.c_void_p),
-                ('row_ptr', C.c_void_p), ('item_ptr', C.c_void_p), ('item_rec', C.c_void_p), ('order', C.c_void_p)]
+                ('row_ptr', C.c_void_p), ('item_ptr', C.c_void_p), ('item_rec', C.c_void_p), ('order', C.c_void_p),
+                ('walk_sets', C.c_void_p), ('walk_counts', C.c_void_p), ('link_src_set', C.c_void_p),
+                ('link_dst_set', C.c_void_p), ('walk_cap', C.c_int32), ('reserved2', C.c_int32)]
 
 
 class S3Error(RuntimeError):
@@ -74,8 +76,11 @@ def lib():
         L.s3_gather.argtypes = [C.POINTER(Graph), C.POINTER(Batch), C.c_int64, C.POINTER(C.c_void_p),
                                 C.c_int64, C.c_int64, C.c_void_p]
         L.s3_gather_ccn.argtypes = L.s3_gather.argtypes
+        L.s3_walk_sets.argtypes = [C.POINTER(Graph), C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, C.c_int32,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]
         L.s3_dump_edges.argtypes = [C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p]
-        for fn in ('s3_extract', 's3_plan', 's3_plan_items', 's3_diffuse', 's3_gather', 's3_gather_ccn', 's3_dump_edges'):
+        for fn in ('s3_extract', 's3_plan', 's3_plan_items', 's3_diffuse', 's3_gather', 's3_gather_ccn', 's3_walk_sets',
+                   's3_dump_edges'):
             getattr(L, fn).restype = C.c_int
         _lib = L
     return _lib

@@ -60,6 +60,9 @@ int64_t s3_num_records(const s3_batch* b) { return b->flow == S3_FLOW_SOP ? 2 * 
 
 int s3_extract_tier(const s3_graph* g, const s3_batch* b) {
     if (!g || !b) return -1;
+    if (b->walk_sets)  // ScaLed: always the sorted-set tier
+        return (b->flow == S3_FLOW_POS && b->strategy == S3_STRATEGY_NONE && b->walk_counts && b->link_src_set &&
+                b->link_dst_set && b->walk_cap > 0) ? 1 : -1;
     const int radius = b->flow == S3_FLOW_POS ? b->num_hops : b->sign_k;
     const bool bitmap_ok = s3_extract_smem_bytes(g->num_nodes, radius) >= 0 && g->num_edges < (int64_t(1) << 32);
     const bool sorted_ok = b->flow == S3_FLOW_POS && b->num_hops == 1 && b->strategy == S3_STRATEGY_NONE;
@@ -68,7 +71,8 @@ int s3_extract_tier(const s3_graph* g, const s3_batch* b) {
 }
 
 int64_t s3_min_arena_words(const s3_graph* g, const s3_batch* b) {
-    if (s3_extract_tier(g, b) == 1) return 2 * ((2 * (g->max_degree + 1) + 31) & ~int64_t(31));
+    if (s3_extract_tier(g, b) == 1)
+        return 2 * ((2 * ((b->walk_sets ? (int64_t)b->walk_cap : g->max_degree) + 1) + 31) & ~int64_t(31));
     return 2 * ((4 * g->num_nodes + 1 + 31) & ~int64_t(31));
 }
 
@@ -144,6 +148,17 @@ int s3_gather(const s3_graph* g, const s3_batch* b, int64_t num_records, float* 
 int s3_gather_ccn(const s3_graph* g, const s3_batch* b, int64_t num_items, float* const* out, int64_t ldo, int64_t row_base,
                   void* stream) {
     return gather_impl(g, b, num_items, out, ldo, row_base, 1, stream);
+}
+
+int s3_walk_sets(const s3_graph* g, const int64_t* starts, int64_t num_starts, int32_t rw_m, int32_t rw_M, uint64_t seed,
+                 int32_t cap, int32_t* sets, int32_t* counts, void* stream) {
+    int rc = check_graph(g, false);
+    if (rc != S3_OK) return rc;
+    if (num_starts < 0 || rw_m < 0 || rw_M < 1 || (int64_t)rw_M * (rw_m + 1) > 8192 || cap < 1 + rw_M * rw_m) return S3_ERR_INVALID_ARG;
+    if (num_starts > 0 && (!starts || !sets || !counts)) return S3_ERR_INVALID_ARG;
+    cudaError_t e = s3::launch_walk_sets(*g, starts, num_starts, rw_m, rw_M, seed, cap, sets, counts,
+                                         static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? S3_OK : cuda_fail(e);
 }
 
 int s3_dump_edges(const s3_batch* b, const int64_t* edge_ptr, int32_t* edges_out, void* stream) {

@@ -35,6 +35,12 @@ struct SortedParams {
     const int64_t* __restrict__ link_dst;
     int64_t num_records;
     int sign_k, store_all;
+    // ScaLed: node lists come from per-node random-walk sets instead of the adjacency lists
+    const int32_t* __restrict__ walk_sets;    // [num_sets, walk_cap] ascending unique, or null
+    const int32_t* __restrict__ walk_counts;  // [num_sets]
+    const int64_t* __restrict__ src_set;      // [num_records] row of walk_sets for the source / destination
+    const int64_t* __restrict__ dst_set;
+    int walk_cap;
     int32_t* arena;
     int64_t arena_words;
     int64_t slab_stride;  // words per CTA slab: prefix arrays of both adjacency lists
@@ -329,10 +335,24 @@ __global__ void __launch_bounds__(kExtractThreads, 4) front_sorted_kernel(Sorted
             continue;
         }
         const int u = (int)a64, v = (int)b64;
-        const int64_t eu0 = p.indptr[u], ev0 = p.indptr[v];
-        const int du = (int)(p.indptr[u + 1] - eu0), dv = (int)(p.indptr[v + 1] - ev0);
-        const int32_t* __restrict__ A = p.indices + eu0;
-        const int32_t* __restrict__ B = p.indices + ev0;
+        // the two sorted node lists whose union (plus u, v) is the subgraph: adjacency lists
+        // (num_hops = 1) or random-walk sets (ScaLed, utils.py:102-105)
+        const int32_t* __restrict__ A;
+        const int32_t* __restrict__ B;
+        int du, dv;
+        if (p.walk_sets) {
+            const int64_t ia = p.src_set[rec], ib = p.dst_set[rec];
+            A = p.walk_sets + ia * p.walk_cap;
+            B = p.walk_sets + ib * p.walk_cap;
+            du = p.walk_counts[ia];
+            dv = p.walk_counts[ib];
+        } else {
+            const int64_t eu0 = p.indptr[u], ev0 = p.indptr[v];
+            A = p.indices + eu0;
+            B = p.indices + ev0;
+            du = (int)(p.indptr[u + 1] - eu0);
+            dv = (int)(p.indptr[v + 1] - ev0);
+        }
         int32_t* PB = PA + du + 1;  // [dv + 1]
 
         // ---- keep flags and their exclusive prefix sums: A minus {u,v}; B minus {u,v} minus A ----
@@ -610,6 +630,11 @@ cudaError_t launch_extract_sorted(const s3_graph& g, const s3_batch& b, cudaStre
     p.num_records = b.num_links;
     p.sign_k = b.sign_k;
     p.store_all = (b.flags & S3_BATCH_STORE_ALL_ROWS) ? 1 : 0;
+    p.walk_sets = b.walk_sets;
+    p.walk_counts = b.walk_counts;
+    p.src_set = b.link_src_set;
+    p.dst_set = b.link_dst_set;
+    p.walk_cap = b.walk_cap;
     p.arena = b.arena;
     p.arena_words = b.arena_words;
     p.off = b.off;
@@ -627,7 +652,7 @@ cudaError_t launch_extract_sorted(const s3_graph& g, const s3_batch& b, cudaStre
         if (e != cudaSuccess) return e;
         c_dev = dev;
     }
-    p.slab_stride = (2 * (g.max_degree + 1) + 31) & ~int64_t(31);
+    p.slab_stride = (2 * ((b.walk_sets ? (int64_t)b.walk_cap : g.max_degree) + 1) + 31) & ~int64_t(31);
     int64_t grid = (int64_t)c_sms * (c_occ > 0 ? c_occ : 1);
     if (grid > p.num_records) grid = p.num_records;
     const int64_t fit = (b.arena_words / 2) / p.slab_stride;

@@ -149,6 +149,37 @@ class PrecomputeResult:
         return self
 
 
+def walk_sets(graph, starts, rw_m, rw_M, seed=0, stream=None):
+    """ScaLed (reference utils.py:425-443, create_rw_cache): sorted node sets of `rw_M` uniform random
+    walks of length `rw_m` from every node in `starts` (int64 tensor).  Returns (sets int32 [S, cap],
+    counts int32 [S]) on the graph's device.  Counter-based RNG: a node's set depends only on
+    (seed, node), never on the other nodes of the call."""
+    lib = L.lib()
+    dev = graph.device
+    starts = torch.as_tensor(starts).to(device=dev, dtype=torch.int64).contiguous()
+    S = int(starts.numel())
+    cap = 1 + int(rw_M) * int(rw_m)
+    sets = torch.empty((S, cap), dtype=torch.int32, device=dev)
+    counts = torch.empty(S, dtype=torch.int32, device=dev)
+    st = stream if stream is not None else torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        L.check(lib.s3_walk_sets(C.byref(graph._c), _ptr(starts), S, int(rw_m), int(rw_M), int(seed) & (2**64 - 1), cap,
+                                 _ptr(sets), _ptr(counts), C.c_void_p(st.cuda_stream)), 's3_walk_sets')
+    return sets, counts
+
+
+def walk_sets_from_cache(cache, nodes, device):
+    """Table for `nodes` (1-D int64 tensor) from a reference-style cache {node id: 1-D tensor of the
+    unique nodes its walks visited} (what create_rw_cache returns)."""
+    lists = [torch.unique(torch.as_tensor(cache[int(v)]).flatten().to(torch.int64)).to(torch.int32) for v in nodes.tolist()]
+    cap = max([int(t.numel()) for t in lists] + [1])
+    sets = torch.zeros((len(lists), cap), dtype=torch.int32)
+    for i, t in enumerate(lists):
+        sets[i, :t.numel()] = t
+    counts = torch.tensor([int(t.numel()) for t in lists], dtype=torch.int32)
+    return sets.to(device), counts.to(device)
+
+
 class _Call:
     """One precompute call: validated arguments, per-call device state and the batch schedule.
 
@@ -158,7 +189,7 @@ class _Call:
     owns its output pieces, and the pieces are concatenated at the end."""
 
     def __init__(self, graph, links, num_hops, sign_k, flow, strategy, batch_records, out, return_graphs,
-                 arena_words, stream, profile, overlap, host_out, force_sorted_tier):
+                 arena_words, stream, profile, overlap, host_out, force_sorted_tier, walk=None):
         self.lib = L.lib()
         if flow not in _FLOW:
             raise NotImplementedError(f"sign_type {flow!r}: no matching configuration (reference utils.py:553)")
@@ -175,6 +206,21 @@ class _Call:
         self.links = links.to(device=self.dev, dtype=torch.int64, non_blocking=True).contiguous()
         self.num_links = int(self.links.shape[1])
         self.num_hops, self.K = int(num_hops), int(sign_k)
+        # ScaLed: per-endpoint random-walk sets replace the h-hop ball
+        self.walk = None
+        if walk is not None:
+            if self.flow != L.FLOW_POS or self.strategy != L.STRATEGY_NONE:
+                raise NotImplementedError("random-walk subgraphs are supported for PoS without CCN rows only")
+            uniq, inv = torch.unique(self.links.reshape(-1), return_inverse=True)
+            inv = inv.reshape(2, -1).contiguous()
+            if 'cache' in walk:
+                sets, counts = walk_sets_from_cache(walk['cache'], uniq.cpu(), self.dev)
+            elif 'sets' in walk:      # table indexed by node id
+                sets, counts = walk['sets'].to(self.dev)[uniq].contiguous(), walk['counts'].to(self.dev)[uniq].contiguous()
+            else:
+                sets, counts = walk_sets(graph, uniq, walk['m'], walk['M'], walk.get('seed', 0), stream)
+            self.walk = dict(sets=sets.contiguous(), counts=counts.contiguous(), src=inv[0].contiguous(),
+                             dst=inv[1].contiguous(), cap=int(sets.shape[1]))
         self.F1 = graph.num_feat + 1
         self.rpl = 2 if self.flow == L.FLOW_SOP else 1          # records per link
         self.nseed = 1 if self.flow == L.FLOW_SOP else 2        # output rows per record (fixed-row flows)
@@ -223,9 +269,12 @@ class _Call:
     def make_batch(self, b0, b1, arena, off, cnt, ctr, row_ptr=None, item_ptr=None, item_rec=None, order=None):
         src = self.links[0, b0:b1] if b1 > b0 else None
         dst = self.links[1, b0:b1] if b1 > b0 else None
+        w = self.walk
         return L.Batch(_ptr(src), _ptr(dst), b1 - b0, self.flow, self.strategy, self.num_hops, self.K, self.flags, 0,
                        _ptr(arena), arena.numel() if arena is not None else 0, _ptr(off), _ptr(cnt), _ptr(ctr),
-                       _ptr(row_ptr), _ptr(item_ptr), _ptr(item_rec), _ptr(order))
+                       _ptr(row_ptr), _ptr(item_ptr), _ptr(item_rec), _ptr(order),
+                       _ptr(w['sets']) if w else None, _ptr(w['counts']) if w else None,
+                       _ptr(w['src'][b0:]) if w else None, _ptr(w['dst'][b0:]) if w else None, w['cap'] if w else 0, 0)
 
     def launch(self, stage, bi, fn_name, *args, on=None):
         """Call one C entry point; with `profile`, bracket it with CUDA events on its stream."""
@@ -471,7 +520,7 @@ class _Call:
 
 def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_records=None, out=None,
                return_graphs=False, arena_words=None, stream=None, profile=None, overlap=False, defer=False,
-               host_out=None, force_sorted_tier=False):
+               host_out=None, force_sorted_tier=False, walk=None):
     """Run the hot path for `links` ([2, L] int64, host or device) on `graph`; returns a
     PrecomputeResult with device tensors.
 
@@ -489,10 +538,13 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
                    `result.finalize()` (stream sync + validation + re-run of overflowed batches) before
                    using the outputs.  Lets several calls be queued back to back.
     return_graphs  also return every record's canonical nodes / hops / local CSR (parity tests).
+    walk           ScaLed subgraphs (reference utils.py:86-150): dict(m=, M=, seed=) to sample on the GPU,
+                   dict(cache={node: tensor}) for a reference-style walk cache, or dict(sets=, counts=) for
+                   a table indexed by node id.  The subgraph of (u, v) is {u, v} ∪ set(u) ∪ set(v).
     Raises ValueError for invalid links (out of range, src == dst), NotImplementedError for an unknown
     strategy (as reference tuned_SIGN.py:235) or an unsupported combination."""
     call = _Call(graph, links, num_hops, sign_k, flow, strategy, batch_records, out, return_graphs, arena_words,
-                 stream, profile, overlap, host_out, force_sorted_tier)
+                 stream, profile, overlap, host_out, force_sorted_tier, walk)
     return call.run(defer)
 
 

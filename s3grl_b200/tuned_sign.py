@@ -51,9 +51,20 @@ def _finish(res, y, host=None):
     return PrecomputedList(xs, row_ptr, y, res.stats)
 
 
+def _walk_request(rw_kwargs, y):
+    """ScaLed: translate the reference's rw_kwargs (sgrl_link_pred.py:130-141) into engine.precompute's
+    `walk` argument.  A walk cache built by the reference's create_rw_cache (cached_pos_rws /
+    cached_neg_rws, picked by y as at utils.py:94-99) is used as is; otherwise the walks are sampled on
+    the GPU (seed = rw_kwargs.get('seed', 0))."""
+    if not rw_kwargs or not rw_kwargs.get('rw_m'):
+        return None
+    cache = rw_kwargs.get('cached_pos_rws') if y == 1 else rw_kwargs.get('cached_neg_rws')
+    if cache:
+        return dict(cache=cache)
+    return dict(m=int(rw_kwargs['rw_m']), M=int(rw_kwargs['rw_M']), seed=int(rw_kwargs.get('seed', 0)))
+
+
 def _reject_unsupported(ratio_per_hop, max_nodes_per_hop, directed, rw_kwargs):
-    if rw_kwargs:
-        raise NotImplementedError("ScaLed random-walk subgraphs (rw_kwargs) are out of scope (SURVEY.md §8f)")
     if directed:
         raise NotImplementedError("directed BFS is out of scope")
     if (ratio_per_hop is not None and ratio_per_hop < 1.0) or max_nodes_per_hop is not None:
@@ -80,7 +91,8 @@ class OptimizedSignOperations:
         assert x is not None                       # reference tuned_SIGN.py:166
         g = device_graph(A, x)
         host = _host_buffers(int(link_index.shape[1]), g.num_feat, sign_kwargs['sign_k'])
-        return _finish(precompute(g, link_index, num_hops, sign_kwargs['sign_k'], flow='PoS', host_out=host), y, host)
+        return _finish(precompute(g, link_index, num_hops, sign_kwargs['sign_k'], flow='PoS', host_out=host,
+                                  walk=_walk_request(rw_kwargs, y)), y, host)
 
     @staticmethod
     def get_PoS_Plus_prepped_ds(link_index, num_hops, A, ratio_per_hop, max_nodes_per_hop, directed, A_csc, x, y,
@@ -89,6 +101,8 @@ class OptimizedSignOperations:
         sel = [0,1] + sorted((N(0) ∪ N(1)) − {0,1}) (the reference raises for it)."""
         _reject_unsupported(ratio_per_hop, max_nodes_per_hop, directed, rw_kwargs)
         assert x is not None                       # reference tuned_SIGN.py:221
+        if rw_kwargs and rw_kwargs.get('rw_m'):
+            raise NotImplementedError("ScaLed random-walk subgraphs with CCN rows (PoS Plus) are not supported")
         strat = sign_kwargs['k_node_set_strategy']
         if strat not in ('union', 'intersection'):
             raise NotImplementedError(f"check strat {strat}")      # reference tuned_SIGN.py:235

@@ -46,6 +46,9 @@ class Case:
         self.X = d['X'] if 'X' in d.files else features_from_spec(str(d['x_spec']), self.A, self.N)
         self.row_ptr = d['row_ptr']
         self.xs = [d[f'x{k}'] for k in range(self.K + 1)]
+        if self.flow == 'scaled':
+            self.sets = {int(k): row[row >= 0].astype(np.int64) for k, row in zip(d['set_nodes'], d['set_table'])}
+            self.rw_m, self.rw_M = int(d['rw_m']), int(d['rw_M'])
         if self.flow == 'pos':
             self.row_gid = d['row_gid']
             self.node_ptr, self.edge_ptr = d['node_ptr'], d['edge_ptr']

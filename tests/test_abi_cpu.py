@@ -43,7 +43,7 @@ def test_constants_match_header():
              'S3_CTR_ITEMS': L.CTR_ITEMS, 'S3_REC_BAD_LINK': L.REC_BAD_LINK, 'S3_ERR_NOT_IMPLEMENTED': L.S3_ERR_NOT_IMPLEMENTED}
     for k, v in pairs.items():
         assert int(defs[k]) == v, k
-    assert ctypes.sizeof(L.Graph) == 64 and ctypes.sizeof(L.Batch) == 120
+    assert ctypes.sizeof(L.Graph) == 64 and ctypes.sizeof(L.Batch) == 160
 
 
 def test_version_and_error_strings(lib):

@@ -362,3 +362,60 @@ def test_self_loops_follow_the_reference_semantics():
             _check_indices(gg, r, f'h={h} link {i}')
         for k in range(K + 1):
             assert_features_close(res.xs[k].cpu().numpy(), ref['xs'][k], what=f'h={h} x{k}')
+
+
+def test_scaled_subgraphs_from_a_walk_cache_match_reference():
+    """ScaLed with the walk sets of the golden fixture (the form the reference's create_rw_cache
+    hands over): everything downstream of the walks is exact — parity with the reference's output,
+    through the tensor API and through the rw_kwargs of the reference-facing call."""
+    from s3grl_b200 import OptimizedSignOperations as Ops
+    c = Case('cora_scaled')
+    g = DeviceGraph(c.A, c.X)
+    cache = {k: torch.from_numpy(v) for k, v in c.sets.items()}
+    res = precompute(g, c.links, 0, c.K, walk=dict(cache=cache), return_graphs=True)
+    ref = orc.scaled_pos_precompute(c.links, c.sets, c.A, c.X, c.K, keep_graphs=True)
+    for i, (gg, r) in enumerate(zip(res.graphs, ref['graphs'])):
+        _check_indices(gg, r, f'scaled link {i}')
+    for k in range(c.K + 1):
+        assert_features_close(res.xs[k].cpu().numpy(), c.xs[k], what=f'scaled x{k}')
+    kw = dict(sign_k=c.K, use_feature=True, sign_type='PoS', optimize_sign=True, k_heuristic=0, k_node_set_strategy=None)
+    rw_kwargs = dict(rw_m=c.rw_m, rw_M=c.rw_M, cached_pos_rws=cache, cached_neg_rws=None, sign=True)
+    out = Ops.get_PoS_prepped_ds(torch.from_numpy(c.links), 0, c.A, 1.0, None, False, None, torch.from_numpy(c.X), 1, kw, rw_kwargs)
+    for k in range(c.K + 1):
+        assert_features_close(out.xs[k].numpy(), c.xs[k], what=f'scaled mirror x{k}')
+
+
+def test_gpu_random_walk_sets():
+    """The CUDA sampler (s3_walk_sets): every set is sorted, unique, contains its start node, has at
+    most 1 + M*m nodes all within m steps of the start; sets depend only on (seed, node); and the
+    set-size distribution matches a NumPy simulation of the same process (the reference's
+    torch_cluster RNG stream cannot be reproduced: parity is distributional)."""
+    import scipy.sparse.csgraph as csg
+    from s3grl_b200 import walk_sets
+    c = Case('cora_scaled')
+    g = DeviceGraph(c.A, c.X)
+    starts = torch.arange(c.N)
+    sets, counts = walk_sets(g, starts, 3, 20, seed=7)
+    sets, counts = sets.cpu().numpy(), counts.cpu().numpy()
+    again, again_n = walk_sets(g, starts[100:200], 3, 20, seed=7)
+    again, again_n = again.cpu().numpy(), again_n.cpu().numpy()
+    assert np.array_equal(again_n, counts[100:200])                                 # independent of the call
+    assert all(np.array_equal(again[i, :again_n[i]], sets[100 + i, :again_n[i]]) for i in range(100))
+    _, other_n = walk_sets(g, starts, 3, 20, seed=8)
+    assert not np.array_equal(other_n.cpu().numpy(), counts)
+    dist = csg.shortest_path(c.A, unweighted=True, indices=np.arange(0, c.N, 37))
+    for row, s in enumerate(range(0, c.N, 37)):
+        nodes = sets[s, :counts[s]]
+        assert s in nodes and counts[s] <= 61 and np.all(np.diff(nodes) > 0) and np.all(dist[row][nodes] <= 3)
+    deg = np.diff(c.A.indptr)
+    assert np.all(counts[deg == 0] == 1)
+    sim = orc.random_walk_sets(c.A, np.arange(c.N), 3, 20, seed=3)
+    sim_mean = np.mean([v.size for v in sim.values()])
+    assert abs(counts.mean() - sim_mean) / sim_mean < 0.03, (counts.mean(), sim_mean)
+    # end to end on sampled walks: identical to the oracle fed with the same sets
+    links = c.links[:, :30]
+    res = precompute(g, links, 0, c.K, walk=dict(m=3, M=20, seed=7))
+    as_dict = {int(s): sets[s, :counts[s]].astype(np.int64) for s in np.unique(links)}
+    ref = orc.scaled_pos_precompute(links, as_dict, c.A, c.X, c.K)
+    for k in range(c.K + 1):
+        assert_features_close(res.xs[k].cpu().numpy(), ref['xs'][k], what=f'sampled x{k}')

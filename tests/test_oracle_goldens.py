@@ -72,3 +72,24 @@ def test_non_optimised_flow_is_an_independent_cross_check():
             assert_features_close(full[k][:2], opt['xs'][k], what=f'link {i} x{k}')
             a, b = c.row_ptr[i], c.row_ptr[i + 1]
             assert_features_close(full[k][:2], c.xs[k][a:b], what=f'link {i} x{k} vs reference golden')
+
+
+def test_scaled_random_walk_flow_matches_reference():
+    """ScaLed: given the same walk sets, the oracle and the reference's own
+    k_hop_subgraph (random-walk branch) + get_PoS_prepped_ds agree."""
+    c = Case('cora_scaled')
+    out = orc.scaled_pos_precompute(c.links, c.sets, c.A, c.X, c.K)
+    assert np.array_equal(out['row_ptr'], c.row_ptr)
+    for k in range(c.K + 1):
+        assert_features_close(out['xs'][k], c.xs[k], what=f'scaled x{k}')
+
+
+def test_oracle_random_walk_sets_are_walks():
+    c = Case('cora_scaled')
+    starts = c.links.reshape(-1)[:40]
+    sets = orc.random_walk_sets(c.A, starts, 3, 20, seed=1)
+    import scipy.sparse.csgraph as csg
+    for s, nodes in sets.items():
+        assert s in nodes and nodes.size <= 61 and np.all(np.diff(nodes) > 0)
+        dist = csg.shortest_path(c.A, unweighted=True, indices=s)
+        assert np.all(dist[nodes] <= 3)
