@@ -63,6 +63,13 @@ extern "C" {
 #define S3_STRATEGY_INTERSECTION 1  /* PoS Plus, common neighbours  tuned_SIGN.py:232-233 */
 #define S3_STRATEGY_UNION 2         /* PoS Plus, union minus {0,1}  tuned_SIGN.py:230-231 */
 
+/* labeling-trick column of the non-optimised SIGN flow (reference node_label, utils.py:296-310) */
+#define S3_LABEL_ZERO 0    /* any other value of node_label: zeros                 */
+#define S3_LABEL_ZO 1      /* 'zo': 1 on the two targets                           */
+#define S3_LABEL_HOP 2     /* 'hop': BFS hop of the node                           */
+#define S3_LABEL_DRNL 3    /* 'drnl': double-radius node labeling, utils.py:211-236 */
+#define S3_LABEL_DEGREE 4  /* 'degree': induced degree capped at 100               */
+
 #define S3_MAX_HOPS 8
 #define S3_MAX_K 7
 
@@ -206,6 +213,18 @@ int s3_gather(const s3_graph* g, const s3_batch* b, int64_t num_records,
               float* const* out, int64_t ldo, int64_t row_base, void* stream);
 int s3_gather_ccn(const s3_graph* g, const s3_batch* b, int64_t num_items,
                   float* const* out, int64_t ldo, int64_t row_base, void* stream);
+
+/* Non-optimised SIGN + SEAL flow (reference utils.py:497-520, tuned_SIGN.py:18-23,
+ * i.e. PyG's SIGN transform on the whole subgraph): every subgraph node is an output row,
+ * x = [z | X_sub], x_k = S x_{k-1}, S = D^-1/2 A_sub D^-1/2. The batch must have been extracted with
+ * S3_BATCH_STORE_ALL_ROWS (PoS flow, S3_STRATEGY_NONE).
+ * s3_plan_full: row_ptr[r] = exclusive scan of the subgraph sizes n, counters[S3_CTR_ROWS] = total.
+ * s3_sign_full: out[k], k = 0..sign_k, [*, ldo] row-major; local node j of record r (canonical order)
+ * lands on row row_base + row_ptr[r] + j. label = S3_LABEL_*. node_out (optional, int64 per output
+ * row) receives the node's global id (the reference keeps it as data.node_id). */
+int s3_plan_full(const s3_batch* b, void* stream);
+int s3_sign_full(const s3_graph* g, const s3_batch* b, int64_t num_records, int32_t label, float* const* out,
+                 int64_t ldo, int64_t row_base, int64_t* node_out, void* stream);
 
 /* ScaLed: sorted node sets of rw_M uniform random walks of length rw_m from every
  * start node — replaces reference utils.py:425-443 (create_rw_cache). sets is [num_starts, cap]

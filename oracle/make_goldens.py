@@ -114,6 +114,28 @@ def make_scaled_case(name, A, links, K, x_spec, rw_m=3, rw_M=20, seed=5):
     print(f"{name}: L={links.shape[1]} sets={keys.size} cap={cap} -> {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def make_full_case(name, A, links, K, num_hops, node_label, X=None, x_spec=None):
+    """The non-optimised PoS flow (optimize_sign=False, utils.py:497-520) through the reference."""
+    A = A.tocsr()
+    A.sort_indices()
+    N = A.shape[0]
+    feats = X if X is not None else features_from_spec(x_spec, A, N)
+    links = np.ascontiguousarray(links, dtype=np.int64)
+    r = rr.ref_full(links, num_hops, A, feats, K, node_label)
+    out = dict(indptr=A.indptr.astype(np.int64), indices=A.indices.astype(np.int32), adata=A.data.astype(np.int64),
+               num_nodes=np.int64(N), links=links, num_hops=np.int64(num_hops), K=np.int64(K), flow=np.str_('full'),
+               strategy=np.str_(''), node_label=np.str_(node_label), row_ptr=r['row_ptr'], node_id=r['node_id'])
+    if X is not None:
+        out['X'] = np.asarray(X, np.float32)
+    else:
+        out['x_spec'] = np.str_(x_spec)
+    for k, x in enumerate(r['xs']):
+        out[f'x{k}'] = x.astype(np.float32)
+    path = os.path.join(OUT, f'ref_{name}.npz')
+    np.savez_compressed(path, **out)
+    print(f"{name}: L={links.shape[1]} R={int(r['row_ptr'][-1])} -> {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 def tiny_graphs():
     """Hand graphs for the edge cases of SURVEY.md A.6: isolated endpoints, n == 2, an
     endpoint whose only neighbour is the other endpoint, pendant paths, a hub, two components."""
@@ -145,6 +167,8 @@ def main():
         make_case(f'tiny_pos_h{h}', A, links, 'pos', 3, h, None, X=X)
     make_case('tiny_posplus_h2', A, links, 'pos', 3, 2, 'intersection', X=X)
     make_case('tiny_sop', A, links, 'sop', 3, X=X)
+    for lab in ('zo', 'hop', 'drnl', 'degree', 'none'):
+        make_full_case(f'tiny_full_{lab}', A, links, 3, 2, lab, X=X)
 
     edges, N, _ = ds.load_graph('cora')
     A, splits = ds.split_links(edges, N, seed=1)
@@ -152,6 +176,9 @@ def main():
     make_case('cora_pos', A, sample_links(splits, 160, 1), 'pos', 3, 3, None, x_spec='synthetic:24:0.3:5')
     make_case('cora_posplus', A, sample_links(splits, 160, 2), 'pos', 3, 3, 'intersection',
               x_spec='synthetic:24:0.3:5')
+
+    make_full_case('cora_full_drnl', A, sample_links(splits, 16, 9), 3, 3, 'drnl', x_spec='synthetic:24:0.3:5')
+    make_full_case('cora_full_zo_h2', A, sample_links(splits, 24, 10), 2, 2, 'zo', x_spec='synthetic:24:0.3:5')
 
     make_scaled_case('cora_scaled', A, sample_links(splits, 120, 6), 3, 'synthetic:24:0.3:5')
 

@@ -168,3 +168,34 @@ def ref_scaled_pos(links, A, X, K, sets):
     keys = ['x'] + [f'x{k}' for k in range(1, K + 1)]
     xs = [np.concatenate([np.asarray(d[key], dtype=np.float32) for d in data_list], 0) for key in keys]
     return dict(xs=xs, row_ptr=np.arange(len(data_list) + 1, dtype=np.int64) * 2)
+
+
+def ref_full(links, num_hops, A, X, K, node_label):
+    """The reference's NON-optimised PoS flow (utils.py:497-520: k_hop_subgraph -> construct_pyg_graph ->
+    TunedSIGN) through extract_enclosing_subgraphs with optimize_sign=False -> dict(xs, row_ptr, node_id)
+    with every link's rows permuted into canonical node order (src, dst, ascending (hop, global id))."""
+    utils, tuned = load_reference()
+    link_index = torch.as_tensor(np.asarray(links), dtype=torch.long)
+    x = torch.as_tensor(np.asarray(X), dtype=torch.float32)
+    kw = {'sign_k': K, 'use_feature': True, 'sign_type': 'PoS', 'optimize_sign': False, 'k_heuristic': 0,
+          'k_node_set_strategy': None}
+    with _quiet():
+        data_list = utils.extract_enclosing_subgraphs(link_index, A, x, 1, num_hops, node_label, 1.0, None, False, None,
+                                                      None, kw, powers_of_A=[], data=None)
+    keys = ['x'] + [f'x{k}' for k in range(1, K + 1)]
+    xs = [[] for _ in keys]
+    row_ptr, node_id = [0], []
+    for i, d in enumerate(data_list):
+        src, dst = int(links[0][i]), int(links[1][i])
+        nodes = d['node_id'].numpy().astype(np.int64)
+        # hop of every node: the same call again (deterministic) for its dists list
+        nodes2, _, dists, _, _ = utils.k_hop_subgraph(src, dst, num_hops, A)
+        assert list(nodes2) == list(nodes)
+        dists = np.asarray(dists)
+        order = np.concatenate([[0, 1], 2 + np.lexsort((nodes[2:], dists[2:]))]).astype(np.int64)
+        node_id.append(nodes[order])
+        for k, key in enumerate(keys):
+            xs[k].append(np.asarray(d[key], dtype=np.float32)[order])
+        row_ptr.append(row_ptr[-1] + nodes.size)
+    return dict(xs=[np.concatenate(v, 0) for v in xs], row_ptr=np.asarray(row_ptr, np.int64),
+                node_id=np.concatenate(node_id))

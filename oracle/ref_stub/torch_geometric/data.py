@@ -3,8 +3,15 @@
 
 
 class Data:
-    def __init__(self, **kwargs):
-        self.__dict__['_store'] = dict(kwargs)
+    def __init__(self, x=None, edge_index=None, **kwargs):
+        # construct_pyg_graph passes x and edge_index positionally (reference utils.py:313)
+        store = {}
+        if x is not None:
+            store['x'] = x
+        if edge_index is not None:
+            store['edge_index'] = edge_index
+        store.update(kwargs)
+        self.__dict__['_store'] = store
 
     def __getattr__(self, key):
         store = self.__dict__['_store']

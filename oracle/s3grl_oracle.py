@@ -16,6 +16,7 @@ node order so results can be compared bit-exactly on indices:
   sgrl_link_pred.py:161-178 SoP global powers `sop_powers`
   tuned_SIGN.py:49-134  get_SoP_prepped_ds    `sop_link`
   utils.py:454-480 hybrid                     `hybrid_precompute`
+  utils.py:497-520 non-optimised PoS flow     `sign_all_rows`, `full_precompute`, `node_labels`
   utils.py:86-150, :425-443 ScaLed walks      `random_walk_sets`, `scaled_pos_link`
   models.py:372    joint matrix layout        `joint_matrix`
 
@@ -296,19 +297,68 @@ def hybrid_precompute(links, num_hops, A, X, K, dtype=np.float32):
     return dict(xs=pos['xs'] + sop['xs'][2:], row_ptr=pos['row_ptr'])
 
 
-def sign_all_rows(src, dst, num_hops, A, X, K, dtype=np.float32):
-    """The NON-optimised flow (utils.py:497-550 + TunedSIGN.__call__, tuned_SIGN.py:18-23 — PyG's
-    SIGN transform on the whole subgraph): x_k = S x_{k-1} for ALL n rows with the zero-one label
-    column.  No paper config uses it; it is restated because it is an independent route to the same
-    numbers: its rows 0 and 1 must equal the optimised PoS flow's output."""
+def node_labels(node_label, hops, lrowptr, lcol):
+    """construct_pyg_graph's labeling-trick column (utils.py:296-310) in canonical local ids.
+    'drnl' restates drnl_node_labeling (utils.py:211-236): BFS distance to local 0 with local 1 removed
+    and vice versa, z = 1 + min + (d//2)*((d//2) + d%2 - 1), z[0] = z[1] = 1, unreachable -> 0."""
+    n = hops.size
+    if node_label == 'zo':
+        return (hops == 0).astype(np.int64)
+    if node_label == 'hop':
+        return hops.astype(np.int64)
+    if node_label == 'degree':
+        return np.minimum(np.diff(lrowptr), 100).astype(np.int64)
+    if node_label == 'drnl':
+        def bfs(start, removed):
+            dist = np.full(n, -1, dtype=np.int64)
+            dist[start] = 0
+            frontier = [start]
+            while frontier:
+                nxt = []
+                for j in frontier:
+                    for i in lcol[lrowptr[j]:lrowptr[j + 1]]:
+                        if i != removed and dist[i] < 0:
+                            dist[i] = dist[j] + 1
+                            nxt.append(int(i))
+                frontier = nxt
+            return dist
+        ds, dd = bfs(0, 1), bfs(1, 0)
+        d = ds + dd
+        z = 1 + np.minimum(ds, dd) + (d // 2) * ((d // 2) + d % 2 - 1)
+        z[(ds < 0) | (dd < 0)] = 0
+        z[:2] = 1
+        return z.astype(np.int64)
+    if node_label in ('de', 'de+'):
+        raise NotImplementedError("two-column labels cannot go through the SIGN flow (utils.py:314)")
+    return np.zeros(n, dtype=np.int64)
+
+
+def sign_all_rows(src, dst, num_hops, A, X, K, dtype=np.float32, node_label='zo', with_nodes=False):
+    """The NON-optimised flow (utils.py:497-520 + construct_pyg_graph utils.py:281-316 +
+    TunedSIGN.__call__, tuned_SIGN.py:18-23 — PyG's SIGN transform on the whole subgraph):
+    x = [z | X_sub], x_k = S x_{k-1} for ALL n rows, rows in canonical node order.  With
+    node_label == 'zo' its rows 0 and 1 must equal the optimised PoS flow's output
+    (SURVEY.md §8a row 9)."""
     nodes, hops, lrowptr, lcol = k_hop_subgraph(src, dst, num_hops, A)
     S, _ = normalized_subgraph(lrowptr, lcol, dtype)
-    label = np.zeros((nodes.size, 1), dtype=dtype)
-    label[:2] = 1
+    label = node_labels(node_label, hops, lrowptr, lcol).astype(dtype).reshape(-1, 1)
     xs = [np.hstack([label, np.asarray(X[nodes], dtype=dtype)])]
     for _ in range(K):
         xs.append(np.asarray(S @ xs[-1], dtype=dtype))
-    return xs
+    return (xs, nodes) if with_nodes else xs
+
+
+def full_precompute(links, num_hops, A, X, K, node_label='drnl', dtype=np.float32):
+    """Whole call of the non-optimised PoS flow in the collated layout: K+1 row-stacked [sum n, F+1]
+    arrays, row_ptr [L+1] and node_id [sum n]."""
+    links = np.asarray(links)
+    per = [sign_all_rows(int(links[0, i]), int(links[1, i]), num_hops, A, X, K, dtype, node_label, True)
+           for i in range(links.shape[1])]
+    row_ptr = np.zeros(links.shape[1] + 1, dtype=np.int64)
+    row_ptr[1:] = np.cumsum([p[1].size for p in per])
+    F1 = X.shape[1] + 1
+    xs = [np.concatenate([p[0][k] for p in per], 0) if per else np.zeros((0, F1), dtype) for k in range(K + 1)]
+    return dict(xs=xs, row_ptr=row_ptr, node_id=np.concatenate([p[1] for p in per]) if per else np.zeros(0, np.int64))
 
 
 def joint_matrix(xs):

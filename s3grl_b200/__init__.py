@@ -10,6 +10,6 @@ The compute lives in lib/libs3grl_b200.so (include/s3grl_b200.h); build it with
 __version__ = '0.1.0'
 
 from .data import Data, PrecomputedList  # noqa: F401
-from .engine import DeviceGraph, PrecomputeResult, algorithmic_bytes, precompute, walk_sets  # noqa: F401
+from .engine import DeviceGraph, PrecomputeResult, algorithmic_bytes, precompute, precompute_full, walk_sets  # noqa: F401
 from .tuned_sign import OptimizedSignOperations  # noqa: F401
 from .utils import extract_enclosing_subgraphs  # noqa: F401

@@ -79,6 +79,9 @@ cudaError_t launch_plan_items(const s3_batch& b, cudaStream_t st);
 cudaError_t launch_diffuse(const s3_graph& g, const s3_batch& b, int64_t num_items, cudaStream_t st);
 cudaError_t launch_gather(const s3_graph& g, const s3_batch& b, int64_t num_items, const OutPtrs& out,
                           int64_t ldo, int64_t row_base, bool ccn, cudaStream_t st);
+cudaError_t launch_plan_full(const s3_batch& b, cudaStream_t st);
+cudaError_t launch_sign_full(const s3_graph& g, const s3_batch& b, int64_t num_records, int label, const OutPtrs& out,
+                             int64_t ldo, int64_t row_base, int64_t* node_out, cudaStream_t st);
 cudaError_t launch_dump_edges(const s3_batch& b, const int64_t* edge_ptr, int32_t* edges_out, cudaStream_t st);
 
 }  // namespace s3

@@ -44,8 +44,9 @@ class PrecomputedList:
     y       : int label shared by the call (reference passes one y per call, utils.py:446) or
               an int64 tensor [L] after concatenation."""
 
-    def __init__(self, xs, row_ptr, y, stats=None):
+    def __init__(self, xs, row_ptr, y, stats=None, extras=None):
         self.xs = list(xs)
+        self.extras = dict(extras or {})     # row-aligned extra keys (non-optimised flow: node_id)
         self.row_ptr = row_ptr
         L = int(row_ptr.shape[0]) - 1
         self.y = y if torch.is_tensor(y) else torch.full((L,), int(y), dtype=torch.long)
@@ -73,6 +74,8 @@ class PrecomputedList:
         d = Data(x=self.xs[0][a:b], y=int(self.y[i]))
         for k in range(1, len(self.xs)):
             d[f'x{k}'] = self.xs[k][a:b]
+        for key, t in self.extras.items():
+            d[key] = t[a:b]
         return d
 
     def __iter__(self):
@@ -87,7 +90,8 @@ class PrecomputedList:
         dev = self.xs[0].device
         xs = [torch.cat([a, b.to(dev)], 0) for a, b in zip(self.xs, other.xs)]
         rp = torch.cat([self.row_ptr, other.row_ptr[1:].to(self.row_ptr.device) + self.row_ptr[-1]])
-        return PrecomputedList(xs, rp, torch.cat([self.y, other.y]))
+        extras = {k: torch.cat([t, other.extras[k].to(t.device)]) for k, t in self.extras.items() if k in other.extras}
+        return PrecomputedList(xs, rp, torch.cat([self.y, other.y]), extras=extras)
 
     def collate(self):
         """-> (data, slices) in the layout of InMemoryDataset.collate: every operator
@@ -97,8 +101,12 @@ class PrecomputedList:
         for k in range(1, len(self.xs)):
             data[f'x{k}'] = self.xs[k]
             slices[f'x{k}'] = self.row_ptr
+        for key, t in self.extras.items():
+            data[key] = t
+            slices[key] = self.row_ptr
         return data, slices
 
     def to(self, device, non_blocking=False):
         return PrecomputedList([x.to(device, non_blocking=non_blocking) for x in self.xs],
-                               self.row_ptr.to(device), self.y, self.stats)
+                               self.row_ptr.to(device), self.y, self.stats,
+                               {k: t.to(device, non_blocking=non_blocking) for k, t in self.extras.items()})

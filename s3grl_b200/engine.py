@@ -548,6 +548,94 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
     return call.run(defer)
 
 
+_LABEL = {'zo': L.LABEL_ZO, 'hop': L.LABEL_HOP, 'drnl': L.LABEL_DRNL, 'degree': L.LABEL_DEGREE}
+
+
+def precompute_full(graph, links, num_hops, sign_k, node_label='drnl', batch_records=None, arena_words=None,
+                    stream=None, profile=None, force_sorted_tier=False, walk=None):
+    """The NON-optimised SIGN + SEAL flow (reference utils.py:497-520 with `powers_of_A` empty:
+    k_hop_subgraph -> construct_pyg_graph(node_label) -> TunedSIGN(sign_k), i.e. PyG's SIGN on the
+    whole enclosing subgraph): every subgraph node is an output row, x = [z | X_sub], x_k = S x_{k-1}.
+
+    Returns a PrecomputeResult whose xs[k] are [sum_i n_i, F+1], row_ptr[i]..row_ptr[i+1] the rows of
+    link i in canonical node order (src, dst, then ascending (hop, global id)), plus `.node_id`
+    (int64 [sum n], the reference's data.node_id).  Rows 0 and 1 of every link equal the optimised
+    PoS flow's output when node_label == 'zo' (SURVEY.md §8a row 9).
+
+    node_label: 'zo' | 'hop' | 'drnl' | 'degree'; any other string gives a zero column, as the
+    reference's else-branch does (utils.py:309-310); 'de' / 'de+' raise (two label columns: the
+    reference's own reshape at utils.py:314 fails for them).
+    Two passes: sizes first (extraction only), then one exact allocation and the SpMM chain."""
+    if node_label in ('de', 'de+'):
+        raise NotImplementedError(f"node_label {node_label!r} yields two columns; the reference's SIGN flow cannot "
+                                  "reshape it either (utils.py:314)")
+    if node_label == 'degree' and graph.has_multi_edges:
+        raise NotImplementedError("node_label 'degree' on a multigraph is not supported")
+    label = _LABEL.get(node_label, L.LABEL_ZERO)
+    call = _Call(graph, links, num_hops, sign_k, 'PoS', None, batch_records or 4096, None, False, arena_words,
+                 stream, profile, False, None, force_sorted_tier, walk)
+    call.flags |= L.BATCH_STORE_ALL_ROWS
+    dev, K, F1, lib = call.dev, call.K, call.F1, call.lib
+    g, st = C.byref(graph._c), call.stream_ptr
+
+    def front(bi):
+        """extract + plan_full of batch bi (retried with a larger arena on overflow) -> (batch, n per record, rows)"""
+        b0, b1 = call.bounds(bi)
+        while True:
+            arena = graph.arena(call.words)
+            off, cnt, order = call.meta(b1 - b0)
+            row_ptr = torch.empty(b1 - b0 + 1, dtype=torch.int64, device=dev)
+            ctr = call.counters[bi]
+            ctr.zero_()
+            batch = call.make_batch(b0, b1, arena, off, cnt, ctr, row_ptr=row_ptr, order=order)
+            call.launch('extract', bi, 's3_extract', g, C.byref(batch), st)
+            L.check(lib.s3_plan_full(C.byref(batch), st), 's3_plan_full')
+            call.stats['launches'] += 3
+            c = ctr.cpu()
+            if int(c[L.CTR_ERRORS]) == 0:
+                return batch, (off, cnt, order, row_ptr, arena), cnt[:, L.CNT_N].to(torch.int64), int(c[L.CTR_ROWS]), c
+            call.account(bi, cnt, {bi: c})      # raises on bad links
+            call.grow()
+
+    with torch.cuda.device(dev), torch.cuda.stream(call.stream):
+        call.counters = torch.zeros((max(call.num_batches, 1), L.NCTR), dtype=torch.int64, device=dev)
+        sizes, rows_per_batch, last = [], [], None
+        for bi in range(call.num_batches):
+            last = front(bi)
+            sizes.append(last[2])
+            rows_per_batch.append(last[3])
+        R = sum(rows_per_batch)
+        need = R * F1 * 4 * (K + 1) + R * 8
+        free, _ = torch.cuda.mem_get_info(dev)
+        if need > free:
+            raise MemoryError(f"the non-optimised flow needs {need / 2**30:.1f} GiB for {R} rows x {K + 1} operators "
+                              f"({free / 2**30:.1f} GiB free): pass fewer links per call")
+        xs = [torch.empty((R, F1), dtype=torch.float32, device=dev) for _ in range(K + 1)]
+        node_id = torch.empty(R, dtype=torch.int64, device=dev)
+        ptrs = (C.c_void_p * (K + 1))(*[o.data_ptr() for o in xs])
+        row_base = 0
+        for bi in range(call.num_batches):
+            cur = last if call.num_batches == 1 else front(bi)
+            batch, _keep, _, rows, c = cur
+            call.launch('sign_full', bi, 's3_sign_full', g, C.byref(batch), int(batch.num_links), label, ptrs, F1,
+                        row_base, _ptr(node_id), st)
+            call.stats['launches'] += 1
+            call.stats['sum_n'] += int(c[L.CTR_SUM_N])
+            call.stats['sum_d'] += int(c[L.CTR_SUM_D])
+            call.stats['max_n'] = max(call.stats['max_n'], int(c[L.CTR_MAX_N]))
+            row_base += rows
+            if call.num_batches > 1:
+                call.stream.synchronize()     # the arena is recycled by the next batch
+        counts = torch.cat(sizes) if sizes else torch.zeros(0, dtype=torch.int64, device=dev)
+        row_ptr = torch.zeros(call.num_links + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(counts, 0, out=row_ptr[1:])
+        call.stream.synchronize()
+    call.stats['rows'] = R
+    res = PrecomputeResult(xs, row_ptr, call.stats)
+    res.node_id = node_id
+    return res
+
+
 def algorithmic_bytes(stats, num_feat, sign_k):
     """SURVEY.md §8d:  sum over links of 4·D + 8·n + 4·F·n + 4·s·(K+1)·(F+1)."""
     return (4 * stats['sum_d'] + 8 * stats['sum_n'] + 4 * num_feat * stats['sum_n']

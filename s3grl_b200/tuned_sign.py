@@ -9,7 +9,7 @@ import os
 import torch
 
 from .data import PrecomputedList
-from .engine import DeviceGraph, precompute
+from .engine import DeviceGraph, precompute, precompute_full
 
 _graph_cache = {}
 
@@ -108,3 +108,19 @@ class OptimizedSignOperations:
             raise NotImplementedError(f"check strat {strat}")      # reference tuned_SIGN.py:235
         g = device_graph(A, x)
         return _finish(precompute(g, link_index, num_hops, sign_kwargs['sign_k'], flow='PoS', strategy=strat), y)
+
+    @staticmethod
+    def get_PoS_full_ds(link_index, num_hops, A, ratio_per_hop, max_nodes_per_hop, directed, A_csc, x, y,
+                        sign_kwargs, rw_kwargs, node_label='drnl'):
+        """The reference's non-optimised PoS branch (utils.py:497-520: k_hop_subgraph ->
+        construct_pyg_graph(node_label) -> TunedSIGN(sign_k)(data, sign_k)); it has no method of its own
+        in the reference, the name follows its siblings.  Every subgraph node is a row of x, x1..xK;
+        `node_id` carries the global ids (canonical order: src, dst, then ascending (hop, id))."""
+        _reject_unsupported(ratio_per_hop, max_nodes_per_hop, directed, rw_kwargs)
+        assert x is not None, "Node features cannot be None. Check logic."      # reference utils.py:312
+        g = device_graph(A, x)
+        res = precompute_full(g, link_index, num_hops, sign_kwargs['sign_k'], node_label=node_label,
+                              walk=_walk_request(rw_kwargs, y))
+        out = _finish(res, y)
+        out.extras['node_id'] = res.node_id.to(out.xs[0].device)
+        return out

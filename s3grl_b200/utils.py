@@ -34,7 +34,14 @@ def extract_enclosing_subgraphs(link_index, A, x, y, num_hops, node_label='drnl'
                                                                max_nodes_per_hop, directed, A_csc, x, y,
                                                                sign_kwargs, rw_kwargs)
     elif not sign_kwargs['optimize_sign']:
-        raise NotImplementedError("the non-optimised SIGN+SEAL flow (optimize_sign=False, utils.py:497-550) "
-                                  "is not on the accelerated path; no paper config uses it")
+        # SIGN + SEAL flow (reference utils.py:497-550)
+        if powers_of_A:
+            # reference utils.py:521-548 runs k_hop_subgraph on every global power with its own node set
+            # and stacks operators whose row counts differ per power: there is no consistent layout to
+            # reproduce, and no config uses it
+            raise NotImplementedError("the non-optimised SoP flow (optimize_sign=False with powers_of_A, "
+                                      "utils.py:521-548) is not supported")
+        return OptimizedSignOperations.get_PoS_full_ds(link_index, num_hops, A, ratio_per_hop, max_nodes_per_hop,
+                                                       directed, A_csc, x, y, sign_kwargs, rw_kwargs, node_label)
     else:
         raise NotImplementedError("No matching configuration for model data prep found. Please check code.")

@@ -49,6 +49,8 @@ class Case:
         if self.flow == 'scaled':
             self.sets = {int(k): row[row >= 0].astype(np.int64) for k, row in zip(d['set_nodes'], d['set_table'])}
             self.rw_m, self.rw_M = int(d['rw_m']), int(d['rw_M'])
+        if self.flow == 'full':
+            self.node_label, self.node_id = str(d['node_label']), d['node_id']
         if self.flow == 'pos':
             self.row_gid = d['row_gid']
             self.node_ptr, self.edge_ptr = d['node_ptr'], d['edge_ptr']

@@ -8,7 +8,7 @@ import torch
 
 from golden_util import Case, assert_features_close, case_names
 from oracle import s3grl_oracle as orc
-from s3grl_b200 import DeviceGraph, datasets as ds, precompute
+from s3grl_b200 import DeviceGraph, datasets as ds, precompute, precompute_full
 
 pytestmark = pytest.mark.gpu
 
@@ -419,3 +419,78 @@ def test_gpu_random_walk_sets():
     ref = orc.scaled_pos_precompute(links, as_dict, c.A, c.X, c.K)
     for k in range(c.K + 1):
         assert_features_close(res.xs[k].cpu().numpy(), ref['xs'][k], what=f'sampled x{k}')
+
+
+@pytest.mark.parametrize('name', case_names('full'))
+def test_non_optimised_flow_against_reference_goldens(name):
+    """SURVEY.md §8a row 9 (reference utils.py:497-520, optimize_sign=False): SIGN on the whole subgraph,
+    all labeling tricks; node ids bit-exact, x an exact copy, x1..xK within tolerance."""
+    c = Case(name)
+    res = precompute_full(DeviceGraph(c.A, c.X), c.links, c.num_hops, c.K, node_label=c.node_label)
+    assert np.array_equal(res.row_ptr.cpu().numpy(), c.row_ptr)
+    assert np.array_equal(res.node_id.cpu().numpy(), c.node_id)
+    assert np.array_equal(res.xs[0].cpu().numpy(), c.xs[0])
+    for k in range(1, c.K + 1):
+        assert_features_close(res.xs[k].cpu().numpy(), c.xs[k], what=f'{name} x{k}')
+
+
+@pytest.mark.parametrize('seed,N,E,F,h,K,label,batch', [
+    (0, 80, 160, 7, 2, 3, 'drnl', None), (1, 400, 900, 130, 3, 2, 'zo', 16), (2, 300, 1500, 200, 2, 4, 'drnl', 7),
+    (3, 1000, 1400, 33, 4, 3, 'hop', None), (4, 64, 500, 1, 1, 5, 'degree', 5), (5, 2000, 3000, 513, 3, 3, 'drnl', 32),
+])
+def test_non_optimised_flow_against_oracle(seed, N, E, F, h, K, label, batch):
+    rng = np.random.default_rng(300 + seed)
+    A = _random_graph(rng, N, E)
+    X = rng.random((N, F), dtype=np.float32)
+    links = rng.integers(0, N, (2, 40))
+    links = links[:, links[0] != links[1]]
+    ref = orc.full_precompute(links, h, A, X, K, label)
+    g = DeviceGraph(A, X)
+    res = precompute_full(g, links, h, K, node_label=label, batch_records=batch)
+    assert np.array_equal(res.row_ptr.cpu().numpy(), ref['row_ptr'])
+    assert np.array_equal(res.node_id.cpu().numpy(), ref['node_id'])
+    assert np.array_equal(res.xs[0].cpu().numpy(), ref['xs'][0])
+    for k in range(1, K + 1):
+        assert_features_close(res.xs[k].cpu().numpy(), ref['xs'][k], what=f'x{k}')
+    if label == 'zo':
+        # rows 0, 1 of the SpMM chain == the optimised PoS flow (row-vector propagation): two
+        # algebraically different CUDA routes to the same numbers
+        opt = precompute(g, links, h, K, 'PoS')
+        rp = res.row_ptr[:-1]
+        for k in range(K + 1):
+            both = torch.stack([res.xs[k][rp], res.xs[k][rp + 1]], 1).reshape(-1, F + 1)
+            assert_features_close(both.cpu().numpy(), opt.xs[k].cpu().numpy(), what=f'full vs optimised x{k}')
+
+
+def test_non_optimised_flow_through_reference_interface():
+    from s3grl_b200 import extract_enclosing_subgraphs
+    c = Case('cora_full_drnl')
+    kw = {'sign_k': c.K, 'use_feature': True, 'sign_type': 'PoS', 'optimize_sign': False, 'k_heuristic': 0,
+          'k_node_set_strategy': None}
+    out = extract_enclosing_subgraphs(torch.as_tensor(c.links), c.A, torch.as_tensor(c.X), 1, c.num_hops, 'drnl',
+                                      sign_kwargs=kw, powers_of_A=[])
+    assert len(out) == c.L
+    d = out[3]
+    a, b = c.row_ptr[3], c.row_ptr[4]
+    assert np.array_equal(d['node_id'].numpy(), c.node_id[a:b]) and d['y'] == 1
+    assert np.array_equal(d['x'].numpy(), c.xs[0][a:b])
+    assert_features_close(d[f'x{c.K}'].numpy(), c.xs[c.K][a:b], what='last operator of link 3')
+    with pytest.raises(NotImplementedError):
+        extract_enclosing_subgraphs(torch.as_tensor(c.links), c.A, torch.as_tensor(c.X), 1, c.num_hops, 'de',
+                                    sign_kwargs=kw, powers_of_A=[])
+    with pytest.raises(NotImplementedError):
+        extract_enclosing_subgraphs(torch.as_tensor(c.links), c.A, torch.as_tensor(c.X), 1, c.num_hops, 'drnl',
+                                    sign_kwargs=kw, powers_of_A=[1, 2, 3])
+
+
+def test_non_optimised_flow_on_the_sorted_tier():
+    rng = np.random.default_rng(77)
+    A = _random_graph(rng, 500, 2500)
+    X = rng.random((500, 40), dtype=np.float32)
+    links = rng.integers(0, 500, (2, 30))
+    links = links[:, links[0] != links[1]]
+    ref = orc.full_precompute(links, 1, A, X, 3, 'drnl')
+    res = precompute_full(DeviceGraph(A, X), links, 1, 3, node_label='drnl', force_sorted_tier=True)
+    assert np.array_equal(res.node_id.cpu().numpy(), ref['node_id'])
+    for k in range(4):
+        assert_features_close(res.xs[k].cpu().numpy(), ref['xs'][k], what=f'x{k}')

@@ -74,6 +74,19 @@ def test_non_optimised_flow_is_an_independent_cross_check():
             assert_features_close(full[k][:2], c.xs[k][a:b], what=f'link {i} x{k} vs reference golden')
 
 
+@pytest.mark.parametrize('name', case_names('full'))
+def test_non_optimised_flow_matches_reference(name):
+    """the reference's optimize_sign=False PoS branch (k_hop_subgraph ->
+    construct_pyg_graph(node_label) -> TunedSIGN) for every labeling trick it accepts."""
+    c = Case(name)
+    out = orc.full_precompute(c.links, c.num_hops, c.A, c.X, c.K, c.node_label)
+    assert np.array_equal(out['row_ptr'], c.row_ptr)
+    assert np.array_equal(out['node_id'], c.node_id)
+    assert np.array_equal(out['xs'][0], c.xs[0]), 'x = [z | X_sub] is an exact copy'
+    for k in range(1, c.K + 1):
+        assert_features_close(out['xs'][k], c.xs[k], what=f'{name} x{k}')
+
+
 def test_scaled_random_walk_flow_matches_reference():
     """ScaLed: given the same walk sets, the oracle and the reference's own
     k_hop_subgraph (random-walk branch) + get_PoS_prepped_ds agree."""
