@@ -90,6 +90,15 @@ def build_workload(name):
         links = ds.all_links(splits)
         return dict(A=A, X=X, links=links, num_hops=3, K=3, flow='PoS', strategy=None,
                     desc=f"Cora (real X F=1433), all {links.shape[1]} links, PoS num_hops=3 sign_k=3")
+    if name == 'cora_full_drnl':     # the non-optimised SIGN + SEAL flow (optimize_sign=False)
+        edges, N, X = ds.load_graph('cora')
+        A, splits = ds.split_links(edges, N, seed=1)
+        X = ds.normalize_features(X)
+        links = ds.all_links(splits)
+        links = links[:, np.sort(np.random.default_rng(5).choice(links.shape[1], 2048, replace=False))]
+        return dict(A=A, X=X, links=links, num_hops=3, K=3, flow='PoS', strategy=None, full='drnl',
+                    desc=f"Cora (real X F=1433), 2048 links sampled (seed 5) of the 3 splits, NON-optimised flow "
+                         f"(optimize_sign=False: SIGN on every subgraph row, DRNL label column) num_hops=3 sign_k=3")
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -157,6 +166,8 @@ def _cpu_chunk(cols):
         if 'sop_powers' not in w:       # the reference builds the global powers once per split
             w['sop_powers'] = orc.sop_powers(w['A'], w['K'])
         out = orc.sop_precompute(w['links'][:, cols], w['A'], w['X'], w['K'], powers=w['sop_powers'])
+    elif w.get('full'):
+        out = orc.full_precompute(w['links'][:, cols], w['num_hops'], w['A'], w['X'], w['K'], w['full'])
     else:
         out = orc.pos_precompute(w['links'][:, cols], w['num_hops'], w['A'], w['X'], w['K'], w['strategy'])
     return int(out['row_ptr'][-1])
@@ -256,6 +267,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='pubmed_pos')
     ap.add_argument('--batch-records', type=int, default=None)
+    ap.add_argument('--links', type=int, default=None, help='use only the first N links of the workload (profiling runs)')
     ap.add_argument('--cpu-links-per-core', type=int, default=400)
     ap.add_argument('--e2e-steps', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -271,6 +283,9 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     is_rmat = args.workload == 'rmat'
     w = None if is_rmat else build_workload(args.workload)
+    if w is not None and args.links:
+        w['links'] = np.ascontiguousarray(w['links'][:, :args.links])
+        w['desc'] += f' (first {args.links} links only)'
 
     if args.impl == 'reference':
         if is_rmat:
@@ -292,7 +307,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from s3grl_b200 import DeviceGraph, algorithmic_bytes, precompute
+    from s3grl_b200 import DeviceGraph, algorithmic_bytes, precompute, precompute_full
     from s3grl_b200 import tuned_sign
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -330,12 +345,16 @@ def main():
         cpu = dict(value=cols.size / dt, unit=UNIT, cores=1, kind="port",
                    sample=f"{cols.size} links sampled uniformly (seed 123), one pass, {dt:.1f} s; single-process oracle port")
         del A_host, X_host
-    fixed = w['strategy'] is None
+    full = w.get('full')
+    fixed = w['strategy'] is None and not full
     out = [torch.empty((2 * Lk, F + 1), dtype=torch.float32, device=dev) for _ in range(K + 1)] if fixed else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def step(profile=None, defer=False):
         flush.zero_()               # L2 flush between steps
+        if full:
+            return precompute_full(g, links_dev, w['num_hops'], K, node_label=full, batch_records=args.batch_records,
+                                   profile=profile)
         return precompute(g, links_dev, w['num_hops'], K, w['flow'], w['strategy'],
                           batch_records=args.batch_records, out=out, profile=profile, overlap=args.overlap,
                           defer=defer and fixed, walk=w.get('walk'))
@@ -344,8 +363,12 @@ def main():
     # is over when the timed region begins
     vis = [v for v in os.environ.get('CUDA_VISIBLE_DEVICES', '').split(',') if v.strip()]
     clocks = ClockSampler(vis[local_rank] if local_rank < len(vis) else local_rank)
+    res = None
     for _ in range(max(args.warmup, 3)):
+        del res
         res = step()
+    if full:
+        res.xs = res.node_id = None
     barrier()
     profile = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -358,6 +381,8 @@ def main():
     pending = []
     for i in range(args.steps):
         res = step(profile, defer=True)     # K steps are queued back to back ...
+        if full:
+            res.xs = res.node_id = None     # 9 GB per step: hand the rows back to the allocator
         pending.append(res)
         step_events[i + 1].record()
         launches += res.stats['launches']               # kernels of libs3grl_b200.so only (not the L2 flush fill)
@@ -379,8 +404,9 @@ def main():
     for stage, bi, a, b in profile:
         stage_ms.setdefault(stage, []).append(a.elapsed_time(b))
     nb = res.stats['batches']
-    gather_ms = float(np.sum(stage_ms.get('gather', [0.0])))
-    gather_launches = len(stage_ms.get('gather', []))
+    hot = 'sign_full' if full else 'gather'
+    gather_ms = float(np.sum(stage_ms.get(hot, [0.0])))
+    gather_launches = len(stage_ms.get(hot, []))
     st = res.stats
     gather_bytes_step = 4 * F * st['sum_n'] + 4 * st['rows'] * (K + 1) * (F + 1)
     path_bytes_step = algorithmic_bytes(st, F, K)
@@ -397,7 +423,7 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(args.workload)
     except Exception:
         pass
-    roofline = dict(bound="hbm", kernel="gather_kernel<8,3>" if F > 1024 else "gather_kernel", achieved=achieved, peak=peak,
+    roofline = dict(bound="hbm", kernel="sign_full_kernel" if full else ("gather_kernel<8,3>" if F > 1024 else "gather_kernel"), achieved=achieved, peak=peak,
                     unit="GB/s", frac=achieved / peak, traffic=traffic, peak_source=peak_src,
                     bytes_per_launch=gather_bytes_step / max(nb, 1), launches_timed=gather_launches,
                     avg_launch_ms=gather_ms / max(gather_launches, 1),
@@ -433,17 +459,17 @@ def main():
         from s3grl_b200 import extract_enclosing_subgraphs
         x_host = torch.from_numpy(w['X']).pin_memory()
         link_index = torch.from_numpy(np.ascontiguousarray(links_host)).pin_memory()
-        sign_kwargs = dict(sign_k=K, use_feature=True, sign_type=w['flow'], optimize_sign=True,
-                           k_heuristic=0 if fixed else 1, k_node_set_strategy=w['strategy'])
+        sign_kwargs = dict(sign_k=K, use_feature=True, sign_type=w['flow'], optimize_sign=not full,
+                           k_heuristic=0 if w['strategy'] is None else 1, k_node_set_strategy=w['strategy'])
         os.environ['S3GRL_DEVICE'] = str(dev)
         os.environ['S3GRL_OUTPUT_DEVICE'] = 'cpu'
-        del out, res
+        del out, res, pending, r
         torch.cuda.empty_cache()
 
         def e2e_step():
             tuned_sign._graph_cache.clear()       # the graph upload is part of every step
             rw_kwargs = dict(rw_m=w['walk']['m'], rw_M=w['walk']['M'], seed=w['walk']['seed'], sign=True) if w.get('walk') else None
-            lst = extract_enclosing_subgraphs(link_index, w['A'], x_host, 1, w['num_hops'], 'zo', 1.0, None, False,
+            lst = extract_enclosing_subgraphs(link_index, w['A'], x_host, 1, w['num_hops'], full or 'zo', 1.0, None, False,
                                               None, rw_kwargs, sign_kwargs, powers_of_A=[] if w['flow'] == 'PoS' else [None] * K,
                                               data=None)
             d2h = sum(x.numel() * 4 for x in lst.xs) + lst.row_ptr.numel() * 8

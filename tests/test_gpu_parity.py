@@ -437,6 +437,7 @@ def test_non_optimised_flow_against_reference_goldens(name):
 @pytest.mark.parametrize('seed,N,E,F,h,K,label,batch', [
     (0, 80, 160, 7, 2, 3, 'drnl', None), (1, 400, 900, 130, 3, 2, 'zo', 16), (2, 300, 1500, 200, 2, 4, 'drnl', 7),
     (3, 1000, 1400, 33, 4, 3, 'hop', None), (4, 64, 500, 1, 1, 5, 'degree', 5), (5, 2000, 3000, 513, 3, 3, 'drnl', 32),
+    (6, 700, 3000, 70, 3, 3, 'drnl', None), (7, 1300, 6000, 40, 3, 2, 'hop', None), (8, 150, 2500, 300, 2, 3, 'drnl', None),
 ])
 def test_non_optimised_flow_against_oracle(seed, N, E, F, h, K, label, batch):
     rng = np.random.default_rng(300 + seed)

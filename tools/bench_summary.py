@@ -1,7 +1,8 @@
 import signal
 signal.signal(signal.SIGPIPE, signal.SIG_DFL)
 import sys, json
-for l in sys.stdin:
+src = open(sys.argv[1]) if len(sys.argv) > 1 else sys.stdin   # file argument or stdin
+for l in src:
     if l.startswith('{'):
         d = json.loads(l); r = d.get("roofline") or {}
         print("value %.0f links/s  %.2f ms/step" % (d["value"], d["ms_per_step"]))
