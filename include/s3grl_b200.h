@@ -233,6 +233,19 @@ int s3_sign_full(const s3_graph* g, const s3_batch* b, int64_t num_records, int3
 int s3_walk_sets(const s3_graph* g, const int64_t* starts, int64_t num_starts, int32_t rw_m, int32_t rw_M,
                  uint64_t seed, int32_t cap, int32_t* sets, int32_t* counts, void* stream);
 
+/* GPU-resident batch assembly: replaces PyG's DataLoader(..., follow_batch=[x1..xK]) /
+ * Batch.from_data_list for the SIGN flows (reference sgrl_link_pred.py:1253-1269) and the feature-wise
+ * concat at the top of SIGNNet.forward (models.py:372).
+ * src: HOST array of num_ops device pointers to the collated operator matrices [R, ld_src] (num_cols
+ * valid columns each); row_ptr [L+1]; link_idx [num_links] the links of the batch (or of a whole shuffled
+ * epoch) in output order. dst [R_out, ld_dst], ld_dst >= num_ops*num_cols: row = [x | x1 | .. | xK] of one
+ * selected row. out_row_ptr [num_links] = first output row of every listed link (exclusive scan of their
+ * row counts), or NULL when every link has exactly rows_per_link rows. batch_vec (optional, [R_out]
+ * int64) receives the position of the row's link in link_idx — PyG's data.batch / x{k}_batch. */
+int s3_joint_rows(const float* const* src, int32_t num_ops, int64_t num_cols, int64_t ld_src, const int64_t* row_ptr,
+                  const int64_t* link_idx, int64_t num_links, const int64_t* out_row_ptr, int32_t rows_per_link,
+                  float* dst, int64_t ld_dst, int64_t* batch_vec, void* stream);
+
 /* Optional dumps for parity checks: canonical global-id edge list of every record,
  * edges[e] = (global row, global col), e in [edge_ptr[r], edge_ptr[r+1]). */
 int s3_dump_edges(const s3_batch* b, const int64_t* edge_ptr, int32_t* edges_out, void* stream);

@@ -188,6 +188,24 @@ int s3_walk_sets(const s3_graph* g, const int64_t* starts, int64_t num_starts, i
     return e == cudaSuccess ? S3_OK : cuda_fail(e);
 }
 
+int s3_joint_rows(const float* const* src, int32_t num_ops, int64_t num_cols, int64_t ld_src, const int64_t* row_ptr,
+                  const int64_t* link_idx, int64_t num_links, const int64_t* out_row_ptr, int32_t rows_per_link, float* dst,
+                  int64_t ld_dst, int64_t* batch_vec, void* stream) {
+    if (!src || num_ops < 1 || num_ops > 2 * S3_MAX_K || num_cols < 1 || num_cols > INT32_MAX / 64 || ld_src < num_cols)
+        return S3_ERR_INVALID_ARG;
+    if (num_links < 0 || ld_dst < (int64_t)num_ops * num_cols || (!out_row_ptr && rows_per_link < 1)) return S3_ERR_INVALID_ARG;
+    if (num_links > 0 && (!row_ptr || !link_idx || !dst)) return S3_ERR_INVALID_ARG;
+    s3::OutPtrs o;
+    memset(&o, 0, sizeof(o));
+    for (int k = 0; k < num_ops; ++k) {
+        if (!src[k]) return S3_ERR_INVALID_ARG;
+        o.p[k] = const_cast<float*>(src[k]);
+    }
+    cudaError_t e = s3::launch_joint_rows(o, num_ops, num_cols, ld_src, row_ptr, link_idx, num_links, out_row_ptr,
+                                          rows_per_link, dst, ld_dst, batch_vec, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? S3_OK : cuda_fail(e);
+}
+
 int s3_dump_edges(const s3_batch* b, const int64_t* edge_ptr, int32_t* edges_out, void* stream) {
     int rc = check_batch(b);
     if (rc != S3_OK) return rc;

@@ -65,7 +65,7 @@ __host__ __device__ inline int64_t ccn_item_words(int K, int64_t n, int cr) {
 }
 
 struct OutPtrs {
-    float* p[S3_MAX_K + 1];
+    float* p[2 * S3_MAX_K];  // K+1 operators; 2K for the hybrid flow (reference utils.py:454-480)
 };
 
 // launchers (defined in the .cu files, called from c_abi.cu)
@@ -82,6 +82,9 @@ cudaError_t launch_gather(const s3_graph& g, const s3_batch& b, int64_t num_item
 cudaError_t launch_plan_full(const s3_batch& b, cudaStream_t st);
 cudaError_t launch_sign_full(const s3_graph& g, const s3_batch& b, int64_t num_records, int label, const OutPtrs& out,
                              int64_t ldo, int64_t row_base, int64_t* node_out, cudaStream_t st);
+cudaError_t launch_joint_rows(const OutPtrs& src, int num_ops, int64_t cols, int64_t ld_src, const int64_t* row_ptr,
+                              const int64_t* link_idx, int64_t num_links, const int64_t* out_row_ptr, int rows_per_link,
+                              float* dst, int64_t ld_dst, int64_t* batch_vec, cudaStream_t st);
 cudaError_t launch_dump_edges(const s3_batch& b, const int64_t* edge_ptr, int32_t* edges_out, cudaStream_t st);
 
 }  // namespace s3
