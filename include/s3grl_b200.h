@@ -137,6 +137,11 @@ typedef struct s3_graph {
  * tier serves graphs of any size but only PoS with num_hops == 1 and S3_STRATEGY_NONE. */
 #define S3_BATCH_FORCE_SORTED_TIER 2
 
+/* PoS Plus union: records whose subgraph fits the shared-memory placement of s3_ccn_chain get their CCN rows
+ * from it and count no CCN work items in s3_plan; the others keep the work-item path (s3_plan_items +
+ * s3_diffuse + s3_gather_ccn). Set the bit for s3_plan AND s3_ccn_chain of the same batch. */
+#define S3_BATCH_CCN_CHAIN 4
+
 /* One batch of records and its scratch. */
 typedef struct s3_batch {
     const int64_t* link_src; /* [num_links] device                                         */
@@ -213,6 +218,13 @@ int s3_gather(const s3_graph* g, const s3_batch* b, int64_t num_records,
               float* const* out, int64_t ldo, int64_t row_base, void* stream);
 int s3_gather_ccn(const s3_graph* g, const s3_batch* b, int64_t num_items,
                   float* const* out, int64_t ldo, int64_t row_base, void* stream);
+
+/* s3_ccn_chain: the CCN rows (rows 2.. of every record) of PoS Plus with S3_STRATEGY_UNION by a hop-limited
+ * SpMM chain over the record's stored CSR instead of s3_plan_items + s3_diffuse + s3_gather_ccn (same
+ * results within fp32 rounding, ~10x fewer FMAs when a record has ~20 CCN rows). Call after s3_plan (row_ptr)
+ * and s3_gather on the same stream; one CTA per record. replaces tuned_SIGN.py:210-258 for the extra rows. */
+int s3_ccn_chain(const s3_graph* g, const s3_batch* b, int64_t num_records, float* const* out, int64_t ldo,
+                 int64_t row_base, void* stream);
 
 /* Non-optimised SIGN + SEAL flow (reference utils.py:497-520, tuned_SIGN.py:18-23,
  * i.e. PyG's SIGN transform on the whole subgraph): every subgraph node is an output row,

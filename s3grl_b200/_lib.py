@@ -15,12 +15,12 @@ LABEL_ZERO, LABEL_ZO, LABEL_HOP, LABEL_DRNL, LABEL_DEGREE = 0, 1, 2, 3, 4
 REC_OK, REC_ARENA_OVERFLOW, REC_BAD_LINK = 0, 1, 2
 OFF_NODES, OFF_ROWPTR, OFF_ROWLEN, OFF_LCOL, OFF_SEL, OFF_F32, NOFF = 0, 1, 2, 3, 4, 5, 6
 CNT_N, CNT_M, CNT_S, CNT_STATUS, CNT_PARTNER, CNT_HOP0, CNT_NSTORE, NCNT = 0, 1, 2, 3, 4, 5, 14, 16
-BATCH_STORE_ALL_ROWS, BATCH_FORCE_SORTED_TIER = 1, 2
+BATCH_STORE_ALL_ROWS, BATCH_FORCE_SORTED_TIER, BATCH_CCN_CHAIN = 1, 2, 4
 CTR_CURSOR, CTR_ERRORS, CTR_ROWS, CTR_ITEMS, CTR_MAX_N, CTR_SUM_N, CTR_SUM_D, CTR_WORK, NCTR = 0, 1, 2, 3, 4, 5, 6, 7, 48
 
 EXPORTS = ['s3_version', 's3_error_string', 's3_last_cuda_error', 's3_num_records', 's3_extract_smem_bytes',
            's3_min_arena_words', 's3_extract_tier',
-           's3_extract', 's3_plan', 's3_plan_items', 's3_diffuse', 's3_gather', 's3_gather_ccn', 's3_plan_full', 's3_sign_full', 's3_joint_rows', 's3_walk_sets', 's3_dump_edges']
+           's3_extract', 's3_plan', 's3_plan_items', 's3_diffuse', 's3_gather', 's3_gather_ccn', 's3_ccn_chain', 's3_plan_full', 's3_sign_full', 's3_joint_rows', 's3_walk_sets', 's3_dump_edges']
 
 
 class Graph(C.Structure):
@@ -77,6 +77,7 @@ def lib():
         L.s3_gather.argtypes = [C.POINTER(Graph), C.POINTER(Batch), C.c_int64, C.POINTER(C.c_void_p),
                                 C.c_int64, C.c_int64, C.c_void_p]
         L.s3_gather_ccn.argtypes = L.s3_gather.argtypes
+        L.s3_ccn_chain.argtypes = L.s3_gather.argtypes
         L.s3_joint_rows.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.s3_plan_full.argtypes = [C.POINTER(Batch), C.c_void_p]
@@ -85,7 +86,7 @@ def lib():
         L.s3_walk_sets.argtypes = [C.POINTER(Graph), C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, C.c_int32,
                                    C.c_void_p, C.c_void_p, C.c_void_p]
         L.s3_dump_edges.argtypes = [C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p]
-        for fn in ('s3_extract', 's3_plan', 's3_plan_items', 's3_diffuse', 's3_gather', 's3_gather_ccn', 's3_plan_full', 's3_sign_full', 's3_joint_rows', 's3_walk_sets',
+        for fn in ('s3_extract', 's3_plan', 's3_plan_items', 's3_diffuse', 's3_gather', 's3_gather_ccn', 's3_ccn_chain', 's3_plan_full', 's3_sign_full', 's3_joint_rows', 's3_walk_sets',
                    's3_dump_edges'):
             getattr(L, fn).restype = C.c_int
         _lib = L

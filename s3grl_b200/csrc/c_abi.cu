@@ -150,6 +150,24 @@ int s3_gather_ccn(const s3_graph* g, const s3_batch* b, int64_t num_items, float
     return gather_impl(g, b, num_items, out, ldo, row_base, 1, stream);
 }
 
+int s3_ccn_chain(const s3_graph* g, const s3_batch* b, int64_t num_records, float* const* out, int64_t ldo, int64_t row_base,
+                 void* stream) {
+    int rc = check_graph(g, true);
+    if (rc != S3_OK) return rc;
+    rc = check_batch(b);
+    if (rc != S3_OK) return rc;
+    if (b->flow != S3_FLOW_POS || b->strategy != S3_STRATEGY_UNION) return S3_ERR_NOT_IMPLEMENTED;
+    if (num_records < 0 || !out || !b->row_ptr || ldo < g->num_feat + 1 || row_base < 0) return S3_ERR_INVALID_ARG;
+    s3::OutPtrs o;
+    memset(&o, 0, sizeof(o));
+    for (int k = 0; k <= b->sign_k; ++k) {
+        if (!out[k]) return S3_ERR_INVALID_ARG;
+        o.p[k] = out[k];
+    }
+    cudaError_t e = s3::launch_ccn_chain(*g, *b, num_records, o, ldo, row_base, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? S3_OK : cuda_fail(e);
+}
+
 int s3_plan_full(const s3_batch* b, void* stream) {
     int rc = check_batch(b);
     if (rc != S3_OK) return rc;

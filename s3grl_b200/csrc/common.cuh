@@ -64,6 +64,15 @@ __host__ __device__ inline int64_t ccn_item_words(int K, int64_t n, int cr) {
     return (nwp + n * nwp + 2 * n * cr + 3) & ~int64_t(3);
 }
 
+// s3_ccn_chain (ccn_chain.cu): a record is served by the chain when its compact CSR and two CW >= 8 operator
+// buffers fit the kernel's shared memory: [dis n | node n | pos n1 | row starts n+1 | cols m | heavy rows | 2 * n * CW]
+constexpr int kChainSmemBytes = 216 * 1024;
+__host__ __device__ inline int64_t chain_fixed_words(int64_t n, int64_t m, int64_t n1) { return 3 * n + n1 + 4 + m + m / 24; }
+__host__ __device__ inline bool chain_eligible(int flags, int strategy, int64_t n, int64_t m, int64_t n1) {
+    return (flags & S3_BATCH_CCN_CHAIN) && strategy == S3_STRATEGY_UNION &&
+           chain_fixed_words(n, m, n1) + 2 * n * 8 <= kChainSmemBytes / 4;
+}
+
 struct OutPtrs {
     float* p[2 * S3_MAX_K];  // K+1 operators; 2K for the hybrid flow (reference utils.py:454-480)
 };
@@ -79,6 +88,8 @@ cudaError_t launch_plan_items(const s3_batch& b, cudaStream_t st);
 cudaError_t launch_diffuse(const s3_graph& g, const s3_batch& b, int64_t num_items, cudaStream_t st);
 cudaError_t launch_gather(const s3_graph& g, const s3_batch& b, int64_t num_items, const OutPtrs& out,
                           int64_t ldo, int64_t row_base, bool ccn, cudaStream_t st);
+cudaError_t launch_ccn_chain(const s3_graph& g, const s3_batch& b, int64_t num_records, const OutPtrs& out, int64_t ldo,
+                             int64_t row_base, cudaStream_t st);
 cudaError_t launch_plan_full(const s3_batch& b, cudaStream_t st);
 cudaError_t launch_sign_full(const s3_graph& g, const s3_batch& b, int64_t num_records, int label, const OutPtrs& out,
                              int64_t ldo, int64_t row_base, int64_t* node_out, cudaStream_t st);

@@ -189,8 +189,11 @@ class _Call:
     owns its output pieces, and the pieces are concatenated at the end."""
 
     def __init__(self, graph, links, num_hops, sign_k, flow, strategy, batch_records, out, return_graphs,
-                 arena_words, stream, profile, overlap, host_out, force_sorted_tier, walk=None):
+                 arena_words, stream, profile, overlap, host_out, force_sorted_tier, walk=None, ccn_mode=None):
         self.lib = L.lib()
+        if ccn_mode not in (None, 'items', 'chain'):
+            raise ValueError("ccn_mode must be None, 'items' or 'chain'")
+        self.ccn_mode = ccn_mode
         if flow not in _FLOW:
             raise NotImplementedError(f"sign_type {flow!r}: no matching configuration (reference utils.py:553)")
         if strategy not in _STRATEGY:
@@ -225,6 +228,11 @@ class _Call:
         self.rpl = 2 if self.flow == L.FLOW_SOP else 1          # records per link
         self.nseed = 1 if self.flow == L.FLOW_SOP else 2        # output rows per record (fixed-row flows)
         self.fixed_rows = self.strategy == L.STRATEGY_NONE
+        # CCN rows of `union`: work items by default; ccn_mode='chain' sends the records that fit shared memory
+        # through the hop-limited SpMM chain (s3_ccn_chain) — fewer FMAs but, measured on PubMed, not faster
+        self.ccn_chain = self.strategy == L.STRATEGY_UNION and self.ccn_mode == 'chain'
+        if self.ccn_mode == 'chain' and self.strategy != L.STRATEGY_UNION:
+            raise NotImplementedError("ccn_mode='chain' serves the union strategy only")
         self.return_graphs, self.profile = bool(return_graphs), profile
         self.stream = stream if stream is not None else torch.cuda.current_stream(self.dev)
         self.stream_ptr = C.c_void_p(self.stream.cuda_stream)
@@ -242,7 +250,8 @@ class _Call:
         self.num_batches = (self.num_links + self.batch_links - 1) // self.batch_links
         self.overlap = bool(overlap) and self.fixed_rows and not self.return_graphs and self.num_batches > 1
         self.flags = ((L.BATCH_STORE_ALL_ROWS if self.return_graphs else 0)
-                      | (L.BATCH_FORCE_SORTED_TIER if force_sorted_tier else 0))
+                      | (L.BATCH_FORCE_SORTED_TIER if force_sorted_tier else 0)
+                      | (L.BATCH_CCN_CHAIN if self.ccn_chain else 0))
         probe = self.make_batch(0, 0, None, None, None, None)
         if self.lib.s3_extract_tier(C.byref(graph._c), C.byref(probe)) < 0:
             L.check(L.S3_ERR_UNSUPPORTED, 's3_extract')
@@ -460,6 +469,11 @@ class _Call:
         batch = self.make_batch(b0, b1, arena, off, cnt, ctr, row_ptr, item_ptr, item_rec, order)
         self.launch('gather', bi, 's3_gather', g, C.byref(batch), nrec, ptrs, self.F1, 0, st)
         self.stats['launches'] += 1
+        if self.ccn_chain and rows > 2 * nrec:
+            # union: hop-limited SpMM chain over the stored CSR, one CTA per record; records too large for its
+            # shared-memory placement were counted as work items by s3_plan and take the path below
+            self.launch('ccn_chain', bi, 's3_ccn_chain', g, C.byref(batch), nrec, ptrs, self.F1, 0, st)
+            self.stats['launches'] += 1
         if items:       # CCN rows: extra work items of 2 (intersection) or 8 (union) selected rows each
             L.check(self.lib.s3_plan_items(C.byref(batch), st), 's3_plan_items')
             self.launch('diffuse', bi, 's3_diffuse', g, C.byref(batch), items, st)
@@ -520,7 +534,7 @@ class _Call:
 
 def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_records=None, out=None,
                return_graphs=False, arena_words=None, stream=None, profile=None, overlap=False, defer=False,
-               host_out=None, force_sorted_tier=False, walk=None):
+               host_out=None, force_sorted_tier=False, walk=None, ccn_mode=None):
     """Run the hot path for `links` ([2, L] int64, host or device) on `graph`; returns a
     PrecomputeResult with device tensors.
 
@@ -541,10 +555,14 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
     walk           ScaLed subgraphs (reference utils.py:86-150): dict(m=, M=, seed=) to sample on the GPU,
                    dict(cache={node: tensor}) for a reference-style walk cache, or dict(sets=, counts=) for
                    a table indexed by node id.  The subgraph of (u, v) is {u, v} ∪ set(u) ∪ set(v).
+    ccn_mode       PoS Plus union only: None / 'items' (default) = s3_diffuse + s3_gather_ccn work items of 8 selected
+                   rows; 'chain' = s3_ccn_chain (a hop-limited SpMM chain per record, 10x fewer FMAs) for the records
+                   that fit its shared-memory placement and work items for the rest.  Measured on PubMed the chain
+                   is barrier / latency bound and not faster (profiles/README.md), so it is opt-in.
     Raises ValueError for invalid links (out of range, src == dst), NotImplementedError for an unknown
     strategy (as reference tuned_SIGN.py:235) or an unsupported combination."""
     call = _Call(graph, links, num_hops, sign_k, flow, strategy, batch_records, out, return_graphs, arena_words,
-                 stream, profile, overlap, host_out, force_sorted_tier, walk)
+                 stream, profile, overlap, host_out, force_sorted_tier, walk, ccn_mode)
     return call.run(defer)
 
 

@@ -495,3 +495,28 @@ def test_non_optimised_flow_on_the_sorted_tier():
     assert np.array_equal(res.node_id.cpu().numpy(), ref['node_id'])
     for k in range(4):
         assert_features_close(res.xs[k].cpu().numpy(), ref['xs'][k], what=f'x{k}')
+
+
+@pytest.mark.parametrize('N,E,F,h,K,L', [(300, 900, 40, 2, 3, 40), (2500, 9000, 70, 3, 3, 12), (5000, 40000, 33, 3, 2, 6),
+                                         (9000, 70000, 20, 3, 3, 4), (600, 2400, 500, 3, 5, 16), (400, 1500, 9, 1, 3, 30),
+                                         (1500, 6000, 127, 3, 3, 20), (700, 2000, 128, 3, 3, 20), (1000, 2600, 3, 4, 4, 30)])
+def test_union_chain_matches_work_item_path(N, E, F, h, K, L):
+    """PoS Plus union: the opt-in hop-limited SpMM chain (s3_ccn_chain, for records that fit shared memory;
+    larger records fall to work items inside the same call) against the default all-work-item path
+    (s3_diffuse + s3_gather_ccn, itself checked against the oracle above), CW = 32 / 16 / 8 and mixed batches."""
+    rng = np.random.default_rng(N)
+    A = _random_graph(rng, N, E)
+    X = rng.random((N, F), dtype=np.float32)
+    links = rng.integers(0, N, (2, L))
+    links = links[:, links[0] != links[1]]
+    g = DeviceGraph(A, X)
+    a = precompute(g, links, h, K, 'PoS', 'union', ccn_mode='chain')   # chain where it fits shared memory, items elsewhere
+    b = precompute(g, links, h, K, 'PoS', 'union')                     # default: work items
+    assert torch.equal(a.row_ptr, b.row_ptr) and a.stats['max_n'] == b.stats['max_n']
+    assert torch.equal(a.xs[0], b.xs[0])                 # x: exact copies on both routes
+    for k in range(1, K + 1):
+        assert_features_close(a.xs[k].cpu().numpy(), b.xs[k].cpu().numpy(), what=f'N={N} x{k}')
+    rp = a.row_ptr[:-1]
+    for k in range(K + 1):                               # rows 0, 1 are produced by kernels 1 + 3 on both routes
+        assert torch.equal(a.xs[k][rp], b.xs[k][rp]) and torch.equal(a.xs[k][rp + 1], b.xs[k][rp + 1])
+    print(f"N={N}: max_n={a.stats['max_n']} rows={a.stats['rows']}")
