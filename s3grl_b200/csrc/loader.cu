@@ -46,7 +46,28 @@ __global__ void __launch_bounds__(kJointThreads) joint_rows_kernel(JointParams p
     if (p.batch_vec)
         for (int r = tid; r < s; r += kJointThreads) p.batch_vec[o0 + r] = b;
     const int cols = p.cols;
-    for (int r = 0; r < s; ++r) {
+    int r = 0;
+    if (NOPS > 0) {
+        // two rows at a time: 2 * NOPS independent loads in flight per thread
+        for (; r + 1 < s; r += 2) {
+            const int64_t soff = (r0 + r) * p.ld_src;
+            float* drow = p.dst + (o0 + r) * p.ld_dst;
+            for (int c = tid; c < cols; c += kJointThreads) {
+                float v[2][NOPS > 0 ? NOPS : 1];
+#pragma unroll
+                for (int op = 0; op < NOPS; ++op) {
+                    v[0][op] = __ldg(p.src.p[op] + soff + c);
+                    v[1][op] = __ldg(p.src.p[op] + soff + p.ld_src + c);
+                }
+#pragma unroll
+                for (int op = 0; op < NOPS; ++op) {
+                    drow[op * cols + c] = v[0][op];
+                    drow[p.ld_dst + op * cols + c] = v[1][op];
+                }
+            }
+        }
+    }
+    for (; r < s; ++r) {
         const int64_t soff = (r0 + r) * p.ld_src;
         float* drow = p.dst + (o0 + r) * p.ld_dst;
         for (int c = tid; c < cols; c += kJointThreads) {

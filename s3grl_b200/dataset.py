@@ -1,0 +1,178 @@
+"""Host-side mirror of the reference's dataset layer for the SIGN models:
+`get_pos_neg_edges` (reference utils.py:637-678) and `SEALDataset` (sgrl_link_pred.py:54-220) — the
+caller of the hot path.  Same constructor arguments, same `process()` sequence (build A from
+`data.edge_index`, pick the split's positive / negative links with the same `np.random.permutation`
+calls, run `extract_enclosing_subgraphs` on positives (y = 1) then negatives (y = 0), collate and
+`torch.save` to `processed_paths[0]`), same file name, and the `(data, slices)` file layout.  The
+subgraph extraction and operator construction run on the GPU (no CPU path); PyG itself is not needed.
+"""
+import os
+
+import numpy as np
+import scipy.sparse as ssp
+import torch
+
+from .data import PrecomputedList
+from .loader import load_collated, save_collated
+from .utils import extract_enclosing_subgraphs
+
+
+def sample_negative_edges(edge_index, num_nodes, num_neg_samples, seed=0):
+    """Stand-in for torch_geometric.utils.negative_sampling(add_self_loops(edge_index), ...) at reference
+    utils.py:645-648: `num_neg_samples` distinct ordered pairs (u, v), u != v, that are not stored edges,
+    drawn uniformly by rejection.  Same distribution, different RNG stream than PyG's sampler."""
+    ei = np.asarray(edge_index)
+    N = int(num_nodes)
+    taken = set((ei[0].astype(np.int64) * N + ei[1].astype(np.int64)).tolist())
+    rng = np.random.default_rng(seed)
+    out = []
+    need = int(num_neg_samples)
+    if need > N * (N - 1) - len(taken):
+        raise ValueError("not enough non-edges")
+    while need > 0:
+        u = rng.integers(0, N, 2 * need + 16)
+        v = rng.integers(0, N, 2 * need + 16)
+        for a, b in zip(u.tolist(), v.tolist()):
+            k = a * N + b
+            if a != b and k not in taken:
+                taken.add(k)
+                out.append((a, b))
+                need -= 1
+                if need == 0:
+                    break
+    return torch.as_tensor(np.asarray(out, dtype=np.int64).reshape(-1, 2).T.copy())
+
+
+def get_pos_neg_edges(split, split_edge, edge_index, num_nodes, percent=100, neg_ratio=1, neg_seed=0):
+    """reference utils.py:637-678, branch for branch; the two `np.random.permutation` calls per branch happen in
+    the reference's order, so with the same NumPy seed and pre-sampled negatives (`edge_neg`, or the
+    `source_node` format) the link ORDER — which fixes the output row order — is identical."""
+    if 'edge' in split_edge['train']:
+        pos_edge = split_edge[split]['edge'].t()
+        if 'edge_neg' in split_edge['train']:
+            neg_edge = split_edge[split]['edge_neg'].t()
+        else:
+            neg_edge = sample_negative_edges(edge_index, num_nodes, pos_edge.size(1) * neg_ratio, neg_seed)
+        num_pos = pos_edge.size(1)
+        perm = np.random.permutation(num_pos)
+        perm = perm[:int(percent / 100 * num_pos)]
+        pos_edge = pos_edge[:, perm]
+        num_neg = neg_edge.size(1)
+        perm = np.random.permutation(num_neg)
+        perm = perm[:int(percent / 100 * num_neg)]
+        neg_edge = neg_edge[:, perm]
+    elif 'source_node' in split_edge['train']:
+        source = split_edge[split]['source_node']
+        target = split_edge[split]['target_node']
+        if split == 'train':
+            target_neg = torch.randint(0, num_nodes, [target.size(0), 1], dtype=torch.long)
+        else:
+            target_neg = split_edge[split]['target_node_neg']
+        num_source = source.size(0)
+        perm = np.random.permutation(num_source)
+        perm = perm[:int(percent / 100 * num_source)]
+        source, target, target_neg = source[perm], target[perm], target_neg[perm, :]
+        pos_edge = torch.stack([source, target])
+        neg_per_target = target_neg.size(1)
+        neg_edge = torch.stack([source.repeat_interleave(neg_per_target), target_neg.view(-1)])
+    else:
+        raise KeyError("split_edge has neither 'edge' nor 'source_node' entries")
+    return pos_edge, neg_edge
+
+
+class SEALDataset:
+    """sgrl_link_pred.py:54-220 for `args.model == 'SIGN'`.  `data` needs `.edge_index` [2, E] (both directions
+    of the training edges), `.x` [N, F], `.num_nodes` and optionally `.edge_weight`; `args` needs `model`,
+    `sign_k`, `optimize_sign`, `k_heuristic`, `k_node_set_strategy` (and `seed` for sampled negatives).
+    After construction `self.lists` is the collated PrecomputedList (on `device`); `self.data, self.slices`
+    are what the reference's `torch.load(self.processed_paths[0])` returns."""
+
+    def __init__(self, root, data, split_edge, num_hops, percent=100, split='train', use_coalesce=False,
+                 node_label='drnl', ratio_per_hop=1.0, max_nodes_per_hop=None, directed=False, rw_kwargs=None,
+                 device='cuda', pairwise=False, pos_pairwise=False, neg_ratio=1, use_feature=False, sign_type="",
+                 args=None):
+        self.root = root
+        self.data_in = data
+        self.split_edge = split_edge
+        self.num_hops = num_hops
+        self.percent = int(percent) if percent >= 1.0 else percent
+        self.split = split
+        self.use_coalesce = use_coalesce
+        self.node_label = node_label
+        self.ratio_per_hop = ratio_per_hop
+        self.max_nodes_per_hop = max_nodes_per_hop
+        self.directed = directed
+        self.device = device
+        self.rw_kwargs = rw_kwargs or {}
+        self.pairwise = pairwise
+        self.pos_pairwise = pos_pairwise
+        self.neg_ratio = neg_ratio
+        self.use_feature = use_feature
+        self.sign_type = sign_type
+        self.args = args
+        if getattr(args, 'model', 'SIGN') != 'SIGN':
+            raise NotImplementedError("only the SIGN datasets are on the accelerated path (SURVEY.md §2)")
+        os.makedirs(self.processed_dir, exist_ok=True)
+        if not os.path.isfile(self.processed_paths[0]):
+            self.process()
+        self.lists = load_collated(self.processed_paths[0], device=device if str(device) != 'cpu' else None)
+        self.data, self.slices = self.lists.collate()
+
+    # --- InMemoryDataset surface the reference relies on ---
+    @property
+    def processed_dir(self):
+        return os.path.join(self.root, 'processed')
+
+    @property
+    def processed_file_names(self):       # sgrl_link_pred.py:87-94
+        name = f'SEAL_{self.split}_data' if self.percent == 100 else f'SEAL_{self.split}_data_{self.percent}'
+        return [name + '.pt']
+
+    @property
+    def processed_paths(self):
+        return [os.path.join(self.processed_dir, f) for f in self.processed_file_names]
+
+    @property
+    def num_features(self):               # sizes the MLP, models.py:316-320
+        return int(self.lists.xs[0].shape[1])
+
+    def __len__(self):
+        return len(self.lists)
+
+    def get(self, idx):
+        return self.lists[idx]
+
+    __getitem__ = get
+
+    def process(self):                    # sgrl_link_pred.py:96-220
+        d, args = self.data_in, self.args
+        pos_edge, neg_edge = get_pos_neg_edges(self.split, self.split_edge, d.edge_index, d.num_nodes, self.percent,
+                                               neg_ratio=self.neg_ratio, neg_seed=getattr(args, 'seed', 0))
+        ei = d.edge_index.cpu().numpy()
+        ew = getattr(d, 'edge_weight', None)
+        edge_weight = np.ones(ei.shape[1], dtype=np.int64) if ew is None else np.asarray(ew.cpu()).reshape(-1)
+        # csr_matrix sums duplicate entries, which is also what `coalesce` does when use_coalesce is set (:102-105)
+        A = ssp.csr_matrix((edge_weight, (ei[0], ei[1])), shape=(d.num_nodes, d.num_nodes))
+        rw_kwargs = None
+        if self.rw_kwargs.get('m'):       # ScaLed: walks are sampled on the GPU inside the call (create_rw_cache, :121-127)
+            rw_kwargs = {"rw_m": self.rw_kwargs.get('m'), "rw_M": self.rw_kwargs.get('M'), "sign": True,
+                         "seed": getattr(args, 'seed', 0), "node_label": self.node_label}
+        sign_kwargs = {"sign_k": args.sign_k, "use_feature": self.use_feature, "sign_type": self.sign_type,
+                       "optimize_sign": args.optimize_sign, "k_heuristic": args.k_heuristic,
+                       "k_node_set_strategy": args.k_node_set_strategy}
+        # the global powers of sgrl_link_pred.py:161-178 are never formed: only their count is used (tuned_sign.py)
+        powers_of_A = [None] * args.sign_k if self.sign_type in ('SoP', 'hybrid') else []
+        os.environ.setdefault('S3GRL_OUTPUT_DEVICE', 'cuda' if str(self.device) != 'cpu' else 'cpu')
+
+        def run(edges, y):
+            return extract_enclosing_subgraphs(edges, A, d.x, y, self.num_hops, self.node_label, self.ratio_per_hop,
+                                               self.max_nodes_per_hop, self.directed, None, rw_kwargs, sign_kwargs,
+                                               powers_of_A=powers_of_A, data=d)
+        if not self.pairwise:
+            out = run(pos_edge, 1) + run(neg_edge, 0)
+        elif self.pos_pairwise:
+            out = run(pos_edge, 1)
+        else:
+            out = run(neg_edge, 0)
+        assert isinstance(out, PrecomputedList)
+        save_collated(out, self.processed_paths[0])
