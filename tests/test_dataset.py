@@ -1,5 +1,5 @@
 """host orchestration mirrors — get_pos_neg_edges (reference utils.py:637-678) against
-outputs of the reference's own function (tests/golden/ref_posneg_edges.npz, generated through oracle/ref_runner
+outputs of the reference's own function (tests/golden/posneg_edges_ref.npz, generated through oracle/ref_runner
 with np.random.seed(11)) and SEALDataset.process (sgrl_link_pred.py:96-220) end to end on the GPU."""
 import os
 from types import SimpleNamespace
@@ -11,7 +11,7 @@ import torch
 from s3grl_b200 import get_pos_neg_edges
 from s3grl_b200.dataset import sample_negative_edges
 
-G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_posneg_edges.npz'))
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'posneg_edges_ref.npz'))
 
 
 def _inputs():
