@@ -136,6 +136,39 @@ def make_full_case(name, A, links, K, num_hops, node_label, X=None, x_spec=None)
     print(f"{name}: L={links.shape[1]} R={int(r['row_ptr'][-1])} -> {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def make_posneg_case():
+    """get_pos_neg_edges (reference utils.py:637-678) on seeded split dictionaries, np.random.seed(11): the link
+    ORDER it produces fixes the output row order.  The 'edge' format carries pre-sampled negatives (edge_neg), so
+    PyG's negative_sampling is not needed; the 'source_node' train split draws negatives with torch.randint and is
+    left out."""
+    import torch
+    utils, _ = rr.load_reference()
+    rng = np.random.default_rng(3)
+    N = 50
+    mk = lambda n: torch.as_tensor(rng.integers(0, N, (n, 2)))      # noqa: E731
+    split_edge = {s: {'edge': mk(n), 'edge_neg': mk(n2)} for s, n, n2 in (('train', 40, 40), ('valid', 9, 11), ('test', 13, 13))}
+    src = {s: {'source_node': torch.as_tensor(rng.integers(0, N, n)), 'target_node': torch.as_tensor(rng.integers(0, N, n)),
+               'target_node_neg': torch.as_tensor(rng.integers(0, N, (n, 3)))} for s, n in (('train', 30), ('valid', 8), ('test', 10))}
+    out = {}
+    for name, se in (('edge', split_edge), ('src', src)):
+        for split in ('train', 'valid', 'test'):
+            for percent in (100, 50):
+                if name == 'src' and split == 'train':
+                    continue
+                np.random.seed(11)
+                p, n = utils.get_pos_neg_edges(split, se, torch.zeros((2, 0), dtype=torch.long), N, percent)
+                out[f'{name}_{split}_{percent}_pos'] = p.numpy()
+                out[f'{name}_{split}_{percent}_neg'] = n.numpy()
+    for s in split_edge:
+        out[f'in_edge_{s}'] = split_edge[s]['edge'].numpy()
+        out[f'in_edgeneg_{s}'] = split_edge[s]['edge_neg'].numpy()
+    for s in src:
+        for k, v in src[s].items():
+            out[f'in_{k}_{s}'] = v.numpy()
+    np.savez_compressed(os.path.join(OUT, 'posneg_edges_ref.npz'), **out)
+    print(f"posneg_edges_ref: {len(out)} arrays")
+
+
 def tiny_graphs():
     """Hand graphs for the edge cases of SURVEY.md A.6: isolated endpoints, n == 2, an
     endpoint whose only neighbour is the other endpoint, pendant paths, a hub, two components."""
@@ -162,6 +195,7 @@ def sample_links(splits, count, seed):
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    make_posneg_case()
     A, links, X = tiny_graphs()
     for h in (1, 2, 3):
         make_case(f'tiny_pos_h{h}', A, links, 'pos', 3, h, None, X=X)
