@@ -16,4 +16,4 @@ from .engine import DeviceGraph, PrecomputeResult, algorithmic_bytes, precompute
 from .tuned_sign import OptimizedSignOperations  # noqa: F401
 from .utils import extract_enclosing_subgraphs  # noqa: F401
 from .loader import JointLoader, joint_rows, load_collated, save_collated  # noqa: F401
-from .dataset import SEALDataset, get_pos_neg_edges  # noqa: F401
+from .dataset import SEALDataset, do_edge_split, get_pos_neg_edges  # noqa: F401

@@ -43,6 +43,36 @@ def sample_negative_edges(edge_index, num_nodes, num_neg_samples, seed=0):
     return torch.as_tensor(np.asarray(out, dtype=np.int64).reshape(-1, 2).T.copy())
 
 
+def do_edge_split(data, fast_split=False, val_ratio=0.05, test_ratio=0.1, neg_ratio=1, seed=1):
+    """reference utils.py:588-634 (`data_passed=True` form): the 85/5/10 link split + 1:1 negatives, returned as the
+    same `split_edge` dictionary ({'train'|'valid'|'test': {'edge': [L,2], 'edge_neg': [L,2]}}) and leaving
+    `data.edge_index` = both directions of the TRAINING edges (what SEALDataset builds A from).  PyG's
+    train_test_split_edges / negative_sampling draw from torch's RNG and are not importable here, so the split is
+    drawn with NumPy (`datasets.split_links`, seeded): same construction, different random stream.  Training
+    positives hold both directions of every training edge."""
+    from . import datasets as ds
+    if fast_split:
+        raise NotImplementedError('Fast split is untested and unsupported.')      # reference utils.py:601
+    if neg_ratio != 1:
+        raise NotImplementedError("neg_ratio != 1 is not supported")
+    ei = data.edge_index.cpu().numpy()
+    und = np.unique(np.stack([np.minimum(ei[0], ei[1]), np.maximum(ei[0], ei[1])], 1), axis=0)
+    und = und[und[:, 0] != und[:, 1]]
+    A_train, splits = ds.split_links(und, int(data.num_nodes), val_ratio, test_ratio, seed)
+    coo = A_train.tocoo()
+    data.edge_index = torch.as_tensor(np.stack([coo.row, coo.col]).astype(np.int64))
+    split_edge = {}
+    for name in ('train', 'valid', 'test'):
+        pos, neg = splits[name]
+        split_edge[name] = {'edge': torch.as_tensor(np.ascontiguousarray(pos.T)),
+                            'edge_neg': torch.as_tensor(np.ascontiguousarray(neg.T))}
+    data.train_pos_edge_index = split_edge['train']['edge'].t()
+    data.train_neg_edge_index = split_edge['train']['edge_neg'].t()
+    data.val_pos_edge_index, data.val_neg_edge_index = split_edge['valid']['edge'].t(), split_edge['valid']['edge_neg'].t()
+    data.test_pos_edge_index, data.test_neg_edge_index = split_edge['test']['edge'].t(), split_edge['test']['edge_neg'].t()
+    return split_edge
+
+
 def get_pos_neg_edges(split, split_edge, edge_index, num_nodes, percent=100, neg_ratio=1, neg_seed=0):
     """reference utils.py:637-678, branch for branch; the two `np.random.permutation` calls per branch happen in
     the reference's order, so with the same NumPy seed and pre-sampled negatives (`edge_neg`, or the

@@ -32,6 +32,30 @@ def test_get_pos_neg_edges_matches_reference(fmt, split, percent):
     assert np.array_equal(neg.numpy(), G[f'{fmt}_{split}_{percent}_neg'])
 
 
+def test_do_edge_split_structure():
+    """reference utils.py:588-634: 85/5/10 split, 1:1 negatives, training positives in both directions, no
+    val/test positive left in the training graph, negatives are non-edges of the full graph."""
+    from s3grl_b200 import datasets as ds, do_edge_split
+    edges, N, _ = ds.load_graph('usair')
+    und = np.asarray(edges)
+    data = SimpleNamespace(edge_index=torch.as_tensor(np.concatenate([und.T, und.T[::-1]], 1).astype(np.int64)), num_nodes=N)
+    se = do_edge_split(data, seed=1)
+    E = np.unique(np.sort(und, 1), axis=0).shape[0]
+    n_v, n_t = int(np.floor(0.05 * E)), int(np.floor(0.1 * E))
+    assert se['valid']['edge'].shape == (n_v, 2) and se['test']['edge'].shape == (n_t, 2)
+    assert se['train']['edge'].shape == (2 * (E - n_v - n_t), 2) == tuple(se['train']['edge_neg'].shape)
+    key = lambda t: set((t[:, 0] * N + t[:, 1]).tolist())           # noqa: E731
+    train = key(data.edge_index.t())
+    assert train == key(se['train']['edge']) and all((b * N + a) in train for a, b in se['train']['edge'].tolist())
+    full = key(torch.as_tensor(np.concatenate([und, und[:, ::-1]], 0).astype(np.int64)))
+    for s in ('valid', 'test'):
+        assert not (key(se[s]['edge']) & train) and key(se[s]['edge']) <= full
+        assert not (key(se[s]['edge_neg']) & full)
+    assert not (key(se['train']['edge_neg']) & train)
+    with pytest.raises(NotImplementedError):
+        do_edge_split(data, fast_split=True)
+
+
 def test_sampled_negatives_are_non_edges():
     ei = torch.as_tensor(np.random.default_rng(0).integers(0, 30, (2, 200)))
     neg = sample_negative_edges(ei, 30, 150, seed=4).numpy()
