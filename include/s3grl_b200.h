@@ -258,6 +258,16 @@ int s3_joint_rows(const float* const* src, int32_t num_ops, int64_t num_cols, in
                   const int64_t* link_idx, int64_t num_links, const int64_t* out_row_ptr, int32_t rows_per_link,
                   float* dst, int64_t ld_dst, int64_t* batch_vec, void* stream);
 
+/* Fused scoring head of SIGNNet for the fixed-row flows, evaluation mode: replaces
+ * models.py:370-376 (operator_diff = Linear -> ELU -> BatchNorm) + models.py:339-346 (center pooling
+ * h[2i] * h[2i+1], k_heuristic = 0) on the loader's joint matrix. tcgen05 TF32 tensor-core GEMM with the
+ * epilogue fused; 256 hidden channels (every paper config).
+ * joint [rows, ld_joint] fp32 (rows even, ld_joint*4 a multiple of 16 bytes, 16-byte aligned base), weight
+ * [256, ld_w] (torch Linear layout), bias / bn_scale / bn_shift [256] with bn_scale = gamma / sqrt(var + eps),
+ * bn_shift = beta - mean * bn_scale; pooled [rows / 2, 256]. */
+int s3_sign_head(const float* joint, int64_t rows, int64_t kdim, int64_t ld_joint, const float* weight, int64_t ld_w,
+                 int64_t hidden, const float* bias, const float* bn_scale, const float* bn_shift, float* pooled, void* stream);
+
 /* Optional dumps for parity checks: canonical global-id edge list of every record,
  * edges[e] = (global row, global col), e in [edge_ptr[r], edge_ptr[r+1]). */
 int s3_dump_edges(const s3_batch* b, const int64_t* edge_ptr, int32_t* edges_out, void* stream);

@@ -17,3 +17,4 @@ from .tuned_sign import OptimizedSignOperations  # noqa: F401
 from .utils import extract_enclosing_subgraphs  # noqa: F401
 from .loader import JointLoader, joint_rows, load_collated, save_collated  # noqa: F401
 from .dataset import SEALDataset, do_edge_split, get_pos_neg_edges  # noqa: F401
+from .head import fold_batchnorm, sign_head  # noqa: F401

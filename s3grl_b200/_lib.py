@@ -20,7 +20,7 @@ CTR_CURSOR, CTR_ERRORS, CTR_ROWS, CTR_ITEMS, CTR_MAX_N, CTR_SUM_N, CTR_SUM_D, CT
 
 EXPORTS = ['s3_version', 's3_error_string', 's3_last_cuda_error', 's3_num_records', 's3_extract_smem_bytes',
            's3_min_arena_words', 's3_extract_tier',
-           's3_extract', 's3_plan', 's3_plan_items', 's3_diffuse', 's3_gather', 's3_gather_ccn', 's3_ccn_chain', 's3_plan_full', 's3_sign_full', 's3_joint_rows', 's3_walk_sets', 's3_dump_edges']
+           's3_extract', 's3_plan', 's3_plan_items', 's3_diffuse', 's3_gather', 's3_gather_ccn', 's3_ccn_chain', 's3_plan_full', 's3_sign_full', 's3_joint_rows', 's3_sign_head', 's3_walk_sets', 's3_dump_edges']
 
 
 class Graph(C.Structure):
@@ -80,13 +80,15 @@ def lib():
         L.s3_ccn_chain.argtypes = L.s3_gather.argtypes
         L.s3_joint_rows.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.s3_sign_head.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.s3_plan_full.argtypes = [C.POINTER(Batch), C.c_void_p]
         L.s3_sign_full.argtypes = [C.POINTER(Graph), C.POINTER(Batch), C.c_int64, C.c_int32, C.POINTER(C.c_void_p),
                                    C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
         L.s3_walk_sets.argtypes = [C.POINTER(Graph), C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, C.c_int32,
                                    C.c_void_p, C.c_void_p, C.c_void_p]
         L.s3_dump_edges.argtypes = [C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p]
-        for fn in ('s3_extract', 's3_plan', 's3_plan_items', 's3_diffuse', 's3_gather', 's3_gather_ccn', 's3_ccn_chain', 's3_plan_full', 's3_sign_full', 's3_joint_rows', 's3_walk_sets',
+        for fn in ('s3_extract', 's3_plan', 's3_plan_items', 's3_diffuse', 's3_gather', 's3_gather_ccn', 's3_ccn_chain', 's3_plan_full', 's3_sign_full', 's3_joint_rows', 's3_sign_head', 's3_walk_sets',
                    's3_dump_edges'):
             getattr(L, fn).restype = C.c_int
         _lib = L

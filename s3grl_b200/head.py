@@ -1,0 +1,50 @@
+"""Fused scoring head of SIGNNet for the fixed-row flows, evaluation mode.
+
+reference models.py:370-376: `x = operator_diff(torch.cat(xs, -1))` with operator_diff = MLP([(K+1)F', hidden],
+batch_norm=True, act_first=True, act='elu', plain_last=False), i.e. Linear -> ELU -> BatchNorm1d (-> dropout,
+identity in eval), then models.py:339-346 `_centre_pool_helper` without CCN rows: h[center] * h[center + 1].
+`sign_head` does both in one tcgen05 (TF32 in, fp32 accumulate) kernel on the loader's joint matrix
+(`JointLoader` batch `.joint`, or a whole epoch); the small link_pred_mlp on [links, hidden] stays in torch.
+TF32 rounds the inputs to 10 mantissa bits: results agree with an fp32 reference to ~1e-3 relative — this is the
+model head, not the precompute path, whose 1e-5 tolerance is untouched.  No CPU path.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+HIDDEN = 256
+
+
+def fold_batchnorm(bn_weight, bn_bias, running_mean, running_var, eps=1e-5):
+    """BatchNorm1d in eval mode as y = x * scale + shift."""
+    scale = bn_weight / torch.sqrt(running_var + eps)
+    return scale.contiguous(), (bn_bias - running_mean * scale).contiguous()
+
+
+def sign_head(joint, lin_weight, lin_bias, bn_scale, bn_shift, out=None, stream=None):
+    """pooled[i] = bn(elu(joint[2i] W^T + b)) * bn(elu(joint[2i+1] W^T + b))  ->  [rows / 2, 256] float32.
+
+    joint [rows, (K+1)F'] contiguous float32 CUDA tensor (rows even; (K+1)F' a multiple of 4 — TMA needs 16-byte
+    row strides), lin_weight [256, (K+1)F'] (torch Linear layout), lin_bias / bn_scale / bn_shift [256]."""
+    lib = L.lib()
+    dev = joint.device
+    if dev.type != 'cuda':
+        raise RuntimeError("sign_head needs CUDA tensors: there is no CPU path")
+    rows, kd = int(joint.shape[0]), int(joint.shape[1])
+    if lin_weight.shape != (HIDDEN, kd):
+        raise NotImplementedError(f"sign_head serves hidden_channels = {HIDDEN} (got weight {tuple(lin_weight.shape)})")
+    if rows % 2 or kd % 4:
+        raise ValueError("rows must be even and (K+1)*F' a multiple of 4 (pad the joint matrix otherwise)")
+    ts = [joint, lin_weight, lin_bias, bn_scale, bn_shift]
+    if not all(t.dtype == torch.float32 and t.is_contiguous() and t.device == dev for t in ts):
+        raise ValueError("all inputs must be contiguous float32 tensors on the joint matrix's device")
+    if out is None:
+        out = torch.empty((rows // 2, HIDDEN), dtype=torch.float32, device=dev)
+    st = stream if stream is not None else torch.cuda.current_stream(dev)
+    p = lambda t: C.c_void_p(t.data_ptr())      # noqa: E731
+    with torch.cuda.device(dev):
+        L.check(lib.s3_sign_head(p(joint), rows, kd, kd, p(lin_weight), kd, HIDDEN, p(lin_bias), p(bn_scale), p(bn_shift),
+                                 p(out), C.c_void_p(st.cuda_stream)), 's3_sign_head')
+    return out
