@@ -264,9 +264,11 @@ int s3_joint_rows(const float* const* src, int32_t num_ops, int64_t num_cols, in
  * epilogue fused; 256 hidden channels (every paper config).
  * joint [rows, ld_joint] fp32 (rows even, ld_joint*4 a multiple of 16 bytes, 16-byte aligned base), weight
  * [256, ld_w] (torch Linear layout), bias / bn_scale / bn_shift [256] with bn_scale = gamma / sqrt(var + eps),
- * bn_shift = beta - mean * bn_scale; pooled [rows / 2, 256]. */
+ * bn_shift = beta - mean * bn_scale. pool != 0: pooled [rows / 2, 256] = h[2i] * h[2i+1]; pool == 0: pooled [rows, 256]
+ * = h itself (PoS Plus: the CCN pooling of models.py:347-367 is then done by the caller). */
 int s3_sign_head(const float* joint, int64_t rows, int64_t kdim, int64_t ld_joint, const float* weight, int64_t ld_w,
-                 int64_t hidden, const float* bias, const float* bn_scale, const float* bn_shift, float* pooled, void* stream);
+                 int64_t hidden, const float* bias, const float* bn_scale, const float* bn_shift, float* pooled, int32_t pool,
+                 void* stream);
 
 /* Optional dumps for parity checks: canonical global-id edge list of every record,
  * edges[e] = (global row, global col), e in [edge_ptr[r], edge_ptr[r+1]). */

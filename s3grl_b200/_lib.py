@@ -81,7 +81,7 @@ def lib():
         L.s3_joint_rows.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.s3_sign_head.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
-                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.s3_plan_full.argtypes = [C.POINTER(Batch), C.c_void_p]
         L.s3_sign_full.argtypes = [C.POINTER(Graph), C.POINTER(Batch), C.c_int64, C.c_int32, C.POINTER(C.c_void_p),
                                    C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]

@@ -225,14 +225,15 @@ int s3_joint_rows(const float* const* src, int32_t num_ops, int64_t num_cols, in
 }
 
 int s3_sign_head(const float* joint, int64_t rows, int64_t kdim, int64_t ld_joint, const float* weight, int64_t ld_w,
-                 int64_t hidden, const float* bias, const float* bn_scale, const float* bn_shift, float* pooled, void* stream) {
+                 int64_t hidden, const float* bias, const float* bn_scale, const float* bn_shift, float* pooled, int32_t pool,
+                 void* stream) {
     if (hidden != 256) return S3_ERR_UNSUPPORTED;
-    if (rows < 0 || (rows & 1) || kdim < 1 || ld_joint < kdim || ld_w < kdim || (ld_joint & 3) || (ld_w & 3)) return S3_ERR_INVALID_ARG;
+    if (rows < 0 || (pool && (rows & 1)) || kdim < 1 || ld_joint < kdim || ld_w < kdim || (ld_joint & 3) || (ld_w & 3)) return S3_ERR_INVALID_ARG;
     if (rows > 0 && (!joint || !weight || !bias || !bn_scale || !bn_shift || !pooled)) return S3_ERR_INVALID_ARG;
     if ((reinterpret_cast<uintptr_t>(joint) & 15) || (reinterpret_cast<uintptr_t>(weight) & 15) ||
         (reinterpret_cast<uintptr_t>(pooled) & 15) || rows > INT32_MAX)
         return S3_ERR_INVALID_ARG;
-    cudaError_t e = s3::launch_sign_head(joint, rows, kdim, ld_joint, weight, ld_w, bias, bn_scale, bn_shift, pooled,
+    cudaError_t e = s3::launch_sign_head(joint, rows, kdim, ld_joint, weight, ld_w, bias, bn_scale, bn_shift, pooled, pool ? 1 : 0,
                                          static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? S3_OK : cuda_fail(e);
 }

@@ -97,7 +97,7 @@ cudaError_t launch_joint_rows(const OutPtrs& src, int num_ops, int64_t cols, int
                               const int64_t* link_idx, int64_t num_links, const int64_t* out_row_ptr, int rows_per_link,
                               float* dst, int64_t ld_dst, int64_t* batch_vec, cudaStream_t st);
 cudaError_t launch_sign_head(const float* x, int64_t rows, int64_t kdim, int64_t ldx, const float* w, int64_t ldw,
-                             const float* bias, const float* scale, const float* shift, float* pooled, cudaStream_t st);
+                             const float* bias, const float* scale, const float* shift, float* pooled, int pool, cudaStream_t st);
 cudaError_t launch_dump_edges(const s3_batch& b, const int64_t* edge_ptr, int32_t* edges_out, cudaStream_t st);
 
 }  // namespace s3

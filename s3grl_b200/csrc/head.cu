@@ -41,7 +41,8 @@ struct HeadParams {
     const float* __restrict__ bias;
     const float* __restrict__ scale;
     const float* __restrict__ shift;
-    float* __restrict__ pooled;  // [rows / 2, 256]
+    float* __restrict__ pooled;  // [rows / 2, 256], or [rows, 256] when pool == 0
+    int pool;
     int64_t rows;
     int num_kb;
 };
@@ -183,7 +184,7 @@ sign_head_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             const int64_t row = (int64_t)tile * kHeadM + q * 32 + lane;
             mbar_wait(&acc_full[as], (t >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float* out = p.pooled + (row >> 1) * kHeadN;
+            float* out = p.pooled + (p.pool ? (row >> 1) : row) * kHeadN;
             for (int c0 = half * (kHeadN / 2); c0 < (half + 1) * (kHeadN / 2); c0 += 32) {
                 uint32_t r[32];
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kHeadN + c0);
@@ -203,9 +204,10 @@ sign_head_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                     float z = __uint_as_float(r[i]) + s_bias[c0 + i];
                     z = z > 0.0f ? z : __expf(z) - 1.0f;             // ELU (alpha = 1)
                     z = fmaf(z, s_scale[c0 + i], s_shift[c0 + i]);   // BatchNorm1d in eval mode as an affine map
-                    v[i] = z * __shfl_xor_sync(0xffffffffu, z, 1);   // h_src * h_dst: rows 2i and 2i+1 sit in adjacent lanes
+                    const float other = __shfl_xor_sync(0xffffffffu, z, 1);
+                    v[i] = p.pool ? z * other : z;                   // h_src * h_dst: rows 2i and 2i+1 sit in adjacent lanes
                 }
-                if (!(lane & 1) && row < p.rows) {
+                if ((!(lane & 1) || !p.pool) && row < p.rows) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 4)
                         *reinterpret_cast<float4*>(out + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -239,7 +241,7 @@ cudaError_t make_map(EncodeTiledFn enc, CUtensorMap* map, const float* base, int
 }  // namespace
 
 cudaError_t launch_sign_head(const float* x, int64_t rows, int64_t kdim, int64_t ldx, const float* w, int64_t ldw,
-                             const float* bias, const float* scale, const float* shift, float* pooled, cudaStream_t st) {
+                             const float* bias, const float* scale, const float* shift, float* pooled, int pool, cudaStream_t st) {
     if (rows == 0) return cudaSuccess;
     static EncodeTiledFn enc = nullptr;
     if (!enc) {
@@ -266,6 +268,7 @@ cudaError_t launch_sign_head(const float* x, int64_t rows, int64_t kdim, int64_t
     p.scale = scale;
     p.shift = shift;
     p.pooled = pooled;
+    p.pool = pool;
     p.rows = rows;
     p.num_kb = (int)((kdim + kHeadKB - 1) / kHeadKB);
     static int sms = 0;

@@ -23,11 +23,12 @@ def fold_batchnorm(bn_weight, bn_bias, running_mean, running_var, eps=1e-5):
     return scale.contiguous(), (bn_bias - running_mean * scale).contiguous()
 
 
-def sign_head(joint, lin_weight, lin_bias, bn_scale, bn_shift, out=None, stream=None):
+def sign_head(joint, lin_weight, lin_bias, bn_scale, bn_shift, out=None, stream=None, pool=True):
     """pooled[i] = bn(elu(joint[2i] W^T + b)) * bn(elu(joint[2i+1] W^T + b))  ->  [rows / 2, 256] float32.
 
     joint [rows, (K+1)F'] contiguous float32 CUDA tensor (rows even; (K+1)F' a multiple of 4 — TMA needs 16-byte
-    row strides), lin_weight [256, (K+1)F'] (torch Linear layout), lin_bias / bn_scale / bn_shift [256]."""
+    row strides), lin_weight [256, (K+1)F'] (torch Linear layout), lin_bias / bn_scale / bn_shift [256].
+    pool=False returns h = bn(elu(joint W^T + b)) itself, [rows, 256] (PoS Plus: CCN pooling stays with the caller)."""
     lib = L.lib()
     dev = joint.device
     if dev.type != 'cuda':
@@ -35,16 +36,16 @@ def sign_head(joint, lin_weight, lin_bias, bn_scale, bn_shift, out=None, stream=
     rows, kd = int(joint.shape[0]), int(joint.shape[1])
     if lin_weight.shape != (HIDDEN, kd):
         raise NotImplementedError(f"sign_head serves hidden_channels = {HIDDEN} (got weight {tuple(lin_weight.shape)})")
-    if rows % 2 or kd % 4:
+    if (pool and rows % 2) or kd % 4:
         raise ValueError("rows must be even and (K+1)*F' a multiple of 4 (pad the joint matrix otherwise)")
     ts = [joint, lin_weight, lin_bias, bn_scale, bn_shift]
     if not all(t.dtype == torch.float32 and t.is_contiguous() and t.device == dev for t in ts):
         raise ValueError("all inputs must be contiguous float32 tensors on the joint matrix's device")
     if out is None:
-        out = torch.empty((rows // 2, HIDDEN), dtype=torch.float32, device=dev)
+        out = torch.empty((rows // 2 if pool else rows, HIDDEN), dtype=torch.float32, device=dev)
     st = stream if stream is not None else torch.cuda.current_stream(dev)
     p = lambda t: C.c_void_p(t.data_ptr())      # noqa: E731
     with torch.cuda.device(dev):
         L.check(lib.s3_sign_head(p(joint), rows, kd, kd, p(lin_weight), kd, HIDDEN, p(lin_bias), p(bn_scale), p(bn_shift),
-                                 p(out), C.c_void_p(st.cuda_stream)), 's3_sign_head')
+                                 p(out), 1 if pool else 0, C.c_void_p(st.cuda_stream)), 's3_sign_head')
     return out

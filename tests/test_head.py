@@ -57,6 +57,19 @@ def test_sign_head_on_loader_batches_and_module_parameters():
         assert err <= 2e-3 * float(ref.abs().max()) + 1e-6
 
 
+def test_sign_head_without_pooling_for_ccn_flows():
+    """pool=False: h itself, for PoS Plus where models.py:347-367 pools a variable number of CCN rows per link."""
+    from s3grl_b200 import sign_head
+    g = torch.Generator(device='cuda').manual_seed(9)
+    joint = torch.rand((777, 100), device='cuda', generator=g) / 4
+    W = (torch.rand((256, 100), device='cuda', generator=g) - 0.5)
+    b, scale, shift = (torch.rand(256, device='cuda', generator=g) - 0.5 for _ in range(3))
+    got = sign_head(joint, W, b, scale + 1.0, shift, pool=False)
+    ref = (torch.nn.functional.elu(joint.double() @ W.double().t() + b.double()) * (scale.double() + 1.0) + shift.double()).float()
+    assert got.shape == (777, 256)
+    assert float((got - ref).abs().max()) <= 2e-3 * float(ref.abs().max()) + 1e-6
+
+
 def test_sign_head_rejects_bad_shapes():
     from s3grl_b200 import sign_head
     z = torch.zeros
