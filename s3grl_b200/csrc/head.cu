@@ -27,12 +27,13 @@ namespace s3 {
 namespace {
 
 constexpr int kHeadN = 256;        // hidden channels (every paper config: hidden_channels = 256)
-constexpr int kHeadM = 128;        // rows per CTA
+constexpr int kHeadM = 128;        // rows per MMA (UMMA_M)
+constexpr int kHeadTileM = 256;    // rows per CTA tile: two MMAs share every [256 x 32] weight stage
 constexpr int kHeadKB = 32;        // tf32 elements per stage along K = one 128-byte swizzle atom
-constexpr int kHeadStages = 4;
+constexpr int kHeadStages = 3;
 constexpr int kHeadEpiWarps = 8;
 constexpr int kHeadThreads = 64 + 32 * kHeadEpiWarps;
-constexpr uint32_t kABytes = kHeadM * kHeadKB * 4;  // 16 KB
+constexpr uint32_t kABytes = kHeadTileM * kHeadKB * 4;  // 32 KB: rows 0-127 | rows 128-255
 constexpr uint32_t kBBytes = kHeadN * kHeadKB * 4;  // 32 KB
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
 constexpr size_t kHeadSmem = (size_t)kHeadStages * kStageBytes + 1024;
@@ -98,18 +99,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// Persistent: one CTA per SM walks the 128-row tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the accumulator is
-// double-buffered in TMEM (2 x 256 columns = all of it), so the MMAs of tile i+1 run while the epilogue warps
-// drain tile i.
+// Persistent: one CTA per SM walks the 256-row tiles blockIdx.x, blockIdx.x + gridDim.x, ... Each tile is two
+// M = 128 accumulators (2 x 256 TMEM columns = all of it) fed from the SAME weight stage, so the [256 x 32] weight
+// tile is read from L2 once per 256 rows (the kernel is L2-throughput bound on those re-reads; measured).
 __global__ void __launch_bounds__(kHeadThreads, 1)
 sign_head_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, HeadParams p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[kHeadStages], empty_bar[kHeadStages], acc_full[2], acc_empty[2];
+    __shared__ __align__(8) uint64_t full_bar[kHeadStages], empty_bar[kHeadStages], acc_full, acc_empty;
     __shared__ uint32_t s_tmem;
     __shared__ float s_bias[kHeadN], s_scale[kHeadN], s_shift[kHeadN];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;  // the swizzle pattern is a function of the address
-    const int num_tiles = (int)((p.rows + kHeadM - 1) / kHeadM);
+    const int num_tiles = (int)((p.rows + kHeadTileM - 1) / kHeadTileM);
 
     for (int i = threadIdx.x; i < kHeadN; i += kHeadThreads) {
         s_bias[i] = p.bias[i];
@@ -121,10 +122,8 @@ sign_head_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&acc_full[s], 1);
-            mbar_init(&acc_empty[s], kHeadEpiWarps);
-        }
+        mbar_init(&acc_full, 1);
+        mbar_init(&acc_empty, kHeadEpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -146,7 +145,7 @@ sign_head_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     mbar_expect_tx(&full_bar[s], kStageBytes);
                     const uint32_t a = tiles + s * kStageBytes;
-                    tma_load_2d(&map_x, &full_bar[s], a, kb * kHeadKB, tile * kHeadM);
+                    tma_load_2d(&map_x, &full_bar[s], a, kb * kHeadKB, tile * kHeadTileM);
                     tma_load_2d(&map_w, &full_bar[s], a + kABytes, kb * kHeadKB, 0);
                 }
             }
@@ -157,10 +156,8 @@ sign_head_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kHeadN >> 3) << 17) | ((uint32_t)(kHeadM >> 4) << 24);
             int it = 0, t = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
-                const int as = t & 1;
-                mbar_wait(&acc_empty[as], ((t >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
+                mbar_wait(&acc_empty, (t & 1) ^ 1);  // the epilogue has drained both accumulators
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t acc = tmem + (uint32_t)(as * kHeadN);
                 for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
                     const int s = it % kHeadStages;
                     const uint32_t ph = (it / kHeadStages) & 1;
@@ -168,26 +165,28 @@ sign_head_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a = tiles + s * kStageBytes;
 #pragma unroll
-                    for (int k = 0; k < kHeadKB / 8; ++k)  // UMMA_K = 8 tf32 = 32 bytes inside the swizzle atom
-                        umma_tf32(acc, umma_desc(a + k * 32), umma_desc(a + kABytes + k * 32), idesc, (kb | k) != 0);
+                    for (int k = 0; k < kHeadKB / 8; ++k) {  // UMMA_K = 8 tf32 = 32 bytes inside the swizzle atom
+                        const uint64_t db = umma_desc(a + kABytes + k * 32);
+                        umma_tf32(tmem, umma_desc(a + k * 32), db, idesc, (kb | k) != 0);
+                        umma_tf32(tmem + kHeadN, umma_desc(a + kABytes / 2 + k * 32), db, idesc, (kb | k) != 0);
+                    }
                     umma_commit(&empty_bar[s]);  // the stage is free once these MMAs have read it
                 }
-                umma_commit(&acc_full[as]);  // accumulator of this tile complete
+                umma_commit(&acc_full);  // both accumulators of this tile complete
             }
         }
     } else {
-        // ===== epilogue: 8 warps; warp w owns TMEM lanes 32*(w % 4) .. +32 and half of the columns =====
+        // ===== epilogue: 8 warps; warp w owns TMEM lanes 32*(w % 4) .. +32 of accumulator (w - 2) / 4 =====
         const int q = warp & 3, half = (warp - 2) >> 2;
         int t = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
-            const int as = t & 1;
-            const int64_t row = (int64_t)tile * kHeadM + q * 32 + lane;
-            mbar_wait(&acc_full[as], (t >> 1) & 1);
+            const int64_t row = (int64_t)tile * kHeadTileM + half * kHeadM + q * 32 + lane;
+            mbar_wait(&acc_full, t & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             float* out = p.pooled + (p.pool ? (row >> 1) : row) * kHeadN;
-            for (int c0 = half * (kHeadN / 2); c0 < (half + 1) * (kHeadN / 2); c0 += 32) {
+            for (int c0 = 0; c0 < kHeadN; c0 += 32) {
                 uint32_t r[32];
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kHeadN + c0);
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * kHeadN + c0);
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -215,7 +214,7 @@ sign_head_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[as]);  // this warp's part of the accumulator may be overwritten
+            if (lane == 0) mbar_arrive(&acc_empty);  // this warp's part of the accumulators may be overwritten
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -259,7 +258,7 @@ cudaError_t launch_sign_head(const float* x, int64_t rows, int64_t kdim, int64_t
         configured = true;
     }
     CUtensorMap map_x, map_w;
-    cudaError_t e = make_map(enc, &map_x, x, rows, kdim, ldx, kHeadM);
+    cudaError_t e = make_map(enc, &map_x, x, rows, kdim, ldx, kHeadTileM);
     if (e != cudaSuccess) return e;
     e = make_map(enc, &map_w, w, kHeadN, kdim, ldw, kHeadN);
     if (e != cudaSuccess) return e;
@@ -279,7 +278,7 @@ cudaError_t launch_sign_head(const float* x, int64_t rows, int64_t kdim, int64_t
         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
     }
-    const int64_t num_tiles = (rows + kHeadM - 1) / kHeadM;
+    const int64_t num_tiles = (rows + kHeadTileM - 1) / kHeadTileM;
     sign_head_kernel<<<(unsigned)(num_tiles < sms ? num_tiles : sms), kHeadThreads, kHeadSmem, st>>>(map_x, map_w, p);
     return cudaGetLastError();
 }
