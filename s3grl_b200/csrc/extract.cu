@@ -58,6 +58,7 @@ struct ExtractParams {
     unsigned long long* counters;
 };
 
+constexpr int kStreamLanes = 4;  // lanes per streamed (hop-K) row
 constexpr int kRowCap = 1536;  // rows whose (start, adjacency offset) are cached in shared memory
 constexpr int kZCap = 1024;    // floats per shared z buffer
 
@@ -107,6 +108,9 @@ __global__ void __launch_bounds__(kExtractThreads, 5) front_kernel(ExtractParams
     const bool pos_flow = p.flow == S3_FLOW_POS;
     const int lane = tid & 31, l8 = tid & 7, grp = tid >> 3;  // 8-lane groups
     constexpr int NG = kExtractThreads / 8;
+    // streamed hop-K rows are mostly low-degree: narrower lane groups leave fewer lanes idle
+    constexpr int NGS = kExtractThreads / kStreamLanes;
+    const int ls = tid & (kStreamLanes - 1), grps = tid / kStreamLanes;
     const int NW = (K + 1) * SC, NWP = (NW + 3) & ~3;
 
     for (;;) {
@@ -460,8 +464,8 @@ __global__ void __launch_bounds__(kExtractThreads, 5) front_kernel(ExtractParams
                     const uint32_t* Lz = Lb + (size_t)max(zl, 0) * W;
                     const uint32_t* Pz = pre + (size_t)max(zl, 0) * W;
                     const int zbase = zl >= 0 ? s_lvl_base[zl] : 0;
-                    for (int jb0 = n_store; jb0 < n_reach; jb0 += NG) {
-                        const int j = jb0 + grp;
+                    for (int jb0 = n_store; jb0 < n_reach; jb0 += NGS) {
+                        const int j = jb0 + grps;
                         const bool valid = j < n_reach;
                         int64_t e0 = 0;
                         int len = 0;
@@ -473,7 +477,7 @@ __global__ void __launch_bounds__(kExtractThreads, 5) front_kernel(ExtractParams
 #pragma unroll
                         for (int c = 0; c < SC; ++c) t[c] = 0.0f;
                         int cntv = 0;
-                        for (int idx = l8; idx < len; idx += 8) {
+                        for (int idx = ls; idx < len; idx += kStreamLanes) {
                             const int c_ = p.indices[e0 + idx];
                             const int w = c_ >> 5, b = c_ & 31;
                             cntv += (V[w] >> b) & 1u;
@@ -491,14 +495,12 @@ __global__ void __launch_bounds__(kExtractThreads, 5) front_kernel(ExtractParams
                         }
 #pragma unroll
                         for (int c = 0; c < SC; ++c) {
-                            t[c] += __shfl_xor_sync(0xffffffffu, t[c], 4);
-                            t[c] += __shfl_xor_sync(0xffffffffu, t[c], 2);
-                            t[c] += __shfl_xor_sync(0xffffffffu, t[c], 1);
+#pragma unroll
+                            for (int d = kStreamLanes / 2; d > 0; d >>= 1) t[c] += __shfl_xor_sync(0xffffffffu, t[c], d);
                         }
-                        cntv += __shfl_xor_sync(0xffffffffu, cntv, 4);
-                        cntv += __shfl_xor_sync(0xffffffffu, cntv, 2);
-                        cntv += __shfl_xor_sync(0xffffffffu, cntv, 1);
-                        if (valid && l8 == 0) {
+#pragma unroll
+                        for (int d = kStreamLanes / 2; d > 0; d >>= 1) cntv += __shfl_xor_sync(0xffffffffu, cntv, d);
+                        if (valid && ls == 0) {
                             const int deg = pos_flow ? cntv : len;
                             const float dis = deg > 0 ? 1.0f / sqrtf((float)deg) : 0.0f;
 #pragma unroll
