@@ -247,7 +247,20 @@ class _Call:
             batch_records = {L.STRATEGY_NONE: 32768, L.STRATEGY_INTERSECTION: 262144, L.STRATEGY_UNION: 8192}[self.strategy]
             batch_records = max(1024, min(batch_records, int(free // 3 // (32768 * 4))))
         self.batch_links = max(1, int(batch_records) // self.rpl)
-        self.num_batches = (self.num_links + self.batch_links - 1) // self.batch_links
+        # batch boundaries (links).  With a pipelined device->host copy the first batches are small (1/8, 1/4, 1/2 of a
+        # batch): the copy engine starts after ~1 ms of compute instead of a whole batch, and PCIe is the bottleneck
+        # of that path.  Results do not depend on the batch composition.
+        starts, pos = [0], 0
+        ramp = [self.batch_links // 8, self.batch_links // 4, self.batch_links // 2] if host_out is not None else []
+        for step in ramp:
+            if step >= 512 and pos + step < self.num_links:
+                pos += step
+                starts.append(pos)
+        while pos + self.batch_links < self.num_links:
+            pos += self.batch_links
+            starts.append(pos)
+        self.starts = starts + [self.num_links]
+        self.num_batches = len(starts) if self.num_links else 0
         self.overlap = bool(overlap) and self.fixed_rows and not self.return_graphs and self.num_batches > 1
         self.flags = ((L.BATCH_STORE_ALL_ROWS if self.return_graphs else 0)
                       | (L.BATCH_FORCE_SORTED_TIER if force_sorted_tier else 0)
@@ -272,8 +285,7 @@ class _Call:
 
     # ------------------------------------------------------------------ helpers
     def bounds(self, bi):
-        b0 = bi * self.batch_links
-        return b0, min(self.num_links, b0 + self.batch_links)
+        return self.starts[bi], self.starts[bi + 1]
 
     def make_batch(self, b0, b1, arena, off, cnt, ctr, row_ptr=None, item_ptr=None, item_rec=None, order=None):
         src = self.links[0, b0:b1] if b1 > b0 else None
@@ -313,7 +325,7 @@ class _Call:
         if int(c[L.CTR_ERRORS]) != 0:
             status = cnt[:, L.CNT_STATUS]
             if bool((status == L.REC_BAD_LINK).any()):
-                bad = int(torch.nonzero(status == L.REC_BAD_LINK)[0]) // self.rpl + bi * self.batch_links
+                bad = int(torch.nonzero(status == L.REC_BAD_LINK)[0]) // self.rpl + self.starts[bi]
                 raise ValueError(f"invalid target link at position {bad}: node id out of range or src == dst")
             return False
         self.stats['sum_n'] += int(c[L.CTR_SUM_N])
