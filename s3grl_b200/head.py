@@ -26,8 +26,9 @@ def fold_batchnorm(bn_weight, bn_bias, running_mean, running_var, eps=1e-5):
 def sign_head(joint, lin_weight, lin_bias, bn_scale, bn_shift, out=None, stream=None, pool=True):
     """pooled[i] = bn(elu(joint[2i] W^T + b)) * bn(elu(joint[2i+1] W^T + b))  ->  [rows / 2, 256] float32.
 
-    joint [rows, (K+1)F'] contiguous float32 CUDA tensor (rows even; (K+1)F' a multiple of 4 — TMA needs 16-byte
-    row strides), lin_weight [256, (K+1)F'] (torch Linear layout), lin_bias / bn_scale / bn_shift [256].
+    joint [rows, (K+1)F'] float32 CUDA tensor (rows even when pooling), lin_weight [256, (K+1)F'] (torch Linear
+    layout), lin_bias / bn_scale / bn_shift [256].  TMA needs 16-byte row strides: the loader's joint matrices
+    already have them (padded row stride); any other operand is copied once into a padded buffer.
     pool=False returns h = bn(elu(joint W^T + b)) itself, [rows, 256] (PoS Plus: CCN pooling stays with the caller)."""
     lib = L.lib()
     dev = joint.device
@@ -36,16 +37,27 @@ def sign_head(joint, lin_weight, lin_bias, bn_scale, bn_shift, out=None, stream=
     rows, kd = int(joint.shape[0]), int(joint.shape[1])
     if lin_weight.shape != (HIDDEN, kd):
         raise NotImplementedError(f"sign_head serves hidden_channels = {HIDDEN} (got weight {tuple(lin_weight.shape)})")
-    if (pool and rows % 2) or kd % 4:
-        raise ValueError("rows must be even and (K+1)*F' a multiple of 4 (pad the joint matrix otherwise)")
-    ts = [joint, lin_weight, lin_bias, bn_scale, bn_shift]
-    if not all(t.dtype == torch.float32 and t.is_contiguous() and t.device == dev for t in ts):
-        raise ValueError("all inputs must be contiguous float32 tensors on the joint matrix's device")
+    if pool and rows % 2:
+        raise ValueError("rows must be even for center pooling")
+
+    def tma_ready(t):
+        """[r, kd] float32 with unit column stride, 16-byte row stride and base; padded copy otherwise."""
+        if (t.dtype == torch.float32 and t.device == dev and t.stride(1) == 1 and t.stride(0) % 4 == 0
+                and t.stride(0) >= kd and t.data_ptr() % 16 == 0):
+            return t
+        buf = torch.zeros((t.shape[0], (kd + 3) // 4 * 4), dtype=torch.float32, device=dev)
+        buf[:, :kd].copy_(t)
+        return buf[:, :kd]
+    joint, lin_weight = tma_ready(joint), tma_ready(lin_weight)
+    vecs = [lin_bias, bn_scale, bn_shift]
+    if not all(t.dtype == torch.float32 and t.is_contiguous() and t.device == dev and t.numel() == HIDDEN for t in vecs):
+        raise ValueError("bias / bn_scale / bn_shift must be contiguous float32 [256] tensors on the joint matrix's device")
     if out is None:
         out = torch.empty((rows // 2 if pool else rows, HIDDEN), dtype=torch.float32, device=dev)
     st = stream if stream is not None else torch.cuda.current_stream(dev)
     p = lambda t: C.c_void_p(t.data_ptr())      # noqa: E731
     with torch.cuda.device(dev):
-        L.check(lib.s3_sign_head(p(joint), rows, kd, kd, p(lin_weight), kd, HIDDEN, p(lin_bias), p(bn_scale), p(bn_shift),
-                                 p(out), 1 if pool else 0, C.c_void_p(st.cuda_stream)), 's3_sign_head')
+        L.check(lib.s3_sign_head(p(joint), rows, kd, int(joint.stride(0)), p(lin_weight), int(lin_weight.stride(0)), HIDDEN,
+                                 p(lin_bias), p(bn_scale), p(bn_shift), p(out), 1 if pool else 0,
+                                 C.c_void_p(st.cuda_stream)), 's3_sign_head')
     return out

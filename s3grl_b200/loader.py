@@ -40,8 +40,8 @@ def load_collated(path, device=None):
 
 
 def joint_rows(xs, row_ptr, link_idx, rows_per_link=None, out=None, want_batch=True, stream=None):
-    """Joint matrix of the listed links: -> (joint [R_out, (K+1)*F'], batch int64 [R_out] or None,
-    ptr int64 [B+1] first row of every listed link).  `xs`: K+1 collated [R, F'] float32 CUDA tensors,
+    """Joint matrix of the listed links: -> (joint [R_out, (K+1)*F'] (a view whose row stride is padded to a multiple
+    of 4 floats), batch int64 [R_out] or None, ptr int64 [B+1] first row of every listed link).  `xs`: K+1 collated [R, F'] float32 CUDA tensors,
     `row_ptr` int64 [L+1], `link_idx` int64 [B] (device).  `rows_per_link`: pass 2 for the fixed-row
     flows (PoS, SoP) to skip the scan and the host sync."""
     lib = L.lib()
@@ -63,20 +63,23 @@ def joint_rows(xs, row_ptr, link_idx, rows_per_link=None, out=None, want_batch=T
         ptr = torch.zeros(B + 1, dtype=torch.int64, device=dev)
         torch.cumsum(counts, 0, out=ptr[1:])
         R, optr = int(ptr[-1]), ptr        # host sync: data-dependent row count
+    kd = nops * F1
+    ld = (kd + 3) // 4 * 4          # 16-byte row stride: what TMA (the fused scoring head) needs
     if out is None:
-        out = torch.empty((R, nops * F1), dtype=torch.float32, device=dev)
-    elif out.shape[0] < R or out.shape[1] != nops * F1 or not out.is_contiguous():
-        raise ValueError("out must be a contiguous [>= R_out, (K+1)*F'] float32 tensor")
+        out = torch.empty((R, ld), dtype=torch.float32, device=dev)
+    elif out.dim() != 2 or out.shape[0] < R or out.shape[1] < kd or out.stride(1) != 1 or out.dtype != torch.float32:
+        raise ValueError("out must be a [>= R_out, >= (K+1)*F'] float32 tensor with unit column stride")
+    ld = int(out.stride(0))
     batch = torch.empty(R, dtype=torch.int64, device=dev) if want_batch else None
     st = stream if stream is not None else torch.cuda.current_stream(dev)
     ptrs = (C.c_void_p * nops)(*[x.data_ptr() for x in xs])
     with torch.cuda.device(dev):
         L.check(lib.s3_joint_rows(ptrs, nops, F1, F1, C.c_void_p(row_ptr.data_ptr()), C.c_void_p(link_idx.data_ptr()), B,
                                   C.c_void_p(optr.data_ptr()) if optr is not None else C.c_void_p(0),
-                                  int(rows_per_link or 0), C.c_void_p(out.data_ptr()), nops * F1,
+                                  int(rows_per_link or 0), C.c_void_p(out.data_ptr()), ld,
                                   C.c_void_p(batch.data_ptr()) if batch is not None else C.c_void_p(0),
                                   C.c_void_p(st.cuda_stream)), 's3_joint_rows')
-    return out[:R], batch, ptr
+    return out[:R, :kd], batch, ptr
 
 
 class JointLoader:
@@ -116,7 +119,7 @@ class JointLoader:
         perm = torch.randperm(n, device=self.dev, generator=self.gen) if self.shuffle else torch.arange(n, device=self.dev)
         K1, F1 = len(self.ds.xs), int(self.ds.xs[0].shape[1])
         if self.fixed and (self._epoch_buf is None or self._epoch_buf.shape[0] < n * self.fixed):
-            self._epoch_buf = torch.empty((n * self.fixed, K1 * F1), dtype=torch.float32, device=self.dev)
+            self._epoch_buf = torch.empty((n * self.fixed, (K1 * F1 + 3) // 4 * 4), dtype=torch.float32, device=self.dev)
         joint, _, ptr = joint_rows(self.ds.xs, self.row_ptr, perm, self.fixed, out=self._epoch_buf if self.fixed else None,
                                    want_batch=False)
         y = self.y[perm]

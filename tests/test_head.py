@@ -12,7 +12,8 @@ def _reference(joint, W, b, scale, shift):
     return (h[0::2] * h[1::2]).float()
 
 
-@pytest.mark.parametrize('rows,kd', [(256, 64), (128, 32), (1000, 2004), (2, 36), (130, 516), (4096, 2004), (33000, 1028)])
+@pytest.mark.parametrize('rows,kd', [(256, 64), (128, 32), (1000, 2004), (2, 36), (130, 516), (4096, 2004), (33000, 1028),
+                                     (600, 1542), (514, 7)])   # 1542 = (K+1) F' of BASELINE config 4: not a multiple of 4
 def test_sign_head_matches_torch(rows, kd):
     from s3grl_b200 import sign_head
     g = torch.Generator(device='cuda').manual_seed(rows + kd)
@@ -48,7 +49,8 @@ def test_sign_head_on_loader_batches_and_module_parameters():
     bn.eval()
     scale, shift = fold_batchnorm(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps)
     for batch in JointLoader(lst, 64, shuffle=True, seed=1):
-        got = sign_head(batch.joint.contiguous(), lin.weight.detach().contiguous(), lin.bias.detach(), scale, shift)
+        assert batch.joint.stride(0) % 4 == 0                         # padded by the loader: consumed in place
+        got = sign_head(batch.joint, lin.weight.detach(), lin.bias.detach(), scale, shift)
         with torch.no_grad():
             h = bn(torch.nn.functional.elu(lin(torch.cat([batch.x] + [batch[f'x{k}'] for k in (1, 2, 3)], -1))))
             center = batch.ptr[:-1]
@@ -78,4 +80,4 @@ def test_sign_head_rejects_bad_shapes():
     with pytest.raises(ValueError):
         sign_head(z((3, 8), device='cuda'), z((256, 8), device='cuda'), z(256, device='cuda'), z(256, device='cuda'), z(256, device='cuda'))
     with pytest.raises(ValueError):
-        sign_head(z((4, 6), device='cuda'), z((256, 6), device='cuda'), z(256, device='cuda'), z(256, device='cuda'), z(256, device='cuda'))
+        sign_head(z((4, 8), device='cuda'), z((256, 8), device='cuda'), z(255, device='cuda'), z(256, device='cuda'), z(256, device='cuda'))

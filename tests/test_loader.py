@@ -63,6 +63,7 @@ def test_joint_rows_matches_collate(fixed, L, F1, K):
     joint, batch, ptr = joint_rows(ds.xs, ds.row_ptr, torch.from_numpy(idx).cuda(), 2 if fixed else None)
     ref_joint, ref_batch, _ = _collate_like_pyg(ds, idx)
     assert np.array_equal(joint.cpu().numpy(), ref_joint)          # pure data movement: bit-exact
+    assert joint.stride(0) % 4 == 0 and joint.shape[1] == (K + 1) * F1
     assert np.array_equal(batch.cpu().numpy(), ref_batch)
     uq, first = np.unique(ref_batch, return_index=True)            # models.py:341 center_indices
     assert np.array_equal(ptr.cpu().numpy()[:-1], first) and int(ptr[-1]) == ref_joint.shape[0]
