@@ -216,7 +216,7 @@ int s3_joint_rows(const float* const* src, int32_t num_ops, int64_t num_cols, in
     s3::OutPtrs o;
     memset(&o, 0, sizeof(o));
     for (int k = 0; k < num_ops; ++k) {
-        if (!src[k]) return S3_ERR_INVALID_ARG;
+        if (!src[k] && num_links > 0) return S3_ERR_INVALID_ARG;
         o.p[k] = const_cast<float*>(src[k]);
     }
     cudaError_t e = s3::launch_joint_rows(o, num_ops, num_cols, ld_src, row_ptr, link_idx, num_links, out_row_ptr,

@@ -520,3 +520,24 @@ def test_union_chain_matches_work_item_path(N, E, F, h, K, L):
     for k in range(K + 1):                               # rows 0, 1 are produced by kernels 1 + 3 on both routes
         assert torch.equal(a.xs[k][rp], b.xs[k][rp]) and torch.equal(a.xs[k][rp + 1], b.xs[k][rp + 1])
     print(f"N={N}: max_n={a.stats['max_n']} rows={a.stats['rows']}")
+
+
+def test_empty_inputs_on_every_entry_point():
+    """Edge case: an empty link list (a split without negatives, an empty shard on a rank) goes through every flow."""
+    from s3grl_b200 import JointLoader, PrecomputedList, joint_rows, sign_head
+    c = Case('tiny_pos_h2')
+    g = DeviceGraph(c.A, c.X)
+    none = np.zeros((2, 0), dtype=np.int64)
+    F1 = c.X.shape[1] + 1
+    for flow, strat in (('PoS', None), ('PoS', 'intersection'), ('PoS', 'union'), ('SoP', None)):
+        res = precompute(g, none, 2, 3, flow, strat)
+        assert res.row_ptr.tolist() == [0] and all(x.shape == (0, F1) for x in res.xs) and len(res.xs) == 4
+    full = precompute_full(g, none, 2, 3, node_label='drnl')
+    assert full.row_ptr.tolist() == [0] and full.xs[0].shape == (0, F1) and full.node_id.numel() == 0
+    res = precompute(g, c.links[:, :5], 2, 3, 'PoS')
+    joint, batch, ptr = joint_rows(res.xs, res.row_ptr, torch.zeros(0, dtype=torch.int64, device='cuda'), 2)
+    assert joint.shape == (0, 4 * F1) and batch.numel() == 0 and ptr.tolist() == [0]
+    assert list(JointLoader(PrecomputedList([x[:0] for x in res.xs], res.row_ptr[:1], torch.zeros(0, dtype=torch.long)).to('cuda'), 8)) == []
+    z = torch.zeros
+    out = sign_head(z((0, 24), device='cuda'), z((256, 24), device='cuda'), z(256, device='cuda'), z(256, device='cuda'), z(256, device='cuda'))
+    assert out.shape == (0, 256)
