@@ -6,15 +6,18 @@
 // utils.py:211-236 (drnl_node_labeling) and tuned_SIGN.py:18-23 (TunedSIGN.__call__ = PyG SIGN:
 // unweighted adj_t, deg = row count, inf -> 0, x_k = adj_t @ x_{k-1}).
 //
-// This is north_star's kernel (2): a segmented, per-subgraph CSR SpMM applied K times. One CTA per
-// (record, chunk of 128 output columns): operator columns are independent, so a CTA carries its
-// column chunk through all K operators on its own and needs no grid-wide synchronisation.
-// x_{k-1} is read back from the operator matrix the same CTA has just written (L1/L2 resident; a
-// __syncthreads() orders the global writes within the CTA), one warp per subgraph row, lanes along
-// the columns: every neighbour costs four coalesced 128-byte loads per warp and the row reduction
-// stays in registers — no atomics, fixed summation order (slots ascending), results independent
-// of scheduling. The padded local CSR of the front kernel (S3_BATCH_STORE_ALL_ROWS) is consumed as
-// is: 32 slots per step, holes skipped through a ballot.
+// This is north_star's kernel (2): a segmented, per-subgraph CSR SpMM applied K times. One CTA (512 threads)
+// per (record, chunk of 128 output columns), the chunks of a record adjacent in a 1-D grid: operator columns are
+// independent, so a CTA carries its columns through all K operators on its own and needs no grid-wide
+// synchronisation. Per CTA the subgraph's compact CSR — row starts, (column, dis[column]) pairs, dis per row,
+// node ids, built from the front kernel's padded CSR (S3_BATCH_STORE_ALL_ROWS) by one block scan over its slots —
+// and x_{k-1} of the current 32 / 64 / 128 columns live in shared memory (112 KB, two CTAs per SM):
+//   * two x buffers (ping-pong) when they fit: the inner loop is LDS.64 (pair, broadcast) + LDS + FFMA per
+//     neighbour and global memory only sees the streaming stores of the results;
+//   * one buffer for larger subgraphs (n <= ~800): x_k is re-loaded from out[k] (coalesced, L2-hot) after a barrier;
+//   * read-back of x_{k-1} from out[k-1] through L2 for anything larger.
+// One warp per row in work-balanced contiguous row ranges, lanes along the columns, row reduction in registers — no
+// atomics, fixed summation order (slots ascending): results are independent of scheduling.
 //
 // Output rows of record r: [row_base + row_ptr[r], + n), local node j -> row j (canonical order:
 // src, dst, then ascending (hop, global id)). Column 0 is the labeling-trick value z_j.
