@@ -256,8 +256,11 @@ class _Call:
             if step >= 512 and pos + step < self.num_links:
                 pos += step
                 starts.append(pos)
-        while pos + self.batch_links < self.num_links:
-            pos += self.batch_links
+        rest = self.num_links - pos
+        nb = max(1, int(round(rest / self.batch_links)))     # even batches: no tiny tail batch (164 000 = 5 x 32 800)
+        size = (rest + nb - 1) // nb
+        while pos + size < self.num_links:
+            pos += size
             starts.append(pos)
         self.starts = starts + [self.num_links]
         self.num_batches = len(starts) if self.num_links else 0
