@@ -218,14 +218,42 @@ def run_reference_arm(args, w, rank, world):
 # clocks
 # ----------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons during the timed region.  NVML in a background thread (nvidia_ml_py) — an
+    `nvidia-smi -lms` child process was measured to stall host-synchronising flows (PoS Plus) by 30-100 ms per
+    query — with the nvidia-smi loop as the fallback when NVML bindings are missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.p = None
+        self.thread = None
+        self.samples = []
         if os.environ.get('S3GRL_BENCH_NO_CLOCKS'):
             return
+        try:
+            import threading
+            import pynvml
+            pynvml.nvmlInit()
+            idx = str(index)
+            h = pynvml.nvmlDeviceGetHandleByUUID(idx) if idx.startswith('GPU-') else pynvml.nvmlDeviceGetHandleByIndex(int(idx))
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.stop_flag = threading.Event()
+
+            def loop():
+                while not self.stop_flag.is_set():
+                    try:
+                        self.samples.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                             int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))))
+                    except Exception:
+                        pass
+                    self.stop_flag.wait(0.1)
+            self.pynvml = pynvml
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.p = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
                                        '-lms', '200', '-i', str(index)], stdout=subprocess.PIPE,
@@ -234,6 +262,18 @@ class ClockSampler:
             self.p = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=1.0)
+            nv = self.pynvml
+            names = [('hw_slowdown', nv.nvmlClocksEventReasonHwSlowdown), ('hw_thermal_slowdown', nv.nvmlClocksEventReasonHwThermalSlowdown),
+                     ('sw_thermal_slowdown', nv.nvmlClocksEventReasonSwThermalSlowdown), ('sw_power_cap', nv.nvmlClocksEventReasonSwPowerCap)]
+            sm = [s for s, _ in self.samples]
+            if not sm:
+                return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+            reasons = sorted({nm for _, r in self.samples for nm, bit in names if r & bit})
+            busy = [s for s in sm if s >= 0.5 * max(sm)]
+            return dict(sm_mhz=float(np.median(busy)), sm_max_mhz=self.mx, reasons=reasons, samples=len(sm), source="nvml")
         if self.p is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         time.sleep(0.15)
@@ -255,7 +295,7 @@ class ClockSampler:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
         busy = [s for s in sm if s >= 0.5 * max(sm)]
         return dict(sm_mhz=float(np.median(busy)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
-                    samples=len(sm))
+                    samples=len(sm), source="nvidia-smi")
 
 
 # ----------------------------------------------------------------------------------------
@@ -364,11 +404,14 @@ def main():
     vis = [v for v in os.environ.get('CUDA_VISIBLE_DEVICES', '').split(',') if v.strip()]
     clocks = ClockSampler(vis[local_rank] if local_rank < len(vis) else local_rank)
     res = None
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(args.warmup, 3)):     # same code path as the timed steps: per-kernel events, deferred validation
         del res
-        res = step()
-    if full:
-        res.xs = res.node_id = None
+        res = step([], defer=True)
+        res.finalize()
+    if not fixed:
+        res.xs = None
+        if full:
+            res.node_id = None
     barrier()
     profile = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -381,8 +424,13 @@ def main():
     pending = []
     for i in range(args.steps):
         res = step(profile, defer=True)     # K steps are queued back to back ...
-        if full:
-            res.xs = res.node_id = None     # 9 GB per step: hand the rows back to the allocator
+        if not fixed:
+            # flows whose outputs are allocated inside the call (data-dependent row counts): hand the rows back to
+            # the allocator before the next step, as a caller that consumes each result would (else every step
+            # pays fresh cudaMallocs of several GB while the GPU idles)
+            res.xs = None
+            if full:
+                res.node_id = None
         pending.append(res)
         step_events[i + 1].record()
         launches += res.stats['launches']               # kernels of libs3grl_b200.so only (not the L2 flush fill)
@@ -404,6 +452,9 @@ def main():
     for stage, bi, a, b in profile:
         stage_ms.setdefault(stage, []).append(a.elapsed_time(b))
     nb = res.stats['batches']
+    if os.environ.get('S3GRL_BENCH_DEBUG'):
+        for stage, v in stage_ms.items():
+            print(stage, [round(t, 2) for t in v[:2 * nb]], file=sys.stderr)
     hot = 'sign_full' if full else 'gather'
     gather_ms = float(np.sum(stage_ms.get(hot, [0.0])))
     gather_launches = len(stage_ms.get(hot, []))

@@ -27,6 +27,7 @@
 namespace s3 {
 namespace {
 
+constexpr int kDiffLanes = 4;  // lanes per row (rows of the reference's graphs are short: 4 leave fewer lanes idle than 8)
 constexpr int kZCap = 4096;  // floats per shared z buffer (2 buffers: 32 KB): n <= 2048 with 2 rows, 512 with 8
 
 struct DiffuseParams {
@@ -43,8 +44,8 @@ template <int SC>
 __global__ void __launch_bounds__(kDiffuseThreads) diffuse_kernel(DiffuseParams p) {
     __shared__ float s_z[2][kZCap];
     const int tid = threadIdx.x, T = kDiffuseThreads;
-    const int l8 = tid & 7, grp = tid >> 3;
-    constexpr int NG = kDiffuseThreads / 8;
+    const int l8 = tid & (kDiffLanes - 1), grp = tid / kDiffLanes;  // lane group of a row
+    constexpr int NG = kDiffuseThreads / kDiffLanes;
     const int64_t item = blockIdx.x;
     const int64_t rec = p.item_rec ? p.item_rec[item] : item;
     const int32_t* cnt = p.cnt + rec * S3_NCNT;
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(kDiffuseThreads) diffuse_kernel(DiffuseParams 
             float t[SC];
 #pragma unroll
             for (int c = 0; c < SC; ++c) t[c] = 0.0f;
-            for (int e = e0 + l8; e < e1; e += 8) {
+            for (int e = e0 + l8; e < e1; e += kDiffLanes) {
                 const int i = lcol[e];  // -1: neighbour outside the subgraph / masked target link
                 if (i >= 0) {
 #pragma unroll
@@ -145,9 +146,8 @@ __global__ void __launch_bounds__(kDiffuseThreads) diffuse_kernel(DiffuseParams 
             }
 #pragma unroll
             for (int c = 0; c < SC; ++c) {
-                t[c] += __shfl_xor_sync(0xffffffffu, t[c], 4);
-                t[c] += __shfl_xor_sync(0xffffffffu, t[c], 2);
-                t[c] += __shfl_xor_sync(0xffffffffu, t[c], 1);
+#pragma unroll
+                for (int d = kDiffLanes / 2; d > 0; d >>= 1) t[c] += __shfl_xor_sync(0xffffffffu, t[c], d);
             }
             if (valid && l8 == 0) {
                 int deg = rowlen[j];

@@ -59,6 +59,8 @@ struct ExtractParams {
 };
 
 constexpr int kStreamLanes = 4;  // lanes per streamed (hop-K) row
+constexpr int kBfsLanes = 4;     // lanes per frontier node in the BFS expansion
+constexpr int kSweepLanes = 4;   // lanes per stored row in the diffusion sweeps
 constexpr int kRowCap = 1536;  // rows whose (start, adjacency offset) are cached in shared memory
 constexpr int kZCap = 1024;    // floats per shared z buffer
 
@@ -109,6 +111,10 @@ __global__ void __launch_bounds__(kExtractThreads, 5) front_kernel(ExtractParams
     const int lane = tid & 31, l8 = tid & 7, grp = tid >> 3;  // 8-lane groups
     constexpr int NG = kExtractThreads / 8;
     // streamed hop-K rows are mostly low-degree: narrower lane groups leave fewer lanes idle
+    constexpr int NGW = kExtractThreads / kSweepLanes;
+    const int lw = tid & (kSweepLanes - 1), grpw = tid / kSweepLanes;
+    constexpr int NGB = kExtractThreads / kBfsLanes;
+    const int lb = tid & (kBfsLanes - 1), grpb = tid / kBfsLanes;
     constexpr int NGS = kExtractThreads / kStreamLanes;
     const int ls = tid & (kStreamLanes - 1), grps = tid / kStreamLanes;
     const int NW = (K + 1) * SC, NWP = (NW + 3) & ~3;
@@ -174,9 +180,9 @@ __global__ void __launch_bounds__(kExtractThreads, 5) front_kernel(ExtractParams
         for (int l = 0; l < h; ++l) {
             uint32_t* cur = Lb + (size_t)l * W;
             // frontier = slab_nodes[flo, n): one 8-lane group per node, 32 B of column ids per step
-            for (int j = flo + grp; j < n; j += NG) {
+            for (int j = flo + grpb; j < n; j += NGB) {
                 const int64_t e0 = slab_estart[j], e1 = e0 + slab_deg[j];
-                for (int64_t e = e0 + l8; e < e1; e += 8) {
+                for (int64_t e = e0 + lb; e < e1; e += kBfsLanes) {
                     const int c = p.indices[e];
                     if (!test_bit(V, c)) atomicOr(&cur[c >> 5], 1u << (c & 31));
                 }
@@ -421,8 +427,8 @@ __global__ void __launch_bounds__(kExtractThreads, 5) front_kernel(ExtractParams
             for (int k = 1; k <= K; ++k) {
                 // stored rows reached by a k-step walk
                 const int nk = min(s_hop_end[min(k, S3_MAX_HOPS + 1)], n_store);
-                for (int jb0 = 0; jb0 < nk; jb0 += NG) {
-                    const int j = jb0 + grp;
+                for (int jb0 = 0; jb0 < nk; jb0 += NGW) {
+                    const int j = jb0 + grpw;
                     const bool valid = j < nk;
                     int e0 = 0, e1 = 0;
                     if (valid) {
@@ -432,7 +438,7 @@ __global__ void __launch_bounds__(kExtractThreads, 5) front_kernel(ExtractParams
                     float t[SC];
 #pragma unroll
                     for (int c = 0; c < SC; ++c) t[c] = 0.0f;
-                    for (int e = e0 + l8; e < e1; e += 8) {
+                    for (int e = e0 + lw; e < e1; e += kSweepLanes) {
                         const int i = lcol[e];  // -1: hole; >= nz: z is an exact zero there
                         if (i >= 0 && i < nz) {
 #pragma unroll
@@ -441,11 +447,10 @@ __global__ void __launch_bounds__(kExtractThreads, 5) front_kernel(ExtractParams
                     }
 #pragma unroll
                     for (int c = 0; c < SC; ++c) {
-                        t[c] += __shfl_xor_sync(0xffffffffu, t[c], 4);
-                        t[c] += __shfl_xor_sync(0xffffffffu, t[c], 2);
-                        t[c] += __shfl_xor_sync(0xffffffffu, t[c], 1);
+#pragma unroll
+                        for (int d = kSweepLanes / 2; d > 0; d >>= 1) t[c] += __shfl_xor_sync(0xffffffffu, t[c], d);
                     }
-                    if (valid && l8 == 0) {
+                    if (valid && lw == 0) {
                         const int deg = pos_flow ? rowlen[j] : slab_deg[j];
                         const float dis = deg > 0 ? 1.0f / sqrtf((float)deg) : 0.0f;
 #pragma unroll
