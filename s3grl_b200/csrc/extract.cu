@@ -108,8 +108,7 @@ __global__ void __launch_bounds__(kExtractThreads, 5) front_kernel(ExtractParams
     uint32_t* slab_estart = reinterpret_cast<uint32_t*>(slab_deg + p.num_nodes);
     int32_t* slab_rp = slab_deg + 2 * p.num_nodes;  // [N + 1]
     const bool pos_flow = p.flow == S3_FLOW_POS;
-    const int lane = tid & 31, l8 = tid & 7, grp = tid >> 3;  // 8-lane groups
-    constexpr int NG = kExtractThreads / 8;
+    const int lane = tid & 31;
     // streamed hop-K rows are mostly low-degree: narrower lane groups leave fewer lanes idle
     constexpr int NGW = kExtractThreads / kSweepLanes;
     const int lw = tid & (kSweepLanes - 1), grpw = tid / kSweepLanes;

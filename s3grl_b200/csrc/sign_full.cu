@@ -297,8 +297,7 @@ __global__ void __launch_bounds__(kFullThreads) sign_full_kernel(FullParams p) {
     extern __shared__ __align__(16) float s_dyn[];
     __shared__ int s_flag;
     __shared__ int s_scan[33];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NWARP = kFullThreads / 32;
+    const int tid = threadIdx.x;
     // 1-D grid, column chunks of a record adjacent: they run at the same time, so the cache lines they
     // share at chunk boundaries are completed in L2 and the record's X rows / CSR are fetched once
     const int ridx = blockIdx.x / p.chunks, chunk = blockIdx.x - ridx * p.chunks;
