@@ -353,6 +353,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
+        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':     # keeps stdout to the one JSON line
+            os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=dev)
 
     def barrier():
@@ -385,15 +387,15 @@ def main():
         cpu = dict(value=cols.size / dt, unit=UNIT, cores=1, kind="port",
                    sample=f"{cols.size} links sampled uniformly (seed 123), one pass, {dt:.1f} s; single-process oracle port")
         del A_host, X_host
-    full = w.get('full')
-    fixed = w['strategy'] is None and not full
+    full_flow = w.get('full')
+    fixed = w['strategy'] is None and not full_flow
     out = [torch.empty((2 * Lk, F + 1), dtype=torch.float32, device=dev) for _ in range(K + 1)] if fixed else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def step(profile=None, defer=False):
         flush.zero_()               # L2 flush between steps
-        if full:
-            return precompute_full(g, links_dev, w['num_hops'], K, node_label=full, batch_records=args.batch_records,
+        if full_flow:
+            return precompute_full(g, links_dev, w['num_hops'], K, node_label=full_flow, batch_records=args.batch_records,
                                    profile=profile)
         return precompute(g, links_dev, w['num_hops'], K, w['flow'], w['strategy'],
                           batch_records=args.batch_records, out=out, profile=profile, overlap=args.overlap,
@@ -410,7 +412,7 @@ def main():
         res.finalize()
     if not fixed:
         res.xs = None
-        if full:
+        if full_flow:
             res.node_id = None
     barrier()
     profile = []
@@ -429,7 +431,7 @@ def main():
             # the allocator before the next step, as a caller that consumes each result would (else every step
             # pays fresh cudaMallocs of several GB while the GPU idles)
             res.xs = None
-            if full:
+            if full_flow:
                 res.node_id = None
         pending.append(res)
         step_events[i + 1].record()
@@ -455,7 +457,7 @@ def main():
     if os.environ.get('S3GRL_BENCH_DEBUG'):
         for stage, v in stage_ms.items():
             print(stage, [round(t, 2) for t in v[:2 * nb]], file=sys.stderr)
-    hot = 'sign_full' if full else 'gather'
+    hot = 'sign_full' if full_flow else 'gather'
     gather_ms = float(np.sum(stage_ms.get(hot, [0.0])))
     gather_launches = len(stage_ms.get(hot, []))
     st = res.stats
@@ -474,7 +476,7 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(args.workload)
     except Exception:
         pass
-    roofline = dict(bound="hbm", kernel="sign_full_kernel" if full else ("gather_kernel<8,3>" if F > 1024 else "gather_kernel"), achieved=achieved, peak=peak,
+    roofline = dict(bound="hbm", kernel="sign_full_kernel" if full_flow else ("gather_kernel<8,3>" if F > 1024 else "gather_kernel"), achieved=achieved, peak=peak,
                     unit="GB/s", frac=achieved / peak, traffic=traffic, peak_source=peak_src,
                     bytes_per_launch=gather_bytes_step / max(nb, 1), launches_timed=gather_launches,
                     avg_launch_ms=gather_ms / max(gather_launches, 1),
@@ -510,7 +512,7 @@ def main():
         from s3grl_b200 import extract_enclosing_subgraphs
         x_host = torch.from_numpy(w['X']).pin_memory()
         link_index = torch.from_numpy(np.ascontiguousarray(links_host)).pin_memory()
-        sign_kwargs = dict(sign_k=K, use_feature=True, sign_type=w['flow'], optimize_sign=not full,
+        sign_kwargs = dict(sign_k=K, use_feature=True, sign_type=w['flow'], optimize_sign=not full_flow,
                            k_heuristic=0 if w['strategy'] is None else 1, k_node_set_strategy=w['strategy'])
         os.environ['S3GRL_DEVICE'] = str(dev)
         os.environ['S3GRL_OUTPUT_DEVICE'] = 'cpu'
@@ -520,7 +522,7 @@ def main():
         def e2e_step():
             tuned_sign._graph_cache.clear()       # the graph upload is part of every step
             rw_kwargs = dict(rw_m=w['walk']['m'], rw_M=w['walk']['M'], seed=w['walk']['seed'], sign=True) if w.get('walk') else None
-            lst = extract_enclosing_subgraphs(link_index, w['A'], x_host, 1, w['num_hops'], full or 'zo', 1.0, None, False,
+            lst = extract_enclosing_subgraphs(link_index, w['A'], x_host, 1, w['num_hops'], full_flow or 'zo', 1.0, None, False,
                                               None, rw_kwargs, sign_kwargs, powers_of_A=[] if w['flow'] == 'PoS' else [None] * K,
                                               data=None)
             d2h = sum(x.numel() * 4 for x in lst.xs) + lst.row_ptr.numel() * 8
