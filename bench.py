@@ -353,9 +353,19 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
-        if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':     # keeps stdout to the one JSON line
-            os.environ['NCCL_DEBUG'] = 'WARN'
-        dist.init_process_group('nccl', device_id=dev)
+        # NCCL prints its version banner on stdout when the box exports NCCL_DEBUG=VERSION: send fd 1 to stderr while
+        # the communicator comes up, so that stdout carries the one JSON line and nothing else
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     def barrier():
         if world > 1:
