@@ -74,6 +74,36 @@ def test_argument_validation_without_gpu(lib):
     assert lib.s3_extract(ctypes.byref(g), ctypes.byref(b), None) == L.S3_ERR_INVALID_ARG      # too many hops
 
 
+def test_argument_validation_of_the_wider_entry_points(lib):
+    """Invalid arguments are rejected before anything is launched (no GPU needed): loader, scoring head, non-optimised
+    flow, union chain."""
+    P = ctypes.c_void_p
+    g = L.Graph(16, 16, 16, 10, 4, 4, 20, 5)
+    b = L.Batch()
+    b.flow, b.strategy, b.sign_k, b.num_hops = L.FLOW_POS, L.STRATEGY_NONE, 3, 2
+    out = (ctypes.c_void_p * 4)(16, 16, 16, 16)
+    # s3_sign_full: unknown label -> NotImplementedError at the Python level; batch without S3_BATCH_STORE_ALL_ROWS -> invalid
+    assert lib.s3_sign_full(ctypes.byref(g), ctypes.byref(b), 0, 9, out, 5, 0, None, None) == L.S3_ERR_NOT_IMPLEMENTED
+    assert lib.s3_sign_full(ctypes.byref(g), ctypes.byref(b), 0, L.LABEL_DRNL, out, 5, 0, None, None) == L.S3_ERR_INVALID_ARG
+    assert lib.s3_plan_full(ctypes.byref(b), None) == L.S3_ERR_INVALID_ARG                      # no row_ptr
+    # s3_ccn_chain serves the union strategy only
+    assert lib.s3_ccn_chain(ctypes.byref(g), ctypes.byref(b), 0, out, 5, 0, None) == L.S3_ERR_NOT_IMPLEMENTED
+    # s3_joint_rows: operator count, leading dimensions
+    assert lib.s3_joint_rows(out, 0, 5, 5, P(16), P(16), 1, None, 2, P(16), 20, None, None) == L.S3_ERR_INVALID_ARG
+    assert lib.s3_joint_rows(out, 4, 5, 4, P(16), P(16), 1, None, 2, P(16), 20, None, None) == L.S3_ERR_INVALID_ARG   # ld_src < cols
+    assert lib.s3_joint_rows(out, 4, 5, 5, P(16), P(16), 1, None, 2, P(16), 19, None, None) == L.S3_ERR_INVALID_ARG   # ld_dst < 4*5
+    assert lib.s3_joint_rows(out, 4, 5, 5, P(16), P(16), 1, None, 0, P(16), 20, None, None) == L.S3_ERR_INVALID_ARG   # no row counts
+    assert lib.s3_joint_rows(out, 4, 5, 5, None, None, 0, None, 2, None, 20, None, None) == L.S3_OK                    # empty: nothing to do
+    # s3_sign_head: hidden size, parity of rows when pooling, 16-byte row strides (TMA)
+    head = lambda rows, kd, ld, ldw, hidden, pool: lib.s3_sign_head(P(16), rows, kd, ld, P(16), ldw, hidden, P(16), P(16), P(16),  # noqa: E731
+                                                                     P(16), pool, None)
+    assert head(4, 8, 8, 8, 128, 1) == L.S3_ERR_UNSUPPORTED
+    assert head(3, 8, 8, 8, 256, 1) == L.S3_ERR_INVALID_ARG
+    assert head(4, 8, 6, 8, 256, 1) == L.S3_ERR_INVALID_ARG
+    assert head(4, 6, 6, 8, 256, 1) == L.S3_ERR_INVALID_ARG
+    assert head(0, 8, 8, 8, 256, 1) == L.S3_OK
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(L, '_lib', None)
     monkeypatch.setattr(L, 'LIB_PATH', str(tmp_path / 'nope.so'))
