@@ -40,7 +40,10 @@ def test_constants_match_header():
              'S3_STRATEGY_INTERSECTION': L.STRATEGY_INTERSECTION, 'S3_MAX_HOPS': L.MAX_HOPS, 'S3_MAX_K': L.MAX_K,
              'S3_NOFF': L.NOFF, 'S3_NCNT': L.NCNT, 'S3_NCTR': L.NCTR, 'S3_OFF_F32': L.OFF_F32,
              'S3_CNT_HOP0': L.CNT_HOP0, 'S3_CNT_PARTNER': L.CNT_PARTNER, 'S3_CTR_SUM_D': L.CTR_SUM_D,
-             'S3_CTR_ITEMS': L.CTR_ITEMS, 'S3_REC_BAD_LINK': L.REC_BAD_LINK, 'S3_ERR_NOT_IMPLEMENTED': L.S3_ERR_NOT_IMPLEMENTED}
+             'S3_CTR_ITEMS': L.CTR_ITEMS, 'S3_REC_BAD_LINK': L.REC_BAD_LINK, 'S3_ERR_NOT_IMPLEMENTED': L.S3_ERR_NOT_IMPLEMENTED,
+             'S3_BATCH_STORE_ALL_ROWS': L.BATCH_STORE_ALL_ROWS, 'S3_BATCH_FORCE_SORTED_TIER': L.BATCH_FORCE_SORTED_TIER,
+             'S3_BATCH_CCN_CHAIN': L.BATCH_CCN_CHAIN, 'S3_LABEL_ZO': L.LABEL_ZO, 'S3_LABEL_HOP': L.LABEL_HOP,
+             'S3_LABEL_DRNL': L.LABEL_DRNL, 'S3_LABEL_DEGREE': L.LABEL_DEGREE, 'S3_LABEL_ZERO': L.LABEL_ZERO}
     for k, v in pairs.items():
         assert int(defs[k]) == v, k
     assert ctypes.sizeof(L.Graph) == 64 and ctypes.sizeof(L.Batch) == 160
