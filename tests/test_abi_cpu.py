@@ -121,3 +121,22 @@ def test_product_package_does_not_import_oracle():
             if f.endswith('.py'):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle', src, flags=re.M), f
+
+
+def test_library_is_sm100a_only_and_the_head_uses_tcgen05(lib, tmp_path):
+    """Static evidence from the built binary (no GPU): every embedded cubin targets sm_100a, and the scoring head's SASS
+    holds the 5th-generation tensor-core / TMA / TMEM instructions (B200_PROFILING.md: UTCHMMA = tcgen05.mma,
+    UTMALDG = cp.async.bulk.tensor, LDTM = tcgen05.ld, UTCBAR = tcgen05.commit)."""
+    import shutil
+    import subprocess
+    if not shutil.which('cuobjdump'):
+        pytest.skip('cuobjdump not on PATH')
+    elfs = subprocess.run(['cuobjdump', '-lelf', L.LIB_PATH], capture_output=True, text=True).stdout
+    names = re.findall(r'ELF file\s+\d+:\s+(\S+)', elfs)
+    assert names and all(n.endswith('.sm_100a.cubin') for n in names), names
+    head = [n for n in names if n.startswith('head.')]
+    assert head, names
+    subprocess.run(['cuobjdump', '-xelf', head[0], L.LIB_PATH], cwd=tmp_path, check=True, capture_output=True)
+    sass = subprocess.run(['cuobjdump', '-sass', str(tmp_path / head[0])], capture_output=True, text=True).stdout
+    for mnemonic in ('UTCHMMA', 'UTMALDG.2D', 'LDTM', 'UTCBAR'):
+        assert mnemonic in sass, mnemonic
