@@ -91,3 +91,57 @@ def test_full_flow_label_columns_are_integers_and_drnl_is_symmetric_in_the_targe
     for i in range(6):
         ra, rb = slice(a['row_ptr'][i], a['row_ptr'][i + 1]), slice(b['row_ptr'][i], b['row_ptr'][i + 1])
         assert np.array_equal(a['node_id'][ra][2:], b['node_id'][rb][2:]) and np.array_equal(za[ra][2:], zb[rb][2:])
+
+
+def test_sop_is_linear_in_x_and_its_first_column_is_the_return_probability():
+    c = Case('usair_sop')
+    links = c.links[:, :10]
+    rng = np.random.default_rng(1)
+    X1, X2 = c.X.astype(np.float64), rng.random(c.X.shape)
+    powers = orc.sop_powers(c.A, c.K, np.float64)
+    a = orc.sop_precompute(links, c.A, X1, c.K, np.float64, powers)
+    b = orc.sop_precompute(links, c.A, X2, c.K, np.float64, powers)
+    s = orc.sop_precompute(links, c.A, X1 + 0.5 * X2, c.K, np.float64, powers)
+    for k in range(c.K + 1):
+        np.testing.assert_allclose(s['xs'][k][:, 1:], a['xs'][k][:, 1:] + 0.5 * b['xs'][k][:, 1:], rtol=1e-10, atol=1e-12)
+        np.testing.assert_array_equal(a['xs'][k][:, 0], b['xs'][k][:, 0])
+    assert np.all(a['xs'][0][:, 0] == 1.0)                                   # tuned_SIGN.py:119-124
+    for i in range(links.shape[1]):                                          # x_k[., 0] = A_hat^k[u, u] (tuned_SIGN.py:106-113)
+        for k in range(1, c.K + 1):
+            assert a['xs'][k][2 * i, 0] == powers[k - 1][links[0, i], links[0, i]]
+            assert a['xs'][k][2 * i + 1, 0] == powers[k - 1][links[1, i], links[1, i]]
+    assert np.all(a['xs'][1][:, 0] == 0.0)                                   # no self loops: no 1-step return
+
+
+def test_hybrid_is_pos_followed_by_sop_operators_two_to_k():
+    c = Case('cora_pos')
+    links = c.links[:, :8]
+    h = orc.hybrid_precompute(links, c.num_hops, c.A, c.X, c.K)
+    p = orc.pos_precompute(links, c.num_hops, c.A, c.X, c.K)
+    s = orc.sop_precompute(links, c.A, c.X, c.K)
+    assert len(h['xs']) == 2 * c.K
+    for k in range(c.K + 1):
+        assert np.array_equal(h['xs'][k], p['xs'][k])
+    for j, k in enumerate(range(2, c.K + 1)):
+        assert np.array_equal(h['xs'][c.K + 1 + j], s['xs'][k])
+
+
+def test_scaled_subgraph_is_a_subset_of_the_m_hop_ball():
+    """Walks of length m never leave the m-hop ball of their start: the ScaLed node set of (u, v) is a subset of the
+    m-hop enclosing subgraph's, and with exhaustive walk sets (= the whole ball) both flows coincide."""
+    c = Case('cora_scaled')
+    links = c.links[:, :10]
+    for i in range(links.shape[1]):
+        u, v = int(links[0, i]), int(links[1, i])
+        sc = orc.scaled_pos_link(u, v, c.sets, c.A, c.X, c.K)
+        ball, _, _, _ = orc.k_hop_subgraph(u, v, c.rw_m, c.A)
+        assert set(sc['nodes'].tolist()) <= set(ball.tolist())
+    import scipy.sparse.csgraph as csg
+    u, v = int(links[0, 0]), int(links[1, 0])
+    dist = csg.shortest_path(c.A, unweighted=True, indices=[u, v])
+    full_sets = {u: np.flatnonzero(dist[0] <= 1), v: np.flatnonzero(dist[1] <= 1)}
+    sc = orc.scaled_pos_link(u, v, full_sets, c.A, c.X, c.K)
+    bf = orc.pos_link(u, v, 1, c.A, c.X, c.K)
+    assert np.array_equal(np.sort(sc['nodes'][2:]), np.sort(bf['nodes'][2:]))
+    for k in range(c.K + 1):
+        assert_features_close(sc['xs'][k], bf['xs'][k], what=f'x{k}')
