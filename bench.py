@@ -13,14 +13,18 @@ reference sgrl_link_pred.py:193-204).  Prints ONE JSON line on rank 0.
                s3grl_b200.extract_enclosing_subgraphs(link_index, A, x, ...) with HOST inputs
                (SciPy CSR, CPU tensors) and HOST outputs: graph + link H2D and the D2H of all
                K+1 operator matrices are inside the timed region.
-* roofline   : dominant kernel (gather) — algorithmic bytes / CUDA-event time vs measured HBM peak.
+* roofline   : the kernel with the largest share of the step, plus every kernel of the path with its own
+               bytes / time / fraction and the measured L2-read and FP32 ceilings (roofline.kernels).
 * cpu_baseline / --impl reference : the oracle port (oracle/s3grl_oracle.py — the reference
                itself is Python and cannot travel to the GPU box) on all host cores.
 
-Multi-GPU (torchrun, one rank per GPU): weak scaling — every rank precomputes a full-size
-shard (the workload's link list in a rank-specific order) against its replica of the graph;
-no data-path collective. The NCCL allgather of the joint rows that training would need is
-timed separately and reported under "allgather".
+Multi-GPU (torchrun, one rank per GPU): STRONG scaling of the same step — the workload's link list is
+sharded cyclically over the ranks, the graph is replicated, and every rank stores its output rows straight
+into every rank's operator matrices over NVLink peer memory (s3_gather_peers: the all-gather of SURVEY.md
+§8e fused into kernel 3), so the timed region ends with the complete matrices on every GPU.  After the
+timed region every rank checks its copy against a single-GPU precompute of the whole list, bit for bit.
+The default run also measures the other BASELINE configs that are not the headline (PoS Plus union,
+R-MAT) with few steps and reports them under "configs".
 """
 import argparse
 import json
@@ -299,6 +303,311 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------
+# measured ceilings besides HBM: L2 -> SM read bandwidth and FP32 FMA rate (csrc/probe.cu)
+# ----------------------------------------------------------------------------------------
+def measure_ceilings(dev):
+    import ctypes as C
+    import torch
+    from s3grl_b200 import _lib as L
+    lib = L.lib()
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    buf = torch.rand(48 << 18, dtype=torch.float32, device=dev)        # 48 MB: stays in the 126 MB L2
+    sink = torch.zeros(4, dtype=torch.float32, device=dev)
+    out = {}
+    for name, call, work in (
+            ('l2_read_GBps', lambda it: lib.s3_probe_l2_read(C.c_void_p(buf.data_ptr()), buf.numel() * 4, it, C.c_void_p(sink.data_ptr()), sms * 8, st),
+             lambda it: buf.numel() * 4 * it / 1e9),
+            ('fp32_TFLOPs', lambda it: lib.s3_probe_fma(it * 64, C.c_void_p(sink.data_ptr()), sms * 8, st),
+             lambda it: 2.0 * sms * 8 * 256 * it * 64 * 128 / 1e12)):
+        L.check(call(2), name)
+        best = 0.0
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            L.check(call(20), name)
+            b.record()
+            b.synchronize()
+            best = max(best, work(20) / (a.elapsed_time(b) / 1e3))
+        out[name] = best
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# one workload on this process group -> the fields of its JSON record
+# ----------------------------------------------------------------------------------------
+def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings, cpu=None):
+    import torch
+    import torch.distributed as dist
+    from s3grl_b200 import DeviceGraph, algorithmic_bytes, precompute, precompute_full
+    from s3grl_b200 import tuned_sign
+    from s3grl_b200.parallel import PeerBuffers, precompute_exchange, shard_range
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    is_rmat = w.get('graph') is not None
+    links_all = w['links']                       # host [2, L]: the whole list of the workload
+    Lk = links_all.shape[1]
+    K = w['K']
+    g = w['graph'] if is_rmat else DeviceGraph(w['A'], w['X'], device=dev)
+    F = g.num_feat
+    full_flow = w.get('full')
+    fixed = w['strategy'] is None and not full_flow
+    exchange = world > 1 and fixed
+    a, b = (0, Lk) if (world == 1 or exchange) else shard_range(Lk, rank, world)
+    links_dev = (w['links_dev'] if is_rmat else torch.from_numpy(np.ascontiguousarray(links_all)).to(dev))[:, a:b].contiguous()
+    Lmine = b - a
+    buffers = PeerBuffers(Lk, F, K, dev) if exchange else None
+    out = ([torch.empty((2 * Lk, F + 1), dtype=torch.float32, device=dev) for _ in range(K + 1)]
+           if fixed and not exchange else None)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step(profile=None):
+        flush.zero_()               # L2 flush between steps
+        if full_flow:
+            return precompute_full(g, links_dev, w['num_hops'], K, node_label=full_flow, batch_records=args.batch_records,
+                                   profile=profile)
+        if exchange:
+            res, _ = precompute_exchange(g, links_dev, w['num_hops'], K, buffers, flow=w['flow'], defer=True,
+                                         batch_records=args.batch_records, profile=profile, overlap=args.overlap,
+                                         walk=w.get('walk'))
+            buffers.barrier()       # on the stream: every rank's rows of this step have landed everywhere
+            return res
+        return precompute(g, links_dev, w['num_hops'], K, w['flow'], w['strategy'], batch_records=args.batch_records, out=out,
+                          profile=profile, overlap=args.overlap, defer=fixed, walk=w.get('walk'), pair=not args.no_pair)
+
+    vis = [v for v in os.environ.get('CUDA_VISIBLE_DEVICES', '').split(',') if v.strip()]
+    local_rank = dev.index
+    clocks = ClockSampler(vis[local_rank] if local_rank < len(vis) else local_rank)
+    res = None
+    for _ in range(max(warmup, 3)):     # same code path as the timed steps: per-kernel events, deferred validation
+        del res
+        res = step([])
+        res.finalize()
+    if not fixed:
+        res.xs = None
+        if full_flow:
+            res.node_id = None
+    barrier()
+    profile = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    launches = 0
+    step_events = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    step_events[0].record()
+    pending = []
+    for i in range(steps):
+        res = step(profile)     # K steps are queued back to back ...
+        if not fixed:
+            # flows whose outputs are allocated inside the call (data-dependent row counts): hand the rows back to
+            # the allocator before the next step, as a caller that consumes each result would
+            res.xs = None
+            if full_flow:
+                res.node_id = None
+        pending.append(res)
+        step_events[i + 1].record()
+        launches += res.stats['launches']               # kernels of libs3grl_b200.so only (not the L2 flush fill)
+    for r in pending:                       # ... then synchronised and validated, inside the timed region
+        r.finalize()
+    host_enqueue_ms = res.stats.get('host_enqueue_ms')
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = Lk * steps / (ms_max / 1e3)          # whole job: the list is processed once per step by all ranks together
+
+    # ---- multi-GPU: every rank's matrices against a single-GPU precompute of the whole list ----
+    exch = None
+    if exchange:
+        check = precompute(g, links_dev, w['num_hops'], K, w['flow'], None, pair=False, walk=w.get('walk'))
+        same = torch.tensor([int(all(torch.equal(buffers.local[k], check.xs[k]) for k in range(K + 1)))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        rows_mine = 2 * (res.stats['links'])
+        nv = rows_mine * (K + 1) * (F + 1) * 4 * (world - 1)
+        exch = dict(kind="s3_gather_peers: kernel 3 stores every output row into all ranks' matrices (NVLink peer memory, "
+                         "CUDA IPC); the timed region ends with one 4-byte NCCL all-reduce per step as the barrier",
+                    equal_to_single_gpu_bitwise=bool(int(same)), nvlink_bytes_out_per_rank_per_step=int(nv),
+                    nvlink_GBps_out_per_rank=nv * steps / (ms_max / 1e3) / 1e9, nvlink_peak_GBps=770.0,
+                    nvlink_peak_source="B200_PROFILING.md: measured peer copy, per direction per GPU")
+        del check
+
+    # ---- per-kernel times from the events recorded on the launching stream during the timed steps ----
+    stage_ms = {}
+    for stage, bi, ea, eb in profile:
+        stage_ms.setdefault(stage, []).append(ea.elapsed_time(eb))
+    st = res.stats
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if 'hbm_gbs' in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    rows_written = st['rows'] if not exchange else 2 * st['links']      # rows this rank produced (paired links included)
+    names = dict(extract="front_sorted_kernel" if is_rmat else "front_kernel", gather="gather_kernel", diffuse="diffuse_kernel",
+                 gather_ccn="gather_kernel (CCN work items)", ccn_chain="ccn_chain_kernel", sign_full="sign_full_kernel")
+    # SURVEY 8d terms per kernel, over the records this rank actually extracted
+    alg = dict(extract=4 * st['sum_d'] + 8 * st['sum_n'],
+               gather=4 * F * st['sum_n'] + 4 * rows_written * (K + 1) * (F + 1),
+               sign_full=4 * F * st['sum_n'] + 4 * st['rows'] * (K + 1) * (F + 1))
+    bound_note = dict(extract="issue / latency bound integer work on shared-memory bitmaps (ncu: profiles/); its HBM fraction is "
+                              "low by nature" if not is_rmat else "latency bound sorted-set intersections over HBM-resident adjacency lists",
+                      gather="L2 -> SM bandwidth and FP32 issue when X is L2-resident (PubMed 39 MB), HBM otherwise",
+                      sign_full="HBM writes")
+    kernels = {}
+    for stage, v in stage_ms.items():
+        tot = float(np.sum(v))
+        k = dict(kernel=names.get(stage, stage), share_of_step=tot / ms, ms_per_step=tot / steps, launches_timed=len(v),
+                 avg_launch_ms=tot / len(v))
+        if stage in alg and tot > 0:
+            k['algorithmic_bytes_per_step'] = int(alg[stage])
+            k['achieved_GBps'] = alg[stage] * steps / (tot / 1e3) / 1e9
+            k['frac_of_hbm'] = k['achieved_GBps'] / peak
+            k['bound_by'] = bound_note.get(stage)
+        if stage == 'gather' and tot > 0 and ceilings:
+            # kernel 3 reads every feature row from L2 once per column pass and issues (K+1-kmin) * SC FMAs per float
+            hop = st.get('hop_nodes')
+            k['l2_read_ceiling_GBps'] = ceilings['l2_read_GBps']
+            k['frac_of_l2_read_ceiling'] = k['achieved_GBps'] / ceilings['l2_read_GBps']
+            if hop:
+                sc = 1 if w['flow'] == 'SoP' else 2
+                fma = sum(n * max(0, K + 1 - l) * sc for l, n in enumerate(hop)) * g.ldx
+                k['fp32_TFLOPs'] = 2.0 * fma * steps / (tot / 1e3) / 1e12
+                k['fp32_ceiling_TFLOPs'] = ceilings['fp32_TFLOPs']
+                k['frac_of_fp32_ceiling'] = k['fp32_TFLOPs'] / ceilings['fp32_TFLOPs']
+        kernels[stage] = k
+    dom = max(kernels, key=lambda s_: kernels[s_]['share_of_step']) if kernels else None
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r2_traffic.json')))
+        traffic = tj.get(wname, {}).get(dom)
+        traffic_src = tj.get('_source')
+    except Exception:
+        pass
+    path_bytes = algorithmic_bytes(st, F, K, per_link=True) if not exchange else None
+    if exchange:      # per-link figures of the whole list: sum over ranks
+        tt = torch.tensor([st['sum_n_links'] or st['sum_n'], st['sum_d_links'] or st['sum_d']], dtype=torch.int64, device=dev)
+        dist.all_reduce(tt)
+        path_bytes = 4 * int(tt[1]) + 8 * int(tt[0]) + 4 * F * int(tt[0]) + 4 * 2 * Lk * (K + 1) * (F + 1)
+    elif world > 1:
+        tt = torch.tensor([path_bytes], dtype=torch.int64, device=dev)
+        dist.all_reduce(tt)
+        path_bytes = int(tt[0])
+    d = kernels.get(dom, {})
+    roofline = dict(bound="hbm", kernel=d.get('kernel'), achieved=d.get('achieved_GBps', 0.0), peak=peak, unit="GB/s",
+                    frac=d.get('frac_of_hbm', 0.0), traffic=traffic, traffic_source=traffic_src, peak_source=peak_src,
+                    dominant_by="share of the step (CUDA events on the launching stream)",
+                    note=d.get('bound_by'),
+                    bytes_per_launch=d.get('algorithmic_bytes_per_step', 0) / max(st['batches'], 1),
+                    launches_timed=d.get('launches_timed'), avg_launch_ms=d.get('avg_launch_ms'),
+                    share_of_step={k_: v_['share_of_step'] for k_, v_ in kernels.items()},
+                    kernels=kernels,
+                    path=dict(achieved=path_bytes * steps / (ms_max / 1e3) / 1e9,
+                              frac=path_bytes * steps / (ms_max / 1e3) / 1e9 / (peak * world),
+                              bytes_per_link=path_bytes / Lk, peak=peak * world,
+                              note="whole path: SURVEY 8d bytes per LINK (a paired link counts its own bytes although it "
+                                   "is served by its partner's record) over the full step time, against N x the HBM peak"))
+    if st.get('mirrors') is not None and fixed:
+        roofline['path']['links_served_by_pairing_this_rank'] = st['mirrors']
+
+    # ---- end to end through the reference-facing call, host buffers in, host buffers out ----
+    e2e = None
+    if want_e2e and not is_rmat:
+        from s3grl_b200 import extract_enclosing_subgraphs
+        sa, sb = shard_range(Lk, rank, world)          # every rank: its contiguous shard, to its own host memory
+        x_host = torch.from_numpy(w['X']).pin_memory()
+        link_index = torch.from_numpy(np.ascontiguousarray(links_all[:, sa:sb])).pin_memory()
+        sign_kwargs = dict(sign_k=K, use_feature=True, sign_type=w['flow'], optimize_sign=not full_flow,
+                           k_heuristic=0 if w['strategy'] is None else 1, k_node_set_strategy=w['strategy'])
+        del out, res, pending, r
+        if buffers is not None:
+            buffers.close()
+            buffers = None
+        torch.cuda.empty_cache()
+
+        def e2e_step():
+            tuned_sign._graph_cache.clear()       # the graph upload is part of every step
+            rw_kwargs = dict(rw_m=w['walk']['m'], rw_M=w['walk']['M'], seed=w['walk']['seed'], sign=True) if w.get('walk') else None
+            lst = extract_enclosing_subgraphs(link_index, w['A'], x_host, 1, w['num_hops'], full_flow or 'zo', 1.0, None, False,
+                                              None, rw_kwargs, sign_kwargs, powers_of_A=[] if w['flow'] == 'PoS' else [None] * K,
+                                              data=None, device=dev, output_device='cpu')
+            d2h = sum(x.numel() * 4 for x in lst.xs) + lst.row_ptr.numel() * 8
+            chk = float(lst.xs[-1][0, 0]) if lst.xs[-1].numel() else 0.0        # touch the host result
+            return d2h, chk
+        for _ in range(2):
+            e2e_step()
+        n_e2e = args.e2e_steps or max(2, min(steps, 10))
+        import gc
+        gc.collect()                 # start the timed region with a clean heap (host hiccups show up in e2e.step_ms)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_ms = []
+        for _ in range(n_e2e):
+            ts = time.perf_counter()
+            d2h, _ = e2e_step()
+            e2e_ms.append(round(1000 * (time.perf_counter() - ts), 2))
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        h2d = g.h2d_bytes + link_index.numel() * 8
+        e2e = dict(value=Lk * n_e2e / float(tt.item()), unit=UNIT, h2d_bytes_per_step=int(h2d),
+                   d2h_bytes_per_step=int(d2h), steps=n_e2e, ms_per_step=1000 * float(tt.item()) / n_e2e, step_ms=e2e_ms,
+                   api="s3grl_b200.extract_enclosing_subgraphs(link_index, A, x, y, num_hops, ..., sign_kwargs, output_device='cpu') "
+                       "-> pinned host tensors" + ("" if world == 1 else f"; every rank uploads the graph, takes the contiguous shard "
+                       f"rank/{world} of the link list and returns its rows to its own host (bytes are per rank)"))
+    if buffers is not None:
+        buffers.close()
+
+    par = ("1 GPU" if world == 1 else
+           (f"strong scaling: link list sharded cyclically x{world}, graph replicated, all-gather of the operator rows fused "
+            f"into kernel 3 (NVLink peer stores) inside the timed region" if exchange else
+            f"strong scaling: link list sharded in contiguous blocks x{world}, graph replicated, rows stay on their rank "
+            f"(data-dependent row counts: no exchange step)"))
+    line = dict(metric=metric_name(wname), value=value, unit=UNIT, n_gpus=world, steps=steps, warmup=max(warmup, 3),
+                ms_per_step=ms_max / steps, higher_is_better=True, scaling="strong", vs_baseline=None,
+                dtype="f32", data="synthetic",
+                config=dict(workload=w['desc'], links_per_step=Lk, links_per_step_this_rank=st['links'],
+                            batch_records=args.batch_records or "auto (32768 for fixed-row flows)",
+                            l2="flushed between steps (256 MiB memset); PubMed's X (39 MB) is L2-resident within a step by "
+                               "nature of the workload, the R-MAT X (5 GB) is not",
+                            pairing=("on: links over the same unordered node pair share one record (both directions of a "
+                                     "training edge); bit-identical to computing each" if fixed and not args.no_pair and not is_rmat
+                                     else "off"),
+                            parallelism=par),
+                clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu,
+                host_enqueue_ms_per_step=host_enqueue_ms,
+                step_ms=[round(step_events[i].elapsed_time(step_events[i + 1]), 3) for i in range(steps)])
+    if exch:
+        line['exchange'] = exch
+    return line
+
+
+def rmat_cpu_baseline(w, g, K):
+    """single-process oracle on a small sample (the fork pool cannot be used once CUDA is up)"""
+    import scipy.sparse as ssp
+    from oracle import s3grl_oracle as orc
+    F, Lk = g.num_feat, w['links'].shape[1]
+    A_host = ssp.csr_matrix((np.ones(g.nnz, np.int8), g.indices.cpu().numpy(), g.indptr.cpu().numpy()),
+                            shape=(g.num_nodes, g.num_nodes))
+    X_host = g.x[:, :F].cpu().numpy()
+    cols = np.random.default_rng(123).choice(Lk, min(Lk, 200), replace=False)
+    t0 = time.perf_counter()
+    orc.pos_precompute(w['links'][:, cols], 1, A_host, X_host, K)
+    dt = time.perf_counter() - t0
+    return dict(value=cols.size / dt, unit=UNIT, cores=1, kind="port",
+                sample=f"{cols.size} links sampled uniformly (seed 123), one pass, {dt:.1f} s; single-process oracle port")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -306,17 +615,20 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='pubmed_pos')
+    ap.add_argument('--configs', default='auto', help="'auto': with the default workload also measure pubmed_posplus_union and rmat "
+                    "(few steps) and report them under \"configs\"; 'none'; or a comma-separated list of workloads")
     ap.add_argument('--batch-records', type=int, default=None)
     ap.add_argument('--links', type=int, default=None, help='use only the first N links of the workload (profiling runs)')
     ap.add_argument('--cpu-links-per-core', type=int, default=400)
     ap.add_argument('--e2e-steps', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-pair', action='store_true', help='switch link pairing off (every link extracts its own subgraph)')
     ap.add_argument('--rmat-nodes', type=int, default=10_000_000)
     ap.add_argument('--rmat-edges', type=int, default=200_000_000)
     ap.add_argument('--rmat-links', type=int, default=4_000_000)
     ap.add_argument('--rmat-degree-cap', type=int, default=512)
-    ap.add_argument('--overlap', action='store_true', help='two-stream front/back overlap (measured slower on PubMed: L2 contention)')
+    ap.add_argument('--overlap', action='store_true', help='two-stream schedule: front kernel of batch i+1 beside kernel 3 of batch i')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -347,8 +659,6 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from s3grl_b200 import DeviceGraph, algorithmic_bytes, precompute, precompute_full
-    from s3grl_b200 import tuned_sign
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
@@ -367,213 +677,44 @@ def main():
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
+    ceilings = measure_ceilings(dev)
     if is_rmat:
         w = build_rmat_workload(args, dev)
-        args.no_e2e = True          # the host-facing call would re-upload a 7 GB graph every step
-    links_host = w['links']
-    if world > 1:   # weak scaling: same link set per rank, rank-specific order
-        links_host = links_host[:, np.random.default_rng(1000 + rank).permutation(links_host.shape[1])]
-    Lk = links_host.shape[1]
-    K = w['K']
-    g = w['graph'] if is_rmat else DeviceGraph(w['A'], w['X'], device=dev)
-    F = g.num_feat
-    links_dev = torch.from_numpy(np.ascontiguousarray(links_host)).to(dev)
-    if is_rmat and not args.no_cpu_baseline and rank == 0 and world == 1:
-        # single-process oracle on a small sample (the fork pool cannot be used once CUDA is up)
-        import scipy.sparse as ssp
-        from oracle import s3grl_oracle as orc
-        A_host = ssp.csr_matrix((np.ones(g.nnz, np.int8), g.indices.cpu().numpy(), g.indptr.cpu().numpy()),
-                                shape=(g.num_nodes, g.num_nodes))
-        X_host = g.x[:, :F].cpu().numpy()
-        cols = np.random.default_rng(123).choice(Lk, min(Lk, 200), replace=False)
-        t0 = time.perf_counter()
-        orc.pos_precompute(links_host[:, cols], 1, A_host, X_host, K)
-        dt = time.perf_counter() - t0
-        cpu = dict(value=cols.size / dt, unit=UNIT, cores=1, kind="port",
-                   sample=f"{cols.size} links sampled uniformly (seed 123), one pass, {dt:.1f} s; single-process oracle port")
-        del A_host, X_host
-    full_flow = w.get('full')
-    fixed = w['strategy'] is None and not full_flow
-    out = [torch.empty((2 * Lk, F + 1), dtype=torch.float32, device=dev) for _ in range(K + 1)] if fixed else None
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+        if not args.no_cpu_baseline and rank == 0 and world == 1:
+            cpu = rmat_cpu_baseline(w, w['graph'], w['K'])
+    line = measure(args, w, args.workload, args.steps, args.warmup, dev, rank, world, not args.no_e2e, ceilings, cpu)
+    line['ceilings'] = dict(ceilings, hbm_copy_GBps=line['roofline']['peak'],
+                            note="measured in this run by csrc/probe.cu (L2-resident 48 MB buffer streamed with 128-bit loads; "
+                                 "8 independent FFMA chains per thread); HBM copy peak from MEASURED_PEAKS.json")
 
-    def step(profile=None, defer=False):
-        flush.zero_()               # L2 flush between steps
-        if full_flow:
-            return precompute_full(g, links_dev, w['num_hops'], K, node_label=full_flow, batch_records=args.batch_records,
-                                   profile=profile)
-        return precompute(g, links_dev, w['num_hops'], K, w['flow'], w['strategy'],
-                          batch_records=args.batch_records, out=out, profile=profile, overlap=args.overlap,
-                          defer=defer and fixed, walk=w.get('walk'))
-
-    # the sampler starts before the warm-up so that nvidia-smi's own start-up (driver queries)
-    # is over when the timed region begins
-    vis = [v for v in os.environ.get('CUDA_VISIBLE_DEVICES', '').split(',') if v.strip()]
-    clocks = ClockSampler(vis[local_rank] if local_rank < len(vis) else local_rank)
-    res = None
-    for _ in range(max(args.warmup, 3)):     # same code path as the timed steps: per-kernel events, deferred validation
-        del res
-        res = step([], defer=True)
-        res.finalize()
-    if not fixed:
-        res.xs = None
-        if full_flow:
-            res.node_id = None
-    barrier()
-    profile = []
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    launches = 0
-    t_host0 = time.perf_counter()
-    step_events = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    step_events[0].record()
-    pending = []
-    for i in range(args.steps):
-        res = step(profile, defer=True)     # K steps are queued back to back ...
-        if not fixed:
-            # flows whose outputs are allocated inside the call (data-dependent row counts): hand the rows back to
-            # the allocator before the next step, as a caller that consumes each result would (else every step
-            # pays fresh cudaMallocs of several GB while the GPU idles)
-            res.xs = None
-            if full_flow:
-                res.node_id = None
-        pending.append(res)
-        step_events[i + 1].record()
-        launches += res.stats['launches']               # kernels of libs3grl_b200.so only (not the L2 flush fill)
-    for r in pending:                       # ... then synchronised and validated, inside the timed region
-        r.finalize()
-    host_enqueue_ms = res.stats.get('host_enqueue_ms')
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    clk = clocks.stop()
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * Lk * args.steps / (ms_max / 1e3)
-
-    # per-kernel times from the events recorded on the launching stream during the timed steps
-    stage_ms = {}
-    for stage, bi, a, b in profile:
-        stage_ms.setdefault(stage, []).append(a.elapsed_time(b))
-    nb = res.stats['batches']
-    if os.environ.get('S3GRL_BENCH_DEBUG'):
-        for stage, v in stage_ms.items():
-            print(stage, [round(t, 2) for t in v[:2 * nb]], file=sys.stderr)
-    hot = 'sign_full' if full_flow else 'gather'
-    gather_ms = float(np.sum(stage_ms.get(hot, [0.0])))
-    gather_launches = len(stage_ms.get(hot, []))
-    st = res.stats
-    gather_bytes_step = 4 * F * st['sum_n'] + 4 * st['rows'] * (K + 1) * (F + 1)
-    path_bytes_step = algorithmic_bytes(st, F, K)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-    except Exception:
-        pass
-    peak = float(peaks.get('hbm_gbs', 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if 'hbm_gbs' in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-    achieved = gather_bytes_step * args.steps / (gather_ms / 1e3) / 1e9 if gather_ms > 0 else 0.0
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(args.workload)
-    except Exception:
-        pass
-    roofline = dict(bound="hbm", kernel="sign_full_kernel" if full_flow else ("gather_kernel<8,3>" if F > 1024 else "gather_kernel"), achieved=achieved, peak=peak,
-                    unit="GB/s", frac=achieved / peak, traffic=traffic, peak_source=peak_src,
-                    bytes_per_launch=gather_bytes_step / max(nb, 1), launches_timed=gather_launches,
-                    avg_launch_ms=gather_ms / max(gather_launches, 1),
-                    share_of_step={k: float(np.sum(v)) / ms for k, v in stage_ms.items()},
-                    path=dict(achieved=path_bytes_step * args.steps / (ms / 1e3) / 1e9,
-                              frac=path_bytes_step * args.steps / (ms / 1e3) / 1e9 / peak,
-                              bytes_per_link=path_bytes_step / Lk,
-                              note="whole path: SURVEY 8d bytes/link over the full step time"))
-
-    # ---- allgather of the joint rows (what training on N GPUs needs), timed separately ----
-    allgather = None
-    if world > 1 and fixed:
-        from s3grl_b200.parallel import allgather_rows
-        shard = [o[:2 * (Lk // world)] for o in out]
-        rp = torch.arange(Lk // world + 1, device=dev, dtype=torch.int64) * 2
-        allgather_rows(shard, rp)
-        barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        full, _ = allgather_rows(shard, rp)
-        a1.record()
-        barrier()
-        ag = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(ag, op=dist.ReduceOp.MAX)
-        nbytes = sum(f.numel() * 4 for f in full)
-        allgather = dict(ms=float(ag.item()), bytes_per_rank_out=nbytes, busbw_GBps=nbytes * (world - 1) / world / (float(ag.item()) / 1e3) / 1e9,
-                         note="NCCL all_gather_into_tensor of one step's joint rows (strong-scaling shard size: links/N per rank)")
-        del full
-
-    # ---- end to end through the reference-facing call, host buffers in, host buffers out ----
-    e2e = None
-    if not args.no_e2e:
-        from s3grl_b200 import extract_enclosing_subgraphs
-        x_host = torch.from_numpy(w['X']).pin_memory()
-        link_index = torch.from_numpy(np.ascontiguousarray(links_host)).pin_memory()
-        sign_kwargs = dict(sign_k=K, use_feature=True, sign_type=w['flow'], optimize_sign=not full_flow,
-                           k_heuristic=0 if w['strategy'] is None else 1, k_node_set_strategy=w['strategy'])
-        os.environ['S3GRL_DEVICE'] = str(dev)
-        os.environ['S3GRL_OUTPUT_DEVICE'] = 'cpu'
-        del out, res, pending, r
+    # ---- the BASELINE configs that are not the headline, few steps each ----
+    extra = []
+    if args.configs == 'auto':
+        extra = ['pubmed_posplus_union', 'rmat'] if args.workload == 'pubmed_pos' and not args.links else []
+    elif args.configs != 'none':
+        extra = [c for c in args.configs.split(',') if c]
+    configs = []
+    for name in extra:
+        del w
         torch.cuda.empty_cache()
-
-        def e2e_step():
-            tuned_sign._graph_cache.clear()       # the graph upload is part of every step
-            rw_kwargs = dict(rw_m=w['walk']['m'], rw_M=w['walk']['M'], seed=w['walk']['seed'], sign=True) if w.get('walk') else None
-            lst = extract_enclosing_subgraphs(link_index, w['A'], x_host, 1, w['num_hops'], full_flow or 'zo', 1.0, None, False,
-                                              None, rw_kwargs, sign_kwargs, powers_of_A=[] if w['flow'] == 'PoS' else [None] * K,
-                                              data=None)
-            d2h = sum(x.numel() * 4 for x in lst.xs) + lst.row_ptr.numel() * 8
-            chk = float(lst.xs[-1][0, 0])        # touch the host result
-            return d2h, chk
-        for _ in range(2):
-            e2e_step()
-        n_e2e = args.e2e_steps or max(2, min(args.steps, 10))
-        import gc
-        gc.collect()                 # start the timed region with a clean heap (host hiccups show up in e2e.step_ms)
-        barrier()
-        t0 = time.perf_counter()
-        e2e_ms = []
-        for _ in range(n_e2e):
-            ts = time.perf_counter()
-            d2h, _ = e2e_step()
-            e2e_ms.append(round(1000 * (time.perf_counter() - ts), 2))
-        torch.cuda.synchronize(dev)
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        h2d = g.h2d_bytes + link_index.numel() * 8
-        e2e = dict(value=world * Lk * n_e2e / float(tt.item()), unit=UNIT, h2d_bytes_per_step=int(h2d),
-                   d2h_bytes_per_step=int(d2h), steps=n_e2e, ms_per_step=1000 * float(tt.item()) / n_e2e, step_ms=e2e_ms,
-                   api="s3grl_b200.extract_enclosing_subgraphs(link_index, A, x, y, num_hops, ..., sign_kwargs) "
-                       "-> host tensors (S3GRL_OUTPUT_DEVICE=cpu)")
-
+        try:
+            if name == 'rmat':
+                w = build_rmat_workload(args, dev)
+            else:
+                w = build_workload(name)
+            sub = measure(args, w, name, 2, 3, dev, rank, world, False, ceilings, None)
+            keep = {k_: sub[k_] for k_ in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'ms_per_step', 'scaling', 'gpu_launches')}
+            keep['config'] = sub['config']
+            keep['roofline'] = {k_: sub['roofline'][k_] for k_ in ('kernel', 'achieved', 'peak', 'frac', 'share_of_step', 'path')}
+            if 'exchange' in sub:
+                keep['exchange'] = sub['exchange']
+            configs.append(keep)
+        except Exception as ex:      # a secondary config must not take the headline line down with it
+            configs.append(dict(metric=metric_name(name), error=f"{type(ex).__name__}: {ex}"[:300]))
+            w = None
     if rank == 0:
-        line = dict(metric=metric_name(args.workload), value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
-                    ms_per_step=ms_max / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype="f32", data="synthetic",
-                    config=dict(workload=w['desc'], links_per_step_per_gpu=Lk, batch_records=args.batch_records or "auto (32768 for fixed-row flows)",
-                                l2="flushed between steps (256 MiB memset); PubMed's X (39 MB) is L2-resident within a step by "
-                                   "nature of the workload, the R-MAT X (5 GB) is not",
-                                parallelism=f"links sharded x{world}, graph replicated, no data-path collective"),
-                    clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu,
-                    host_enqueue_ms_per_step=host_enqueue_ms,
-                    step_ms=[round(step_events[i].elapsed_time(step_events[i + 1]), 3) for i in range(args.steps)])
-        if allgather:
-            line['allgather'] = allgather
+        if configs:
+            line['configs'] = configs
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define S3_VERSION 100
+#define S3_VERSION 200
 
 /* return codes (the reference raises Python exceptions; see INTEGRATION.md for the mapping) */
 #define S3_OK 0
@@ -71,12 +71,16 @@ extern "C" {
 #define S3_LABEL_DEGREE 4  /* 'degree': induced degree capped at 100               */
 
 #define S3_MAX_HOPS 8
+#define S3_MAX_PEERS 8 /* GPUs of one NVLink domain served by s3_gather_peers */
 #define S3_MAX_K 7
+#define S3_MAX_K_UNION 5 /* S3_STRATEGY_UNION: larger sign_k returns S3_ERR_NOT_IMPLEMENTED from every entry point */
 
 /* per-record status written by s3_extract into cnt[S3_CNT_STATUS] */
 #define S3_REC_OK 0
 #define S3_REC_ARENA_OVERFLOW 1  /* arena too small: re-run the batch with a larger arena            */
 #define S3_REC_BAD_LINK 2        /* node id out of range or src == dst               */
+#define S3_REC_MIRROR 3          /* s3_pair_links found an earlier link over the same node pair: nothing is    */
+                                 /* extracted; the earlier link's s3_gather writes this link's rows as well     */
 
 /* per-record int64 offsets (in 4-byte words from the arena base), off[rec*S3_NOFF + i] */
 /* Only rows j < cnt[S3_CNT_NSTORE] are stored (see s3_extract).                                */
@@ -112,6 +116,9 @@ extern "C" {
 #define S3_CTR_SUM_N 5     /* sum of n  (roofline accounting: 4*F*sum_n feature bytes)    */
 #define S3_CTR_SUM_D 6     /* sum over subgraph nodes of their global degree (4*D bytes)  */
 #define S3_CTR_WORK 7      /* work-queue head of the persistent extraction CTAs           */
+#define S3_CTR_SUM_N_ALL 8 /* sum of n over every LINK served (a record counts once per paired link too) */
+#define S3_CTR_SUM_D_ALL 9 /* same for D: the SURVEY 8d per-link figures with pairing switched on        */
+#define S3_CTR_MIRRORS 10  /* links served by another link's record (s3_pair_links)                      */
 #define S3_CTR_CLASS0 16   /* + c: records whose n has floor(log2 n) == c (size classes)  */
 #define S3_NCTR 48
 
@@ -178,6 +185,17 @@ typedef struct s3_batch {
     const int64_t* link_dst_set;  /* [num_links] ... destination                             */
     int32_t walk_cap;
     int32_t reserved2;
+    /* Link pairing (fixed-row PoS only; all three NULL / 0 otherwise). Training positives arrive as (u,v) AND
+     * (v,u) (PyG train_test_split_edges): same enclosing subgraph, rows 0 and 1 swapped. `mirror`
+     * is the chain table s3_pair_links built over the WHOLE link list of the call (indexed by global link
+     * index); record r serves global link  out_link ? out_link[r] : link_base + r.  A record whose link is a
+     * chain member is skipped by s3_extract (S3_REC_MIRROR); s3_gather of the chain's first link writes the
+     * members' rows too, at row 2 * (member's global link index). With out_link the output rows of record r
+     * are 2 * out_link[r] (+0, +1) instead of row_base + 2r: any partition of the link list over GPUs writes
+     * straight into the layout of the whole list. */
+    const int64_t* out_link;      /* [num_links] global link index of every record, or NULL   */
+    const int64_t* mirror;        /* [links of the whole call] chain table, or NULL           */
+    int64_t link_base;            /* global link index of record 0 when out_link is NULL      */
 } s3_batch;
 
 int s3_version(void);
@@ -269,6 +287,46 @@ int s3_joint_rows(const float* const* src, int32_t num_ops, int64_t num_cols, in
 int s3_sign_head(const float* joint, int64_t rows, int64_t kdim, int64_t ld_joint, const float* weight, int64_t ld_w,
                  int64_t hidden, const float* bias, const float* bn_scale, const float* bn_shift, float* pooled, int32_t pool,
                  void* stream);
+
+/* Link pairing (see s3_batch.mirror): for every unordered node pair {u,v} that occurs more than once in the link
+ * list (both directions of a training edge, or repeats), the link with the lowest index keeps the work and the
+ * others become members of its chain:
+ *   mirror[i] >= 0   link i is the first of its pair; mirror[i] is the first member of its chain
+ *   mirror[i] == -1  link i has no other link over its pair (or is invalid: out of range / src == dst)
+ *   mirror[i] <= -2  link i is a member: v = -2 - mirror[i], bit 0 of v = rows swapped relative to the first
+ *                    link (opposite direction), (v >> 1) - 1 = next member or -1.
+ * Which member follows which is scheduling dependent; the rows written are not. table: scratch of
+ * 2 * s3_pair_table_slots(num_links) int64 words. Results are exact: the extraction / diffusion / gather of
+ * (u,v) and (v,u) are bit-identical up to the row swap (the two seed rows are accumulated in ascending
+ * global-id order). */
+int64_t s3_pair_table_slots(int64_t num_links);
+int s3_pair_links(const int64_t* link_src, const int64_t* link_dst, int64_t num_links, int64_t num_nodes,
+                  int64_t* table, int64_t table_slots, int64_t* mirror, void* stream);
+
+/* Fused gather + all-gather over NVLink peer memory: as s3_gather for the fixed-row flows, but every
+ * output row is stored into the operator matrices of ALL num_dst GPUs (this one included) instead of one local
+ * copy followed by an NCCL all-gather. dst_bases: HOST array of num_dst (<= 8) device pointers, each the base of
+ * one GPU's buffer mapped into this process (s3_peer_open); operator k of a buffer starts at base + k * op_stride
+ * floats and is [*, ldo] row-major. Rows land at 2 * (global link index) (out_link / link_base / mirror as in
+ * s3_batch). No flag is spun on: completion is the kernel boundary followed by the caller's barrier. */
+int s3_gather_peers(const s3_graph* g, const s3_batch* b, int64_t num_records, float* const* dst_bases, int32_t num_dst,
+                    int64_t op_stride, int64_t ldo, void* stream);
+
+/* Peer memory for s3_gather_peers: one cudaMalloc'ed buffer per GPU, exported as a 64-byte CUDA IPC handle that
+ * the other ranks of the node open (peer access is enabled lazily by the open). Plain CUDA runtime IPC; the
+ * handles travel through the caller's own channel (torch.distributed all_gather_object in parallel.py). */
+#define S3_PEER_HANDLE_BYTES 64
+int s3_peer_alloc(int64_t bytes, void** ptr);
+int s3_peer_free(void* ptr);
+int s3_peer_export(void* ptr, unsigned char* handle /* [S3_PEER_HANDLE_BYTES] */);
+int s3_peer_open(const unsigned char* handle, void** ptr);
+int s3_peer_close(void* ptr);
+
+/* Measurement aids (bench.py roofline): the L2 -> SM read bandwidth (the grid streams an L2-sized buffer `iters`
+ * times with 128-bit L1-bypassing loads: bytes * iters per launch) and the FP32 FMA issue rate
+ * (ctas * 256 threads * iters * 128 FMAs per launch). Nothing on the product path calls them. */
+int s3_probe_l2_read(const float* buf, int64_t bytes, int32_t iters, float* sink, int32_t ctas, void* stream);
+int s3_probe_fma(int32_t iters, float* sink, int32_t ctas, void* stream);
 
 /* Optional dumps for parity checks: canonical global-id edge list of every record,
  * edges[e] = (global row, global col), e in [edge_ptr[r], edge_ptr[r+1]). */

@@ -10,17 +10,21 @@ LIB_PATH = os.path.join(HERE, 'lib', 'libs3grl_b200.so')
 S3_OK, S3_ERR_INVALID_ARG, S3_ERR_UNSUPPORTED, S3_ERR_CUDA, S3_ERR_NOT_IMPLEMENTED, S3_ERR_WORKSPACE = 0, 1, 2, 3, 4, 5
 FLOW_POS, FLOW_SOP = 0, 1
 STRATEGY_NONE, STRATEGY_INTERSECTION, STRATEGY_UNION = 0, 1, 2
-MAX_HOPS, MAX_K = 8, 7
+MAX_HOPS, MAX_K, MAX_K_UNION, MAX_PEERS, PEER_HANDLE_BYTES = 8, 7, 5, 8, 64
+VERSION = 200
 LABEL_ZERO, LABEL_ZO, LABEL_HOP, LABEL_DRNL, LABEL_DEGREE = 0, 1, 2, 3, 4
-REC_OK, REC_ARENA_OVERFLOW, REC_BAD_LINK = 0, 1, 2
+REC_OK, REC_ARENA_OVERFLOW, REC_BAD_LINK, REC_MIRROR = 0, 1, 2, 3
 OFF_NODES, OFF_ROWPTR, OFF_ROWLEN, OFF_LCOL, OFF_SEL, OFF_F32, NOFF = 0, 1, 2, 3, 4, 5, 6
 CNT_N, CNT_M, CNT_S, CNT_STATUS, CNT_PARTNER, CNT_HOP0, CNT_NSTORE, NCNT = 0, 1, 2, 3, 4, 5, 14, 16
 BATCH_STORE_ALL_ROWS, BATCH_FORCE_SORTED_TIER, BATCH_CCN_CHAIN = 1, 2, 4
 CTR_CURSOR, CTR_ERRORS, CTR_ROWS, CTR_ITEMS, CTR_MAX_N, CTR_SUM_N, CTR_SUM_D, CTR_WORK, NCTR = 0, 1, 2, 3, 4, 5, 6, 7, 48
+CTR_SUM_N_ALL, CTR_SUM_D_ALL, CTR_MIRRORS = 8, 9, 10
 
 EXPORTS = ['s3_version', 's3_error_string', 's3_last_cuda_error', 's3_num_records', 's3_extract_smem_bytes',
            's3_min_arena_words', 's3_extract_tier',
-           's3_extract', 's3_plan', 's3_plan_items', 's3_diffuse', 's3_gather', 's3_gather_ccn', 's3_ccn_chain', 's3_plan_full', 's3_sign_full', 's3_joint_rows', 's3_sign_head', 's3_walk_sets', 's3_dump_edges']
+           's3_extract', 's3_plan', 's3_plan_items', 's3_diffuse', 's3_gather', 's3_gather_ccn', 's3_ccn_chain', 's3_plan_full', 's3_sign_full', 's3_joint_rows', 's3_sign_head', 's3_walk_sets', 's3_dump_edges',
+           's3_pair_table_slots', 's3_pair_links', 's3_gather_peers', 's3_peer_alloc', 's3_peer_free', 's3_peer_export',
+           's3_peer_open', 's3_peer_close', 's3_probe_l2_read', 's3_probe_fma']
 
 
 class Graph(C.Structure):
@@ -37,7 +41,8 @@ class Batch(C.Structure):
                 ('off', C.c_void_p), ('cnt', C.c_void_p), ('counters', C.c_void_p),
                 ('row_ptr', C.c_void_p), ('item_ptr', C.c_void_p), ('item_rec', C.c_void_p), ('order', C.c_void_p),
                 ('walk_sets', C.c_void_p), ('walk_counts', C.c_void_p), ('link_src_set', C.c_void_p),
-                ('link_dst_set', C.c_void_p), ('walk_cap', C.c_int32), ('reserved2', C.c_int32)]
+                ('link_dst_set', C.c_void_p), ('walk_cap', C.c_int32), ('reserved2', C.c_int32),
+                ('out_link', C.c_void_p), ('mirror', C.c_void_p), ('link_base', C.c_int64)]
 
 
 class S3Error(RuntimeError):
@@ -88,8 +93,21 @@ def lib():
         L.s3_walk_sets.argtypes = [C.POINTER(Graph), C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, C.c_int32,
                                    C.c_void_p, C.c_void_p, C.c_void_p]
         L.s3_dump_edges.argtypes = [C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.s3_pair_table_slots.restype = C.c_int64
+        L.s3_pair_table_slots.argtypes = [C.c_int64]
+        L.s3_pair_links.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.s3_gather_peers.argtypes = [C.POINTER(Graph), C.POINTER(Batch), C.c_int64, C.POINTER(C.c_void_p), C.c_int32,
+                                      C.c_int64, C.c_int64, C.c_void_p]
+        L.s3_probe_l2_read.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+        L.s3_probe_fma.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+        L.s3_peer_alloc.argtypes = [C.c_int64, C.POINTER(C.c_void_p)]
+        L.s3_peer_free.argtypes = [C.c_void_p]
+        L.s3_peer_export.argtypes = [C.c_void_p, C.c_char_p]
+        L.s3_peer_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        L.s3_peer_close.argtypes = [C.c_void_p]
         for fn in ('s3_extract', 's3_plan', 's3_plan_items', 's3_diffuse', 's3_gather', 's3_gather_ccn', 's3_ccn_chain', 's3_plan_full', 's3_sign_full', 's3_joint_rows', 's3_sign_head', 's3_walk_sets',
-                   's3_dump_edges'):
+                   's3_dump_edges', 's3_pair_links', 's3_gather_peers', 's3_peer_alloc', 's3_peer_free', 's3_peer_export',
+                   's3_peer_open', 's3_peer_close', 's3_probe_l2_read', 's3_probe_fma'):
             getattr(L, fn).restype = C.c_int
         _lib = L
     return _lib

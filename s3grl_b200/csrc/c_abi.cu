@@ -19,6 +19,8 @@ int check_batch(const s3_batch* b) {
     if (b->flow == S3_FLOW_POS && (b->strategy < S3_STRATEGY_NONE || b->strategy > S3_STRATEGY_UNION))
         return S3_ERR_NOT_IMPLEMENTED;  // reference: NotImplementedError(f"check strat {strat}"), tuned_SIGN.py:235
     if (b->sign_k < 1 || b->sign_k > S3_MAX_K) return S3_ERR_INVALID_ARG;
+    // the 8-row CCN work items of `union` are instantiated up to sign_k = 5 (gather_sc8_k*.cu)
+    if (b->flow == S3_FLOW_POS && b->strategy == S3_STRATEGY_UNION && b->sign_k > S3_MAX_K_UNION) return S3_ERR_NOT_IMPLEMENTED;
     const int radius = b->flow == S3_FLOW_POS ? b->num_hops : b->sign_k;
     if (radius < 0 || radius > S3_MAX_HOPS) return S3_ERR_INVALID_ARG;
     if (b->num_links > 0 && (!b->link_src || !b->link_dst || !b->arena || !b->off || !b->cnt || !b->counters))
@@ -148,6 +150,90 @@ int s3_gather(const s3_graph* g, const s3_batch* b, int64_t num_records, float* 
 int s3_gather_ccn(const s3_graph* g, const s3_batch* b, int64_t num_items, float* const* out, int64_t ldo, int64_t row_base,
                   void* stream) {
     return gather_impl(g, b, num_items, out, ldo, row_base, 1, stream);
+}
+
+int s3_gather_peers(const s3_graph* g, const s3_batch* b, int64_t num_records, float* const* dst_bases, int32_t num_dst,
+                    int64_t op_stride, int64_t ldo, void* stream) {
+    int rc = check_graph(g, true);
+    if (rc != S3_OK) return rc;
+    rc = check_batch(b);
+    if (rc != S3_OK) return rc;
+    if (b->strategy != S3_STRATEGY_NONE && b->flow == S3_FLOW_POS) return S3_ERR_NOT_IMPLEMENTED;  // fixed-row flows only
+    if (num_records < 0 || !dst_bases || num_dst < 1 || num_dst > S3_MAX_PEERS || ldo < g->num_feat + 1 || op_stride < 0)
+        return S3_ERR_INVALID_ARG;
+    s3::PeerDst peers;
+    peers.num_dst = num_dst;
+    peers.op_stride = op_stride;
+    for (int d = 0; d < S3_MAX_PEERS; ++d) peers.base[d] = nullptr;
+    for (int d = 0; d < num_dst; ++d) {
+        if (!dst_bases[d]) return S3_ERR_INVALID_ARG;
+        peers.base[d] = dst_bases[d];
+    }
+    s3::OutPtrs o;
+    memset(&o, 0, sizeof(o));
+    cudaError_t e = s3::launch_gather(*g, *b, num_records, o, ldo, b->link_base * 2 /* rows per link */, false,
+                                      static_cast<cudaStream_t>(stream), &peers);
+    return e == cudaSuccess ? S3_OK : cuda_fail(e);
+}
+
+int64_t s3_pair_table_slots(int64_t num_links) {
+    int64_t slots = 64;
+    while (slots < 2 * num_links) slots <<= 1;
+    return slots;
+}
+
+int s3_pair_links(const int64_t* link_src, const int64_t* link_dst, int64_t num_links, int64_t num_nodes, int64_t* table,
+                  int64_t table_slots, int64_t* mirror, void* stream) {
+    if (num_links < 0 || num_nodes <= 0 || num_nodes > INT32_MAX) return S3_ERR_INVALID_ARG;
+    if (num_links == 0) return S3_OK;
+    if (!link_src || !link_dst || !table || !mirror) return S3_ERR_INVALID_ARG;
+    if (table_slots < 2 * num_links || (table_slots & (table_slots - 1))) return S3_ERR_WORKSPACE;
+    cudaError_t e = s3::launch_pair_links(link_src, link_dst, num_links, num_nodes, table, table_slots, mirror,
+                                          static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? S3_OK : cuda_fail(e);
+}
+
+int s3_probe_l2_read(const float* buf, int64_t bytes, int32_t iters, float* sink, int32_t ctas, void* stream) {
+    if (!buf || !sink || bytes < 16 * 1024 || (bytes & 15) || iters < 1 || ctas < 1 || (reinterpret_cast<uintptr_t>(buf) & 15))
+        return S3_ERR_INVALID_ARG;
+    cudaError_t e = s3::launch_probe_l2_read(buf, bytes, iters, sink, ctas, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? S3_OK : cuda_fail(e);
+}
+
+int s3_probe_fma(int32_t iters, float* sink, int32_t ctas, void* stream) {
+    if (!sink || iters < 1 || ctas < 1) return S3_ERR_INVALID_ARG;
+    cudaError_t e = s3::launch_probe_fma(iters, sink, ctas, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? S3_OK : cuda_fail(e);
+}
+
+int s3_peer_alloc(int64_t bytes, void** ptr) {
+    if (bytes <= 0 || !ptr) return S3_ERR_INVALID_ARG;
+    cudaError_t e = s3::peer_alloc(bytes, ptr);
+    return e == cudaSuccess ? S3_OK : cuda_fail(e);
+}
+
+int s3_peer_free(void* ptr) {
+    if (!ptr) return S3_OK;
+    cudaError_t e = s3::peer_free(ptr);
+    return e == cudaSuccess ? S3_OK : cuda_fail(e);
+}
+
+int s3_peer_export(void* ptr, unsigned char* handle) {
+    if (!ptr || !handle) return S3_ERR_INVALID_ARG;
+    cudaError_t e = s3::peer_export(ptr, handle);
+    return e == cudaSuccess ? S3_OK : cuda_fail(e);
+}
+
+int s3_peer_open(const unsigned char* handle, void** ptr) {
+    if (!handle || !ptr) return S3_ERR_INVALID_ARG;
+    cudaError_t e = s3::peer_open(handle, ptr);
+    return e == cudaSuccess ? S3_OK : cuda_fail(e);
+}
+
+int s3_peer_close(void* ptr) {
+    if (!ptr) return S3_OK;
+    cudaError_t e = s3::peer_close(ptr);
+    return e == cudaSuccess ? S3_OK : cuda_fail(e);
 }
 
 int s3_ccn_chain(const s3_graph* g, const s3_batch* b, int64_t num_records, float* const* out, int64_t ldo, int64_t row_base,

@@ -256,12 +256,9 @@ cudaError_t launch_ccn_chain(const s3_graph& g, const s3_batch& b, int64_t num_r
     if (num_records == 0) return cudaSuccess;
     if (!b.row_ptr || b.flow != S3_FLOW_POS || b.strategy != S3_STRATEGY_UNION || !(b.flags & S3_BATCH_CCN_CHAIN))
         return cudaErrorInvalidValue;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(ccn_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemBytes);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static LaunchCache cache;  // the shared-memory opt-in is per device
+    cudaError_t e = cache.get(reinterpret_cast<const void*>(ccn_chain_kernel), kChainThreads, kChainSmemBytes, nullptr, nullptr);
+    if (e != cudaSuccess) return e;
     ChainParams p;
     p.x = g.x;
     p.ldx = g.ldx;

@@ -2,6 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
+
+#include <mutex>
 
 #include "../../include/s3grl_b200.h"
 
@@ -73,8 +76,60 @@ __host__ __device__ inline bool chain_eligible(int flags, int strategy, int64_t 
            chain_fixed_words(n, m, n1) + 2 * n * 8 <= kChainSmemBytes / 4;
 }
 
+// link pairing (pair.cu) applies to fixed-row PoS batches whose rows are not all stored (no parity dump)
+inline bool batch_pairing(const s3_batch& b) {
+    return b.mirror && b.flow == S3_FLOW_POS && b.strategy == S3_STRATEGY_NONE && !(b.flags & S3_BATCH_STORE_ALL_ROWS) &&
+           !b.walk_sets;
+}
+
 struct OutPtrs {
     float* p[2 * S3_MAX_K];  // K+1 operators; 2K for the hybrid flow (reference utils.py:454-480)
+};
+
+// Launch configuration that depends on the device: the opt-in to > 48 KB of dynamic shared memory
+// (cudaFuncSetAttribute is per context) and the SM count / occupancy of a persistent kernel. Cached per
+// (device, shared-memory size) because the queries are slow host calls; safe for several devices and
+// threads in one process.
+struct LaunchCache {
+    static constexpr int kDevices = 64;
+    std::mutex mu;
+    size_t configured[kDevices] = {};
+    size_t occ_smem[kDevices] = {};
+    int sms[kDevices] = {};
+    int occ[kDevices] = {};
+    bool have[kDevices] = {};
+    // func: the kernel; threads / smem: its launch shape. sms_out / occ_out may be null (attribute only).
+    cudaError_t get(const void* func, int threads, size_t smem, int* sms_out, int* occ_out) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        if (dev < 0 || dev >= kDevices) return cudaErrorInvalidDevice;
+        std::lock_guard<std::mutex> lock(mu);
+        if (smem > configured[dev] || (smem > 0 && configured[dev] == 0)) {
+            e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            configured[dev] = smem;
+        }
+        if (sms_out || occ_out) {
+            if (!have[dev] || occ_smem[dev] != smem) {
+                e = cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+                if (e != cudaSuccess) return e;
+                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[dev], func, threads, smem);
+                if (e != cudaSuccess) return e;
+                have[dev] = true;
+                occ_smem[dev] = smem;
+            }
+            if (sms_out) *sms_out = sms[dev];
+            if (occ_out) *occ_out = occ[dev];
+        }
+        return cudaSuccess;
+    }
+};
+
+struct PeerDst {  // s3_gather_peers destinations
+    float* base[S3_MAX_PEERS];
+    int num_dst;
+    int64_t op_stride;
 };
 
 // launchers (defined in the .cu files, called from c_abi.cu)
@@ -87,7 +142,16 @@ cudaError_t launch_plan(const s3_batch& b, cudaStream_t st);
 cudaError_t launch_plan_items(const s3_batch& b, cudaStream_t st);
 cudaError_t launch_diffuse(const s3_graph& g, const s3_batch& b, int64_t num_items, cudaStream_t st);
 cudaError_t launch_gather(const s3_graph& g, const s3_batch& b, int64_t num_items, const OutPtrs& out,
-                          int64_t ldo, int64_t row_base, bool ccn, cudaStream_t st);
+                          int64_t ldo, int64_t row_base, bool ccn, cudaStream_t st, const PeerDst* peers = nullptr);
+cudaError_t launch_pair_links(const int64_t* src, const int64_t* dst, int64_t L, int64_t N, int64_t* table, int64_t slots,
+                              int64_t* mirror, cudaStream_t st);
+cudaError_t launch_probe_l2_read(const float* buf, int64_t bytes, int iters, float* sink, int ctas, cudaStream_t st);
+cudaError_t launch_probe_fma(int iters, float* sink, int ctas, cudaStream_t st);
+cudaError_t peer_alloc(int64_t bytes, void** ptr);
+cudaError_t peer_free(void* ptr);
+cudaError_t peer_export(void* ptr, unsigned char* handle);
+cudaError_t peer_open(const unsigned char* handle, void** ptr);
+cudaError_t peer_close(void* ptr);
 cudaError_t launch_ccn_chain(const s3_graph& g, const s3_batch& b, int64_t num_records, const OutPtrs& out, int64_t ldo,
                              int64_t row_base, cudaStream_t st);
 cudaError_t launch_plan_full(const s3_batch& b, cudaStream_t st);

@@ -56,6 +56,9 @@ struct ExtractParams {
     int64_t* off;
     int32_t* cnt;
     unsigned long long* counters;
+    const int64_t* __restrict__ out_link;  // link pairing (s3_batch): global link index of a record
+    const int64_t* __restrict__ mirror;    // chain table of s3_pair_links, or null
+    int64_t link_base;
 };
 
 constexpr int kStreamLanes = 4;  // lanes per streamed (hop-K) row
@@ -136,6 +139,18 @@ __global__ void __launch_bounds__(kExtractThreads, 5) front_kernel(ExtractParams
         }
         int32_t* cnt = p.cnt + rec * S3_NCNT;
         int64_t* off = p.off + rec * S3_NOFF;
+        const int64_t gl = !p.mirror ? 0 : (p.out_link ? p.out_link[rec] : p.link_base + rec);  // pairing: PoS only
+        if (p.mirror && p.mirror[gl] <= -2) {
+            // an earlier link over the same node pair does the work and writes this link's rows (pair.cu)
+            if (tid == 0) {
+                for (int i = 0; i < S3_NCNT; ++i) cnt[i] = 0;
+                for (int i = 0; i < S3_NOFF; ++i) off[i] = 0;
+                cnt[S3_CNT_STATUS] = S3_REC_MIRROR;
+                cnt[S3_CNT_PARTNER] = -1;
+                atomicAdd(&p.counters[S3_CTR_MIRRORS], 1ull);
+            }
+            continue;
+        }
         if (a < 0 || b < 0 || a >= p.num_nodes || b >= p.num_nodes || a == b) {
             if (tid == 0) {
                 for (int i = 0; i < S3_NCNT; ++i) cnt[i] = 0;
@@ -552,6 +567,13 @@ __global__ void __launch_bounds__(kExtractThreads, 5) front_kernel(ExtractParams
             atomicMax(&p.counters[S3_CTR_MAX_N], (unsigned long long)n);
             atomicAdd(&p.counters[S3_CTR_SUM_N], (unsigned long long)n);
             atomicAdd(&p.counters[S3_CTR_SUM_D], (unsigned long long)D);
+            // per-LINK figures (SURVEY 8d sums over links): this record also serves its chain members
+            unsigned long long served = 1;
+            if (p.mirror) {
+                for (long long m = p.mirror[gl]; m >= 0; m = ((-2 - (long long)p.mirror[m]) >> 1) - 1) ++served;
+            }
+            atomicAdd(&p.counters[S3_CTR_SUM_N_ALL], served * (unsigned long long)n);
+            atomicAdd(&p.counters[S3_CTR_SUM_D_ALL], served * (unsigned long long)D);
         }
     }
 }
@@ -572,7 +594,7 @@ __global__ void order_kernel(const int32_t* __restrict__ cnt, const unsigned lon
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= num_records) return;
     const int32_t* c = cnt + r * S3_NCNT;
-    if (c[S3_CNT_STATUS] == S3_REC_BAD_LINK) return;  // not classed; its slot stays -1
+    if (c[S3_CNT_STATUS] == S3_REC_BAD_LINK || c[S3_CNT_STATUS] == S3_REC_MIRROR) return;  // not classed; slots stay -1
     const int n = c[S3_CNT_N];
     order[s_off[31 - __clz(n)] + c[S3_CNT_CLASSPOS]] = (int32_t)r;
 }
@@ -592,28 +614,13 @@ namespace {
 template <int SC>
 cudaError_t launch_front(ExtractParams& p, const s3_graph& g, const s3_batch& b, cudaStream_t st, int* rc_out) {
     const size_t smem = (size_t)s3_extract_smem_bytes(g.num_nodes, p.radius);
-    static size_t configured = 0;
-    if (smem > configured) {  // static (37 KB) + dynamic shared memory may exceed the 48 KB default limit
-        cudaError_t e = cudaFuncSetAttribute(front_kernel<SC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
-    // device queries are slow host calls: cache them per (device, smem) pair
-    static int c_dev = -1, c_sms = 0, c_occ = 0;
-    static size_t c_smem = 0;
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
+    // function attributes and occupancy are per device: cache them per (device, smem), under a lock
+    static LaunchCache cache;
+    int sms = 0, occ = 0;
+    cudaError_t e = cache.get(reinterpret_cast<const void*>(front_kernel<SC>), kExtractThreads, smem, &sms, &occ);
     if (e != cudaSuccess) return e;
-    if (dev != c_dev || smem != c_smem) {
-        e = cudaDeviceGetAttribute(&c_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c_occ, front_kernel<SC>, kExtractThreads, smem);
-        if (e != cudaSuccess) return e;
-        c_dev = dev;
-        c_smem = smem;
-    }
     p.slab_stride = (4 * g.num_nodes + 1 + 31) & ~int64_t(31);
-    int64_t grid = (int64_t)c_sms * (c_occ > 0 ? c_occ : 1);
+    int64_t grid = (int64_t)sms * (occ > 0 ? occ : 1);
     if (grid > p.num_records) grid = p.num_records;
     const int64_t fit = (b.arena_words / 2) / p.slab_stride;  // slabs may take at most half of the arena
     if (grid > fit) grid = fit;
@@ -650,6 +657,9 @@ cudaError_t launch_extract_bitmap(const s3_graph& g, const s3_batch& b, cudaStre
     p.off = b.off;
     p.cnt = b.cnt;
     p.counters = reinterpret_cast<unsigned long long*>(b.counters);
+    p.out_link = b.out_link;
+    p.mirror = batch_pairing(b) ? b.mirror : nullptr;
+    p.link_base = b.link_base;
     if (p.num_records == 0) return cudaSuccess;
     return b.flow == S3_FLOW_POS ? launch_front<2>(p, g, b, st, rc_out) : launch_front<1>(p, g, b, st, rc_out);
 }

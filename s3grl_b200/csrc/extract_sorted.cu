@@ -641,17 +641,10 @@ cudaError_t launch_extract_sorted(const s3_graph& g, const s3_batch& b, cudaStre
     p.cnt = b.cnt;
     p.counters = reinterpret_cast<unsigned long long*>(b.counters);
     if (p.num_records == 0) return cudaSuccess;
-    static int c_dev = -1, c_sms = 0, c_occ = 0;
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
+    static LaunchCache cache;  // per device: SM count and occupancy of the persistent kernel
+    int c_sms = 0, c_occ = 0;
+    cudaError_t e = cache.get(reinterpret_cast<const void*>(front_sorted_kernel), kExtractThreads, 0, &c_sms, &c_occ);
     if (e != cudaSuccess) return e;
-    if (dev != c_dev) {
-        e = cudaDeviceGetAttribute(&c_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c_occ, front_sorted_kernel, kExtractThreads, 0);
-        if (e != cudaSuccess) return e;
-        c_dev = dev;
-    }
     p.slab_stride = (2 * ((b.walk_sets ? (int64_t)b.walk_cap : g.max_degree) + 1) + 31) & ~int64_t(31);
     int64_t grid = (int64_t)c_sms * (c_occ > 0 ? c_occ : 1);
     if (grid > p.num_records) grid = p.num_records;

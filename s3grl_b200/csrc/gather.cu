@@ -5,7 +5,7 @@
 namespace s3 {
 
 cudaError_t launch_gather(const s3_graph& g, const s3_batch& b, int64_t num_items, const OutPtrs& out, int64_t ldo,
-                          int64_t row_base, bool ccn, cudaStream_t st) {
+                          int64_t row_base, bool ccn, cudaStream_t st, const PeerDst* peers) {
     if (num_items == 0) return cudaSuccess;
     if (g.num_nodes * (g.ldx / 4) >= (int64_t(1) << 32)) return cudaErrorInvalidValue;  // 32-bit row offsets
     GatherParams p;
@@ -27,6 +27,18 @@ cudaError_t launch_gather(const s3_graph& g, const s3_batch& b, int64_t num_item
     p.out = out;
     p.ldo = ldo;
     p.row_base = row_base;
+    p.out_link = ccn ? nullptr : b.out_link;
+    p.mirror = (!ccn && batch_pairing(b)) ? b.mirror : nullptr;
+    p.link_base = b.link_base;
+    p.num_dst = 0;
+    p.op_stride = 0;
+    for (int d = 0; d < S3_MAX_PEERS; ++d) p.dst_base[d] = nullptr;
+    if (peers) {
+        if (ccn || peers->num_dst < 1 || peers->num_dst > S3_MAX_PEERS) return cudaErrorInvalidValue;
+        p.num_dst = peers->num_dst;
+        p.op_stride = peers->op_stride;
+        for (int d = 0; d < peers->num_dst; ++d) p.dst_base[d] = peers->base[d];
+    }
 
     int C, tpr;
     const int F4 = p.F4;
@@ -45,7 +57,9 @@ cudaError_t launch_gather(const s3_graph& g, const s3_batch& b, int64_t num_item
     const int G = kGatherThreads / tpr;
     const size_t tile_bytes = (size_t)kTile * NWP * 4 + kTile * 4;
     const size_t red_bytes = (size_t)(G - 1) * NW * C * tpr * 16;
-    const size_t smem = tile_bytes > red_bytes ? tile_bytes : red_bytes;
+    const size_t row_bytes = (size_t)C * tpr * 16;  // one staged output row of the column chunk
+    size_t smem = tile_bytes > red_bytes ? tile_bytes : red_bytes;
+    if (row_bytes > smem) smem = row_bytes;
     dim3 grid((unsigned)num_items, (unsigned)colchunks);
     const int K1 = b.sign_k + 1;
     if (sc == 8) {  // union with sign_k > 5 is not instantiated

@@ -44,6 +44,15 @@ struct GatherParams {
     int ccn;                               // 1: CCN work items (item_rec/item_ptr), 0: the records' own rows
     OutPtrs out;
     int64_t ldo, row_base;
+    // link pairing and explicit output placement (s3_batch.out_link / mirror / link_base); null / 0 when unused
+    const int64_t* __restrict__ out_link;
+    const int64_t* __restrict__ mirror;
+    int64_t link_base;
+    // s3_gather_peers: every row goes to num_dst buffers (this GPU's and its NVLink peers'), operator k of buffer
+    // d at dst_base[d] + k * op_stride; num_dst == 0: the single local destination `out`
+    int num_dst;
+    float* dst_base[S3_MAX_PEERS];
+    int64_t op_stride;
 };
 // per-(SC, K1 range) translation units, so that the ~130 instantiations compile in parallel
 #define S3_DECL_GATHER_TU(name) \
@@ -77,6 +86,9 @@ struct GatherCtx {
     float* s_w;
     uint32_t* s_off;  // float4 index of every staged node's feature row
     int tid, grp, G;
+    // PoS records: the two seeds are accumulated in ascending GLOBAL id order, so that (u,v) and (v,u) produce
+    // bit-identical rows (link pairing, pair.cu); true when local 0 has the larger global id
+    bool swap01;
 };
 
 template <int K1, int SC, int KMIN>
@@ -114,11 +126,16 @@ __device__ __forceinline__ void accumulate_range(float4 (&acc)[K1 * SC][C], int 
     for (int base = lo; base < hi; base += kTile) {
         const int tn = min(kTile, hi - base);
         __syncthreads();
-        if (tid < tn) s_off[tid] = (uint32_t)cx.nodes[base + tid] * cx.ldx4;
+        const bool sw = cx.swap01 && base == 0;  // the seeds sit at the head of the first range
+        if (tid < tn) s_off[tid] = (uint32_t)cx.nodes[base + ((sw && tid < 2) ? 1 - tid : tid)] * cx.ldx4;
         {
             const float4* src = cx.wgt4 + (int64_t)base * (NWP / 4);
             float4* dst = reinterpret_cast<float4*>(s_w);
-            for (int i = tid; i < tn * (NWP / 4); i += kGatherThreads) dst[i] = src[i];
+            for (int i = tid; i < tn * (NWP / 4); i += kGatherThreads) {
+                int si = i;
+                if (sw && i < 2 * (NWP / 4)) si = i < NWP / 4 ? i + NWP / 4 : i - NWP / 4;
+                dst[i] = src[si];
+            }
         }
         __syncthreads();
 
@@ -238,6 +255,7 @@ __global__ void __launch_bounds__(kGatherThreads, gather_min_blocks(K1 * SC * C)
     cx.tid = tid;
     cx.grp = grp;
     cx.G = G;
+    cx.swap01 = SC == 2 && !p.ccn && p.flow == S3_FLOW_POS && n >= 2 && nodes[0] > nodes[1];
 
     float4 acc[NW][C];
 #pragma unroll
@@ -283,25 +301,45 @@ __global__ void __launch_bounds__(kGatherThreads, gather_min_blocks(K1 * SC * C)
                     }
         }
     }
-    if (grp != 0) return;
 
+    // ---- epilogue: every output row is staged through shared memory and stored with consecutive lanes on
+    // consecutive floats (rows are 4-byte aligned only: ldo = F + 1), to this GPU's operator matrices or, for
+    // s3_gather_peers, to every GPU's; chain members of a paired link get the same rows (seed rows exchanged
+    // for the opposite direction).
     const int first_sel = p.ccn ? nseed + chunk * SC : 0;  // index of this item's first selected row
-    const int64_t row0 = p.row_base + (p.row_ptr ? p.row_ptr[rec] : rec * (int64_t)nseed) + first_sel;
+    const int rpl = p.flow == S3_FLOW_SOP ? 2 : 1;  // records per link (SoP: one per endpoint)
+    const int64_t gl = p.out_link ? p.out_link[rec / rpl] : p.link_base + rec / rpl;  // global link index (fixed-row flows)
+    const int64_t row0 = (p.out_link ? (gl * rpl + rec % rpl) * nseed
+                                     : p.row_base + (p.row_ptr ? p.row_ptr[rec] : rec * (int64_t)nseed)) + first_sel;
+    const long long chain = (p.mirror && !p.ccn) ? (long long)p.mirror[gl] : -1;
+    float* s_row = reinterpret_cast<float*>(smem4);  // [C * tpr * 4]
+    const int f0 = blockIdx.y * C * tpr * 4;         // first feature of this CTA's column chunk
+    const int nfl = min(C * tpr * 4, p.F - f0);
+    const int ndst = p.num_dst > 0 ? p.num_dst : 1;
 #pragma unroll
     for (int q = 0; q < NW; ++q) {
         const int k = q / SC, c = q - k * SC;
-        if (first_sel + c >= s) continue;
-        float* orow = p.out.p[k] + (row0 + c) * p.ldo;
-        if (blockIdx.y == 0 && lane == 0) orow[0] = lab[q];
+        const bool live = first_sel + c < s;  // uniform over the CTA
+        __syncthreads();
+        if (live && grp == 0) {
 #pragma unroll
-        for (int i = 0; i < C; ++i) {
-            if (!colok[i]) continue;
-            const int f = 4 * col[i];
-            float* o = orow + 1 + f;
-            if (f + 0 < p.F) o[0] = acc[q][i].x;
-            if (f + 1 < p.F) o[1] = acc[q][i].y;
-            if (f + 2 < p.F) o[2] = acc[q][i].z;
-            if (f + 3 < p.F) o[3] = acc[q][i].w;
+            for (int i = 0; i < C; ++i) reinterpret_cast<float4*>(s_row)[i * tpr + lane] = acc[q][i];
+        }
+        __syncthreads();
+        if (!live) continue;
+        const float labv = lab[q];
+        int64_t row = row0 + c;
+        long long m = chain;
+        for (;;) {
+            for (int d = 0; d < ndst; ++d) {
+                float* orow = (p.num_dst > 0 ? p.dst_base[d] + (int64_t)k * p.op_stride : p.out.p[k]) + row * p.ldo;
+                for (int idx = tid; idx < nfl; idx += kGatherThreads) orow[1 + f0 + idx] = s_row[idx];
+                if (blockIdx.y == 0 && tid == 0) orow[0] = labv;
+            }
+            if (m < 0) break;
+            const long long v = -2 - (long long)p.mirror[m];
+            row = (int64_t)m * nseed + ((v & 1) ? SC - 1 - c : c);
+            m = (v >> 1) - 1;
         }
     }
 }

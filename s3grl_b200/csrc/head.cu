@@ -251,14 +251,12 @@ cudaError_t launch_sign_head(const float* x, int64_t rows, int64_t kdim, int64_t
         if (qres != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
         enc = reinterpret_cast<EncodeTiledFn>(fn);
     }
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(sign_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadSmem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static LaunchCache cache;  // per device: shared-memory opt-in and SM count
+    int sms = 0;
+    cudaError_t e = cache.get(reinterpret_cast<const void*>(sign_head_kernel), kHeadThreads, kHeadSmem, &sms, nullptr);
+    if (e != cudaSuccess) return e;
     CUtensorMap map_x, map_w;
-    cudaError_t e = make_map(enc, &map_x, x, rows, kdim, ldx, kHeadTileM);
+    e = make_map(enc, &map_x, x, rows, kdim, ldx, kHeadTileM);
     if (e != cudaSuccess) return e;
     e = make_map(enc, &map_w, w, kHeadN, kdim, ldw, kHeadN);
     if (e != cudaSuccess) return e;
@@ -270,14 +268,6 @@ cudaError_t launch_sign_head(const float* x, int64_t rows, int64_t kdim, int64_t
     p.pool = pool;
     p.rows = rows;
     p.num_kb = (int)((kdim + kHeadKB - 1) / kHeadKB);
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        e = cudaGetDevice(&dev);
-        if (e != cudaSuccess) return e;
-        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return e;
-    }
     const int64_t num_tiles = (rows + kHeadTileM - 1) / kHeadTileM;
     sign_head_kernel<<<(unsigned)(num_tiles < sms ? num_tiles : sms), kHeadThreads, kHeadSmem, st>>>(map_x, map_w, p);
     return cudaGetLastError();

@@ -472,12 +472,9 @@ cudaError_t launch_sign_full(const s3_graph& g, const s3_batch& b, int64_t num_r
     p.ldo = ldo;
     p.row_base = row_base;
     p.node_out = node_out;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(sign_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFullSmemBytes);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static LaunchCache cache;  // the shared-memory opt-in is per device
+    cudaError_t e = cache.get(reinterpret_cast<const void*>(sign_full_kernel), kFullThreads, kFullSmemBytes, nullptr, nullptr);
+    if (e != cudaSuccess) return e;
     p.smem_floats = kFullSmemBytes / 4;
     p.chunks = (p.F1 + kFullCols - 1) / kFullCols;
     if (num_records * p.chunks > 0x7fffffff) return cudaErrorInvalidValue;

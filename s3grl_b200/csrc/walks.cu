@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(kWalkThreads) walk_sets_kernel(const int64_t* 
             const int d = (int)(indptr[cur + 1] - e0);
             if (d > 0) {
                 const uint64_t r = mix64(mix64(seed ^ (uint64_t)s * 0xD1B54A32D192ED03ull) + ((uint64_t)w << 20) + (uint64_t)t);
-                cur = indices[e0 + (int64_t)(((r >> 11) * (uint64_t)d) >> 53)];  // floor(u * d), u in [0,1) with 53 bits
+                cur = indices[e0 + (int64_t)__umul64hi(r, (uint64_t)d)];  // floor(r / 2^64 * d): uniform in [0, d) for any degree
             }
             s_v[w * (rw_m + 1) + t] = cur;
         }

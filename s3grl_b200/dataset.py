@@ -196,21 +196,15 @@ class SEALDataset:
         def run(edges, y):
             return extract_enclosing_subgraphs(edges, A, d.x, y, self.num_hops, self.node_label, self.ratio_per_hop,
                                                self.max_nodes_per_hop, self.directed, None, rw_kwargs, sign_kwargs,
-                                               powers_of_A=powers_of_A, data=d)
-        # keep the operator matrices in HBM between the two calls and the collate (this call only)
-        saved = os.environ.get('S3GRL_OUTPUT_DEVICE')
-        os.environ['S3GRL_OUTPUT_DEVICE'] = 'cuda' if str(self.device) != 'cpu' else 'cpu'
-        try:
-            if not self.pairwise:
-                out = run(pos_edge, 1) + run(neg_edge, 0)
-            elif self.pos_pairwise:
-                out = run(pos_edge, 1)
-            else:
-                out = run(neg_edge, 0)
-        finally:
-            if saved is None:
-                os.environ.pop('S3GRL_OUTPUT_DEVICE', None)
-            else:
-                os.environ['S3GRL_OUTPUT_DEVICE'] = saved
+                                               powers_of_A=powers_of_A, data=d,
+                                               device=None if str(self.device) == 'cpu' else self.device,
+                                               # the operator matrices stay in HBM between the two calls and the collate
+                                               output_device='cuda' if str(self.device) != 'cpu' else 'cpu')
+        if not self.pairwise:
+            out = run(pos_edge, 1) + run(neg_edge, 0)
+        elif self.pos_pairwise:
+            out = run(pos_edge, 1)
+        else:
+            out = run(neg_edge, 0)
         assert isinstance(out, PrecomputedList)
         save_collated(out, self.processed_paths[0])

@@ -180,6 +180,24 @@ def walk_sets_from_cache(cache, nodes, device):
     return sets.to(device), counts.to(device)
 
 
+def pair_links(links, num_nodes, stream=None):
+    """s3_pair_links (csrc/pair.cu) over a device link list [2, L] int64 -> (mirror int64 [L], scratch table).
+    mirror is the chain table described in include/s3grl_b200.h: >= 0 first link of a node pair with the first
+    member of its chain, -1 unpaired, <= -2 member (served by the first link's record).  Keep `table` alive
+    until the stream has run the two kernels."""
+    lib = L.lib()
+    dev = links.device
+    n = int(links.shape[1])
+    slots = int(lib.s3_pair_table_slots(n))
+    table = torch.empty(2 * slots, dtype=torch.int64, device=dev)
+    mirror = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
+    st = stream if stream is not None else torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        L.check(lib.s3_pair_links(_ptr(links[0]), _ptr(links[1]), n, int(num_nodes), _ptr(table), slots, _ptr(mirror),
+                                  C.c_void_p(st.cuda_stream)), 's3_pair_links')
+    return mirror[:n] if n else mirror[:0], table
+
+
 class _Call:
     """One precompute call: validated arguments, per-call device state and the batch schedule.
 
@@ -189,7 +207,8 @@ class _Call:
     owns its output pieces, and the pieces are concatenated at the end."""
 
     def __init__(self, graph, links, num_hops, sign_k, flow, strategy, batch_records, out, return_graphs,
-                 arena_words, stream, profile, overlap, host_out, force_sorted_tier, walk=None, ccn_mode=None):
+                 arena_words, stream, profile, overlap, host_out, force_sorted_tier, walk=None, ccn_mode=None,
+                 pair=True, out_link=None, mirror=None, peers=None):
         self.lib = L.lib()
         if ccn_mode not in (None, 'items', 'chain'):
             raise ValueError("ccn_mode must be None, 'items' or 'chain'")
@@ -209,6 +228,8 @@ class _Call:
         self.links = links.to(device=self.dev, dtype=torch.int64, non_blocking=True).contiguous()
         self.num_links = int(self.links.shape[1])
         self.num_hops, self.K = int(num_hops), int(sign_k)
+        if self.K > L.MAX_K_UNION and strategy == 'union' and flow == 'PoS':
+            raise NotImplementedError(f"PoS Plus union is built for sign_k <= {L.MAX_K_UNION}")
         # ScaLed: per-endpoint random-walk sets replace the h-hop ball
         self.walk = None
         if walk is not None:
@@ -280,8 +301,36 @@ class _Call:
                 words = max(words, graph._arena.numel())
         self.words = max(words, 4 * int(self.lib.s3_min_arena_words(C.byref(graph._c), C.byref(probe))))
         self.out, self.out_ptrs = out, None
+        # link pairing (csrc/pair.cu): one record per unordered node pair, the other direction is a row swap.
+        # Fixed-row PoS on the bitmap tier only; `out_link` / `mirror` / `peers` come from parallel.precompute_exchange
+        # (this call then holds a subset of a larger link list and writes rows at their global positions).
+        tier = int(self.lib.s3_extract_tier(C.byref(graph._c), C.byref(probe)))
+        can_pair = (self.flow == L.FLOW_POS and self.fixed_rows and not self.return_graphs and self.walk is None
+                    and tier == 0)
+        self.pair = bool(pair) and can_pair and mirror is None
+        if (mirror is not None or out_link is not None or peers is not None) and not self.fixed_rows:
+            raise NotImplementedError("out_link / mirror / peers serve the fixed-row flows only")
+        if mirror is not None and not can_pair:
+            mirror = None       # every rank of an exchange takes the same decision: all links are computed directly
+        self.mirror = None if mirror is None else mirror.to(device=self.dev, dtype=torch.int64).contiguous()
+        self.out_link = None if out_link is None else out_link.to(device=self.dev, dtype=torch.int64).contiguous()
+        if self.out_link is not None and self.out_link.numel() != self.num_links:
+            raise ValueError("out_link must hold one global link index per link")
+        self.peers = peers
+        self.total_links = self.num_links      # links of the whole list the output is laid out for
+        if self.mirror is not None:
+            self.total_links = int(self.mirror.numel())
+        elif peers is not None:
+            self.total_links = int(peers.num_links)
+        if self.out_link is None and self.total_links != self.num_links:
+            raise ValueError("a call over a subset of the link list needs out_link")
+        if peers is not None and (host_out is not None or out is not None):
+            raise ValueError("peers owns the output buffers: out / host_out cannot be combined with it")
         self.stats = dict(records=self.num_links * self.rpl, links=self.num_links, sum_n=0, sum_d=0, max_n=0, rows=0,
-                          retries=0, batches=self.num_batches, launches=0)
+                          retries=0, batches=self.num_batches, launches=0, sum_n_links=0, sum_d_links=0, mirrors=0)
+        # inputs above were produced on the current stream; self.stream may be another one
+        self._prep_done = torch.cuda.Event()
+        self._prep_done.record(torch.cuda.current_stream(self.dev))
         self.pieces, self.row_counts = [], []
         self.graphs = [] if self.return_graphs else None
         self.counters = None
@@ -294,11 +343,13 @@ class _Call:
         src = self.links[0, b0:b1] if b1 > b0 else None
         dst = self.links[1, b0:b1] if b1 > b0 else None
         w = self.walk
+        ol = getattr(self, 'out_link', None)
         return L.Batch(_ptr(src), _ptr(dst), b1 - b0, self.flow, self.strategy, self.num_hops, self.K, self.flags, 0,
                        _ptr(arena), arena.numel() if arena is not None else 0, _ptr(off), _ptr(cnt), _ptr(ctr),
                        _ptr(row_ptr), _ptr(item_ptr), _ptr(item_rec), _ptr(order),
                        _ptr(w['sets']) if w else None, _ptr(w['counts']) if w else None,
-                       _ptr(w['src'][b0:]) if w else None, _ptr(w['dst'][b0:]) if w else None, w['cap'] if w else 0, 0)
+                       _ptr(w['src'][b0:]) if w else None, _ptr(w['dst'][b0:]) if w else None, w['cap'] if w else 0, 0,
+                       _ptr(ol[b0:]) if ol is not None and b1 > b0 else None, _ptr(getattr(self, 'mirror', None)), b0)
 
     def launch(self, stage, bi, fn_name, *args, on=None):
         """Call one C entry point; with `profile`, bracket it with CUDA events on its stream."""
@@ -333,6 +384,9 @@ class _Call:
             return False
         self.stats['sum_n'] += int(c[L.CTR_SUM_N])
         self.stats['sum_d'] += int(c[L.CTR_SUM_D])
+        self.stats['sum_n_links'] += int(c[L.CTR_SUM_N_ALL])
+        self.stats['sum_d_links'] += int(c[L.CTR_SUM_D_ALL])
+        self.stats['mirrors'] += int(c[L.CTR_MIRRORS])
         self.stats['max_n'] = max(self.stats['max_n'], int(c[L.CTR_MAX_N]))
         return True
 
@@ -365,6 +419,20 @@ class _Call:
         return off, cnt, order
 
     # ------------------------------------------------------------------ fixed-row flows
+    def pair_links(self):
+        """s3_pair_links over the call's link list -> self.mirror (chain table, see include/s3grl_b200.h)."""
+        self.mirror, self._pair_table = pair_links(self.links, self.graph.num_nodes, self.stream)
+        self.stats['launches'] += 2
+
+    def gather_fixed(self, bi, batch, nrec, row_base, st, on=None):
+        """Kernel 3 of a fixed-row batch: s3_gather into this GPU's matrices, or s3_gather_peers into every GPU's."""
+        g = C.byref(self.graph._c)
+        if self.peers is None:
+            return self.launch('gather', bi, 's3_gather', g, C.byref(batch), nrec, self.out_ptrs, self.F1, row_base, st, on=on)
+        pb = self.peers
+        return self.launch('gather', bi, 's3_gather_peers', g, C.byref(batch), nrec, pb.base_array, pb.world, pb.op_stride,
+                           self.F1, st, on=on)
+
     def enqueue_fixed_batch(self, bi, arena):
         g, st = C.byref(self.graph._c), self.stream_ptr
         b0, b1 = self.bounds(bi)
@@ -374,7 +442,7 @@ class _Call:
         batch = self.make_batch(b0, b1, arena, off, cnt, self.counters[bi], order=order)
         row_base = b0 * self.rpl * self.nseed
         self.launch('extract', bi, 's3_extract', g, C.byref(batch), st)
-        self.launch('gather', bi, 's3_gather', g, C.byref(batch), nrec, self.out_ptrs, self.F1, row_base, st)
+        self.gather_fixed(bi, batch, nrec, row_base, st)
         self.stats['launches'] += 3         # front kernel, order kernel, gather kernel
         if self.host_out is not None:      # pipelined D2H of this batch's rows
             r0, r1 = row_base, b1 * self.rpl * self.nseed
@@ -410,8 +478,7 @@ class _Call:
             front_done = torch.cuda.Event()
             front_done.record(sF)
             sB.wait_event(front_done)
-            self.launch('gather', bi, 's3_gather', g, C.byref(batch), nrec, self.out_ptrs, self.F1,
-                        b0 * self.rpl * self.nseed, pB, on=sB)
+            self.gather_fixed(bi, batch, nrec, b0 * self.rpl * self.nseed, pB, on=sB)
             done = torch.cuda.Event()
             done.record(sB)
             back_done.append(done)
@@ -451,6 +518,11 @@ class _Call:
                 self.sync()
                 host_counters = self.counters.cpu()       # one D2H for every batch's counters
                 todo = [bi for bi, cnt in metas if not self.account(bi, cnt, host_counters)]
+                done = [cnt for bi, cnt in metas if bi not in todo]
+                if self.profile is not None and done:     # nodes per hop over all records: FMA count of kernel 3
+                    hops = sum(cnt[:, L.CNT_HOP0:L.CNT_HOP0 + L.MAX_HOPS + 1].sum(0, dtype=torch.int64) for cnt in done)
+                    prev = self.stats.get('hop_nodes', [0] * (L.MAX_HOPS + 1))
+                    self.stats['hop_nodes'] = [a + int(b) for a, b in zip(prev, hops.cpu())]
                 if not todo:
                     return
                 if self.return_graphs and self.graphs:
@@ -515,6 +587,7 @@ class _Call:
     def run(self, defer):
         dev, K, F1, Lk = self.dev, self.K, self.F1, self.num_links
         with torch.cuda.device(dev), torch.cuda.stream(self.stream):
+            self.stream.wait_event(self._prep_done)
             self.counters = torch.zeros((max(self.num_batches, 1), L.NCTR), dtype=torch.int64, device=dev)
             if self.host_out is not None:
                 self.copy_stream = self.graph.streams()[1]
@@ -522,8 +595,14 @@ class _Call:
                 ready.record(self.stream)
                 self.copy_stream.wait_event(ready)
             if self.fixed_rows:
-                R = 2 * Lk
-                if self.out is None:
+                R = 2 * self.total_links
+                if self.pair and Lk > 1:
+                    self.pair_links()
+                if self.peers is not None:
+                    if not (self.peers.rows >= R and self.peers.cols == F1 and self.peers.num_ops == K + 1):
+                        raise ValueError("peer buffers do not match this call: need K+1 operators of [>= 2L, F+1]")
+                    self.out = self.peers.local
+                elif self.out is None:
                     self.out = [torch.empty((R, F1), dtype=torch.float32, device=dev) for _ in range(K + 1)]
                 elif not (len(self.out) == K + 1 and all(o.shape[0] >= R and o.shape[1] == F1 and o.is_contiguous()
                                                          for o in self.out)):
@@ -531,7 +610,7 @@ class _Call:
                 self.out_ptrs = (C.c_void_p * (K + 1))(*[o.data_ptr() for o in self.out])
                 metas, keep = self.enqueue_fixed(list(range(self.num_batches)))
                 xs = [o[:R] for o in self.out]
-                row_ptr = torch.arange(Lk + 1, dtype=torch.int64, device=dev) * 2
+                row_ptr = torch.arange(self.total_links + 1, dtype=torch.int64, device=dev) * 2
                 self.stats['rows'] = R
                 result = PrecomputeResult(xs, row_ptr, self.stats, self.graphs)
                 result._keep = keep
@@ -549,7 +628,8 @@ class _Call:
 
 def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_records=None, out=None,
                return_graphs=False, arena_words=None, stream=None, profile=None, overlap=False, defer=False,
-               host_out=None, force_sorted_tier=False, walk=None, ccn_mode=None):
+               host_out=None, force_sorted_tier=False, walk=None, ccn_mode=None, pair=True, out_link=None, mirror=None,
+               peers=None):
     """Run the hot path for `links` ([2, L] int64, host or device) on `graph`; returns a
     PrecomputeResult with device tensors.
 
@@ -574,10 +654,16 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
                    rows; 'chain' = s3_ccn_chain (a hop-limited SpMM chain per record, 10x fewer FMAs) for the records
                    that fit its shared-memory placement and work items for the rest.  Measured on PubMed the chain
                    is barrier / latency bound and not faster (profiles/README.md), so it is opt-in.
+    pair           (PoS without CCN rows, bitmap tier) link pairing: links over the same unordered node pair — both
+                   directions of a training edge, SURVEY.md A.7 — share one record; the other direction's rows are
+                   the same rows exchanged, bit for bit (csrc/pair.cu).  On by default; results do not depend on it.
+    out_link, mirror, peers   used by parallel.precompute_exchange: `links` is a subset of a larger list, out_link
+                   its global link indices, mirror the chain table of the whole list and peers the PeerBuffers every
+                   output row is stored into (this GPU's and its NVLink peers').
     Raises ValueError for invalid links (out of range, src == dst), NotImplementedError for an unknown
     strategy (as reference tuned_SIGN.py:235) or an unsupported combination."""
     call = _Call(graph, links, num_hops, sign_k, flow, strategy, batch_records, out, return_graphs, arena_words,
-                 stream, profile, overlap, host_out, force_sorted_tier, walk, ccn_mode)
+                 stream, profile, overlap, host_out, force_sorted_tier, walk, ccn_mode, pair, out_link, mirror, peers)
     return call.run(defer)
 
 
@@ -669,7 +755,10 @@ def precompute_full(graph, links, num_hops, sign_k, node_label='drnl', batch_rec
     return res
 
 
-def algorithmic_bytes(stats, num_feat, sign_k):
-    """SURVEY.md §8d:  sum over links of 4·D + 8·n + 4·F·n + 4·s·(K+1)·(F+1)."""
-    return (4 * stats['sum_d'] + 8 * stats['sum_n'] + 4 * num_feat * stats['sum_n']
-            + 4 * stats['rows'] * (sign_k + 1) * (num_feat + 1))
+def algorithmic_bytes(stats, num_feat, sign_k, per_link=True):
+    """SURVEY.md §8d:  sum over links of 4·D + 8·n + 4·F·n + 4·s·(K+1)·(F+1).
+    per_link=True sums n and D over every LINK served (the survey's definition); per_link=False over the records
+    actually extracted — smaller when link pairing served (v,u) from the record of (u,v)."""
+    n = stats['sum_n_links'] if per_link and stats.get('sum_n_links') else stats['sum_n']
+    d = stats['sum_d_links'] if per_link and stats.get('sum_d_links') else stats['sum_d']
+    return 4 * d + 8 * n + 4 * num_feat * n + 4 * stats['rows'] * (sign_k + 1) * (num_feat + 1)

@@ -3,6 +3,8 @@ replicated, and ONE collective — an allgather of the precomputed operator rows
 holds the whole joint matrix for training.  The reference has no distributed
 code at all; torch.distributed (NCCL on GPUs, gloo in the CPU tests) is plumbing only.
 """
+import ctypes as C
+
 import torch
 import torch.distributed as dist
 
@@ -61,3 +63,112 @@ def precompute_sharded(graph, links, num_hops, sign_k, flow='PoS', strategy=None
         return res.xs, res.row_ptr, res.stats
     xs, row_ptr = allgather_rows(res.xs, res.row_ptr, group)
     return xs, row_ptr, res.stats
+
+
+# ----------------------------------------------------------------------------------------------
+# Fused gather + all-gather over NVLink peer memory (the path's one exchange step)
+# ----------------------------------------------------------------------------------------------
+def cyclic_shard(num_links, rank, world_size):
+    """Global link indices owned by `rank` under the cyclic partition i = rank (mod world): balanced over the
+    link list's blocks (train positives, negatives, ...), over the skew of subgraph sizes and over the paired
+    links that cost nothing.  The shards of all ranks partition range(num_links)."""
+    return range(int(rank), int(num_links), int(world_size))
+
+
+class _DevMem:
+    """Raw device allocation presented through __cuda_array_interface__ so that torch can view it."""
+
+    def __init__(self, ptr, nfloats):
+        self.__cuda_array_interface__ = dict(shape=(int(nfloats),), typestr='<f4', data=(int(ptr), False), version=2)
+
+
+class PeerBuffers:
+    """The K+1 operator matrices [2 * num_links, F+1] of the WHOLE link list on every GPU of the node, each
+    rank's copy mapped into every other rank (csrc/peer.cu: cudaMalloc + CUDA IPC handles exchanged through
+    torch.distributed).  s3_gather_peers stores every output row into all of them, so when the last kernel
+    of a step has finished and the ranks have met at `barrier()`, every GPU holds the complete matrices:
+    the all-gather of SURVEY.md §8e happens inside kernel 3, row by row, overlapped with the computation.
+
+    .local     K+1 torch views [2 * num_links, F+1] of this GPU's copy
+    .bases     device pointers of all ranks' copies (this rank's own at index rank)"""
+
+    def __init__(self, num_links, num_feat, sign_k, device, group=None):
+        from . import _lib as L
+        self._L, self._lib = L, L.lib()
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > L.MAX_PEERS:
+            raise NotImplementedError(f"s3_gather_peers serves up to {L.MAX_PEERS} GPUs of one NVLink domain")
+        self.device = torch.device(device)
+        self.num_links, self.cols, self.num_ops = int(num_links), int(num_feat) + 1, int(sign_k) + 1
+        self.rows = 2 * self.num_links
+        self.op_stride = (self.rows * self.cols + 31) // 32 * 32        # floats; operators start on 128-byte lines
+        nbytes = max(self.num_ops * self.op_stride * 4, 256)
+        self._opened = []
+        with torch.cuda.device(self.device):
+            ptr = C.c_void_p()
+            L.check(self._lib.s3_peer_alloc(nbytes, C.byref(ptr)), 's3_peer_alloc')
+            self._ptr = ptr.value
+            handle = C.create_string_buffer(L.PEER_HANDLE_BYTES)
+            L.check(self._lib.s3_peer_export(C.c_void_p(self._ptr), handle), 's3_peer_export')
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            self.bases = []
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    self.bases.append(self._ptr)
+                    continue
+                p = C.c_void_p()
+                L.check(self._lib.s3_peer_open(C.create_string_buffer(h, L.PEER_HANDLE_BYTES), C.byref(p)), 's3_peer_open')
+                self._opened.append(p.value)
+                self.bases.append(p.value)
+        self.base_array = (C.c_void_p * self.world)(*self.bases)
+        self._mem = _DevMem(self._ptr, self.num_ops * self.op_stride)
+        flat = torch.as_tensor(self._mem, device=self.device)
+        self.local = [flat[k * self.op_stride:k * self.op_stride + self.rows * self.cols].view(self.rows, self.cols)
+                      for k in range(self.num_ops)]
+        self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.barrier()
+
+    def barrier(self):
+        """All ranks' kernels enqueued so far (on the current stream) have finished before any rank's later work
+        on its current stream starts: one tiny NCCL all-reduce, no flag is spun on."""
+        dist.all_reduce(self._flag, group=self.group)
+
+    def close(self):
+        if self._ptr is None:
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)           # nobody may still be storing into a buffer that goes away
+        with torch.cuda.device(self.device):
+            for p in self._opened:
+                self._lib.s3_peer_close(C.c_void_p(p))
+            self.local = None
+            self._lib.s3_peer_free(C.c_void_p(self._ptr))
+        self._ptr, self._opened = None, []
+
+
+def precompute_exchange(graph, links, num_hops, sign_k, buffers, flow='PoS', defer=False, **kw):
+    """Fixed-row flows on all GPUs of the node, with the all-gather fused into kernel 3: every rank gets the
+    WHOLE link list, pairs it (same table on every rank), takes the cyclic shard `rank (mod world)` of it and
+    stores each of its output rows — and the rows of the links paired with them — into every rank's
+    `buffers` at the row of the link's position in the whole list.  After `buffers.barrier()` (called here
+    unless defer=True) buffers.local holds the complete operator matrices on every GPU, bit-identical to a
+    single-GPU precompute of the whole list.  Returns (result of this rank's shard, mirror table)."""
+    from .engine import pair_links, precompute
+    dev = graph.device
+    links = torch.as_tensor(links).to(device=dev, dtype=torch.int64).contiguous()
+    n = int(links.shape[1])
+    if n != buffers.num_links:
+        raise ValueError("buffers were sized for another link list")
+    mirror, table = (None, None)
+    if flow == 'PoS' and n > 1 and not kw.get('walk') and kw.get('pair', True):
+        mirror, table = pair_links(links, graph.num_nodes, kw.get('stream'))
+    kw.pop('pair', None)
+    idx = torch.arange(buffers.rank, n, buffers.world, device=dev, dtype=torch.int64)
+    res = precompute(graph, links[:, idx].contiguous(), num_hops, sign_k, flow, None, out_link=idx, mirror=mirror,
+                     peers=buffers, pair=False, defer=defer, **kw)
+    res._pair_table = table
+    if not defer:
+        buffers.barrier()
+    return res, mirror

@@ -1,8 +1,16 @@
 """Drop-in mirror of the reference's `OptimizedSignOperations` (tuned_SIGN.py:47-262): same
 static-method names, argument order and meaning, same exceptions; the work is done by the
 CUDA path (s3grl_b200.engine.precompute).  Results come back as a `PrecomputedList`
-(a sequence of Data with keys x, y, x1..xK) on `S3GRL_OUTPUT_DEVICE` ('cpu' by default, as the
-reference returns CPU tensors; 'cuda' keeps them in HBM for a GPU-resident loader).
+(a sequence of Data with keys x, y, x1..xK).
+
+Three keyword-only arguments follow the reference's positional ones on every method:
+    device         CUDA device the graph is uploaded to ('cuda' by default)
+    output_device  'cpu' (default: the reference returns CPU tensors; rows are copied to pinned host memory
+                   batch by batch while the next batch computes) or 'cuda' (the operator matrices stay in HBM
+                   for a GPU-resident loader)
+    graph          an engine.DeviceGraph to use instead of uploading (A, x)
+The environment variables S3GRL_DEVICE / S3GRL_OUTPUT_DEVICE only supply the defaults of the first two; nothing
+in the package writes to os.environ.
 """
 import os
 
@@ -14,10 +22,22 @@ from .engine import DeviceGraph, precompute, precompute_full
 _graph_cache = {}
 
 
-def device_graph(A, x, device=None):
+def _default_device(device):
+    return device if device is not None else os.environ.get('S3GRL_DEVICE', 'cuda')
+
+
+def _default_output(output_device):
+    out = output_device if output_device is not None else os.environ.get('S3GRL_OUTPUT_DEVICE', 'cpu')
+    return 'cpu' if str(out) == 'cpu' else 'cuda'
+
+
+def device_graph(A, x, device=None, graph=None):
     """Upload (A, x) once per (matrix, feature) pair; the reference re-uses one A and x across
-    the positive and negative call of a split (sgrl_link_pred.py:193-203)."""
-    device = device or os.environ.get('S3GRL_DEVICE', 'cuda')
+    the positive and negative call of a split (sgrl_link_pred.py:193-203).  The cache holds the one
+    most recent graph and checks identity of A and x (not just their ids); pass `graph=` to bypass it."""
+    if graph is not None:
+        return graph
+    device = _default_device(device)
     key = (id(A), id(x), str(device))
     hit = _graph_cache.get(key)
     if hit is not None and hit[0] is A and hit[1] is x:
@@ -28,16 +48,16 @@ def device_graph(A, x, device=None):
     return g
 
 
-def _host_buffers(num_links, num_feat, K):
+def _host_buffers(num_links, num_feat, K, output_device):
     """Pinned host outputs for a fixed-row flow (2 rows per link), or None when the operator
     matrices are to stay in HBM."""
-    if os.environ.get('S3GRL_OUTPUT_DEVICE', 'cpu') != 'cpu':
+    if _default_output(output_device) != 'cpu':
         return None
     return [torch.empty((2 * num_links, num_feat + 1), dtype=torch.float32, pin_memory=True) for _ in range(K + 1)]
 
 
-def _finish(res, y, host=None):
-    out_dev = os.environ.get('S3GRL_OUTPUT_DEVICE', 'cpu')
+def _finish(res, y, host=None, output_device=None):
+    out_dev = _default_output(output_device)
     xs, row_ptr = res.xs, res.row_ptr
     if host is not None:          # already copied batch by batch, overlapped with the kernels
         return PrecomputedList(host, row_ptr.cpu(), y, res.stats)
@@ -74,29 +94,29 @@ def _reject_unsupported(ratio_per_hop, max_nodes_per_hop, directed, rw_kwargs):
 
 class OptimizedSignOperations:
     @staticmethod
-    def get_SoP_prepped_ds(powers_of_A, link_index, A, x, y):
+    def get_SoP_prepped_ds(powers_of_A, link_index, A, x, y, *, device=None, output_device=None, graph=None):
         """reference tuned_SIGN.py:49.  `powers_of_A` only supplies K = len(powers_of_A): the
         rows Â^k[u,:] are recomputed on the GPU from A by K-hop row propagation instead of
         being read out of global SpGEMM powers (sgrl_link_pred.py:161-178)."""
         K = len(powers_of_A) if not isinstance(powers_of_A, int) else powers_of_A
-        g = device_graph(A, x)
-        host = _host_buffers(int(link_index.shape[1]), g.num_feat, K)
-        return _finish(precompute(g, link_index, 0, K, flow='SoP', host_out=host), y, host)
+        g = device_graph(A, x, device, graph)
+        host = _host_buffers(int(link_index.shape[1]), g.num_feat, K, output_device)
+        return _finish(precompute(g, link_index, 0, K, flow='SoP', host_out=host), y, host, output_device)
 
     @staticmethod
     def get_PoS_prepped_ds(link_index, num_hops, A, ratio_per_hop, max_nodes_per_hop, directed, A_csc, x, y,
-                           sign_kwargs, rw_kwargs):
+                           sign_kwargs, rw_kwargs, *, device=None, output_device=None, graph=None):
         """reference tuned_SIGN.py:137-189."""
         _reject_unsupported(ratio_per_hop, max_nodes_per_hop, directed, rw_kwargs)
         assert x is not None                       # reference tuned_SIGN.py:166
-        g = device_graph(A, x)
-        host = _host_buffers(int(link_index.shape[1]), g.num_feat, sign_kwargs['sign_k'])
+        g = device_graph(A, x, device, graph)
+        host = _host_buffers(int(link_index.shape[1]), g.num_feat, sign_kwargs['sign_k'], output_device)
         return _finish(precompute(g, link_index, num_hops, sign_kwargs['sign_k'], flow='PoS', host_out=host,
-                                  walk=_walk_request(rw_kwargs, y)), y, host)
+                                  walk=_walk_request(rw_kwargs, y)), y, host, output_device)
 
     @staticmethod
     def get_PoS_Plus_prepped_ds(link_index, num_hops, A, ratio_per_hop, max_nodes_per_hop, directed, A_csc, x, y,
-                                sign_kwargs, rw_kwargs):
+                                sign_kwargs, rw_kwargs, *, device=None, output_device=None, graph=None):
         """reference tuned_SIGN.py:192-262.  `union` follows the paper semantics
         sel = [0,1] + sorted((N(0) ∪ N(1)) − {0,1}) (the reference raises for it)."""
         _reject_unsupported(ratio_per_hop, max_nodes_per_hop, directed, rw_kwargs)
@@ -106,21 +126,22 @@ class OptimizedSignOperations:
         strat = sign_kwargs['k_node_set_strategy']
         if strat not in ('union', 'intersection'):
             raise NotImplementedError(f"check strat {strat}")      # reference tuned_SIGN.py:235
-        g = device_graph(A, x)
-        return _finish(precompute(g, link_index, num_hops, sign_kwargs['sign_k'], flow='PoS', strategy=strat), y)
+        g = device_graph(A, x, device, graph)
+        return _finish(precompute(g, link_index, num_hops, sign_kwargs['sign_k'], flow='PoS', strategy=strat), y,
+                       output_device=output_device)
 
     @staticmethod
     def get_PoS_full_ds(link_index, num_hops, A, ratio_per_hop, max_nodes_per_hop, directed, A_csc, x, y,
-                        sign_kwargs, rw_kwargs, node_label='drnl'):
+                        sign_kwargs, rw_kwargs, node_label='drnl', *, device=None, output_device=None, graph=None):
         """The reference's non-optimised PoS branch (utils.py:497-520: k_hop_subgraph ->
         construct_pyg_graph(node_label) -> TunedSIGN(sign_k)(data, sign_k)); it has no method of its own
         in the reference, the name follows its siblings.  Every subgraph node is a row of x, x1..xK;
         `node_id` carries the global ids (canonical order: src, dst, then ascending (hop, id))."""
         _reject_unsupported(ratio_per_hop, max_nodes_per_hop, directed, rw_kwargs)
         assert x is not None, "Node features cannot be None. Check logic."      # reference utils.py:312
-        g = device_graph(A, x)
+        g = device_graph(A, x, device, graph)
         res = precompute_full(g, link_index, num_hops, sign_kwargs['sign_k'], node_label=node_label,
                               walk=_walk_request(rw_kwargs, y))
-        out = _finish(res, y)
+        out = _finish(res, y, output_device=output_device)
         out.extras['node_id'] = res.node_id.to(out.xs[0].device)
         return out

@@ -43,14 +43,17 @@ def test_constants_match_header():
              'S3_CTR_ITEMS': L.CTR_ITEMS, 'S3_REC_BAD_LINK': L.REC_BAD_LINK, 'S3_ERR_NOT_IMPLEMENTED': L.S3_ERR_NOT_IMPLEMENTED,
              'S3_BATCH_STORE_ALL_ROWS': L.BATCH_STORE_ALL_ROWS, 'S3_BATCH_FORCE_SORTED_TIER': L.BATCH_FORCE_SORTED_TIER,
              'S3_BATCH_CCN_CHAIN': L.BATCH_CCN_CHAIN, 'S3_LABEL_ZO': L.LABEL_ZO, 'S3_LABEL_HOP': L.LABEL_HOP,
-             'S3_LABEL_DRNL': L.LABEL_DRNL, 'S3_LABEL_DEGREE': L.LABEL_DEGREE, 'S3_LABEL_ZERO': L.LABEL_ZERO}
+             'S3_LABEL_DRNL': L.LABEL_DRNL, 'S3_LABEL_DEGREE': L.LABEL_DEGREE, 'S3_LABEL_ZERO': L.LABEL_ZERO,
+             'S3_REC_MIRROR': L.REC_MIRROR, 'S3_CTR_SUM_N_ALL': L.CTR_SUM_N_ALL, 'S3_CTR_SUM_D_ALL': L.CTR_SUM_D_ALL,
+             'S3_CTR_MIRRORS': L.CTR_MIRRORS, 'S3_MAX_PEERS': L.MAX_PEERS, 'S3_MAX_K_UNION': L.MAX_K_UNION,
+             'S3_PEER_HANDLE_BYTES': L.PEER_HANDLE_BYTES, 'S3_VERSION': L.VERSION}
     for k, v in pairs.items():
         assert int(defs[k]) == v, k
-    assert ctypes.sizeof(L.Graph) == 64 and ctypes.sizeof(L.Batch) == 160
+    assert ctypes.sizeof(L.Graph) == 64 and ctypes.sizeof(L.Batch) == 184
 
 
 def test_version_and_error_strings(lib):
-    assert lib.s3_version() == 100
+    assert lib.s3_version() == L.VERSION == 200
     assert lib.s3_error_string(0) == b'ok'
     assert b'strategy' in lib.s3_error_string(L.S3_ERR_NOT_IMPLEMENTED)
 

@@ -233,7 +233,7 @@ def test_pubmed_full_size_sample_and_properties():
     for k in range(4):
         a = fwd.xs[k].view(-1, 2, 501)
         b = rev.xs[k].view(-1, 2, 501).flip(1)
-        assert_features_close(a.cpu().numpy(), b.cpu().numpy(), tol=2e-6, what=f'swap x{k}')
+        assert torch.equal(a, b), f"swap x{k}: (u,v) and (v,u) must be the same bits (link pairing relies on it)"
     # oracle on a sample
     ref = orc.pos_precompute(sub[:, :48], 3, A, X, 3, keep_graphs=True)
     got = precompute(g, sub[:, :48], 3, 3, return_graphs=True)
@@ -541,3 +541,95 @@ def test_empty_inputs_on_every_entry_point():
     z = torch.zeros
     out = sign_head(z((0, 24), device='cuda'), z((256, 24), device='cuda'), z(256, device='cuda'), z(256, device='cuda'), z(256, device='cuda'))
     assert out.shape == (0, 256)
+
+
+# ------------------------------------------------------------------------------------------------
+# link pairing (csrc/pair.cu): (u,v) and (v,u) share one record, the second one is an exact row swap
+# ------------------------------------------------------------------------------------------------
+def _pair_reference(links, N):
+    """NumPy restatement of the chain table's contract: classes of links over the same unordered node pair."""
+    first, members = {}, {}
+    for i, (u, v) in enumerate(links.T.tolist()):
+        if u < 0 or v < 0 or u >= N or v >= N or u == v:
+            continue
+        key = (min(u, v), max(u, v))
+        if key in first:
+            members[first[key]].append(i)
+        else:
+            first[key] = i
+            members[i] = []
+    return members
+
+
+def test_pair_links_chain_table():
+    from s3grl_b200.engine import pair_links
+    rng = np.random.default_rng(7)
+    N = 50
+    base = rng.integers(0, N, (2, 400))
+    links = np.concatenate([base, base[::-1][:, ::3], base[:, ::5], np.array([[3, -1, N, 9], [3, 4, 5, 9]])], axis=1)
+    links = links[:, rng.permutation(links.shape[1])]
+    mirror, _table = pair_links(torch.from_numpy(links).cuda(), N)
+    m = mirror.cpu().numpy()
+    ref = _pair_reference(links, N)
+    seen = set()
+    for p, mem in ref.items():
+        chain, j = [], m[p]
+        assert j >= -1, f'link {p} keeps the work'
+        while j >= 0:
+            v = -2 - m[j]
+            assert v >= 0
+            assert (v & 1) == int(links[0, j] != links[0, p]), 'swap bit = opposite direction'
+            chain.append(int(j))
+            j = (v >> 1) - 1
+        assert sorted(chain) == mem, f'chain of link {p}'
+        seen.update(chain)
+        seen.add(p)
+    for i in range(links.shape[1]):          # invalid links stay unpaired
+        if i not in seen:
+            assert m[i] == -1
+
+
+def test_pairing_is_bit_exact_and_independent_of_batching():
+    """PubMed-shaped train positives hold both directions of every edge.  With pairing the reverse link's rows are
+    written by the forward link's record; the result must be the same BITS as without pairing, for any batch
+    size, and a sub-list (different pairs available) must reproduce the same bits as the full list."""
+    edges, N, X = ds.load_graph('cora')
+    X = ds.normalize_features(X)
+    A, splits = ds.split_links(edges, N, seed=1)
+    links = ds.all_links(splits)[:, :6000]
+    g = DeviceGraph(A, X)
+    plain = precompute(g, links, 3, 3, pair=False)
+    paired = precompute(g, links, 3, 3, pair=True)
+    assert paired.stats['mirrors'] > 500 and plain.stats['mirrors'] == 0
+    assert paired.stats['sum_n_links'] == plain.stats['sum_n'] == plain.stats['sum_n_links']
+    assert paired.stats['sum_n'] < plain.stats['sum_n']
+    small = precompute(g, links, 3, 3, pair=True, batch_records=700)
+    for k in range(4):
+        assert torch.equal(plain.xs[k], paired.xs[k]), f'x{k}: pairing changed bits'
+        assert torch.equal(plain.xs[k], small.xs[k]), f'x{k}: batch size changed bits'
+    sub = np.ascontiguousarray(links[:, 1000:3000])
+    part = precompute(g, sub, 3, 3)
+    for k in range(4):
+        assert torch.equal(part.xs[k], paired.xs[k][2000:6000])
+    # (u,v) against (v,u): exact row swap
+    rev = precompute(g, np.ascontiguousarray(links[::-1]), 3, 3, pair=False)
+    for k in range(4):
+        assert torch.equal(plain.xs[k].view(-1, 2, X.shape[1] + 1), rev.xs[k].view(-1, 2, X.shape[1] + 1).flip(1))
+
+
+def test_pairing_with_host_output_and_overlap():
+    """Rows of a paired link are written by an EARLIER batch: the pipelined device-to-host copy of its own batch
+    and the two-stream schedule must still see them."""
+    edges, N, X = ds.load_graph('cora')
+    X = ds.normalize_features(X)
+    A, splits = ds.split_links(edges, N, seed=1)
+    links = ds.all_links(splits)[:, :5000]
+    g = DeviceGraph(A, X)
+    want = precompute(g, links, 3, 3, pair=False)
+    host = [torch.empty((2 * links.shape[1], X.shape[1] + 1), dtype=torch.float32, pin_memory=True) for _ in range(4)]
+    precompute(g, links, 3, 3, host_out=host, batch_records=1024)
+    torch.cuda.synchronize()
+    over = precompute(g, links, 3, 3, overlap=True, batch_records=1024)
+    for k in range(4):
+        assert torch.equal(host[k], want.xs[k].cpu())
+        assert torch.equal(over.xs[k], want.xs[k])
