@@ -443,6 +443,9 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
     stage_ms = {}
     for stage, bi, ea, eb in profile:
         stage_ms.setdefault(stage, []).append(ea.elapsed_time(eb))
+    if os.environ.get('S3GRL_BENCH_DEBUG'):
+        for stage, v in stage_ms.items():
+            print(stage, [round(t_, 2) for t_ in v[:3 * res.stats['batches']]], file=sys.stderr)
     st = res.stats
     peaks = {}
     try:

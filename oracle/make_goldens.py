@@ -68,6 +68,9 @@ def make_case(name, A, links, flow, K, num_hops=0, strategy=None, X=None, x_spec
     elif flow == 'sop':
         r = rr.ref_sop(links, A, feats, K)
         extra = {}
+    elif flow == 'hybrid':
+        r = rr.ref_hybrid(links, num_hops, A, feats, K)
+        extra = {}
     else:
         raise ValueError(flow)
     out = dict(indptr=A.indptr.astype(np.int64), indices=A.indices.astype(np.int32),
@@ -193,8 +196,28 @@ def sample_links(splits, count, seed):
     return links[:, pick]
 
 
+def round2_cases():
+    """Fixtures added in round 2 (VERDICT r1 "parity holes"): the hybrid flow, the headline PubMed graph with the
+    bench's F = 500 feature spec (PoS and PoS Plus intersection), and Router (BASELINE config 4)."""
+    A, links, X = tiny_graphs()
+    make_case('tiny_hybrid', A, links, 'hybrid', 3, 2, None, X=X)
+    edges, N, _ = ds.load_graph('usair')
+    A, splits = ds.split_links(edges, N, seed=1)
+    make_case('usair_hybrid', A, sample_links(splits, 40, 5), 'hybrid', 3, 2, None, x_spec='synthetic:16:0.5:6')
+    edges, N, _ = ds.load_graph('pubmed')
+    A, splits = ds.split_links(edges, N, seed=1)
+    make_case('pubmed_pos', A, sample_links(splits, 24, 11), 'pos', 3, 3, None, x_spec='synthetic:500:0.1:0')
+    make_case('pubmed_posplus', A, sample_links(splits, 24, 12), 'pos', 3, 3, 'intersection', x_spec='synthetic:500:0.1:0')
+    edges, N, _ = ds.load_graph('router')
+    A, splits = ds.split_links(edges, N, seed=1)
+    make_case('router_pos_k5', A, sample_links(splits, 60, 13), 'pos', 5, 2, None, x_spec='synthetic:32:0.5:8')
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if '--round2' in sys.argv:          # only the fixtures added in round 2 (the others are unchanged)
+        round2_cases()
+        return
     make_posneg_case()
     A, links, X = tiny_graphs()
     for h in (1, 2, 3):
@@ -230,6 +253,7 @@ def main():
     edges, N, _ = ds.load_graph('power')
     A, splits = ds.split_links(edges, N, seed=1)
     make_case('power_pos_k5', A, sample_links(splits, 100, 4), 'pos', 5, 2, None, x_spec='synthetic:8:1.0:9')
+    round2_cases()
 
 
 if __name__ == '__main__':

@@ -149,6 +149,23 @@ def ref_sop(links, A, X, K):
     return dict(xs=xs, row_ptr=np.arange(len(data_list) + 1, dtype=np.int64) * 2)
 
 
+def ref_hybrid(links, num_hops, A, X, K):
+    """The hybrid flow (utils.py:454-480) through the reference's own dispatcher: PoS x, x1..xK followed by the SoP
+    operators x2..xK stored as x{K+1}..x{2K-1} -> dict(xs (2K operators), row_ptr)."""
+    utils, tuned = load_reference()
+    link_index = torch.as_tensor(np.asarray(links), dtype=torch.long)
+    x = torch.as_tensor(np.asarray(X), dtype=torch.float32)
+    kw = {'sign_k': K, 'use_feature': True, 'sign_type': 'hybrid', 'optimize_sign': True, 'k_heuristic': 0,
+          'k_node_set_strategy': None}
+    powers = ref_sop_powers(A, K)
+    with _quiet():
+        data_list = utils.extract_enclosing_subgraphs(link_index, A, x, 1, num_hops, 'zo', 1.0, None, False, None, None, kw,
+                                                      powers_of_A=powers, data=None)
+    keys = ['x'] + [f'x{k}' for k in range(1, 2 * K)]
+    xs = [np.concatenate([np.asarray(d[key], dtype=np.float32) for d in data_list], 0) for key in keys]
+    return dict(xs=xs, row_ptr=np.arange(len(data_list) + 1, dtype=np.int64) * 2)
+
+
 def ref_scaled_pos(links, A, X, K, sets):
     """ScaLed through the reference's own code: get_PoS_prepped_ds with rw_kwargs carrying a walk
     cache (utils.py:94-105 picks cached_pos_rws for y = 1) -> dict(xs, row_ptr).  `sets` is

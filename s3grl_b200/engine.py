@@ -186,6 +186,9 @@ def pair_links(links, num_nodes, stream=None):
     member of its chain, -1 unpaired, <= -2 member (served by the first link's record).  Keep `table` alive
     until the stream has run the two kernels."""
     lib = L.lib()
+    if links.dim() != 2 or links.shape[0] != 2 or links.dtype != torch.int64 or not links.is_cuda:
+        raise ValueError("links must be a [2, L] int64 CUDA tensor")
+    links = links.contiguous()
     dev = links.device
     n = int(links.shape[1])
     slots = int(lib.s3_pair_table_slots(n))

@@ -45,7 +45,8 @@ class Case:
         self.strategy = str(d['strategy']) or None
         self.X = d['X'] if 'X' in d.files else features_from_spec(str(d['x_spec']), self.A, self.N)
         self.row_ptr = d['row_ptr']
-        self.xs = [d[f'x{k}'] for k in range(self.K + 1)]
+        self.num_ops = 2 * self.K if self.flow == 'hybrid' else self.K + 1      # hybrid: x, x1..xK, then SoP x2..xK
+        self.xs = [d[f'x{k}'] for k in range(self.num_ops)]
         if self.flow == 'scaled':
             self.sets = {int(k): row[row >= 0].astype(np.int64) for k, row in zip(d['set_nodes'], d['set_table'])}
             self.rw_m, self.rw_M = int(d['rw_m']), int(d['rw_M'])

@@ -633,3 +633,33 @@ def test_pairing_with_host_output_and_overlap():
     for k in range(4):
         assert torch.equal(host[k], want.xs[k].cpu())
         assert torch.equal(over.xs[k], want.xs[k])
+
+
+@pytest.mark.parametrize('name', case_names('hybrid'))
+def test_hybrid_against_reference_goldens(name):
+    """SURVEY.md §8a row 11 pinned by the reference itself: utils.py:454-480 (sign_type='hybrid') ran through
+    oracle/ref_runner.py produced the fixture; here the CUDA path goes through the mirrored dispatcher."""
+    from s3grl_b200 import extract_enclosing_subgraphs
+    c = Case(name)
+    sign_kwargs = dict(sign_k=c.K, use_feature=True, sign_type='hybrid', optimize_sign=True, k_heuristic=0,
+                       k_node_set_strategy=None)
+    out = extract_enclosing_subgraphs(torch.from_numpy(c.links), c.A, torch.from_numpy(c.X), 1, c.num_hops, 'zo', 1.0, None,
+                                      False, None, None, sign_kwargs, powers_of_A=[None] * c.K, data=None)
+    assert len(out.xs) == 2 * c.K and np.array_equal(out.row_ptr.cpu().numpy(), c.row_ptr)
+    for k in range(2 * c.K):
+        assert_features_close(out.xs[k].cpu().numpy(), c.xs[k], what=f'{name} x{k}')
+
+
+def test_explicit_device_and_output_arguments():
+    """device= / output_device= / graph= replace the process-global switches of round 1."""
+    from s3grl_b200 import extract_enclosing_subgraphs
+    c = Case('cora_pos')
+    kw = dict(sign_k=c.K, use_feature=True, sign_type='PoS', optimize_sign=True, k_heuristic=0, k_node_set_strategy=None)
+    args = (torch.from_numpy(c.links[:, :20]), c.A, torch.from_numpy(c.X), 1, c.num_hops, 'zo', 1.0, None, False, None, None, kw)
+    on_host = extract_enclosing_subgraphs(*args, powers_of_A=[], data=None)
+    on_dev = extract_enclosing_subgraphs(*args, powers_of_A=[], data=None, device='cuda:0', output_device='cuda')
+    g = DeviceGraph(c.A, c.X)
+    with_graph = extract_enclosing_subgraphs(*args, powers_of_A=[], data=None, graph=g, output_device='cuda')
+    assert not on_host.xs[0].is_cuda and on_dev.xs[0].is_cuda and with_graph.xs[0].is_cuda
+    for k in range(c.K + 1):
+        assert torch.equal(on_host.xs[k], on_dev.xs[k].cpu()) and torch.equal(on_dev.xs[k], with_graph.xs[k])

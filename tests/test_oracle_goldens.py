@@ -34,6 +34,18 @@ def test_sop_matches_reference(name):
         assert_features_close(out['xs'][k], c.xs[k], what=f'{name} x{k}')
 
 
+@pytest.mark.parametrize('name', case_names('hybrid'))
+def test_hybrid_matches_reference(name):
+    """the reference's own dispatcher (utils.py:454-480) with sign_type='hybrid' — PoS x, x1..xK
+    then the SoP operators x2..xK as x{K+1}..x{2K-1}."""
+    c = Case(name)
+    out = orc.hybrid_precompute(c.links, c.num_hops, c.A, c.X, c.K)
+    assert len(out['xs']) == 2 * c.K == len(c.xs)
+    assert np.array_equal(out['row_ptr'], c.row_ptr)
+    for k in range(2 * c.K):
+        assert_features_close(out['xs'][k], c.xs[k], what=f'{name} x{k}')
+
+
 def test_union_rule_is_superset_of_intersection():
     c = Case('usair_posplus')
     inter = orc.pos_precompute(c.links[:, :20], c.num_hops, c.A, c.X, c.K, 'intersection', keep_graphs=True)
