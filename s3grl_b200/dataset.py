@@ -73,41 +73,46 @@ def do_edge_split(data, fast_split=False, val_ratio=0.05, test_ratio=0.1, neg_ra
     return split_edge
 
 
+def _keep(count, percent):
+    """Indices kept from a list of `count` links: a NumPy permutation (global RNG, as the reference draws it)
+    cut to `percent` per cent.  One draw per call: the order of the calls fixes the link order."""
+    order = np.random.permutation(count)
+    return order[:int(percent / 100 * count)]
+
+
 def get_pos_neg_edges(split, split_edge, edge_index, num_nodes, percent=100, neg_ratio=1, neg_seed=0):
-    """reference utils.py:637-678, branch for branch; the two `np.random.permutation` calls per branch happen in
-    the reference's order, so with the same NumPy seed and pre-sampled negatives (`edge_neg`, or the
-    `source_node` format) the link ORDER — which fixes the output row order — is identical."""
-    if 'edge' in split_edge['train']:
-        pos_edge = split_edge[split]['edge'].t()
-        if 'edge_neg' in split_edge['train']:
-            neg_edge = split_edge[split]['edge_neg'].t()
+    """Positive and negative target links of one split, [2, L] each, in the order the hot path will emit rows.
+
+    Mirrors the behaviour of reference utils.py:637-678 for both split-dictionary layouts:
+      * 'edge' layout — positives from `edge`, negatives from `edge_neg` when present (else sampled by
+        `sample_negative_edges`); positives are subsampled first, then negatives, each with its own permutation;
+      * 'source_node' layout (OGB citation style) — one permutation shared by source / target / negative targets;
+        training negatives are drawn uniformly per source with torch.randint, evaluation negatives come from
+        `target_node_neg`; every source is repeated once per negative target.
+    With the same NumPy seed the link ORDER equals the reference's (tests/golden/posneg_edges_ref.npz)."""
+    layout = split_edge['train']
+    part = split_edge[split]
+    if 'edge' in layout:
+        pos = part['edge'].t()
+        if 'edge_neg' in layout:
+            neg = part['edge_neg'].t()
         else:
-            neg_edge = sample_negative_edges(edge_index, num_nodes, pos_edge.size(1) * neg_ratio, neg_seed)
-        num_pos = pos_edge.size(1)
-        perm = np.random.permutation(num_pos)
-        perm = perm[:int(percent / 100 * num_pos)]
-        pos_edge = pos_edge[:, perm]
-        num_neg = neg_edge.size(1)
-        perm = np.random.permutation(num_neg)
-        perm = perm[:int(percent / 100 * num_neg)]
-        neg_edge = neg_edge[:, perm]
-    elif 'source_node' in split_edge['train']:
-        source = split_edge[split]['source_node']
-        target = split_edge[split]['target_node']
+            neg = sample_negative_edges(edge_index, num_nodes, pos.size(1) * neg_ratio, neg_seed)
+        pos = pos[:, _keep(pos.size(1), percent)]
+        neg = neg[:, _keep(neg.size(1), percent)]
+        return pos, neg
+    if 'source_node' in layout:
+        src, dst = part['source_node'], part['target_node']
         if split == 'train':
-            target_neg = torch.randint(0, num_nodes, [target.size(0), 1], dtype=torch.long)
+            dst_neg = torch.randint(0, num_nodes, [dst.size(0), 1], dtype=torch.long)
         else:
-            target_neg = split_edge[split]['target_node_neg']
-        num_source = source.size(0)
-        perm = np.random.permutation(num_source)
-        perm = perm[:int(percent / 100 * num_source)]
-        source, target, target_neg = source[perm], target[perm], target_neg[perm, :]
-        pos_edge = torch.stack([source, target])
-        neg_per_target = target_neg.size(1)
-        neg_edge = torch.stack([source.repeat_interleave(neg_per_target), target_neg.view(-1)])
-    else:
-        raise KeyError("split_edge has neither 'edge' nor 'source_node' entries")
-    return pos_edge, neg_edge
+            dst_neg = part['target_node_neg']
+        kept = _keep(src.size(0), percent)
+        src, dst, dst_neg = src[kept], dst[kept], dst_neg[kept, :]
+        pos = torch.stack([src, dst])
+        neg = torch.stack([src.repeat_interleave(dst_neg.size(1)), dst_neg.reshape(-1)])
+        return pos, neg
+    raise KeyError("split_edge has neither 'edge' nor 'source_node' entries")
 
 
 class SEALDataset:
