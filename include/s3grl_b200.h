@@ -322,6 +322,25 @@ int s3_peer_export(void* ptr, unsigned char* handle /* [S3_PEER_HANDLE_BYTES] */
 int s3_peer_open(const unsigned char* handle, void** ptr);
 int s3_peer_close(void* ptr);
 
+/* CCN segment pooling on the GPU (north_star kernel 3 "center / CCN pooling"; reference models.py:339-367,
+ * SIGNNet._centre_pool_helper with k_heuristic: the center product h_src * h_dst next to global_mean_pool /
+ * global_add_pool of a link's rows beyond its two targets). src [R, ld_src] row-major with num_cols valid columns,
+ * rows grouped per link by row_ptr [num_links + 1] (row 0 = src, row 1 = dst, rows 2.. = CCN rows). One output row
+ * per link, out [num_links, ld_out]:
+ *   S3_POOL_OUT_CENTER  [ src * dst | pool(rows 2..) ]   2 * num_cols   (the input of link_pred_mlp, models.py:357-362)
+ *   S3_POOL_OUT_ROWS    [ src | dst | pool(rows 2..) ]   3 * num_cols   (pooled output mode of the precompute path:
+ *                                                                        pooling operator rows BEFORE the MLP is a
+ *                                                                        different model than the reference's)
+ * mode S3_POOL_SUM / S3_POOL_MEAN (k_pool_strategy 'sum' / 'mean'; an empty segment gives zeros, as torch_scatter
+ * does; 'concat' needs exactly k_heuristic extra rows per link, which PoS Plus does not guarantee: not built).
+ * Rows are added in ascending order: results are bit-reproducible. */
+#define S3_POOL_SUM 1
+#define S3_POOL_MEAN 2
+#define S3_POOL_OUT_CENTER 0
+#define S3_POOL_OUT_ROWS 1
+int s3_segment_pool(const float* src, int64_t ld_src, int64_t num_cols, const int64_t* row_ptr, int64_t num_links, int32_t mode,
+                    int32_t layout, float* out, int64_t ld_out, void* stream);
+
 /* Measurement aids (bench.py roofline): the L2 -> SM read bandwidth (the grid streams an L2-sized buffer `iters`
  * times with 128-bit L1-bypassing loads: bytes * iters per launch) and the FP32 FMA issue rate
  * (ctas * 256 threads * iters * 128 FMAs per launch). Nothing on the product path calls them. */

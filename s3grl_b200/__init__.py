@@ -12,9 +12,9 @@ The compute lives in lib/libs3grl_b200.so (include/s3grl_b200.h); build it with
 __version__ = '0.1.0'
 
 from .data import Data, PrecomputedList  # noqa: F401
-from .engine import DeviceGraph, PrecomputeResult, algorithmic_bytes, precompute, precompute_full, walk_sets  # noqa: F401
+from .engine import DeviceGraph, PrecomputeResult, algorithmic_bytes, pool_rows, precompute, precompute_full, walk_sets  # noqa: F401
 from .tuned_sign import OptimizedSignOperations  # noqa: F401
 from .utils import extract_enclosing_subgraphs  # noqa: F401
 from .loader import JointLoader, joint_rows, load_collated, save_collated  # noqa: F401
 from .dataset import SEALDataset, do_edge_split, get_pos_neg_edges  # noqa: F401
-from .head import fold_batchnorm, sign_head  # noqa: F401
+from .head import fold_batchnorm, segment_pool, sign_head, sign_head_ccn  # noqa: F401

@@ -193,6 +193,19 @@ int s3_pair_links(const int64_t* link_src, const int64_t* link_dst, int64_t num_
     return e == cudaSuccess ? S3_OK : cuda_fail(e);
 }
 
+int s3_segment_pool(const float* src, int64_t ld_src, int64_t num_cols, const int64_t* row_ptr, int64_t num_links, int32_t mode,
+                    int32_t layout, float* out, int64_t ld_out, void* stream) {
+    if (mode != S3_POOL_SUM && mode != S3_POOL_MEAN) return S3_ERR_NOT_IMPLEMENTED;  // reference: "Check pool strat" (models.py:333)
+    if (layout != S3_POOL_OUT_CENTER && layout != S3_POOL_OUT_ROWS) return S3_ERR_INVALID_ARG;
+    const int64_t width = (layout == S3_POOL_OUT_CENTER ? 2 : 3) * num_cols;
+    if (num_links < 0 || num_cols < 1 || num_cols > INT32_MAX / 4 || ld_src < num_cols || ld_out < width) return S3_ERR_INVALID_ARG;
+    if (num_links > 0 && (!src || !row_ptr || !out)) return S3_ERR_INVALID_ARG;
+    if (num_links > INT32_MAX) return S3_ERR_INVALID_ARG;
+    cudaError_t e = s3::launch_segment_pool(src, ld_src, num_cols, row_ptr, num_links, mode, layout, out, ld_out,
+                                            static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? S3_OK : cuda_fail(e);
+}
+
 int s3_probe_l2_read(const float* buf, int64_t bytes, int32_t iters, float* sink, int32_t ctas, void* stream) {
     if (!buf || !sink || bytes < 16 * 1024 || (bytes & 15) || iters < 1 || ctas < 1 || (reinterpret_cast<uintptr_t>(buf) & 15))
         return S3_ERR_INVALID_ARG;

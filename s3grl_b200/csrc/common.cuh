@@ -145,6 +145,8 @@ cudaError_t launch_gather(const s3_graph& g, const s3_batch& b, int64_t num_item
                           int64_t ldo, int64_t row_base, bool ccn, cudaStream_t st, const PeerDst* peers = nullptr);
 cudaError_t launch_pair_links(const int64_t* src, const int64_t* dst, int64_t L, int64_t N, int64_t* table, int64_t slots,
                               int64_t* mirror, cudaStream_t st);
+cudaError_t launch_segment_pool(const float* src, int64_t ld, int64_t cols, const int64_t* row_ptr, int64_t num_links, int mode,
+                                int layout, float* out, int64_t ld_out, cudaStream_t st);
 cudaError_t launch_probe_l2_read(const float* buf, int64_t bytes, int iters, float* sink, int ctas, cudaStream_t st);
 cudaError_t launch_probe_fma(int iters, float* sink, int ctas, cudaStream_t st);
 cudaError_t peer_alloc(int64_t bytes, void** ptr);

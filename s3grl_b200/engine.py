@@ -758,6 +758,20 @@ def precompute_full(graph, links, num_hops, sign_k, node_label='drnl', batch_rec
     return res
 
 
+def pool_rows(result, mode='sum'):
+    """Pooled output mode (SURVEY.md §7 'pooling semantics'): every link keeps three rows per operator —
+    src, dst and the sum / mean of its CCN rows — instead of 2 + #CCN.  Runs s3_segment_pool over each operator
+    matrix of a PoS Plus result and returns a PrecomputeResult with xs[k] [3L, F+1], row_ptr = 3 * arange.
+    NOTE: this pools operator rows BEFORE the model's MLP, which is a different model than the reference's
+    (it pools hidden rows, models.py:347-362); the parity check is "reduce the oracle's rows"."""
+    from .head import segment_pool
+    nl = int(result.row_ptr.numel()) - 1
+    xs = [segment_pool(x, result.row_ptr, mode, 'rows').view(3 * nl, x.shape[1]) for x in result.xs]
+    row_ptr = torch.arange(nl + 1, dtype=torch.int64, device=result.row_ptr.device) * 3
+    stats = dict(result.stats, rows=3 * nl, pooled=mode)
+    return PrecomputeResult(xs, row_ptr, stats, result.graphs)
+
+
 def algorithmic_bytes(stats, num_feat, sign_k, per_link=True):
     """SURVEY.md §8d:  sum over links of 4·D + 8·n + 4·F·n + 4·s·(K+1)·(F+1).
     per_link=True sums n and D over every LINK served (the survey's definition); per_link=False over the records

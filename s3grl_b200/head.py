@@ -61,3 +61,45 @@ def sign_head(joint, lin_weight, lin_bias, bn_scale, bn_shift, out=None, stream=
                                  p(lin_bias), p(bn_scale), p(bn_shift), p(out), 1 if pool else 0,
                                  C.c_void_p(st.cuda_stream)), 's3_sign_head')
     return out
+
+
+_POOL = {'sum': L.POOL_SUM, 'mean': L.POOL_MEAN}
+
+
+def segment_pool(rows, row_ptr, mode='mean', layout='center', out=None, stream=None):
+    """CCN pooling on the GPU (csrc/pool.cu; reference models.py:339-367 with k_heuristic set).
+
+    rows [R, C] float32 CUDA tensor grouped per link by row_ptr [L+1] (row 0 = src, row 1 = dst, rows 2.. = CCN rows).
+    layout 'center' -> [L, 2C] = [src * dst | pool(rows 2..)]  (the input of SIGNNet.link_pred_mlp);
+    layout 'rows'   -> [L, 3C] = [src | dst | pool(rows 2..)]  (pooled output mode of the precompute path).
+    mode 'mean' | 'sum' (k_pool_strategy); anything else raises NotImplementedError as models.py:333 does
+    ('concat' needs exactly k_heuristic extra rows per link, which PoS Plus does not guarantee)."""
+    if mode not in _POOL:
+        raise NotImplementedError(f"Check pool strat: {mode}")
+    if layout not in ('center', 'rows'):
+        raise ValueError("layout must be 'center' or 'rows'")
+    lib = L.lib()
+    dev = rows.device
+    if dev.type != 'cuda' or rows.dtype != torch.float32 or rows.dim() != 2 or rows.stride(1) != 1:
+        raise ValueError("rows must be a [R, C] float32 CUDA tensor with unit column stride (no CPU path)")
+    row_ptr = row_ptr.to(device=dev, dtype=torch.int64).contiguous()
+    nl, cols = int(row_ptr.numel()) - 1, int(rows.shape[1])
+    width = (2 if layout == 'center' else 3) * cols
+    if out is None:
+        out = torch.empty((nl, width), dtype=torch.float32, device=dev)
+    st = stream if stream is not None else torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        L.check(lib.s3_segment_pool(C.c_void_p(rows.data_ptr()), int(rows.stride(0)) if rows.shape[0] > 1 else cols, cols,
+                                    C.c_void_p(row_ptr.data_ptr()), nl, _POOL[mode],
+                                    L.POOL_OUT_CENTER if layout == 'center' else L.POOL_OUT_ROWS,
+                                    C.c_void_p(out.data_ptr()), int(out.stride(0)) if nl > 1 else width,
+                                    C.c_void_p(st.cuda_stream)), 's3_segment_pool')
+    return out
+
+
+def sign_head_ccn(joint, row_ptr, lin_weight, lin_bias, bn_scale, bn_shift, k_pool_strategy='mean', stream=None):
+    """SIGNNet.forward up to link_pred_mlp for the PoS Plus flows (models.py:370-376 + :347-362), evaluation mode:
+    h = bn(elu(joint W^T + b)) on the tensor cores (s3_sign_head, pool = 0), then per link
+    [h_src * h_dst | mean or sum of its CCN rows' h] on the GPU (s3_segment_pool) -> [L, 512]."""
+    h = sign_head(joint, lin_weight, lin_bias, bn_scale, bn_shift, stream=stream, pool=False)
+    return segment_pool(h, row_ptr, k_pool_strategy, 'center', stream=stream)
