@@ -360,7 +360,8 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
     a, b = (0, Lk) if (world == 1 or exchange) else shard_range(Lk, rank, world)
     links_dev = (w['links_dev'] if is_rmat else torch.from_numpy(np.ascontiguousarray(links_all)).to(dev))[:, a:b].contiguous()
     Lmine = b - a
-    buffers = PeerBuffers(Lk, F, K, dev) if exchange else None
+    buffers = PeerBuffers(Lk, F, K, dev, backend=args.exchange_backend) if exchange else None
+    exchange_backend = buffers.backend if exchange else None
     out = ([torch.empty((2 * Lk, F + 1), dtype=torch.float32, device=dev) for _ in range(K + 1)]
            if fixed and not exchange else None)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
@@ -431,9 +432,13 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
         same = torch.tensor([int(all(torch.equal(buffers.local[k], check.xs[k]) for k in range(K + 1)))], device=dev)
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
         rows_mine = 2 * (res.stats['links'])
-        nv = rows_mine * (K + 1) * (F + 1) * 4 * (world - 1)
-        exch = dict(kind="s3_gather_peers: kernel 3 stores every output row into all ranks' matrices (NVLink peer memory, "
-                         "CUDA IPC); the timed region ends with one 4-byte NCCL all-reduce per step as the barrier",
+        # NVLink egress of a rank: its rows once through the NVSwitch multicast object, or once per peer over P2P
+        nv = rows_mine * (K + 1) * (F + 1) * 4 * (1 if exchange_backend == 'multicast' else world - 1)
+        exch = dict(kind="s3_gather_peers: kernel 3 stores every output row into all ranks' matrices ("
+                         + ("one store to an NVSwitch multicast address, torch symmetric memory as plumbing" if exchange_backend == 'multicast'
+                            else "one store per peer over NVLink P2P, cudaMalloc + CUDA IPC")
+                         + "); the timed region ends with one 4-byte NCCL all-reduce per step as the barrier",
+                    backend=exchange_backend,
                     equal_to_single_gpu_bitwise=bool(int(same)), nvlink_bytes_out_per_rank_per_step=int(nv),
                     nvlink_GBps_out_per_rank=nv * steps / (ms_max / 1e3) / 1e9, nvlink_peak_GBps=770.0,
                     nvlink_peak_source="B200_PROFILING.md: measured peer copy, per direction per GPU")
@@ -631,6 +636,7 @@ def main():
     ap.add_argument('--rmat-edges', type=int, default=200_000_000)
     ap.add_argument('--rmat-links', type=int, default=4_000_000)
     ap.add_argument('--rmat-degree-cap', type=int, default=512)
+    ap.add_argument('--exchange-backend', default='auto', choices=['auto', 'multicast', 'ipc'])
     ap.add_argument('--overlap', action='store_true', help='two-stream schedule: front kernel of batch i+1 beside kernel 3 of batch i')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))

@@ -84,15 +84,21 @@ class _DevMem:
 
 class PeerBuffers:
     """The K+1 operator matrices [2 * num_links, F+1] of the WHOLE link list on every GPU of the node, each
-    rank's copy mapped into every other rank (csrc/peer.cu: cudaMalloc + CUDA IPC handles exchanged through
-    torch.distributed).  s3_gather_peers stores every output row into all of them, so when the last kernel
-    of a step has finished and the ranks have met at `barrier()`, every GPU holds the complete matrices:
-    the all-gather of SURVEY.md §8e happens inside kernel 3, row by row, overlapped with the computation.
+    rank's copy reachable from every other rank.  s3_gather_peers stores every output row into all of them, so
+    when the last kernel of a step has finished and the ranks have met at `barrier()`, every GPU holds the
+    complete matrices: the all-gather of SURVEY.md §8e happens inside kernel 3, row by row, overlapped with the
+    computation.  Two ways to reach the peers (backend='auto' tries them in this order):
+
+    'multicast'  torch symmetric memory (cuMem VMM allocation + NVSwitch multicast object, plumbing only): ONE
+                 store to the multicast address lands in every GPU's copy, so a rank's NVLink egress is its own
+                 rows once instead of once per peer — what makes the exchange disappear behind the compute at 8 GPUs.
+    'ipc'        cudaMalloc + CUDA IPC handles (csrc/peer.cu) exchanged through torch.distributed: one store per
+                 peer over NVLink P2P.
 
     .local     K+1 torch views [2 * num_links, F+1] of this GPU's copy
-    .bases     device pointers of all ranks' copies (this rank's own at index rank)"""
+    .dst       device pointers kernel 3 stores to: [multicast address] or all ranks' copies"""
 
-    def __init__(self, num_links, num_feat, sign_k, device, group=None):
+    def __init__(self, num_links, num_feat, sign_k, device, group=None, backend='auto'):
         from . import _lib as L
         self._L, self._lib = L, L.lib()
         self.group = group
@@ -103,16 +109,54 @@ class PeerBuffers:
         self.num_links, self.cols, self.num_ops = int(num_links), int(num_feat) + 1, int(sign_k) + 1
         self.rows = 2 * self.num_links
         self.op_stride = (self.rows * self.cols + 31) // 32 * 32        # floats; operators start on 128-byte lines
-        nbytes = max(self.num_ops * self.op_stride * 4, 256)
-        self._opened = []
+        self._nfloats = max(self.num_ops * self.op_stride, 64)
+        self._opened, self._ptr, self._symm = [], None, None
+        self.backend = None
+        if backend in ('auto', 'multicast'):
+            try:
+                self._init_multicast()
+            except Exception as ex:          # every rank must take the same branch: agree below
+                self._symm, self._why_not_multicast = None, f"{type(ex).__name__}: {ex}"[:200]
+            ok = torch.tensor([1 if self._symm is not None else 0], dtype=torch.int32, device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok) == 1:
+                self.backend = 'multicast'
+            else:
+                self._symm = None
+                if backend == 'multicast':
+                    raise RuntimeError("NVSwitch multicast is not available: " + getattr(self, '_why_not_multicast', 'a peer failed'))
+        if self.backend is None:
+            self._init_ipc()
+            self.backend = 'ipc'
+        self.world_dst = len(self.dst)
+        self.base_array = (C.c_void_p * self.world_dst)(*self.dst)
+        self.local = [self._flat[k * self.op_stride:k * self.op_stride + self.rows * self.cols].view(self.rows, self.cols)
+                      for k in range(self.num_ops)]
+        self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.barrier()
+
+    def _init_multicast(self):
+        import torch.distributed._symmetric_memory as symm_mem
+        grp = self.group if self.group is not None else dist.group.WORLD
+        t = symm_mem.empty(self._nfloats, dtype=torch.float32, device=self.device)
+        hdl = symm_mem.rendezvous(t, grp)
+        mc = int(hdl.multicast_ptr or 0)
+        if not mc:
+            raise RuntimeError("the symmetric-memory handle has no multicast address")
+        self._symm, self._flat = hdl, t
+        self.bases = [int(p) for p in hdl.buffer_ptrs]
+        self.dst = [mc]
+
+    def _init_ipc(self):
+        L = self._L
         with torch.cuda.device(self.device):
             ptr = C.c_void_p()
-            L.check(self._lib.s3_peer_alloc(nbytes, C.byref(ptr)), 's3_peer_alloc')
+            L.check(self._lib.s3_peer_alloc(self._nfloats * 4, C.byref(ptr)), 's3_peer_alloc')
             self._ptr = ptr.value
             handle = C.create_string_buffer(L.PEER_HANDLE_BYTES)
             L.check(self._lib.s3_peer_export(C.c_void_p(self._ptr), handle), 's3_peer_export')
             handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            dist.all_gather_object(handles, bytes(handle.raw), group=self.group)
             self.bases = []
             for r, h in enumerate(handles):
                 if r == self.rank:
@@ -122,13 +166,9 @@ class PeerBuffers:
                 L.check(self._lib.s3_peer_open(C.create_string_buffer(h, L.PEER_HANDLE_BYTES), C.byref(p)), 's3_peer_open')
                 self._opened.append(p.value)
                 self.bases.append(p.value)
-        self.base_array = (C.c_void_p * self.world)(*self.bases)
-        self._mem = _DevMem(self._ptr, self.num_ops * self.op_stride)
-        flat = torch.as_tensor(self._mem, device=self.device)
-        self.local = [flat[k * self.op_stride:k * self.op_stride + self.rows * self.cols].view(self.rows, self.cols)
-                      for k in range(self.num_ops)]
-        self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self.barrier()
+        self.dst = list(self.bases)
+        self._mem = _DevMem(self._ptr, self._nfloats)
+        self._flat = torch.as_tensor(self._mem, device=self.device)
 
     def barrier(self):
         """All ranks' kernels enqueued so far (on the current stream) have finished before any rank's later work
@@ -136,16 +176,18 @@ class PeerBuffers:
         dist.all_reduce(self._flag, group=self.group)
 
     def close(self):
-        if self._ptr is None:
+        if self._flat is None:
             return
         torch.cuda.synchronize(self.device)
         dist.barrier(group=self.group)           # nobody may still be storing into a buffer that goes away
-        with torch.cuda.device(self.device):
-            for p in self._opened:
-                self._lib.s3_peer_close(C.c_void_p(p))
-            self.local = None
-            self._lib.s3_peer_free(C.c_void_p(self._ptr))
-        self._ptr, self._opened = None, []
+        self.local = None
+        if self.backend == 'ipc':
+            with torch.cuda.device(self.device):
+                for p in self._opened:
+                    self._lib.s3_peer_close(C.c_void_p(p))
+                self._flat = None
+                self._lib.s3_peer_free(C.c_void_p(self._ptr))
+        self._flat, self._symm, self._ptr, self._opened = None, None, None, []
 
 
 def precompute_exchange(graph, links, num_hops, sign_k, buffers, flow='PoS', defer=False, **kw):

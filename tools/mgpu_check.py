@@ -29,26 +29,30 @@ def main():
         X = ds.normalize_features(X) if X is not None else ds.synthetic_features(N, 40, 0.5, 0)
         links = ds.all_links(splits)[:, :nl]
         g = DeviceGraph(A, X, device=dev)
-        buf = PeerBuffers(links.shape[1], g.num_feat, K, dev)
-        for o in buf.local:
-            o.fill_(float('nan'))
-        torch.cuda.synchronize(dev)
-        buf.barrier()
-        for rep, kw in enumerate((dict(), dict(batch_records=512, overlap=True))):
-            res, mirror = precompute_exchange(g, links, hops, K, buf, flow=flow, **kw)
+        for backend in ('auto', 'ipc'):
+            buf = PeerBuffers(links.shape[1], g.num_feat, K, dev, backend=backend)
+            if rank == 0:
+                print(f"PeerBuffers backend {backend!r} -> {buf.backend}"
+                      + (f" ({getattr(buf, '_why_not_multicast', '')})" if buf.backend != 'multicast' and backend == 'auto' else ''), flush=True)
+            for o in buf.local:
+                o.fill_(float('nan'))
             torch.cuda.synchronize(dev)
-            want = precompute(g, links, hops, K, flow, pair=False)
-            same = all(torch.equal(buf.local[k], want.xs[k]) for k in range(K + 1))
-            if not same:
-                bad = [int((buf.local[k] != want.xs[k]).any(1).sum()) for k in range(K + 1)]
-                print(f"rank {rank}: {name} {flow} rep {rep}: rows differing per operator {bad}", flush=True)
-                ok.zero_()
-            elif rank == 0:
-                print(f"{name} {flow} h={hops} K={K} {links.shape[1]} links, world {dist.get_world_size()}, rep {rep}: "
-                      f"every rank's matrices equal the single-GPU result bit for bit "
-                      f"(this rank extracted {res.stats['links'] - res.stats['mirrors']} records)", flush=True)
             buf.barrier()
-        buf.close()
+            for rep, kw in enumerate((dict(), dict(batch_records=512, overlap=True))):
+                res, mirror = precompute_exchange(g, links, hops, K, buf, flow=flow, **kw)
+                torch.cuda.synchronize(dev)
+                want = precompute(g, links, hops, K, flow, pair=False)
+                same = all(torch.equal(buf.local[k], want.xs[k]) for k in range(K + 1))
+                if not same:
+                    bad = [int((buf.local[k] != want.xs[k]).any(1).sum()) for k in range(K + 1)]
+                    print(f"rank {rank}: {name} {flow} {buf.backend} rep {rep}: rows differing per operator {bad}", flush=True)
+                    ok.zero_()
+                elif rank == 0:
+                    print(f"{name} {flow} h={hops} K={K} {links.shape[1]} links, world {dist.get_world_size()}, {buf.backend}, rep {rep}: "
+                          f"every rank's matrices equal the single-GPU result bit for bit "
+                          f"(this rank extracted {res.stats['links'] - res.stats['mirrors']} records)", flush=True)
+                buf.barrier()
+            buf.close()
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if rank == 0:
         print('MGPU_OK' if int(ok) else 'MGPU_FAIL', flush=True)
