@@ -319,6 +319,8 @@ def measure_ceilings(dev):
             ('l2_read_GBps', lambda it: lib.s3_probe_l2_read(C.c_void_p(buf.data_ptr()), buf.numel() * 4, it, C.c_void_p(sink.data_ptr()), sms * 8, st),
              lambda it: buf.numel() * 4 * it / 1e9),
             ('fp32_TFLOPs', lambda it: lib.s3_probe_fma(it * 64, C.c_void_p(sink.data_ptr()), sms * 8, st),
+             lambda it: 2.0 * sms * 8 * 256 * it * 64 * 128 / 1e12),
+            ('fp32x2_TFLOPs', lambda it: lib.s3_probe_fma2(it * 64, C.c_void_p(sink.data_ptr()), sms * 8, st),
              lambda it: 2.0 * sms * 8 * 256 * it * 64 * 128 / 1e12)):
         L.check(call(2), name)
         best = 0.0
@@ -433,7 +435,7 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
         rows_mine = 2 * (res.stats['links'])
         # NVLink egress of a rank: its rows once through the NVSwitch multicast object, or once per peer over P2P
-        nv = rows_mine * (K + 1) * (F + 1) * 4 * (1 if exchange_backend == 'multicast' else world - 1)
+        nv = rows_mine * K * (F + 1) * 4 * (1 if exchange_backend == 'multicast' else world - 1)   # operator 0 stays local
         exch = dict(kind="s3_gather_peers: kernel 3 stores every output row into all ranks' matrices ("
                          + ("one store to an NVSwitch multicast address, torch symmetric memory as plumbing" if exchange_backend == 'multicast'
                             else "one store per peer over NVLink P2P, cudaMalloc + CUDA IPC")
@@ -636,7 +638,7 @@ def main():
     ap.add_argument('--rmat-edges', type=int, default=200_000_000)
     ap.add_argument('--rmat-links', type=int, default=4_000_000)
     ap.add_argument('--rmat-degree-cap', type=int, default=512)
-    ap.add_argument('--exchange-backend', default='auto', choices=['auto', 'multicast', 'ipc'])
+    ap.add_argument('--exchange-backend', default='ipc', choices=['auto', 'multicast', 'ipc'])
     ap.add_argument('--overlap', action='store_true', help='two-stream schedule: front kernel of batch i+1 beside kernel 3 of batch i')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))

@@ -308,9 +308,16 @@ int s3_pair_links(const int64_t* link_src, const int64_t* link_dst, int64_t num_
  * copy followed by an NCCL all-gather. dst_bases: HOST array of num_dst (<= 8) device pointers, each the base of
  * one GPU's buffer mapped into this process (s3_peer_open); operator k of a buffer starts at base + k * op_stride
  * floats and is [*, ldo] row-major. Rows land at 2 * (global link index) (out_link / link_base / mirror as in
- * s3_batch). No flag is spun on: completion is the kernel boundary followed by the caller's barrier. */
+ * s3_batch). No flag is spun on: completion is the kernel boundary followed by the caller's barrier.
+ * skip_op0 != 0: operator 0 (x = [1 | X[node]], an exact copy of the features every GPU already holds) is not
+ * stored at all; every GPU then writes those rows itself for the whole link list with s3_fill_x0 — a quarter less
+ * NVLink traffic at sign_k = 3. */
 int s3_gather_peers(const s3_graph* g, const s3_batch* b, int64_t num_records, float* const* dst_bases, int32_t num_dst,
-                    int64_t op_stride, int64_t ldo, void* stream);
+                    int64_t op_stride, int64_t ldo, int32_t skip_op0, void* stream);
+/* x (operator 0) of the fixed-row flows for a whole link list: out0 [2 * num_links, ldo], row 2i = [1 | X[src_i]],
+ * row 2i+1 = [1 | X[dst_i]] (reference tuned_SIGN.py:181 / :119-124); rows of invalid links are left untouched. */
+int s3_fill_x0(const s3_graph* g, const int64_t* link_src, const int64_t* link_dst, int64_t num_links, float* out0, int64_t ldo,
+               void* stream);
 
 /* Peer memory for s3_gather_peers: one cudaMalloc'ed buffer per GPU, exported as a 64-byte CUDA IPC handle that
  * the other ranks of the node open (peer access is enabled lazily by the open). Plain CUDA runtime IPC; the
@@ -346,6 +353,7 @@ int s3_segment_pool(const float* src, int64_t ld_src, int64_t num_cols, const in
  * (ctas * 256 threads * iters * 128 FMAs per launch). Nothing on the product path calls them. */
 int s3_probe_l2_read(const float* buf, int64_t bytes, int32_t iters, float* sink, int32_t ctas, void* stream);
 int s3_probe_fma(int32_t iters, float* sink, int32_t ctas, void* stream);
+int s3_probe_fma2(int32_t iters, float* sink, int32_t ctas, void* stream); /* the same FMAs as packed pairs (fma.rn.f32x2 / FFMA2) */
 
 /* Optional dumps for parity checks: canonical global-id edge list of every record,
  * edges[e] = (global row, global col), e in [edge_ptr[r], edge_ptr[r+1]). */

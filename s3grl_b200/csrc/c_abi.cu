@@ -153,7 +153,7 @@ int s3_gather_ccn(const s3_graph* g, const s3_batch* b, int64_t num_items, float
 }
 
 int s3_gather_peers(const s3_graph* g, const s3_batch* b, int64_t num_records, float* const* dst_bases, int32_t num_dst,
-                    int64_t op_stride, int64_t ldo, void* stream) {
+                    int64_t op_stride, int64_t ldo, int32_t skip_op0, void* stream) {
     int rc = check_graph(g, true);
     if (rc != S3_OK) return rc;
     rc = check_batch(b);
@@ -164,6 +164,7 @@ int s3_gather_peers(const s3_graph* g, const s3_batch* b, int64_t num_records, f
     s3::PeerDst peers;
     peers.num_dst = num_dst;
     peers.op_stride = op_stride;
+    peers.skip_op0 = skip_op0 ? 1 : 0;
     for (int d = 0; d < S3_MAX_PEERS; ++d) peers.base[d] = nullptr;
     for (int d = 0; d < num_dst; ++d) {
         if (!dst_bases[d]) return S3_ERR_INVALID_ARG;
@@ -173,6 +174,16 @@ int s3_gather_peers(const s3_graph* g, const s3_batch* b, int64_t num_records, f
     memset(&o, 0, sizeof(o));
     cudaError_t e = s3::launch_gather(*g, *b, num_records, o, ldo, b->link_base * 2 /* rows per link */, false,
                                       static_cast<cudaStream_t>(stream), &peers);
+    return e == cudaSuccess ? S3_OK : cuda_fail(e);
+}
+
+int s3_fill_x0(const s3_graph* g, const int64_t* link_src, const int64_t* link_dst, int64_t num_links, float* out0, int64_t ldo,
+               void* stream) {
+    int rc = check_graph(g, true);
+    if (rc != S3_OK) return rc;
+    if (num_links < 0 || ldo < g->num_feat + 1) return S3_ERR_INVALID_ARG;
+    if (num_links > 0 && (!link_src || !link_dst || !out0)) return S3_ERR_INVALID_ARG;
+    cudaError_t e = s3::launch_fill_x0(*g, link_src, link_dst, num_links, out0, ldo, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? S3_OK : cuda_fail(e);
 }
 
@@ -216,6 +227,12 @@ int s3_probe_l2_read(const float* buf, int64_t bytes, int32_t iters, float* sink
 int s3_probe_fma(int32_t iters, float* sink, int32_t ctas, void* stream) {
     if (!sink || iters < 1 || ctas < 1) return S3_ERR_INVALID_ARG;
     cudaError_t e = s3::launch_probe_fma(iters, sink, ctas, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? S3_OK : cuda_fail(e);
+}
+
+int s3_probe_fma2(int32_t iters, float* sink, int32_t ctas, void* stream) {
+    if (!sink || iters < 1 || ctas < 1) return S3_ERR_INVALID_ARG;
+    cudaError_t e = s3::launch_probe_fma2(iters, sink, ctas, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? S3_OK : cuda_fail(e);
 }
 

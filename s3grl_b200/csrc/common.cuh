@@ -130,6 +130,7 @@ struct PeerDst {  // s3_gather_peers destinations
     float* base[S3_MAX_PEERS];
     int num_dst;
     int64_t op_stride;
+    int skip_op0;
 };
 
 // launchers (defined in the .cu files, called from c_abi.cu)
@@ -143,12 +144,15 @@ cudaError_t launch_plan_items(const s3_batch& b, cudaStream_t st);
 cudaError_t launch_diffuse(const s3_graph& g, const s3_batch& b, int64_t num_items, cudaStream_t st);
 cudaError_t launch_gather(const s3_graph& g, const s3_batch& b, int64_t num_items, const OutPtrs& out,
                           int64_t ldo, int64_t row_base, bool ccn, cudaStream_t st, const PeerDst* peers = nullptr);
+cudaError_t launch_fill_x0(const s3_graph& g, const int64_t* src, const int64_t* dst, int64_t num_links, float* out, int64_t ldo,
+                           cudaStream_t st);
 cudaError_t launch_pair_links(const int64_t* src, const int64_t* dst, int64_t L, int64_t N, int64_t* table, int64_t slots,
                               int64_t* mirror, cudaStream_t st);
 cudaError_t launch_segment_pool(const float* src, int64_t ld, int64_t cols, const int64_t* row_ptr, int64_t num_links, int mode,
                                 int layout, float* out, int64_t ld_out, cudaStream_t st);
 cudaError_t launch_probe_l2_read(const float* buf, int64_t bytes, int iters, float* sink, int ctas, cudaStream_t st);
 cudaError_t launch_probe_fma(int iters, float* sink, int ctas, cudaStream_t st);
+cudaError_t launch_probe_fma2(int iters, float* sink, int ctas, cudaStream_t st);
 cudaError_t peer_alloc(int64_t bytes, void** ptr);
 cudaError_t peer_free(void* ptr);
 cudaError_t peer_export(void* ptr, unsigned char* handle);

@@ -31,12 +31,14 @@ cudaError_t launch_gather(const s3_graph& g, const s3_batch& b, int64_t num_item
     p.mirror = (!ccn && batch_pairing(b)) ? b.mirror : nullptr;
     p.link_base = b.link_base;
     p.num_dst = 0;
+    p.skip_op0 = 0;
     p.op_stride = 0;
     for (int d = 0; d < S3_MAX_PEERS; ++d) p.dst_base[d] = nullptr;
     if (peers) {
         if (ccn || peers->num_dst < 1 || peers->num_dst > S3_MAX_PEERS) return cudaErrorInvalidValue;
         p.num_dst = peers->num_dst;
         p.op_stride = peers->op_stride;
+        p.skip_op0 = peers->skip_op0;
         for (int d = 0; d < peers->num_dst; ++d) p.dst_base[d] = peers->base[d];
     }
 
@@ -77,6 +79,30 @@ cudaError_t launch_gather(const s3_graph& g, const s3_batch& b, int64_t num_item
                        : K1 <= 6 ? launch_gather_sc2_mid(p, K1, C, grid, smem, st) : launch_gather_sc2_hi(p, K1, C, grid, smem, st);
     return K1 <= 4 ? launch_gather_sc1_lo(p, K1, C, grid, smem, st)
                    : K1 <= 6 ? launch_gather_sc1_mid(p, K1, C, grid, smem, st) : launch_gather_sc1_hi(p, K1, C, grid, smem, st);
+}
+
+namespace {
+// x (operator 0) of the fixed-row flows for a whole link list: row 2i = [1 | X[src_i]], row 2i+1 = [1 | X[dst_i]]
+// (tuned_SIGN.py:181 x = subg_x[[0,1]] with the zero-one label; SoP tuned_SIGN.py:119-124). Plain copy, one CTA per row.
+__global__ void __launch_bounds__(128) fill_x0_kernel(const float* __restrict__ x, int64_t ldx, int F, int64_t num_nodes,
+                                                      const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
+                                                      float* __restrict__ out, int64_t ldo) {
+    const int64_t row = blockIdx.x, link = row >> 1;
+    const int64_t a = src[link], b = dst[link];
+    if (a < 0 || b < 0 || a >= num_nodes || b >= num_nodes || a == b) return;  // invalid link: flagged by s3_extract
+    const float* xr = x + ((row & 1) ? b : a) * ldx;
+    float* o = out + row * ldo;
+    if (threadIdx.x == 0) o[0] = 1.0f;
+    for (int f = threadIdx.x; f < F; f += 128) o[1 + f] = __ldg(xr + f);
+}
+}  // namespace
+
+cudaError_t launch_fill_x0(const s3_graph& g, const int64_t* src, const int64_t* dst, int64_t num_links, float* out, int64_t ldo,
+                           cudaStream_t st) {
+    if (num_links == 0) return cudaSuccess;
+    if (2 * num_links > 0x7fffffff) return cudaErrorInvalidValue;
+    fill_x0_kernel<<<(unsigned)(2 * num_links), 128, 0, st>>>(g.x, g.ldx, (int)g.num_feat, g.num_nodes, src, dst, out, ldo);
+    return cudaGetLastError();
 }
 
 }  // namespace s3

@@ -53,6 +53,9 @@ struct GatherParams {
     int num_dst;
     float* dst_base[S3_MAX_PEERS];
     int64_t op_stride;
+    // s3_gather_peers: operator 0 (x itself, an exact copy of [1 | X[node]]) is not sent over NVLink — every GPU holds
+    // X and writes those rows locally for the whole link list (s3_fill_x0): a quarter less traffic at K = 3
+    int skip_op0;
 };
 // per-(SC, K1 range) translation units, so that the ~130 instantiations compile in parallel
 #define S3_DECL_GATHER_TU(name) \
@@ -319,7 +322,7 @@ __global__ void __launch_bounds__(kGatherThreads, gather_min_blocks(K1 * SC * C)
 #pragma unroll
     for (int q = 0; q < NW; ++q) {
         const int k = q / SC, c = q - k * SC;
-        const bool live = first_sel + c < s;  // uniform over the CTA
+        const bool live = first_sel + c < s && !(p.skip_op0 && k == 0);  // uniform over the CTA
         __syncthreads();
         if (live && grp == 0) {
 #pragma unroll

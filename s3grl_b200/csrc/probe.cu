@@ -54,7 +54,37 @@ __global__ void __launch_bounds__(256) probe_fma_kernel(int iters, float* sink) 
     if (s == 1234.5f) sink[0] = s;
 }
 
+// the same chains as packed FP32 pairs: fma.rn.f32x2 (SASS FFMA2), two FMAs per issued instruction
+__global__ void __launch_bounds__(256) probe_fma2_kernel(int iters, float* sink) {
+    unsigned long long a[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float2 v = make_float2(1.0f + 0.001f * (threadIdx.x + q), 1.0f + 0.002f * (threadIdx.x + q));
+        a[q] = *reinterpret_cast<const unsigned long long*>(&v);
+    }
+    const float2 m2 = make_float2(0.999f, 0.998f), c2 = make_float2(0.001f, 0.002f);
+    const unsigned long long m = *reinterpret_cast<const unsigned long long*>(&m2), c = *reinterpret_cast<const unsigned long long*>(&c2);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a[q]) : "l"(m), "l"(c));
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float2 v = *reinterpret_cast<const float2*>(&a[q]);
+        s += v.x + v.y;
+    }
+    if (s == 1234.5f) sink[0] = s;
+}
+
 }  // namespace
+
+cudaError_t launch_probe_fma2(int iters, float* sink, int ctas, cudaStream_t st) {
+    probe_fma2_kernel<<<ctas, 256, 0, st>>>(iters, sink);   // 128 FMAs per thread per iteration, as probe_fma
+    return cudaGetLastError();
+}
 
 cudaError_t launch_probe_l2_read(const float* buf, int64_t bytes, int iters, float* sink, int ctas, cudaStream_t st) {
     probe_l2_read_kernel<<<ctas, 256, 0, st>>>(reinterpret_cast<const float4*>(buf), bytes / 16, iters, sink);

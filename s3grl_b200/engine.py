@@ -434,7 +434,7 @@ class _Call:
             return self.launch('gather', bi, 's3_gather', g, C.byref(batch), nrec, self.out_ptrs, self.F1, row_base, st, on=on)
         pb = self.peers
         return self.launch('gather', bi, 's3_gather_peers', g, C.byref(batch), nrec, pb.base_array, pb.world_dst, pb.op_stride,
-                           self.F1, st, on=on)
+                           self.F1, 1 if pb.local_x0 else 0, st, on=on)
 
     def enqueue_fixed_batch(self, bi, arena):
         g, st = C.byref(self.graph._c), self.stream_ptr
@@ -462,7 +462,8 @@ class _Call:
         g = C.byref(self.graph._c)
         sF, sB = self.graph.streams()
         arenas = (self.graph.arena(self.words, 0), self.graph.arena(self.words, 1))
-        self.counters[torch.as_tensor(todo, device=self.dev)] = 0
+        for bi in todo:                      # per-batch memsets: no host synchronisation
+            self.counters[bi].zero_()
         start = torch.cuda.Event()
         start.record(self.stream)
         sF.wait_event(start)

@@ -87,19 +87,24 @@ class PeerBuffers:
     rank's copy reachable from every other rank.  s3_gather_peers stores every output row into all of them, so
     when the last kernel of a step has finished and the ranks have met at `barrier()`, every GPU holds the
     complete matrices: the all-gather of SURVEY.md §8e happens inside kernel 3, row by row, overlapped with the
-    computation.  Two ways to reach the peers (backend='auto' tries them in this order):
+    computation.  Two ways to reach the peers:
 
+    'ipc'        (default) cudaMalloc + CUDA IPC handles (csrc/peer.cu) exchanged through torch.distributed: one
+                 store per peer over NVLink P2P.  Measured steady (2 x B200: 15.1 ms per PubMed step, +-0.05).
     'multicast'  torch symmetric memory (cuMem VMM allocation + NVSwitch multicast object, plumbing only): ONE
-                 store to the multicast address lands in every GPU's copy, so a rank's NVLink egress is its own
-                 rows once instead of once per peer — what makes the exchange disappear behind the compute at 8 GPUs.
-    'ipc'        cudaMalloc + CUDA IPC handles (csrc/peer.cu) exchanged through torch.distributed: one store per
-                 peer over NVLink P2P.
+                 store to the multicast address lands in every GPU's copy.  Bit-exact too, but the 4-byte-aligned row
+                 stores through the switch were erratic on this pool (15.9 .. 48 ms per step on 2 GPUs), and a GPU
+                 still has to RECEIVE (N-1)/N of the matrices either way: opt-in.  'auto' tries it first.
+
+    Operator 0 (x itself = [1 | X[node]]) never crosses NVLink when local_x0 is set: every GPU holds X and fills
+    those rows for the whole list with s3_fill_x0 (a quarter less traffic at sign_k = 3).
 
     .local     K+1 torch views [2 * num_links, F+1] of this GPU's copy
     .dst       device pointers kernel 3 stores to: [multicast address] or all ranks' copies"""
 
-    def __init__(self, num_links, num_feat, sign_k, device, group=None, backend='auto'):
+    def __init__(self, num_links, num_feat, sign_k, device, group=None, backend='ipc', local_x0=True):
         from . import _lib as L
+        self.local_x0 = bool(local_x0)      # operator 0 is written locally by every GPU (s3_fill_x0), not exchanged
         self._L, self._lib = L, L.lib()
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
@@ -207,6 +212,12 @@ def precompute_exchange(graph, links, num_hops, sign_k, buffers, flow='PoS', def
     if flow == 'PoS' and n > 1 and not kw.get('walk') and kw.get('pair', True):
         mirror, table = pair_links(links, graph.num_nodes, kw.get('stream'))
     kw.pop('pair', None)
+    if buffers.local_x0:       # x of every link, locally: the one operator that is a plain copy of resident data
+        st = kw.get('stream') or torch.cuda.current_stream(dev)
+        with torch.cuda.device(dev):
+            buffers._L.check(buffers._lib.s3_fill_x0(C.byref(graph._c), C.c_void_p(links[0].data_ptr()),
+                                                     C.c_void_p(links[1].data_ptr()), n, C.c_void_p(buffers.local[0].data_ptr()),
+                                                     buffers.cols, C.c_void_p(st.cuda_stream)), 's3_fill_x0')
     idx = torch.arange(buffers.rank, n, buffers.world, device=dev, dtype=torch.int64)
     res = precompute(graph, links[:, idx].contiguous(), num_hops, sign_k, flow, None, out_link=idx, mirror=mirror,
                      peers=buffers, pair=False, defer=defer, **kw)
