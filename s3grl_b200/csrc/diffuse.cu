@@ -28,7 +28,10 @@ namespace s3 {
 namespace {
 
 constexpr int kDiffLanes = 4;  // lanes per row (rows of the reference's graphs are short: 4 leave fewer lanes idle than 8)
-constexpr int kZCap = 4096;  // floats per shared z buffer (2 buffers: 32 KB): n <= 2048 with 2 rows, 512 with 8
+// floats per shared z buffer (two buffers, dynamic shared memory): 2-row items (intersection) n <= 2048 in 32 KB;
+// 8-row items (union) n <= 1536 in 96 KB, two CTAs per SM — with the 32 KB of round 1 every PubMed union item above
+// 512 nodes (most of them: mean n = 930) kept z in global memory and the sweeps ran at L2 latency
+__host__ __device__ constexpr int z_cap(int sc) { return sc == 8 ? 1536 * 8 : 4096; }
 
 struct DiffuseParams {
     const int64_t* __restrict__ indptr;  // SoP: global degrees
@@ -42,7 +45,8 @@ struct DiffuseParams {
 
 template <int SC>
 __global__ void __launch_bounds__(kDiffuseThreads) diffuse_kernel(DiffuseParams p) {
-    __shared__ float s_z[2][kZCap];
+    extern __shared__ float s_zbuf[];  // [2][z_cap(SC)]
+    constexpr int kZCap = z_cap(SC);
     const int tid = threadIdx.x, T = kDiffuseThreads;
     const int l8 = tid & (kDiffLanes - 1), grp = tid / kDiffLanes;  // lane group of a row
     constexpr int NG = kDiffuseThreads / kDiffLanes;
@@ -65,8 +69,8 @@ __global__ void __launch_bounds__(kDiffuseThreads) diffuse_kernel(DiffuseParams 
     float* lab = item_f;
     float* wgt = item_f + NWP;
     const bool z_shared = (int64_t)n * SC <= kZCap;
-    float* zA = z_shared ? s_z[0] : wgt + (int64_t)n * NWP;
-    float* zB = z_shared ? s_z[1] : wgt + (int64_t)n * NWP + (int64_t)n * SC;
+    float* zA = z_shared ? s_zbuf : wgt + (int64_t)n * NWP;
+    float* zB = z_shared ? s_zbuf + kZCap : wgt + (int64_t)n * NWP + (int64_t)n * SC;
 
     // selected local rows of this item
     int r[SC];
@@ -207,10 +211,15 @@ cudaError_t launch_diffuse(const s3_graph& g, const s3_batch& b, int64_t num_ite
     p.item_rec = b.item_rec;
     p.flow = b.flow;
     p.sign_k = b.sign_k;
-    if (ccn_rows(b.strategy) == 8)
-        diffuse_kernel<8><<<(unsigned)num_items, kDiffuseThreads, 0, st>>>(p);
-    else
-        diffuse_kernel<2><<<(unsigned)num_items, kDiffuseThreads, 0, st>>>(p);
+    if (ccn_rows(b.strategy) == 8) {
+        static LaunchCache cache;  // the > 48 KB shared-memory opt-in is per device
+        constexpr size_t smem = 2 * (size_t)z_cap(8) * sizeof(float);
+        cudaError_t e = cache.get(reinterpret_cast<const void*>(diffuse_kernel<8>), kDiffuseThreads, smem, nullptr, nullptr);
+        if (e != cudaSuccess) return e;
+        diffuse_kernel<8><<<(unsigned)num_items, kDiffuseThreads, smem, st>>>(p);
+    } else {
+        diffuse_kernel<2><<<(unsigned)num_items, kDiffuseThreads, 2 * (size_t)z_cap(2) * sizeof(float), st>>>(p);
+    }
     return cudaGetLastError();
 }
 

@@ -59,7 +59,7 @@ cudaError_t launch_gather(const s3_graph& g, const s3_batch& b, int64_t num_item
     const int G = kGatherThreads / tpr;
     const size_t tile_bytes = (size_t)kTile * NWP * 4 + kTile * 4;
     const size_t red_bytes = (size_t)(G - 1) * NW * C * tpr * 16;
-    const size_t row_bytes = (size_t)C * tpr * 16;  // one staged output row of the column chunk
+    const size_t row_bytes = (size_t)C * tpr * 16 + 32;  // one staged output row of the column chunk (+ label, slack)
     size_t smem = tile_bytes > red_bytes ? tile_bytes : red_bytes;
     if (row_bytes > smem) smem = row_bytes;
     dim3 grid((unsigned)num_items, (unsigned)colchunks);

@@ -305,19 +305,22 @@ __global__ void __launch_bounds__(kGatherThreads, gather_min_blocks(K1 * SC * C)
         }
     }
 
-    // ---- epilogue: every output row is staged through shared memory and stored with consecutive lanes on
-    // consecutive floats (rows are 4-byte aligned only: ldo = F + 1), to this GPU's operator matrices or, for
-    // s3_gather_peers, to every GPU's; chain members of a paired link get the same rows (seed rows exchanged
-    // for the opposite direction).
+    // ---- epilogue: every output row is staged through shared memory exactly as it lies in memory ([label | features],
+    // rows are only 4-byte aligned: ldo = F + 1) and stored with 16-byte vectors from the first 16-byte boundary on
+    // (scalar head / tail), to this GPU's operator matrices or, for s3_gather_peers, to every GPU's — full 128-bit
+    // stores are what NVLink needs: 4-byte stores reached 150 GB/s per GPU on 8 x B200. Chain members of a paired
+    // link get the same rows (seed rows exchanged for the opposite direction).
     const int first_sel = p.ccn ? nseed + chunk * SC : 0;  // index of this item's first selected row
     const int rpl = p.flow == S3_FLOW_SOP ? 2 : 1;  // records per link (SoP: one per endpoint)
     const int64_t gl = p.out_link ? p.out_link[rec / rpl] : p.link_base + rec / rpl;  // global link index (fixed-row flows)
     const int64_t row0 = (p.out_link ? (gl * rpl + rec % rpl) * nseed
                                      : p.row_base + (p.row_ptr ? p.row_ptr[rec] : rec * (int64_t)nseed)) + first_sel;
     const long long chain = (p.mirror && !p.ccn) ? (long long)p.mirror[gl] : -1;
-    float* s_row = reinterpret_cast<float*>(smem4);  // [C * tpr * 4]
+    float* s_row = reinterpret_cast<float*>(smem4);  // element e of the output row sits at s_row[e - f0]
     const int f0 = blockIdx.y * C * tpr * 4;         // first feature of this CTA's column chunk
     const int nfl = min(C * tpr * 4, p.F - f0);
+    const int e_lo = blockIdx.y == 0 ? 0 : 1 + f0;   // elements [e_lo, e_hi) of every row are this CTA's
+    const int e_hi = 1 + f0 + nfl;
     const int ndst = p.num_dst > 0 ? p.num_dst : 1;
 #pragma unroll
     for (int q = 0; q < NW; ++q) {
@@ -326,18 +329,33 @@ __global__ void __launch_bounds__(kGatherThreads, gather_min_blocks(K1 * SC * C)
         __syncthreads();
         if (live && grp == 0) {
 #pragma unroll
-            for (int i = 0; i < C; ++i) reinterpret_cast<float4*>(s_row)[i * tpr + lane] = acc[q][i];
+            for (int i = 0; i < C; ++i) {
+                float* d = s_row + 1 + 4 * (i * tpr + lane);
+                d[0] = acc[q][i].x;
+                d[1] = acc[q][i].y;
+                d[2] = acc[q][i].z;
+                d[3] = acc[q][i].w;
+            }
+            if (lane == 0) s_row[0] = lab[q];  // the label / self-return column (read by chunk 0 only)
         }
         __syncthreads();
-        if (!live) continue;
-        const float labv = lab[q];
+        if (!live || e_hi <= e_lo) continue;
         int64_t row = row0 + c;
         long long m = chain;
         for (;;) {
             for (int d = 0; d < ndst; ++d) {
                 float* orow = (p.num_dst > 0 ? p.dst_base[d] + (int64_t)k * p.op_stride : p.out.p[k]) + row * p.ldo;
-                for (int idx = tid; idx < nfl; idx += kGatherThreads) orow[1 + f0 + idx] = s_row[idx];
-                if (blockIdx.y == 0 && tid == 0) orow[0] = labv;
+                const int mis = (int)((reinterpret_cast<uintptr_t>(orow + e_lo) >> 2) & 3);
+                const int head = min((4 - mis) & 3, e_hi - e_lo);
+                const int nvec = (e_hi - e_lo - head) >> 2;
+                const int ev = e_lo + head;  // first element on a 16-byte boundary
+                for (int v = tid; v < nvec; v += kGatherThreads) {
+                    const float* sp = s_row + (ev + 4 * v - f0);
+                    *reinterpret_cast<float4*>(orow + ev + 4 * v) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                }
+                const int et = ev + 4 * nvec;  // scalar head [e_lo, ev) and tail [et, e_hi)
+                if (tid < head) orow[e_lo + tid] = s_row[e_lo + tid - f0];
+                if (tid >= 32 && tid - 32 < e_hi - et) orow[et + tid - 32] = s_row[et + tid - 32 - f0];
             }
             if (m < 0) break;
             const long long v = -2 - (long long)p.mirror[m];
