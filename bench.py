@@ -343,7 +343,7 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
     import torch.distributed as dist
     from s3grl_b200 import DeviceGraph, algorithmic_bytes, precompute, precompute_full
     from s3grl_b200 import tuned_sign
-    from s3grl_b200.parallel import PeerBuffers, precompute_exchange, shard_range
+    from s3grl_b200.parallel import PeerBuffers, exchange_finish, precompute_exchange, shard_range
 
     def barrier():
         if world > 1:
@@ -374,10 +374,10 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
             return precompute_full(g, links_dev, w['num_hops'], K, node_label=full_flow, batch_records=args.batch_records,
                                    profile=profile)
         if exchange:
-            res, _ = precompute_exchange(g, links_dev, w['num_hops'], K, buffers, flow=w['flow'], defer=True,
-                                         batch_records=args.batch_records, profile=profile, overlap=args.overlap,
-                                         walk=w.get('walk'))
-            buffers.barrier()       # on the stream: every rank's rows of this step have landed everywhere
+            res, mirror = precompute_exchange(g, links_dev, w['num_hops'], K, buffers, flow=w['flow'], defer=True,
+                                              batch_records=args.batch_records, profile=profile, overlap=args.overlap,
+                                              walk=w.get('walk'))
+            exchange_finish(buffers, mirror)    # on the stream: barrier (all rows have landed), then the paired links' rows
             return res
         return precompute(g, links_dev, w['num_hops'], K, w['flow'], w['strategy'], batch_records=args.batch_records, out=out,
                           profile=profile, overlap=args.overlap, defer=fixed, walk=w.get('walk'), pair=not args.no_pair)
@@ -435,7 +435,8 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
         rows_mine = 2 * (res.stats['links'])
         # NVLink egress of a rank: its rows once through the NVSwitch multicast object, or once per peer over P2P
-        nv = rows_mine * K * (F + 1) * 4 * (1 if exchange_backend == 'multicast' else world - 1)   # operator 0 stays local
+        rows_sent = 2 * (res.stats['links'] - res.stats['mirrors'])     # paired links' rows and operator 0 stay local
+        nv = rows_sent * K * (F + 1) * 4 * (1 if exchange_backend == 'multicast' else world - 1)
         exch = dict(kind="s3_gather_peers: kernel 3 stores every output row into all ranks' matrices ("
                          + ("one store to an NVSwitch multicast address, torch symmetric memory as plumbing" if exchange_backend == 'multicast'
                             else "one store per peer over NVLink P2P, cudaMalloc + CUDA IPC")
@@ -638,7 +639,8 @@ def main():
     ap.add_argument('--rmat-edges', type=int, default=200_000_000)
     ap.add_argument('--rmat-links', type=int, default=4_000_000)
     ap.add_argument('--rmat-degree-cap', type=int, default=512)
-    ap.add_argument('--exchange-backend', default='ipc', choices=['auto', 'multicast', 'ipc'])
+    ap.add_argument('--exchange-backend', default=None, choices=['auto', 'multicast', 'ipc'],
+                    help='default: ipc on 2 GPUs, multicast (with ipc as fallback) from 4 GPUs on')
     ap.add_argument('--overlap', action='store_true', help='two-stream schedule: front kernel of batch i+1 beside kernel 3 of batch i')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))

@@ -196,6 +196,16 @@ typedef struct s3_batch {
     const int64_t* out_link;      /* [num_links] global link index of every record, or NULL   */
     const int64_t* mirror;        /* [links of the whole call] chain table, or NULL           */
     int64_t link_base;            /* global link index of record 0 when out_link is NULL      */
+    /* Per-hop caps of the BFS (reference utils.py:66-70: sample_ratio, max_nodes_per_hop), PoS flows. A hop with
+     * c new nodes keeps k = min(int(ratio_per_hop * c), max_nodes_per_hop) of them — the reference's counts. The
+     * reference picks them with random.sample (no reproducible semantics; raises on Python >= 3.11); here they are
+     * the k nodes with the smallest  fmix32(node XOR cap_seed)  (murmur3's 32-bit finaliser, a bijection: no
+     * ties), so the subgraph is a function of (link, seed) alone and the oracle restates it exactly. As in the
+     * reference the dropped nodes stay visited and do not return at a later hop. ratio_per_hop <= 0 or >= 1 and
+     * max_nodes_per_hop <= 0 switch the respective cap off (a zeroed struct caps nothing). */
+    double ratio_per_hop;
+    int32_t max_nodes_per_hop;
+    uint32_t cap_seed;
 } s3_batch;
 
 int s3_version(void);
@@ -309,11 +319,19 @@ int s3_pair_links(const int64_t* link_src, const int64_t* link_dst, int64_t num_
  * one GPU's buffer mapped into this process (s3_peer_open); operator k of a buffer starts at base + k * op_stride
  * floats and is [*, ldo] row-major. Rows land at 2 * (global link index) (out_link / link_base / mirror as in
  * s3_batch). No flag is spun on: completion is the kernel boundary followed by the caller's barrier.
- * skip_op0 != 0: operator 0 (x = [1 | X[node]], an exact copy of the features every GPU already holds) is not
- * stored at all; every GPU then writes those rows itself for the whole link list with s3_fill_x0 — a quarter less
- * NVLink traffic at sign_k = 3. */
+ * flags: S3_PEERS_LOCAL_X0 — operator 0 (x = [1 | X[node]], an exact copy of the features every GPU already holds)
+ * is not stored at all; every GPU writes those rows itself for the whole link list with s3_fill_x0 (a quarter less
+ * NVLink traffic at sign_k = 3).  S3_PEERS_LOCAL_MIRRORS — the rows of paired links (chain members of
+ * s3_pair_links) are not stored either; after the exchange (barrier) every GPU copies them from the first link's
+ * rows in its own memory with s3_fill_mirrors (23 % fewer rows over NVLink on the PubMed link list). */
+#define S3_PEERS_LOCAL_X0 1
+#define S3_PEERS_LOCAL_MIRRORS 2
 int s3_gather_peers(const s3_graph* g, const s3_batch* b, int64_t num_records, float* const* dst_bases, int32_t num_dst,
-                    int64_t op_stride, int64_t ldo, int32_t skip_op0, void* stream);
+                    int64_t op_stride, int64_t ldo, int32_t flags, void* stream);
+/* Rows of every chain member of `mirror` (s3_pair_links over the whole list) copied from the chain's first link,
+ * seed rows exchanged for the opposite direction: ops[k], k = first_op..num_ops-1, [2 * num_links, ldo] row-major. */
+int s3_fill_mirrors(const int64_t* mirror, int64_t num_links, float* const* ops, int32_t first_op, int32_t num_ops,
+                    int64_t num_cols, int64_t ldo, void* stream);
 /* x (operator 0) of the fixed-row flows for a whole link list: out0 [2 * num_links, ldo], row 2i = [1 | X[src_i]],
  * row 2i+1 = [1 | X[dst_i]] (reference tuned_SIGN.py:181 / :119-124); rows of invalid links are left untouched. */
 int s3_fill_x0(const s3_graph* g, const int64_t* link_src, const int64_t* link_dst, int64_t num_links, float* out0, int64_t ldo,

@@ -62,8 +62,36 @@ def _neighbors(fringe, indptr, indices):
     return np.unique(np.concatenate(parts)) if parts else np.empty(0, dtype=np.int64)
 
 
-def k_hop_subgraph(src, dst, num_hops, A):
-    """utils.py:47-85 (undirected, sample_ratio=1, no per-hop cap, no random walks).
+def hash_rank(nodes, seed=0):
+    """Rank key of the deterministic per-hop cap: murmur3's 32-bit finaliser of (node XOR seed).  It is a
+    bijection of the 32-bit ids, so distinct nodes never tie."""
+    h = (np.asarray(nodes, dtype=np.uint64) ^ np.uint64(seed & 0xFFFFFFFF)) & np.uint64(0xFFFFFFFF)
+    h ^= h >> np.uint64(16)
+    h = (h * np.uint64(0x85EBCA6B)) & np.uint64(0xFFFFFFFF)
+    h ^= h >> np.uint64(13)
+    h = (h * np.uint64(0xC2B2AE35)) & np.uint64(0xFFFFFFFF)
+    h ^= h >> np.uint64(16)
+    return h
+
+
+def cap_fringe(fringe, ratio_per_hop, max_nodes_per_hop, seed=0):
+    """utils.py:66-70 with a DETERMINISTIC rule in place of random.sample (which has no reproducible semantics and
+    raises on Python >= 3.11): the hop keeps k = min(int(ratio * len), max) nodes — the reference's
+    counts — and they are the k nodes of the fringe with the smallest hash_rank.  Returned ascending."""
+    k = fringe.size
+    if ratio_per_hop is not None and ratio_per_hop < 1.0:
+        k = int(ratio_per_hop * fringe.size)
+    if max_nodes_per_hop is not None and max_nodes_per_hop < k:
+        k = int(max_nodes_per_hop)
+    if k >= fringe.size:
+        return fringe
+    keep = np.argsort(hash_rank(fringe, seed), kind='stable')[:k]
+    return np.sort(fringe[keep])
+
+
+def k_hop_subgraph(src, dst, num_hops, A, ratio_per_hop=1.0, max_nodes_per_hop=None, cap_seed=0):
+    """utils.py:47-85 (undirected, no random walks).  Per-hop caps follow `cap_fringe`; as in the reference the
+    nodes a cap drops stay `visited` (utils.py:64-65 runs before the sampling) and never come back at a later hop.
 
     Returns (nodes[n] int64 canonical, hops[n] int32, lrowptr[n+1] int64, lcol[m] int32) where
     (lrowptr, lcol) is the induced adjacency on `nodes` in local ids with the target link
@@ -81,9 +109,10 @@ def k_hop_subgraph(src, dst, num_hops, A):
     for dist in range(1, num_hops + 1):
         cand = _neighbors(fringe, indptr, indices)
         fringe = cand[~visited[cand]]              # np.unique output is ascending
+        visited[fringe] = True                     # before the cap: utils.py:64-65
+        fringe = cap_fringe(fringe, ratio_per_hop, max_nodes_per_hop, cap_seed)
         if fringe.size == 0:
             break
-        visited[fringe] = True
         nodes.append(fringe.astype(np.int64))
         hops.append(np.full(fringe.size, dist, dtype=np.int32))
     nodes = np.concatenate(nodes)
@@ -145,11 +174,12 @@ def normalized_subgraph(lrowptr, lcol, dtype=np.float32):
     return ssp.csr_matrix((vals, lcol, lrowptr), shape=(n, n)), dis
 
 
-def pos_link(src, dst, num_hops, A, X, K, strategy=None, dtype=np.float32):
+def pos_link(src, dst, num_hops, A, X, K, strategy=None, dtype=np.float32, caps=None):
     """One link through the optimised PoS / PoS-Plus flow (tuned_SIGN.py:147-187, :202-260).
+    caps: None or dict(ratio_per_hop=, max_nodes_per_hop=, cap_seed=) for k_hop_subgraph.
 
     Returns dict: nodes, hops, lrowptr, lcol, sel (local ids), xs = [x, x1..xK] each [s, F+1]."""
-    nodes, hops, lrowptr, lcol = k_hop_subgraph(src, dst, num_hops, A)
+    nodes, hops, lrowptr, lcol = k_hop_subgraph(src, dst, num_hops, A, **(caps or {}))
     n = nodes.size
     S, _ = normalized_subgraph(lrowptr, lcol, dtype)
     sel = select_rows(lrowptr, lcol, strategy)
@@ -218,13 +248,13 @@ def scaled_pos_precompute(links, sets, A, X, K, dtype=np.float32, keep_graphs=Fa
     return out
 
 
-def pos_precompute(links, num_hops, A, X, K, strategy=None, dtype=np.float32, keep_graphs=False):
+def pos_precompute(links, num_hops, A, X, K, strategy=None, dtype=np.float32, keep_graphs=False, caps=None):
     """Whole call of get_PoS_prepped_ds / get_PoS_Plus_prepped_ds over `links` [2, L], in the
     collated layout PyG's InMemoryDataset.collate produces:
     K+1 row-stacked [R, F+1] arrays and row_ptr [L+1]."""
     links = np.asarray(links)
     L = links.shape[1]
-    per = [pos_link(int(links[0, i]), int(links[1, i]), num_hops, A, X, K, strategy, dtype)
+    per = [pos_link(int(links[0, i]), int(links[1, i]), num_hops, A, X, K, strategy, dtype, caps)
            for i in range(L)]
     row_ptr = np.zeros(L + 1, dtype=np.int64)
     row_ptr[1:] = np.cumsum([p['sel'].size for p in per])

@@ -12,6 +12,7 @@ FLOW_POS, FLOW_SOP = 0, 1
 STRATEGY_NONE, STRATEGY_INTERSECTION, STRATEGY_UNION = 0, 1, 2
 MAX_HOPS, MAX_K, MAX_K_UNION, MAX_PEERS, PEER_HANDLE_BYTES = 8, 7, 5, 8, 64
 VERSION = 200
+PEERS_LOCAL_X0, PEERS_LOCAL_MIRRORS = 1, 2
 POOL_SUM, POOL_MEAN, POOL_OUT_CENTER, POOL_OUT_ROWS = 1, 2, 0, 1
 LABEL_ZERO, LABEL_ZO, LABEL_HOP, LABEL_DRNL, LABEL_DEGREE = 0, 1, 2, 3, 4
 REC_OK, REC_ARENA_OVERFLOW, REC_BAD_LINK, REC_MIRROR = 0, 1, 2, 3
@@ -24,7 +25,7 @@ CTR_SUM_N_ALL, CTR_SUM_D_ALL, CTR_MIRRORS = 8, 9, 10
 EXPORTS = ['s3_version', 's3_error_string', 's3_last_cuda_error', 's3_num_records', 's3_extract_smem_bytes',
            's3_min_arena_words', 's3_extract_tier',
            's3_extract', 's3_plan', 's3_plan_items', 's3_diffuse', 's3_gather', 's3_gather_ccn', 's3_ccn_chain', 's3_plan_full', 's3_sign_full', 's3_joint_rows', 's3_sign_head', 's3_walk_sets', 's3_dump_edges',
-           's3_pair_table_slots', 's3_pair_links', 's3_gather_peers', 's3_fill_x0', 's3_peer_alloc', 's3_peer_free', 's3_peer_export',
+           's3_pair_table_slots', 's3_pair_links', 's3_gather_peers', 's3_fill_x0', 's3_fill_mirrors', 's3_peer_alloc', 's3_peer_free', 's3_peer_export',
            's3_peer_open', 's3_peer_close', 's3_probe_l2_read', 's3_probe_fma', 's3_probe_fma2', 's3_segment_pool']
 
 
@@ -43,7 +44,8 @@ class Batch(C.Structure):
                 ('row_ptr', C.c_void_p), ('item_ptr', C.c_void_p), ('item_rec', C.c_void_p), ('order', C.c_void_p),
                 ('walk_sets', C.c_void_p), ('walk_counts', C.c_void_p), ('link_src_set', C.c_void_p),
                 ('link_dst_set', C.c_void_p), ('walk_cap', C.c_int32), ('reserved2', C.c_int32),
-                ('out_link', C.c_void_p), ('mirror', C.c_void_p), ('link_base', C.c_int64)]
+                ('out_link', C.c_void_p), ('mirror', C.c_void_p), ('link_base', C.c_int64),
+                ('ratio_per_hop', C.c_double), ('max_nodes_per_hop', C.c_int32), ('cap_seed', C.c_uint32)]
 
 
 class S3Error(RuntimeError):
@@ -99,6 +101,8 @@ def lib():
         L.s3_pair_links.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.s3_gather_peers.argtypes = [C.POINTER(Graph), C.POINTER(Batch), C.c_int64, C.POINTER(C.c_void_p), C.c_int32,
                                       C.c_int64, C.c_int64, C.c_int32, C.c_void_p]
+        L.s3_fill_mirrors.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int64, C.c_int64,
+                                      C.c_void_p]
         L.s3_fill_x0.argtypes = [C.POINTER(Graph), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
         L.s3_probe_l2_read.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
         L.s3_segment_pool.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
@@ -111,7 +115,7 @@ def lib():
         L.s3_peer_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
         L.s3_peer_close.argtypes = [C.c_void_p]
         for fn in ('s3_extract', 's3_plan', 's3_plan_items', 's3_diffuse', 's3_gather', 's3_gather_ccn', 's3_ccn_chain', 's3_plan_full', 's3_sign_full', 's3_joint_rows', 's3_sign_head', 's3_walk_sets',
-                   's3_dump_edges', 's3_pair_links', 's3_gather_peers', 's3_fill_x0', 's3_peer_alloc', 's3_peer_free', 's3_peer_export',
+                   's3_dump_edges', 's3_pair_links', 's3_gather_peers', 's3_fill_x0', 's3_fill_mirrors', 's3_peer_alloc', 's3_peer_free', 's3_peer_export',
                    's3_peer_open', 's3_peer_close', 's3_probe_l2_read', 's3_probe_fma', 's3_probe_fma2', 's3_segment_pool'):
             getattr(L, fn).restype = C.c_int
         _lib = L

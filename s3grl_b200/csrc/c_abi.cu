@@ -153,7 +153,7 @@ int s3_gather_ccn(const s3_graph* g, const s3_batch* b, int64_t num_items, float
 }
 
 int s3_gather_peers(const s3_graph* g, const s3_batch* b, int64_t num_records, float* const* dst_bases, int32_t num_dst,
-                    int64_t op_stride, int64_t ldo, int32_t skip_op0, void* stream) {
+                    int64_t op_stride, int64_t ldo, int32_t flags, void* stream) {
     int rc = check_graph(g, true);
     if (rc != S3_OK) return rc;
     rc = check_batch(b);
@@ -164,7 +164,8 @@ int s3_gather_peers(const s3_graph* g, const s3_batch* b, int64_t num_records, f
     s3::PeerDst peers;
     peers.num_dst = num_dst;
     peers.op_stride = op_stride;
-    peers.skip_op0 = skip_op0 ? 1 : 0;
+    peers.skip_op0 = (flags & S3_PEERS_LOCAL_X0) ? 1 : 0;
+    peers.skip_chain = (flags & S3_PEERS_LOCAL_MIRRORS) ? 1 : 0;
     for (int d = 0; d < S3_MAX_PEERS; ++d) peers.base[d] = nullptr;
     for (int d = 0; d < num_dst; ++d) {
         if (!dst_bases[d]) return S3_ERR_INVALID_ARG;
@@ -184,6 +185,21 @@ int s3_fill_x0(const s3_graph* g, const int64_t* link_src, const int64_t* link_d
     if (num_links < 0 || ldo < g->num_feat + 1) return S3_ERR_INVALID_ARG;
     if (num_links > 0 && (!link_src || !link_dst || !out0)) return S3_ERR_INVALID_ARG;
     cudaError_t e = s3::launch_fill_x0(*g, link_src, link_dst, num_links, out0, ldo, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? S3_OK : cuda_fail(e);
+}
+
+int s3_fill_mirrors(const int64_t* mirror, int64_t num_links, float* const* ops, int32_t first_op, int32_t num_ops, int64_t num_cols,
+                    int64_t ldo, void* stream) {
+    if (num_links < 0 || first_op < 0 || num_ops < first_op || num_ops > 2 * S3_MAX_K || num_cols < 1 || ldo < num_cols)
+        return S3_ERR_INVALID_ARG;
+    if (num_links > 0 && (!mirror || !ops)) return S3_ERR_INVALID_ARG;
+    s3::OutPtrs o;
+    memset(&o, 0, sizeof(o));
+    for (int k = first_op; k < num_ops; ++k) {
+        if (!ops[k] && num_links > 0) return S3_ERR_INVALID_ARG;
+        o.p[k] = ops[k];
+    }
+    cudaError_t e = s3::launch_fill_mirrors(mirror, num_links, o, first_op, num_ops, num_cols, ldo, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? S3_OK : cuda_fail(e);
 }
 

@@ -76,6 +76,42 @@ __host__ __device__ inline bool chain_eligible(int flags, int strategy, int64_t 
            chain_fixed_words(n, m, n1) + 2 * n * 8 <= kChainSmemBytes / 4;
 }
 
+// ---- deterministic per-hop cap (s3_batch.ratio_per_hop / max_nodes_per_hop / cap_seed; reference utils.py:66-70) ----
+__host__ __device__ inline uint32_t fmix32(uint32_t h) {  // murmur3 finaliser: a bijection of the 32-bit ids
+    h ^= h >> 16;
+    h *= 0x85ebca6bu;
+    h ^= h >> 13;
+    h *= 0xc2b2ae35u;
+    h ^= h >> 16;
+    return h;
+}
+// nodes a hop keeps out of `count` new ones: min(int(ratio * count), max) as the reference computes it
+__host__ __device__ inline int cap_keep(int count, double ratio, int max_nodes) {
+    int k = count;
+    if (ratio > 0.0 && ratio < 1.0) k = (int)(ratio * (double)count);
+    if (max_nodes > 0 && max_nodes < k) k = max_nodes;
+    return k;
+}
+inline bool batch_caps(const s3_batch& b) {
+    return b.flow == S3_FLOW_POS && !b.walk_sets && ((b.ratio_per_hop > 0.0 && b.ratio_per_hop < 1.0) || b.max_nodes_per_hop > 0);
+}
+// One pass of the 4 x 8-bit radix select over 32-bit rank keys, run by the whole CTA after its threads have filled
+// hist[256] with the counts of the keys that match `prefix` on the higher bytes: thread 0 finds the byte of the
+// krem-th smallest key. sel[0] = prefix (in/out), sel[1] = krem (in/out). Contains two __syncthreads().
+__device__ __forceinline__ void radix_pick(int* hist, int* sel) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int krem = sel[1], cum = 0, b = 0;
+        for (; b < 255; ++b) {
+            if (cum + hist[b] >= krem) break;
+            cum += hist[b];
+        }
+        sel[0] = (int)(((uint32_t)sel[0] << 8) | (uint32_t)b);
+        sel[1] = krem - cum;
+    }
+    __syncthreads();
+}
+
 // link pairing (pair.cu) applies to fixed-row PoS batches whose rows are not all stored (no parity dump)
 inline bool batch_pairing(const s3_batch& b) {
     return b.mirror && b.flow == S3_FLOW_POS && b.strategy == S3_STRATEGY_NONE && !(b.flags & S3_BATCH_STORE_ALL_ROWS) &&
@@ -131,6 +167,7 @@ struct PeerDst {  // s3_gather_peers destinations
     int num_dst;
     int64_t op_stride;
     int skip_op0;
+    int skip_chain;
 };
 
 // launchers (defined in the .cu files, called from c_abi.cu)
@@ -144,6 +181,8 @@ cudaError_t launch_plan_items(const s3_batch& b, cudaStream_t st);
 cudaError_t launch_diffuse(const s3_graph& g, const s3_batch& b, int64_t num_items, cudaStream_t st);
 cudaError_t launch_gather(const s3_graph& g, const s3_batch& b, int64_t num_items, const OutPtrs& out,
                           int64_t ldo, int64_t row_base, bool ccn, cudaStream_t st, const PeerDst* peers = nullptr);
+cudaError_t launch_fill_mirrors(const int64_t* mirror, int64_t num_links, const OutPtrs& ops, int first_op, int num_ops,
+                                int64_t cols, int64_t ldo, cudaStream_t st);
 cudaError_t launch_fill_x0(const s3_graph& g, const int64_t* src, const int64_t* dst, int64_t num_links, float* out, int64_t ldo,
                            cudaStream_t st);
 cudaError_t launch_pair_links(const int64_t* src, const int64_t* dst, int64_t L, int64_t N, int64_t* table, int64_t slots,

@@ -28,10 +28,10 @@ namespace s3 {
 namespace {
 
 constexpr int kDiffLanes = 4;  // lanes per row (rows of the reference's graphs are short: 4 leave fewer lanes idle than 8)
-// floats per shared z buffer (two buffers, dynamic shared memory): 2-row items (intersection) n <= 2048 in 32 KB;
-// 8-row items (union) n <= 1536 in 96 KB, two CTAs per SM — with the 32 KB of round 1 every PubMed union item above
-// 512 nodes (most of them: mean n = 930) kept z in global memory and the sweeps ran at L2 latency
-__host__ __device__ constexpr int z_cap(int sc) { return sc == 8 ? 1536 * 8 : 4096; }
+// floats per shared z buffer (two buffers, dynamic shared memory): n <= 2048 with 2 rows, 512 with 8. Measured in
+// round 2: 96 KB for the 8-row union items (n <= 1536, two CTAs per SM) was SLOWER than 32 KB with z of the larger
+// items in global memory (306 vs 276 ms per PubMed step): the sweeps are latency bound and want resident CTAs.
+__host__ __device__ constexpr int z_cap(int) { return 4096; }
 
 struct DiffuseParams {
     const int64_t* __restrict__ indptr;  // SoP: global degrees

@@ -59,6 +59,10 @@ struct ExtractParams {
     const int64_t* __restrict__ out_link;  // link pairing (s3_batch): global link index of a record
     const int64_t* __restrict__ mirror;    // chain table of s3_pair_links, or null
     int64_t link_base;
+    int caps;                              // per-hop caps active (s3_batch.ratio_per_hop / max_nodes_per_hop)
+    double cap_ratio;
+    int cap_max;
+    uint32_t cap_seed;
 };
 
 constexpr int kStreamLanes = 4;  // lanes per streamed (hop-K) row
@@ -84,6 +88,45 @@ __device__ __forceinline__ int local_id(int g, int s0, int s1, int nseed, const 
     if (nseed == 2 && g == s1) lid = 1;
     if (g == s0) lid = 0;
     return lid;
+}
+
+// Deterministic per-hop cap (reference utils.py:66-70): keep the `keep` nodes of the level bitmap `cur` with the
+// smallest fmix32(node ^ seed) — 4 x 8-bit radix select over the rank keys (a bijection of the ids: no ties), then
+// the dropped bits are cleared. Whole CTA; `hist` = 256 + 2 ints of shared scratch. Not on the hot path of the
+// reference's configurations (none caps), hence not inlined.
+__device__ __noinline__ void cap_level(uint32_t* cur, int w0, int w1, int keep, uint32_t seed, int* hist) {
+    int* sel = hist + 256;
+    if (threadIdx.x == 0) {
+        sel[0] = 0;
+        sel[1] = keep;
+    }
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        const uint32_t prefix = (uint32_t)sel[0];
+        for (int w = w0; w < w1; ++w) {
+            uint32_t bb = cur[w];
+            while (bb) {
+                const int bit = __ffs(bb) - 1;
+                bb &= bb - 1;
+                const uint32_t hsh = fmix32((uint32_t)(w * 32 + bit) ^ seed);
+                if (pass == 0 || (hsh >> (shift + 8)) == prefix) atomicAdd(&hist[(hsh >> shift) & 255u], 1);
+            }
+        }
+        radix_pick(hist, sel);
+    }
+    const uint32_t thr = (uint32_t)sel[0];  // rank key of the keep-th smallest
+    for (int w = w0; w < w1; ++w) {
+        uint32_t bb = cur[w], kept = 0u;
+        while (bb) {
+            const int bit = __ffs(bb) - 1;
+            bb &= bb - 1;
+            if (fmix32((uint32_t)(w * 32 + bit) ^ seed) <= thr) kept |= 1u << bit;
+        }
+        cur[w] = kept;
+    }
+    __syncthreads();
 }
 
 template <int SC>  // selected rows of the first work item == number of seeds: 2 (PoS), 1 (SoP)
@@ -191,6 +234,7 @@ __global__ void __launch_bounds__(kExtractThreads, 5) front_kernel(ExtractParams
         const int chunk = (W + T - 1) / T;
         const int w0 = min(W, tid * chunk), w1 = min(W, w0 + chunk);
         int nlev = 0, n = nseed, flo = 0;
+        bool capped = false;
         for (int l = 0; l < h; ++l) {
             uint32_t* cur = Lb + (size_t)l * W;
             // frontier = slab_nodes[flo, n): one 8-lane group per node, 32 B of column ids per step
@@ -211,6 +255,16 @@ __global__ void __launch_bounds__(kExtractThreads, 5) front_kernel(ExtractParams
             }
             int total;
             int run = block_exclusive_scan(local, s_scan, &total);
+            if (p.caps) {  // utils.py:66-70; V keeps the dropped nodes (visited), the level bitmap loses them
+                const int keep = cap_keep(total, p.cap_ratio, p.cap_max);
+                if (keep < total) {  // block-uniform
+                    cap_level(cur, w0, w1, keep, p.cap_seed, reinterpret_cast<int*>(&s_z[0][0]));
+                    capped = true;
+                    local = 0;
+                    for (int w = w0; w < w1; ++w) local += __popc(cur[w]);
+                    run = block_exclusive_scan(local, s_scan, &total);
+                }
+            }
             uint32_t* pl = pre + (size_t)l * W;
             for (int w = w0; w < w1; ++w) {
                 const uint32_t bits = cur[w];
@@ -240,6 +294,20 @@ __global__ void __launch_bounds__(kExtractThreads, 5) front_kernel(ExtractParams
             flo = n;
             n += total;
             nlev = l + 1;
+            __syncthreads();
+        }
+        if (capped) {  // V = members only from here on (it was "visited" during the BFS): seeds + kept levels
+            __syncthreads();
+            for (int i = tid; i < W; i += T) {
+                uint32_t bits = 0u;
+                for (int l = 0; l < h; ++l) bits |= Lb[(size_t)l * W + i];
+                V[i] = bits;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                V[s0 >> 5] |= 1u << (s0 & 31);
+                if (nseed == 2) V[s1 >> 5] |= 1u << (s1 & 31);
+            }
             __syncthreads();
         }
         // D = sum of global degrees (block reduction); hop_end[l] = nodes of hop <= l
@@ -657,6 +725,10 @@ cudaError_t launch_extract_bitmap(const s3_graph& g, const s3_batch& b, cudaStre
     p.off = b.off;
     p.cnt = b.cnt;
     p.counters = reinterpret_cast<unsigned long long*>(b.counters);
+    p.caps = batch_caps(b) ? 1 : 0;
+    p.cap_ratio = b.ratio_per_hop;
+    p.cap_max = b.max_nodes_per_hop;
+    p.cap_seed = b.cap_seed;
     p.out_link = b.out_link;
     p.mirror = batch_pairing(b) ? b.mirror : nullptr;
     p.link_base = b.link_base;

@@ -41,6 +41,10 @@ struct SortedParams {
     const int64_t* __restrict__ src_set;      // [num_records] row of walk_sets for the source / destination
     const int64_t* __restrict__ dst_set;
     int walk_cap;
+    int caps;  // per-hop cap of the one hop (s3_batch.ratio_per_hop / max_nodes_per_hop / cap_seed)
+    double cap_ratio;
+    int cap_max;
+    uint32_t cap_seed;
     int32_t* arena;
     int64_t arena_words;
     int64_t slab_stride;  // words per CTA slab: prefix arrays of both adjacency lists
@@ -356,36 +360,74 @@ __global__ void __launch_bounds__(kExtractThreads, 4) front_sorted_kernel(Sorted
         int32_t* PB = PA + du + 1;  // [dv + 1]
 
         // ---- keep flags and their exclusive prefix sums: A minus {u,v}; B minus {u,v} minus A ----
+        // (with a per-hop cap: a second round keeps only the nodes whose rank key is <= the selected threshold)
         int nA = 0, nB = 0;
-        for (int base = 0; base < du; base += T) {
-            const int i = base + tid;
-            int f = 0;
-            if (i < du) {
-                const int x = A[i];
-                f = (x != u && x != v) ? 1 : 0;
+        bool use_thr = false;
+        uint32_t thr = 0u;
+        for (int round = 0; round < 2; ++round) {
+            nA = 0;
+            nB = 0;
+            for (int base = 0; base < du; base += T) {
+                const int i = base + tid;
+                int f = 0;
+                if (i < du) {
+                    const int x = A[i];
+                    f = (x != u && x != v && (!use_thr || fmix32((uint32_t)x ^ p.cap_seed) <= thr)) ? 1 : 0;
+                }
+                int tot;
+                const int ex = block_exclusive_scan(f, s_scan, &tot);
+                if (i < du) PA[i] = nA + ex;
+                nA += tot;
+                __syncthreads();
             }
-            int tot;
-            const int ex = block_exclusive_scan(f, s_scan, &tot);
-            if (i < du) PA[i] = nA + ex;
-            nA += tot;
-            __syncthreads();
-        }
-        for (int base = 0; base < dv; base += T) {
-            const int k = base + tid;
-            int f = 0;
-            if (k < dv) {
-                const int y = B[k];
-                f = (y != u && y != v && !contains(A, du, y)) ? 1 : 0;
+            for (int base = 0; base < dv; base += T) {
+                const int k = base + tid;
+                int f = 0;
+                if (k < dv) {
+                    const int y = B[k];
+                    f = (y != u && y != v && (!use_thr || fmix32((uint32_t)y ^ p.cap_seed) <= thr) && !contains(A, du, y)) ? 1 : 0;
+                }
+                int tot;
+                const int ex = block_exclusive_scan(f, s_scan, &tot);
+                if (k < dv) PB[k] = nB + ex;
+                nB += tot;
+                __syncthreads();
             }
-            int tot;
-            const int ex = block_exclusive_scan(f, s_scan, &tot);
-            if (k < dv) PB[k] = nB + ex;
-            nB += tot;
+            if (tid == 0) {
+                PA[du] = nA;
+                PB[dv] = nB;
+            }
+            const int keep = (p.caps && !p.walk_sets && round == 0) ? cap_keep(nA + nB, p.cap_ratio, p.cap_max) : nA + nB;
+            if (keep >= nA + nB) break;  // block-uniform: no cap, or nothing to drop
+            // utils.py:66-70 with the deterministic rule: radix select of the keep-th smallest rank key among the
+            // kept elements of both lists (scratch: the z buffers, not live yet)
+            int* hist = reinterpret_cast<int*>(&s_z[0][0]);
+            int* sel = hist + 256;
+            __syncthreads();  // PA[du], PB[dv]
+            if (tid == 0) {
+                sel[0] = 0;
+                sel[1] = keep;
+            }
+            for (int pass = 0; pass < 4; ++pass) {
+                const int shift = 24 - 8 * pass;
+                for (int i = tid; i < 256; i += T) hist[i] = 0;
+                __syncthreads();
+                const uint32_t prefix = (uint32_t)sel[0];
+                for (int i = tid; i < du; i += T) {
+                    if (PA[i + 1] == PA[i]) continue;
+                    const uint32_t hsh = fmix32((uint32_t)A[i] ^ p.cap_seed);
+                    if (pass == 0 || (hsh >> (shift + 8)) == prefix) atomicAdd(&hist[(hsh >> shift) & 255u], 1);
+                }
+                for (int k = tid; k < dv; k += T) {
+                    if (PB[k + 1] == PB[k]) continue;
+                    const uint32_t hsh = fmix32((uint32_t)B[k] ^ p.cap_seed);
+                    if (pass == 0 || (hsh >> (shift + 8)) == prefix) atomicAdd(&hist[(hsh >> shift) & 255u], 1);
+                }
+                radix_pick(hist, sel);
+            }
+            thr = (uint32_t)sel[0];
+            use_thr = true;
             __syncthreads();
-        }
-        if (tid == 0) {
-            PA[du] = nA;
-            PB[dv] = nB;
         }
         const int n = 2 + nA + nB;
 
@@ -635,6 +677,10 @@ cudaError_t launch_extract_sorted(const s3_graph& g, const s3_batch& b, cudaStre
     p.src_set = b.link_src_set;
     p.dst_set = b.link_dst_set;
     p.walk_cap = b.walk_cap;
+    p.caps = batch_caps(b) ? 1 : 0;
+    p.cap_ratio = b.ratio_per_hop;
+    p.cap_max = b.max_nodes_per_hop;
+    p.cap_seed = b.cap_seed;
     p.arena = b.arena;
     p.arena_words = b.arena_words;
     p.off = b.off;

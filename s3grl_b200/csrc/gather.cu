@@ -32,6 +32,7 @@ cudaError_t launch_gather(const s3_graph& g, const s3_batch& b, int64_t num_item
     p.link_base = b.link_base;
     p.num_dst = 0;
     p.skip_op0 = 0;
+    p.skip_chain = 0;
     p.op_stride = 0;
     for (int d = 0; d < S3_MAX_PEERS; ++d) p.dst_base[d] = nullptr;
     if (peers) {
@@ -39,6 +40,7 @@ cudaError_t launch_gather(const s3_graph& g, const s3_batch& b, int64_t num_item
         p.num_dst = peers->num_dst;
         p.op_stride = peers->op_stride;
         p.skip_op0 = peers->skip_op0;
+        p.skip_chain = peers->skip_chain;
         for (int d = 0; d < peers->num_dst; ++d) p.dst_base[d] = peers->base[d];
     }
 
@@ -96,6 +98,39 @@ __global__ void __launch_bounds__(128) fill_x0_kernel(const float* __restrict__ 
     for (int f = threadIdx.x; f < F; f += 128) o[1 + f] = __ldg(xr + f);
 }
 }  // namespace
+
+namespace {
+// Rows of paired links, locally: one CTA per link that heads a chain copies its two rows of operators first_op..
+// to every chain member (rows exchanged for the opposite direction). Plain copy, consecutive lanes on consecutive
+// floats.
+__global__ void __launch_bounds__(128) fill_mirrors_kernel(const int64_t* __restrict__ mirror, OutPtrs ops, int first_op,
+                                                           int num_ops, int cols, int64_t ldo) {
+    const int64_t p = blockIdx.x;
+    long long m = mirror[p];
+    if (m < 0) return;  // unpaired, or a member itself
+    while (m >= 0) {
+        const long long v = -2 - (long long)mirror[m];
+        const int swap = (int)(v & 1);
+        for (int k = first_op; k < num_ops; ++k) {
+            const float* src = ops.p[k] + 2 * p * ldo;
+            float* dst = ops.p[k] + 2 * m * ldo;
+            for (int i = threadIdx.x; i < 2 * cols; i += 128) {
+                const int r = i >= cols ? 1 : 0, c = i - r * cols;
+                dst[(swap ? 1 - r : r) * ldo + c] = src[r * ldo + c];
+            }
+        }
+        m = (v >> 1) - 1;
+    }
+}
+}  // namespace
+
+cudaError_t launch_fill_mirrors(const int64_t* mirror, int64_t num_links, const OutPtrs& ops, int first_op, int num_ops,
+                                int64_t cols, int64_t ldo, cudaStream_t st) {
+    if (num_links == 0) return cudaSuccess;
+    if (num_links > 0x7fffffff) return cudaErrorInvalidValue;
+    fill_mirrors_kernel<<<(unsigned)num_links, 128, 0, st>>>(mirror, ops, first_op, num_ops, (int)cols, ldo);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_fill_x0(const s3_graph& g, const int64_t* src, const int64_t* dst, int64_t num_links, float* out, int64_t ldo,
                            cudaStream_t st) {

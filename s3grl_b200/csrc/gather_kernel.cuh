@@ -56,6 +56,9 @@ struct GatherParams {
     // s3_gather_peers: operator 0 (x itself, an exact copy of [1 | X[node]]) is not sent over NVLink — every GPU holds
     // X and writes those rows locally for the whole link list (s3_fill_x0): a quarter less traffic at K = 3
     int skip_op0;
+    // s3_gather_peers: rows of paired links (chain members) are not sent either — every GPU copies them from the
+    // first link's rows after the exchange (s3_fill_mirrors): 23 % fewer rows over NVLink on the PubMed list
+    int skip_chain;
 };
 // per-(SC, K1 range) translation units, so that the ~130 instantiations compile in parallel
 #define S3_DECL_GATHER_TU(name) \
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(kGatherThreads, gather_min_blocks(K1 * SC * C)
     const int64_t gl = p.out_link ? p.out_link[rec / rpl] : p.link_base + rec / rpl;  // global link index (fixed-row flows)
     const int64_t row0 = (p.out_link ? (gl * rpl + rec % rpl) * nseed
                                      : p.row_base + (p.row_ptr ? p.row_ptr[rec] : rec * (int64_t)nseed)) + first_sel;
-    const long long chain = (p.mirror && !p.ccn) ? (long long)p.mirror[gl] : -1;
+    const long long chain = (p.mirror && !p.ccn && !p.skip_chain) ? (long long)p.mirror[gl] : -1;
     float* s_row = reinterpret_cast<float*>(smem4);  // element e of the output row sits at s_row[e - f0]
     const int f0 = blockIdx.y * C * tpr * 4;         // first feature of this CTA's column chunk
     const int nfl = min(C * tpr * 4, p.F - f0);

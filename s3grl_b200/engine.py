@@ -211,8 +211,14 @@ class _Call:
 
     def __init__(self, graph, links, num_hops, sign_k, flow, strategy, batch_records, out, return_graphs,
                  arena_words, stream, profile, overlap, host_out, force_sorted_tier, walk=None, ccn_mode=None,
-                 pair=True, out_link=None, mirror=None, peers=None):
+                 pair=True, out_link=None, mirror=None, peers=None, ratio_per_hop=1.0, max_nodes_per_hop=None, cap_seed=0):
         self.lib = L.lib()
+        # per-hop caps of the BFS (reference utils.py:66-70) with the deterministic rank rule of include/s3grl_b200.h
+        self.cap_ratio = 1.0 if ratio_per_hop is None else float(ratio_per_hop)
+        self.cap_max = 0 if max_nodes_per_hop is None else int(max_nodes_per_hop)
+        self.cap_seed = int(cap_seed) & 0xFFFFFFFF
+        if self.cap_ratio <= 0.0 or self.cap_max < 0:
+            raise ValueError("ratio_per_hop must be in (0, 1] and max_nodes_per_hop positive (or None)")
         if ccn_mode not in (None, 'items', 'chain'):
             raise ValueError("ccn_mode must be None, 'items' or 'chain'")
         self.ccn_mode = ccn_mode
@@ -352,7 +358,8 @@ class _Call:
                        _ptr(row_ptr), _ptr(item_ptr), _ptr(item_rec), _ptr(order),
                        _ptr(w['sets']) if w else None, _ptr(w['counts']) if w else None,
                        _ptr(w['src'][b0:]) if w else None, _ptr(w['dst'][b0:]) if w else None, w['cap'] if w else 0, 0,
-                       _ptr(ol[b0:]) if ol is not None and b1 > b0 else None, _ptr(getattr(self, 'mirror', None)), b0)
+                       _ptr(ol[b0:]) if ol is not None and b1 > b0 else None, _ptr(getattr(self, 'mirror', None)), b0,
+                       self.cap_ratio, self.cap_max, self.cap_seed)
 
     def launch(self, stage, bi, fn_name, *args, on=None):
         """Call one C entry point; with `profile`, bracket it with CUDA events on its stream."""
@@ -434,7 +441,7 @@ class _Call:
             return self.launch('gather', bi, 's3_gather', g, C.byref(batch), nrec, self.out_ptrs, self.F1, row_base, st, on=on)
         pb = self.peers
         return self.launch('gather', bi, 's3_gather_peers', g, C.byref(batch), nrec, pb.base_array, pb.world_dst, pb.op_stride,
-                           self.F1, 1 if pb.local_x0 else 0, st, on=on)
+                           self.F1, pb.flags, st, on=on)
 
     def enqueue_fixed_batch(self, bi, arena):
         g, st = C.byref(self.graph._c), self.stream_ptr
@@ -633,7 +640,7 @@ class _Call:
 def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_records=None, out=None,
                return_graphs=False, arena_words=None, stream=None, profile=None, overlap=False, defer=False,
                host_out=None, force_sorted_tier=False, walk=None, ccn_mode=None, pair=True, out_link=None, mirror=None,
-               peers=None):
+               peers=None, ratio_per_hop=1.0, max_nodes_per_hop=None, cap_seed=0):
     """Run the hot path for `links` ([2, L] int64, host or device) on `graph`; returns a
     PrecomputeResult with device tensors.
 
@@ -661,13 +668,19 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
     pair           (PoS without CCN rows, bitmap tier) link pairing: links over the same unordered node pair — both
                    directions of a training edge, SURVEY.md A.7 — share one record; the other direction's rows are
                    the same rows exchanged, bit for bit (csrc/pair.cu).  On by default; results do not depend on it.
+    ratio_per_hop, max_nodes_per_hop, cap_seed   the reference's per-hop caps (utils.py:66-70) for the PoS flows: a hop
+                   with c new nodes keeps min(int(ratio_per_hop * c), max_nodes_per_hop) of them.  The reference picks
+                   them with random.sample (no reproducible semantics, raises on Python >= 3.11); here they are the
+                   nodes with the smallest fmix32(node ^ cap_seed), so a subgraph depends on (link, seed) only and
+                   the oracle restates it exactly.  Ignored by SoP and by ScaLed walk subgraphs, as in the reference.
     out_link, mirror, peers   used by parallel.precompute_exchange: `links` is a subset of a larger list, out_link
                    its global link indices, mirror the chain table of the whole list and peers the PeerBuffers every
                    output row is stored into (this GPU's and its NVLink peers').
     Raises ValueError for invalid links (out of range, src == dst), NotImplementedError for an unknown
     strategy (as reference tuned_SIGN.py:235) or an unsupported combination."""
     call = _Call(graph, links, num_hops, sign_k, flow, strategy, batch_records, out, return_graphs, arena_words,
-                 stream, profile, overlap, host_out, force_sorted_tier, walk, ccn_mode, pair, out_link, mirror, peers)
+                 stream, profile, overlap, host_out, force_sorted_tier, walk, ccn_mode, pair, out_link, mirror, peers,
+                 ratio_per_hop, max_nodes_per_hop, cap_seed)
     return call.run(defer)
 
 
@@ -675,7 +688,8 @@ _LABEL = {'zo': L.LABEL_ZO, 'hop': L.LABEL_HOP, 'drnl': L.LABEL_DRNL, 'degree': 
 
 
 def precompute_full(graph, links, num_hops, sign_k, node_label='drnl', batch_records=None, arena_words=None,
-                    stream=None, profile=None, force_sorted_tier=False, walk=None):
+                    stream=None, profile=None, force_sorted_tier=False, walk=None, ratio_per_hop=1.0, max_nodes_per_hop=None,
+                    cap_seed=0):
     """The NON-optimised SIGN + SEAL flow (reference utils.py:497-520 with `powers_of_A` empty:
     k_hop_subgraph -> construct_pyg_graph(node_label) -> TunedSIGN(sign_k), i.e. PyG's SIGN on the
     whole enclosing subgraph): every subgraph node is an output row, x = [z | X_sub], x_k = S x_{k-1}.
@@ -696,7 +710,8 @@ def precompute_full(graph, links, num_hops, sign_k, node_label='drnl', batch_rec
         raise NotImplementedError("node_label 'degree' on a multigraph is not supported")
     label = _LABEL.get(node_label, L.LABEL_ZERO)
     call = _Call(graph, links, num_hops, sign_k, 'PoS', None, batch_records or 4096, None, False, arena_words,
-                 stream, profile, False, None, force_sorted_tier, walk)
+                 stream, profile, False, None, force_sorted_tier, walk, ratio_per_hop=ratio_per_hop,
+                 max_nodes_per_hop=max_nodes_per_hop, cap_seed=cap_seed)
     call.flags |= L.BATCH_STORE_ALL_ROWS
     dev, K, F1, lib = call.dev, call.K, call.F1, call.lib
     g, st = C.byref(graph._c), call.stream_ptr

@@ -102,9 +102,13 @@ class PeerBuffers:
     .local     K+1 torch views [2 * num_links, F+1] of this GPU's copy
     .dst       device pointers kernel 3 stores to: [multicast address] or all ranks' copies"""
 
-    def __init__(self, num_links, num_feat, sign_k, device, group=None, backend='ipc', local_x0=True):
+    def __init__(self, num_links, num_feat, sign_k, device, group=None, backend=None, local_x0=True, local_mirrors=True):
         from . import _lib as L
         self.local_x0 = bool(local_x0)      # operator 0 is written locally by every GPU (s3_fill_x0), not exchanged
+        self.local_mirrors = bool(local_mirrors)   # rows of paired links are copied locally after the exchange
+        self.flags = (L.PEERS_LOCAL_X0 if self.local_x0 else 0) | (L.PEERS_LOCAL_MIRRORS if self.local_mirrors else 0)
+        if backend is None:    # measured on this pool (profiles/): P2P stores are steady and fastest on 2 GPUs, the
+            backend = 'ipc' if dist.get_world_size(group) <= 2 else 'auto'     # multicast path wins from 4 GPUs on
         self._L, self._lib = L, L.lib()
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
@@ -223,5 +227,19 @@ def precompute_exchange(graph, links, num_hops, sign_k, buffers, flow='PoS', def
                      peers=buffers, pair=False, defer=defer, **kw)
     res._pair_table = table
     if not defer:
-        buffers.barrier()
+        exchange_finish(buffers, mirror, kw.get('stream'))
     return res, mirror
+
+
+def exchange_finish(buffers, mirror, stream=None):
+    """End of an exchange step, on the stream: the barrier (every rank's rows have landed everywhere), then — with
+    local_mirrors — every GPU copies the rows of the paired links from their first link's rows in its own memory."""
+    buffers.barrier()
+    if mirror is not None and buffers.local_mirrors and buffers.num_ops > 1:
+        dev = buffers.device
+        st = stream or torch.cuda.current_stream(dev)
+        ptrs = (C.c_void_p * buffers.num_ops)(*[o.data_ptr() for o in buffers.local])
+        with torch.cuda.device(dev):
+            buffers._L.check(buffers._lib.s3_fill_mirrors(C.c_void_p(mirror.data_ptr()), buffers.num_links, ptrs,
+                                                          1 if buffers.local_x0 else 0, buffers.num_ops, buffers.cols, buffers.cols,
+                                                          C.c_void_p(st.cuda_stream)), 's3_fill_mirrors')

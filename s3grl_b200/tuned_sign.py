@@ -84,12 +84,17 @@ def _walk_request(rw_kwargs, y):
     return dict(m=int(rw_kwargs['rw_m']), M=int(rw_kwargs['rw_M']), seed=int(rw_kwargs.get('seed', 0)))
 
 
-def _reject_unsupported(ratio_per_hop, max_nodes_per_hop, directed, rw_kwargs):
+CAP_SEED = 0     # seed of the deterministic per-hop cap; set it (or pass cap_seed=) to draw another sample
+
+
+def _caps(ratio_per_hop, max_nodes_per_hop, directed, cap_seed=None):
+    """The reference's `ratio_per_hop` / `max_nodes_per_hop` (utils.py:66-70) as engine keywords.  The reference
+    samples with random.sample on a set — unreproducible, and a TypeError on Python >= 3.11 — so the counts are the
+    reference's and the choice is the deterministic rank rule of include/s3grl_b200.h (smallest fmix32(node ^ seed))."""
     if directed:
         raise NotImplementedError("directed BFS is out of scope")
-    if (ratio_per_hop is not None and ratio_per_hop < 1.0) or max_nodes_per_hop is not None:
-        raise NotImplementedError("per-hop random down-sampling has no reproducible reference "
-                                  "(random.sample on a set, utils.py:66-70) and is not supported")
+    return dict(ratio_per_hop=1.0 if ratio_per_hop is None else ratio_per_hop, max_nodes_per_hop=max_nodes_per_hop,
+                cap_seed=CAP_SEED if cap_seed is None else cap_seed)
 
 
 class OptimizedSignOperations:
@@ -105,21 +110,21 @@ class OptimizedSignOperations:
 
     @staticmethod
     def get_PoS_prepped_ds(link_index, num_hops, A, ratio_per_hop, max_nodes_per_hop, directed, A_csc, x, y,
-                           sign_kwargs, rw_kwargs, *, device=None, output_device=None, graph=None):
+                           sign_kwargs, rw_kwargs, *, device=None, output_device=None, graph=None, cap_seed=None):
         """reference tuned_SIGN.py:137-189."""
-        _reject_unsupported(ratio_per_hop, max_nodes_per_hop, directed, rw_kwargs)
+        caps = _caps(ratio_per_hop, max_nodes_per_hop, directed, cap_seed)
         assert x is not None                       # reference tuned_SIGN.py:166
         g = device_graph(A, x, device, graph)
         host = _host_buffers(int(link_index.shape[1]), g.num_feat, sign_kwargs['sign_k'], output_device)
         return _finish(precompute(g, link_index, num_hops, sign_kwargs['sign_k'], flow='PoS', host_out=host,
-                                  walk=_walk_request(rw_kwargs, y)), y, host, output_device)
+                                  walk=_walk_request(rw_kwargs, y), **caps), y, host, output_device)
 
     @staticmethod
     def get_PoS_Plus_prepped_ds(link_index, num_hops, A, ratio_per_hop, max_nodes_per_hop, directed, A_csc, x, y,
-                                sign_kwargs, rw_kwargs, *, device=None, output_device=None, graph=None):
+                                sign_kwargs, rw_kwargs, *, device=None, output_device=None, graph=None, cap_seed=None):
         """reference tuned_SIGN.py:192-262.  `union` follows the paper semantics
         sel = [0,1] + sorted((N(0) ∪ N(1)) − {0,1}) (the reference raises for it)."""
-        _reject_unsupported(ratio_per_hop, max_nodes_per_hop, directed, rw_kwargs)
+        caps = _caps(ratio_per_hop, max_nodes_per_hop, directed, cap_seed)
         assert x is not None                       # reference tuned_SIGN.py:221
         if rw_kwargs and rw_kwargs.get('rw_m'):
             raise NotImplementedError("ScaLed random-walk subgraphs with CCN rows (PoS Plus) are not supported")
@@ -127,21 +132,22 @@ class OptimizedSignOperations:
         if strat not in ('union', 'intersection'):
             raise NotImplementedError(f"check strat {strat}")      # reference tuned_SIGN.py:235
         g = device_graph(A, x, device, graph)
-        return _finish(precompute(g, link_index, num_hops, sign_kwargs['sign_k'], flow='PoS', strategy=strat), y,
+        return _finish(precompute(g, link_index, num_hops, sign_kwargs['sign_k'], flow='PoS', strategy=strat, **caps), y,
                        output_device=output_device)
 
     @staticmethod
     def get_PoS_full_ds(link_index, num_hops, A, ratio_per_hop, max_nodes_per_hop, directed, A_csc, x, y,
-                        sign_kwargs, rw_kwargs, node_label='drnl', *, device=None, output_device=None, graph=None):
+                        sign_kwargs, rw_kwargs, node_label='drnl', *, device=None, output_device=None, graph=None,
+                        cap_seed=None):
         """The reference's non-optimised PoS branch (utils.py:497-520: k_hop_subgraph ->
         construct_pyg_graph(node_label) -> TunedSIGN(sign_k)(data, sign_k)); it has no method of its own
         in the reference, the name follows its siblings.  Every subgraph node is a row of x, x1..xK;
         `node_id` carries the global ids (canonical order: src, dst, then ascending (hop, id))."""
-        _reject_unsupported(ratio_per_hop, max_nodes_per_hop, directed, rw_kwargs)
+        caps = _caps(ratio_per_hop, max_nodes_per_hop, directed, cap_seed)
         assert x is not None, "Node features cannot be None. Check logic."      # reference utils.py:312
         g = device_graph(A, x, device, graph)
         res = precompute_full(g, link_index, num_hops, sign_kwargs['sign_k'], node_label=node_label,
-                              walk=_walk_request(rw_kwargs, y))
+                              walk=_walk_request(rw_kwargs, y), **caps)
         out = _finish(res, y, output_device=output_device)
         out.extras['node_id'] = res.node_id.to(out.xs[0].device)
         return out

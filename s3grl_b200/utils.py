@@ -10,8 +10,9 @@ from .tuned_sign import OptimizedSignOperations
 def extract_enclosing_subgraphs(link_index, A, x, y, num_hops, node_label='drnl',
                                 ratio_per_hop=1.0, max_nodes_per_hop=None,
                                 directed=False, A_csc=None, rw_kwargs=None, sign_kwargs=None, powers_of_A=None,
-                                data=None, *, device=None, output_device=None, graph=None):
+                                data=None, *, device=None, output_device=None, graph=None, cap_seed=None):
     where = dict(device=device, output_device=output_device, graph=graph)
+    pos_where = dict(where, cap_seed=cap_seed)      # the PoS flows take the per-hop caps (utils.py:66-70); SoP has no BFS
     if not sign_kwargs:
         raise NotImplementedError("only the SIGN flows (sign_kwargs) are on the accelerated path; "
                                   "SEAL / DRNL subgraph datasets are out of scope (SURVEY.md §2)")
@@ -20,7 +21,7 @@ def extract_enclosing_subgraphs(link_index, A, x, y, num_hops, node_label='drnl'
         sign_k = sign_kwargs['sign_k']
         sup = OptimizedSignOperations.get_PoS_prepped_ds(link_index, num_hops, A, ratio_per_hop,
                                                          max_nodes_per_hop, directed, A_csc, x, y,
-                                                         sign_kwargs, rw_kwargs, **where)
+                                                         sign_kwargs, rw_kwargs, **pos_where)
         if sign_k == 1:
             return sup
         sop = OptimizedSignOperations.get_SoP_prepped_ds(powers_of_A, link_index, A, x, y, **where)
@@ -30,11 +31,11 @@ def extract_enclosing_subgraphs(link_index, A, x, y, num_hops, node_label='drnl'
     elif not powers_of_A and sign_kwargs['optimize_sign'] and not sign_kwargs['k_heuristic']:
         return OptimizedSignOperations.get_PoS_prepped_ds(link_index, num_hops, A, ratio_per_hop,
                                                           max_nodes_per_hop, directed, A_csc, x, y,
-                                                          sign_kwargs, rw_kwargs, **where)
+                                                          sign_kwargs, rw_kwargs, **pos_where)
     elif not powers_of_A and sign_kwargs['optimize_sign'] and sign_kwargs['k_heuristic']:
         return OptimizedSignOperations.get_PoS_Plus_prepped_ds(link_index, num_hops, A, ratio_per_hop,
                                                                max_nodes_per_hop, directed, A_csc, x, y,
-                                                               sign_kwargs, rw_kwargs, **where)
+                                                               sign_kwargs, rw_kwargs, **pos_where)
     elif not sign_kwargs['optimize_sign']:
         # SIGN + SEAL flow (reference utils.py:497-550)
         if powers_of_A:
@@ -44,6 +45,6 @@ def extract_enclosing_subgraphs(link_index, A, x, y, num_hops, node_label='drnl'
             raise NotImplementedError("the non-optimised SoP flow (optimize_sign=False with powers_of_A, "
                                       "utils.py:521-548) is not supported")
         return OptimizedSignOperations.get_PoS_full_ds(link_index, num_hops, A, ratio_per_hop, max_nodes_per_hop,
-                                                       directed, A_csc, x, y, sign_kwargs, rw_kwargs, node_label, **where)
+                                                       directed, A_csc, x, y, sign_kwargs, rw_kwargs, node_label, **pos_where)
     else:
         raise NotImplementedError("No matching configuration for model data prep found. Please check code.")

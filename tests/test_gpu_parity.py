@@ -333,10 +333,12 @@ def test_sop_and_k5_through_reference_interface():
     out = Ops.get_PoS_prepped_ds(torch.from_numpy(c.links), 2, c.A, 1.0, None, False, None, torch.from_numpy(c.X), 0, kw, None)
     for k in range(6):
         assert_features_close(out.xs[k].numpy(), c.xs[k], what=f'yeast x{k}')
-    with pytest.raises(NotImplementedError):
-        Ops.get_PoS_prepped_ds(torch.from_numpy(c.links), 2, c.A, 0.5, None, False, None, torch.from_numpy(c.X), 0, kw, None)
-    with pytest.raises(NotImplementedError):
-        Ops.get_PoS_prepped_ds(torch.from_numpy(c.links), 2, c.A, 1.0, 50, False, None, torch.from_numpy(c.X), 0, kw, None)
+    with pytest.raises(NotImplementedError):      # directed BFS (utils.py:58-63) stays out of scope
+        Ops.get_PoS_prepped_ds(torch.from_numpy(c.links), 2, c.A, 1.0, None, True, None, torch.from_numpy(c.X), 0, kw, None)
+    capped = Ops.get_PoS_prepped_ds(torch.from_numpy(c.links), 2, c.A, 1.0, 50, False, None, torch.from_numpy(c.X), 0, kw, None)
+    ref = orc.pos_precompute(c.links, 2, c.A, c.X, 5, None, caps=dict(ratio_per_hop=1.0, max_nodes_per_hop=50, cap_seed=0))
+    for k in range(6):
+        assert_features_close(capped.xs[k].numpy(), ref['xs'][k], what=f'yeast capped x{k}')
 
 
 def test_self_loops_follow_the_reference_semantics():
@@ -663,3 +665,67 @@ def test_explicit_device_and_output_arguments():
     assert not on_host.xs[0].is_cuda and on_dev.xs[0].is_cuda and with_graph.xs[0].is_cuda
     for k in range(c.K + 1):
         assert torch.equal(on_host.xs[k], on_dev.xs[k].cpu()) and torch.equal(on_dev.xs[k], with_graph.xs[k])
+
+
+# ------------------------------------------------------------------------------------------------
+# per-hop caps (reference utils.py:66-70) with the deterministic rank rule
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('ratio,max_nodes,seed,hops', [(1.0, 5, 0, 3), (0.5, None, 7, 2), (0.7, 12, 3, 3), (1.0, 1, 9, 2),
+                                                          (0.3, 40, 1, 3), (1.0, 10000, 0, 2)])
+def test_per_hop_caps_bitmap_tier(ratio, max_nodes, seed, hops):
+    """Capped BFS on the bitmap tier against the oracle's restatement of the same rule: node lists, hop labels and
+    induced edges bit-exact, operators within tolerance; PoS Plus and the non-optimised flow take the same subgraphs."""
+    c = Case('cora_pos')
+    links = c.links[:, :60]
+    caps = dict(ratio_per_hop=ratio, max_nodes_per_hop=max_nodes, cap_seed=seed)
+    g = DeviceGraph(c.A, c.X)
+    for strategy in (None, 'intersection'):
+        ref = orc.pos_precompute(links, hops, c.A, c.X, c.K, strategy, keep_graphs=True, caps=caps)
+        res = precompute(g, links, hops, c.K, 'PoS', strategy, return_graphs=True, **caps)
+        assert np.array_equal(res.row_ptr.cpu().numpy(), ref['row_ptr'])
+        for i, (gg, r) in enumerate(zip(res.graphs, ref['graphs'])):
+            _check_indices(gg, r, f'caps {caps} link {i}')
+        for k in range(c.K + 1):
+            assert_features_close(res.xs[k].cpu().numpy(), ref['xs'][k], what=f'x{k}')
+    # without return_graphs (streamed hop-K rows, link pairing) the same numbers come out
+    plain = precompute(g, links, hops, c.K, 'PoS', None, **caps)
+    ref = orc.pos_precompute(links, hops, c.A, c.X, c.K, None, caps=caps)
+    for k in range(c.K + 1):
+        assert_features_close(plain.xs[k].cpu().numpy(), ref['xs'][k], what=f'x{k} (hot path)')
+    if max_nodes is not None and max_nodes < 100:
+        n_max = 2 + hops * max_nodes
+        assert plain.stats['max_n'] <= n_max
+
+
+@pytest.mark.parametrize('ratio,max_nodes,seed', [(1.0, 8, 0), (0.5, None, 5), (0.9, 30, 2), (1.0, 1, 4)])
+def test_per_hop_caps_sorted_tier(ratio, max_nodes, seed):
+    """The large-graph tier (num_hops = 1) with a cap: the hub rows of an R-MAT-like graph shrink to the cap."""
+    rng = np.random.default_rng(300 + seed)
+    A = _random_graph(rng, 2000, 30000)
+    hub = int(np.argmax(np.diff(A.indptr)))
+    X = rng.random((2000, 17), dtype=np.float32)
+    links = rng.integers(0, 2000, (2, 80))
+    links[0, :8] = hub
+    links = links[:, links[0] != links[1]]
+    caps = dict(ratio_per_hop=ratio, max_nodes_per_hop=max_nodes, cap_seed=seed)
+    ref = orc.pos_precompute(links, 1, A, X, 3, None, keep_graphs=True, caps=caps)
+    res = precompute(DeviceGraph(A, X), links, 1, 3, 'PoS', None, return_graphs=True, force_sorted_tier=True, **caps)
+    for i, (gg, r) in enumerate(zip(res.graphs, ref['graphs'])):
+        _check_indices(gg, r, f'link {i}')
+    for k in range(4):
+        assert_features_close(res.xs[k].cpu().numpy(), ref['xs'][k], what=f'x{k}')
+    both = precompute(DeviceGraph(A, X), links, 1, 3, 'PoS', None, **caps)          # bitmap tier: same subgraphs
+    for k in range(4):
+        assert_features_close(both.xs[k].cpu().numpy(), ref['xs'][k], what=f'bitmap x{k}')
+
+
+def test_per_hop_caps_through_the_reference_interface():
+    """ratio_per_hop / max_nodes_per_hop of extract_enclosing_subgraphs (utils.py:446) are honoured, not rejected."""
+    from s3grl_b200 import extract_enclosing_subgraphs
+    c = Case('cora_pos')
+    kw = dict(sign_k=c.K, use_feature=True, sign_type='PoS', optimize_sign=True, k_heuristic=0, k_node_set_strategy=None)
+    out = extract_enclosing_subgraphs(torch.from_numpy(c.links[:, :30]), c.A, torch.from_numpy(c.X), 1, 3, 'zo', 0.6, 25, False,
+                                      None, None, kw, powers_of_A=[], data=None, cap_seed=11)
+    ref = orc.pos_precompute(c.links[:, :30], 3, c.A, c.X, c.K, None, caps=dict(ratio_per_hop=0.6, max_nodes_per_hop=25, cap_seed=11))
+    for k in range(c.K + 1):
+        assert_features_close(out.xs[k].numpy(), ref['xs'][k], what=f'x{k}')
