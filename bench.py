@@ -106,23 +106,44 @@ def build_workload(name):
     raise SystemExit(f"unknown workload {name}")
 
 
-def build_rmat_workload(args, dev):
-    """BASELINE config 5: R-MAT (0.57, 0.19, 0.19, 0.05), ids reduced mod N, symmetrised,
-    de-duplicated; F = 128 row-normalised features; half the targets are edges, half random pairs;
-    num_hops = 1, sign_k = 3.  Built on the GPU.  Targets are restricted to endpoints of degree <=
-    --rmat-degree-cap: the exact one-hop subgraph of a hub link has 10^4..10^5 nodes and ~10^8
-    adjacency entries to intersect (the reference only copes with such graphs through random
-    per-hop caps, which have no reproducible semantics), see DESIGN.md §6."""
+_RMAT = {}
+
+
+def build_rmat_graph(args, dev):
+    """BASELINE config 5 (SURVEY.md §8d): R-MAT (0.57, 0.19, 0.19, 0.05), ids reduced mod N, symmetrised, de-duplicated;
+    F = 128 row-normalised features.  Built on the GPU once per process (seeds 42 / 43)."""
     import torch
     from s3grl_b200 import DeviceGraph, datasets as ds
-    N, E, Lk, cap = args.rmat_nodes, args.rmat_edges, args.rmat_links, args.rmat_degree_cap
-    scale = int(np.ceil(np.log2(N)))
-    indptr, indices = ds.rmat_csr_torch(scale, E, N, seed=42, device=dev)
+    key = (args.rmat_nodes, args.rmat_edges, str(dev))
+    if key not in _RMAT:
+        _RMAT.clear()
+        N, E = args.rmat_nodes, args.rmat_edges
+        scale = int(np.ceil(np.log2(N)))
+        indptr, indices = ds.rmat_csr_torch(scale, E, N, seed=42, device=dev)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(43)
+        X = torch.rand((N, 128), device=dev, generator=gen)
+        X /= X.sum(1, keepdim=True)
+        g = DeviceGraph.from_device_csr(indptr, indices, X)
+        _RMAT[key] = dict(g=g, indptr=indptr, indices=indices, deg=indptr[1:] - indptr[:-1], scale=scale)
+    return _RMAT[key]
+
+
+def build_rmat_workload(args, dev, degree_cap=None, num_links=None, max_nodes_per_hop=None):
+    """Targets on the R-MAT graph: half stored edges, half random pairs (seed 44), num_hops = 1, sign_k = 3.
+    degree_cap        restrict targets to endpoints of degree <= cap (0 / None: any degree).  The EXACT one-hop subgraph
+                      of a hub link has 10^4..10^5 nodes and ~10^8 adjacency entries to intersect — the reference only
+                      copes with such graphs through its per-hop caps (utils.py:66-70), see DESIGN.md §6.
+    max_nodes_per_hop the reference's cap, with this implementation's deterministic rank rule: every subgraph has at
+                      most 2 + cap nodes, so targets of ANY degree are served."""
+    import torch
+    G = build_rmat_graph(args, dev)
+    g, indptr, indices, deg = G['g'], G['indptr'], G['indices'], G['deg']
+    N, E = args.rmat_nodes, args.rmat_edges
+    Lk = num_links or args.rmat_links
+    cap = args.rmat_degree_cap if degree_cap is None else degree_cap
+    lim = cap if cap and cap > 0 else int(deg.max())
     gen = torch.Generator(device=dev)
-    gen.manual_seed(43)
-    X = torch.rand((N, 128), device=dev, generator=gen)
-    X /= X.sum(1, keepdim=True)
-    deg = indptr[1:] - indptr[:-1]
     gen.manual_seed(44)
     nnz = indices.numel()
     # positives: uniformly sampled stored entries (u, v) with both degrees <= cap
@@ -131,21 +152,22 @@ def build_rmat_workload(args, dev):
         e = torch.randint(0, nnz, (Lk,), device=dev, generator=gen)
         u = torch.searchsorted(indptr, e, right=True) - 1
         v = indices[e].to(torch.int64)
-        ok = (deg[u] <= cap) & (deg[v] <= cap)
+        ok = (deg[u] <= lim) & (deg[v] <= lim)
         pos = torch.cat([pos, torch.stack([u[ok], v[ok]])], 1)
     neg = torch.empty((2, 0), dtype=torch.int64, device=dev)
     while neg.shape[1] < Lk - Lk // 2:
         u = torch.randint(0, N, (Lk,), device=dev, generator=gen)
         v = torch.randint(0, N, (Lk,), device=dev, generator=gen)
-        ok = (u != v) & (deg[u] <= cap) & (deg[v] <= cap)
+        ok = (u != v) & (deg[u] <= lim) & (deg[v] <= lim)
         neg = torch.cat([neg, torch.stack([u[ok], v[ok]])], 1)
     links = torch.cat([pos[:, :Lk // 2], neg[:, :Lk - Lk // 2]], 1).contiguous()
-    g = DeviceGraph.from_device_csr(indptr, indices, X)
-    desc = (f"synthetic R-MAT (0.57,0.19,0.19,0.05) scale {scale}, N={N}, {E} edge samples -> nnz={nnz}, max degree "
+    desc = (f"synthetic R-MAT (0.57,0.19,0.19,0.05) scale {G['scale']}, N={N}, {E} edge samples -> nnz={nnz}, max degree "
             f"{g.max_degree}; X F=128 uniform row-normalised; {Lk} targets (half edges, half random pairs) with endpoint "
-            f"degree <= {cap}; PoS num_hops=1 sign_k=3; graph and targets generated on the GPU (seeds 42/43/44)")
+            f"degree {'<= ' + str(cap) if cap and cap > 0 else 'unrestricted'}; PoS num_hops=1 sign_k=3"
+            + (f", max_nodes_per_hop={max_nodes_per_hop} (deterministic rank rule)" if max_nodes_per_hop else ", exact subgraphs (no per-hop cap)")
+            + "; graph and targets generated on the GPU (seeds 42/43/44)")
     return dict(graph=g, links_dev=links, links=links.cpu().numpy(), num_hops=1, K=3, flow='PoS', strategy=None, desc=desc,
-                A=None, X=None)
+                A=None, X=None, caps=dict(max_nodes_per_hop=max_nodes_per_hop) if max_nodes_per_hop else {})
 
 
 # ----------------------------------------------------------------------------------------
@@ -362,6 +384,7 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
     a, b = (0, Lk) if (world == 1 or exchange) else shard_range(Lk, rank, world)
     links_dev = (w['links_dev'] if is_rmat else torch.from_numpy(np.ascontiguousarray(links_all)).to(dev))[:, a:b].contiguous()
     Lmine = b - a
+    caps = w.get('caps') or {}
     buffers = PeerBuffers(Lk, F, K, dev, backend=args.exchange_backend) if exchange else None
     exchange_backend = buffers.backend if exchange else None
     out = ([torch.empty((2 * Lk, F + 1), dtype=torch.float32, device=dev) for _ in range(K + 1)]
@@ -376,11 +399,11 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
         if exchange:
             res, mirror = precompute_exchange(g, links_dev, w['num_hops'], K, buffers, flow=w['flow'], defer=True,
                                               batch_records=args.batch_records, profile=profile, overlap=args.overlap,
-                                              walk=w.get('walk'))
+                                              walk=w.get('walk'), **caps)
             exchange_finish(buffers, mirror)    # on the stream: barrier (all rows have landed), then the paired links' rows
             return res
         return precompute(g, links_dev, w['num_hops'], K, w['flow'], w['strategy'], batch_records=args.batch_records, out=out,
-                          profile=profile, overlap=args.overlap, defer=fixed, walk=w.get('walk'), pair=not args.no_pair)
+                          profile=profile, overlap=args.overlap, defer=fixed, walk=w.get('walk'), pair=not args.no_pair, **caps)
 
     vis = [v for v in os.environ.get('CUDA_VISIBLE_DEVICES', '').split(',') if v.strip()]
     local_rank = dev.index
@@ -430,7 +453,7 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
     # ---- multi-GPU: every rank's matrices against a single-GPU precompute of the whole list ----
     exch = None
     if exchange:
-        check = precompute(g, links_dev, w['num_hops'], K, w['flow'], None, pair=False, walk=w.get('walk'))
+        check = precompute(g, links_dev, w['num_hops'], K, w['flow'], None, pair=False, walk=w.get('walk'), **caps)
         same = torch.tensor([int(all(torch.equal(buffers.local[k], check.xs[k]) for k in range(K + 1)))], device=dev)
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
         rows_mine = 2 * (res.stats['links'])
@@ -513,6 +536,19 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
         dist.all_reduce(tt)
         path_bytes = int(tt[0])
     d = kernels.get(dom, {})
+    streamed = None
+    if is_rmat and st.get('sum_read'):
+        # the sorted tier does not scan the adjacency list of a hub row (binary-search probes instead): index bytes it
+        # really streams = the two merged lists + the rows of the low-degree nodes, against the 4*D of SURVEY 8d
+        rd = torch.tensor([st['sum_read'], st['sum_n']], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(rd)
+        sb = 4 * int(rd[0]) + 16 * int(rd[1]) + 4 * F * int(rd[1]) + 4 * 2 * Lk * (K + 1) * (F + 1)
+        streamed = dict(bytes_per_link=sb / Lk, achieved=sb * steps / (ms_max / 1e3) / 1e9,
+                        frac=sb * steps / (ms_max / 1e3) / 1e9 / (peak * world),
+                        note="index bytes the bit-matrix method really streams (merged lists + low-degree rows; hub rows are "
+                             "probed) + indptr + features + outputs: the honest denominator for this tier; path.frac above "
+                             "keeps SURVEY 8d's 4*D, which this method never reads")
     roofline = dict(bound="hbm", kernel=d.get('kernel'), achieved=d.get('achieved_GBps', 0.0), peak=peak, unit="GB/s",
                     frac=d.get('frac_of_hbm', 0.0), traffic=traffic, traffic_source=traffic_src, peak_source=peak_src,
                     dominant_by="share of the step (CUDA events on the launching stream)",
@@ -528,6 +564,8 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
                                    "is served by its partner's record) over the full step time, against N x the HBM peak"))
     if st.get('mirrors') is not None and fixed:
         roofline['path']['links_served_by_pairing_this_rank'] = st['mirrors']
+    if streamed:
+        roofline['path_streamed'] = streamed
 
     # ---- end to end through the reference-facing call, host buffers in, host buffers out ----
     e2e = None
@@ -613,7 +651,7 @@ def rmat_cpu_baseline(w, g, K):
     X_host = g.x[:, :F].cpu().numpy()
     cols = np.random.default_rng(123).choice(Lk, min(Lk, 200), replace=False)
     t0 = time.perf_counter()
-    orc.pos_precompute(w['links'][:, cols], 1, A_host, X_host, K)
+    orc.pos_precompute(w['links'][:, cols], 1, A_host, X_host, K, caps=w.get('caps') or None)
     dt = time.perf_counter() - t0
     return dict(value=cols.size / dt, unit=UNIT, cores=1, kind="port",
                 sample=f"{cols.size} links sampled uniformly (seed 123), one pass, {dt:.1f} s; single-process oracle port")
@@ -638,7 +676,8 @@ def main():
     ap.add_argument('--rmat-nodes', type=int, default=10_000_000)
     ap.add_argument('--rmat-edges', type=int, default=200_000_000)
     ap.add_argument('--rmat-links', type=int, default=4_000_000)
-    ap.add_argument('--rmat-degree-cap', type=int, default=512)
+    ap.add_argument('--rmat-degree-cap', type=int, default=512, help='targets restricted to endpoints of at most this degree (0: any)')
+    ap.add_argument('--max-nodes-per-hop', type=int, default=None, help="rmat: the reference's per-hop cap (deterministic rank rule)")
     ap.add_argument('--exchange-backend', default=None, choices=['auto', 'multicast', 'ipc'],
                     help='default: ipc on 2 GPUs, multicast (with ipc as fallback) from 4 GPUs on')
     ap.add_argument('--overlap', action='store_true', help='two-stream schedule: front kernel of batch i+1 beside kernel 3 of batch i')
@@ -646,7 +685,7 @@ def main():
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
-    is_rmat = args.workload == 'rmat'
+    is_rmat = args.workload.startswith('rmat')
     w = None if is_rmat else build_workload(args.workload)
     if w is not None and args.links:
         w['links'] = np.ascontiguousarray(w['links'][:, :args.links])
@@ -692,7 +731,8 @@ def main():
 
     ceilings = measure_ceilings(dev)
     if is_rmat:
-        w = build_rmat_workload(args, dev)
+        w = (build_rmat_workload(args, dev, degree_cap=0, max_nodes_per_hop=args.max_nodes_per_hop or 1024) if args.workload == 'rmat_hopcap'
+             else build_rmat_workload(args, dev, max_nodes_per_hop=args.max_nodes_per_hop))
         if not args.no_cpu_baseline and rank == 0 and world == 1:
             cpu = rmat_cpu_baseline(w, w['graph'], w['K'])
     line = measure(args, w, args.workload, args.steps, args.warmup, dev, rank, world, not args.no_e2e, ceilings, cpu)
@@ -703,7 +743,8 @@ def main():
     # ---- the BASELINE configs that are not the headline, few steps each ----
     extra = []
     if args.configs == 'auto':
-        extra = ['pubmed_posplus_union', 'rmat'] if args.workload == 'pubmed_pos' and not args.links else []
+        extra = (['pubmed_posplus_union', 'rmat', 'rmat_deg4096', 'rmat_hopcap'] if args.workload == 'pubmed_pos' and not args.links
+                 else [])
     elif args.configs != 'none':
         extra = [c for c in args.configs.split(',') if c]
     configs = []
@@ -711,14 +752,19 @@ def main():
         del w
         torch.cuda.empty_cache()
         try:
-            if name == 'rmat':
+            if name == 'rmat':                 # BASELINE config 5 as in round 1: endpoint degree <= 512, exact subgraphs
                 w = build_rmat_workload(args, dev)
+            elif name == 'rmat_deg4096':       # larger hubs, exact subgraphs, a 400 k-link sample
+                w = build_rmat_workload(args, dev, degree_cap=4096, num_links=min(args.rmat_links, 400_000))
+            elif name == 'rmat_hopcap':        # targets of ANY degree through the reference's per-hop cap
+                w = build_rmat_workload(args, dev, degree_cap=0, num_links=min(args.rmat_links, 1_000_000), max_nodes_per_hop=1024)
             else:
                 w = build_workload(name)
             sub = measure(args, w, name, 2, 3, dev, rank, world, False, ceilings, None)
             keep = {k_: sub[k_] for k_ in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'ms_per_step', 'scaling', 'gpu_launches')}
             keep['config'] = sub['config']
-            keep['roofline'] = {k_: sub['roofline'][k_] for k_ in ('kernel', 'achieved', 'peak', 'frac', 'share_of_step', 'path')}
+            keep['roofline'] = {k_: sub['roofline'][k_] for k_ in ('kernel', 'achieved', 'peak', 'frac', 'share_of_step', 'path', 'path_streamed')
+                                if k_ in sub['roofline']}
             if 'exchange' in sub:
                 keep['exchange'] = sub['exchange']
             configs.append(keep)

@@ -119,6 +119,9 @@ extern "C" {
 #define S3_CTR_SUM_N_ALL 8 /* sum of n over every LINK served (a record counts once per paired link too) */
 #define S3_CTR_SUM_D_ALL 9 /* same for D: the SURVEY 8d per-link figures with pairing switched on        */
 #define S3_CTR_MIRRORS 10  /* links served by another link's record (s3_pair_links)                      */
+#define S3_CTR_SUM_READ 11 /* sorted tier: adjacency entries the method really streams (the two merged lists + */
+                           /* the rows of low-degree nodes; hub rows are probed by binary search instead): the  */
+                           /* index bytes of its roofline, in place of the 4*D of the SURVEY formula            */
 #define S3_CTR_CLASS0 16   /* + c: records whose n has floor(log2 n) == c (size classes)  */
 #define S3_NCTR 48
 

@@ -102,7 +102,8 @@ struct BitCtx {
 };
 
 __device__ __forceinline__ bool bitmatrix_record(const SortedParams& p, const BitCtx& cx, int32_t* rowptr, int32_t* rowlen,
-                                                 int& m_out, int64_t& base2, int64_t& base3, unsigned long long& my_deg) {
+                                                 int& m_out, int64_t& base2, int64_t& base3, unsigned long long& my_deg,
+                                                 unsigned long long& my_read) {
     constexpr int SC = 2;
     const int T = kExtractThreads, tid = threadIdx.x, K = p.sign_k;
     const int lane = tid & 31, wid = tid >> 5, l8 = tid & 7, grp = tid >> 3;
@@ -139,6 +140,7 @@ __device__ __forceinline__ bool bitmatrix_record(const SortedParams& p, const Bi
             cx.s_deg[j] = d;
             my_deg += (unsigned long long)d;
             big = d > tau ? 1 : 0;
+            if (!big) my_read += (unsigned long long)d;  // adjacency entries this method really streams
         }
         int tot;
         const int ex = block_exclusive_scan(big, cx.s_scan, &tot);
@@ -444,6 +446,7 @@ __global__ void __launch_bounds__(kExtractThreads, 4) front_sorted_kernel(Sorted
         int64_t base2 = 0, base3 = 0;
         int m = 0;
         unsigned long long my_deg = 0;
+        unsigned long long my_read = tid == 0 ? (unsigned long long)(du + dv) : 0ull;  // the two merged lists
 
         if (!overflow) {
             // ---- merge into the canonical order ----
@@ -452,8 +455,10 @@ __global__ void __launch_bounds__(kExtractThreads, 4) front_sorted_kernel(Sorted
                 nodes_g[1] = v;
             }
             for (int i = tid; i < du; i += T) {
-                const int x = A[i];
-                if (x != u && x != v) nodes_g[2 + PA[i] + PB[lower_bound(B, dv, x)]] = x;
+                if (PA[i + 1] != PA[i]) {  // kept (not a target, not dropped by the per-hop cap)
+                    const int x = A[i];
+                    nodes_g[2 + PA[i] + PB[lower_bound(B, dv, x)]] = x;
+                }
             }
             for (int k = tid; k < dv; k += T) {
                 if (PB[k + 1] != PB[k]) {  // kept
@@ -479,7 +484,7 @@ __global__ void __launch_bounds__(kExtractThreads, 4) front_sorted_kernel(Sorted
                 cx.s_z = &s_z[0][0];
                 cx.s_scan = s_scan;
                 cx.s_base = &s_base;
-                overflow = bitmatrix_record(p, cx, rowptr, rowlen, m, base2, base3, my_deg);
+                overflow = bitmatrix_record(p, cx, rowptr, rowlen, m, base2, base3, my_deg, my_read);
             } else {
             // ======== large subgraphs: per-row intersections, exact count -> scan -> fill ========
             // ---- count pass: |N(g_j) ∩ S| minus the masked target link, one warp per row ----
@@ -490,6 +495,7 @@ __global__ void __launch_bounds__(kExtractThreads, 4) front_sorted_kernel(Sorted
                 if (lane == 0) my_deg += (unsigned long long)d;
                 const int32_t* __restrict__ Nj = p.indices + e0;
                 const bool by_nodes = (int64_t)n * (32 - __clz(d | 1)) * 2 < d;  // (ii) for hub rows
+                if (lane == 0 && !by_nodes) my_read += 2ull * (unsigned long long)d;  // count pass + fill pass
                 int c_row = 0;
                 if (!by_nodes) {
                     for (int e = lane; e < ((d + 31) & ~31); e += 32) {
@@ -631,6 +637,8 @@ __global__ void __launch_bounds__(kExtractThreads, 4) front_sorted_kernel(Sorted
 
         for (int d = 16; d > 0; d >>= 1) my_deg += __shfl_down_sync(0xffffffffu, my_deg, d);
         if (lane == 0 && my_deg) atomicAdd(&p.counters[S3_CTR_SUM_D], my_deg);
+        for (int d = 16; d > 0; d >>= 1) my_read += __shfl_down_sync(0xffffffffu, my_read, d);
+        if (lane == 0 && my_read) atomicAdd(&p.counters[S3_CTR_SUM_READ], my_read);
         __syncthreads();
         if (tid == 0) {
             off[S3_OFF_NODES] = base1;

@@ -11,6 +11,7 @@ PyTorch is used for device memory, streams and (in parallel.py) torch.distribute
 compute is in libs3grl_b200.so.  There is no CPU fallback.
 """
 import ctypes as C
+import os
 import time
 
 import numpy as np
@@ -19,6 +20,7 @@ import torch
 
 from . import _lib as L
 
+_NVTX = bool(os.environ.get('S3GRL_NVTX'))      # read once at import: NVTX ranges around every kernel launch
 _STRATEGY = {None: L.STRATEGY_NONE, '': L.STRATEGY_NONE, 'intersection': L.STRATEGY_INTERSECTION,
              'union': L.STRATEGY_UNION}
 _FLOW = {'PoS': L.FLOW_POS, 'SoP': L.FLOW_SOP}
@@ -362,8 +364,19 @@ class _Call:
                        self.cap_ratio, self.cap_max, self.cap_seed)
 
     def launch(self, stage, bi, fn_name, *args, on=None):
-        """Call one C entry point; with `profile`, bracket it with CUDA events on its stream."""
+        """Call one C entry point; with `profile`, bracket it with CUDA events on its stream.  With S3GRL_NVTX=1
+        in the environment every launch sits in an NVTX range "s3:<stage>" (ranges around kernels 1-3
+        for nsys / ncu --nvtx filtering)."""
         fn = getattr(self.lib, fn_name)
+        if _NVTX:
+            torch.cuda.nvtx.range_push(f"s3:{stage}:{bi}")
+            try:
+                return self._launch(stage, bi, fn, fn_name, args, on)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        return self._launch(stage, bi, fn, fn_name, args, on)
+
+    def _launch(self, stage, bi, fn, fn_name, args, on):
         if self.profile is None:
             return L.check(fn(*args), fn_name)
         on = self.stream if on is None else on
@@ -397,6 +410,7 @@ class _Call:
         self.stats['sum_n_links'] += int(c[L.CTR_SUM_N_ALL])
         self.stats['sum_d_links'] += int(c[L.CTR_SUM_D_ALL])
         self.stats['mirrors'] += int(c[L.CTR_MIRRORS])
+        self.stats['sum_read'] = self.stats.get('sum_read', 0) + int(c[L.CTR_SUM_READ])
         self.stats['max_n'] = max(self.stats['max_n'], int(c[L.CTR_MAX_N]))
         return True
 

@@ -102,10 +102,13 @@ class PeerBuffers:
     .local     K+1 torch views [2 * num_links, F+1] of this GPU's copy
     .dst       device pointers kernel 3 stores to: [multicast address] or all ranks' copies"""
 
-    def __init__(self, num_links, num_feat, sign_k, device, group=None, backend=None, local_x0=True, local_mirrors=True):
+    def __init__(self, num_links, num_feat, sign_k, device, group=None, backend=None, local_x0=None, local_mirrors=None):
         from . import _lib as L
-        self.local_x0 = bool(local_x0)      # operator 0 is written locally by every GPU (s3_fill_x0), not exchanged
-        self.local_mirrors = bool(local_mirrors)   # rows of paired links are copied locally after the exchange
+        # NVLink ingress only binds from 4 GPUs on (measured: profiles/README.md); on 2 GPUs the two extra local
+        # passes cost more than the bytes they save
+        many = dist.get_world_size(group) >= 4
+        self.local_x0 = many if local_x0 is None else bool(local_x0)        # operator 0 written locally (s3_fill_x0)
+        self.local_mirrors = many if local_mirrors is None else bool(local_mirrors)   # paired links' rows copied locally
         self.flags = (L.PEERS_LOCAL_X0 if self.local_x0 else 0) | (L.PEERS_LOCAL_MIRRORS if self.local_mirrors else 0)
         if backend is None:    # measured on this pool (profiles/): P2P stores are steady and fastest on 2 GPUs, the
             backend = 'ipc' if dist.get_world_size(group) <= 2 else 'auto'     # multicast path wins from 4 GPUs on

@@ -45,7 +45,7 @@ def test_constants_match_header():
              'S3_BATCH_CCN_CHAIN': L.BATCH_CCN_CHAIN, 'S3_LABEL_ZO': L.LABEL_ZO, 'S3_LABEL_HOP': L.LABEL_HOP,
              'S3_LABEL_DRNL': L.LABEL_DRNL, 'S3_LABEL_DEGREE': L.LABEL_DEGREE, 'S3_LABEL_ZERO': L.LABEL_ZERO,
              'S3_REC_MIRROR': L.REC_MIRROR, 'S3_CTR_SUM_N_ALL': L.CTR_SUM_N_ALL, 'S3_CTR_SUM_D_ALL': L.CTR_SUM_D_ALL,
-             'S3_CTR_MIRRORS': L.CTR_MIRRORS, 'S3_MAX_PEERS': L.MAX_PEERS, 'S3_MAX_K_UNION': L.MAX_K_UNION,
+             'S3_CTR_MIRRORS': L.CTR_MIRRORS, 'S3_CTR_SUM_READ': L.CTR_SUM_READ, 'S3_MAX_PEERS': L.MAX_PEERS, 'S3_MAX_K_UNION': L.MAX_K_UNION,
              'S3_PEER_HANDLE_BYTES': L.PEER_HANDLE_BYTES, 'S3_VERSION': L.VERSION}
     for k, v in pairs.items():
         assert int(defs[k]) == v, k
