@@ -389,10 +389,15 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
     exchange_backend = buffers.backend if exchange else None
     out = ([torch.empty((2 * Lk, F + 1), dtype=torch.float32, device=dev) for _ in range(K + 1)]
            if fixed and not exchange else None)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    # L2 between timed iterations: a step of the fixed-row flows WRITES its K+1 operator matrices — far more than the
+    # 126 MB L2 (PubMed: 2.6 GB, on every rank of an exchange) — so every step starts with none of its inputs cached;
+    # the flows with smaller outputs get an explicit 256 MiB fill
+    out_bytes = 2 * Lk * (K + 1) * (F + 1) * 4
+    flush = None if (fixed and out_bytes >= (512 << 20)) else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def step(profile=None):
-        flush.zero_()               # L2 flush between steps
+        if flush is not None:
+            flush.zero_()               # L2 flush between steps
         if full_flow:
             return precompute_full(g, links_dev, w['num_hops'], K, node_label=full_flow, batch_records=args.batch_records,
                                    profile=profile)
@@ -627,8 +632,9 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
                 dtype="f32", data="synthetic",
                 config=dict(workload=w['desc'], links_per_step=Lk, links_per_step_this_rank=st['links'],
                             batch_records=args.batch_records or "auto (32768 for fixed-row flows)",
-                            l2="flushed between steps (256 MiB memset); PubMed's X (39 MB) is L2-resident within a step by "
-                               "nature of the workload, the R-MAT X (5 GB) is not",
+                            l2=(f"every step writes {out_bytes / 2**30:.1f} GiB of operator rows (>> 126 MB L2) before the next one starts: "
+                                "no input survives in L2 between steps" if flush is None else "flushed between steps (256 MiB memset)")
+                               + "; PubMed's X (39 MB) is L2-resident WITHIN a step by nature of the workload, the R-MAT X (5 GB) is not",
                             pairing=("on: links over the same unordered node pair share one record (both directions of a "
                                      "training edge); bit-identical to computing each" if fixed and not args.no_pair and not is_rmat
                                      else "off"),

@@ -96,7 +96,7 @@ class JointLoader:
         y           [B]                labels,  num_graphs = B
     """
 
-    def __init__(self, dataset, batch_size, shuffle=False, seed=0, drop_last=False):
+    def __init__(self, dataset, batch_size, shuffle=False, seed=0, drop_last=False, reuse_epoch_buffer=False):
         if dataset.xs[0].device.type != 'cuda':
             raise RuntimeError("JointLoader needs the dataset on a CUDA device (PrecomputedList.to('cuda'))")
         self.ds, self.batch_size, self.shuffle, self.drop_last = dataset, int(batch_size), bool(shuffle), bool(drop_last)
@@ -108,6 +108,11 @@ class JointLoader:
         counts = self.row_ptr[1:] - self.row_ptr[:-1]
         L_ = len(dataset)
         self.fixed = int(counts[0]) if L_ and bool((counts == counts[0]).all()) else None
+        # Batches are views of the epoch's joint matrix.  By default every __iter__ allocates a fresh matrix, so batches
+        # (and tensors saved for backward) stay valid across epochs and concurrent iterators, as PyG's DataLoader
+        # batches do; reuse_epoch_buffer=True keeps ONE matrix for all epochs (no allocation per epoch) and the
+        # batches of an epoch are invalidated by the next __iter__.
+        self.reuse_epoch_buffer = bool(reuse_epoch_buffer)
         self._epoch_buf = None
 
     def __len__(self):
@@ -118,10 +123,12 @@ class JointLoader:
         n, bs = len(self.ds), self.batch_size
         perm = torch.randperm(n, device=self.dev, generator=self.gen) if self.shuffle else torch.arange(n, device=self.dev)
         K1, F1 = len(self.ds.xs), int(self.ds.xs[0].shape[1])
-        if self.fixed and (self._epoch_buf is None or self._epoch_buf.shape[0] < n * self.fixed):
-            self._epoch_buf = torch.empty((n * self.fixed, (K1 * F1 + 3) // 4 * 4), dtype=torch.float32, device=self.dev)
-        joint, _, ptr = joint_rows(self.ds.xs, self.row_ptr, perm, self.fixed, out=self._epoch_buf if self.fixed else None,
-                                   want_batch=False)
+        buf = None
+        if self.fixed and self.reuse_epoch_buffer:
+            if self._epoch_buf is None or self._epoch_buf.shape[0] < n * self.fixed:
+                self._epoch_buf = torch.empty((n * self.fixed, (K1 * F1 + 3) // 4 * 4), dtype=torch.float32, device=self.dev)
+            buf = self._epoch_buf
+        joint, _, ptr = joint_rows(self.ds.xs, self.row_ptr, perm, self.fixed, out=buf, want_batch=False)
         y = self.y[perm]
         ptr_host = None if self.fixed else ptr[::bs].cpu().tolist() + [int(ptr[-1])]
         for bi in range(len(self)):

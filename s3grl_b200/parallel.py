@@ -219,12 +219,19 @@ def precompute_exchange(graph, links, num_hops, sign_k, buffers, flow='PoS', def
     if flow == 'PoS' and n > 1 and not kw.get('walk') and kw.get('pair', True):
         mirror, table = pair_links(links, graph.num_nodes, kw.get('stream'))
     kw.pop('pair', None)
-    if buffers.local_x0:       # x of every link, locally: the one operator that is a plain copy of resident data
-        st = kw.get('stream') or torch.cuda.current_stream(dev)
+    if buffers.local_x0:       # x of every link, locally: the one operator that is a plain copy of resident data.
+        # Independent of everything else in the step: it runs on a side stream beside the front / gather kernels
+        # and is joined in exchange_finish.
+        main = kw.get('stream') or torch.cuda.current_stream(dev)
+        side = graph.streams()[0]
+        side.wait_stream(main)
         with torch.cuda.device(dev):
             buffers._L.check(buffers._lib.s3_fill_x0(C.byref(graph._c), C.c_void_p(links[0].data_ptr()),
                                                      C.c_void_p(links[1].data_ptr()), n, C.c_void_p(buffers.local[0].data_ptr()),
-                                                     buffers.cols, C.c_void_p(st.cuda_stream)), 's3_fill_x0')
+                                                     buffers.cols, C.c_void_p(side.cuda_stream)), 's3_fill_x0')
+        buffers._x0_done = torch.cuda.Event()
+        buffers._x0_done.record(side)
+        buffers._x0_links = links          # alive until the side stream has read them
     idx = torch.arange(buffers.rank, n, buffers.world, device=dev, dtype=torch.int64)
     res = precompute(graph, links[:, idx].contiguous(), num_hops, sign_k, flow, None, out_link=idx, mirror=mirror,
                      peers=buffers, pair=False, defer=defer, **kw)
@@ -237,10 +244,13 @@ def precompute_exchange(graph, links, num_hops, sign_k, buffers, flow='PoS', def
 def exchange_finish(buffers, mirror, stream=None):
     """End of an exchange step, on the stream: the barrier (every rank's rows have landed everywhere), then — with
     local_mirrors — every GPU copies the rows of the paired links from their first link's rows in its own memory."""
+    dev = buffers.device
+    st = stream or torch.cuda.current_stream(dev)
+    if getattr(buffers, '_x0_done', None) is not None:      # join the side stream that filled operator 0
+        st.wait_event(buffers._x0_done)
+        buffers._x0_done = None
     buffers.barrier()
     if mirror is not None and buffers.local_mirrors and buffers.num_ops > 1:
-        dev = buffers.device
-        st = stream or torch.cuda.current_stream(dev)
         ptrs = (C.c_void_p * buffers.num_ops)(*[o.data_ptr() for o in buffers.local])
         with torch.cuda.device(dev):
             buffers._L.check(buffers._lib.s3_fill_mirrors(C.c_void_p(mirror.data_ptr()), buffers.num_links, ptrs,

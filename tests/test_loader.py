@@ -95,3 +95,22 @@ def test_joint_loader_epoch(fixed):
     plain = next(iter(JointLoader(ds, 32)))
     assert np.array_equal(plain.joint.cpu().numpy(), _collate_like_pyg(ds, np.arange(32))[0])
     assert first2.shape == (32,)
+
+
+@pytest.mark.gpu
+def test_batches_stay_valid_across_epochs_and_iterators():
+    """PyG's DataLoader hands out independent batches; by default so does JointLoader (a fresh epoch matrix per
+    __iter__): a batch kept from epoch 1 — e.g. saved for backward — is not overwritten by epoch 2 or a second iterator."""
+    from s3grl_b200 import JointLoader
+    rng = np.random.default_rng(6)
+    ds = _dataset(rng, 96, 9, 2, True).to('cuda')
+    loader = JointLoader(ds, 32, shuffle=True, seed=1)
+    kept = next(iter(loader))
+    snapshot = kept.joint.clone()
+    for a, b in zip(loader, loader):             # two concurrent iterators, then a further epoch
+        assert a.joint.data_ptr() != b.joint.data_ptr()
+    list(loader)
+    assert torch.equal(kept.joint, snapshot)
+    reuse = JointLoader(ds, 32, shuffle=True, seed=1, reuse_epoch_buffer=True)     # opt-in: one matrix for every epoch
+    p0 = next(iter(reuse)).joint.data_ptr()
+    assert next(iter(reuse)).joint.data_ptr() == p0
