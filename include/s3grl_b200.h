@@ -316,6 +316,15 @@ int64_t s3_pair_table_slots(int64_t num_links);
 int s3_pair_links(const int64_t* link_src, const int64_t* link_dst, int64_t num_links, int64_t num_nodes,
                   int64_t* table, int64_t table_slots, int64_t* mirror, void* stream);
 
+/* Negative sampling on the GPU (input side; replaces torch_geometric.utils.negative_sampling at
+ * reference utils.py:645-648): candidate i is the ordered pair (u, v) drawn from a counter-based hash of (seed, i);
+ * valid[i] = 1 when u != v, (u, v) is not a stored entry of g (columns ascending: binary search) and no candidate
+ * j < i is the same pair. The caller keeps the first `count` valid candidates in index order (deterministic) and
+ * asks for more candidates if there are too few. table: 2 * table_slots int64 words, table_slots a power of two
+ * >= 2 * num_candidates (s3_pair_table_slots). g.x is not read. */
+int s3_negative_candidates(const s3_graph* g, int64_t num_candidates, uint64_t seed, int64_t* table, int64_t table_slots,
+                           int64_t* cand_src, int64_t* cand_dst, uint8_t* valid, void* stream);
+
 /* Fused gather + all-gather over NVLink peer memory: as s3_gather for the fixed-row flows, but every
  * output row is stored into the operator matrices of ALL num_dst GPUs (this one included) instead of one local
  * copy followed by an NCCL all-gather. dst_bases: HOST array of num_dst (<= 8) device pointers, each the base of

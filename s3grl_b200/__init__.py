@@ -16,5 +16,5 @@ from .engine import DeviceGraph, PrecomputeResult, algorithmic_bytes, pool_rows,
 from .tuned_sign import OptimizedSignOperations  # noqa: F401
 from .utils import extract_enclosing_subgraphs  # noqa: F401
 from .loader import JointLoader, joint_rows, load_collated, save_collated  # noqa: F401
-from .dataset import SEALDataset, do_edge_split, get_pos_neg_edges  # noqa: F401
+from .dataset import SEALDataset, do_edge_split, do_edge_split_gpu, get_pos_neg_edges, sample_negative_edges_gpu  # noqa: F401
 from .head import fold_batchnorm, segment_pool, sign_head, sign_head_ccn  # noqa: F401

@@ -252,6 +252,19 @@ int s3_probe_fma2(int32_t iters, float* sink, int32_t ctas, void* stream) {
     return e == cudaSuccess ? S3_OK : cuda_fail(e);
 }
 
+int s3_negative_candidates(const s3_graph* g, int64_t num_candidates, uint64_t seed, int64_t* table, int64_t table_slots,
+                           int64_t* cand_src, int64_t* cand_dst, uint8_t* valid, void* stream) {
+    int rc = check_graph(g, false);
+    if (rc != S3_OK) return rc;
+    if (num_candidates < 0) return S3_ERR_INVALID_ARG;
+    if (num_candidates == 0) return S3_OK;
+    if (!table || !cand_src || !cand_dst || !valid) return S3_ERR_INVALID_ARG;
+    if (table_slots < 2 * num_candidates || (table_slots & (table_slots - 1))) return S3_ERR_WORKSPACE;
+    cudaError_t e = s3::launch_negative_candidates(*g, num_candidates, seed, table, table_slots, cand_src, cand_dst, valid,
+                                                   static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? S3_OK : cuda_fail(e);
+}
+
 int s3_peer_alloc(int64_t bytes, void** ptr) {
     if (bytes <= 0 || !ptr) return S3_ERR_INVALID_ARG;
     cudaError_t e = s3::peer_alloc(bytes, ptr);

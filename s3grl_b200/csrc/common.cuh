@@ -192,6 +192,8 @@ cudaError_t launch_segment_pool(const float* src, int64_t ld, int64_t cols, cons
 cudaError_t launch_probe_l2_read(const float* buf, int64_t bytes, int iters, float* sink, int ctas, cudaStream_t st);
 cudaError_t launch_probe_fma(int iters, float* sink, int ctas, cudaStream_t st);
 cudaError_t launch_probe_fma2(int iters, float* sink, int ctas, cudaStream_t st);
+cudaError_t launch_negative_candidates(const s3_graph& g, int64_t M, uint64_t seed, int64_t* table, int64_t slots, int64_t* src,
+                                       int64_t* dst, uint8_t* valid, cudaStream_t st);
 cudaError_t peer_alloc(int64_t bytes, void** ptr);
 cudaError_t peer_free(void* ptr);
 cudaError_t peer_export(void* ptr, unsigned char* handle);

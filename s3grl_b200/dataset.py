@@ -43,6 +43,81 @@ def sample_negative_edges(edge_index, num_nodes, num_neg_samples, seed=0):
     return torch.as_tensor(np.asarray(out, dtype=np.int64).reshape(-1, 2).T.copy())
 
 
+def sample_negative_edges_gpu(indptr, indices, num_nodes, num_neg_samples, seed=0, device='cuda'):
+    """GPU negative sampling (csrc/pair.cu, s3_negative_candidates; reference utils.py:645-648): `num_neg_samples`
+    distinct ordered pairs (u, v), u != v, that are not stored entries of the CSR (int64 indptr, int32 indices with
+    ascending columns, on `device`).  Candidates come from a counter-based hash of (seed, index); the first
+    `num_neg_samples` valid ones in index order are kept, so the result depends on (graph, seed) only.
+    Returns an int64 [2, num_neg_samples] tensor on the device.  No CPU path."""
+    import ctypes as C
+    from . import _lib as L
+    lib = L.lib()
+    dev = torch.device(device)
+    indptr = torch.as_tensor(indptr).to(device=dev, dtype=torch.int64).contiguous()
+    indices = torch.as_tensor(indices).to(device=dev, dtype=torch.int32).contiguous()
+    N, need = int(num_nodes), int(num_neg_samples)
+    if need > N * (N - 1) - int(indices.numel()):
+        raise ValueError("not enough non-edges")
+    g = L.Graph(C.c_void_p(indptr.data_ptr()), C.c_void_p(indices.data_ptr()), None, N, 0, 0, int(indices.numel()), 0)
+    density = float(indices.numel()) / max(1.0, float(N) * N)
+    M = max(1024, int(need * (1.1 + 2 * density)) + 64)
+    st = torch.cuda.current_stream(dev)
+    while True:
+        slots = int(lib.s3_pair_table_slots(M))
+        table = torch.empty(2 * slots, dtype=torch.int64, device=dev)
+        src = torch.empty(M, dtype=torch.int64, device=dev)
+        dst = torch.empty(M, dtype=torch.int64, device=dev)
+        valid = torch.empty(M, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            L.check(lib.s3_negative_candidates(C.byref(g), M, int(seed) & (2**64 - 1), C.c_void_p(table.data_ptr()), slots,
+                                               C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), C.c_void_p(valid.data_ptr()),
+                                               C.c_void_p(st.cuda_stream)), 's3_negative_candidates')
+        keep = torch.nonzero(valid, as_tuple=False).flatten()          # ascending candidate index
+        if int(keep.numel()) >= need:
+            keep = keep[:need]
+            return torch.stack([src[keep], dst[keep]])
+        M *= 2          # a prefix of a longer candidate list: the kept pairs so far stay the same
+
+
+def do_edge_split_gpu(edge_index, num_nodes, val_ratio=0.05, test_ratio=0.1, seed=1, device='cuda'):
+    """The link split of reference utils.py:588-634 on the GPU: undirected edges are permuted
+    (torch.randperm on the device, seeded), cut 5 / 10 / 85 %, the training graph's CSR is built on the device and all
+    negatives come from s3_negative_candidates — validation / test negatives avoid every edge of the full graph,
+    training negatives the training edges, as `datasets.split_links` does on the host (same construction; the random
+    stream is this implementation's, as PyG's is not reproducible here).
+    Returns (indptr int64 [N+1], indices int32 [nnz] of the training graph, split_edge) with split_edge in the
+    reference's layout {'train'|'valid'|'test': {'edge': [L, 2], 'edge_neg': [L, 2]}}, everything on the device;
+    training positives hold both directions of every training edge."""
+    dev = torch.device(device)
+    ei = torch.as_tensor(edge_index).to(dev)
+    N = int(num_nodes)
+    lo, hi = torch.minimum(ei[0], ei[1]), torch.maximum(ei[0], ei[1])
+    key = torch.unique(lo[lo != hi] * N + hi[lo != hi])
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(int(seed))
+    key = key[torch.randperm(key.numel(), device=dev, generator=gen)]
+    E = int(key.numel())
+    n_v, n_t = int(val_ratio * E), int(test_ratio * E)
+    und = torch.stack([key // N, key % N])
+    val, test, train = und[:, :n_v], und[:, n_v:n_v + n_t], und[:, n_v + n_t:]
+
+    def csr(u2):
+        k = torch.unique(torch.cat([u2[0] * N + u2[1], u2[1] * N + u2[0]]))
+        row = k // N
+        indptr = torch.zeros(N + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(torch.bincount(row, minlength=N), 0, out=indptr[1:])
+        return indptr, (k % N).to(torch.int32)
+    full_ptr, full_idx = csr(und)
+    tr_ptr, tr_idx = csr(train)
+    vt_neg = sample_negative_edges_gpu(full_ptr, full_idx, N, n_v + n_t, seed=int(seed) * 3 + 1, device=dev)
+    train_pos = torch.cat([train, train.flip(0)], 1)
+    train_neg = sample_negative_edges_gpu(tr_ptr, tr_idx, N, train_pos.shape[1], seed=int(seed) * 3 + 2, device=dev)
+    split_edge = {'train': {'edge': train_pos.t().contiguous(), 'edge_neg': train_neg.t().contiguous()},
+                  'valid': {'edge': val.t().contiguous(), 'edge_neg': vt_neg[:, :n_v].t().contiguous()},
+                  'test': {'edge': test.t().contiguous(), 'edge_neg': vt_neg[:, n_v:].t().contiguous()}}
+    return tr_ptr, tr_idx, split_edge
+
+
 def do_edge_split(data, fast_split=False, val_ratio=0.05, test_ratio=0.1, neg_ratio=1, seed=1):
     """reference utils.py:588-634 (`data_passed=True` form): the 85/5/10 link split + 1:1 negatives, returned as the
     same `split_edge` dictionary ({'train'|'valid'|'test': {'edge': [L,2], 'edge_neg': [L,2]}}) and leaving

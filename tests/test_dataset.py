@@ -106,3 +106,43 @@ def test_seal_dataset_process_end_to_end(tmp_path, sign_type, k_heuristic, optim
     assert torch.equal(again.lists.xs[2].cpu(), dset.lists.xs[2].cpu())
     seen = sum(b.num_graphs for b in JointLoader(dset.lists, 16, shuffle=True, seed=0))
     assert seen == 40
+
+
+@pytest.mark.gpu
+def test_gpu_negative_sampling_and_edge_split():
+    """SURVEY.md §8f row 4 (input side): s3_negative_candidates / do_edge_split_gpu against the properties the
+    reference's split guarantees (utils.py:588-634, :645-648)."""
+    from s3grl_b200 import DeviceGraph, do_edge_split_gpu, precompute, sample_negative_edges_gpu
+    edges, N, X = ds.load_graph('cora')
+    A = ds.adjacency(edges, N)
+    neg = sample_negative_edges_gpu(A.indptr, A.indices, N, 20000, seed=5)
+    again = sample_negative_edges_gpu(A.indptr, A.indices, N, 20000, seed=5)
+    more = sample_negative_edges_gpu(A.indptr, A.indices, N, 30000, seed=5)
+    other = sample_negative_edges_gpu(A.indptr, A.indices, N, 20000, seed=6)
+    assert torch.equal(neg, again) and torch.equal(more[:, :20000], neg) and not torch.equal(neg, other)
+    n = neg.cpu().numpy()
+    assert n.shape == (2, 20000) and (n[0] != n[1]).all() and n.min() >= 0 and n.max() < N
+    assert np.unique(n[0] * N + n[1]).size == 20000                                # distinct ordered pairs
+    assert not np.asarray(A[n[0], n[1]]).any()                                      # none is an edge
+    hist = np.bincount(n.reshape(-1), minlength=N)                                  # endpoints roughly uniform
+    assert hist.min() > 0 and hist.max() < 5 * hist.mean()
+    # the whole split on the device, then straight into the hot path
+    e2 = torch.as_tensor(np.concatenate([edges.T, edges.T[::-1]], 1))
+    indptr, indices, se = do_edge_split_gpu(e2, N, seed=1)
+    E = edges.shape[0]
+    n_v, n_t = int(0.05 * E), int(0.1 * E)
+    assert se['valid']['edge'].shape == (n_v, 2) and se['test']['edge'].shape == (n_t, 2)
+    assert se['train']['edge'].shape == (2 * (E - n_v - n_t), 2) == tuple(se['train']['edge_neg'].shape)
+    key = lambda t: set((t[:, 0] * N + t[:, 1]).cpu().tolist())           # noqa: E731
+    full = set((edges[:, 0] * N + edges[:, 1]).tolist()) | set((edges[:, 1] * N + edges[:, 0]).tolist())
+    rows = torch.repeat_interleave(torch.arange(N, device=indptr.device), indptr[1:] - indptr[:-1])
+    train = set((rows * N + indices.long()).cpu().tolist())
+    assert train == key(se['train']['edge']) and int(indptr[-1]) == 2 * (E - n_v - n_t)
+    for s_ in ('valid', 'test'):
+        assert not (key(se[s_]['edge']) & train) and key(se[s_]['edge']) <= full
+        assert not (key(se[s_]['edge_neg']) & full)
+    assert not (key(se['train']['edge_neg']) & train)
+    g = DeviceGraph.from_device_csr(indptr, indices, torch.as_tensor(ds.normalize_features(X)[:, :64].copy()).to(indptr.device))
+    links = torch.cat([se['valid']['edge'], se['valid']['edge_neg']]).t().contiguous()
+    res = precompute(g, links, 2, 3)
+    assert res.xs[0].shape == (2 * links.shape[1], 65) and bool(torch.isfinite(res.xs[3]).all())
