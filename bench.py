@@ -423,6 +423,29 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
         if full_flow:
             res.node_id = None
     barrier()
+    # One step of a fixed-row flow has no host-dependent control flow: capture it once as a CUDA graph and replay it
+    # K times (one launch per step, so a descheduled host thread on a shared box cannot starve the GPU between the
+    # ~20 kernel launches of a step). The events around every kernel are event-record nodes of the graph: after the
+    # last replay they hold that step's per-kernel times. Falls back to eager launches if the capture fails.
+    graph_step, graph_res, graph_profile, graph_note = None, None, [], None
+    if fixed and not args.no_graph:
+        try:
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cg):
+                graph_res = step(graph_profile)
+            cg.replay()
+            torch.cuda.synchronize(dev)
+            graph_step = cg
+        except Exception as ex:
+            graph_step, graph_res, graph_profile = None, None, []
+            graph_note = f"capture failed, eager launches: {type(ex).__name__}: {ex}"[:200]
+            torch.cuda.synchronize(dev)
+        if world > 1:       # every rank replays a graph, or none does
+            okg = torch.tensor([1 if graph_step is not None else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(okg, op=dist.ReduceOp.MIN)
+            if int(okg) == 0 and graph_step is not None:
+                graph_step, graph_res, graph_profile, graph_note = None, None, [], "capture failed on another rank, eager launches"
+        barrier()
     profile = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -430,21 +453,30 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
     launches = 0
     step_events = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
     step_events[0].record()
-    pending = []
+    pending, r = [], None
+    t_enq = time.perf_counter()
     for i in range(steps):
-        res = step(profile)     # K steps are queued back to back ...
-        if not fixed:
-            # flows whose outputs are allocated inside the call (data-dependent row counts): hand the rows back to
-            # the allocator before the next step, as a caller that consumes each result would
-            res.xs = None
-            if full_flow:
-                res.node_id = None
-        pending.append(res)
+        if graph_step is not None:
+            graph_step.replay()
+            res = graph_res
+        else:
+            res = step(profile)     # K steps are queued back to back ...
+            if not fixed:
+                # flows whose outputs are allocated inside the call (data-dependent row counts): hand the rows back to
+                # the allocator before the next step, as a caller that consumes each result would
+                res.xs = None
+                if full_flow:
+                    res.node_id = None
+            pending.append(res)
         step_events[i + 1].record()
         launches += res.stats['launches']               # kernels of libs3grl_b200.so only (not the L2 flush fill)
+    host_enqueue_ms = 1000 * (time.perf_counter() - t_enq) / steps
+    if graph_step is not None:
+        torch.cuda.current_stream(dev).synchronize()
+        graph_res.finalize()                # validation of the replayed step (its counters), inside the timed region
+        profile = graph_profile             # per-kernel events of the LAST replayed step
     for r in pending:                       # ... then synchronised and validated, inside the timed region
         r.finalize()
-    host_enqueue_ms = res.stats.get('host_enqueue_ms')
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -479,6 +511,7 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
     stage_ms = {}
     for stage, bi, ea, eb in profile:
         stage_ms.setdefault(stage, []).append(ea.elapsed_time(eb))
+    ev_steps = 1 if graph_step is not None else steps      # steps the per-kernel events cover
     if os.environ.get('S3GRL_BENCH_DEBUG'):
         for stage, v in stage_ms.items():
             print(stage, [round(t_, 2) for t_ in v[:3 * res.stats['batches']]], file=sys.stderr)
@@ -504,11 +537,11 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
     kernels = {}
     for stage, v in stage_ms.items():
         tot = float(np.sum(v))
-        k = dict(kernel=names.get(stage, stage), share_of_step=tot / ms, ms_per_step=tot / steps, launches_timed=len(v),
+        k = dict(kernel=names.get(stage, stage), share_of_step=tot / (ms * ev_steps / steps), ms_per_step=tot / ev_steps, launches_timed=len(v),
                  avg_launch_ms=tot / len(v))
         if stage in alg and tot > 0:
             k['algorithmic_bytes_per_step'] = int(alg[stage])
-            k['achieved_GBps'] = alg[stage] * steps / (tot / 1e3) / 1e9
+            k['achieved_GBps'] = alg[stage] * ev_steps / (tot / 1e3) / 1e9
             k['frac_of_hbm'] = k['achieved_GBps'] / peak
             k['bound_by'] = bound_note.get(stage)
         if stage == 'gather' and tot > 0 and ceilings:
@@ -519,7 +552,7 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
             if hop:
                 sc = 1 if w['flow'] == 'SoP' else 2
                 fma = sum(n * max(0, K + 1 - l) * sc for l, n in enumerate(hop)) * g.ldx
-                k['fp32_TFLOPs'] = 2.0 * fma * steps / (tot / 1e3) / 1e12
+                k['fp32_TFLOPs'] = 2.0 * fma * ev_steps / (tot / 1e3) / 1e12
                 k['fp32_ceiling_TFLOPs'] = ceilings['fp32_TFLOPs']
                 k['frac_of_fp32_ceiling'] = k['fp32_TFLOPs'] / ceilings['fp32_TFLOPs']
         kernels[stage] = k
@@ -556,7 +589,7 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
                              "keeps SURVEY 8d's 4*D, which this method never reads")
     roofline = dict(bound="hbm", kernel=d.get('kernel'), achieved=d.get('achieved_GBps', 0.0), peak=peak, unit="GB/s",
                     frac=d.get('frac_of_hbm', 0.0), traffic=traffic, traffic_source=traffic_src, peak_source=peak_src,
-                    dominant_by="share of the step (CUDA events on the launching stream)",
+                    dominant_by="share of the step (CUDA events on the launching stream" + ("; event-record nodes of the replayed CUDA graph, last timed step)" if graph_step is not None else ")"),
                     note=d.get('bound_by'),
                     bytes_per_launch=d.get('algorithmic_bytes_per_step', 0) / max(st['batches'], 1),
                     launches_timed=d.get('launches_timed'), avg_launch_ms=d.get('avg_launch_ms'),
@@ -640,6 +673,8 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
                                      else "off"),
                             parallelism=par),
                 clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu,
+                timed_region=("one CUDA graph replay per step (captured from the same engine call after the warm-up)" if graph_step is not None
+                              else "eager kernel launches" + (f" ({graph_note})" if graph_note else "")),
                 host_enqueue_ms_per_step=host_enqueue_ms,
                 step_ms=[round(step_events[i].elapsed_time(step_events[i + 1]), 3) for i in range(steps)])
     if exch:
@@ -678,6 +713,7 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='eager kernel launches in the timed region instead of one CUDA graph replay per step')
     ap.add_argument('--no-pair', action='store_true', help='switch link pairing off (every link extracts its own subgraph)')
     ap.add_argument('--rmat-nodes', type=int, default=10_000_000)
     ap.add_argument('--rmat-edges', type=int, default=200_000_000)

@@ -182,6 +182,13 @@ def walk_sets_from_cache(cache, nodes, device):
     return sets.to(device), counts.to(device)
 
 
+def _free_bytes(dev):
+    """Free device memory; not queried while a CUDA graph is being captured (sizes were settled by the warm-up)."""
+    if torch.cuda.is_current_stream_capturing():
+        return 1 << 62
+    return torch.cuda.mem_get_info(dev)[0]
+
+
 def pair_links(links, num_nodes, stream=None):
     """s3_pair_links (csrc/pair.cu) over a device link list [2, L] int64 -> (mirror int64 [L], scratch table).
     mirror is the chain table described in include/s3grl_b200.h: >= 0 first link of a node pair with the first
@@ -275,7 +282,7 @@ class _Call:
             # fixed rows: 32 Ki records amortise the launch tails.  PoS Plus ends every batch with a host
             # sync, so intersection (small scratch) takes everything in as few batches as memory allows;
             # union multiplies the float scratch by the CCN work items and stays small.
-            free, _ = torch.cuda.mem_get_info(self.dev)
+            free = _free_bytes(self.dev)
             batch_records = {L.STRATEGY_NONE: 32768, L.STRATEGY_INTERSECTION: 262144, L.STRATEGY_UNION: 8192}[self.strategy]
             batch_records = max(1024, min(batch_records, int(free // 3 // (32768 * 4))))
         self.batch_links = max(1, int(batch_records) // self.rpl)
@@ -306,7 +313,7 @@ class _Call:
         if arena_words:
             words = int(arena_words)
         else:   # ~128 KiB of scratch per record to start with (PubMed h=3 averages ~60 KiB), grown on overflow
-            free, _ = torch.cuda.mem_get_info(self.dev)
+            free = _free_bytes(self.dev)
             words = max(1 << 22, min(min(int(batch_records), self.num_links * self.rpl) * 32768, free // 16))
             if graph._arena is not None:
                 words = max(words, graph._arena.numel())
@@ -380,7 +387,10 @@ class _Call:
         if self.profile is None:
             return L.check(fn(*args), fn_name)
         on = self.stream if on is None else on
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # inside a CUDA-graph capture the events become event-record nodes (external=True): after a replay they hold
+        # that replay's timestamps, so the per-kernel times of a graph-replayed step can still be read back
+        ext = torch.cuda.is_current_stream_capturing()
+        e0, e1 = torch.cuda.Event(enable_timing=True, external=ext), torch.cuda.Event(enable_timing=True, external=ext)
         e0.record(on)
         L.check(fn(*args), fn_name)
         e1.record(on)
