@@ -138,6 +138,13 @@ typedef struct s3_graph {
     int64_t ldx;            /* row stride in floats, multiple of 4, >= F    */
     int64_t num_edges;      /* indptr[num_nodes]; < 2^32 for the bitmap tier */
     int64_t max_degree;     /* largest row of the CSR (sizes the sorted tier's slabs) */
+    /* Optional hub index of the sorted-set tier (all three 0 / NULL: not used). hub_id[v] = index of v among the
+     * num_hubs highest-degree nodes, or -1; hub_bits is their num_hubs x ceil(num_hubs / 32) adjacency bit matrix
+     * (s3_build_hub_bits). Whether two hubs are adjacent is then ONE bit probe instead of a binary search in an
+     * adjacency list of 10^3..10^5 entries — the probe chains that bound the R-MAT configuration in round 1. */
+    const int32_t* hub_id;    /* [num_nodes]                                  */
+    const uint32_t* hub_bits; /* [num_hubs * ((num_hubs + 31) / 32)], zeroed by the caller before s3_build_hub_bits */
+    int64_t num_hubs;
 } s3_graph;
 
 /* s3_batch.flags: keep every row of the induced adjacency (parity dumps). Without it rows of
@@ -315,6 +322,10 @@ int s3_sign_head(const float* joint, int64_t rows, int64_t kdim, int64_t ld_join
 int64_t s3_pair_table_slots(int64_t num_links);
 int s3_pair_links(const int64_t* link_src, const int64_t* link_dst, int64_t num_links, int64_t num_nodes,
                   int64_t* table, int64_t table_slots, int64_t* mirror, void* stream);
+
+/* Fills g->hub_bits from the CSR: bit (hub_id[u], hub_id[v]) for every stored entry (u, v) between two hubs.
+ * hub_id and num_hubs come from the caller (any choice of hubs is valid: the index only short-cuts look-ups). */
+int s3_build_hub_bits(const s3_graph* g, void* stream);
 
 /* Negative sampling on the GPU (input side; replaces torch_geometric.utils.negative_sampling at
  * reference utils.py:645-648): candidate i is the ordered pair (u, v) drawn from a counter-based hash of (seed, i);

@@ -252,6 +252,14 @@ int s3_probe_fma2(int32_t iters, float* sink, int32_t ctas, void* stream) {
     return e == cudaSuccess ? S3_OK : cuda_fail(e);
 }
 
+int s3_build_hub_bits(const s3_graph* g, void* stream) {
+    int rc = check_graph(g, false);
+    if (rc != S3_OK) return rc;
+    if (!g->hub_id || !g->hub_bits || g->num_hubs <= 0 || g->num_hubs > (int64_t(1) << 20)) return S3_ERR_INVALID_ARG;
+    cudaError_t e = s3::launch_build_hub_bits(*g, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? S3_OK : cuda_fail(e);
+}
+
 int s3_negative_candidates(const s3_graph* g, int64_t num_candidates, uint64_t seed, int64_t* table, int64_t table_slots,
                            int64_t* cand_src, int64_t* cand_dst, uint8_t* valid, void* stream) {
     int rc = check_graph(g, false);

@@ -31,6 +31,9 @@ struct SortedParams {
     const int64_t* __restrict__ indptr;
     const int32_t* __restrict__ indices;
     int64_t num_nodes;
+    const int32_t* __restrict__ hub_id;     // optional hub index (s3_graph): null when absent
+    const uint32_t* __restrict__ hub_bits;
+    int hub_words;                          // words per row of the hub bit matrix
     const int64_t* __restrict__ link_src;
     const int64_t* __restrict__ link_dst;
     int64_t num_records;
@@ -172,8 +175,18 @@ __device__ __forceinline__ bool bitmatrix_record(const SortedParams& p, const Bi
             ja = jb;
             jb = t;
         }
-        const int ga = nodes[ja];  // search g_b in N(g_a), the shorter list
-        if (contains(p.indices + p.indptr[ga], cx.s_deg[ja], nodes[jb])) {
+        const int ga = nodes[ja], gb = nodes[jb];
+        bool adj;
+        int ha = -1, hb = -1;
+        if (p.hub_id) {
+            ha = p.hub_id[ga];
+            hb = p.hub_id[gb];
+        }
+        if (ha >= 0 && hb >= 0)  // both among the graph's hubs: one bit probe
+            adj = (p.hub_bits[(size_t)ha * p.hub_words + (hb >> 5)] >> (hb & 31)) & 1u;
+        else                      // search g_b in N(g_a), the shorter list
+            adj = contains(p.indices + p.indptr[ga], cx.s_deg[ja], gb);
+        if (adj) {
             atomicOr(&M[ja * nw + (jb >> 5)], 1u << (jb & 31));
             atomicOr(&M[jb * nw + (ja >> 5)], 1u << (ja & 31));
         }
@@ -664,7 +677,31 @@ __global__ void __launch_bounds__(kExtractThreads, 4) front_sorted_kernel(Sorted
     }
 }
 
+// hub index: one warp per hub row sets the bits of its hub neighbours
+__global__ void __launch_bounds__(256) hub_bits_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                                       int64_t num_nodes, const int32_t* __restrict__ hub_id, uint32_t* hub_bits,
+                                                       int hub_words) {
+    const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (v >= num_nodes) return;
+    const int h = hub_id[v];
+    if (h < 0) return;
+    const int64_t e0 = indptr[v], e1 = indptr[v + 1];
+    for (int64_t e = e0 + lane; e < e1; e += 32) {
+        const int hc = hub_id[indices[e]];
+        if (hc >= 0) atomicOr(&hub_bits[(size_t)h * hub_words + (hc >> 5)], 1u << (hc & 31));
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_build_hub_bits(const s3_graph& g, cudaStream_t st) {
+    if (!g.hub_id || !g.hub_bits || g.num_hubs <= 0) return cudaErrorInvalidValue;
+    const int64_t threads = g.num_nodes * 32;
+    hub_bits_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(g.indptr, g.indices, g.num_nodes, g.hub_id,
+                                                                       const_cast<uint32_t*>(g.hub_bits), (int)((g.num_hubs + 31) / 32));
+    return cudaGetLastError();
+}
 
 // defined in extract.cu
 cudaError_t launch_order(const s3_batch& b, int64_t num_records, cudaStream_t st);
@@ -675,6 +712,9 @@ cudaError_t launch_extract_sorted(const s3_graph& g, const s3_batch& b, cudaStre
     p.indptr = g.indptr;
     p.indices = g.indices;
     p.num_nodes = g.num_nodes;
+    p.hub_id = (g.hub_id && g.hub_bits && g.num_hubs > 0) ? g.hub_id : nullptr;
+    p.hub_bits = g.hub_bits;
+    p.hub_words = (int)((g.num_hubs + 31) / 32);
     p.link_src = b.link_src;
     p.link_dst = b.link_dst;
     p.num_records = b.num_links;

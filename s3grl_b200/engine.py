@@ -117,6 +117,32 @@ class DeviceGraph:
         self._streams = None
         return self
 
+    def ensure_hub_index(self, max_hubs=49152, min_degree=128, force=False):
+        """Hub index of the sorted-set tier (include/s3grl_b200.h, s3_graph.hub_*): the `max_hubs` highest-degree
+        nodes of degree >= min_degree get an id and a hub x hub adjacency bit matrix (max_hubs^2 / 8 bytes: 302 MB at
+        the default), so that the adjacency of two hubs inside a subgraph is one bit probe instead of a binary search
+        in a list of up to 10^5 entries.  Built once per graph, on first use of the sorted tier.  Results do not
+        depend on it."""
+        if getattr(self, '_hub', None) is not None and not force:
+            return self._hub[2]
+        deg = self.indptr[1:] - self.indptr[:-1]
+        k = min(int(max_hubs), self.num_nodes)
+        top, idx = torch.topk(deg, k)
+        idx = idx[top >= int(min_degree)]
+        H = int(idx.numel())
+        if H < 2:
+            self._hub = (None, None, 0)
+            return 0
+        hub_id = torch.full((self.num_nodes,), -1, dtype=torch.int32, device=self.device)
+        hub_id[idx] = torch.arange(H, dtype=torch.int32, device=self.device)
+        bits = torch.zeros(H * ((H + 31) // 32), dtype=torch.int32, device=self.device)
+        self._hub = (hub_id, bits, H)
+        self._c.hub_id, self._c.hub_bits, self._c.num_hubs = hub_id.data_ptr(), bits.data_ptr(), H
+        with torch.cuda.device(self.device):
+            L.check(L.lib().s3_build_hub_bits(C.byref(self._c), C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
+                    's3_build_hub_bits')
+        return H
+
     # scratch arenas (int32 words), grown on demand and kept across calls; the second one is
     # only allocated by the overlapped (two-stream, double-buffered) schedule
     def arena(self, words, slot=0):
@@ -323,6 +349,8 @@ class _Call:
         # Fixed-row PoS on the bitmap tier only; `out_link` / `mirror` / `peers` come from parallel.precompute_exchange
         # (this call then holds a subset of a larger link list and writes rows at their global positions).
         tier = int(self.lib.s3_extract_tier(C.byref(graph._c), C.byref(probe)))
+        if tier == 1 and self.walk is None and not torch.cuda.is_current_stream_capturing():
+            graph.ensure_hub_index()
         can_pair = (self.flow == L.FLOW_POS and self.fixed_rows and not self.return_graphs and self.walk is None
                     and tier == 0)
         self.pair = bool(pair) and can_pair and mirror is None

@@ -112,7 +112,7 @@ def test_seal_dataset_process_end_to_end(tmp_path, sign_type, k_heuristic, optim
 def test_gpu_negative_sampling_and_edge_split():
     """SURVEY.md §8f row 4 (input side): s3_negative_candidates / do_edge_split_gpu against the properties the
     reference's split guarantees (utils.py:588-634, :645-648)."""
-    from s3grl_b200 import DeviceGraph, do_edge_split_gpu, precompute, sample_negative_edges_gpu
+    from s3grl_b200 import DeviceGraph, datasets as ds, do_edge_split_gpu, precompute, sample_negative_edges_gpu
     edges, N, X = ds.load_graph('cora')
     A = ds.adjacency(edges, N)
     neg = sample_negative_edges_gpu(A.indptr, A.indices, N, 20000, seed=5)

@@ -729,3 +729,37 @@ def test_per_hop_caps_through_the_reference_interface():
     ref = orc.pos_precompute(c.links[:, :30], 3, c.A, c.X, c.K, None, caps=dict(ratio_per_hop=0.6, max_nodes_per_hop=25, cap_seed=11))
     for k in range(c.K + 1):
         assert_features_close(out.xs[k].numpy(), ref['xs'][k], what=f'x{k}')
+
+
+def test_hub_index_changes_nothing_but_the_lookups():
+    """The sorted tier's hub x hub bit matrix (s3_build_hub_bits) only short-cuts adjacency look-ups between
+    high-degree nodes: same bits with and without it, and the same subgraphs as the oracle."""
+    rng = np.random.default_rng(77)
+    N = 3000
+    A = _random_graph(rng, N, 20000)
+    hubs = rng.choice(N, 40, replace=False)                      # 40 hubs, densely connected to everything and each other
+    extra = np.stack([np.repeat(hubs, 400), rng.integers(0, N, 40 * 400)], 1)
+    hh = np.stack(np.meshgrid(hubs, hubs), -1).reshape(-1, 2)
+    hh = hh[rng.random(hh.shape[0]) < 0.5]
+    e = np.concatenate([extra, hh])
+    e = e[e[:, 0] != e[:, 1]]
+    import scipy.sparse as ssp
+    B = ssp.csr_matrix((np.ones(e.shape[0], np.int64), (e[:, 0], e[:, 1])), shape=(N, N))
+    A = ((A + B + B.T) > 0).astype(np.int64).tocsr()
+    A.sort_indices()
+    X = rng.random((N, 12), dtype=np.float32)
+    links = rng.integers(0, N, (2, 120))
+    links[0, :10] = hubs[:10]                                     # hub targets: many hub-hub pairs per subgraph
+    links[1, 10:20] = hubs[10:20]
+    links = links[:, links[0] != links[1]]
+    g_plain = DeviceGraph(A, X)
+    g_plain._hub = (None, None, 0)                                # index switched off
+    g_hub = DeviceGraph(A, X)
+    assert g_hub.ensure_hub_index(max_hubs=64, min_degree=100) >= 40
+    a = precompute(g_plain, links, 1, 3, force_sorted_tier=True, return_graphs=True)
+    b = precompute(g_hub, links, 1, 3, force_sorted_tier=True, return_graphs=True)
+    for k in range(4):
+        assert torch.equal(a.xs[k], b.xs[k])
+    ref = orc.pos_precompute(links[:, :30], 1, A, X, 3, None, keep_graphs=True)
+    for i, r in enumerate(ref['graphs']):
+        _check_indices(b.graphs[i], r, f'hub link {i}')
