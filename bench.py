@@ -604,6 +604,9 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
         roofline['path']['links_served_by_pairing_this_rank'] = st['mirrors']
     if streamed:
         roofline['path_streamed'] = streamed
+    if getattr(g, '_hub', None) and g._hub[2]:
+        roofline['hub_index'] = dict(hubs=g._hub[2], min_degree=getattr(g, 'hub_min_degree', None),
+                                     bit_matrix_bytes=int(g._hub[1].numel()) * 4)
 
     # ---- end to end through the reference-facing call, host buffers in, host buffers out ----
     e2e = None

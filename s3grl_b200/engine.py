@@ -117,7 +117,7 @@ class DeviceGraph:
         self._streams = None
         return self
 
-    def ensure_hub_index(self, max_hubs=49152, min_degree=128, force=False):
+    def ensure_hub_index(self, max_hubs=None, min_degree=128, force=False):
         """Hub index of the sorted-set tier (include/s3grl_b200.h, s3_graph.hub_*): the `max_hubs` highest-degree
         nodes of degree >= min_degree get an id and a hub x hub adjacency bit matrix (max_hubs^2 / 8 bytes: 302 MB at
         the default), so that the adjacency of two hubs inside a subgraph is one bit probe instead of a binary search
@@ -125,6 +125,8 @@ class DeviceGraph:
         depend on it."""
         if getattr(self, '_hub', None) is not None and not force:
             return self._hub[2]
+        if max_hubs is None:       # bit matrix of max_hubs^2 / 8 bytes: 0.3 GB, or 2.1 GB for graphs of millions of nodes
+            max_hubs = int(os.environ.get('S3GRL_MAX_HUBS', 131072 if self.num_nodes > 2_000_000 else 49152))
         deg = self.indptr[1:] - self.indptr[:-1]
         k = min(int(max_hubs), self.num_nodes)
         top, idx = torch.topk(deg, k)
@@ -137,6 +139,7 @@ class DeviceGraph:
         hub_id[idx] = torch.arange(H, dtype=torch.int32, device=self.device)
         bits = torch.zeros(H * ((H + 31) // 32), dtype=torch.int32, device=self.device)
         self._hub = (hub_id, bits, H)
+        self.hub_min_degree = int(top[H - 1])
         self._c.hub_id, self._c.hub_bits, self._c.num_hubs = hub_id.data_ptr(), bits.data_ptr(), H
         with torch.cuda.device(self.device):
             L.check(L.lib().s3_build_hub_bits(C.byref(self._c), C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
