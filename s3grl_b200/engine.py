@@ -125,8 +125,11 @@ class DeviceGraph:
         depend on it."""
         if getattr(self, '_hub', None) is not None and not force:
             return self._hub[2]
-        if max_hubs is None:       # bit matrix of max_hubs^2 / 8 bytes: 0.3 GB, or 2.1 GB for graphs of millions of nodes
-            max_hubs = int(os.environ.get('S3GRL_MAX_HUBS', 131072 if self.num_nodes > 2_000_000 else 49152))
+        if max_hubs is None:
+            # bit matrix of max_hubs^2 / 8 bytes: 0.3 GB; 8.6 GB for graphs of millions of nodes when the GPU has the
+            # room (B200: 180 GB).  Measured on the 10 M-node R-MAT: 49 152 hubs 2.73 M links/s, 131 072 3.19 M, 262 144 3.46 M
+            big = self.num_nodes > 2_000_000 and torch.cuda.mem_get_info(self.device)[0] > (48 << 30)
+            max_hubs = int(os.environ.get('S3GRL_MAX_HUBS', 262144 if big else 49152))
         deg = self.indptr[1:] - self.indptr[:-1]
         k = min(int(max_hubs), self.num_nodes)
         top, idx = torch.topk(deg, k)
