@@ -763,3 +763,25 @@ def test_hub_index_changes_nothing_but_the_lookups():
     ref = orc.pos_precompute(links[:, :30], 1, A, X, 3, None, keep_graphs=True)
     for i, r in enumerate(ref['graphs']):
         _check_indices(b.graphs[i], r, f'hub link {i}')
+
+
+def test_walks_reach_every_neighbour_of_a_hub():
+    """the neighbour pick must be uniform for degrees >= 2048 (a 53-bit product overflowed there and hubs only
+    ever stepped to their first 2048 neighbours).  Star graph of degree 10 000: one-step walks from the centre, under
+    many seeds, must land on late neighbours as often as on early ones."""
+    import scipy.sparse as ssp
+    from s3grl_b200 import walk_sets
+    D = 10000
+    row = np.concatenate([np.zeros(D, np.int64), np.arange(1, D + 1)])
+    col = np.concatenate([np.arange(1, D + 1), np.zeros(D, np.int64)])
+    A = ssp.csr_matrix((np.ones(2 * D, np.int64), (row, col)), shape=(D + 1, D + 1))
+    g = DeviceGraph(A, np.zeros((D + 1, 4), np.float32))
+    hit = np.zeros(D + 1, np.int64)
+    for seed in range(40):
+        sets, counts = walk_sets(g, torch.zeros(1, dtype=torch.int64), 1, 200, seed=seed)      # 200 one-step walks
+        nodes = sets[0, :int(counts[0])].cpu().numpy()
+        hit[nodes] += 1
+    leaves = hit[1:]
+    assert leaves[2048:].sum() > 0.7 * leaves.sum() * (D - 2048) / D          # late neighbours are reachable, in proportion
+    quart = leaves.reshape(4, -1).sum(1)
+    assert quart.min() > 0.8 * quart.mean()
