@@ -145,6 +145,11 @@ typedef struct s3_graph {
     const int32_t* hub_id;    /* [num_nodes]                                  */
     const uint32_t* hub_bits; /* [num_hubs * ((num_hubs + 31) / 32)], zeroed by the caller before s3_build_hub_bits */
     int64_t num_hubs;
+    /* Optional size proxy per node (NULL: not used), filled by s3_node_proxy: deg(v) + sum of its neighbours' degrees —
+     * an estimate of how much of the graph a BFS from v touches. With s3_batch.front_order set, s3_extract hands the
+     * records to its persistent CTAs in descending proxy(src) + proxy(dst) (longest first), which trims the tail of
+     * the launch; results do not depend on it. */
+    const int32_t* size_proxy; /* [num_nodes]                                 */
 } s3_graph;
 
 /* s3_batch.flags: keep every row of the induced adjacency (parity dumps). Without it rows of
@@ -216,6 +221,9 @@ typedef struct s3_batch {
     double ratio_per_hop;
     int32_t max_nodes_per_hop;
     uint32_t cap_seed;
+    /* Optional [num_records] scratch: with s3_graph.size_proxy, s3_extract first sorts the records by descending
+     * size proxy into it (counting sort over 128 logarithmic classes) and its CTAs take them in that order. */
+    int32_t* front_order;
 } s3_batch;
 
 int s3_version(void);
@@ -322,6 +330,9 @@ int s3_sign_head(const float* joint, int64_t rows, int64_t kdim, int64_t ld_join
 int64_t s3_pair_table_slots(int64_t num_links);
 int s3_pair_links(const int64_t* link_src, const int64_t* link_dst, int64_t num_links, int64_t num_nodes,
                   int64_t* table, int64_t table_slots, int64_t* mirror, void* stream);
+
+/* size_proxy[v] = min(INT32_MAX, deg(v) + sum over v's neighbours of their degree). out: [num_nodes] int32. */
+int s3_node_proxy(const s3_graph* g, int32_t* out, void* stream);
 
 /* Fills g->hub_bits from the CSR: bit (hub_id[u], hub_id[v]) for every stored entry (u, v) between two hubs.
  * hub_id and num_hubs come from the caller (any choice of hubs is valid: the index only short-cuts look-ups). */

@@ -26,13 +26,14 @@ EXPORTS = ['s3_version', 's3_error_string', 's3_last_cuda_error', 's3_num_record
            's3_min_arena_words', 's3_extract_tier',
            's3_extract', 's3_plan', 's3_plan_items', 's3_diffuse', 's3_gather', 's3_gather_ccn', 's3_ccn_chain', 's3_plan_full', 's3_sign_full', 's3_joint_rows', 's3_sign_head', 's3_walk_sets', 's3_dump_edges',
            's3_pair_table_slots', 's3_pair_links', 's3_gather_peers', 's3_fill_x0', 's3_fill_mirrors', 's3_peer_alloc', 's3_peer_free', 's3_peer_export',
-           's3_peer_open', 's3_peer_close', 's3_probe_l2_read', 's3_probe_fma', 's3_probe_fma2', 's3_segment_pool', 's3_negative_candidates', 's3_build_hub_bits']
+           's3_peer_open', 's3_peer_close', 's3_probe_l2_read', 's3_probe_fma', 's3_probe_fma2', 's3_segment_pool', 's3_negative_candidates', 's3_build_hub_bits', 's3_node_proxy']
 
 
 class Graph(C.Structure):
     _fields_ = [('indptr', C.c_void_p), ('indices', C.c_void_p), ('x', C.c_void_p),
                 ('num_nodes', C.c_int64), ('num_feat', C.c_int64), ('ldx', C.c_int64), ('num_edges', C.c_int64),
-                ('max_degree', C.c_int64), ('hub_id', C.c_void_p), ('hub_bits', C.c_void_p), ('num_hubs', C.c_int64)]
+                ('max_degree', C.c_int64), ('hub_id', C.c_void_p), ('hub_bits', C.c_void_p), ('num_hubs', C.c_int64),
+                ('size_proxy', C.c_void_p)]
 
 
 class Batch(C.Structure):
@@ -45,7 +46,8 @@ class Batch(C.Structure):
                 ('walk_sets', C.c_void_p), ('walk_counts', C.c_void_p), ('link_src_set', C.c_void_p),
                 ('link_dst_set', C.c_void_p), ('walk_cap', C.c_int32), ('reserved2', C.c_int32),
                 ('out_link', C.c_void_p), ('mirror', C.c_void_p), ('link_base', C.c_int64),
-                ('ratio_per_hop', C.c_double), ('max_nodes_per_hop', C.c_int32), ('cap_seed', C.c_uint32)]
+                ('ratio_per_hop', C.c_double), ('max_nodes_per_hop', C.c_int32), ('cap_seed', C.c_uint32),
+                ('front_order', C.c_void_p)]
 
 
 class S3Error(RuntimeError):
@@ -110,6 +112,7 @@ def lib():
         L.s3_negative_candidates.argtypes = [C.POINTER(Graph), C.c_int64, C.c_uint64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                              C.c_void_p, C.c_void_p]
         L.s3_build_hub_bits.argtypes = [C.POINTER(Graph), C.c_void_p]
+        L.s3_node_proxy.argtypes = [C.POINTER(Graph), C.c_void_p, C.c_void_p]
         L.s3_probe_fma.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
         L.s3_probe_fma2.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
         L.s3_peer_alloc.argtypes = [C.c_int64, C.POINTER(C.c_void_p)]
@@ -119,7 +122,7 @@ def lib():
         L.s3_peer_close.argtypes = [C.c_void_p]
         for fn in ('s3_extract', 's3_plan', 's3_plan_items', 's3_diffuse', 's3_gather', 's3_gather_ccn', 's3_ccn_chain', 's3_plan_full', 's3_sign_full', 's3_joint_rows', 's3_sign_head', 's3_walk_sets',
                    's3_dump_edges', 's3_pair_links', 's3_gather_peers', 's3_fill_x0', 's3_fill_mirrors', 's3_peer_alloc', 's3_peer_free', 's3_peer_export',
-                   's3_peer_open', 's3_peer_close', 's3_probe_l2_read', 's3_probe_fma', 's3_probe_fma2', 's3_segment_pool', 's3_negative_candidates', 's3_build_hub_bits'):
+                   's3_peer_open', 's3_peer_close', 's3_probe_l2_read', 's3_probe_fma', 's3_probe_fma2', 's3_segment_pool', 's3_negative_candidates', 's3_build_hub_bits', 's3_node_proxy'):
             getattr(L, fn).restype = C.c_int
         _lib = L
     return _lib

@@ -252,6 +252,14 @@ int s3_probe_fma2(int32_t iters, float* sink, int32_t ctas, void* stream) {
     return e == cudaSuccess ? S3_OK : cuda_fail(e);
 }
 
+int s3_node_proxy(const s3_graph* g, int32_t* out, void* stream) {
+    int rc = check_graph(g, false);
+    if (rc != S3_OK) return rc;
+    if (!out) return S3_ERR_INVALID_ARG;
+    cudaError_t e = s3::launch_node_proxy(*g, out, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? S3_OK : cuda_fail(e);
+}
+
 int s3_build_hub_bits(const s3_graph* g, void* stream) {
     int rc = check_graph(g, false);
     if (rc != S3_OK) return rc;

@@ -175,6 +175,7 @@ cudaError_t launch_extract_bitmap(const s3_graph& g, const s3_batch& b, cudaStre
 cudaError_t launch_extract_sorted(const s3_graph& g, const s3_batch& b, cudaStream_t st, int* rc_out);
 cudaError_t launch_order(const s3_batch& b, int64_t num_records, cudaStream_t st);
 cudaError_t launch_build_hub_bits(const s3_graph& g, cudaStream_t st);
+cudaError_t launch_node_proxy(const s3_graph& g, int32_t* out, cudaStream_t st);
 cudaError_t launch_walk_sets(const s3_graph& g, const int64_t* starts, int64_t num_starts, int rw_m, int rw_M, uint64_t seed,
                              int cap, int32_t* sets, int32_t* counts, cudaStream_t st);
 cudaError_t launch_plan(const s3_batch& b, cudaStream_t st);

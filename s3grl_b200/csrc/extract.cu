@@ -59,6 +59,7 @@ struct ExtractParams {
     const int64_t* __restrict__ out_link;  // link pairing (s3_batch): global link index of a record
     const int64_t* __restrict__ mirror;    // chain table of s3_pair_links, or null
     int64_t link_base;
+    const int32_t* __restrict__ front_order;  // records in descending size proxy, or null: link order
     int caps;                              // per-hop caps active (s3_batch.ratio_per_hop / max_nodes_per_hop)
     double cap_ratio;
     int cap_max;
@@ -168,8 +169,8 @@ __global__ void __launch_bounds__(kExtractThreads, 5) front_kernel(ExtractParams
         __syncthreads();
         if (tid == 0) s_rec = (long long)atomicAdd(&p.counters[S3_CTR_WORK], 1ull);
         __syncthreads();
-        const int64_t rec = s_rec;
-        if (rec >= p.num_records) break;
+        if (s_rec >= p.num_records) break;
+        const int64_t rec = p.front_order ? (int64_t)p.front_order[s_rec] : (int64_t)s_rec;  // longest first
 
         int64_t a, b;
         if (pos_flow) {
@@ -667,7 +668,69 @@ __global__ void order_kernel(const int32_t* __restrict__ cnt, const unsigned lon
     order[s_off[31 - __clz(n)] + c[S3_CNT_CLASSPOS]] = (int32_t)r;
 }
 
+// ---- longest-first hand-out of the records: counting sort by a size proxy over 128 logarithmic classes ----
+__device__ __forceinline__ int proxy_class(long long key) {  // 4 * floor(log2 key) + the next two bits, 0..127
+    if (key < 4) return (int)key;
+    const int hb = 63 - __clzll(key);
+    return min(127, 4 * hb + (int)((key >> (hb - 2)) & 3));
+}
+
+__device__ __forceinline__ long long record_key(const ExtractParams& p, const int32_t* __restrict__ proxy, int64_t r) {
+    const int64_t l = p.flow == S3_FLOW_POS ? r : (r >> 1);
+    const int64_t a = p.link_src[l], b = p.link_dst[l];
+    if (a < 0 || b < 0 || a >= p.num_nodes || b >= p.num_nodes) return 0;
+    if (p.flow != S3_FLOW_POS) return proxy[(r & 1) ? b : a];
+    if (p.mirror) {
+        const int64_t gl = p.out_link ? p.out_link[r] : p.link_base + r;
+        if (p.mirror[gl] <= -2) return 0;  // served by another record: no work
+    }
+    return (long long)proxy[a] + proxy[b];
+}
+
+__global__ void front_hist_kernel(ExtractParams p, const int32_t* __restrict__ proxy, int* hist) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < p.num_records) atomicAdd(&hist[proxy_class(record_key(p, proxy, r))], 1);
+}
+
+__global__ void front_scatter_kernel(ExtractParams p, const int32_t* __restrict__ proxy, int* hist, int32_t* order) {
+    __shared__ int s_start[128];
+    if (threadIdx.x == 0) {  // descending classes; hist[128 + c] is the running cursor of class c
+        int acc = 0;
+        for (int c = 127; c >= 0; --c) {
+            s_start[c] = acc;
+            acc += hist[c];
+        }
+    }
+    __syncthreads();
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p.num_records) return;
+    const int c = proxy_class(record_key(p, proxy, r));
+    order[s_start[c] + atomicAdd(&hist[128 + c], 1)] = (int32_t)r;
+}
+
+// size proxy of every node: its degree plus its neighbours' degrees (one warp per node)
+__global__ void __launch_bounds__(256) node_proxy_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                                         int64_t num_nodes, int32_t* __restrict__ out) {
+    const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (v >= num_nodes) return;
+    const int64_t e0 = indptr[v], e1 = indptr[v + 1];
+    long long acc = 0;
+    for (int64_t e = e0 + lane; e < e1; e += 32) {
+        const int c = indices[e];
+        acc += indptr[c + 1] - indptr[c];
+    }
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+    if (lane == 0) out[v] = (int32_t)min((long long)INT_MAX, acc + (e1 - e0));
+}
+
 }  // namespace
+
+cudaError_t launch_node_proxy(const s3_graph& g, int32_t* out, cudaStream_t st) {
+    const int64_t threads = g.num_nodes * 32;
+    node_proxy_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(g.indptr, g.indices, g.num_nodes, out);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_order(const s3_batch& b, int64_t num_records, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(b.order, 0xff, (size_t)num_records * 4, st);  // -1: skipped by kernel 3
@@ -697,6 +760,17 @@ cudaError_t launch_front(ExtractParams& p, const s3_graph& g, const s3_batch& b,
         return cudaSuccess;
     }
     p.slab_words = grid * p.slab_stride;
+    p.front_order = nullptr;
+    if (b.front_order && g.size_proxy && p.num_records > 2 * grid && b.arena_words >= 256) {
+        // the histogram lives at the head of the arena: the slabs there are not written before the front kernel starts
+        int* hist = reinterpret_cast<int*>(b.arena);
+        e = cudaMemsetAsync(hist, 0, 256 * sizeof(int), st);
+        if (e != cudaSuccess) return e;
+        const unsigned blocks = (unsigned)((p.num_records + 255) / 256);
+        front_hist_kernel<<<blocks, 256, 0, st>>>(p, g.size_proxy, hist);
+        front_scatter_kernel<<<blocks, 256, 0, st>>>(p, g.size_proxy, hist, b.front_order);
+        p.front_order = b.front_order;
+    }
     front_kernel<SC><<<(unsigned)grid, kExtractThreads, smem, st>>>(p);
     e = cudaGetLastError();
     if (e != cudaSuccess || !b.order) return e;

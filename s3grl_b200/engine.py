@@ -117,6 +117,17 @@ class DeviceGraph:
         self._streams = None
         return self
 
+    def ensure_size_proxy(self):
+        """Per-node size proxy (s3_node_proxy: degree + neighbours' degrees) for the longest-first hand-out of records
+        in the front kernel.  Built once per graph on first use of the bitmap tier; results do not depend on it."""
+        if getattr(self, '_proxy', None) is None:
+            self._proxy = torch.empty(self.num_nodes, dtype=torch.int32, device=self.device)
+            with torch.cuda.device(self.device):
+                L.check(L.lib().s3_node_proxy(C.byref(self._c), _ptr(self._proxy),
+                                              C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), 's3_node_proxy')
+            self._c.size_proxy = self._proxy.data_ptr()
+        return self._proxy
+
     def ensure_hub_index(self, max_hubs=None, min_degree=128, force=False):
         """Hub index of the sorted-set tier (include/s3grl_b200.h, s3_graph.hub_*): the `max_hubs` highest-degree
         nodes of degree >= min_degree get an id and a hub x hub adjacency bit matrix (max_hubs^2 / 8 bytes: 302 MB at
@@ -357,6 +368,9 @@ class _Call:
         tier = int(self.lib.s3_extract_tier(C.byref(graph._c), C.byref(probe)))
         if tier == 1 and self.walk is None and not torch.cuda.is_current_stream_capturing():
             graph.ensure_hub_index()
+        self.sorted_front = tier == 0 and not self.return_graphs and os.environ.get('S3GRL_FRONT_ORDER', '1') != '0'
+        if self.sorted_front and not torch.cuda.is_current_stream_capturing():
+            graph.ensure_size_proxy()
         can_pair = (self.flow == L.FLOW_POS and self.fixed_rows and not self.return_graphs and self.walk is None
                     and tier == 0)
         self.pair = bool(pair) and can_pair and mirror is None
@@ -402,7 +416,8 @@ class _Call:
                        _ptr(w['sets']) if w else None, _ptr(w['counts']) if w else None,
                        _ptr(w['src'][b0:]) if w else None, _ptr(w['dst'][b0:]) if w else None, w['cap'] if w else 0, 0,
                        _ptr(ol[b0:]) if ol is not None and b1 > b0 else None, _ptr(getattr(self, 'mirror', None)), b0,
-                       self.cap_ratio, self.cap_max, self.cap_seed)
+                       self.cap_ratio, self.cap_max, self.cap_seed,
+                       _ptr(getattr(self, '_front_order', None)) if b1 > b0 else None)
 
     def launch(self, stage, bi, fn_name, *args, on=None):
         """Call one C entry point; with `profile`, bracket it with CUDA events on its stream.  With S3GRL_NVTX=1
@@ -483,7 +498,9 @@ class _Call:
     def meta(self, nrec):
         off = torch.empty((nrec, L.NOFF), dtype=torch.int64, device=self.dev)
         cnt = torch.empty((nrec, L.NCNT), dtype=torch.int32, device=self.dev)
-        order = torch.empty(nrec, dtype=torch.int32, device=self.dev)
+        both = torch.empty(2 * nrec, dtype=torch.int32, device=self.dev)     # one allocation: same lifetime
+        order = both[:nrec]
+        self._front_order = both[nrec:] if getattr(self, 'sorted_front', False) else None
         return off, cnt, order
 
     # ------------------------------------------------------------------ fixed-row flows

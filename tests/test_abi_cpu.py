@@ -49,7 +49,7 @@ def test_constants_match_header():
              'S3_PEER_HANDLE_BYTES': L.PEER_HANDLE_BYTES, 'S3_VERSION': L.VERSION}
     for k, v in pairs.items():
         assert int(defs[k]) == v, k
-    assert ctypes.sizeof(L.Graph) == 88 and ctypes.sizeof(L.Batch) == 200
+    assert ctypes.sizeof(L.Graph) == 96 and ctypes.sizeof(L.Batch) == 208
 
 
 def test_version_and_error_strings(lib):
