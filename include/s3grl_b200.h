@@ -164,6 +164,10 @@ typedef struct s3_graph {
  * s3_diffuse + s3_gather_ccn). Set the bit for s3_plan AND s3_ccn_chain of the same batch. */
 #define S3_BATCH_CCN_CHAIN 4
 
+/* The front kernel takes 3 instead of 5 CTA slots per SM, so that kernel 3 of the previous batch (on another stream,
+ * waiting on NVLink stores in the multi-GPU exchange) stays resident beside it. */
+#define S3_BATCH_SHARE_SMS 8
+
 /* One batch of records and its scratch. */
 typedef struct s3_batch {
     const int64_t* link_src; /* [num_links] device                                         */

@@ -18,7 +18,7 @@ LABEL_ZERO, LABEL_ZO, LABEL_HOP, LABEL_DRNL, LABEL_DEGREE = 0, 1, 2, 3, 4
 REC_OK, REC_ARENA_OVERFLOW, REC_BAD_LINK, REC_MIRROR = 0, 1, 2, 3
 OFF_NODES, OFF_ROWPTR, OFF_ROWLEN, OFF_LCOL, OFF_SEL, OFF_F32, NOFF = 0, 1, 2, 3, 4, 5, 6
 CNT_N, CNT_M, CNT_S, CNT_STATUS, CNT_PARTNER, CNT_HOP0, CNT_NSTORE, NCNT = 0, 1, 2, 3, 4, 5, 14, 16
-BATCH_STORE_ALL_ROWS, BATCH_FORCE_SORTED_TIER, BATCH_CCN_CHAIN = 1, 2, 4
+BATCH_STORE_ALL_ROWS, BATCH_FORCE_SORTED_TIER, BATCH_CCN_CHAIN, BATCH_SHARE_SMS = 1, 2, 4, 8
 CTR_CURSOR, CTR_ERRORS, CTR_ROWS, CTR_ITEMS, CTR_MAX_N, CTR_SUM_N, CTR_SUM_D, CTR_WORK, NCTR = 0, 1, 2, 3, 4, 5, 6, 7, 48
 CTR_SUM_N_ALL, CTR_SUM_D_ALL, CTR_MIRRORS, CTR_SUM_READ = 8, 9, 10, 11
 

@@ -751,6 +751,9 @@ cudaError_t launch_front(ExtractParams& p, const s3_graph& g, const s3_batch& b,
     cudaError_t e = cache.get(reinterpret_cast<const void*>(front_kernel<SC>), kExtractThreads, smem, &sms, &occ);
     if (e != cudaSuccess) return e;
     p.slab_stride = (4 * g.num_nodes + 1 + 31) & ~int64_t(31);
+    // S3_BATCH_SHARE_SMS: the caller runs kernel 3 of the previous batch beside this launch (two-stream schedule of the
+    // multi-GPU exchange, where kernel 3 waits on NVLink): leave two CTA slots per SM's worth of registers to it
+    if ((b.flags & S3_BATCH_SHARE_SMS) && occ > 3) occ = 3;
     int64_t grid = (int64_t)sms * (occ > 0 ? occ : 1);
     if (grid > p.num_records) grid = p.num_records;
     const int64_t fit = (b.arena_words / 2) / p.slab_stride;  // slabs may take at most half of the arena

@@ -347,7 +347,8 @@ class _Call:
         self.starts = starts + [self.num_links]
         self.num_batches = len(starts) if self.num_links else 0
         self.overlap = bool(overlap) and self.fixed_rows and not self.return_graphs and self.num_batches > 1
-        self.flags = ((L.BATCH_STORE_ALL_ROWS if self.return_graphs else 0)
+        self.flags = ((L.BATCH_SHARE_SMS if (self.overlap and peers is not None) else 0)
+                      | (L.BATCH_STORE_ALL_ROWS if self.return_graphs else 0)
                       | (L.BATCH_FORCE_SORTED_TIER if force_sorted_tier else 0)
                       | (L.BATCH_CCN_CHAIN if self.ccn_chain else 0))
         probe = self.make_batch(0, 0, None, None, None, None)

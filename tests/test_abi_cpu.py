@@ -42,7 +42,7 @@ def test_constants_match_header():
              'S3_CNT_HOP0': L.CNT_HOP0, 'S3_CNT_PARTNER': L.CNT_PARTNER, 'S3_CTR_SUM_D': L.CTR_SUM_D,
              'S3_CTR_ITEMS': L.CTR_ITEMS, 'S3_REC_BAD_LINK': L.REC_BAD_LINK, 'S3_ERR_NOT_IMPLEMENTED': L.S3_ERR_NOT_IMPLEMENTED,
              'S3_BATCH_STORE_ALL_ROWS': L.BATCH_STORE_ALL_ROWS, 'S3_BATCH_FORCE_SORTED_TIER': L.BATCH_FORCE_SORTED_TIER,
-             'S3_BATCH_CCN_CHAIN': L.BATCH_CCN_CHAIN, 'S3_LABEL_ZO': L.LABEL_ZO, 'S3_LABEL_HOP': L.LABEL_HOP,
+             'S3_BATCH_CCN_CHAIN': L.BATCH_CCN_CHAIN, 'S3_BATCH_SHARE_SMS': L.BATCH_SHARE_SMS, 'S3_LABEL_ZO': L.LABEL_ZO, 'S3_LABEL_HOP': L.LABEL_HOP,
              'S3_LABEL_DRNL': L.LABEL_DRNL, 'S3_LABEL_DEGREE': L.LABEL_DEGREE, 'S3_LABEL_ZERO': L.LABEL_ZERO,
              'S3_REC_MIRROR': L.REC_MIRROR, 'S3_CTR_SUM_N_ALL': L.CTR_SUM_N_ALL, 'S3_CTR_SUM_D_ALL': L.CTR_SUM_D_ALL,
              'S3_CTR_MIRRORS': L.CTR_MIRRORS, 'S3_CTR_SUM_READ': L.CTR_SUM_READ, 'S3_MAX_PEERS': L.MAX_PEERS, 'S3_MAX_K_UNION': L.MAX_K_UNION,
