@@ -546,7 +546,7 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
             k['bound_by'] = bound_note.get(stage)
         if stage == 'gather' and tot > 0 and ceilings:
             # kernel 3 reads every feature row from L2 once per column pass and issues (K+1-kmin) * SC FMAs per float
-            hop = st.get('hop_nodes')
+            hop = res.hop_nodes() if hasattr(res, 'hop_nodes') else None
             k['l2_read_ceiling_GBps'] = ceilings['l2_read_GBps']
             k['frac_of_l2_read_ceiling'] = k['achieved_GBps'] / ceilings['l2_read_GBps']
             if hop:

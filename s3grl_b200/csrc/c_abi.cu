@@ -67,7 +67,7 @@ int s3_extract_tier(const s3_graph* g, const s3_batch* b) {
                 b->link_dst_set && b->walk_cap > 0) ? 1 : -1;
     const int radius = b->flow == S3_FLOW_POS ? b->num_hops : b->sign_k;
     const bool bitmap_ok = s3_extract_smem_bytes(g->num_nodes, radius) >= 0 && g->num_edges < (int64_t(1) << 32);
-    const bool sorted_ok = b->flow == S3_FLOW_POS && b->num_hops == 1 && b->strategy == S3_STRATEGY_NONE;
+    const bool sorted_ok = b->flow == S3_FLOW_POS && b->num_hops == 1;  // PoS and PoS Plus (round 2)
     if (sorted_ok && ((b->flags & S3_BATCH_FORCE_SORTED_TIER) || !bitmap_ok)) return 1;
     return bitmap_ok ? 0 : -1;
 }

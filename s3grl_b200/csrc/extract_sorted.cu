@@ -38,6 +38,7 @@ struct SortedParams {
     const int64_t* __restrict__ link_dst;
     int64_t num_records;
     int sign_k, store_all;
+    int strategy;  // PoS Plus row selection (S3_STRATEGY_*): needs store_all
     // ScaLed: node lists come from per-node random-walk sets instead of the adjacency lists
     const int32_t* __restrict__ walk_sets;    // [num_sets, walk_cap] ascending unique, or null
     const int32_t* __restrict__ walk_counts;  // [num_sets]
@@ -86,6 +87,58 @@ __device__ __forceinline__ int lookup(const int32_t* nodes, int n, int u, int v,
 }
 
 
+// ---- PoS Plus on this tier (reference tuned_SIGN.py:228-238) + the float scratch of the record's work items ----
+// With num_hops = 1 every non-seed node of the subgraph is a neighbour of u or of v, and the target-link mask only
+// touches the seed-seed entry, so the selected rows beyond [0, 1] are: intersection — the nodes that sit in BOTH
+// adjacency lists A = N(u) and B = N(v); union — every node c >= 2. They are written in ascending local id behind
+// `sel`, then ONE allocation takes [sel | float scratch of item 0 | scratch of the CCN work items] (the CCN items must
+// follow item 0 contiguously: diffuse.cu / gather_kernel.cuh address them from OFF_F32). Returns false on overflow.
+__device__ __forceinline__ bool select_and_allocate(const SortedParams& p, const int32_t* nodes, int n, const int32_t* __restrict__ A,
+                                                    int du, const int32_t* __restrict__ B, int dv, int* s_scan, long long* s_base,
+                                                    int& s_out, int64_t& base_sel, int64_t& base3) {
+    const int T = kExtractThreads, tid = threadIdx.x, K = p.sign_k;
+    int extra = 0;
+    if (p.strategy == S3_STRATEGY_UNION) {
+        extra = n - 2;
+    } else if (p.strategy == S3_STRATEGY_INTERSECTION) {
+        for (int base = 2; base < n; base += T) {
+            const int c = base + tid;
+            const int f = (c < n && contains(A, du, nodes[c]) && contains(B, dv, nodes[c])) ? 1 : 0;
+            int tot;
+            block_exclusive_scan(f, s_scan, &tot);
+            extra += tot;
+            __syncthreads();
+        }
+    }
+    const int s = 2 + extra, cr = ccn_rows(p.strategy);
+    const int64_t wsel = ((int64_t)extra + 31) & ~int64_t(31);
+    const int64_t wf = (item_words(S3_FLOW_POS, K, n) + (int64_t)ccn_items(s, 2, cr) * ccn_item_words(K, n, cr) + 31) & ~int64_t(31);
+    __syncthreads();
+    if (tid == 0) *s_base = (long long)atomicAdd(&p.counters[S3_CTR_CURSOR], (unsigned long long)(wsel + wf));
+    __syncthreads();
+    base_sel = p.slab_words + *s_base;
+    base3 = base_sel + wsel;
+    s_out = s;
+    if (base3 + wf > p.arena_words) return false;
+    int32_t* sel = p.arena + base_sel;
+    if (p.strategy == S3_STRATEGY_UNION) {
+        for (int c = 2 + tid; c < n; c += T) sel[c - 2] = c;
+    } else if (p.strategy == S3_STRATEGY_INTERSECTION) {
+        int run = 0;
+        for (int base = 2; base < n; base += T) {
+            const int c = base + tid;
+            const int f = (c < n && contains(A, du, nodes[c]) && contains(B, dv, nodes[c])) ? 1 : 0;
+            int tot;
+            const int ex = block_exclusive_scan(f, s_scan, &tot);
+            if (f) sel[run + ex] = c;
+            run += tot;
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    return true;
+}
+
 // ---- bit-matrix path (n <= kBitCap) ---------------------------------------------------------
 // The induced adjacency is an n x n symmetric bit matrix M. Every unordered pair is decided ONCE
 // and both bits are set:
@@ -102,11 +155,14 @@ struct BitCtx {
     float* s_z;            // [2 * kZCapS] shared
     int* s_scan;
     long long* s_base;
+    const int32_t* A;  // the two merged lists (row selection of PoS Plus)
+    const int32_t* B;
+    int du, dv;
 };
 
 __device__ __forceinline__ bool bitmatrix_record(const SortedParams& p, const BitCtx& cx, int32_t* rowptr, int32_t* rowlen,
                                                  int& m_out, int64_t& base2, int64_t& base3, unsigned long long& my_deg,
-                                                 unsigned long long& my_read) {
+                                                 unsigned long long& my_read, int& s_out, int64_t& base_sel) {
     constexpr int SC = 2;
     const int T = kExtractThreads, tid = threadIdx.x, K = p.sign_k;
     const int lane = tid & 31, wid = tid >> 5, l8 = tid & 7, grp = tid >> 3;
@@ -118,15 +174,14 @@ __device__ __forceinline__ bool bitmatrix_record(const SortedParams& p, const Bi
     const int mwords = n * nw;
     const bool m_shared = mwords <= kMCapS;
 
-    // allocation: [bit matrix, when it does not fit in shared memory] [float scratch of the work item]
+    // allocation: the bit matrix, when it does not fit in shared memory (the float scratch follows the row selection)
     const int64_t wordsM = m_shared ? 0 : (((int64_t)mwords + 31) & ~int64_t(31));
-    const int64_t wordsF = (item_words(S3_FLOW_POS, K, n) + 31) & ~int64_t(31);
     __syncthreads();
-    if (tid == 0) *cx.s_base = (long long)atomicAdd(&p.counters[S3_CTR_CURSOR], (unsigned long long)(wordsM + wordsF));
+    if (tid == 0) *cx.s_base = (long long)atomicAdd(&p.counters[S3_CTR_CURSOR], (unsigned long long)wordsM);
     __syncthreads();
     const int64_t baseM = p.slab_words + *cx.s_base;
     base3 = baseM + wordsM;
-    if (base3 + wordsF > p.arena_words) return true;  // overflow
+    if (baseM + wordsM > p.arena_words) return true;  // overflow
     uint32_t* M = m_shared ? cx.s_M : reinterpret_cast<uint32_t*>(p.arena + baseM);
     for (int i = tid; i < mwords; i += T) M[i] = 0u;
 
@@ -207,8 +262,8 @@ __device__ __forceinline__ bool bitmatrix_record(const SortedParams& p, const Bi
     }
     __syncthreads();
 
-    // optional CSR for dumps: rowlen, rowptr, lcol (ascending local id)
-    base2 = base3;
+    // optional CSR for dumps / CCN work items: rowlen, rowptr, lcol (ascending local id)
+    base2 = baseM;
     m_out = 0;
     if (p.store_all) {
         int m = 0;
@@ -248,6 +303,9 @@ __device__ __forceinline__ bool bitmatrix_record(const SortedParams& p, const Bi
         for (int d = 16; d > 0; d >>= 1) my_m += __shfl_down_sync(0xffffffffu, my_m, d);
         m_out = 0;  // not reduced across the block: CNT_M is exact only for dumps
     }
+
+    // ---- selected rows (PoS Plus) and the float scratch of the work items ----
+    if (!select_and_allocate(p, nodes, n, cx.A, cx.du, cx.B, cx.dv, cx.s_scan, cx.s_base, s_out, base_sel, base3)) return true;
 
     // ---- diffusion of the target rows over the bit rows ----
     float* item_f = reinterpret_cast<float*>(p.arena + base3);
@@ -456,8 +514,8 @@ __global__ void __launch_bounds__(kExtractThreads, 4) front_sorted_kernel(Sorted
         int32_t* nodes_g = p.arena + base1;
         int32_t* rowptr = nodes_g + n;
         int32_t* rowlen = rowptr + n + 1;
-        int64_t base2 = 0, base3 = 0;
-        int m = 0;
+        int64_t base2 = 0, base3 = 0, base_sel = 0;
+        int m = 0, s_sel = 2;
         unsigned long long my_deg = 0;
         unsigned long long my_read = tid == 0 ? (unsigned long long)(du + dv) : 0ull;  // the two merged lists
 
@@ -497,7 +555,11 @@ __global__ void __launch_bounds__(kExtractThreads, 4) front_sorted_kernel(Sorted
                 cx.s_z = &s_z[0][0];
                 cx.s_scan = s_scan;
                 cx.s_base = &s_base;
-                overflow = bitmatrix_record(p, cx, rowptr, rowlen, m, base2, base3, my_deg, my_read);
+                cx.A = A;
+                cx.B = B;
+                cx.du = du;
+                cx.dv = dv;
+                overflow = bitmatrix_record(p, cx, rowptr, rowlen, m, base2, base3, my_deg, my_read, s_sel, base_sel);
             } else {
             // ======== large subgraphs: per-row intersections, exact count -> scan -> fill ========
             // ---- count pass: |N(g_j) ∩ S| minus the masked target link, one warp per row ----
@@ -539,14 +601,12 @@ __global__ void __launch_bounds__(kExtractThreads, 4) front_sorted_kernel(Sorted
             }
             if (tid == 0) rowptr[n] = m;
 
-            // ---- allocation 1b: lcol[m];  allocation 2: float scratch of the work item ----
+            // ---- allocation 1b: lcol[m] (the float scratch follows the row selection) ----
             const int64_t words2 = ((int64_t)m + 31) & ~int64_t(31);
-            const int64_t words3 = (item_words(S3_FLOW_POS, K, n) + 31) & ~int64_t(31);
-            if (tid == 0) s_base = (long long)atomicAdd(&p.counters[S3_CTR_CURSOR], (unsigned long long)(words2 + words3));
+            if (tid == 0) s_base = (long long)atomicAdd(&p.counters[S3_CTR_CURSOR], (unsigned long long)words2);
             __syncthreads();
             base2 = p.slab_words + s_base;
-            base3 = base2 + words2;
-            overflow = base3 + words3 > p.arena_words;
+            overflow = base2 + words2 > p.arena_words;
 
             if (!overflow) {
                 int32_t* lcol = p.arena + base2;
@@ -578,7 +638,9 @@ __global__ void __launch_bounds__(kExtractThreads, 4) front_sorted_kernel(Sorted
                     }
                 }
                 __syncthreads();
-
+                // ---- selected rows (PoS Plus) and the float scratch of the work items ----
+                overflow = !select_and_allocate(p, nodes, n, A, du, B, dv, s_scan, &s_base, s_sel, base_sel, base3);
+              if (!overflow) {
                 // ---- diffusion of the target rows: K sweeps over every row (num_hops = 1 <= K) ----
                 float* item_f = reinterpret_cast<float*>(p.arena + base3);
                 float* lab = item_f;
@@ -644,6 +706,7 @@ __global__ void __launch_bounds__(kExtractThreads, 4) front_sorted_kernel(Sorted
                     znext = tmp;
                 }
                 for (int q = tid; q < NWP; q += T) lab[q] = q < NW ? wgt[q] + wgt[NWP + q] : 0.0f;
+              }
             }
             }  // per-row path
         }
@@ -658,12 +721,12 @@ __global__ void __launch_bounds__(kExtractThreads, 4) front_sorted_kernel(Sorted
             off[S3_OFF_ROWPTR] = base1 + n;
             off[S3_OFF_ROWLEN] = base1 + 2 * (int64_t)n + 1;
             off[S3_OFF_LCOL] = base2;
-            off[S3_OFF_SEL] = base2;
+            off[S3_OFF_SEL] = base_sel;
             off[S3_OFF_F32] = base3;
             for (int i = 0; i < S3_NCNT; ++i) cnt[i] = 0;
             cnt[S3_CNT_N] = n;
             cnt[S3_CNT_M] = m;
-            cnt[S3_CNT_S] = overflow ? 0 : 2;
+            cnt[S3_CNT_S] = overflow ? 0 : s_sel;
             cnt[S3_CNT_STATUS] = overflow ? S3_REC_ARENA_OVERFLOW : S3_REC_OK;
             cnt[S3_CNT_PARTNER] = -1;
             cnt[S3_CNT_HOP0] = 2;
@@ -719,7 +782,8 @@ cudaError_t launch_extract_sorted(const s3_graph& g, const s3_batch& b, cudaStre
     p.link_dst = b.link_dst;
     p.num_records = b.num_links;
     p.sign_k = b.sign_k;
-    p.store_all = (b.flags & S3_BATCH_STORE_ALL_ROWS) ? 1 : 0;
+    p.strategy = b.flow == S3_FLOW_POS ? b.strategy : S3_STRATEGY_NONE;
+    p.store_all = ((b.flags & S3_BATCH_STORE_ALL_ROWS) || p.strategy != S3_STRATEGY_NONE) ? 1 : 0;  // CCN items sweep the CSR
     p.walk_sets = b.walk_sets;
     p.walk_counts = b.walk_counts;
     p.src_set = b.link_src_set;

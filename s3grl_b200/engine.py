@@ -446,6 +446,14 @@ class _Call:
         e1.record(on)
         self.profile.append((stage, bi, e0, e1))
 
+    def hop_nodes(self):
+        """Nodes per hop summed over all records of the call (needs profile=...); call after finalize()."""
+        tot = [0] * (L.MAX_HOPS + 1)
+        for cnt in getattr(self, '_hop_cnts', []):
+            hops = cnt[:, L.CNT_HOP0:L.CNT_HOP0 + L.MAX_HOPS + 1].sum(0, dtype=torch.int64).cpu()
+            tot = [a + int(b) for a, b in zip(tot, hops)]
+        return tot
+
     def grow(self):
         self.stats['retries'] += 1
         self.words = int(self.words * 2)
@@ -605,11 +613,8 @@ class _Call:
                 self.sync()
                 host_counters = self.counters.cpu()       # one D2H for every batch's counters
                 todo = [bi for bi, cnt in metas if not self.account(bi, cnt, host_counters)]
-                done = [cnt for bi, cnt in metas if bi not in todo]
-                if self.profile is not None and done:     # nodes per hop over all records: FMA count of kernel 3
-                    hops = sum(cnt[:, L.CNT_HOP0:L.CNT_HOP0 + L.MAX_HOPS + 1].sum(0, dtype=torch.int64) for cnt in done)
-                    prev = self.stats.get('hop_nodes', [0] * (L.MAX_HOPS + 1))
-                    self.stats['hop_nodes'] = [a + int(b) for a, b in zip(prev, hops.cpu())]
+                if self.profile is not None:       # per-hop node counts (FMA count of kernel 3) are summed lazily: hop_nodes()
+                    self._hop_cnts = getattr(self, '_hop_cnts', []) + [cnt for bi, cnt in metas if bi not in todo]
                 if not todo:
                     return
                 if self.return_graphs and self.graphs:
@@ -702,6 +707,7 @@ class _Call:
                 result = PrecomputeResult(xs, row_ptr, self.stats, self.graphs)
                 result._keep = keep
                 result._finalize = lambda: self.finalize_fixed(metas)
+                result.hop_nodes = self.hop_nodes
                 return result if defer else result.finalize()
             self.run_variable()
             xs = [torch.cat([p[k] for p in self.pieces], 0) if self.pieces else torch.empty((0, F1), device=dev)

@@ -785,3 +785,36 @@ def test_walks_reach_every_neighbour_of_a_hub():
     assert leaves[2048:].sum() > 0.7 * leaves.sum() * (D - 2048) / D          # late neighbours are reachable, in proportion
     quart = leaves.reshape(4, -1).sum(1)
     assert quart.min() > 0.8 * quart.mean()
+
+
+@pytest.mark.parametrize('strategy', ['intersection', 'union'])
+@pytest.mark.parametrize('seed,N,E,F,K', [(0, 300, 900, 9, 3), (1, 2000, 30000, 33, 3), (3, 64, 80, 4, 2)])
+def test_sorted_tier_pos_plus(strategy, seed, N, E, F, K):
+    """PoS Plus (tuned_SIGN.py:192-262) on the large-graph tier, forced on small graphs so the oracle can check it:
+    selected rows, indices and operators; and the same rows as the bitmap tier produces."""
+    rng = np.random.default_rng(400 + seed)
+    A = _random_graph(rng, N, E)
+    hub = int(np.argmax(np.diff(A.indptr)))
+    X = rng.random((N, F), dtype=np.float32)
+    links = rng.integers(0, N, (2, 50))
+    links[0, :5] = hub
+    links = links[:, links[0] != links[1]]
+    e = np.stack(A.nonzero(), 1)
+    links = np.concatenate([links, e[rng.choice(e.shape[0], 10, replace=False)].T], axis=1)     # true edges: the mask matters
+    ref = orc.pos_precompute(links, 1, A, X, K, strategy, keep_graphs=True)
+    g = DeviceGraph(A, X)
+    res = precompute(g, links, 1, K, 'PoS', strategy, return_graphs=True, force_sorted_tier=True)
+    assert np.array_equal(res.row_ptr.cpu().numpy(), ref['row_ptr'])
+    for i, (gg, r) in enumerate(zip(res.graphs, ref['graphs'])):
+        _check_indices(gg, r, f'{strategy} link {i}')
+    for k in range(K + 1):
+        assert_features_close(res.xs[k].cpu().numpy(), ref['xs'][k], what=f'{strategy} x{k}')
+    bitmap = precompute(g, links, 1, K, 'PoS', strategy)
+    assert torch.equal(bitmap.row_ptr, res.row_ptr)
+    for k in range(K + 1):
+        assert_features_close(res.xs[k].cpu().numpy(), bitmap.xs[k].cpu().numpy(), tol=2e-6, what=f'tiers {strategy} x{k}')
+    capped = precompute(g, links, 1, K, 'PoS', strategy, force_sorted_tier=True, max_nodes_per_hop=6, cap_seed=2)
+    refc = orc.pos_precompute(links, 1, A, X, K, strategy, caps=dict(max_nodes_per_hop=6, cap_seed=2))
+    assert np.array_equal(capped.row_ptr.cpu().numpy(), refc['row_ptr'])
+    for k in range(K + 1):
+        assert_features_close(capped.xs[k].cpu().numpy(), refc['xs'][k], what=f'capped {strategy} x{k}')
