@@ -263,8 +263,10 @@ class _Call:
 
     def __init__(self, graph, links, num_hops, sign_k, flow, strategy, batch_records, out, return_graphs,
                  arena_words, stream, profile, overlap, host_out, force_sorted_tier, walk=None, ccn_mode=None,
-                 pair=True, out_link=None, mirror=None, peers=None, ratio_per_hop=1.0, max_nodes_per_hop=None, cap_seed=0):
+                 pair=True, out_link=None, mirror=None, peers=None, ratio_per_hop=1.0, max_nodes_per_hop=None, cap_seed=0,
+                 fronts_first=False):
         self.lib = L.lib()
+        self.fronts_first = bool(fronts_first)
         # per-hop caps of the BFS (reference utils.py:66-70) with the deterministic rank rule of include/s3grl_b200.h
         self.cap_ratio = 1.0 if ratio_per_hop is None else float(ratio_per_hop)
         self.cap_max = 0 if max_nodes_per_hop is None else int(max_nodes_per_hop)
@@ -583,10 +585,34 @@ class _Call:
             self.stream.wait_event(back_done[-1])
         return metas, keep
 
+    def enqueue_fixed_fronts_first(self, todo):
+        """Both front kernels, then both gathers (two arenas, one stream).  Used by the odd ranks of an 8-GPU exchange
+        while the even ranks run front / gather / front / gather: the two halves of the node then store their rows
+        over NVLink at different times, and a GPU's NVLink ingress (the limiter there) is not asked for all eight
+        ranks' rows at once."""
+        g, st = C.byref(self.graph._c), self.stream_ptr
+        arenas = (self.graph.arena(self.words, 0), self.graph.arena(self.words, 1))
+        metas, staged = [], []
+        for idx, bi in enumerate(todo):
+            b0, b1 = self.bounds(bi)
+            nrec = (b1 - b0) * self.rpl
+            off, cnt, order = self.meta(nrec)
+            self.counters[bi].zero_()
+            batch = self.make_batch(b0, b1, arenas[idx], off, cnt, self.counters[bi], order=order)
+            self.launch('extract', bi, 's3_extract', g, C.byref(batch), st)
+            staged.append((bi, batch, nrec, b0 * self.rpl * self.nseed))
+            metas.append((bi, cnt))
+        for bi, batch, nrec, row_base in staged:
+            self.gather_fixed(bi, batch, nrec, row_base, st)
+        self.stats['launches'] += 3 * len(todo)
+        return metas, staged
+
     def enqueue_fixed(self, todo):
         t0 = time.perf_counter()
         if self.overlap:
             metas, keep = self.enqueue_fixed_overlapped(todo)
+        elif self.fronts_first and len(todo) == 2 and self.host_out is None and not self.return_graphs:
+            metas, keep = self.enqueue_fixed_fronts_first(todo)
         else:
             metas, keep = [], None
             arena = self.graph.arena(self.words)
@@ -722,7 +748,7 @@ class _Call:
 def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_records=None, out=None,
                return_graphs=False, arena_words=None, stream=None, profile=None, overlap=False, defer=False,
                host_out=None, force_sorted_tier=False, walk=None, ccn_mode=None, pair=True, out_link=None, mirror=None,
-               peers=None, ratio_per_hop=1.0, max_nodes_per_hop=None, cap_seed=0):
+               peers=None, ratio_per_hop=1.0, max_nodes_per_hop=None, cap_seed=0, fronts_first=False):
     """Run the hot path for `links` ([2, L] int64, host or device) on `graph`; returns a
     PrecomputeResult with device tensors.
 
@@ -762,7 +788,7 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
     strategy (as reference tuned_SIGN.py:235) or an unsupported combination."""
     call = _Call(graph, links, num_hops, sign_k, flow, strategy, batch_records, out, return_graphs, arena_words,
                  stream, profile, overlap, host_out, force_sorted_tier, walk, ccn_mode, pair, out_link, mirror, peers,
-                 ratio_per_hop, max_nodes_per_hop, cap_seed)
+                 ratio_per_hop, max_nodes_per_hop, cap_seed, fronts_first)
     return call.run(defer)
 
 

@@ -4,6 +4,7 @@ holds the whole joint matrix for training.  The reference has n
 code at all; torch.distributed (NCCL on GPUs, gloo in the CPU tests) is plumbing only.
 """
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -106,6 +107,7 @@ class PeerBuffers:
         from . import _lib as L
         # NVLink ingress only binds from 4 GPUs on (measured: profiles/README.md); on 2 GPUs the two extra local
         # passes cost more than the bytes they save
+        self.antiphase = os.environ.get('S3GRL_ANTIPHASE', '1') != '0'
         many = dist.get_world_size(group) >= 4
         self.local_x0 = many if local_x0 is None else bool(local_x0)        # operator 0 written locally (s3_fill_x0)
         self.local_mirrors = many if local_mirrors is None else bool(local_mirrors)   # paired links' rows copied locally
@@ -233,6 +235,13 @@ def precompute_exchange(graph, links, num_hops, sign_k, buffers, flow='PoS', def
         buffers._x0_done.record(side)
         buffers._x0_links = links          # alive until the side stream has read them
     idx = torch.arange(buffers.rank, n, buffers.world, device=dev, dtype=torch.int64)
+    if buffers.world >= 8 and kw.get('batch_records') is None and not kw.get('overlap') and buffers.antiphase:
+        # NVLink ingress binds when all eight ranks run kernel 3 at once (eight senders ask a port for 0.98 GB/ms, it
+        # takes 0.62): two batches per rank, even ranks front / gather / front / gather, odd ranks front / front /
+        # gather / gather, so that mostly four ranks store at a time
+        records = int(idx.numel()) * (2 if flow == 'SoP' else 1)
+        kw['batch_records'] = (records + 1) // 2 + (1 if flow == 'SoP' else 0)
+        kw['fronts_first'] = bool(buffers.rank & 1)
     res = precompute(graph, links[:, idx].contiguous(), num_hops, sign_k, flow, None, out_link=idx, mirror=mirror,
                      peers=buffers, pair=False, defer=defer, **kw)
     res._pair_table = table

@@ -11,13 +11,12 @@ from s3grl_b200.tuned_sign import _host_buffers, _finish
 w = bench.build_workload('pubmed_pos')
 x_host = torch.from_numpy(w['X']).pin_memory()
 links = torch.from_numpy(np.ascontiguousarray(w['links'])).pin_memory()
-os.environ['S3GRL_OUTPUT_DEVICE'] = 'cpu'
 rows = []
 for it in range(16):
     t0 = time.perf_counter()
     g = DeviceGraph(w['A'], x_host)
     t1 = time.perf_counter()
-    host = _host_buffers(links.shape[1], g.num_feat, 3)
+    host = _host_buffers(links.shape[1], g.num_feat, 3, 'cpu')
     t2 = time.perf_counter()
     res = precompute(g, links, 3, 3, flow='PoS', host_out=host)
     t3 = time.perf_counter()

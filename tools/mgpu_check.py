@@ -38,7 +38,9 @@ def main():
                 o.fill_(float('nan'))
             torch.cuda.synchronize(dev)
             buf.barrier()
-            for rep, kw in enumerate((dict(), dict(batch_records=512, overlap=True))):
+            half = (links.shape[1] // dist.get_world_size() + 1) // 2 * (2 if flow == 'SoP' else 1) + 2
+            for rep, kw in enumerate((dict(), dict(batch_records=512, overlap=True),
+                                      dict(batch_records=half, fronts_first=bool(rank & 1)))):     # the 8-GPU anti-phase schedule
                 res, mirror = precompute_exchange(g, links, hops, K, buf, flow=flow, **kw)
                 torch.cuda.synchronize(dev)
                 want = precompute(g, links, hops, K, flow, pair=False)
