@@ -107,7 +107,8 @@ class PeerBuffers:
         from . import _lib as L
         # NVLink ingress only binds from 4 GPUs on (measured: profiles/README.md); on 2 GPUs the two extra local
         # passes cost more than the bytes they save
-        self.antiphase = os.environ.get('S3GRL_ANTIPHASE', '1') != '0'
+        # measured on 8 x B200: 5.37 vs 5.43 ms per PubMed step — the senders, not the receivers, are the limit; opt-in
+        self.antiphase = os.environ.get('S3GRL_ANTIPHASE', '0') != '0'
         many = dist.get_world_size(group) >= 4
         self.local_x0 = many if local_x0 is None else bool(local_x0)        # operator 0 written locally (s3_fill_x0)
         self.local_mirrors = many if local_mirrors is None else bool(local_mirrors)   # paired links' rows copied locally
