@@ -527,7 +527,7 @@ class _Call:
             return self.launch('gather', bi, 's3_gather', g, C.byref(batch), nrec, self.out_ptrs, self.F1, row_base, st, on=on)
         pb = self.peers
         return self.launch('gather', bi, 's3_gather_peers', g, C.byref(batch), nrec, pb.base_array, pb.world_dst, pb.op_stride,
-                           self.F1, pb.flags, st, on=on)
+                           pb.ld, pb.flags, st, on=on)
 
     def enqueue_fixed_batch(self, bi, arena):
         g, st = C.byref(self.graph._c), self.stream_ptr

@@ -123,7 +123,11 @@ class PeerBuffers:
         self.device = torch.device(device)
         self.num_links, self.cols, self.num_ops = int(num_links), int(num_feat) + 1, int(sign_k) + 1
         self.rows = 2 * self.num_links
-        self.op_stride = (self.rows * self.cols + 31) // 32 * 32        # floats; operators start on 128-byte lines
+        # row stride of the exchanged matrices: F + 1 (PyG's contiguous layout) or padded to a multiple of 32 floats, so
+        # that every row starts on a 128-byte line and remote stores are whole lines (S3GRL_PEER_ROWS=pad; the .local
+        # views are then strided [rows, F + 1] windows of [rows, ld])
+        self.ld = (self.cols + 31) // 32 * 32 if os.environ.get('S3GRL_PEER_ROWS', 'packed') == 'pad' else self.cols
+        self.op_stride = (self.rows * self.ld + 31) // 32 * 32        # floats; operators start on 128-byte lines
         self._nfloats = max(self.num_ops * self.op_stride, 64)
         self._opened, self._ptr, self._symm = [], None, None
         self.backend = None
@@ -145,7 +149,7 @@ class PeerBuffers:
             self.backend = 'ipc'
         self.world_dst = len(self.dst)
         self.base_array = (C.c_void_p * self.world_dst)(*self.dst)
-        self.local = [self._flat[k * self.op_stride:k * self.op_stride + self.rows * self.cols].view(self.rows, self.cols)
+        self.local = [self._flat[k * self.op_stride:k * self.op_stride + self.rows * self.ld].view(self.rows, self.ld)[:, :self.cols]
                       for k in range(self.num_ops)]
         self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.barrier()
@@ -231,7 +235,7 @@ def precompute_exchange(graph, links, num_hops, sign_k, buffers, flow='PoS', def
         with torch.cuda.device(dev):
             buffers._L.check(buffers._lib.s3_fill_x0(C.byref(graph._c), C.c_void_p(links[0].data_ptr()),
                                                      C.c_void_p(links[1].data_ptr()), n, C.c_void_p(buffers.local[0].data_ptr()),
-                                                     buffers.cols, C.c_void_p(side.cuda_stream)), 's3_fill_x0')
+                                                     buffers.ld, C.c_void_p(side.cuda_stream)), 's3_fill_x0')
         buffers._x0_done = torch.cuda.Event()
         buffers._x0_done.record(side)
         buffers._x0_links = links          # alive until the side stream has read them
@@ -264,5 +268,5 @@ def exchange_finish(buffers, mirror, stream=None):
         ptrs = (C.c_void_p * buffers.num_ops)(*[o.data_ptr() for o in buffers.local])
         with torch.cuda.device(dev):
             buffers._L.check(buffers._lib.s3_fill_mirrors(C.c_void_p(mirror.data_ptr()), buffers.num_links, ptrs,
-                                                          1 if buffers.local_x0 else 0, buffers.num_ops, buffers.cols, buffers.cols,
+                                                          1 if buffers.local_x0 else 0, buffers.num_ops, buffers.cols, buffers.ld,
                                                           C.c_void_p(st.cuda_stream)), 's3_fill_mirrors')
