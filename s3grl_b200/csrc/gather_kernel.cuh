@@ -97,6 +97,30 @@ struct GatherCtx {
     bool swap01;
 };
 
+// Packed FP32 pairs (sm_100a FFMA2, PTX fma.rn.f32x2): two IEEE fused multiply-adds per issued instruction — the same
+// bits as two scalar FFMAs, half the issue slots. The kernel is issue-bound on the L2-resident workloads (ncu: 67 %
+// issue active, FFMA 42 % of the instructions), not FP32-pipe-bound (0.26 of the FFMA ceiling).
+__device__ __forceinline__ unsigned long long pack2(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ void fma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+constexpr bool kUseF32x2 = true;
+// accumulator of one float4 column: two packed pairs (x, y), (z, w) kept packed for the whole kernel
+struct Acc {
+    unsigned long long lo, hi;
+};
+__device__ __forceinline__ float4 acc_to_float4(const Acc& a) {
+    float4 v;
+    unpack2(a.lo, v.x, v.y);
+    unpack2(a.hi, v.z, v.w);
+    return v;
+}
+
 template <int K1, int SC, int KMIN>
 __device__ __forceinline__ void load_weights(float (&w)[K1 * SC], const float* wrow) {
     if (SC == 2) {
@@ -124,7 +148,7 @@ __device__ __forceinline__ void load_weights(float (&w)[K1 * SC], const float* w
 // Accumulate nodes [lo, hi) of the record; only operators k >= KMIN carry weight there.
 // FULL: every lane owns a valid column (rows are padded), so the loads carry no predicates.
 template <int K1, int SC, int C, int KMIN, bool FULL>
-__device__ __forceinline__ void accumulate_range(float4 (&acc)[K1 * SC][C], int lo, int hi, const GatherCtx<C>& cx) {
+__device__ __forceinline__ void accumulate_range(Acc (&acc)[K1 * SC][C], int lo, int hi, const GatherCtx<C>& cx) {
     constexpr int NW = K1 * SC, NWP = (NW + 3) & ~3, Q0 = KMIN * SC;
     float* s_w = cx.s_w;
     uint32_t* s_off = cx.s_off;
@@ -160,15 +184,23 @@ __device__ __forceinline__ void accumulate_range(float4 (&acc)[K1 * SC][C], int 
             for (int u = 0; u < kU; ++u) {
                 float w[NW];
                 load_weights<K1, SC, KMIN>(w, s_w + (t + u * G) * NWP);
-#pragma unroll
-                for (int q = Q0; q < NW; ++q)
+                if (kUseF32x2) {
+                    unsigned long long xlo[C], xhi[C];
 #pragma unroll
                     for (int i = 0; i < C; ++i) {
-                        acc[q][i].x = fmaf(w[q], xv[u][i].x, acc[q][i].x);
-                        acc[q][i].y = fmaf(w[q], xv[u][i].y, acc[q][i].y);
-                        acc[q][i].z = fmaf(w[q], xv[u][i].z, acc[q][i].z);
-                        acc[q][i].w = fmaf(w[q], xv[u][i].w, acc[q][i].w);
+                        xlo[i] = pack2(xv[u][i].x, xv[u][i].y);
+                        xhi[i] = pack2(xv[u][i].z, xv[u][i].w);
                     }
+#pragma unroll
+                    for (int q = Q0; q < NW; ++q) {
+                        const unsigned long long ww = pack2(w[q], w[q]);
+#pragma unroll
+                        for (int i = 0; i < C; ++i) {
+                            fma2(acc[q][i].lo, ww, xlo[i]);
+                            fma2(acc[q][i].hi, ww, xhi[i]);
+                        }
+                    }
+                }
             }
         }
         // tail of the tile, one row at a time (same order of accumulation: ascending node index)
@@ -180,22 +212,24 @@ __device__ __forceinline__ void accumulate_range(float4 (&acc)[K1 * SC][C], int 
                 xv[i] = (FULL || cx.colok[i]) ? __ldg(cx.xcol[i] + o) : make_float4(0.f, 0.f, 0.f, 0.f);
             float w[NW];
             load_weights<K1, SC, KMIN>(w, s_w + t * NWP);
+            if (kUseF32x2) {
 #pragma unroll
-            for (int q = Q0; q < NW; ++q)
+                for (int q = Q0; q < NW; ++q) {
+                    const unsigned long long ww = pack2(w[q], w[q]);
 #pragma unroll
-                for (int i = 0; i < C; ++i) {
-                    acc[q][i].x = fmaf(w[q], xv[i].x, acc[q][i].x);
-                    acc[q][i].y = fmaf(w[q], xv[i].y, acc[q][i].y);
-                    acc[q][i].z = fmaf(w[q], xv[i].z, acc[q][i].z);
-                    acc[q][i].w = fmaf(w[q], xv[i].w, acc[q][i].w);
+                    for (int i = 0; i < C; ++i) {
+                        fma2(acc[q][i].lo, ww, pack2(xv[i].x, xv[i].y));
+                        fma2(acc[q][i].hi, ww, pack2(xv[i].z, xv[i].w));
+                    }
                 }
+            }
         }
     }
 }
 
 template <int K1, int SC, int C, int KMIN, bool FULL>
 struct RangeDispatch {
-    __device__ __forceinline__ static void run(int kmin, float4 (&acc)[K1 * SC][C], int lo, int hi, const GatherCtx<C>& cx) {
+    __device__ __forceinline__ static void run(int kmin, Acc (&acc)[K1 * SC][C], int lo, int hi, const GatherCtx<C>& cx) {
         if (kmin == KMIN)
             accumulate_range<K1, SC, C, KMIN, FULL>(acc, lo, hi, cx);
         else
@@ -204,7 +238,7 @@ struct RangeDispatch {
 };
 template <int K1, int SC, int C, bool FULL>
 struct RangeDispatch<K1, SC, C, K1, FULL> {
-    __device__ __forceinline__ static void run(int, float4 (&)[K1 * SC][C], int, int, const GatherCtx<C>&) {}
+    __device__ __forceinline__ static void run(int, Acc (&)[K1 * SC][C], int, int, const GatherCtx<C>&) {}
 };
 
 // Occupancy target by accumulator footprint (K1*SC*C float4 per thread): the kernel is latency /
@@ -263,11 +297,11 @@ __global__ void __launch_bounds__(kGatherThreads, gather_min_blocks(K1 * SC * C)
     cx.G = G;
     cx.swap01 = SC == 2 && !p.ccn && p.flow == S3_FLOW_POS && n >= 2 && nodes[0] > nodes[1];
 
-    float4 acc[NW][C];
+    Acc acc[NW][C];
 #pragma unroll
     for (int q = 0; q < NW; ++q)
 #pragma unroll
-        for (int i = 0; i < C; ++i) acc[q][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < C; ++i) acc[q][i].lo = acc[q][i].hi = 0ull;  // (0.f, 0.f)
 
     // hop ranges of the canonical node order; the records' own rows are the seeds, CCN rows are
     // hop-1 nodes (one hop closer to everything: kmin shifts down by one)
@@ -290,7 +324,7 @@ __global__ void __launch_bounds__(kGatherThreads, gather_min_blocks(K1 * SC * C)
 #pragma unroll
             for (int q = 0; q < NW; ++q)
 #pragma unroll
-                for (int i = 0; i < C; ++i) red[(((grp - 1) * NW + q) * C + i) * tpr + lane] = acc[q][i];
+                for (int i = 0; i < C; ++i) red[(((grp - 1) * NW + q) * C + i) * tpr + lane] = acc_to_float4(acc[q][i]);
         }
         __syncthreads();
         if (grp == 0) {
@@ -300,10 +334,13 @@ __global__ void __launch_bounds__(kGatherThreads, gather_min_blocks(K1 * SC * C)
 #pragma unroll
                     for (int i = 0; i < C; ++i) {
                         const float4 v = red[(((g - 1) * NW + q) * C + i) * tpr + lane];
-                        acc[q][i].x += v.x;
-                        acc[q][i].y += v.y;
-                        acc[q][i].z += v.z;
-                        acc[q][i].w += v.w;
+                        float4 a = acc_to_float4(acc[q][i]);
+                        a.x += v.x;
+                        a.y += v.y;
+                        a.z += v.z;
+                        a.w += v.w;
+                        acc[q][i].lo = pack2(a.x, a.y);
+                        acc[q][i].hi = pack2(a.z, a.w);
                     }
         }
     }
@@ -334,10 +371,11 @@ __global__ void __launch_bounds__(kGatherThreads, gather_min_blocks(K1 * SC * C)
 #pragma unroll
             for (int i = 0; i < C; ++i) {
                 float* d = s_row + 1 + 4 * (i * tpr + lane);
-                d[0] = acc[q][i].x;
-                d[1] = acc[q][i].y;
-                d[2] = acc[q][i].z;
-                d[3] = acc[q][i].w;
+                const float4 a = acc_to_float4(acc[q][i]);
+                d[0] = a.x;
+                d[1] = a.y;
+                d[2] = a.z;
+                d[3] = a.w;
             }
             if (lane == 0) s_row[0] = lab[q];  // the label / self-return column (read by chunk 0 only)
         }
