@@ -192,7 +192,8 @@ int s3_fill_mirrors(const int64_t* mirror, int64_t num_links, float* const* ops,
                     int64_t ldo, void* stream) {
     if (num_links < 0 || first_op < 0 || num_ops < first_op || num_ops > 2 * S3_MAX_K || num_cols < 1 || ldo < num_cols)
         return S3_ERR_INVALID_ARG;
-    if (num_links > 0 && (!mirror || !ops)) return S3_ERR_INVALID_ARG;
+    if (num_links == 0) return S3_OK;
+    if (!mirror || !ops) return S3_ERR_INVALID_ARG;
     s3::OutPtrs o;
     memset(&o, 0, sizeof(o));
     for (int k = first_op; k < num_ops; ++k) {

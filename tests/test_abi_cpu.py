@@ -110,6 +110,69 @@ def test_argument_validation_of_the_wider_entry_points(lib):
     assert head(0, 8, 8, 8, 256, 1) == L.S3_OK
 
 
+def test_argument_validation_of_the_round2_entry_points(lib):
+    """Link pairing, the peer exchange, pooling, negative sampling, the graph-level helpers: invalid arguments come back
+    as error codes before anything is launched (no GPU needed)."""
+    P = ctypes.c_void_p
+    g = L.Graph(16, 16, 16, 10, 4, 4, 20, 5)
+    b = L.Batch()
+    b.flow, b.strategy, b.sign_k, b.num_hops = L.FLOW_POS, L.STRATEGY_NONE, 3, 2
+    # s3_pair_links: table must hold >= 2 * L slots, a power of two
+    assert lib.s3_pair_table_slots(0) == 64 and lib.s3_pair_table_slots(100) == 256 and lib.s3_pair_table_slots(164000) == 524288
+    assert lib.s3_pair_links(P(16), P(16), 100, 50, P(16), 128, P(16), None) == L.S3_ERR_WORKSPACE
+    assert lib.s3_pair_links(P(16), P(16), 100, 50, P(16), 300, P(16), None) == L.S3_ERR_WORKSPACE       # not a power of two
+    assert lib.s3_pair_links(None, P(16), 100, 50, P(16), 256, P(16), None) == L.S3_ERR_INVALID_ARG
+    assert lib.s3_pair_links(None, None, 0, 50, None, 0, None, None) == L.S3_OK                               # empty list
+    # s3_gather_peers: fixed-row flows only, 1..8 destinations
+    dst = (ctypes.c_void_p * 9)(*([16] * 9))
+    assert lib.s3_gather_peers(ctypes.byref(g), ctypes.byref(b), 0, dst, 9, 100, 5, 0, None) == L.S3_ERR_INVALID_ARG
+    assert lib.s3_gather_peers(ctypes.byref(g), ctypes.byref(b), 0, dst, 0, 100, 5, 0, None) == L.S3_ERR_INVALID_ARG
+    assert lib.s3_gather_peers(ctypes.byref(g), ctypes.byref(b), 0, dst, 2, 100, 4, 0, None) == L.S3_ERR_INVALID_ARG   # ldo < F + 1
+    b.strategy = L.STRATEGY_UNION
+    assert lib.s3_gather_peers(ctypes.byref(g), ctypes.byref(b), 0, dst, 2, 100, 5, 0, None) == L.S3_ERR_NOT_IMPLEMENTED
+    b.sign_k = L.MAX_K_UNION + 1          # union is built for sign_k <= 5: rejected by every entry point, up front
+    assert lib.s3_extract(ctypes.byref(g), ctypes.byref(b), None) == L.S3_ERR_NOT_IMPLEMENTED
+    b.strategy, b.sign_k = L.STRATEGY_NONE, 3
+    # s3_fill_x0 / s3_fill_mirrors
+    assert lib.s3_fill_x0(ctypes.byref(g), P(16), P(16), 4, P(16), 4, None) == L.S3_ERR_INVALID_ARG            # ldo < F + 1
+    assert lib.s3_fill_x0(ctypes.byref(g), None, None, 0, None, 5, None) == L.S3_OK
+    ops = (ctypes.c_void_p * 4)(16, 16, 16, 16)
+    assert lib.s3_fill_mirrors(P(16), 4, ops, 5, 4, 5, 5, None) == L.S3_ERR_INVALID_ARG                         # first_op > num_ops
+    assert lib.s3_fill_mirrors(None, 0, None, 1, 4, 5, 5, None) == L.S3_OK
+    # s3_segment_pool: k_pool_strategy and layout
+    assert lib.s3_segment_pool(P(16), 8, 8, P(16), 4, 3, L.POOL_OUT_CENTER, P(16), 16, None) == L.S3_ERR_NOT_IMPLEMENTED   # 'concat'
+    assert lib.s3_segment_pool(P(16), 8, 8, P(16), 4, L.POOL_SUM, 7, P(16), 16, None) == L.S3_ERR_INVALID_ARG
+    assert lib.s3_segment_pool(P(16), 8, 8, P(16), 4, L.POOL_SUM, L.POOL_OUT_ROWS, P(16), 16, None) == L.S3_ERR_INVALID_ARG  # ld_out < 3 * cols
+    assert lib.s3_segment_pool(None, 8, 8, None, 0, L.POOL_MEAN, L.POOL_OUT_CENTER, None, 16, None) == L.S3_OK
+    # s3_negative_candidates / s3_build_hub_bits / s3_node_proxy / probes / peer memory
+    assert lib.s3_negative_candidates(ctypes.byref(g), 100, 1, P(16), 128, P(16), P(16), P(16), None) == L.S3_ERR_WORKSPACE
+    assert lib.s3_negative_candidates(ctypes.byref(g), 0, 1, None, 0, None, None, None, None) == L.S3_OK
+    assert lib.s3_build_hub_bits(ctypes.byref(g), None) == L.S3_ERR_INVALID_ARG                                 # no hub index attached
+    assert lib.s3_node_proxy(ctypes.byref(g), None, None) == L.S3_ERR_INVALID_ARG
+    assert lib.s3_probe_l2_read(None, 1 << 20, 1, P(16), 8, None) == L.S3_ERR_INVALID_ARG
+    assert lib.s3_probe_fma(0, P(16), 8, None) == L.S3_ERR_INVALID_ARG
+    assert lib.s3_peer_alloc(0, ctypes.byref(ctypes.c_void_p())) == L.S3_ERR_INVALID_ARG
+    assert lib.s3_peer_export(None, ctypes.create_string_buffer(64)) == L.S3_ERR_INVALID_ARG
+    assert lib.s3_peer_free(None) == L.S3_OK and lib.s3_peer_close(None) == L.S3_OK
+
+
+def test_per_hop_cap_counts_match_the_reference_formula():
+    """k = min(int(ratio * c), max) (reference utils.py:66-70) — the oracle's cap_fringe keeps exactly that many nodes,
+    the same ones for the same seed, and a subset relation holds between caps."""
+    import numpy as np
+    from oracle import s3grl_oracle as orc
+    fringe = np.arange(100, 1100, 3)
+    for ratio, mx in ((1.0, None), (0.5, None), (1.0, 40), (0.3, 1000), (0.9, 7), (0.001, None)):
+        kept = orc.cap_fringe(fringe, ratio, mx, seed=5)
+        k = fringe.size if ratio >= 1.0 else int(ratio * fringe.size)
+        k = min(k, mx) if mx is not None else k
+        assert kept.size == k and np.all(np.diff(kept) > 0) and np.isin(kept, fringe).all()
+        assert np.array_equal(kept, orc.cap_fringe(fringe, ratio, mx, seed=5))
+    small, large = orc.cap_fringe(fringe, 1.0, 10, seed=1), orc.cap_fringe(fringe, 1.0, 50, seed=1)
+    assert np.isin(small, large).all()              # the k smallest rank keys are nested
+    assert not np.array_equal(orc.cap_fringe(fringe, 1.0, 10, seed=1), orc.cap_fringe(fringe, 1.0, 10, seed=2))
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(L, '_lib', None)
     monkeypatch.setattr(L, 'LIB_PATH', str(tmp_path / 'nope.so'))
