@@ -808,7 +808,7 @@ def main():
             sub = measure(args, w, name, 2, 3, dev, rank, world, False, ceilings, None)
             keep = {k_: sub[k_] for k_ in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'ms_per_step', 'scaling', 'gpu_launches')}
             keep['config'] = sub['config']
-            keep['roofline'] = {k_: sub['roofline'][k_] for k_ in ('kernel', 'achieved', 'peak', 'frac', 'share_of_step', 'path', 'path_streamed')
+            keep['roofline'] = {k_: sub['roofline'][k_] for k_ in ('kernel', 'achieved', 'peak', 'frac', 'share_of_step', 'path', 'path_streamed', 'hub_index')
                                 if k_ in sub['roofline']}
             if 'exchange' in sub:
                 keep['exchange'] = sub['exchange']
