@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'lib', 'libs3grl_b200.so')
+LIB_PATH = os.environ.get('S3GRL_LIB') or os.path.join(HERE, 'lib', 'libs3grl_b200.so')     # S3GRL_LIB: A/B builds
 
 # constants mirrored from the header
 S3_OK, S3_ERR_INVALID_ARG, S3_ERR_UNSUPPORTED, S3_ERR_CUDA, S3_ERR_NOT_IMPLEMENTED, S3_ERR_WORKSPACE = 0, 1, 2, 3, 4, 5

@@ -66,7 +66,21 @@ struct ExtractParams {
     uint32_t cap_seed;
 };
 
-constexpr int kStreamLanes = 4;  // lanes per streamed (hop-K) row
+#ifndef S3_STREAM_LANES
+#define S3_STREAM_LANES 4
+#endif
+#ifdef S3_V_LDG
+#define S3_IDX(ptr, i) __ldg((ptr) + (i))
+#else
+#define S3_IDX(ptr, i) (ptr)[i]
+#endif
+#ifndef S3_V_UNROLL
+#define S3_V_UNROLL 2  // streamed rows: two adjacency loads in flight per lane (measured: 14.11 -> 13.94 ms per PubMed step;
+                       // 3 and 4 no better, `unroll 1` on the sweep / BFS loops 5 % worse than the compiler's own choice)
+#endif
+#define S3_PRAGMA_(x) _Pragma(#x)
+#define S3_UNROLL(n) S3_PRAGMA_(unroll n)
+constexpr int kStreamLanes = S3_STREAM_LANES;  // lanes per streamed (hop-K) row
 constexpr int kBfsLanes = 4;     // lanes per frontier node in the BFS expansion
 constexpr int kSweepLanes = 4;   // lanes per stored row in the diffusion sweeps
 constexpr int kRowCap = 1536;  // rows whose (start, adjacency offset) are cached in shared memory
@@ -131,7 +145,10 @@ __device__ __noinline__ void cap_level(uint32_t* cur, int w0, int w1, int keep, 
 }
 
 template <int SC>  // selected rows of the first work item == number of seeds: 2 (PoS), 1 (SoP)
-__global__ void __launch_bounds__(kExtractThreads, 5) front_kernel(ExtractParams p) {
+#ifndef S3_FRONT_BLOCKS
+#define S3_FRONT_BLOCKS 5  // resident CTAs per SM the register budget is sized for (48 registers)
+#endif
+__global__ void __launch_bounds__(kExtractThreads, S3_FRONT_BLOCKS) front_kernel(ExtractParams p) {
     extern __shared__ uint32_t sm[];
     const int W = p.W, h = p.radius, T = kExtractThreads, tid = threadIdx.x, K = p.sign_k;
     constexpr int nseed = SC;
@@ -242,7 +259,7 @@ __global__ void __launch_bounds__(kExtractThreads, 5) front_kernel(ExtractParams
             for (int j = flo + grpb; j < n; j += NGB) {
                 const int64_t e0 = slab_estart[j], e1 = e0 + slab_deg[j];
                 for (int64_t e = e0 + lb; e < e1; e += kBfsLanes) {
-                    const int c = p.indices[e];
+                    const int c = S3_IDX(p.indices, e);
                     if (!test_bit(V, c)) atomicOr(&cur[c >> 5], 1u << (c & 31));
                 }
             }
@@ -414,7 +431,7 @@ __global__ void __launch_bounds__(kExtractThreads, 5) front_kernel(ExtractParams
                 int lid = -1;
                 bool in = false;
                 if (ok) {
-                    const int c = p.indices[(int64_t)es[j] + (slot - rp[j])];
+                    const int c = S3_IDX(p.indices, (int64_t)es[j] + (slot - rp[j]));
                     in = test_bit(V, c);
                     if (pos_flow && ((j == 0 && c == s1) || (j == 1 && c == s0))) in = false;  // utils.py:79-80
                     if (in) lid = local_id(c, s0, s1, nseed, Lb, pre, s_lvl_base, nlev, W);
@@ -565,8 +582,9 @@ __global__ void __launch_bounds__(kExtractThreads, 5) front_kernel(ExtractParams
 #pragma unroll
                         for (int c = 0; c < SC; ++c) t[c] = 0.0f;
                         int cntv = 0;
+S3_UNROLL(S3_V_UNROLL)
                         for (int idx = ls; idx < len; idx += kStreamLanes) {
-                            const int c_ = p.indices[e0 + idx];
+                            const int c_ = S3_IDX(p.indices, e0 + idx);
                             const int w = c_ >> 5, b = c_ & 31;
                             cntv += (V[w] >> b) & 1u;
                             int i = -1;
