@@ -78,8 +78,17 @@ cudaError_t launch_gather_sc8_k6(const GatherParams& p, int C, dim3 grid, size_t
 namespace {
 
 
-constexpr int kTile = 64;  // nodes staged per tile
-constexpr int kU = 4;      // nodes in flight per row group
+#ifndef S3_KTILE
+#define S3_KTILE 128
+#endif
+#ifndef S3_GATHER_BLOCKS
+#define S3_GATHER_BLOCKS 8
+#endif
+constexpr int kTile = S3_KTILE;  // nodes staged per tile
+// feature rows in flight per row group, by accumulator footprint (float4 per thread). Measured on PubMed PoS (8 float4):
+// 2 rows 14.2 ms per step, 4 13.0, 8 12.2, 16 12.0 (with 128-node tiles) — the loads are L2 hits ~600 cycles away and the
+// compiler interleaves them with the FFMA2s inside the 64-register budget
+__host__ __device__ constexpr int rows_in_flight(int acc4) { return acc4 <= 8 ? 16 : acc4 <= 16 ? 8 : 4; }
 
 
 template <int C>
@@ -150,6 +159,7 @@ __device__ __forceinline__ void load_weights(float (&w)[K1 * SC], const float* w
 template <int K1, int SC, int C, int KMIN, bool FULL>
 __device__ __forceinline__ void accumulate_range(Acc (&acc)[K1 * SC][C], int lo, int hi, const GatherCtx<C>& cx) {
     constexpr int NW = K1 * SC, NWP = (NW + 3) & ~3, Q0 = KMIN * SC;
+    constexpr int kU = FULL ? rows_in_flight(NW * C) : 4;  // predicated loads (foreign row strides) keep round 1's depth
     float* s_w = cx.s_w;
     uint32_t* s_off = cx.s_off;
     const int tid = cx.tid, grp = cx.grp, G = cx.G;
@@ -243,7 +253,7 @@ struct RangeDispatch<K1, SC, C, K1, FULL> {
 
 // Occupancy target by accumulator footprint (K1*SC*C float4 per thread): the kernel is latency /
 // L2-throughput bound, and 8 CTAs of 4 warps per SM stream 16 TB/s where 5 CTAs streamed 12 TB/s.
-constexpr int gather_min_blocks(int acc4) { return acc4 <= 8 ? 8 : acc4 <= 12 ? 6 : acc4 <= 16 ? 5 : acc4 <= 24 ? 3 : 2; }
+constexpr int gather_min_blocks(int acc4) { return acc4 <= 8 ? S3_GATHER_BLOCKS : acc4 <= 12 ? 6 : acc4 <= 16 ? 5 : acc4 <= 24 ? 3 : 2; }
 
 template <int K1, int SC, int C, bool FULL>
 __global__ void __launch_bounds__(kGatherThreads, gather_min_blocks(K1 * SC * C)) gather_kernel(GatherParams p) {
