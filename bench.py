@@ -529,11 +529,15 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
     # SURVEY 8d terms per kernel, over the records this rank actually extracted
     alg = dict(extract=4 * st['sum_d'] + 8 * st['sum_n'],
                gather=4 * F * st['sum_n'] + 4 * rows_written * (K + 1) * (F + 1),
-               sign_full=4 * F * st['sum_n'] + 4 * st['rows'] * (K + 1) * (F + 1))
+               sign_full=4 * F * st['sum_n'] + 4 * st['rows'] * (K + 1) * (F + 1),
+               # union: the chain reads every subgraph's feature rows once and writes the CCN rows of all K+1 operators
+               ccn_chain=4 * F * st['sum_n'] + 4 * max(0, st['rows'] - 2 * st['records']) * (K + 1) * (F + 1))
     bound_note = dict(extract="issue / latency bound integer work on shared-memory bitmaps (ncu: profiles/); its HBM fraction is "
                               "low by nature" if not is_rmat else "latency bound sorted-set intersections over HBM-resident adjacency lists",
                       gather="L2 -> SM bandwidth and FP32 issue when X is L2-resident (PubMed 39 MB), HBM otherwise",
-                      sign_full="HBM writes")
+                      sign_full="HBM writes",
+                      ccn_chain="shared-memory bandwidth: every induced edge of a level reads one row segment of the previous "
+                                "level's [n][CW] buffer (DESIGN.md section 4); X is L2-resident on PubMed")
     kernels = {}
     for stage, v in stage_ms.items():
         tot = float(np.sum(v))

@@ -1,5 +1,5 @@
-// Kernel 6 — PoS Plus CCN rows by a hop-limited SpMM chain (used for the `union` strategy, whose
-// selected rows are ALL hop-1 nodes: ~20 rows per PubMed link).
+// Kernel 6 — PoS Plus CCN rows by a hop-limited SpMM chain: the default route of the `union` strategy, whose
+// selected rows are ALL hop-1 nodes (~20 rows per PubMed link).
 //
 // Replaces reference tuned_SIGN.py:210-258 for the extra selected rows (x_k[sel] = S^k[sel] @ subg_x),
 // like kernels 2 + 3 (diffuse.cu + gather_kernel.cuh) do, with a different factorisation. The weight
@@ -7,24 +7,42 @@
 // subgraph node): 41 MFMA for a mean PubMed union record, FP32-issue bound. Here the operators are
 // propagated as whole matrices but only on the rows that can still reach a selected row:
 //      x_k = S x_{k-1}   on rows of hop <= 1 + K - k      (selected rows are hop <= 1)
-// i.e. x_1 on the whole subgraph, x_2 on hops <= K-1, ... x_K on hops <= 1: (m_1 + m_2 + .. ) * F' FMAs,
-// 3.3 MFMA for the same record. One CTA per record walks the F' columns in sub-chunks of CW columns;
-// per sub-chunk the scaled operator y_{k-1} = D^-1/2 x_{k-1} lives in one buffer and y_k in another
-// (the inner loop is a bare sum over the neighbours' rows), and the compact CSR is staged once per CTA.
-// Everything a record needs lives in shared memory (compact CSR + two [n][CW] buffers, CW = 32/16/8 by
-// subgraph size); records too large for that (n > ~2.3 k) keep the work-item path of kernels 2 + 3 —
-// s3_plan counts no CCN items for the records this kernel serves (S3_BATCH_CCN_CHAIN). CW/4 lanes cooperate
-// on a row with one float4 each, 128/CW rows per warp step; sums run in slot order: results do not depend
-// on scheduling.
+// i.e. x_1 on the whole subgraph, x_2 on hops <= K-1, ... x_K on hops <= 1: (m_1 + m_2 + ..) * F' additions,
+// 3.3 M for the same record — and no weights, no s3_diffuse. The bound is shared-memory bandwidth: every
+// induced edge of a level reads one row segment of the previous level's buffer (round 2, second session;
+// round 1's version of this kernel was one 1024-thread CTA per record with K + 2 barriers per 8-32-column
+// sub-chunk, per-CTA compaction of the padded CSR and rows handed to lane groups in node order: 323-455 ms per
+// PubMed step, barrier / divergence bound).
 //
-// Rows 0 and 1 of every record still come from kernels 1 + 3 (bit-identical for every strategy); this
-// kernel writes rows 2.. (the CCN rows, ascending local id) of all K+1 operators.
+// Two kernels:
+//  * chain_prep_kernel, one WARP per record, in place in the record's arena: the padded local CSR (rows own
+//    deg_G slots, holes are -1) becomes  crow int32[n+1] | ccol uint16[m]  and the rows of every hop are
+//    ordered by descending induced degree (counting sort, 32 buckets) into rorder uint16[n] — lane groups of
+//    a warp then work on rows of the same length. Heavy rows (degree >= 31) lead their hop's segment.
+//  * chain_kernel<T>, one CTA per (record, column slab): CSR and order staged once, then per sub-chunk of
+//    CW columns  y_0 = D^-1/2 [X | label]  ->  K levels ping-ponging between two [n][CW] shared buffers.
+//    The LAST level of a sub-chunk writes nothing to shared memory, so it runs in the same barrier interval
+//    as the y_0 fill of the next sub-chunk: K barriers per sub-chunk instead of K + 2. CW/4 lanes cooperate on a
+//    row (one float4 each); heavy rows and all rows of the last level (few rows, long dependent chains) are
+//    taken by a whole warp, edges split over its lane groups and combined by a fixed shuffle tree.
+//    Records are classed by the shared memory they need: CW = 32 wherever it fits (a 128-byte row segment per
+//    quarter warp is bank-conflict free; 64-byte segments conflict 1.5x, 32-byte ones 2.1x on random rows), in
+//    256-thread CTAs (<= 54 KB, 4 per SM), 512 (<= 110 KB, 2 per SM) or 1024 (<= 222 KB); then CW = 16 / 8 / 4
+//    in 1024-thread CTAs. Records beyond that (n > ~4 000) keep the work-item path (s3_plan counts their items).
+//
+// Sums run in a fixed order per record (slot order inside a lane group, fixed shuffle tree for warp-wide rows):
+// results do not depend on scheduling, batch composition or slab count. Rows 0 and 1 of every record still
+// come from kernels 1 + 3 (bit-identical for every strategy); this kernel writes rows 2.. (the CCN rows,
+// ascending local id) of all K+1 operators.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace s3 {
 namespace {
 
-constexpr int kChainThreads = 1024;
+constexpr int kHeavyDeg = 31;  // rows with at least this many neighbours: bucket 0 of the degree sort, one warp each
+constexpr int kPrefetchRows = 6;  // X rows of the next sub-chunk a lane group keeps in registers
 
 struct ChainParams {
     const float* __restrict__ x;
@@ -32,16 +50,22 @@ struct ChainParams {
     int F;  // feature columns; column index F of the chain is the label column (output column 0)
     int32_t* arena;
     const int64_t* __restrict__ off;
-    const int32_t* __restrict__ cnt;
+    int32_t* cnt;
     const int64_t* __restrict__ row_ptr;
     const int32_t* __restrict__ order;  // may be null
-    int sign_k, strategy, flags;
+    int64_t num_records;
+    int sign_k, strategy, flags, policy, cls;
     OutPtrs out;
     int64_t ldo, row_base;
 };
 
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float4 f4_scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 f4_shfl_xor(float4 a, int d) {
+    return make_float4(__shfl_xor_sync(0xffffffffu, a.x, d), __shfl_xor_sync(0xffffffffu, a.y, d),
+                       __shfl_xor_sync(0xffffffffu, a.z, d), __shfl_xor_sync(0xffffffffu, a.w, d));
+}
 
 // store the four chain columns f0..f0+3 of one output row: feature f -> output column f + 1, f == F (label) -> column 0
 __device__ __forceinline__ void store_row(float* orow, int f0, int F, float4 v) {
@@ -54,110 +78,251 @@ __device__ __forceinline__ void store_row(float* orow, int f0, int F, float4 v) 
     }
 }
 
-constexpr int kHeavyDeg = 24;  // rows with more neighbours are processed by a whole warp, edges split over lane groups
+// ------------------------------------------------------------------------------------------------------------
+// prep: one warp per record, in place. rowptr[n+1] -> crow (compact row starts), lcol[D slots] -> ccol uint16[m]
+// (slot order: rows ascending, neighbours ascending), rowlen[n] -> rorder uint16[n] (per hop: descending degree
+// bucket min(deg, 31), node order inside a bucket). cnt[S3_CNT_NSTORE] = -1 marks the record as converted.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kPrepWarps = 8;
 
-__device__ __forceinline__ float4 f4_shfl_xor(float4 a, int d) {
-    return make_float4(__shfl_xor_sync(0xffffffffu, a.x, d), __shfl_xor_sync(0xffffffffu, a.y, d),
-                       __shfl_xor_sync(0xffffffffu, a.z, d), __shfl_xor_sync(0xffffffffu, a.w, d));
+__global__ void __launch_bounds__(kPrepWarps * 32) chain_prep_kernel(ChainParams p) {
+    __shared__ int s_off[kPrepWarps][32];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const int64_t rec = (int64_t)blockIdx.x * kPrepWarps + w;
+    if (rec >= p.num_records) return;
+    int32_t* cnt = p.cnt + rec * S3_NCNT;
+    if (cnt[S3_CNT_STATUS] != S3_REC_OK) return;
+    const int n = cnt[S3_CNT_N], s = cnt[S3_CNT_S], m = cnt[S3_CNT_M];
+    const int n1 = cnt[S3_CNT_HOP0] + cnt[S3_CNT_HOP0 + 1];
+    if (s <= 2 || cnt[S3_CNT_NSTORE] < 0) return;  // no CCN rows / already converted
+    if (!chain_eligible(p.flags, p.strategy, n, m, n1)) return;
+    const int64_t* off = p.off + rec * S3_NOFF;
+    int32_t* rowptr = p.arena + off[S3_OFF_ROWPTR];
+    int32_t* rowlen = p.arena + off[S3_OFF_ROWLEN];
+    int32_t* lcol = p.arena + off[S3_OFF_LCOL];
+    uint16_t* ccol = reinterpret_cast<uint16_t*>(lcol);
+    uint16_t* rorder = reinterpret_cast<uint16_t*>(rowlen);
+
+    // 1. columns: stream the padded slots, keep the non-holes. The compact position of a slot never exceeds its
+    //    padded position and a uint16 is half an int32, so every store lands below the next step's loads.
+    const int Dslots = rowptr[n];
+    int running = 0;
+    int c = lane < Dslots ? lcol[lane] : -1;
+    for (int base = 0; base < Dslots; base += 32) {
+        const int e_next = base + 32 + lane;
+        const int c_next = e_next < Dslots ? lcol[e_next] : -1;  // loaded before this step's stores (higher addresses)
+        const unsigned keep = __ballot_sync(full, c >= 0);
+        if (c >= 0) ccol[running + __popc(keep & lt)] = (uint16_t)c;
+        running += __popc(keep);
+        c = c_next;
+    }
+    __syncwarp();
+    // 2. row starts of the compact CSR: exclusive scan of the induced degrees
+    running = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int j = base + lane;
+        const int d = j < n ? rowlen[j] : 0;
+        int inc = d;
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) {
+            const int t = __shfl_up_sync(full, inc, sft);
+            if (lane >= sft) inc += t;
+        }
+        if (j < n) rowptr[j] = running + inc - d;
+        running += __shfl_sync(full, inc, 31);
+    }
+    if (lane == 0) rowptr[n] = running;
+    __syncwarp();  // crow is read back below by other lanes
+    // 3. per hop: rows in descending degree bucket (counting sort; ranks inside a step from match_any: deterministic)
+    int a = 0;
+    for (int l = 0; l <= S3_MAX_HOPS; ++l) {
+        const int b = a + cnt[S3_CNT_HOP0 + l];
+        if (b > a) {
+            s_off[w][lane] = 0;
+            __syncwarp();
+            for (int j = a + lane; j < b; j += 32) {
+                const int d = rowptr[j + 1] - rowptr[j];
+                atomicAdd(&s_off[w][31 - min(d, 31)], 1);
+            }
+            __syncwarp();
+            const int v = s_off[w][lane];
+            int inc = v;
+#pragma unroll
+            for (int sft = 1; sft < 32; sft <<= 1) {
+                const int t = __shfl_up_sync(full, inc, sft);
+                if (lane >= sft) inc += t;
+            }
+            __syncwarp();
+            s_off[w][lane] = inc - v;
+            __syncwarp();
+            for (int base = a; base < b; base += 32) {
+                const int j = base + lane;
+                const bool valid = j < b;
+                const int bucket = valid ? 31 - min(rowptr[j + 1] - rowptr[j], 31) : 32 + lane;
+                const unsigned same = __match_any_sync(full, bucket);
+                const int rank = __popc(same & lt);
+                const int o = valid ? s_off[w][bucket] : 0;
+                __syncwarp();
+                if (valid && rank == 0) s_off[w][bucket] = o + __popc(same);
+                __syncwarp();
+                if (valid) rorder[a + o + rank] = (uint16_t)j;
+            }
+            __syncwarp();
+        }
+        a = b;
+    }
+    if (lane == 0) cnt[S3_CNT_NSTORE] = -1;
 }
 
-// All K levels for the chain columns [cs, cs + CW) of every sub-chunk. CW/4 lanes cooperate on a row (one float4
-// each), 128/CW rows per warp step; rows with more than kHeavyDeg neighbours (hubs: one of them would hold up the
-// whole level) are taken out of that schedule and processed one per warp, their edges split over the 128/CW lane
-// groups and combined by a fixed shuffle tree. The X rows of the NEXT sub-chunk are fetched into registers before
-// the levels of the current one, so their latency hides behind the shared-memory work.
-// smem: crow/ccol compact CSR, cdis, cnode, cpos, heavy-row list, and two [n][CW] buffers.
-template <int CW>
-__device__ __forceinline__ void chain_columns(const ChainParams& p, int n, int n1, const int* hop_end, const int* crow,
-                                              const int* ccol, const float* cdis, const int* cpos, const int* cnode,
-                                              const int* heavy, int nheavy, float4* bufA, float4* bufB, int64_t orow0) {
-    constexpr int LPR = CW / 4, RPW = 32 / LPR;  // lanes per row, rows per warp step
-    constexpr int MAXR = 8;                      // rows of level 0 a thread may own (n <= MAXR * groups, checked by the caller)
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NWARP = blockDim.x >> 5;
+// ------------------------------------------------------------------------------------------------------------
+// the chain
+// ------------------------------------------------------------------------------------------------------------
+struct ChainRec {
+    int n, n1, m;
+    int64_t orow0;
+    const int32_t* nodes;  // global
+    const int* crow;       // shared from here on
+    const float* cdis;
+    const int* cpos;
+    const uint16_t* rorder;
+    const uint16_t* ccol;
+    const int* hop_end;  // [S3_MAX_HOPS + 2]
+    const int* nheavy;   // [S3_MAX_HOPS + 1] heavy rows leading every hop's segment of rorder
+};
+
+// One level for the chain columns [cs, cs + CW): x_k = D^-1/2 (sum over neighbours of y_{k-1}), y_k = D^-1/2 x_k.
+// `next` is null for the last level (k == K), which only writes the output rows.
+template <int CW, int T>
+__device__ __forceinline__ void chain_level(const ChainParams& p, const ChainRec& r, int k, const float4* __restrict__ prev,
+                                            float4* __restrict__ next, int cs) {
+    constexpr int LPR = CW / 4, RPW = 32 / LPR, G = T / LPR, NWARP = T / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane / LPR, l = lane - sub * LPR;
+    const int g = warp * RPW + sub;
     const int K = p.sign_k, F = p.F;
-    const int G = NWARP * RPW, g = warp * RPW + sub;  // row groups of the CTA
-    const int R0 = hop_end[min(1 + K, S3_MAX_HOPS + 1)];
-    float4 pre[MAXR];
-    auto fetch = [&](int cs) {
-        const int f0 = cs + 4 * l;
-#pragma unroll
-        for (int u = 0; u < MAXR; ++u) {
-            const int j = g + u * G;
-            pre[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j < R0 && f0 < p.ldx && cs <= F) pre[u] = __ldg(reinterpret_cast<const float4*>(p.x + (int64_t)cnode[j] * p.ldx + f0));
+    const int f0 = cs + 4 * l;
+    const int top = min(1 + K - k, S3_MAX_HOPS + 1);
+    const int Rk = r.hop_end[top];
+    const bool last = next == nullptr;
+    float* outk = p.out.p[k];
+
+    auto finish = [&](int j, float4 acc) {
+        const float dj = r.cdis[j];
+        const float4 xv = f4_scale(acc, dj);  // x_k[j]
+        if (!last) next[j * LPR + l] = f4_scale(xv, dj);
+        if (j >= 2 && j < r.n1) {
+            const int pos = r.cpos[j];
+            if (pos >= 0) store_row(outk + (r.orow0 + pos) * p.ldo, f0, F, xv);
         }
     };
-    fetch(0);
-    for (int cs = 0; cs <= F; cs += CW) {
-        const int f0 = cs + 4 * l;
-        __syncthreads();  // the previous sub-chunk is done with the buffers
-        // level 0: y_0 = D^-1/2 [X | label] on the rows x_1 needs (hop <= 1 + K); x itself for the CCN rows
-#pragma unroll
-        for (int u = 0; u < MAXR; ++u) {
-            const int j = g + u * G;
-            if (j < R0) {
-                float4 v = pre[u];
-                const float lab = j < 2 ? 1.0f : 0.0f;  // zero-one label, tuned_SIGN.py:234
-                if (f0 == F) v.x = lab;
-                else if (f0 + 1 == F) v.y = lab;
-                else if (f0 + 2 == F) v.z = lab;
-                else if (f0 + 3 == F) v.w = lab;
-                bufA[j * LPR + l] = f4_scale(v, cdis[j]);
-                if (j >= 2 && j < n1) {
-                    const int pos = cpos[j];
-                    if (pos >= 0) store_row(p.out.p[0] + (orow0 + pos) * p.ldo, f0, F, v);
-                }
-            }
-        }
-        fetch(cs + CW);  // in flight during the K levels below
-        __syncthreads();
-        for (int k = 1; k <= K; ++k) {
-            const float4* prev = (k & 1) ? bufA : bufB;
-            float4* next = (k & 1) ? bufB : bufA;
-            const int Rk = hop_end[min(1 + K - k, S3_MAX_HOPS + 1)];
-            for (int j = g; j < Rk; j += G) {
-                const int e0 = crow[j], e1 = crow[j + 1];
-                if (e1 - e0 > kHeavyDeg) continue;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    if (!last) {
+        // light rows: one lane group per row, rows of a warp step have (nearly) the same length
+        for (int idx = g; idx < Rk; idx += G) {
+            const int j = r.rorder[idx];
+            const int e0 = r.crow[j], e1 = r.crow[j + 1];
+            if (e1 - e0 >= kHeavyDeg) continue;
+            float4 acc = f4_zero();
 #pragma unroll 4
-                for (int e = e0; e < e1; ++e) acc = f4_add(acc, prev[ccol[e] * LPR + l]);
-                const float dj = cdis[j];
-                const float4 xv = f4_scale(acc, dj);  // x_k[j]
-                next[j * LPR + l] = f4_scale(xv, dj);
-                if (j >= 2 && j < n1) {
-                    const int pos = cpos[j];
-                    if (pos >= 0) store_row(p.out.p[k] + (orow0 + pos) * p.ldo, f0, F, xv);
-                }
-            }
-            for (int hi = warp; hi < nheavy; hi += NWARP) {
-                const int j = heavy[hi];
-                if (j >= Rk) break;  // the list ascends
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                const int e1 = crow[j + 1];
-#pragma unroll 2
-                for (int e = crow[j] + sub; e < e1; e += RPW) acc = f4_add(acc, prev[ccol[e] * LPR + l]);
-#pragma unroll
-                for (int d = LPR; d < 32; d <<= 1) acc = f4_add(acc, f4_shfl_xor(acc, d));
-                if (sub == 0) {
-                    const float dj = cdis[j];
-                    const float4 xv = f4_scale(acc, dj);
-                    next[j * LPR + l] = f4_scale(xv, dj);
-                    if (j >= 2 && j < n1) {
-                        const int pos = cpos[j];
-                        if (pos >= 0) store_row(p.out.p[k] + (orow0 + pos) * p.ldo, f0, F, xv);
-                    }
-                }
-            }
-            __syncthreads();
+            for (int e = e0; e < e1; ++e) acc = f4_add(acc, prev[(int)r.ccol[e] * LPR + l]);
+            finish(j, acc);
         }
+    }
+    // warp-wide rows: the heavy rows of every hop in range — and every row of the last level (hop <= 1: a few
+    // rows whose dependent chains would otherwise leave the SM idle). Edges split over the lane groups.
+    int a = 0;
+    for (int h = 0; h <= min(top, S3_MAX_HOPS); ++h) {
+        const int b = r.hop_end[h];
+        const int cntw = last ? b - a : r.nheavy[h];
+        for (int hi = warp; hi < cntw; hi += NWARP) {
+            const int j = r.rorder[a + hi];
+            if (last && j < 2) continue;  // rows 0 and 1 of the last level are neither read nor written
+            const int e1 = r.crow[j + 1];
+            float4 acc = f4_zero();
+#pragma unroll 2
+            for (int e = r.crow[j] + sub; e < e1; e += RPW) acc = f4_add(acc, prev[(int)r.ccol[e] * LPR + l]);
+#pragma unroll
+            for (int d = LPR; d < 32; d <<= 1) acc = f4_add(acc, f4_shfl_xor(acc, d));
+            if (sub == 0) finish(j, acc);
+        }
+        a = b;
     }
 }
 
-__global__ void __launch_bounds__(kChainThreads, 1) ccn_chain_kernel(ChainParams p) {
+// All sub-chunks [c0, c1) of a record's column slab.
+template <int CW, int T>
+__device__ __forceinline__ void chain_columns(const ChainParams& p, const ChainRec& r, float4* buf0, float4* buf1, int c0, int c1) {
+    constexpr int LPR = CW / 4, RPW = 32 / LPR, G = T / LPR;
+    constexpr int MAXR = kPrefetchRows;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / LPR, l = lane - sub * LPR;
+    const int g = warp * RPW + sub;
+    const int K = p.sign_k, F = p.F;
+    const int R0 = r.hop_end[min(1 + K, S3_MAX_HOPS + 1)];
+    auto buf = [&](int i) -> float4* { return (i & 1) ? buf1 : buf0; };  // no indexed local array (stack)
+
+    auto load_x = [&](int j, int cs) -> float4 {  // columns cs + 4l .. of [X | label] of local node j; the label is patched in
+        const int f0 = cs + 4 * l;
+        float4 v = f4_zero();
+        if (f0 < p.ldx) v = __ldg(reinterpret_cast<const float4*>(p.x + (int64_t)r.nodes[j] * p.ldx + f0));
+        return v;
+    };
+    auto put_y0 = [&](int j, float4 v, float4* dst, int cs) {
+        const int f0 = cs + 4 * l;
+        const float lab = j < 2 ? 1.0f : 0.0f;  // zero-one label, tuned_SIGN.py:234
+        if (f0 == F) v.x = lab;
+        else if (f0 + 1 == F) v.y = lab;
+        else if (f0 + 2 == F) v.z = lab;
+        else if (f0 + 3 == F) v.w = lab;
+        dst[j * LPR + l] = f4_scale(v, r.cdis[j]);
+        if (j >= 2 && j < r.n1) {  // operator 0 of a CCN row: the row itself
+            const int pos = r.cpos[j];
+            if (pos >= 0) store_row(p.out.p[0] + (r.orow0 + pos) * p.ldo, f0, F, v);
+        }
+    };
+
+    float4 pre[MAXR];
+    auto fetch = [&](int cs) {
+#pragma unroll
+        for (int u = 0; u < MAXR; ++u) {
+            const int j = g + u * G;
+            pre[u] = j < R0 ? load_x(j, cs) : f4_zero();
+        }
+    };
+    if (c0 >= c1) return;
+    fetch(c0 * CW);
+    int w = 0;  // buffer that receives y_0 of the current sub-chunk
+    for (int ci = c0; ci <= c1; ++ci) {
+        const int cs = ci * CW;
+        if (ci < c1) {
+            // y_0 of this sub-chunk (the buffer was last read two barriers ago)
+#pragma unroll
+            for (int u = 0; u < MAXR; ++u) {
+                const int j = g + u * G;
+                if (j < R0) put_y0(j, pre[u], buf(w), cs);
+            }
+            for (int j = g + MAXR * G; j < R0; j += G) put_y0(j, load_x(j, cs), buf(w), cs);
+            if (ci + 1 < c1) fetch(cs + CW);  // in flight during the levels below
+        }
+        // last level of the previous sub-chunk: reads the other buffer, writes global memory only
+        if (ci > c0) chain_level<CW, T>(p, r, K, buf(w ^ 1), nullptr, cs - CW);
+        if (ci == c1) break;
+        __syncthreads();
+        for (int k = 1; k < K; ++k) {
+            chain_level<CW, T>(p, r, k, buf(w ^ ((k - 1) & 1)), buf(w ^ (k & 1)), cs);
+            __syncthreads();
+        }
+        w ^= (K & 1);
+    }
+}
+
+template <int T>
+__global__ void __launch_bounds__(T, 1024 / T) chain_kernel(ChainParams p) {
     extern __shared__ __align__(16) int s_dyn[];
-    __shared__ int s_scan[33];
     __shared__ int s_hop_end[S3_MAX_HOPS + 2];
+    __shared__ int s_nheavy[S3_MAX_HOPS + 1];
     const int tid = threadIdx.x;
     const int32_t rec = p.order ? p.order[blockIdx.x] : (int32_t)blockIdx.x;
     if (rec < 0) return;
@@ -168,85 +333,92 @@ __global__ void __launch_bounds__(kChainThreads, 1) ccn_chain_kernel(ChainParams
     if (s <= 2) return;  // no CCN rows
     // records that do not fit the shared-memory placement keep the work-item path (s3_plan counted their items)
     if (!chain_eligible(p.flags, p.strategy, n, m, n1)) return;
+    const int shape = chain_shape(n, m, n1, p.policy);
+    if ((shape >> 8) != p.cls) return;  // served by the launch of another CTA size
+    const int cw = shape & 255;
+    // column slab of this CTA
+    const int nchunks = p.F / cw + 1;  // chain columns 0..F
+    const int per = (nchunks + (int)gridDim.y - 1) / (int)gridDim.y;
+    const int c0 = (int)blockIdx.y * per, c1 = min(nchunks, c0 + per);
+    if (c0 >= c1) return;
+
     const int64_t* off = p.off + (int64_t)rec * S3_NOFF;
-    const int32_t* nodes = p.arena + off[S3_OFF_NODES];
-    const int32_t* rowptr = p.arena + off[S3_OFF_ROWPTR];  // padded
-    const int32_t* rowlen = p.arena + off[S3_OFF_ROWLEN];
-    const int32_t* lcol = p.arena + off[S3_OFF_LCOL];      // padded, -1 holes
+    const int32_t* g_crow = p.arena + off[S3_OFF_ROWPTR];                                      // compact (chain_prep_kernel)
+    const uint32_t* g_rorder = reinterpret_cast<const uint32_t*>(p.arena + off[S3_OFF_ROWLEN]);  // uint16[n]
+    const uint32_t* g_ccol = reinterpret_cast<const uint32_t*>(p.arena + off[S3_OFF_LCOL]);      // uint16[m]
     const int32_t* sel = p.arena + off[S3_OFF_SEL];
+
+    // shared memory: [buf0 n*CW | buf1 n*CW | crow n+1 | cdis n | cpos n1 | rorder (n+1)/2 words | ccol (m+1)/2 words]
+    float4* buf0 = reinterpret_cast<float4*>(s_dyn);
+    float4* buf1 = buf0 + (int64_t)n * (cw / 4);
+    int* crow = reinterpret_cast<int*>(buf1 + (int64_t)n * (cw / 4));
+    float* cdis = reinterpret_cast<float*>(crow + n + 1);
+    int* cpos = reinterpret_cast<int*>(cdis + n);
+    uint32_t* rorder32 = reinterpret_cast<uint32_t*>(cpos + n1);
+    uint32_t* ccol32 = rorder32 + (n + 1) / 2;
+
     if (tid == 0) {
         int acc = 0;
         for (int l = 0; l <= S3_MAX_HOPS; ++l) {
             acc += cnt[S3_CNT_HOP0 + l];
             s_hop_end[l] = acc;
+            s_nheavy[l] = 0;
         }
         s_hop_end[S3_MAX_HOPS + 1] = acc;
     }
-    const int64_t orow0 = p.row_base + p.row_ptr[rec];
-
-    // shared memory: [bufA n*CW | bufB n*CW | cdis n | cnode n | cpos n1 | crow n+1 | ccol m | heavy rows m/24]
-    const int64_t S = kChainSmemBytes / 4;
-    const int64_t fixed = chain_fixed_words(n, m, n1);
-    const int cw = fixed + 2 * (int64_t)n * 32 <= S ? 32 : (fixed + 2 * (int64_t)n * 16 <= S ? 16 : 8);
-    float4* bufA = reinterpret_cast<float4*>(s_dyn);
-    float4* bufB = bufA + (int64_t)n * (cw / 4);
-    float* cdis = reinterpret_cast<float*>(bufB + (int64_t)n * (cw / 4));
-    int* cnode = reinterpret_cast<int*>(cdis + n);
-    int* cpos = cnode + n;
-    int* crow = cpos + n1;
-    int* ccol = crow + n + 1;
-    int* heavy = ccol + m;  // rows with more than kHeavyDeg neighbours, ascending (at most m / kHeavyDeg of them)
-    __shared__ int s_nheavy;
-
-    for (int j = tid; j < n; j += kChainThreads) {
-        const int d = rowlen[j];
+    for (int j = tid; j <= n; j += T) crow[j] = g_crow[j];
+    for (int j = tid; j < n1; j += T) cpos[j] = -1;
+    for (int i = tid; i < (n + 1) / 2; i += T) rorder32[i] = g_rorder[i];
+    for (int i = tid; i < (m + 1) / 2; i += T) ccol32[i] = g_ccol[i];
+    __syncthreads();
+    for (int j = tid; j < n; j += T) {
+        const int d = crow[j + 1] - crow[j];
         cdis[j] = d > 0 ? 1.0f / sqrtf((float)d) : 0.0f;  // tuned_SIGN.py:212-216, inf -> 0
-        cnode[j] = nodes[j];
-    }
-    for (int j = tid; j < n1; j += kChainThreads) cpos[j] = -1;
-    __syncthreads();
-    for (int q = tid; q < s - 2; q += kChainThreads) cpos[sel[q]] = 2 + q;  // output row of every CCN node
-    {
-        // compact CSR: row starts = scan of the induced degrees; columns = the non-hole slots in slot order
-        int running = 0;
-        for (int base = 0; base < n; base += kChainThreads) {
-            const int j = base + tid;
-            const int d = j < n ? rowlen[j] : 0;
-            int tile_total;
-            const int ex = block_exclusive_scan(d, s_scan, &tile_total);
-            if (j < n) crow[j] = running + ex;
-            running += tile_total;
-            __syncthreads();
-        }
-        if (tid == 0) crow[n] = running;
-        running = 0;
-        for (int base = 0; base < n; base += kChainThreads) {
-            const int j = base + tid;
-            const bool hv = j < n && rowlen[j] > kHeavyDeg;
-            int tile_total;
-            const int ex = block_exclusive_scan(hv ? 1 : 0, s_scan, &tile_total);
-            if (hv) heavy[running + ex] = j;
-            running += tile_total;
-            __syncthreads();
-        }
-        if (tid == 0) s_nheavy = running;
-        const int Dslots = rowptr[n];
-        running = 0;
-        for (int base = 0; base < Dslots; base += kChainThreads) {
-            const int e = base + tid;
-            const int col = e < Dslots ? lcol[e] : -1;
-            int tile_total;
-            const int ex = block_exclusive_scan(col >= 0 ? 1 : 0, s_scan, &tile_total);
-            if (col >= 0) ccol[running + ex] = col;
-            running += tile_total;
-            __syncthreads();
+        if (d >= kHeavyDeg) {
+            int h = 0;
+            while (j >= s_hop_end[h]) ++h;
+            atomicAdd(&s_nheavy[h], 1);
         }
     }
+    for (int q = tid; q < s - 2; q += T) cpos[sel[q]] = 2 + q;  // output row of every CCN node
     __syncthreads();
 
-    if (cw == 32) chain_columns<32>(p, n, n1, s_hop_end, crow, ccol, cdis, cpos, cnode, heavy, s_nheavy, bufA, bufB, orow0);
-    else if (cw == 16) chain_columns<16>(p, n, n1, s_hop_end, crow, ccol, cdis, cpos, cnode, heavy, s_nheavy, bufA, bufB, orow0);
-    else chain_columns<8>(p, n, n1, s_hop_end, crow, ccol, cdis, cpos, cnode, heavy, s_nheavy, bufA, bufB, orow0);
+    ChainRec r;
+    r.n = n;
+    r.n1 = n1;
+    r.m = m;
+    r.orow0 = p.row_base + p.row_ptr[rec];
+    r.nodes = p.arena + off[S3_OFF_NODES];
+    r.crow = crow;
+    r.cdis = cdis;
+    r.cpos = cpos;
+    r.rorder = reinterpret_cast<const uint16_t*>(rorder32);
+    r.ccol = reinterpret_cast<const uint16_t*>(ccol32);
+    r.hop_end = s_hop_end;
+    r.nheavy = s_nheavy;
+    if (cw == 32) chain_columns<32, T>(p, r, buf0, buf1, c0, c1);
+    else if (cw == 16) chain_columns<16, T>(p, r, buf0, buf1, c0, c1);
+    else if (cw == 8) chain_columns<8, T>(p, r, buf0, buf1, c0, c1);
+    else chain_columns<4, T>(p, r, buf0, buf1, c0, c1);
+}
+
+int env_int(const char* name, int dflt, int lo, int hi) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    const int x = atoi(v);
+    return x < lo ? lo : (x > hi ? hi : x);
+}
+
+template <int T>
+cudaError_t launch_class(const ChainParams& p, int cls, int slabs, cudaStream_t st) {
+    static LaunchCache cache;  // the shared-memory opt-in is per device
+    const size_t smem = (size_t)chain_class_bytes(cls);
+    cudaError_t e = cache.get(reinterpret_cast<const void*>(chain_kernel<T>), T, smem, nullptr, nullptr);
+    if (e != cudaSuccess) return e;
+    ChainParams q = p;
+    q.cls = cls;
+    chain_kernel<T><<<dim3((unsigned)p.num_records, (unsigned)slabs), T, smem, st>>>(q);
+    return cudaGetLastError();
 }
 
 }  // namespace
@@ -256,9 +428,6 @@ cudaError_t launch_ccn_chain(const s3_graph& g, const s3_batch& b, int64_t num_r
     if (num_records == 0) return cudaSuccess;
     if (!b.row_ptr || b.flow != S3_FLOW_POS || b.strategy != S3_STRATEGY_UNION || !(b.flags & S3_BATCH_CCN_CHAIN))
         return cudaErrorInvalidValue;
-    static LaunchCache cache;  // the shared-memory opt-in is per device
-    cudaError_t e = cache.get(reinterpret_cast<const void*>(ccn_chain_kernel), kChainThreads, kChainSmemBytes, nullptr, nullptr);
-    if (e != cudaSuccess) return e;
     ChainParams p;
     p.x = g.x;
     p.ldx = g.ldx;
@@ -268,14 +437,26 @@ cudaError_t launch_ccn_chain(const s3_graph& g, const s3_batch& b, int64_t num_r
     p.cnt = b.cnt;
     p.row_ptr = b.row_ptr;
     p.order = b.order;
+    p.num_records = num_records;
     p.sign_k = b.sign_k;
     p.strategy = b.strategy;
     p.flags = b.flags;
+    // tuning knobs (A/B runs): which (CW, CTA size) a record gets, and how many CTAs share a record's columns
+    p.policy = env_int("S3GRL_CHAIN_POLICY", 0, 0, 2);
+    p.cls = 0;
     p.out = out;
     p.ldo = ldo;
     p.row_base = row_base;
-    ccn_chain_kernel<<<(unsigned)num_records, kChainThreads, kChainSmemBytes, st>>>(p);
-    return cudaGetLastError();
+    const int slabs = env_int("S3GRL_CHAIN_SLABS", 1, 1, 16);
+    chain_prep_kernel<<<(unsigned)((num_records + kPrepWarps - 1) / kPrepWarps), kPrepWarps * 32, 0, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    // largest CTAs first: their records are the long ones
+    e = launch_class<1024>(p, 2, slabs, st);
+    if (e != cudaSuccess) return e;
+    e = launch_class<512>(p, 1, slabs, st);
+    if (e != cudaSuccess) return e;
+    return launch_class<256>(p, 0, slabs, st);
 }
 
 }  // namespace s3

@@ -67,13 +67,36 @@ __host__ __device__ inline int64_t ccn_item_words(int K, int64_t n, int cr) {
     return (nwp + n * nwp + 2 * n * cr + 3) & ~int64_t(3);
 }
 
-// s3_ccn_chain (ccn_chain.cu): a record is served by the chain when its compact CSR and two CW >= 8 operator
-// buffers fit the kernel's shared memory: [dis n | node n | pos n1 | row starts n+1 | cols m | heavy rows | 2 * n * CW]
-constexpr int kChainSmemBytes = 216 * 1024;
-__host__ __device__ inline int64_t chain_fixed_words(int64_t n, int64_t m, int64_t n1) { return 3 * n + n1 + 4 + m + m / 24; }
+// s3_ccn_chain (ccn_chain.cu): a record is served by the chain when its compact CSR (uint16 columns) and two
+// [n][CW] operator buffers fit a CTA's shared memory with CW >= 4:
+//   [2 * n * CW | row starts n+1 | dis n | pos n1 | row order n/2 | cols m/2]   words
+// CTA sizes ("classes"): 256 threads / 54 KB (4 per SM), 512 / 110 KB (2 per SM), 1024 / 222 KB.
+__host__ __device__ inline int64_t chain_words(int64_t n, int64_t m, int64_t n1, int cw) {
+    return 2 * n * cw + (n + 1) + n + n1 + (n + 2) / 2 + (m + 2) / 2 + 8;
+}
+__host__ __device__ inline int chain_class_bytes(int cls) { return cls == 0 ? 54 * 1024 : (cls == 1 ? 110 * 1024 : 222 * 1024); }
+__host__ __device__ inline bool chain_fits(int64_t n, int64_t m, int64_t n1, int cw, int cls) {
+    return 4 * chain_words(n, m, n1, cw) <= chain_class_bytes(cls);
+}
 __host__ __device__ inline bool chain_eligible(int flags, int strategy, int64_t n, int64_t m, int64_t n1) {
-    return (flags & S3_BATCH_CCN_CHAIN) && strategy == S3_STRATEGY_UNION &&
-           chain_fixed_words(n, m, n1) + 2 * n * 8 <= kChainSmemBytes / 4;
+    return (flags & S3_BATCH_CCN_CHAIN) && strategy == S3_STRATEGY_UNION && n < 65536 && chain_fits(n, m, n1, 4, 2);
+}
+// (CW, class) of an eligible record as CW | class << 8. policy 0: the widest sub-chunk first (128-byte row segments
+// are free of bank conflicts), in the smallest CTA that holds it; 1: two CTAs per SM at CW = 16 before one at CW = 32;
+// 2: occupancy first.
+__host__ __device__ inline int chain_shape(int64_t n, int64_t m, int64_t n1, int policy) {
+#define S3_CHAIN_TRY(cw, cls) \
+    if (chain_fits(n, m, n1, cw, cls)) return (cw) | ((cls) << 8)
+    S3_CHAIN_TRY(32, 0);
+    if (policy == 2) S3_CHAIN_TRY(16, 0);
+    S3_CHAIN_TRY(32, 1);
+    if (policy != 0) S3_CHAIN_TRY(16, 1);
+    if (policy == 2) S3_CHAIN_TRY(8, 1);
+    if (policy != 1) S3_CHAIN_TRY(32, 2);
+    S3_CHAIN_TRY(16, 2);
+    S3_CHAIN_TRY(8, 2);
+#undef S3_CHAIN_TRY
+    return 4 | (2 << 8);
 }
 
 // ---- deterministic per-hop cap (s3_batch.ratio_per_hop / max_nodes_per_hop / cap_seed; reference utils.py:66-70) ----

@@ -47,7 +47,7 @@ struct ExtractParams {
     const int64_t* __restrict__ link_src;
     const int64_t* __restrict__ link_dst;
     int64_t num_records;
-    int flow, strategy, radius, sign_k, store_all;
+    int flow, strategy, radius, sign_k, store_all, flags;
     int W;  // bitmap words
     int32_t* arena;
     int64_t arena_words;
@@ -489,7 +489,10 @@ __global__ void __launch_bounds__(kExtractThreads, S3_FRONT_BLOCKS) front_kernel
             }
 
             // ---------------- allocation 2: float scratch of the record's work items ----------------
-            const int64_t words3 = (item_words(p.flow, K, n) + (int64_t)ccn_items(s, nseed, ccn_rows(p.strategy)) * ccn_item_words(K, n, ccn_rows(p.strategy)) + 31) & ~int64_t(31);
+            // records whose CCN rows go through s3_ccn_chain need no work-item scratch for them (s3_plan counts none)
+            const bool chained = chain_eligible(p.flags, p.strategy, n, s_m, s_hop_end[1]);
+            const int64_t items3 = chained ? 0 : ccn_items(s, nseed, ccn_rows(p.strategy));
+            const int64_t words3 = (item_words(p.flow, K, n) + items3 * ccn_item_words(K, n, ccn_rows(p.strategy)) + 31) & ~int64_t(31);
             if (tid == 0) s_base = (long long)atomicAdd(&p.counters[S3_CTR_CURSOR], (unsigned long long)words3);
             __syncthreads();
             base3 = p.slab_words + s_base;
@@ -814,6 +817,7 @@ cudaError_t launch_extract_bitmap(const s3_graph& g, const s3_batch& b, cudaStre
     p.radius = b.flow == S3_FLOW_POS ? b.num_hops : b.sign_k;
     p.sign_k = b.sign_k;
     p.store_all = (p.strategy != S3_STRATEGY_NONE) || (b.flags & S3_BATCH_STORE_ALL_ROWS);
+    p.flags = b.flags;
     p.W = (int)((g.num_nodes + 31) / 32);
     p.arena = b.arena;
     p.arena_words = b.arena_words;

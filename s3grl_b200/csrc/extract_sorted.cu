@@ -37,7 +37,7 @@ struct SortedParams {
     const int64_t* __restrict__ link_src;
     const int64_t* __restrict__ link_dst;
     int64_t num_records;
-    int sign_k, store_all;
+    int sign_k, store_all, flags;
     int strategy;  // PoS Plus row selection (S3_STRATEGY_*): needs store_all
     // ScaLed: node lists come from per-node random-walk sets instead of the adjacency lists
     const int32_t* __restrict__ walk_sets;    // [num_sets, walk_cap] ascending unique, or null
@@ -95,7 +95,7 @@ __device__ __forceinline__ int lookup(const int32_t* nodes, int n, int u, int v,
 // follow item 0 contiguously: diffuse.cu / gather_kernel.cuh address them from OFF_F32). Returns false on overflow.
 __device__ __forceinline__ bool select_and_allocate(const SortedParams& p, const int32_t* nodes, int n, const int32_t* __restrict__ A,
                                                     int du, const int32_t* __restrict__ B, int dv, int* s_scan, long long* s_base,
-                                                    int& s_out, int64_t& base_sel, int64_t& base3) {
+                                                    int& s_out, int64_t& base_sel, int64_t& base3, int m) {
     const int T = kExtractThreads, tid = threadIdx.x, K = p.sign_k;
     int extra = 0;
     if (p.strategy == S3_STRATEGY_UNION) {
@@ -112,7 +112,9 @@ __device__ __forceinline__ bool select_and_allocate(const SortedParams& p, const
     }
     const int s = 2 + extra, cr = ccn_rows(p.strategy);
     const int64_t wsel = ((int64_t)extra + 31) & ~int64_t(31);
-    const int64_t wf = (item_words(S3_FLOW_POS, K, n) + (int64_t)ccn_items(s, 2, cr) * ccn_item_words(K, n, cr) + 31) & ~int64_t(31);
+    // records whose CCN rows go through s3_ccn_chain need no work-item scratch for them (one hop: every node is hop <= 1)
+    const int64_t items = chain_eligible(p.flags, p.strategy, n, m, n) ? 0 : ccn_items(s, 2, cr);
+    const int64_t wf = (item_words(S3_FLOW_POS, K, n) + items * ccn_item_words(K, n, cr) + 31) & ~int64_t(31);
     __syncthreads();
     if (tid == 0) *s_base = (long long)atomicAdd(&p.counters[S3_CTR_CURSOR], (unsigned long long)(wsel + wf));
     __syncthreads();
@@ -305,7 +307,7 @@ __device__ __forceinline__ bool bitmatrix_record(const SortedParams& p, const Bi
     }
 
     // ---- selected rows (PoS Plus) and the float scratch of the work items ----
-    if (!select_and_allocate(p, nodes, n, cx.A, cx.du, cx.B, cx.dv, cx.s_scan, cx.s_base, s_out, base_sel, base3)) return true;
+    if (!select_and_allocate(p, nodes, n, cx.A, cx.du, cx.B, cx.dv, cx.s_scan, cx.s_base, s_out, base_sel, base3, m_out)) return true;
 
     // ---- diffusion of the target rows over the bit rows ----
     float* item_f = reinterpret_cast<float*>(p.arena + base3);
@@ -639,7 +641,7 @@ __global__ void __launch_bounds__(kExtractThreads, 4) front_sorted_kernel(Sorted
                 }
                 __syncthreads();
                 // ---- selected rows (PoS Plus) and the float scratch of the work items ----
-                overflow = !select_and_allocate(p, nodes, n, A, du, B, dv, s_scan, &s_base, s_sel, base_sel, base3);
+                overflow = !select_and_allocate(p, nodes, n, A, du, B, dv, s_scan, &s_base, s_sel, base_sel, base3, m);
               if (!overflow) {
                 // ---- diffusion of the target rows: K sweeps over every row (num_hops = 1 <= K) ----
                 float* item_f = reinterpret_cast<float*>(p.arena + base3);
@@ -784,6 +786,7 @@ cudaError_t launch_extract_sorted(const s3_graph& g, const s3_batch& b, cudaStre
     p.sign_k = b.sign_k;
     p.strategy = b.flow == S3_FLOW_POS ? b.strategy : S3_STRATEGY_NONE;
     p.store_all = ((b.flags & S3_BATCH_STORE_ALL_ROWS) || p.strategy != S3_STRATEGY_NONE) ? 1 : 0;  // CCN items sweep the CSR
+    p.flags = b.flags;
     p.walk_sets = b.walk_sets;
     p.walk_counts = b.walk_counts;
     p.src_set = b.link_src_set;

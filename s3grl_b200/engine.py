@@ -312,11 +312,15 @@ class _Call:
         self.rpl = 2 if self.flow == L.FLOW_SOP else 1          # records per link
         self.nseed = 1 if self.flow == L.FLOW_SOP else 2        # output rows per record (fixed-row flows)
         self.fixed_rows = self.strategy == L.STRATEGY_NONE
-        # CCN rows of `union`: work items by default; ccn_mode='chain' sends the records that fit shared memory
-        # through the hop-limited SpMM chain (s3_ccn_chain) — fewer FMAs but, measured on PubMed, not faster
-        self.ccn_chain = self.strategy == L.STRATEGY_UNION and self.ccn_mode == 'chain'
+        # CCN rows of `union`: the hop-limited SpMM chain (s3_ccn_chain) for every record that fits its shared-memory
+        # placement (n up to ~4 000) and CCN work items (s3_diffuse + s3_gather_ccn) for the rest; ccn_mode='items'
+        # sends everything through the work items (round 1's default, ~4x slower on PubMed).  The chain converts the
+        # stored CSR in place, so a parity dump (return_graphs) keeps the work items.
         if self.ccn_mode == 'chain' and self.strategy != L.STRATEGY_UNION:
             raise NotImplementedError("ccn_mode='chain' serves the union strategy only")
+        if self.ccn_mode == 'chain' and return_graphs:
+            raise NotImplementedError("ccn_mode='chain' rewrites the stored CSR in place: not with return_graphs")
+        self.ccn_chain = self.strategy == L.STRATEGY_UNION and (self.ccn_mode == 'chain' or (self.ccn_mode is None and not return_graphs))
         self.return_graphs, self.profile = bool(return_graphs), profile
         self.stream = stream if stream is not None else torch.cuda.current_stream(self.dev)
         self.stream_ptr = C.c_void_p(self.stream.cuda_stream)
@@ -328,7 +332,8 @@ class _Call:
             # sync, so intersection (small scratch) takes everything in as few batches as memory allows;
             # union multiplies the float scratch by the CCN work items and stays small.
             free = _free_bytes(self.dev)
-            batch_records = {L.STRATEGY_NONE: 32768, L.STRATEGY_INTERSECTION: 262144, L.STRATEGY_UNION: 8192}[self.strategy]
+            batch_records = {L.STRATEGY_NONE: 32768, L.STRATEGY_INTERSECTION: 262144,
+                             L.STRATEGY_UNION: 32768 if self.ccn_chain else 8192}[self.strategy]
             batch_records = max(1024, min(batch_records, int(free // 3 // (32768 * 4))))
         self.batch_links = max(1, int(batch_records) // self.rpl)
         # batch boundaries (links).  With a pipelined device->host copy the first batches are small (1/8, 1/4, 1/2 of a
@@ -753,7 +758,7 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
     PrecomputeResult with device tensors.
 
     batch_records  records per batch (default: 32768 for fixed-row flows, as many as memory allows for
-                   PoS Plus intersection, 8192 for union).
+                   PoS Plus intersection, 32768 for union (8192 with ccn_mode='items')).
     out            K+1 preallocated [>= 2L, F+1] float32 device tensors (fixed-row flows only).
     profile        a list that receives (stage, batch, start_event, end_event) for every kernel launch,
                    so the caller can time each kernel on its launching stream with CUDA events.
@@ -769,10 +774,11 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
     walk           ScaLed subgraphs (reference utils.py:86-150): dict(m=, M=, seed=) to sample on the GPU,
                    dict(cache={node: tensor}) for a reference-style walk cache, or dict(sets=, counts=) for
                    a table indexed by node id.  The subgraph of (u, v) is {u, v} ∪ set(u) ∪ set(v).
-    ccn_mode       PoS Plus union only: None / 'items' (default) = s3_diffuse + s3_gather_ccn work items of 8 selected
-                   rows; 'chain' = s3_ccn_chain (a hop-limited SpMM chain per record, 10x fewer FMAs) for the records
-                   that fit its shared-memory placement and work items for the rest.  Measured on PubMed the chain
-                   is barrier / latency bound and not faster (profiles/README.md), so it is opt-in.
+    ccn_mode       PoS Plus union only: None / 'chain' (default) = s3_ccn_chain, a hop-limited SpMM chain per record
+                   (12x fewer additions than the weight formulation, shared-memory-bandwidth bound) for the records that
+                   fit its shared-memory placement (n up to ~4 000) and work items for the rest; 'items' = s3_diffuse +
+                   s3_gather_ccn work items of 8 selected rows for every record (round 1's route; also what
+                   return_graphs=True uses, because the chain converts the stored CSR in place).
     pair           (PoS without CCN rows, bitmap tier) link pairing: links over the same unordered node pair — both
                    directions of a training edge, SURVEY.md A.7 — share one record; the other direction's rows are
                    the same rows exchanged, bit for bit (csrc/pair.cu).  On by default; results do not depend on it.
