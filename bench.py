@@ -525,17 +525,20 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if 'hbm_gbs' in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
     rows_written = st['rows'] if not exchange else 2 * st['links']      # rows this rank produced (paired links included)
     names = dict(extract="front_sorted_kernel" if is_rmat else "front_kernel", gather="gather_kernel", diffuse="diffuse_kernel",
-                 gather_ccn="gather_kernel (CCN work items)", ccn_chain="ccn_chain_kernel", sign_full="sign_full_kernel")
+                 gather_ccn="gather_kernel (CCN work items)", ccn_chain="chain_kernel", sign_full="sign_full_kernel",
+                 collate="scatter_rows_kernel")
     # SURVEY 8d terms per kernel, over the records this rank actually extracted
     alg = dict(extract=4 * st['sum_d'] + 8 * st['sum_n'],
                gather=4 * F * st['sum_n'] + 4 * rows_written * (K + 1) * (F + 1),
                sign_full=4 * F * st['sum_n'] + 4 * st['rows'] * (K + 1) * (F + 1),
                # union: the chain reads every subgraph's feature rows once and writes the CCN rows of all K+1 operators
-               ccn_chain=4 * F * st['sum_n'] + 4 * max(0, st['rows'] - 2 * st['records']) * (K + 1) * (F + 1))
+               ccn_chain=4 * F * st['sum_n'] + 4 * max(0, (st.get('rows_computed') or st['rows']) - 2 * st['records']) * (K + 1) * (F + 1),
+               collate=2 * 4 * st['rows'] * (K + 1) * (F + 1))
     bound_note = dict(extract="issue / latency bound integer work on shared-memory bitmaps (ncu: profiles/); its HBM fraction is "
                               "low by nature" if not is_rmat else "latency bound sorted-set intersections over HBM-resident adjacency lists",
                       gather="L2 -> SM bandwidth and FP32 issue when X is L2-resident (PubMed 39 MB), HBM otherwise",
                       sign_full="HBM writes",
+                      collate="HBM copy (placement of the batches' pieces, replication of paired links' rows)",
                       ccn_chain="shared-memory bandwidth: every induced edge of a level reads one row segment of the previous "
                                 "level's [n][CW] buffer (DESIGN.md section 4); X is L2-resident on PubMed")
     kernels = {}
@@ -677,7 +680,9 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
                                + "; PubMed's X (39 MB) is L2-resident WITHIN a step by nature of the workload, the R-MAT X (5 GB) is not",
                             pairing=("on: links over the same unordered node pair share one record (both directions of a "
                                      "training edge); bit-identical to computing each" if fixed and not args.no_pair and not is_rmat
-                                     else "off"),
+                                     else ("on: one record per unordered node pair, the other direction's rows are placed by "
+                                           "s3_scatter_rows (rows 0 / 1 exchanged; CCN rows within fp32 rounding of computing each)"
+                                           if not fixed and not full_flow and not args.no_pair and not is_rmat else "off")),
                             parallelism=par),
                 clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu,
                 timed_region=("one CUDA graph replay per step (captured from the same engine call after the warm-up)" if graph_step is not None

@@ -370,6 +370,19 @@ int s3_gather_peers(const s3_graph* g, const s3_batch* b, int64_t num_records, f
  * seed rows exchanged for the opposite direction: ops[k], k = first_op..num_ops-1, [2 * num_links, ldo] row-major. */
 int s3_fill_mirrors(const int64_t* mirror, int64_t num_links, float* const* ops, int32_t first_op, int32_t num_ops,
                     int64_t num_cols, int64_t ldo, void* stream);
+/* Link pairing for the flows with data-dependent row counts (PoS Plus; reference sgrl_link_pred.py:193-204 precomputes
+ * (u,v) and (v,u), which differ only in the order of rows 0 and 1: the CCN rows of tuned_SIGN.py:228-238 are the same
+ * set in the same ascending local order). The caller runs the path on the chain heads only (mirror[i] >= -1) and
+ * places every link's rows from its head's record.
+ * s3_pair_heads: head_code[i] = 2 * head(i) + swap(i) for every link of the table (swap: opposite direction).
+ * s3_scatter_rows: record r of a piece (rows src_row_ptr[r] .. src_row_ptr[r+1] of src[k], k < num_ops, [*, ld_src])
+ * is copied to rows dst_row_ptr[link] .. of dst[k] for link = link_idx ? link_idx[r] : link_base + r and, with a
+ * table, for every member of that link's chain (rows 0 / 1 exchanged where swap is set). mirror == NULL: a plain
+ * placement of the piece — PyG's collate of reference sgrl_link_pred.py:204 for one batch of records. */
+int s3_pair_heads(const int64_t* mirror, int64_t num_links, int64_t* head_code, void* stream);
+int s3_scatter_rows(float* const* src, int64_t ld_src, const int64_t* src_row_ptr, int64_t num_records,
+                    const int64_t* link_idx, int64_t link_base, const int64_t* mirror, const int64_t* dst_row_ptr,
+                    float* const* dst, int64_t ld_dst, int32_t num_ops, int64_t num_cols, void* stream);
 /* x (operator 0) of the fixed-row flows for a whole link list: out0 [2 * num_links, ldo], row 2i = [1 | X[src_i]],
  * row 2i+1 = [1 | X[dst_i]] (reference tuned_SIGN.py:181 / :119-124); rows of invalid links are left untouched. */
 int s3_fill_x0(const s3_graph* g, const int64_t* link_src, const int64_t* link_dst, int64_t num_links, float* out0, int64_t ldo,

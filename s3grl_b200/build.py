@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, 'csrc')
 BUILD = os.path.join(HERE, '..', 'build')
 LIB_DIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIB_DIR, 'libs3grl_b200.so')
-SOURCES = ['pair.cu', 'peer.cu', 'probe.cu', 'pool.cu', 'extract.cu', 'extract_sorted.cu', 'walks.cu', 'plan.cu', 'diffuse.cu', 'sign_full.cu', 'ccn_chain.cu', 'loader.cu', 'head.cu', 'gather.cu', 'gather_sc1_lo.cu', 'gather_sc1_mid.cu',
+SOURCES = ['pair.cu', 'expand.cu', 'peer.cu', 'probe.cu', 'pool.cu', 'extract.cu', 'extract_sorted.cu', 'walks.cu', 'plan.cu', 'diffuse.cu', 'sign_full.cu', 'ccn_chain.cu', 'loader.cu', 'head.cu', 'gather.cu', 'gather_sc1_lo.cu', 'gather_sc1_mid.cu',
            'gather_sc1_hi.cu', 'gather_sc2_lo.cu', 'gather_sc2_mid.cu', 'gather_sc2_hi.cu', 'gather_sc8_k2.cu', 'gather_sc8_k3.cu',
            'gather_sc8_k4.cu', 'gather_sc8_k5.cu', 'gather_sc8_k6.cu', 'c_abi.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',

@@ -221,6 +221,35 @@ int s3_pair_links(const int64_t* link_src, const int64_t* link_dst, int64_t num_
     return e == cudaSuccess ? S3_OK : cuda_fail(e);
 }
 
+int s3_pair_heads(const int64_t* mirror, int64_t num_links, int64_t* head_code, void* stream) {
+    if (num_links < 0) return S3_ERR_INVALID_ARG;
+    if (num_links == 0) return S3_OK;
+    if (!mirror || !head_code) return S3_ERR_INVALID_ARG;
+    cudaError_t e = s3::launch_pair_heads(mirror, num_links, head_code, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? S3_OK : cuda_fail(e);
+}
+
+int s3_scatter_rows(float* const* src, int64_t ld_src, const int64_t* src_row_ptr, int64_t num_records, const int64_t* link_idx,
+                    int64_t link_base, const int64_t* mirror, const int64_t* dst_row_ptr, float* const* dst, int64_t ld_dst,
+                    int32_t num_ops, int64_t num_cols, void* stream) {
+    if (num_records < 0 || num_ops < 1 || num_ops > 2 * S3_MAX_K || num_cols < 1 || num_cols > INT32_MAX || ld_src < num_cols ||
+        ld_dst < num_cols || link_base < 0 || num_records > INT32_MAX)
+        return S3_ERR_INVALID_ARG;
+    if (num_records == 0) return S3_OK;
+    if (!src || !dst || !src_row_ptr || !dst_row_ptr) return S3_ERR_INVALID_ARG;
+    s3::OutPtrs a, b;
+    memset(&a, 0, sizeof(a));
+    memset(&b, 0, sizeof(b));
+    for (int k = 0; k < num_ops; ++k) {
+        if (!src[k] || !dst[k]) return S3_ERR_INVALID_ARG;
+        a.p[k] = src[k];
+        b.p[k] = dst[k];
+    }
+    cudaError_t e = s3::launch_scatter_rows(a, ld_src, src_row_ptr, num_records, link_idx, link_base, mirror, dst_row_ptr, b, ld_dst,
+                                            num_ops, num_cols, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? S3_OK : cuda_fail(e);
+}
+
 int s3_segment_pool(const float* src, int64_t ld_src, int64_t num_cols, const int64_t* row_ptr, int64_t num_links, int32_t mode,
                     int32_t layout, float* out, int64_t ld_out, void* stream) {
     if (mode != S3_POOL_SUM && mode != S3_POOL_MEAN) return S3_ERR_NOT_IMPLEMENTED;  // reference: "Check pool strat" (models.py:333)

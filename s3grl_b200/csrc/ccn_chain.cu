@@ -183,24 +183,43 @@ struct ChainRec {
     int n, n1, m;
     int64_t orow0;
     const int32_t* nodes;  // global
-    const int* crow;       // shared from here on
-    const float* cdis;
+    const uint2* meta;     // shared from here on: rows in processing order, {first edge, local id | degree << 16}
+    const float* cdis;     // D^-1/2 by local id
     const int* cpos;
-    const uint16_t* rorder;
     const uint16_t* ccol;
     const int* hop_end;  // [S3_MAX_HOPS + 2]
-    const int* nheavy;   // [S3_MAX_HOPS + 1] heavy rows leading every hop's segment of rorder
+    const int* nheavy;   // [S3_MAX_HOPS + 1] heavy rows leading every hop's segment of the processing order
+    const float* dtab;   // [2][32]: 1/sqrt(d) and its square for d < 32
+    int* ctr;            // [2][S3_MAX_K + 1] row hand-out counters of the middle levels
 };
+
+#ifndef S3_CHAIN_GRAB
+#define S3_CHAIN_GRAB 1
+#endif
+constexpr int kGrabSteps = S3_CHAIN_GRAB;  // warp steps a warp takes from the hand-out counter at once (0: static round robin)
+
+// D neighbours of one row, D a compile-time bound shared by the rows of the warp step (they are sorted by degree)
+template <int D, int LPR>
+__device__ __forceinline__ float4 row_sum(const float4* __restrict__ prev, const uint16_t* __restrict__ cc, int d, int l) {
+    int c[D];
+#pragma unroll
+    for (int t = 0; t < D; ++t) c[t] = t < d ? (int)cc[t] : -1;
+    float4 acc = f4_zero();
+#pragma unroll
+    for (int t = 0; t < D; ++t)
+        if (c[t] >= 0) acc = f4_add(acc, prev[c[t] * LPR + l]);
+    return acc;
+}
 
 // One level for the chain columns [cs, cs + CW): x_k = D^-1/2 (sum over neighbours of y_{k-1}), y_k = D^-1/2 x_k.
 // `next` is null for the last level (k == K), which only writes the output rows.
 template <int CW, int T>
 __device__ __forceinline__ void chain_level(const ChainParams& p, const ChainRec& r, int k, const float4* __restrict__ prev,
-                                            float4* __restrict__ next, int cs) {
-    constexpr int LPR = CW / 4, RPW = 32 / LPR, G = T / LPR, NWARP = T / 32;
+                                            float4* __restrict__ next, int cs, int* ctr) {
+    constexpr int LPR = CW / 4, RPW = 32 / LPR, NWARP = T / 32;
+    const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane / LPR, l = lane - sub * LPR;
-    const int g = warp * RPW + sub;
     const int K = p.sign_k, F = p.F;
     const int f0 = cs + 4 * l;
     const int top = min(1 + K - k, S3_MAX_HOPS + 1);
@@ -208,28 +227,6 @@ __device__ __forceinline__ void chain_level(const ChainParams& p, const ChainRec
     const bool last = next == nullptr;
     float* outk = p.out.p[k];
 
-    auto finish = [&](int j, float4 acc) {
-        const float dj = r.cdis[j];
-        const float4 xv = f4_scale(acc, dj);  // x_k[j]
-        if (!last) next[j * LPR + l] = f4_scale(xv, dj);
-        if (j >= 2 && j < r.n1) {
-            const int pos = r.cpos[j];
-            if (pos >= 0) store_row(outk + (r.orow0 + pos) * p.ldo, f0, F, xv);
-        }
-    };
-
-    if (!last) {
-        // light rows: one lane group per row, rows of a warp step have (nearly) the same length
-        for (int idx = g; idx < Rk; idx += G) {
-            const int j = r.rorder[idx];
-            const int e0 = r.crow[j], e1 = r.crow[j + 1];
-            if (e1 - e0 >= kHeavyDeg) continue;
-            float4 acc = f4_zero();
-#pragma unroll 4
-            for (int e = e0; e < e1; ++e) acc = f4_add(acc, prev[(int)r.ccol[e] * LPR + l]);
-            finish(j, acc);
-        }
-    }
     // warp-wide rows: the heavy rows of every hop in range — and every row of the last level (hop <= 1: a few
     // rows whose dependent chains would otherwise leave the SM idle). Edges split over the lane groups.
     int a = 0;
@@ -237,23 +234,82 @@ __device__ __forceinline__ void chain_level(const ChainParams& p, const ChainRec
         const int b = r.hop_end[h];
         const int cntw = last ? b - a : r.nheavy[h];
         for (int hi = warp; hi < cntw; hi += NWARP) {
-            const int j = r.rorder[a + hi];
+            const uint2 mt = r.meta[a + hi];
+            const int j = (int)(mt.y & 0xffffu), d = (int)(mt.y >> 16);
             if (last && j < 2) continue;  // rows 0 and 1 of the last level are neither read nor written
-            const int e1 = r.crow[j + 1];
+            const uint16_t* cc = r.ccol + mt.x;
             float4 acc = f4_zero();
 #pragma unroll 2
-            for (int e = r.crow[j] + sub; e < e1; e += RPW) acc = f4_add(acc, prev[(int)r.ccol[e] * LPR + l]);
+            for (int e = sub; e < d; e += RPW) acc = f4_add(acc, prev[(int)cc[e] * LPR + l]);
 #pragma unroll
-            for (int d = LPR; d < 32; d <<= 1) acc = f4_add(acc, f4_shfl_xor(acc, d));
-            if (sub == 0) finish(j, acc);
+            for (int sft = LPR; sft < 32; sft <<= 1) acc = f4_add(acc, f4_shfl_xor(acc, sft));
+            if (sub == 0) {
+                const float dj = r.cdis[j];
+                const float4 xv = f4_scale(acc, dj);  // x_k[j]
+                if (!last) next[j * LPR + l] = f4_scale(xv, dj);
+                if (j >= 2 && j < r.n1) {
+                    const int pos = r.cpos[j];
+                    if (pos >= 0) store_row(outk + (r.orow0 + pos) * p.ldo, f0, F, xv);
+                }
+            }
         }
         a = b;
+    }
+    if (last) return;
+
+    // light rows: one lane group per row, rows handed out kGrabSteps warp steps at a time from a shared counter
+    // (the processing order is by descending degree inside a hop: the rows of a warp step have the same length,
+    // and the warps that were busy with heavy rows simply take fewer steps)
+    constexpr int kSteps = kGrabSteps > 0 ? kGrabSteps : 1;
+    for (int base = warp * RPW;;) {
+        if (kGrabSteps > 0) {
+            if (lane == 0) base = atomicAdd(ctr, kSteps * RPW);
+            base = __shfl_sync(full, base, 0);
+        }
+        if (base >= Rk) break;
+#pragma unroll 1
+        for (int st = 0; st < kSteps; ++st) {
+            const int idx = base + st * RPW + sub;
+            uint2 mt = make_uint2(0u, 0u);
+            if (idx < Rk) mt = r.meta[idx];
+            const int j = (int)(mt.y & 0xffffu);
+            int d = (int)(mt.y >> 16);
+            const bool act = idx < Rk && d < kHeavyDeg;
+            if (!act) d = 0;
+            const int dmax = __reduce_max_sync(full, d);
+            if (base + st * RPW >= Rk) break;
+            const uint16_t* cc = r.ccol + mt.x;
+            float4 acc;
+            switch (dmax) {
+                case 0: acc = f4_zero(); break;
+                case 1: acc = row_sum<1, LPR>(prev, cc, d, l); break;
+                case 2: acc = row_sum<2, LPR>(prev, cc, d, l); break;
+                case 3: acc = row_sum<3, LPR>(prev, cc, d, l); break;
+                case 4: acc = row_sum<4, LPR>(prev, cc, d, l); break;
+                case 5: acc = row_sum<5, LPR>(prev, cc, d, l); break;
+                case 6: acc = row_sum<6, LPR>(prev, cc, d, l); break;
+                case 7: acc = row_sum<7, LPR>(prev, cc, d, l); break;
+                case 8: acc = row_sum<8, LPR>(prev, cc, d, l); break;
+                default: {
+                    acc = f4_zero();
+                    for (int t0 = 0; t0 < dmax; t0 += 4) acc = f4_add(acc, row_sum<4, LPR>(prev, cc + t0, d - t0, l));
+                }
+            }
+            if (act) {
+                next[j * LPR + l] = f4_scale(acc, r.dtab[32 + d]);  // y_k[j] = x_k[j] / sqrt(d) = acc / d
+                if (j >= 2 && j < r.n1) {
+                    const int pos = r.cpos[j];
+                    if (pos >= 0) store_row(outk + (r.orow0 + pos) * p.ldo, f0, F, f4_scale(acc, r.dtab[d]));
+                }
+            }
+        }
+        if (kGrabSteps == 0) base += NWARP * RPW;
     }
 }
 
 // All sub-chunks [c0, c1) of a record's column slab.
 template <int CW, int T>
-__device__ __forceinline__ void chain_columns(const ChainParams& p, const ChainRec& r, float4* buf0, float4* buf1, int c0, int c1) {
+__device__ __forceinline__ void chain_columns(const ChainParams& p, const ChainRec& r, float4* buf0, int c0, int c1) {
     constexpr int LPR = CW / 4, RPW = 32 / LPR, G = T / LPR;
     constexpr int MAXR = kPrefetchRows;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -261,7 +317,8 @@ __device__ __forceinline__ void chain_columns(const ChainParams& p, const ChainR
     const int g = warp * RPW + sub;
     const int K = p.sign_k, F = p.F;
     const int R0 = r.hop_end[min(1 + K, S3_MAX_HOPS + 1)];
-    auto buf = [&](int i) -> float4* { return (i & 1) ? buf1 : buf0; };  // no indexed local array (stack)
+    const int bstride = r.n * LPR;  // float4 per buffer
+    auto buf = [&](int i) -> float4* { return buf0 + (i & 1) * bstride; };
 
     auto load_x = [&](int j, int cs) -> float4 {  // columns cs + 4l .. of [X | label] of local node j; the label is patched in
         const int f0 = cs + 4 * l;
@@ -271,11 +328,13 @@ __device__ __forceinline__ void chain_columns(const ChainParams& p, const ChainR
     };
     auto put_y0 = [&](int j, float4 v, float4* dst, int cs) {
         const int f0 = cs + 4 * l;
-        const float lab = j < 2 ? 1.0f : 0.0f;  // zero-one label, tuned_SIGN.py:234
-        if (f0 == F) v.x = lab;
-        else if (f0 + 1 == F) v.y = lab;
-        else if (f0 + 2 == F) v.z = lab;
-        else if (f0 + 3 == F) v.w = lab;
+        if (f0 + 3 >= F && f0 <= F) {  // the sub-chunk that holds the label column
+            const float lab = j < 2 ? 1.0f : 0.0f;  // zero-one label, tuned_SIGN.py:234
+            if (f0 == F) v.x = lab;
+            else if (f0 + 1 == F) v.y = lab;
+            else if (f0 + 2 == F) v.z = lab;
+            else v.w = lab;
+        }
         dst[j * LPR + l] = f4_scale(v, r.cdis[j]);
         if (j >= 2 && j < r.n1) {  // operator 0 of a CCN row: the row itself
             const int pos = r.cpos[j];
@@ -296,7 +355,10 @@ __device__ __forceinline__ void chain_columns(const ChainParams& p, const ChainR
     int w = 0;  // buffer that receives y_0 of the current sub-chunk
     for (int ci = c0; ci <= c1; ++ci) {
         const int cs = ci * CW;
+        int* ctr = r.ctr + (ci & 1) * (S3_MAX_K + 1);
         if (ci < c1) {
+            // the hand-out counters of the next sub-chunk's middle levels (last used two sub-chunks ago)
+            if (threadIdx.x < S3_MAX_K + 1) r.ctr[((ci + 1) & 1) * (S3_MAX_K + 1) + threadIdx.x] = 0;
             // y_0 of this sub-chunk (the buffer was last read two barriers ago)
 #pragma unroll
             for (int u = 0; u < MAXR; ++u) {
@@ -307,11 +369,11 @@ __device__ __forceinline__ void chain_columns(const ChainParams& p, const ChainR
             if (ci + 1 < c1) fetch(cs + CW);  // in flight during the levels below
         }
         // last level of the previous sub-chunk: reads the other buffer, writes global memory only
-        if (ci > c0) chain_level<CW, T>(p, r, K, buf(w ^ 1), nullptr, cs - CW);
+        if (ci > c0) chain_level<CW, T>(p, r, K, buf(w ^ 1), nullptr, cs - CW, nullptr);
         if (ci == c1) break;
         __syncthreads();
         for (int k = 1; k < K; ++k) {
-            chain_level<CW, T>(p, r, k, buf(w ^ ((k - 1) & 1)), buf(w ^ (k & 1)), cs);
+            chain_level<CW, T>(p, r, k, buf(w ^ ((k - 1) & 1)), buf(w ^ (k & 1)), cs, ctr + k);
             __syncthreads();
         }
         w ^= (K & 1);
@@ -323,6 +385,8 @@ __global__ void __launch_bounds__(T, 1024 / T) chain_kernel(ChainParams p) {
     extern __shared__ __align__(16) int s_dyn[];
     __shared__ int s_hop_end[S3_MAX_HOPS + 2];
     __shared__ int s_nheavy[S3_MAX_HOPS + 1];
+    __shared__ int s_ctr[2 * (S3_MAX_K + 1)];
+    __shared__ float s_dtab[64];
     const int tid = threadIdx.x;
     const int32_t rec = p.order ? p.order[blockIdx.x] : (int32_t)blockIdx.x;
     if (rec < 0) return;
@@ -343,19 +407,17 @@ __global__ void __launch_bounds__(T, 1024 / T) chain_kernel(ChainParams p) {
     if (c0 >= c1) return;
 
     const int64_t* off = p.off + (int64_t)rec * S3_NOFF;
-    const int32_t* g_crow = p.arena + off[S3_OFF_ROWPTR];                                      // compact (chain_prep_kernel)
-    const uint32_t* g_rorder = reinterpret_cast<const uint32_t*>(p.arena + off[S3_OFF_ROWLEN]);  // uint16[n]
+    const int32_t* g_crow = p.arena + off[S3_OFF_ROWPTR];                                        // compact (chain_prep_kernel)
+    const uint16_t* g_rorder = reinterpret_cast<const uint16_t*>(p.arena + off[S3_OFF_ROWLEN]);  // uint16[n]
     const uint32_t* g_ccol = reinterpret_cast<const uint32_t*>(p.arena + off[S3_OFF_LCOL]);      // uint16[m]
     const int32_t* sel = p.arena + off[S3_OFF_SEL];
 
-    // shared memory: [buf0 n*CW | buf1 n*CW | crow n+1 | cdis n | cpos n1 | rorder (n+1)/2 words | ccol (m+1)/2 words]
+    // shared memory: [buf0 n*CW | buf1 n*CW | meta 2n | cdis n | cpos n1 | ccol (m+1)/2 words]
     float4* buf0 = reinterpret_cast<float4*>(s_dyn);
-    float4* buf1 = buf0 + (int64_t)n * (cw / 4);
-    int* crow = reinterpret_cast<int*>(buf1 + (int64_t)n * (cw / 4));
-    float* cdis = reinterpret_cast<float*>(crow + n + 1);
+    uint2* meta = reinterpret_cast<uint2*>(buf0 + 2 * (int64_t)n * (cw / 4));
+    float* cdis = reinterpret_cast<float*>(meta + n);
     int* cpos = reinterpret_cast<int*>(cdis + n);
-    uint32_t* rorder32 = reinterpret_cast<uint32_t*>(cpos + n1);
-    uint32_t* ccol32 = rorder32 + (n + 1) / 2;
+    uint32_t* ccol32 = reinterpret_cast<uint32_t*>(cpos + n1);
 
     if (tid == 0) {
         int acc = 0;
@@ -366,19 +428,28 @@ __global__ void __launch_bounds__(T, 1024 / T) chain_kernel(ChainParams p) {
         }
         s_hop_end[S3_MAX_HOPS + 1] = acc;
     }
-    for (int j = tid; j <= n; j += T) crow[j] = g_crow[j];
+    if (tid < 2 * (S3_MAX_K + 1)) s_ctr[tid] = 0;
+    if (tid < 32) {
+        const float dis = tid > 0 ? 1.0f / sqrtf((float)tid) : 0.0f;  // tuned_SIGN.py:212-216, inf -> 0
+        s_dtab[tid] = dis;
+        s_dtab[32 + tid] = dis * dis;
+    }
     for (int j = tid; j < n1; j += T) cpos[j] = -1;
-    for (int i = tid; i < (n + 1) / 2; i += T) rorder32[i] = g_rorder[i];
     for (int i = tid; i < (m + 1) / 2; i += T) ccol32[i] = g_ccol[i];
     __syncthreads();
-    for (int j = tid; j < n; j += T) {
-        const int d = crow[j + 1] - crow[j];
-        cdis[j] = d > 0 ? 1.0f / sqrtf((float)d) : 0.0f;  // tuned_SIGN.py:212-216, inf -> 0
+    for (int idx = tid; idx < n; idx += T) {  // rows in processing order
+        const int j = g_rorder[idx];
+        const int e0 = g_crow[j], d = g_crow[j + 1] - e0;
+        meta[idx] = make_uint2((unsigned)e0, (unsigned)j | ((unsigned)d << 16));
         if (d >= kHeavyDeg) {
             int h = 0;
-            while (j >= s_hop_end[h]) ++h;
+            while (idx >= s_hop_end[h]) ++h;  // the order permutes rows inside their hop
             atomicAdd(&s_nheavy[h], 1);
         }
+    }
+    for (int j = tid; j < n; j += T) {
+        const int d = g_crow[j + 1] - g_crow[j];
+        cdis[j] = d > 0 ? 1.0f / sqrtf((float)d) : 0.0f;
     }
     for (int q = tid; q < s - 2; q += T) cpos[sel[q]] = 2 + q;  // output row of every CCN node
     __syncthreads();
@@ -389,17 +460,18 @@ __global__ void __launch_bounds__(T, 1024 / T) chain_kernel(ChainParams p) {
     r.m = m;
     r.orow0 = p.row_base + p.row_ptr[rec];
     r.nodes = p.arena + off[S3_OFF_NODES];
-    r.crow = crow;
+    r.meta = meta;
     r.cdis = cdis;
     r.cpos = cpos;
-    r.rorder = reinterpret_cast<const uint16_t*>(rorder32);
     r.ccol = reinterpret_cast<const uint16_t*>(ccol32);
     r.hop_end = s_hop_end;
     r.nheavy = s_nheavy;
-    if (cw == 32) chain_columns<32, T>(p, r, buf0, buf1, c0, c1);
-    else if (cw == 16) chain_columns<16, T>(p, r, buf0, buf1, c0, c1);
-    else if (cw == 8) chain_columns<8, T>(p, r, buf0, buf1, c0, c1);
-    else chain_columns<4, T>(p, r, buf0, buf1, c0, c1);
+    r.dtab = s_dtab;
+    r.ctr = s_ctr;
+    if (cw == 32) chain_columns<32, T>(p, r, buf0, c0, c1);
+    else if (cw == 16) chain_columns<16, T>(p, r, buf0, c0, c1);
+    else if (cw == 8) chain_columns<8, T>(p, r, buf0, c0, c1);
+    else chain_columns<4, T>(p, r, buf0, c0, c1);
 }
 
 int env_int(const char* name, int dflt, int lo, int hi) {

@@ -69,10 +69,10 @@ __host__ __device__ inline int64_t ccn_item_words(int K, int64_t n, int cr) {
 
 // s3_ccn_chain (ccn_chain.cu): a record is served by the chain when its compact CSR (uint16 columns) and two
 // [n][CW] operator buffers fit a CTA's shared memory with CW >= 4:
-//   [2 * n * CW | row starts n+1 | dis n | pos n1 | row order n/2 | cols m/2]   words
+//   [2 * n * CW | row records 2n | dis n | pos n1 | cols m/2]   words
 // CTA sizes ("classes"): 256 threads / 54 KB (4 per SM), 512 / 110 KB (2 per SM), 1024 / 222 KB.
 __host__ __device__ inline int64_t chain_words(int64_t n, int64_t m, int64_t n1, int cw) {
-    return 2 * n * cw + (n + 1) + n + n1 + (n + 2) / 2 + (m + 2) / 2 + 8;
+    return 2 * n * cw + 2 * n + n + n1 + (m + 2) / 2 + 8;
 }
 __host__ __device__ inline int chain_class_bytes(int cls) { return cls == 0 ? 54 * 1024 : (cls == 1 ? 110 * 1024 : 222 * 1024); }
 __host__ __device__ inline bool chain_fits(int64_t n, int64_t m, int64_t n1, int cw, int cls) {
@@ -212,6 +212,10 @@ cudaError_t launch_fill_x0(const s3_graph& g, const int64_t* src, const int64_t*
                            cudaStream_t st);
 cudaError_t launch_pair_links(const int64_t* src, const int64_t* dst, int64_t L, int64_t N, int64_t* table, int64_t slots,
                               int64_t* mirror, cudaStream_t st);
+cudaError_t launch_pair_heads(const int64_t* mirror, int64_t L, int64_t* head_code, cudaStream_t st);
+cudaError_t launch_scatter_rows(const OutPtrs& src, int64_t ld_src, const int64_t* src_row_ptr, int64_t num_records,
+                                const int64_t* link_idx, int64_t link_base, const int64_t* mirror, const int64_t* dst_row_ptr,
+                                const OutPtrs& dst, int64_t ld_dst, int num_ops, int64_t cols, cudaStream_t st);
 cudaError_t launch_segment_pool(const float* src, int64_t ld, int64_t cols, const int64_t* row_ptr, int64_t num_links, int mode,
                                 int layout, float* out, int64_t ld_out, cudaStream_t st);
 cudaError_t launch_probe_l2_read(const float* buf, int64_t bytes, int iters, float* sink, int ctas, cudaStream_t st);

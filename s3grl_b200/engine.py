@@ -336,23 +336,7 @@ class _Call:
                              L.STRATEGY_UNION: 32768 if self.ccn_chain else 8192}[self.strategy]
             batch_records = max(1024, min(batch_records, int(free // 3 // (32768 * 4))))
         self.batch_links = max(1, int(batch_records) // self.rpl)
-        # batch boundaries (links).  With a pipelined device->host copy the first batches are small (1/8, 1/4, 1/2 of a
-        # batch): the copy engine starts after ~1 ms of compute instead of a whole batch, and PCIe is the bottleneck
-        # of that path.  Results do not depend on the batch composition.
-        starts, pos = [0], 0
-        ramp = [self.batch_links // 8, self.batch_links // 4, self.batch_links // 2] if host_out is not None else []
-        for step in ramp:
-            if step >= 512 and pos + step < self.num_links:
-                pos += step
-                starts.append(pos)
-        rest = self.num_links - pos
-        nb = max(1, int(round(rest / self.batch_links)))     # even batches: no tiny tail batch (164 000 = 5 x 32 800)
-        size = (rest + nb - 1) // nb
-        while pos + size < self.num_links:
-            pos += size
-            starts.append(pos)
-        self.starts = starts + [self.num_links]
-        self.num_batches = len(starts) if self.num_links else 0
+        self.set_batches()
         self.overlap = bool(overlap) and self.fixed_rows and not self.return_graphs and self.num_batches > 1
         self.flags = ((L.BATCH_SHARE_SMS if (self.overlap and peers is not None) else 0)
                       | (L.BATCH_STORE_ALL_ROWS if self.return_graphs else 0)
@@ -382,6 +366,10 @@ class _Call:
         can_pair = (self.flow == L.FLOW_POS and self.fixed_rows and not self.return_graphs and self.walk is None
                     and tier == 0)
         self.pair = bool(pair) and can_pair and mirror is None
+        # PoS Plus: (u,v) and (v,u) share everything but the order of rows 0 and 1 (csrc/expand.cu): the path runs on
+        # one link per unordered node pair and s3_scatter_rows places every link's rows.  Not with a parity dump.
+        self.pair_var = (bool(pair) and self.flow == L.FLOW_POS and not self.fixed_rows and not self.return_graphs
+                         and mirror is None and out_link is None and peers is None)
         if (mirror is not None or out_link is not None or peers is not None) and not self.fixed_rows:
             raise NotImplementedError("out_link / mirror / peers serve the fixed-row flows only")
         if mirror is not None and not can_pair:
@@ -410,6 +398,25 @@ class _Call:
         self.counters = None
 
     # ------------------------------------------------------------------ helpers
+    def set_batches(self):
+        """Batch boundaries (links).  With a pipelined device->host copy the first batches are small (1/8, 1/4, 1/2 of a
+        batch): the copy engine starts after ~1 ms of compute instead of a whole batch, and PCIe is the bottleneck
+        of that path.  Results do not depend on the batch composition."""
+        starts, pos = [0], 0
+        ramp = [self.batch_links // 8, self.batch_links // 4, self.batch_links // 2] if self.host_out is not None else []
+        for step in ramp:
+            if step >= 512 and pos + step < self.num_links:
+                pos += step
+                starts.append(pos)
+        rest = self.num_links - pos
+        nb = max(1, int(round(rest / self.batch_links)))     # even batches: no tiny tail batch (164 000 = 5 x 32 800)
+        size = (rest + nb - 1) // nb
+        while pos + size < self.num_links:
+            pos += size
+            starts.append(pos)
+        self.starts = starts + [self.num_links]
+        self.num_batches = len(starts) if self.num_links else 0
+
     def bounds(self, bi):
         return self.starts[bi], self.starts[bi + 1]
 
@@ -740,13 +747,55 @@ class _Call:
                 result._finalize = lambda: self.finalize_fixed(metas)
                 result.hop_nodes = self.hop_nodes
                 return result if defer else result.finalize()
+            head_idx, head_code, var_mirror = None, None, None
+            if self.pair_var and Lk > 1:
+                # chain table of the whole list; the path then runs on the chain heads only
+                var_mirror, self._pair_table = pair_links(self.links, self.graph.num_nodes, self.stream)
+                is_head = var_mirror >= -1
+                head_idx = torch.nonzero(is_head).flatten()
+                self.stats['launches'] += 2
+                if int(head_idx.numel()) < Lk:
+                    head_code = torch.empty(Lk, dtype=torch.int64, device=dev)
+                    L.check(self.lib.s3_pair_heads(_ptr(var_mirror), Lk, _ptr(head_code), self.stream_ptr), 's3_pair_heads')
+                    self.stats['launches'] += 1
+                    self.stats['mirrors'] = Lk - int(head_idx.numel())
+                    self.links = self.links[:, head_idx].contiguous()
+                    self.num_links = int(head_idx.numel())
+                    self.stats['records'] = self.num_links * self.rpl
+                    self.set_batches()
+                    self.counters = torch.zeros((max(self.num_batches, 1), L.NCTR), dtype=torch.int64, device=dev)
+                else:
+                    head_idx, var_mirror = None, None
             self.run_variable()
-            xs = [torch.cat([p[k] for p in self.pieces], 0) if self.pieces else torch.empty((0, F1), device=dev)
-                  for k in range(K + 1)]
             counts = torch.cat(self.row_counts) if self.row_counts else torch.zeros(0, dtype=torch.int64, device=dev)
+            if head_idx is not None:      # rows of every link of the list = rows of its head's record
+                rank = torch.cumsum(is_head, 0) - 1
+                counts = counts[rank[head_code >> 1]]
             row_ptr = torch.zeros(Lk + 1, dtype=torch.int64, device=dev)
             torch.cumsum(counts, 0, out=row_ptr[1:])
+            self.stats['rows_computed'] = sum(int(p[0].shape[0]) for p in self.pieces)   # without the paired links' copies
+            if not self.pieces:
+                xs = [torch.empty((0, F1), dtype=torch.float32, device=dev) for _ in range(K + 1)]
+            elif len(self.pieces) == 1 and head_idx is None:
+                xs = self.pieces[0]
+            else:
+                # collate: every batch's piece placed (and, with pairing, replicated) by s3_scatter_rows
+                R = int(row_ptr[-1])
+                xs = [torch.empty((R, F1), dtype=torch.float32, device=dev) for _ in range(K + 1)]
+                dst = (C.c_void_p * (K + 1))(*[o.data_ptr() for o in xs])
+                for bi, piece in enumerate(self.pieces):
+                    b0, b1 = self.bounds(bi)
+                    prp = torch.zeros(b1 - b0 + 1, dtype=torch.int64, device=dev)
+                    torch.cumsum(self.row_counts[bi], 0, out=prp[1:])
+                    src = (C.c_void_p * (K + 1))(*[o.data_ptr() for o in piece])
+                    self.launch('collate', bi, 's3_scatter_rows', src, F1, _ptr(prp), b1 - b0,
+                                _ptr(head_idx[b0:b1]) if head_idx is not None else None, b0, _ptr(var_mirror), _ptr(row_ptr),
+                                dst, F1, K + 1, F1, self.stream_ptr)
+                    self.stats['launches'] += 1
+                    self._keep_var = getattr(self, '_keep_var', []) + [prp]
+                self.pieces = []
             self.stats['rows'] = int(xs[0].shape[0])
+            self.stats['links'] = Lk
             return PrecomputeResult(xs, row_ptr, self.stats, self.graphs)
 
 

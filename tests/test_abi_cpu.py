@@ -154,6 +154,15 @@ def test_argument_validation_of_the_round2_entry_points(lib):
     assert lib.s3_peer_alloc(0, ctypes.byref(ctypes.c_void_p())) == L.S3_ERR_INVALID_ARG
     assert lib.s3_peer_export(None, ctypes.create_string_buffer(64)) == L.S3_ERR_INVALID_ARG
     assert lib.s3_peer_free(None) == L.S3_OK and lib.s3_peer_close(None) == L.S3_OK
+    # pairing of the flows with data-dependent row counts (csrc/expand.cu)
+    arr = (ctypes.c_void_p * 4)(16, 16, 16, 16)
+    assert lib.s3_pair_heads(None, 0, None, None) == L.S3_OK and lib.s3_pair_heads(None, 3, P(16), None) == L.S3_ERR_INVALID_ARG
+    assert lib.s3_pair_heads(P(16), -1, P(16), None) == L.S3_ERR_INVALID_ARG
+    assert lib.s3_scatter_rows(arr, 5, P(16), 0, None, 0, None, P(16), arr, 5, 4, 5, None) == L.S3_OK       # nothing to place
+    assert lib.s3_scatter_rows(arr, 4, P(16), 2, None, 0, None, P(16), arr, 5, 4, 5, None) == L.S3_ERR_INVALID_ARG   # ld < cols
+    assert lib.s3_scatter_rows(arr, 5, None, 2, None, 0, None, P(16), arr, 5, 4, 5, None) == L.S3_ERR_INVALID_ARG    # no row_ptr
+    assert lib.s3_scatter_rows(arr, 5, P(16), 2, None, 0, None, P(16), arr, 5, 0, 5, None) == L.S3_ERR_INVALID_ARG   # no operators
+    assert lib.s3_scatter_rows(arr, 5, P(16), 2, None, -1, None, P(16), arr, 5, 4, 5, None) == L.S3_ERR_INVALID_ARG
 
 
 def test_per_hop_cap_counts_match_the_reference_formula():

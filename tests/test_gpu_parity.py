@@ -532,6 +532,82 @@ def test_union_chain_matches_work_item_path(N, E, F, h, K, L):
     print(f"N={N}: max_n={a.stats['max_n']} rows={a.stats['rows']}")
 
 
+@pytest.mark.parametrize('strategy', ['intersection', 'union'])
+def test_pos_plus_pairing_places_both_directions(strategy):
+    """PoS Plus with link pairing (csrc/expand.cu): a list holding (u,v), (v,u) and exact repeats runs the path once per
+    unordered node pair; every link still gets its own rows — rows 0 / 1 exchanged for the opposite direction (bit-exact:
+    they come from kernels 1 + 3), the CCN rows within fp32 rounding of computing the link on its own — and the oracle
+    agrees with all of them. Several batches: the head of a chain and its members sit in different pieces."""
+    rng = np.random.default_rng(91)
+    A = _random_graph(rng, 500, 2200)
+    X = rng.random((500, 37), dtype=np.float32)
+    e = np.stack(A.nonzero(), 1)
+    base = np.concatenate([e[rng.choice(e.shape[0], 25, replace=False)].T, rng.integers(0, 500, (2, 15))], axis=1)
+    base = base[:, base[0] != base[1]]
+    links = np.concatenate([base, base[::-1, :20], base[:, 5:12], rng.integers(0, 500, (2, 6))], axis=1)
+    links = links[:, links[0] != links[1]]
+    links = links[:, rng.permutation(links.shape[1])]
+    g = DeviceGraph(A, X)
+    ref = orc.pos_precompute(links, 2, A, X, 3, strategy)
+    for batch in (None, 7):
+        on = precompute(g, links, 2, 3, 'PoS', strategy, batch_records=batch)
+        off = precompute(g, links, 2, 3, 'PoS', strategy, batch_records=batch, pair=False)
+        assert on.stats['mirrors'] >= 27 and off.stats['mirrors'] == 0
+        assert np.array_equal(on.row_ptr.cpu().numpy(), ref['row_ptr']) and torch.equal(on.row_ptr, off.row_ptr)
+        rp = on.row_ptr[:-1]
+        for k in range(4):
+            assert_features_close(on.xs[k].cpu().numpy(), ref['xs'][k], what=f'{strategy} paired x{k}')
+            assert_features_close(on.xs[k].cpu().numpy(), off.xs[k].cpu().numpy(), tol=2e-6, what=f'{strategy} pair on/off x{k}')
+            assert torch.equal(on.xs[k][rp], off.xs[k][rp]) and torch.equal(on.xs[k][rp + 1], off.xs[k][rp + 1])
+        assert torch.equal(on.xs[0], off.xs[0])
+
+
+def test_scatter_rows_entry_point():
+    """s3_pair_heads / s3_scatter_rows through the raw C ABI against a NumPy restatement of the placement."""
+    import ctypes as C
+    from s3grl_b200 import _lib as L
+    from s3grl_b200.engine import pair_links
+    lib = L.lib()
+    rng = np.random.default_rng(5)
+    u = rng.integers(0, 30, 200)
+    v = (u + 1 + rng.integers(0, 28, 200)) % 30
+    links = torch.from_numpy(np.stack([u, v])).cuda()
+    Lk = links.shape[1]
+    mirror, _table = pair_links(links, 30)
+    code = torch.empty(Lk, dtype=torch.int64, device='cuda')
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    L.check(lib.s3_pair_heads(C.c_void_p(mirror.data_ptr()), Lk, C.c_void_p(code.data_ptr()), st), 's3_pair_heads')
+    code_h, m_h = code.cpu().numpy(), mirror.cpu().numpy()
+    first = {}
+    for i in range(Lk):
+        key = (min(u[i], v[i]), max(u[i], v[i]))
+        first.setdefault(key, i)
+        h = first[key]
+        assert code_h[i] >> 1 == h and (code_h[i] & 1) == int(u[i] != u[h]) and (m_h[i] >= -1) == (h == i)
+    heads = np.array(sorted(set(first.values())))
+    counts = rng.integers(2, 6, heads.size)
+    prp = np.concatenate([[0], np.cumsum(counts)])
+    cols, ops = 11, 3
+    src = [torch.from_numpy(rng.random((int(prp[-1]), cols), dtype=np.float32)).cuda() for _ in range(ops)]
+    rank = {int(h): r for r, h in enumerate(heads)}
+    full_counts = np.array([counts[rank[int(c >> 1)]] for c in code_h])
+    frp = np.concatenate([[0], np.cumsum(full_counts)])
+    dst = [torch.zeros((int(frp[-1]), cols), dtype=torch.float32, device='cuda') for _ in range(ops)]
+    sp = (C.c_void_p * ops)(*[t.data_ptr() for t in src])
+    dp = (C.c_void_p * ops)(*[t.data_ptr() for t in dst])
+    t_prp, t_heads, t_frp = torch.from_numpy(prp).cuda(), torch.from_numpy(heads).cuda(), torch.from_numpy(frp).cuda()
+    L.check(lib.s3_scatter_rows(sp, cols, C.c_void_p(t_prp.data_ptr()), heads.size, C.c_void_p(t_heads.data_ptr()), 0,
+                                C.c_void_p(mirror.data_ptr()), C.c_void_p(t_frp.data_ptr()), dp, cols, ops, cols, st), 's3_scatter_rows')
+    for k in range(ops):
+        got, s_h = dst[k].cpu().numpy(), src[k].cpu().numpy()
+        for i in range(Lk):
+            r = rank[int(code_h[i] >> 1)]
+            rows = s_h[prp[r]:prp[r + 1]].copy()
+            if code_h[i] & 1:
+                rows[[0, 1]] = rows[[1, 0]]
+            assert np.array_equal(got[frp[i]:frp[i + 1]], rows), (k, i)
+
+
 def test_empty_inputs_on_every_entry_point():
     """Edge case: an empty link list (a split without negatives, an empty shard on a rank) goes through every flow."""
     from s3grl_b200 import JointLoader, PrecomputedList, joint_rows, sign_head
