@@ -551,6 +551,19 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
             k['achieved_GBps'] = alg[stage] * ev_steps / (tot / 1e3) / 1e9
             k['frac_of_hbm'] = k['achieved_GBps'] / peak
             k['bound_by'] = bound_note.get(stage)
+        if stage == 'ccn_chain' and tot > 0 and st.get('chain_reads'):
+            # the chain's own roofline: every induced edge of a level reads one row segment of the previous level's
+            # shared-memory buffer; over all sub-chunks that is 4 * (F + 1) bytes per (edge, level)
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            smem_peak = 128.0 * sms * float(clk.get('sm_max_mhz') or 1965.0) * 1e6 / 1e9      # 128 B / clk / SM
+            sm_bytes = st['chain_reads'] * 4 * (F + 1)
+            k['smem_bytes_per_step'] = int(sm_bytes)
+            k['smem_GBps'] = sm_bytes * ev_steps / (tot / 1e3) / 1e9
+            k['smem_peak_GBps'] = smem_peak
+            k['frac_of_smem_peak'] = k['smem_GBps'] / smem_peak
+            k['smem_peak_source'] = "128 B/clk/SM (B300_MICROARCH.md, LDS crossbar) x SMs x max SM clock; conflict-free"
+            k['records_chained'] = st.get('chain_records')
+            k['mean_n_chained'] = st['chain_n'] / max(1, st.get('chain_records') or 1)
         if stage == 'gather' and tot > 0 and ceilings:
             # kernel 3 reads every feature row from L2 once per column pass and issues (K+1-kmin) * SC FMAs per float
             hop = res.hop_nodes() if hasattr(res, 'hop_nodes') else None
@@ -601,7 +614,7 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
                     bytes_per_launch=d.get('algorithmic_bytes_per_step', 0) / max(st['batches'], 1),
                     launches_timed=d.get('launches_timed'), avg_launch_ms=d.get('avg_launch_ms'),
                     share_of_step={k_: v_['share_of_step'] for k_, v_ in kernels.items()},
-                    kernels=kernels,
+                    kernels=kernels, dominant=d,
                     path=dict(achieved=path_bytes * steps / (ms_max / 1e3) / 1e9,
                               frac=path_bytes * steps / (ms_max / 1e3) / 1e9 / (peak * world),
                               bytes_per_link=path_bytes / Lk, peak=peak * world,
@@ -817,7 +830,7 @@ def main():
             sub = measure(args, w, name, 2, 3, dev, rank, world, False, ceilings, None)
             keep = {k_: sub[k_] for k_ in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'ms_per_step', 'scaling', 'gpu_launches')}
             keep['config'] = sub['config']
-            keep['roofline'] = {k_: sub['roofline'][k_] for k_ in ('kernel', 'achieved', 'peak', 'frac', 'share_of_step', 'path', 'path_streamed', 'hub_index')
+            keep['roofline'] = {k_: sub['roofline'][k_] for k_ in ('kernel', 'achieved', 'peak', 'frac', 'share_of_step', 'path', 'path_streamed', 'hub_index', 'dominant')
                                 if k_ in sub['roofline']}
             if 'exchange' in sub:
                 keep['exchange'] = sub['exchange']

@@ -122,6 +122,11 @@ extern "C" {
 #define S3_CTR_SUM_READ 11 /* sorted tier: adjacency entries the method really streams (the two merged lists + */
                            /* the rows of low-degree nodes; hub rows are probed by binary search instead): the  */
                            /* index bytes of its roofline, in place of the 4*D of the SURVEY formula            */
+#define S3_CTR_CHAIN_READS 12   /* s3_ccn_chain: row segments its levels read, summed over the records it served:   */
+                               /* sum_k (induced edges of the rows of hop <= 1 + K - k) — times 4 * (F + 1) bytes = */
+                               /* the shared-memory traffic that bounds the kernel (its roofline in bench.py)       */
+#define S3_CTR_CHAIN_RECORDS 13 /* records s3_ccn_chain served (the others took the CCN work items)                */
+#define S3_CTR_CHAIN_N 14      /* sum of n over those records                                                       */
 #define S3_CTR_CLASS0 16   /* + c: records whose n has floor(log2 n) == c (size classes)  */
 #define S3_NCTR 48
 
@@ -275,6 +280,11 @@ int s3_gather_ccn(const s3_graph* g, const s3_batch* b, int64_t num_items,
  * and s3_gather on the same stream; one CTA per record. replaces tuned_SIGN.py:210-258 for the extra rows. */
 int s3_ccn_chain(const s3_graph* g, const s3_batch* b, int64_t num_records, float* const* out, int64_t ldo,
                  int64_t row_base, void* stream);
+/* Placement of a record in s3_ccn_chain by its size (n nodes, m directed induced edges, n1 nodes of hop <= 1):
+ * -1 if the record does not fit the chain's shared memory (it takes the CCN work items), else
+ * columns_per_sub_chunk | cta_class << 8 with cta_class 0 / 1 / 2 = 256 / 512 / 1024 threads. Host-side helper
+ * (no GPU): the same function the kernels and s3_plan evaluate. */
+int s3_chain_shape(int64_t n, int64_t m, int64_t n1);
 
 /* Non-optimised SIGN + SEAL flow (reference utils.py:497-520, tuned_SIGN.py:18-23,
  * i.e. PyG's SIGN transform on the whole subgraph): every subgraph node is an output row,

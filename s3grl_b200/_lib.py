@@ -21,10 +21,11 @@ CNT_N, CNT_M, CNT_S, CNT_STATUS, CNT_PARTNER, CNT_HOP0, CNT_NSTORE, NCNT = 0, 1,
 BATCH_STORE_ALL_ROWS, BATCH_FORCE_SORTED_TIER, BATCH_CCN_CHAIN, BATCH_SHARE_SMS = 1, 2, 4, 8
 CTR_CURSOR, CTR_ERRORS, CTR_ROWS, CTR_ITEMS, CTR_MAX_N, CTR_SUM_N, CTR_SUM_D, CTR_WORK, NCTR = 0, 1, 2, 3, 4, 5, 6, 7, 48
 CTR_SUM_N_ALL, CTR_SUM_D_ALL, CTR_MIRRORS, CTR_SUM_READ = 8, 9, 10, 11
+CTR_CHAIN_READS, CTR_CHAIN_RECORDS, CTR_CHAIN_N = 12, 13, 14
 
 EXPORTS = ['s3_version', 's3_error_string', 's3_last_cuda_error', 's3_num_records', 's3_extract_smem_bytes',
            's3_min_arena_words', 's3_extract_tier',
-           's3_extract', 's3_plan', 's3_plan_items', 's3_diffuse', 's3_gather', 's3_gather_ccn', 's3_ccn_chain', 's3_plan_full', 's3_sign_full', 's3_joint_rows', 's3_sign_head', 's3_walk_sets', 's3_dump_edges',
+           's3_extract', 's3_plan', 's3_plan_items', 's3_diffuse', 's3_gather', 's3_gather_ccn', 's3_ccn_chain', 's3_chain_shape', 's3_plan_full', 's3_sign_full', 's3_joint_rows', 's3_sign_head', 's3_walk_sets', 's3_dump_edges',
            's3_pair_table_slots', 's3_pair_links', 's3_pair_heads', 's3_scatter_rows', 's3_gather_peers', 's3_fill_x0', 's3_fill_mirrors', 's3_peer_alloc', 's3_peer_free', 's3_peer_export',
            's3_peer_open', 's3_peer_close', 's3_probe_l2_read', 's3_probe_fma', 's3_probe_fma2', 's3_segment_pool', 's3_negative_candidates', 's3_build_hub_bits', 's3_node_proxy']
 
@@ -88,6 +89,8 @@ def lib():
                                 C.c_int64, C.c_int64, C.c_void_p]
         L.s3_gather_ccn.argtypes = L.s3_gather.argtypes
         L.s3_ccn_chain.argtypes = L.s3_gather.argtypes
+        L.s3_chain_shape.argtypes = [C.c_int64, C.c_int64, C.c_int64]
+        L.s3_chain_shape.restype = C.c_int
         L.s3_joint_rows.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.s3_sign_head.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,

@@ -359,6 +359,12 @@ int s3_ccn_chain(const s3_graph* g, const s3_batch* b, int64_t num_records, floa
     return e == cudaSuccess ? S3_OK : cuda_fail(e);
 }
 
+int s3_chain_shape(int64_t n, int64_t m, int64_t n1) {
+    if (n < 2 || m < 0 || n1 < 2 || n1 > n) return -1;
+    if (!s3::chain_eligible(S3_BATCH_CCN_CHAIN, S3_STRATEGY_UNION, n, m, n1)) return -1;
+    return s3::chain_shape(n, m, n1, 0);
+}
+
 int s3_plan_full(const s3_batch* b, void* stream) {
     int rc = check_batch(b);
     if (rc != S3_OK) return rc;

@@ -51,6 +51,7 @@ struct ChainParams {
     int32_t* arena;
     const int64_t* __restrict__ off;
     int32_t* cnt;
+    unsigned long long* counters;
     const int64_t* __restrict__ row_ptr;
     const int32_t* __restrict__ order;  // may be null
     int64_t num_records;
@@ -173,7 +174,21 @@ __global__ void __launch_bounds__(kPrepWarps * 32) chain_prep_kernel(ChainParams
         }
         a = b;
     }
-    if (lane == 0) cnt[S3_CNT_NSTORE] = -1;
+    if (lane == 0) {
+        cnt[S3_CNT_NSTORE] = -1;
+        // accounting for the kernel's roofline: row segments the K levels read (bench.py)
+        int hop_end[S3_MAX_HOPS + 2], acc = 0;
+        for (int l = 0; l <= S3_MAX_HOPS; ++l) {
+            acc += cnt[S3_CNT_HOP0 + l];
+            hop_end[l] = acc;
+        }
+        hop_end[S3_MAX_HOPS + 1] = acc;
+        unsigned long long reads = 0;
+        for (int k = 1; k <= p.sign_k; ++k) reads += (unsigned long long)rowptr[hop_end[min(1 + p.sign_k - k, S3_MAX_HOPS + 1)]];
+        atomicAdd(&p.counters[S3_CTR_CHAIN_READS], reads);
+        atomicAdd(&p.counters[S3_CTR_CHAIN_RECORDS], 1ull);
+        atomicAdd(&p.counters[S3_CTR_CHAIN_N], (unsigned long long)n);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -507,6 +522,7 @@ cudaError_t launch_ccn_chain(const s3_graph& g, const s3_batch& b, int64_t num_r
     p.arena = b.arena;
     p.off = b.off;
     p.cnt = b.cnt;
+    p.counters = reinterpret_cast<unsigned long long*>(b.counters);
     p.row_ptr = b.row_ptr;
     p.order = b.order;
     p.num_records = num_records;

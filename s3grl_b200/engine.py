@@ -493,6 +493,8 @@ class _Call:
         self.stats['sum_d_links'] += int(c[L.CTR_SUM_D_ALL])
         self.stats['mirrors'] += int(c[L.CTR_MIRRORS])
         self.stats['sum_read'] = self.stats.get('sum_read', 0) + int(c[L.CTR_SUM_READ])
+        for key, slot in (('chain_reads', L.CTR_CHAIN_READS), ('chain_records', L.CTR_CHAIN_RECORDS), ('chain_n', L.CTR_CHAIN_N)):
+            self.stats[key] = self.stats.get(key, 0) + int(c[slot])
         self.stats['max_n'] = max(self.stats['max_n'], int(c[L.CTR_MAX_N]))
         return True
 
@@ -698,6 +700,8 @@ class _Call:
             self.stats['launches'] += 3
         self.pieces.append(xs)
         self.row_counts.append(row_ptr[1:] - row_ptr[:-1])
+        if getattr(self, '_rec_n', None) is not None:        # pairing: per-link accounting needs every record's n
+            self._rec_n.append(cnt[:, L.CNT_N].to(torch.int64))
         return off, cnt, True
 
     def run_variable(self):
@@ -764,6 +768,7 @@ class _Call:
                     self.stats['records'] = self.num_links * self.rpl
                     self.set_batches()
                     self.counters = torch.zeros((max(self.num_batches, 1), L.NCTR), dtype=torch.int64, device=dev)
+                    self._rec_n = []
                 else:
                     head_idx, var_mirror = None, None
             self.run_variable()
@@ -771,6 +776,12 @@ class _Call:
             if head_idx is not None:      # rows of every link of the list = rows of its head's record
                 rank = torch.cumsum(is_head, 0) - 1
                 counts = counts[rank[head_code >> 1]]
+                # SURVEY 8d sums over LINKS: a paired link counts its own subgraph although its head's record serves it
+                # (n exactly; D scaled by the same ratio — the per-record D is not kept)
+                served = torch.bincount(head_code >> 1, minlength=Lk)[head_idx]
+                n_links = int((torch.cat(self._rec_n) * served).sum()) if self._rec_n else 0
+                self.stats['sum_d_links'] = int(self.stats['sum_d'] * n_links / max(1, self.stats['sum_n']))
+                self.stats['sum_n_links'] = n_links
             row_ptr = torch.zeros(Lk + 1, dtype=torch.int64, device=dev)
             torch.cumsum(counts, 0, out=row_ptr[1:])
             self.stats['rows_computed'] = sum(int(p[0].shape[0]) for p in self.pieces)   # without the paired links' copies

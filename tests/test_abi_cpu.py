@@ -45,7 +45,8 @@ def test_constants_match_header():
              'S3_BATCH_CCN_CHAIN': L.BATCH_CCN_CHAIN, 'S3_BATCH_SHARE_SMS': L.BATCH_SHARE_SMS, 'S3_LABEL_ZO': L.LABEL_ZO, 'S3_LABEL_HOP': L.LABEL_HOP,
              'S3_LABEL_DRNL': L.LABEL_DRNL, 'S3_LABEL_DEGREE': L.LABEL_DEGREE, 'S3_LABEL_ZERO': L.LABEL_ZERO,
              'S3_REC_MIRROR': L.REC_MIRROR, 'S3_CTR_SUM_N_ALL': L.CTR_SUM_N_ALL, 'S3_CTR_SUM_D_ALL': L.CTR_SUM_D_ALL,
-             'S3_CTR_MIRRORS': L.CTR_MIRRORS, 'S3_CTR_SUM_READ': L.CTR_SUM_READ, 'S3_MAX_PEERS': L.MAX_PEERS, 'S3_MAX_K_UNION': L.MAX_K_UNION,
+             'S3_CTR_MIRRORS': L.CTR_MIRRORS, 'S3_CTR_SUM_READ': L.CTR_SUM_READ, 'S3_CTR_CHAIN_READS': L.CTR_CHAIN_READS,
+             'S3_CTR_CHAIN_RECORDS': L.CTR_CHAIN_RECORDS, 'S3_CTR_CHAIN_N': L.CTR_CHAIN_N, 'S3_MAX_PEERS': L.MAX_PEERS, 'S3_MAX_K_UNION': L.MAX_K_UNION,
              'S3_PEER_HANDLE_BYTES': L.PEER_HANDLE_BYTES, 'S3_VERSION': L.VERSION}
     for k, v in pairs.items():
         assert int(defs[k]) == v, k
@@ -163,6 +164,29 @@ def test_argument_validation_of_the_round2_entry_points(lib):
     assert lib.s3_scatter_rows(arr, 5, None, 2, None, 0, None, P(16), arr, 5, 4, 5, None) == L.S3_ERR_INVALID_ARG    # no row_ptr
     assert lib.s3_scatter_rows(arr, 5, P(16), 2, None, 0, None, P(16), arr, 5, 0, 5, None) == L.S3_ERR_INVALID_ARG   # no operators
     assert lib.s3_scatter_rows(arr, 5, P(16), 2, None, -1, None, P(16), arr, 5, 4, 5, None) == L.S3_ERR_INVALID_ARG
+
+
+def test_chain_placement_by_record_size(lib):
+    """s3_chain_shape (host-side, the function s3_plan and the chain kernels evaluate): the widest sub-chunk that fits,
+    in the smallest CTA; wider never follows narrower as records grow; beyond ~4 000 nodes the work items keep the record."""
+    shape = lambda n, m, n1: lib.s3_chain_shape(n, m, n1)
+    assert shape(1, 0, 1) == -1 and shape(100, 400, 200) == -1                      # not a subgraph
+    assert shape(120, 500, 30) == 32 | (0 << 8)                                      # 256-thread CTA, 4 per SM
+    assert shape(300, 1500, 40) == 32 | (1 << 8) and shape(700, 3500, 50) == 32 | (2 << 8)
+    assert shape(1200, 6000, 60) == 16 | (2 << 8) and shape(2500, 14000, 90) == 8 | (2 << 8)
+    assert shape(3600, 20000, 120) == 4 | (2 << 8) and shape(9000, 50000, 300) == -1 and shape(70000, 70000, 5) == -1
+    last = (32, 0)
+    for n in range(20, 6000, 37):
+        sh = shape(n, 5 * n, min(n, 40))
+        if sh < 0:
+            assert n > 3000
+            last = (0, 3)
+            continue
+        cw, cls = sh & 255, sh >> 8
+        assert cw in (32, 16, 8, 4) and cls in (0, 1, 2) and (cw < last[0] or (cw == last[0] and cls >= last[1])), (n, cw, cls, last)
+        bytes_needed = 4 * (2 * n * cw + 3 * n + min(n, 40) + (5 * n + 2) // 2 + 8)
+        assert bytes_needed <= (54, 110, 222)[cls] * 1024
+        last = (cw, cls)
 
 
 def test_per_hop_cap_counts_match_the_reference_formula():
