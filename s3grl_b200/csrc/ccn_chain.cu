@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kPrepWarps * 32) chain_prep_kernel(ChainParams
     const int n = cnt[S3_CNT_N], s = cnt[S3_CNT_S], m = cnt[S3_CNT_M];
     const int n1 = cnt[S3_CNT_HOP0] + cnt[S3_CNT_HOP0 + 1];
     if (s <= 2 || cnt[S3_CNT_NSTORE] < 0) return;  // no CCN rows / already converted
-    if (!chain_eligible(p.flags, p.strategy, n, m, n1)) return;
+    if (!chain_eligible(p.flags, p.strategy, n, m, n1) && !chain_spill_eligible(p.flags, p.strategy, n, m, n1, s, p.sign_k)) return;
     const int64_t* off = p.off + rec * S3_NOFF;
     int32_t* rowptr = p.arena + off[S3_OFF_ROWPTR];
     int32_t* rowlen = p.arena + off[S3_OFF_ROWLEN];
@@ -215,7 +215,7 @@ constexpr int kGrabSteps = S3_CHAIN_GRAB;  // warp steps a warp takes from the h
 
 // D neighbours of one row, D a compile-time bound shared by the rows of the warp step (they are sorted by degree)
 template <int D, int LPR>
-__device__ __forceinline__ float4 row_sum(const float4* __restrict__ prev, const uint16_t* __restrict__ cc, int d, int l) {
+__device__ __forceinline__ float4 row_sum(const float4* prev, const uint16_t* cc, int d, int l) {
     int c[D];
 #pragma unroll
     for (int t = 0; t < D; ++t) c[t] = t < d ? (int)cc[t] : -1;
@@ -229,8 +229,10 @@ __device__ __forceinline__ float4 row_sum(const float4* __restrict__ prev, const
 // One level for the chain columns [cs, cs + CW): x_k = D^-1/2 (sum over neighbours of y_{k-1}), y_k = D^-1/2 x_k.
 // `next` is null for the last level (k == K), which only writes the output rows.
 template <int CW, int T>
-__device__ __forceinline__ void chain_level(const ChainParams& p, const ChainRec& r, int k, const float4* __restrict__ prev,
-                                            float4* __restrict__ next, int cs, int* ctr) {
+// (prev / next are NOT __restrict__: in the spill class they are global memory written earlier in the same kernel, which the
+// non-coherent load path a const __restrict__ pointer invites must not serve)
+__device__ __forceinline__ void chain_level(const ChainParams& p, const ChainRec& r, int k, const float4* prev, float4* next, int cs,
+                                            int* ctr) {
     constexpr int LPR = CW / 4, RPW = 32 / LPR, NWARP = T / 32;
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -395,7 +397,8 @@ __device__ __forceinline__ void chain_columns(const ChainParams& p, const ChainR
     }
 }
 
-template <int T>
+// SPILL: the records of class 3 — operator buffers in the record's global float scratch instead of shared memory
+template <int T, bool SPILL>
 __global__ void __launch_bounds__(T, 1024 / T) chain_kernel(ChainParams p) {
     extern __shared__ __align__(16) int s_dyn[];
     __shared__ int s_hop_end[S3_MAX_HOPS + 2];
@@ -410,11 +413,16 @@ __global__ void __launch_bounds__(T, 1024 / T) chain_kernel(ChainParams p) {
     const int n = cnt[S3_CNT_N], s = cnt[S3_CNT_S], m = cnt[S3_CNT_M];
     const int n1 = cnt[S3_CNT_HOP0] + cnt[S3_CNT_HOP0 + 1];
     if (s <= 2) return;  // no CCN rows
-    // records that do not fit the shared-memory placement keep the work-item path (s3_plan counted their items)
-    if (!chain_eligible(p.flags, p.strategy, n, m, n1)) return;
-    const int shape = chain_shape(n, m, n1, p.policy);
-    if ((shape >> 8) != p.cls) return;  // served by the launch of another CTA size
-    const int cw = shape & 255;
+    // records that fit neither placement keep the work-item path (s3_plan counted their items)
+    int cw = 32;
+    if (SPILL) {
+        if (!chain_spill_eligible(p.flags, p.strategy, n, m, n1, s, p.sign_k)) return;
+    } else {
+        if (!chain_eligible(p.flags, p.strategy, n, m, n1)) return;
+        const int shape = chain_shape(n, m, n1, p.policy);
+        if ((shape >> 8) != p.cls) return;  // served by the launch of another CTA size
+        cw = shape & 255;
+    }
     // column slab of this CTA
     const int nchunks = p.F / cw + 1;  // chain columns 0..F
     const int per = (nchunks + (int)gridDim.y - 1) / (int)gridDim.y;
@@ -427,9 +435,11 @@ __global__ void __launch_bounds__(T, 1024 / T) chain_kernel(ChainParams p) {
     const uint32_t* g_ccol = reinterpret_cast<const uint32_t*>(p.arena + off[S3_OFF_LCOL]);      // uint16[m]
     const int32_t* sel = p.arena + off[S3_OFF_SEL];
 
-    // shared memory: [buf0 n*CW | buf1 n*CW | meta 2n | cdis n | cpos n1 | ccol (m+1)/2 words]
-    float4* buf0 = reinterpret_cast<float4*>(s_dyn);
-    uint2* meta = reinterpret_cast<uint2*>(buf0 + 2 * (int64_t)n * (cw / 4));
+    // shared memory: [buf0 n*CW | buf1 n*CW | meta 2n | cdis n | cpos n1 | ccol (m+1)/2 words]; SPILL: the two buffers sit
+    // behind the record's own work item in its float scratch (128-byte aligned, 2 * n * 32 floats)
+    float4* buf0 = SPILL ? reinterpret_cast<float4*>(p.arena + off[S3_OFF_F32] + item_words(S3_FLOW_POS, p.sign_k, n))
+                         : reinterpret_cast<float4*>(s_dyn);
+    uint2* meta = SPILL ? reinterpret_cast<uint2*>(s_dyn) : reinterpret_cast<uint2*>(buf0 + 2 * (int64_t)n * (cw / 4));
     float* cdis = reinterpret_cast<float*>(meta + n);
     int* cpos = reinterpret_cast<int*>(cdis + n);
     uint32_t* ccol32 = reinterpret_cast<uint32_t*>(cpos + n1);
@@ -496,15 +506,15 @@ int env_int(const char* name, int dflt, int lo, int hi) {
     return x < lo ? lo : (x > hi ? hi : x);
 }
 
-template <int T>
+template <int T, bool SPILL>
 cudaError_t launch_class(const ChainParams& p, int cls, int slabs, cudaStream_t st) {
     static LaunchCache cache;  // the shared-memory opt-in is per device
     const size_t smem = (size_t)chain_class_bytes(cls);
-    cudaError_t e = cache.get(reinterpret_cast<const void*>(chain_kernel<T>), T, smem, nullptr, nullptr);
+    cudaError_t e = cache.get(reinterpret_cast<const void*>(chain_kernel<T, SPILL>), T, smem, nullptr, nullptr);
     if (e != cudaSuccess) return e;
     ChainParams q = p;
     q.cls = cls;
-    chain_kernel<T><<<dim3((unsigned)p.num_records, (unsigned)slabs), T, smem, st>>>(q);
+    chain_kernel<T, SPILL><<<dim3((unsigned)p.num_records, (unsigned)slabs), T, smem, st>>>(q);
     return cudaGetLastError();
 }
 
@@ -540,11 +550,13 @@ cudaError_t launch_ccn_chain(const s3_graph& g, const s3_batch& b, int64_t num_r
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     // largest CTAs first: their records are the long ones
-    e = launch_class<1024>(p, 2, slabs, st);
+    e = launch_class<1024, true>(p, 3, 1, st);  // the few records whose buffers live in global memory: longest of all
     if (e != cudaSuccess) return e;
-    e = launch_class<512>(p, 1, slabs, st);
+    e = launch_class<1024, false>(p, 2, slabs, st);
     if (e != cudaSuccess) return e;
-    return launch_class<256>(p, 0, slabs, st);
+    e = launch_class<512, false>(p, 1, slabs, st);
+    if (e != cudaSuccess) return e;
+    return launch_class<256, false>(p, 0, slabs, st);
 }
 
 }  // namespace s3

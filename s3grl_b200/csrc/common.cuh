@@ -81,6 +81,14 @@ __host__ __device__ inline bool chain_fits(int64_t n, int64_t m, int64_t n1, int
 __host__ __device__ inline bool chain_eligible(int flags, int strategy, int64_t n, int64_t m, int64_t n1) {
     return (flags & S3_BATCH_CCN_CHAIN) && strategy == S3_STRATEGY_UNION && n < 65536 && chain_fits(n, m, n1, 4, 2);
 }
+// Records too large for that placement ("spill" class 3: n up to ~9 000) keep the CSR in shared memory and the two
+// [n][32] buffers in the float scratch the front kernel reserved for their CCN work items — global memory, read
+// through L2 — provided that scratch is large enough (two or more work items' worth).
+__host__ __device__ inline bool chain_spill_eligible(int flags, int strategy, int64_t n, int64_t m, int64_t n1, int s, int K) {
+    if (!(flags & S3_BATCH_CCN_CHAIN) || strategy != S3_STRATEGY_UNION || n >= 65536 || chain_fits(n, m, n1, 4, 2)) return false;
+    if (4 * (3 * n + n1 + (m + 2) / 2 + 8) > chain_class_bytes(2)) return false;
+    return (int64_t)ccn_items(s, 2, 8) * ccn_item_words(K, n, 8) >= 64 * n + 8;
+}
 // (CW, class) of an eligible record as CW | class << 8. policy 0: the widest sub-chunk first (128-byte row segments
 // are free of bank conflicts), in the smallest CTA that holds it; 1: two CTAs per SM at CW = 16 before one at CW = 32;
 // 2: occupancy first.

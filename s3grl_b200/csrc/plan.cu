@@ -7,14 +7,16 @@ namespace s3 {
 namespace {
 
 // Single CTA: exclusive scans of s (rows) and of the CCN work items ceil((s - seeds) / 8) over all records.
-__device__ __forceinline__ int record_items(const int32_t* c, int nseed, int cr, int flags, int strategy) {
+__device__ __forceinline__ int record_items(const int32_t* c, int nseed, int cr, int flags, int strategy, int K) {
     const int s = c[S3_CNT_S];
-    if (chain_eligible(flags, strategy, c[S3_CNT_N], c[S3_CNT_M], c[S3_CNT_HOP0] + c[S3_CNT_HOP0 + 1])) return 0;
+    const int n1 = c[S3_CNT_HOP0] + c[S3_CNT_HOP0 + 1];
+    if (chain_eligible(flags, strategy, c[S3_CNT_N], c[S3_CNT_M], n1)) return 0;
+    if (chain_spill_eligible(flags, strategy, c[S3_CNT_N], c[S3_CNT_M], n1, s, K)) return 0;
     return ccn_items(s, nseed, cr);
 }
 
 __global__ void __launch_bounds__(1024) plan_scan_kernel(const int32_t* __restrict__ cnt, int64_t num_records, int nseed, int cr,
-                                                         int flags, int strategy,
+                                                         int flags, int strategy, int K,
                                                          int64_t* __restrict__ row_ptr, int64_t* __restrict__ item_ptr,
                                                          unsigned long long* counters) {
     __shared__ long long s_rows[1024], s_items[1024];
@@ -25,7 +27,7 @@ __global__ void __launch_bounds__(1024) plan_scan_kernel(const int32_t* __restri
     for (int64_t r = r0; r < r1; ++r) {
         const int s = cnt[r * S3_NCNT + S3_CNT_S];
         rows += s;
-        items += record_items(cnt + r * S3_NCNT, nseed, cr, flags, strategy);
+        items += record_items(cnt + r * S3_NCNT, nseed, cr, flags, strategy, K);
     }
     s_rows[tid] = rows;
     s_items[tid] = items;
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(1024) plan_scan_kernel(const int32_t* __restri
         row_ptr[r] = row_run;
         item_ptr[r] = item_run;
         row_run += s;
-        item_run += record_items(cnt + r * S3_NCNT, nseed, cr, flags, strategy);
+        item_run += record_items(cnt + r * S3_NCNT, nseed, cr, flags, strategy, K);
     }
     if (tid == T - 1) {
         row_ptr[num_records] = s_rows[tid];
@@ -112,7 +114,7 @@ __global__ void dump_edges_kernel(const int32_t* __restrict__ arena, const int64
 
 cudaError_t launch_plan(const s3_batch& b, cudaStream_t st) {
     const int64_t R = s3_num_records(&b);
-    plan_scan_kernel<<<1, 1024, 0, st>>>(b.cnt, R, num_seeds(b.flow), ccn_rows(b.strategy), b.flags, b.strategy, b.row_ptr, b.item_ptr,
+    plan_scan_kernel<<<1, 1024, 0, st>>>(b.cnt, R, num_seeds(b.flow), ccn_rows(b.strategy), b.flags, b.strategy, b.sign_k, b.row_ptr, b.item_ptr,
                                          reinterpret_cast<unsigned long long*>(b.counters));
     return cudaGetLastError();
 }
