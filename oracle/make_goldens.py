@@ -62,9 +62,13 @@ def make_case(name, A, links, flow, K, num_hops=0, strategy=None, X=None, x_spec
     feats = X if X is not None else features_from_spec(x_spec, A, N)
     links = np.ascontiguousarray(links, dtype=np.int64)
     if flow == 'pos':
-        r = rr.ref_pos(links, num_hops, A, feats, K, strategy)
+        r = rr.ref_pos(links, num_hops, A, feats, K, strategy, repair_union_typo=strategy == 'union')
         extra = _graph_dump(links, num_hops, A)
         extra['row_gid'] = r['row_gid']
+        if strategy == 'union':
+            extra['reference_repair'] = np.str_(
+                "tuned_SIGN.py:243 `[[0] * (csr_shape - 2)]` read as `[[0]] * (csr_shape - 2)` (the intersection branch's "
+                "line 247) by oracle/ref_runner.union_typo_repaired at run time; /root/reference unmodified on disk")
     elif flow == 'sop':
         r = rr.ref_sop(links, A, feats, K)
         extra = {}
@@ -213,10 +217,30 @@ def round2_cases():
     make_case('router_pos_k5', A, sample_links(splits, 60, 13), 'pos', 5, 2, None, x_spec='synthetic:32:0.5:8')
 
 
+def union_cases():
+    """PoS Plus `union` (BASELINE config 3) against the reference with its label-column literal repaired: hand graphs,
+    USAir, Cora and the PubMed graph with the bench's F = 500 feature spec."""
+    A, links, X = tiny_graphs()
+    make_case('tiny_posplus_union_h2', A, links, 'pos', 3, 2, 'union', X=X)
+    make_case('tiny_posplus_union_h1_k5', A, links, 'pos', 5, 1, 'union', X=X)
+    edges, N, _ = ds.load_graph('usair')
+    A, splits = ds.split_links(edges, N, seed=1)
+    make_case('usair_posplus_union', A, sample_links(splits, 40, 21), 'pos', 3, 2, 'union', x_spec='synthetic:16:0.5:6')
+    edges, N, _ = ds.load_graph('cora')
+    A, splits = ds.split_links(edges, N, seed=1)
+    make_case('cora_posplus_union', A, sample_links(splits, 60, 22), 'pos', 3, 3, 'union', x_spec='synthetic:24:0.3:5')
+    edges, N, _ = ds.load_graph('pubmed')
+    A, splits = ds.split_links(edges, N, seed=1)
+    make_case('pubmed_posplus_union', A, sample_links(splits, 12, 23), 'pos', 3, 3, 'union', x_spec='synthetic:500:0.1:0')
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     if '--round2' in sys.argv:          # only the fixtures added in round 2 (the others are unchanged)
         round2_cases()
+        return
+    if '--union' in sys.argv:           # only the union fixtures (round 2, third session)
+        union_cases()
         return
     make_posneg_case()
     A, links, X = tiny_graphs()
@@ -254,6 +278,7 @@ def main():
     A, splits = ds.split_links(edges, N, seed=1)
     make_case('power_pos_k5', A, sample_links(splits, 100, 4), 'pos', 5, 2, None, x_spec='synthetic:8:1.0:9')
     round2_cases()
+    union_cases()
 
 
 if __name__ == '__main__':

@@ -69,20 +69,61 @@ def ref_k_hop(src, dst, num_hops, A):
     return cn, dists[order], edges
 
 
+class _TorchWithLabelColumnRepaired:
+    """Stand-in for the name `torch` inside the reference's tuned_SIGN module while a `union` golden is generated.
+    tuned_SIGN.py:243 builds the zero-one label column of the union branch from the ragged literal
+    `[[1]] + [[1]] + [[0] * (n - 2)]` — one inner list of n - 2 zeros where the intersection branch four lines below
+    (`[[0]] * (n - 2)`: n - 2 inner lists) shows what was meant — so `torch.tensor` raises ValueError for every
+    subgraph that does not have exactly 3 nodes.  This proxy forwards everything to torch and only makes `tensor()` of
+    exactly that literal return the intended (n, 1) column.  /root/reference itself is never modified; fixtures made
+    this way carry `reference_repair` in the file and "union" in their name."""
+
+    def __init__(self, real):
+        self._real = real
+        self.repairs = 0
+
+    def __getattr__(self, name):
+        return getattr(self._real, name)
+
+    def tensor(self, data, *args, **kwargs):
+        if (isinstance(data, list) and len(data) == 3 and data[0] == [1] and data[1] == [1] and isinstance(data[2], list)
+                and len(data[2]) != 1 and all(v == 0 for v in data[2])):
+            self.repairs += 1
+            return self._real.tensor([[1], [1]] + [[0]] * len(data[2]), *args, **kwargs)
+        return self._real.tensor(data, *args, **kwargs)
+
+
+@contextlib.contextmanager
+def union_typo_repaired():
+    """Within the block the reference's PoS Plus `union` branch builds its label column as its `intersection` branch does
+    (see _TorchWithLabelColumnRepaired).  Yields the proxy (its `repairs` counts the literals it replaced)."""
+    _, tuned = load_reference()
+    real = tuned.torch
+    proxy = _TorchWithLabelColumnRepaired(real)
+    tuned.torch = proxy
+    try:
+        yield proxy
+    finally:
+        tuned.torch = real
+
+
 def _sign_kwargs(K, strategy):
     return {'sign_k': K, 'use_feature': True, 'sign_type': 'PoS', 'optimize_sign': True,
             'k_heuristic': 0 if strategy is None else 1, 'k_node_set_strategy': strategy}
 
 
-def ref_pos(links, num_hops, A, X, K, strategy=None):
+def ref_pos(links, num_hops, A, X, K, strategy=None, repair_union_typo=False):
     """get_PoS_prepped_ds / get_PoS_Plus_prepped_ds (tuned_SIGN.py:137-262) through
     extract_enclosing_subgraphs (utils.py:446-496) -> dict(xs, row_ptr, row_gid) with the rows
     of every link put in canonical order: row 0 = src, row 1 = dst, extra rows by ascending
-    global id (== ascending canonical local id, all extra rows being hop-1 nodes)."""
+    global id (== ascending canonical local id, all extra rows being hop-1 nodes).
+    strategy='union' runs the UNMODIFIED reference unless repair_union_typo=True (union_typo_repaired above): unmodified,
+    it raises ValueError at tuned_SIGN.py:243 for every link whose subgraph does not have exactly 3 nodes."""
     utils, tuned = load_reference()
     link_index = torch.as_tensor(np.asarray(links), dtype=torch.long)
     x = torch.as_tensor(np.asarray(X), dtype=torch.float32)
-    with _quiet():
+    ctx = union_typo_repaired() if (repair_union_typo and strategy == 'union') else contextlib.nullcontext()
+    with _quiet(), ctx:
         data_list = utils.extract_enclosing_subgraphs(
             link_index, A, x, 1, num_hops, 'zo', 1.0, None, False, None, None,
             _sign_kwargs(K, strategy), powers_of_A=[], data=None)

@@ -24,9 +24,15 @@ Pinning (see tests/test_oracle_vs_reference.py, oracle/make_goldens.py): the ref
 NO tests or golden vectors for this path, so the oracle is pinned
 against outputs of the reference's own functions, imported unmodified from /root/reference
 behind the stand-in packages in oracle/ref_stub, run in the build container and committed as
-tests/golden/ref_*.npz.  The `union` strategy cannot be pinned that way — the reference
-raises ValueError at tuned_SIGN.py:243 — so for `union` parity is UNPINNED and follows the
-documented rule below.
+tests/golden/ref_*.npz.  The `union` strategy: the unmodified reference raises ValueError at
+tuned_SIGN.py:243 (a ragged literal for the label column) unless the subgraph has exactly 3 nodes.
+It is pinned (a) unmodified, on such 3-node subgraphs (tests/test_oracle_vs_reference.py), and
+(b) against the reference with that ONE literal repaired at run time
+(oracle/ref_runner.union_typo_repaired; fixtures ref_*_union*.npz, plus the live hypothesis test).
+The repaired reference selects src and dst a second time among the extra rows (its target-link
+mask leaves explicit zeros that `neighbors` reports); the rule here is the paper's,
+[0, 1] + (N(0) ∪ N(1)) − {0, 1}, and the tests check that the two additional reference rows are
+bit-identical copies of rows 0 / 1 before dropping them (tests/golden_util.drop_duplicated_seed_rows).
 
 Canonical order (SURVEY.md Appendix A.5): nodes = [src, dst] then ascending (hop, global id);
 induced edges sorted by (local row, local col); extra selected rows ascending local id.
@@ -147,7 +153,8 @@ def select_rows(lrowptr, lcol, strategy):
     """Row selection, tuned_SIGN.py:173 (PoS) and :228-238 (PoS Plus).
     strategy None -> [0,1]; 'intersection' -> [0,1] + common neighbours of local 0 and 1 in
     the masked subgraph; 'union' -> [0,1] + (N(0) ∪ N(1)) − {0,1} (paper semantics; the
-    reference code raises for union).  Extra rows ascending local id."""
+    reference code raises for union, SURVEY.md A.4, and with its literal repaired additionally repeats
+    rows 0 and 1 — module docstring).  Extra rows ascending local id."""
     if strategy is None:
         return np.array([0, 1], dtype=np.int32)
     n0 = lcol[lrowptr[0]:lrowptr[1]]

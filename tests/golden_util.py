@@ -56,6 +56,35 @@ class Case:
             self.row_gid = d['row_gid']
             self.node_ptr, self.edge_ptr = d['node_ptr'], d['edge_ptr']
             self.nodes, self.hops, self.edges = d['nodes'], d['hops'], d['edges']
+        self.reference_repair = str(d['reference_repair']) if 'reference_repair' in d.files else ''
+        if self.strategy == 'union':      # fixtures hold the reference's LITERAL rows: see drop_duplicated_seed_rows
+            self._drop_duplicated_seed_rows()
+
+    def _drop_duplicated_seed_rows(self):
+        self.literal_row_ptr, self.literal_xs, self.literal_row_gid = self.row_ptr, self.xs, self.row_gid
+        self.row_ptr, self.row_gid, self.xs = drop_duplicated_seed_rows(self.links, self.row_ptr, self.row_gid, self.xs, self.name)
+
+
+def drop_duplicated_seed_rows(links, row_ptr, row_gid, xs, what=''):
+    """`union` outputs of the reference (its tuned_SIGN.py:243 typo repaired, see oracle/ref_runner.union_typo_repaired)
+    -> the same in the framework's row selection.  k_hop_subgraph masks the target link by ASSIGNING 0 to [0, 1] and
+    [1, 0] (utils.py:78-79), which leaves two explicitly stored zeros in the CSR, and `neighbors` (utils.py:40) returns
+    stored column ids — so N(0) contains 1, N(1) contains 0, and the union selects src and dst a second time among the
+    extra rows.  The framework (like the paper) selects [0, 1] + (N(0) ∪ N(1)) − {0, 1}.  This checks that the two extra
+    rows are bit-identical copies of rows 0 / 1 in every operator and removes them.  -> (row_ptr, row_gid, xs)"""
+    L = links.shape[1]
+    keep = np.ones(row_gid.size, dtype=bool)
+    for i in range(L):
+        a, b = int(row_ptr[i]), int(row_ptr[i + 1])
+        src, dst = int(links[0][i]), int(links[1][i])
+        assert row_gid[a] == src and row_gid[a + 1] == dst
+        for seed_row, gid in ((a, src), (a + 1, dst)):
+            dup = a + 2 + np.flatnonzero(row_gid[a + 2:b] == gid)
+            assert dup.size == 1, f'{what} link {i}: expected exactly one duplicate of seed {gid}'
+            for x in xs:
+                assert np.array_equal(x[dup[0]], x[seed_row]), f'{what} link {i}: duplicate row differs'
+            keep[dup[0]] = False
+    return row_ptr - 2 * np.arange(L + 1, dtype=row_ptr.dtype), row_gid[keep], [x[keep] for x in xs]
 
 
 def assert_features_close(got, ref, tol=1e-5, what=''):

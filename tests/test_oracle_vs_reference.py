@@ -2,14 +2,15 @@
 by oracle/ref_runner.py) on generated graphs — SURVEY.md §4 / §8c.  The committed goldens pin fixed cases; this test
 draws new graphs and links every run (hypothesis, derandomised so that CI is reproducible) and compares node sets,
 hop labels, induced + masked edge sets (bit-exact) and operators (1e-5 of max|ref|) for PoS, PoS Plus intersection,
-SoP, hybrid and the non-optimised flow.  Build-container only: skipped where the reference checkout is absent
+PoS Plus union (the reference's ragged label-column literal at tuned_SIGN.py:243 repaired at run time, and — unmodified —
+on the 3-node subgraphs it happens to accept), SoP, hybrid and the non-optimised flow.  Build-container only: skipped where the reference checkout is absent
 (the GPU box), and never imported by the product."""
 import numpy as np
 import pytest
 import scipy.sparse as ssp
 from hypothesis import HealthCheck, given, settings, strategies as st
 
-from golden_util import assert_features_close
+from golden_util import assert_features_close, drop_duplicated_seed_rows
 from oracle import ref_runner as rr
 from oracle import s3grl_oracle as orc
 
@@ -66,6 +67,45 @@ def test_pos_and_pos_plus(gl, num_hops, K, strategy):
     assert np.array_equal(gid, ref['row_gid'])
     for k in range(K + 1):
         assert_features_close(out['xs'][k], ref['xs'][k], what=f'x{k}')
+
+
+@settings(**SETTINGS)
+@given(graph_and_links(), st.integers(1, 3), st.integers(1, 4))
+def test_pos_plus_union_against_the_repaired_reference(gl, num_hops, K):
+    """BASELINE config 3.  The reference's union branch with its one broken literal repaired (ref_runner.union_typo_repaired);
+    its rows are the framework's plus src and dst selected a second time (golden_util.drop_duplicated_seed_rows)."""
+    A, X, links = gl
+    ref = rr.ref_pos(links, num_hops, A, X, K, 'union', repair_union_typo=True)
+    row_ptr, row_gid, xs = drop_duplicated_seed_rows(links, ref['row_ptr'], ref['row_gid'], ref['xs'])
+    out = orc.pos_precompute(links, num_hops, A, X, K, 'union', keep_graphs=True)
+    assert np.array_equal(out['row_ptr'], row_ptr)
+    assert np.array_equal(np.concatenate([g['nodes'][g['sel']] for g in out['graphs']]), row_gid)
+    for k in range(K + 1):
+        assert_features_close(out['xs'][k], xs[k], what=f'x{k}')
+
+
+def test_union_on_the_unmodified_reference():
+    """What the reference does for `union` as it stands: ValueError (the ragged literal of tuned_SIGN.py:243) unless the
+    subgraph has exactly 3 nodes, where `[[1]] + [[1]] + [[0] * 1]` happens to be rectangular — those links pin the oracle's
+    union against the UNMODIFIED code."""
+    # wedges a - c - b (h = 1: nodes {a, b, c}) next to a 4-cycle (4 nodes) and an isolated pair (2 nodes)
+    e = np.array([(0, 2), (1, 2), (3, 5), (4, 5), (6, 7), (7, 8), (8, 9), (9, 6)])
+    n = 12
+    row, col = np.concatenate([e[:, 0], e[:, 1]]), np.concatenate([e[:, 1], e[:, 0]])
+    A = ssp.csr_matrix((np.ones(row.size, dtype=np.int64), (row, col)), shape=(n, n))
+    A.sort_indices()
+    X = np.random.default_rng(0).random((n, 4), dtype=np.float32)
+    wedges = np.array([[0, 3, 1, 2], [1, 4, 0, 0]])          # (0,1), (3,4), (1,0): 3 nodes; (2,0) at h=1: {2, 0, 1}
+    ref = rr.ref_pos(wedges, 1, A, X, 3, 'union')             # no repair
+    row_ptr, row_gid, xs = drop_duplicated_seed_rows(wedges, ref['row_ptr'], ref['row_gid'], ref['xs'])
+    out = orc.pos_precompute(wedges, 1, A, X, 3, 'union', keep_graphs=True)
+    assert np.array_equal(out['row_ptr'], row_ptr)
+    assert np.array_equal(np.concatenate([g['nodes'][g['sel']] for g in out['graphs']]), row_gid)
+    for k in range(4):
+        assert_features_close(out['xs'][k], xs[k], what=f'x{k}')
+    for bad in ([[6], [8]], [[10], [11]]):                    # 4 nodes / 2 nodes
+        with pytest.raises(ValueError):
+            rr.ref_pos(np.array(bad), 1, A, X, 3, 'union')
 
 
 @settings(**SETTINGS)
