@@ -393,6 +393,14 @@ int s3_pair_heads(const int64_t* mirror, int64_t num_links, int64_t* head_code, 
 int s3_scatter_rows(float* const* src, int64_t ld_src, const int64_t* src_row_ptr, int64_t num_records,
                     const int64_t* link_idx, int64_t link_base, const int64_t* mirror, const int64_t* dst_row_ptr,
                     float* const* dst, int64_t ld_dst, int32_t num_ops, int64_t num_cols, void* stream);
+/* s3_scatter_rows with the record's first lead_rows (0..2) rows written a second time in front of its rows: destination
+ * rows [r_0 .. r_{lead-1} | r_0 .. r_{s-1}] (exchanged like rows 0 / 1 for an opposite-direction chain member), so
+ * dst_row_ptr must count s + min(lead_rows, s) rows per link. lead_rows = 2 is the `compat_explicit_zero` layout of the
+ * PoS Plus union: the reference (tuned_SIGN.py:230-231 on the masked subgraph of utils.py:78-79, whose explicit zeros
+ * `neighbors` reports) selects src and dst a second time among the extra rows — SURVEY.md A.4. */
+int s3_scatter_rows_lead(float* const* src, int64_t ld_src, const int64_t* src_row_ptr, int64_t num_records,
+                         const int64_t* link_idx, int64_t link_base, const int64_t* mirror, const int64_t* dst_row_ptr,
+                         float* const* dst, int64_t ld_dst, int32_t num_ops, int64_t num_cols, int32_t lead_rows, void* stream);
 /* x (operator 0) of the fixed-row flows for a whole link list: out0 [2 * num_links, ldo], row 2i = [1 | X[src_i]],
  * row 2i+1 = [1 | X[dst_i]] (reference tuned_SIGN.py:181 / :119-124); rows of invalid links are left untouched. */
 int s3_fill_x0(const s3_graph* g, const int64_t* link_src, const int64_t* link_dst, int64_t num_links, float* out0, int64_t ldo,

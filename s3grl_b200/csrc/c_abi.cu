@@ -229,11 +229,11 @@ int s3_pair_heads(const int64_t* mirror, int64_t num_links, int64_t* head_code, 
     return e == cudaSuccess ? S3_OK : cuda_fail(e);
 }
 
-int s3_scatter_rows(float* const* src, int64_t ld_src, const int64_t* src_row_ptr, int64_t num_records, const int64_t* link_idx,
-                    int64_t link_base, const int64_t* mirror, const int64_t* dst_row_ptr, float* const* dst, int64_t ld_dst,
-                    int32_t num_ops, int64_t num_cols, void* stream) {
+int s3_scatter_rows_lead(float* const* src, int64_t ld_src, const int64_t* src_row_ptr, int64_t num_records, const int64_t* link_idx,
+                         int64_t link_base, const int64_t* mirror, const int64_t* dst_row_ptr, float* const* dst, int64_t ld_dst,
+                         int32_t num_ops, int64_t num_cols, int32_t lead_rows, void* stream) {
     if (num_records < 0 || num_ops < 1 || num_ops > 2 * S3_MAX_K || num_cols < 1 || num_cols > INT32_MAX || ld_src < num_cols ||
-        ld_dst < num_cols || link_base < 0 || num_records > INT32_MAX)
+        ld_dst < num_cols || link_base < 0 || num_records > INT32_MAX || lead_rows < 0 || lead_rows > 2)
         return S3_ERR_INVALID_ARG;
     if (num_records == 0) return S3_OK;
     if (!src || !dst || !src_row_ptr || !dst_row_ptr) return S3_ERR_INVALID_ARG;
@@ -246,8 +246,15 @@ int s3_scatter_rows(float* const* src, int64_t ld_src, const int64_t* src_row_pt
         b.p[k] = dst[k];
     }
     cudaError_t e = s3::launch_scatter_rows(a, ld_src, src_row_ptr, num_records, link_idx, link_base, mirror, dst_row_ptr, b, ld_dst,
-                                            num_ops, num_cols, static_cast<cudaStream_t>(stream));
+                                            num_ops, num_cols, static_cast<cudaStream_t>(stream), lead_rows);
     return e == cudaSuccess ? S3_OK : cuda_fail(e);
+}
+
+int s3_scatter_rows(float* const* src, int64_t ld_src, const int64_t* src_row_ptr, int64_t num_records, const int64_t* link_idx,
+                    int64_t link_base, const int64_t* mirror, const int64_t* dst_row_ptr, float* const* dst, int64_t ld_dst,
+                    int32_t num_ops, int64_t num_cols, void* stream) {
+    return s3_scatter_rows_lead(src, ld_src, src_row_ptr, num_records, link_idx, link_base, mirror, dst_row_ptr, dst, ld_dst, num_ops,
+                                num_cols, 0, stream);
 }
 
 int s3_segment_pool(const float* src, int64_t ld_src, int64_t num_cols, const int64_t* row_ptr, int64_t num_links, int32_t mode,

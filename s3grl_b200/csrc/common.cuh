@@ -223,7 +223,7 @@ cudaError_t launch_pair_links(const int64_t* src, const int64_t* dst, int64_t L,
 cudaError_t launch_pair_heads(const int64_t* mirror, int64_t L, int64_t* head_code, cudaStream_t st);
 cudaError_t launch_scatter_rows(const OutPtrs& src, int64_t ld_src, const int64_t* src_row_ptr, int64_t num_records,
                                 const int64_t* link_idx, int64_t link_base, const int64_t* mirror, const int64_t* dst_row_ptr,
-                                const OutPtrs& dst, int64_t ld_dst, int num_ops, int64_t cols, cudaStream_t st);
+                                const OutPtrs& dst, int64_t ld_dst, int num_ops, int64_t cols, cudaStream_t st, int lead = 0);
 cudaError_t launch_segment_pool(const float* src, int64_t ld, int64_t cols, const int64_t* row_ptr, int64_t num_links, int mode,
                                 int layout, float* out, int64_t ld_out, cudaStream_t st);
 cudaError_t launch_probe_l2_read(const float* buf, int64_t bytes, int iters, float* sink, int ctas, cudaStream_t st);

@@ -43,7 +43,11 @@ struct ScatterParams {
     int64_t link_base;
     const long long* __restrict__ mirror;     // chain table over the whole link list, or null
     const int64_t* __restrict__ dst_row_ptr;  // [links + 1] rows of the collated output
+    int lead;  // the record's first `lead` rows are written a second time in front of its rows (s3_scatter_rows_lead)
 };
+
+// one record's rows at destination row d0: [its first `lead` rows again |] its s rows
+__device__ __forceinline__ void place_record(const ScatterParams& p, int64_t s0, int s, int64_t d0, bool swap);
 
 __device__ __forceinline__ void copy_rows(const ScatterParams& p, int64_t s0, int s, int64_t d0, bool swap) {
     const int tid = threadIdx.x, cols = p.cols;
@@ -75,17 +79,23 @@ __device__ __forceinline__ void copy_rows(const ScatterParams& p, int64_t s0, in
     }
 }
 
+__device__ __forceinline__ void place_record(const ScatterParams& p, int64_t s0, int s, int64_t d0, bool swap) {
+    const int lead = min(p.lead, s);
+    if (lead > 0) copy_rows(p, s0, lead, d0, swap);
+    copy_rows(p, s0, s, d0 + lead, swap);
+}
+
 __global__ void __launch_bounds__(kScatterThreads) scatter_rows_kernel(ScatterParams p) {
     const int64_t r = blockIdx.x;
     const int64_t s0 = p.src_row_ptr[r];
     const int s = (int)(p.src_row_ptr[r + 1] - s0);
     if (s <= 0) return;
     const int64_t link = p.link_idx ? p.link_idx[r] : p.link_base + r;
-    copy_rows(p, s0, s, p.dst_row_ptr[link], false);
+    place_record(p, s0, s, p.dst_row_ptr[link], false);
     if (!p.mirror) return;
     for (long long m = p.mirror[link]; m >= 0;) {
         const long long enc = -2 - p.mirror[m];
-        copy_rows(p, s0, s, p.dst_row_ptr[m], (enc & 1) != 0);
+        place_record(p, s0, s, p.dst_row_ptr[m], (enc & 1) != 0);
         m = (enc >> 1) - 1;
     }
 }
@@ -101,7 +111,7 @@ cudaError_t launch_pair_heads(const int64_t* mirror, int64_t L, int64_t* head_co
 
 cudaError_t launch_scatter_rows(const OutPtrs& src, int64_t ld_src, const int64_t* src_row_ptr, int64_t num_records,
                                 const int64_t* link_idx, int64_t link_base, const int64_t* mirror, const int64_t* dst_row_ptr,
-                                const OutPtrs& dst, int64_t ld_dst, int num_ops, int64_t cols, cudaStream_t st) {
+                                const OutPtrs& dst, int64_t ld_dst, int num_ops, int64_t cols, cudaStream_t st, int lead) {
     if (num_records == 0) return cudaSuccess;
     if (num_records > 0x7fffffff) return cudaErrorInvalidValue;
     ScatterParams p;
@@ -116,6 +126,7 @@ cudaError_t launch_scatter_rows(const OutPtrs& src, int64_t ld_src, const int64_
     p.link_base = link_base;
     p.mirror = reinterpret_cast<const long long*>(mirror);
     p.dst_row_ptr = dst_row_ptr;
+    p.lead = lead;
     scatter_rows_kernel<<<(unsigned)num_records, kScatterThreads, 0, st>>>(p);
     return cudaGetLastError();
 }

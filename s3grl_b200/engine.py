@@ -264,9 +264,12 @@ class _Call:
     def __init__(self, graph, links, num_hops, sign_k, flow, strategy, batch_records, out, return_graphs,
                  arena_words, stream, profile, overlap, host_out, force_sorted_tier, walk=None, ccn_mode=None,
                  pair=True, out_link=None, mirror=None, peers=None, ratio_per_hop=1.0, max_nodes_per_hop=None, cap_seed=0,
-                 fronts_first=False):
+                 fronts_first=False, compat_explicit_zero=False):
         self.lib = L.lib()
         self.fronts_first = bool(fronts_first)
+        self.compat_explicit_zero = bool(compat_explicit_zero)
+        if self.compat_explicit_zero and not (flow == 'PoS' and strategy == 'union'):
+            raise ValueError("compat_explicit_zero only changes the PoS Plus union row selection")
         # per-hop caps of the BFS (reference utils.py:66-70) with the deterministic rank rule of include/s3grl_b200.h
         self.cap_ratio = 1.0 if ratio_per_hop is None else float(ratio_per_hop)
         self.cap_max = 0 if max_nodes_per_hop is None else int(max_nodes_per_hop)
@@ -782,12 +785,17 @@ class _Call:
                 n_links = int((torch.cat(self._rec_n) * served).sum()) if self._rec_n else 0
                 self.stats['sum_d_links'] = int(self.stats['sum_d'] * n_links / max(1, self.stats['sum_n']))
                 self.stats['sum_n_links'] = n_links
+            # compat_explicit_zero: the reference's literal union selects src and dst a second time; the
+            # collate below writes rows 0 / 1 of every record twice — [0, 1, 0, 1, CCN rows] — nothing is recomputed
+            lead = 2 if self.compat_explicit_zero else 0
+            if lead:
+                counts = counts + lead
             row_ptr = torch.zeros(Lk + 1, dtype=torch.int64, device=dev)
             torch.cumsum(counts, 0, out=row_ptr[1:])
             self.stats['rows_computed'] = sum(int(p[0].shape[0]) for p in self.pieces)   # without the paired links' copies
             if not self.pieces:
                 xs = [torch.empty((0, F1), dtype=torch.float32, device=dev) for _ in range(K + 1)]
-            elif len(self.pieces) == 1 and head_idx is None:
+            elif len(self.pieces) == 1 and head_idx is None and not lead:
                 xs = self.pieces[0]
             else:
                 # collate: every batch's piece placed (and, with pairing, replicated) by s3_scatter_rows
@@ -799,9 +807,9 @@ class _Call:
                     prp = torch.zeros(b1 - b0 + 1, dtype=torch.int64, device=dev)
                     torch.cumsum(self.row_counts[bi], 0, out=prp[1:])
                     src = (C.c_void_p * (K + 1))(*[o.data_ptr() for o in piece])
-                    self.launch('collate', bi, 's3_scatter_rows', src, F1, _ptr(prp), b1 - b0,
+                    self.launch('collate', bi, 's3_scatter_rows_lead', src, F1, _ptr(prp), b1 - b0,
                                 _ptr(head_idx[b0:b1]) if head_idx is not None else None, b0, _ptr(var_mirror), _ptr(row_ptr),
-                                dst, F1, K + 1, F1, self.stream_ptr)
+                                dst, F1, K + 1, F1, lead, self.stream_ptr)
                     self.stats['launches'] += 1
                     self._keep_var = getattr(self, '_keep_var', []) + [prp]
                 self.pieces = []
@@ -813,7 +821,8 @@ class _Call:
 def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_records=None, out=None,
                return_graphs=False, arena_words=None, stream=None, profile=None, overlap=False, defer=False,
                host_out=None, force_sorted_tier=False, walk=None, ccn_mode=None, pair=True, out_link=None, mirror=None,
-               peers=None, ratio_per_hop=1.0, max_nodes_per_hop=None, cap_seed=0, fronts_first=False):
+               peers=None, ratio_per_hop=1.0, max_nodes_per_hop=None, cap_seed=0, fronts_first=False,
+               compat_explicit_zero=False):
     """Run the hot path for `links` ([2, L] int64, host or device) on `graph`; returns a
     PrecomputeResult with device tensors.
 
@@ -847,6 +856,12 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
                    them with random.sample (no reproducible semantics, raises on Python >= 3.11); here they are the
                    nodes with the smallest fmix32(node ^ cap_seed), so a subgraph depends on (link, seed) only and
                    the oracle restates it exactly.  Ignored by SoP and by ScaLed walk subgraphs, as in the reference.
+    compat_explicit_zero   PoS Plus union only.  False (default, what is benchmarked): the paper's selection
+                   [0, 1] + (N(0) ∪ N(1)) − {0, 1}.  True: the code-literal selection of the reference with its ragged
+                   label-column literal (tuned_SIGN.py:243) repaired — its target-link mask leaves explicit zeros that
+                   `neighbors` reports, so src and dst are selected a second time: every link gets the rows
+                   [0, 1, 0, 1, CCN rows] (the reference's own order of the rows beyond the first two is CPython set order).
+                   Pinned by tests/golden/ref_*_union*.npz, which hold the literal rows.
     out_link, mirror, peers   used by parallel.precompute_exchange: `links` is a subset of a larger list, out_link
                    its global link indices, mirror the chain table of the whole list and peers the PeerBuffers every
                    output row is stored into (this GPU's and its NVLink peers').
@@ -854,7 +869,7 @@ def precompute(graph, links, num_hops, sign_k, flow='PoS', strategy=None, batch_
     strategy (as reference tuned_SIGN.py:235) or an unsupported combination."""
     call = _Call(graph, links, num_hops, sign_k, flow, strategy, batch_records, out, return_graphs, arena_words,
                  stream, profile, overlap, host_out, force_sorted_tier, walk, ccn_mode, pair, out_link, mirror, peers,
-                 ratio_per_hop, max_nodes_per_hop, cap_seed, fronts_first)
+                 ratio_per_hop, max_nodes_per_hop, cap_seed, fronts_first, compat_explicit_zero)
     return call.run(defer)
 
 

@@ -123,7 +123,9 @@ class OptimizedSignOperations:
     def get_PoS_Plus_prepped_ds(link_index, num_hops, A, ratio_per_hop, max_nodes_per_hop, directed, A_csc, x, y,
                                 sign_kwargs, rw_kwargs, *, device=None, output_device=None, graph=None, cap_seed=None):
         """reference tuned_SIGN.py:192-262.  `union` follows the paper semantics
-        sel = [0,1] + sorted((N(0) ∪ N(1)) − {0,1}) (the reference raises for it)."""
+        sel = [0,1] + sorted((N(0) ∪ N(1)) − {0,1}); the reference raises for it (a ragged literal at :243) and, with
+        that literal repaired, selects src and dst a second time — `sign_kwargs['compat_explicit_zero'] = True` reproduces
+        those rows ([0, 1, 0, 1, CCN rows]; SURVEY A.4, engine.precompute)."""
         caps = _caps(ratio_per_hop, max_nodes_per_hop, directed, cap_seed)
         assert x is not None                       # reference tuned_SIGN.py:221
         if rw_kwargs and rw_kwargs.get('rw_m'):
@@ -132,8 +134,9 @@ class OptimizedSignOperations:
         if strat not in ('union', 'intersection'):
             raise NotImplementedError(f"check strat {strat}")      # reference tuned_SIGN.py:235
         g = device_graph(A, x, device, graph)
-        return _finish(precompute(g, link_index, num_hops, sign_kwargs['sign_k'], flow='PoS', strategy=strat, **caps), y,
-                       output_device=output_device)
+        compat = bool(sign_kwargs.get('compat_explicit_zero', False)) and strat == 'union'
+        return _finish(precompute(g, link_index, num_hops, sign_kwargs['sign_k'], flow='PoS', strategy=strat,
+                                  compat_explicit_zero=compat, **caps), y, output_device=output_device)
 
     @staticmethod
     def get_PoS_full_ds(link_index, num_hops, A, ratio_per_hop, max_nodes_per_hop, directed, A_csc, x, y,

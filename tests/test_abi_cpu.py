@@ -164,6 +164,9 @@ def test_argument_validation_of_the_round2_entry_points(lib):
     assert lib.s3_scatter_rows(arr, 5, None, 2, None, 0, None, P(16), arr, 5, 4, 5, None) == L.S3_ERR_INVALID_ARG    # no row_ptr
     assert lib.s3_scatter_rows(arr, 5, P(16), 2, None, 0, None, P(16), arr, 5, 0, 5, None) == L.S3_ERR_INVALID_ARG   # no operators
     assert lib.s3_scatter_rows(arr, 5, P(16), 2, None, -1, None, P(16), arr, 5, 4, 5, None) == L.S3_ERR_INVALID_ARG
+    assert lib.s3_scatter_rows_lead(arr, 5, P(16), 0, None, 0, None, P(16), arr, 5, 4, 5, 2, None) == L.S3_OK
+    assert lib.s3_scatter_rows_lead(arr, 5, P(16), 2, None, 0, None, P(16), arr, 5, 4, 5, 3, None) == L.S3_ERR_INVALID_ARG   # lead_rows > 2
+    assert lib.s3_scatter_rows_lead(arr, 5, P(16), 2, None, 0, None, P(16), arr, 5, 4, 5, -1, None) == L.S3_ERR_INVALID_ARG
 
 
 def test_chain_placement_by_record_size(lib):

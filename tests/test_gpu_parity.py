@@ -606,6 +606,45 @@ def test_scatter_rows_entry_point():
             if code_h[i] & 1:
                 rows[[0, 1]] = rows[[1, 0]]
             assert np.array_equal(got[frp[i]:frp[i + 1]], rows), (k, i)
+    # s3_scatter_rows_lead: rows 0 / 1 of every record written a second time in front (compat_explicit_zero layout)
+    frp2 = frp + 2 * np.arange(Lk + 1)
+    dst2 = [torch.zeros((int(frp2[-1]), cols), dtype=torch.float32, device='cuda') for _ in range(ops)]
+    dp2 = (C.c_void_p * ops)(*[t.data_ptr() for t in dst2])
+    t_frp2 = torch.from_numpy(frp2).cuda()
+    L.check(lib.s3_scatter_rows_lead(sp, cols, C.c_void_p(t_prp.data_ptr()), heads.size, C.c_void_p(t_heads.data_ptr()), 0,
+                                     C.c_void_p(mirror.data_ptr()), C.c_void_p(t_frp2.data_ptr()), dp2, cols, ops, cols, 2, st),
+            's3_scatter_rows_lead')
+    for k in range(ops):
+        got, ref = dst2[k].cpu().numpy(), dst[k].cpu().numpy()
+        for i in range(Lk):
+            rows = ref[frp[i]:frp[i + 1]]
+            assert np.array_equal(got[frp2[i]:frp2[i + 1]], np.concatenate([rows[:2], rows])), (k, i)
+
+
+@pytest.mark.parametrize('name', [n for n in case_names('pos') if 'union' in n])
+def test_union_compat_explicit_zero_reproduces_the_literal_reference_rows(name):
+    """with compat_explicit_zero the union rows are the code-literal ones of the reference (its label-column
+    literal repaired, oracle/ref_runner.union_typo_repaired) — src and dst selected a second time.  The fixtures hold the
+    literal rows with the extra rows in ascending global id; the framework writes [0, 1, 0, 1, CCN rows]."""
+    c = Case(name)
+    g = DeviceGraph(c.A, c.X)
+    for pair in (True, False):
+        res = precompute(g, c.links, c.num_hops, c.K, 'PoS', 'union', compat_explicit_zero=True, pair=pair)
+        rp = res.row_ptr.cpu().numpy()
+        assert np.array_equal(rp, c.literal_row_ptr)
+        for i in range(c.L):
+            a, b = int(rp[i]), int(rp[i + 1])
+            gid = c.row_gid[c.row_ptr[i]:c.row_ptr[i + 1]]                      # framework selection: src, dst, CCN ascending
+            gid = np.concatenate([gid[:2], gid[:2], gid[2:]])
+            order = np.concatenate([[0, 1], 2 + np.argsort(gid[2:], kind='stable')])
+            assert np.array_equal(gid[order], c.literal_row_gid[a:b])
+            for k in range(c.K + 1):
+                got = res.xs[k][a:b].cpu().numpy()[order]
+                assert_features_close(got, c.literal_xs[k][a:b], what=f'{name} link {i} x{k} (pair={pair})')
+    plain = precompute(g, c.links, c.num_hops, c.K, 'PoS', 'union')
+    assert np.array_equal(plain.row_ptr.cpu().numpy(), c.row_ptr)
+    with pytest.raises(ValueError):
+        precompute(g, c.links, c.num_hops, c.K, 'PoS', 'intersection', compat_explicit_zero=True)
 
 
 def test_empty_inputs_on_every_entry_point():
