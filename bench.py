@@ -540,7 +540,9 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
                       sign_full="HBM writes",
                       collate="HBM copy (placement of the batches' pieces, replication of paired links' rows)",
                       ccn_chain="shared-memory bandwidth: every induced edge of a level reads one row segment of the previous "
-                                "level's [n][CW] buffer (DESIGN.md section 4); X is L2-resident on PubMed")
+                                "level's [n][CW] buffer (DESIGN.md section 4); X is L2-resident on PubMed; the records that would "
+                                "run at CW <= 8 keep their buffers in a global-memory pool and read them through L2 instead "
+                                "(s3_ccn_chain_pooled) — the same row segments, counted in the same figure")
     kernels = {}
     for stage, v in stage_ms.items():
         tot = float(np.sum(v))
@@ -562,6 +564,9 @@ def measure(args, w, wname, steps, warmup, dev, rank, world, want_e2e, ceilings,
             k['smem_peak_GBps'] = smem_peak
             k['frac_of_smem_peak'] = k['smem_GBps'] / smem_peak
             k['smem_peak_source'] = "128 B/clk/SM (B300_MICROARCH.md, LDS crossbar) x SMs x max SM clock; conflict-free"
+            if ceilings and ceilings.get('l2_read_GBps'):       # the pooled records' segments come from L2: second ceiling
+                k['l2_read_ceiling_GBps'] = ceilings['l2_read_GBps']
+                k['frac_of_l2_read_ceiling'] = k['smem_GBps'] / ceilings['l2_read_GBps']
             k['records_chained'] = st.get('chain_records')
             k['mean_n_chained'] = st['chain_n'] / max(1, st.get('chain_records') or 1)
         if stage == 'gather' and tot > 0 and ceilings:

@@ -280,6 +280,14 @@ int s3_gather_ccn(const s3_graph* g, const s3_batch* b, int64_t num_items,
  * and s3_gather on the same stream; one CTA per record. replaces tuned_SIGN.py:210-258 for the extra rows. */
 int s3_ccn_chain(const s3_graph* g, const s3_batch* b, int64_t num_records, float* const* out, int64_t ldo,
                  int64_t row_base, void* stream);
+/* s3_ccn_chain with a caller-owned pool for the large records: a record whose shared-memory placement would run at a
+ * sub-chunk width CW <= pool_cw (4, 8, 16 or 32: s3_chain_shape & 255) keeps its CSR in shared memory and takes its two
+ * [n][32] operator buffers from one of pool_slots slots of slot_floats floats each (a slot serves records with
+ * 64 * n <= slot_floats; slot_floats a multiple of 32; pool 128-byte aligned), read and written through L2. pool_busy
+ * [pool_slots] int32 must be zero on entry and is zero again when the kernels have finished. pool_slots == 0: s3_ccn_chain. */
+int s3_ccn_chain_pooled(const s3_graph* g, const s3_batch* b, int64_t num_records, float* const* out, int64_t ldo,
+                        int64_t row_base, float* pool, int32_t* pool_busy, int64_t slot_floats, int32_t pool_slots,
+                        int32_t pool_cw, void* stream);
 /* Placement of a record in s3_ccn_chain by its size (n nodes, m directed induced edges, n1 nodes of hop <= 1):
  * -1 if the record does not fit the chain's shared memory (it takes the CCN work items), else
  * columns_per_sub_chunk | cta_class << 8 with cta_class 0 / 1 / 2 = 256 / 512 / 1024 threads. Host-side helper

@@ -25,7 +25,7 @@ CTR_CHAIN_READS, CTR_CHAIN_RECORDS, CTR_CHAIN_N = 12, 13, 14
 
 EXPORTS = ['s3_version', 's3_error_string', 's3_last_cuda_error', 's3_num_records', 's3_extract_smem_bytes',
            's3_min_arena_words', 's3_extract_tier',
-           's3_extract', 's3_plan', 's3_plan_items', 's3_diffuse', 's3_gather', 's3_gather_ccn', 's3_ccn_chain', 's3_chain_shape', 's3_plan_full', 's3_sign_full', 's3_joint_rows', 's3_sign_head', 's3_walk_sets', 's3_dump_edges',
+           's3_extract', 's3_plan', 's3_plan_items', 's3_diffuse', 's3_gather', 's3_gather_ccn', 's3_ccn_chain', 's3_ccn_chain_pooled', 's3_chain_shape', 's3_plan_full', 's3_sign_full', 's3_joint_rows', 's3_sign_head', 's3_walk_sets', 's3_dump_edges',
            's3_pair_table_slots', 's3_pair_links', 's3_pair_heads', 's3_scatter_rows', 's3_scatter_rows_lead', 's3_gather_peers', 's3_fill_x0', 's3_fill_mirrors', 's3_peer_alloc', 's3_peer_free', 's3_peer_export',
            's3_peer_open', 's3_peer_close', 's3_probe_l2_read', 's3_probe_fma', 's3_probe_fma2', 's3_segment_pool', 's3_negative_candidates', 's3_build_hub_bits', 's3_node_proxy']
 
@@ -89,6 +89,7 @@ def lib():
                                 C.c_int64, C.c_int64, C.c_void_p]
         L.s3_gather_ccn.argtypes = L.s3_gather.argtypes
         L.s3_ccn_chain.argtypes = L.s3_gather.argtypes
+        L.s3_ccn_chain_pooled.argtypes = L.s3_gather.argtypes[:-1] + [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
         L.s3_chain_shape.argtypes = [C.c_int64, C.c_int64, C.c_int64]
         L.s3_chain_shape.restype = C.c_int
         L.s3_joint_rows.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
@@ -128,7 +129,7 @@ def lib():
         L.s3_peer_export.argtypes = [C.c_void_p, C.c_char_p]
         L.s3_peer_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
         L.s3_peer_close.argtypes = [C.c_void_p]
-        for fn in ('s3_extract', 's3_plan', 's3_plan_items', 's3_diffuse', 's3_gather', 's3_gather_ccn', 's3_ccn_chain', 's3_plan_full', 's3_sign_full', 's3_joint_rows', 's3_sign_head', 's3_walk_sets',
+        for fn in ('s3_extract', 's3_plan', 's3_plan_items', 's3_diffuse', 's3_gather', 's3_gather_ccn', 's3_ccn_chain', 's3_ccn_chain_pooled', 's3_plan_full', 's3_sign_full', 's3_joint_rows', 's3_sign_head', 's3_walk_sets',
                    's3_dump_edges', 's3_pair_links', 's3_pair_heads', 's3_scatter_rows', 's3_scatter_rows_lead', 's3_gather_peers', 's3_fill_x0', 's3_fill_mirrors', 's3_peer_alloc', 's3_peer_free', 's3_peer_export',
                    's3_peer_open', 's3_peer_close', 's3_probe_l2_read', 's3_probe_fma', 's3_probe_fma2', 's3_segment_pool', 's3_negative_candidates', 's3_build_hub_bits', 's3_node_proxy'):
             getattr(L, fn).restype = C.c_int

@@ -348,22 +348,30 @@ int s3_peer_close(void* ptr) {
     return e == cudaSuccess ? S3_OK : cuda_fail(e);
 }
 
-int s3_ccn_chain(const s3_graph* g, const s3_batch* b, int64_t num_records, float* const* out, int64_t ldo, int64_t row_base,
-                 void* stream) {
+int s3_ccn_chain_pooled(const s3_graph* g, const s3_batch* b, int64_t num_records, float* const* out, int64_t ldo, int64_t row_base,
+                        float* pool, int32_t* pool_busy, int64_t slot_floats, int32_t pool_slots, int32_t pool_cw, void* stream) {
     int rc = check_graph(g, true);
     if (rc != S3_OK) return rc;
     rc = check_batch(b);
     if (rc != S3_OK) return rc;
     if (b->flow != S3_FLOW_POS || b->strategy != S3_STRATEGY_UNION) return S3_ERR_NOT_IMPLEMENTED;
     if (num_records < 0 || !out || !b->row_ptr || ldo < g->num_feat + 1 || row_base < 0) return S3_ERR_INVALID_ARG;
+    if (pool_slots < 0 || (pool_slots > 0 && (!pool || !pool_busy || slot_floats < 64 || (slot_floats & 31) || pool_cw < 4 || pool_cw > 32)))
+        return S3_ERR_INVALID_ARG;
     s3::OutPtrs o;
     memset(&o, 0, sizeof(o));
     for (int k = 0; k <= b->sign_k; ++k) {
         if (!out[k]) return S3_ERR_INVALID_ARG;
         o.p[k] = out[k];
     }
-    cudaError_t e = s3::launch_ccn_chain(*g, *b, num_records, o, ldo, row_base, static_cast<cudaStream_t>(stream));
+    cudaError_t e = s3::launch_ccn_chain(*g, *b, num_records, o, ldo, row_base, static_cast<cudaStream_t>(stream), pool, pool_busy,
+                                         slot_floats, pool_slots, pool_cw);
     return e == cudaSuccess ? S3_OK : cuda_fail(e);
+}
+
+int s3_ccn_chain(const s3_graph* g, const s3_batch* b, int64_t num_records, float* const* out, int64_t ldo, int64_t row_base,
+                 void* stream) {
+    return s3_ccn_chain_pooled(g, b, num_records, out, ldo, row_base, nullptr, nullptr, 0, 0, 0, stream);
 }
 
 int s3_chain_shape(int64_t n, int64_t m, int64_t n1) {

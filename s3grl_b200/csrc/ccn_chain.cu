@@ -28,7 +28,15 @@
 //    Records are classed by the shared memory they need: CW = 32 wherever it fits (a 128-byte row segment per
 //    quarter warp is bank-conflict free; 64-byte segments conflict 1.5x, 32-byte ones 2.1x on random rows), in
 //    256-thread CTAs (<= 54 KB, 4 per SM), 512 (<= 110 KB, 2 per SM) or 1024 (<= 222 KB); then CW = 16 / 8 / 4
-//    in 1024-thread CTAs. Records beyond that (n > ~4 000) keep the work-item path (s3_plan counts their items).
+//    in 1024-thread CTAs. Records beyond that (n > ~4 000) keep their CSR in shared memory and the two buffers in the
+//    float scratch of their work items ("spill" class, CW = 32, global memory).
+//  * pooled route (s3_ccn_chain_pooled, third session of round 2): records that would run at CW <= pool_cw in shared
+//    memory (default 8: n > ~1 700, 21 % of PubMed's records with 73 % of the traffic) run the spill kernel instead with
+//    their two [n][32] buffers in a slot of a caller-owned pool — 16 sub-chunks with 128-byte row segments (no bank
+//    conflicts, 4-8x fewer barriers and fills) against 63-126, paid for with L2 latency. The launch is split by the
+//    shared memory the CSR needs (54 / 110 / 222 KB) so that what is left of the SM's 256 KB serves the pool as L1.
+//    Measured on the PubMed union step (chain ms): all in shared memory 356, pool_cw 8: 322 (319 with the split),
+//    16: 338, 32: 447 (398 with the split) — profiles/README.md.
 //
 // Sums run in a fixed order per record (slot order inside a lane group, fixed shuffle tree for warp-wide rows):
 // results do not depend on scheduling, batch composition or slab count. Rows 0 and 1 of every record still
@@ -58,7 +66,18 @@ struct ChainParams {
     int sign_k, strategy, flags, policy, cls;
     OutPtrs out;
     int64_t ldo, row_base;
+    // pooled route (s3_ccn_chain_pooled): records whose shared-memory placement would run at CW <= pool_cw keep their CSR in
+    // shared memory and take two [n][32] operator buffers from a slot of a caller-owned global pool (read through L2 / L1)
+    float* pool;
+    int* pool_busy;  // [pool_slots] 0 = free
+    int64_t slot_floats;
+    int pool_slots, pool_cw;
+    int pool_split;  // pooled records run in the smallest of 1: {110, 222} KB / 2: {54, 110, 222} KB launches that holds their CSR
 };
+
+__device__ __forceinline__ bool chain_pooled(const ChainParams& p, int n, int cw) {
+    return p.pool != nullptr && cw <= p.pool_cw && 64 * (int64_t)n <= p.slot_floats;
+}
 
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float4 f4_scale(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
@@ -415,13 +434,24 @@ __global__ void __launch_bounds__(T, 1024 / T) chain_kernel(ChainParams p) {
     if (s <= 2) return;  // no CCN rows
     // records that fit neither placement keep the work-item path (s3_plan counted their items)
     int cw = 32;
+    bool pooled = false;
     if (SPILL) {
-        if (!chain_spill_eligible(p.flags, p.strategy, n, m, n1, s, p.sign_k)) return;
+        if (!chain_spill_eligible(p.flags, p.strategy, n, m, n1, s, p.sign_k)) {
+            if (!chain_eligible(p.flags, p.strategy, n, m, n1) || !chain_pooled(p, n, chain_shape(n, m, n1, p.policy) & 255)) return;
+            pooled = true;
+            // the smallest launch whose shared memory holds the record's CSR: what it leaves of the 256 KB is L1 for the pool
+            const int64_t need = 4 * (3 * (int64_t)n + n1 + (m + 2) / 2 + 8);
+            const int target = (p.pool_split >= 2 && need <= chain_class_bytes(0)) ? 5 : ((p.pool_split >= 1 && need <= chain_class_bytes(1)) ? 4 : 3);
+            if (target != p.cls) return;  // served by another pooled launch
+        } else if (p.cls != 3) {
+            return;
+        }
     } else {
         if (!chain_eligible(p.flags, p.strategy, n, m, n1)) return;
         const int shape = chain_shape(n, m, n1, p.policy);
         if ((shape >> 8) != p.cls) return;  // served by the launch of another CTA size
         cw = shape & 255;
+        if (chain_pooled(p, n, cw)) return;  // served by the pooled launch
     }
     // column slab of this CTA
     const int nchunks = p.F / cw + 1;  // chain columns 0..F
@@ -439,6 +469,20 @@ __global__ void __launch_bounds__(T, 1024 / T) chain_kernel(ChainParams p) {
     // behind the record's own work item in its float scratch (128-byte aligned, 2 * n * 32 floats)
     float4* buf0 = SPILL ? reinterpret_cast<float4*>(p.arena + off[S3_OFF_F32] + item_words(S3_FLOW_POS, p.sign_k, n))
                          : reinterpret_cast<float4*>(s_dyn);
+    __shared__ int s_slot;
+    if (SPILL && pooled) {
+        // a free slot of the pool, starting from this SM's own pair (the spill launch holds one CTA per SM, so the first try
+        // succeeds and a slot's lines stay in the L2 partition of the SM that keeps using it)
+        if (tid == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            int slot = (int)((2u * smid) % (unsigned)p.pool_slots);
+            while (atomicCAS(&p.pool_busy[slot], 0, 1) != 0) slot = slot + 1 == p.pool_slots ? 0 : slot + 1;
+            s_slot = slot;
+        }
+        __syncthreads();
+        buf0 = reinterpret_cast<float4*>(p.pool + (int64_t)s_slot * p.slot_floats);
+    }
     uint2* meta = SPILL ? reinterpret_cast<uint2*>(s_dyn) : reinterpret_cast<uint2*>(buf0 + 2 * (int64_t)n * (cw / 4));
     float* cdis = reinterpret_cast<float*>(meta + n);
     int* cpos = reinterpret_cast<int*>(cdis + n);
@@ -497,6 +541,10 @@ __global__ void __launch_bounds__(T, 1024 / T) chain_kernel(ChainParams p) {
     else if (cw == 16) chain_columns<16, T>(p, r, buf0, c0, c1);
     else if (cw == 8) chain_columns<8, T>(p, r, buf0, c0, c1);
     else chain_columns<4, T>(p, r, buf0, c0, c1);
+    if (SPILL && pooled) {
+        __syncthreads();  // every thread's last reads of the slot
+        if (tid == 0) atomicExch(&p.pool_busy[s_slot], 0);
+    }
 }
 
 int env_int(const char* name, int dflt, int lo, int hi) {
@@ -509,7 +557,7 @@ int env_int(const char* name, int dflt, int lo, int hi) {
 template <int T, bool SPILL>
 cudaError_t launch_class(const ChainParams& p, int cls, int slabs, cudaStream_t st) {
     static LaunchCache cache;  // the shared-memory opt-in is per device
-    const size_t smem = (size_t)chain_class_bytes(cls);
+    const size_t smem = (size_t)chain_class_bytes(cls == 4 ? 1 : (cls == 5 ? 0 : cls));  // 4 / 5: pooled launches with less shared memory
     cudaError_t e = cache.get(reinterpret_cast<const void*>(chain_kernel<T, SPILL>), T, smem, nullptr, nullptr);
     if (e != cudaSuccess) return e;
     ChainParams q = p;
@@ -521,7 +569,8 @@ cudaError_t launch_class(const ChainParams& p, int cls, int slabs, cudaStream_t 
 }  // namespace
 
 cudaError_t launch_ccn_chain(const s3_graph& g, const s3_batch& b, int64_t num_records, const OutPtrs& out, int64_t ldo,
-                             int64_t row_base, cudaStream_t st) {
+                             int64_t row_base, cudaStream_t st, float* pool, int* pool_busy, int64_t slot_floats, int pool_slots,
+                             int pool_cw) {
     if (num_records == 0) return cudaSuccess;
     if (!b.row_ptr || b.flow != S3_FLOW_POS || b.strategy != S3_STRATEGY_UNION || !(b.flags & S3_BATCH_CCN_CHAIN))
         return cudaErrorInvalidValue;
@@ -542,6 +591,12 @@ cudaError_t launch_ccn_chain(const s3_graph& g, const s3_batch& b, int64_t num_r
     // tuning knobs (A/B runs): which (CW, CTA size) a record gets, and how many CTAs share a record's columns
     p.policy = env_int("S3GRL_CHAIN_POLICY", 0, 0, 2);
     p.cls = 0;
+    p.pool = pool_slots > 0 ? pool : nullptr;
+    p.pool_busy = pool_busy;
+    p.slot_floats = slot_floats;
+    p.pool_slots = pool_slots;
+    p.pool_cw = pool_cw;
+    p.pool_split = 0;
     p.out = out;
     p.ldo = ldo;
     p.row_base = row_base;
@@ -550,8 +605,13 @@ cudaError_t launch_ccn_chain(const s3_graph& g, const s3_batch& b, int64_t num_r
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     // largest CTAs first: their records are the long ones
-    e = launch_class<1024, true>(p, 3, 1, st);  // the few records whose buffers live in global memory: longest of all
+    p.pool_split = p.pool ? env_int("S3GRL_CHAIN_POOL_SPLIT", 2, 0, 2) : 0;
+    e = launch_class<1024, true>(p, 3, 1, st);  // the records whose buffers live in global memory: longest of all
     if (e != cudaSuccess) return e;
+    for (int cls = 4; cls < 4 + p.pool_split; ++cls) {
+        e = launch_class<1024, true>(p, cls, 1, st);
+        if (e != cudaSuccess) return e;
+    }
     e = launch_class<1024, false>(p, 2, slabs, st);
     if (e != cudaSuccess) return e;
     e = launch_class<512, false>(p, 1, slabs, st);

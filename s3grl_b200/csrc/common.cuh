@@ -237,7 +237,8 @@ cudaError_t peer_export(void* ptr, unsigned char* handle);
 cudaError_t peer_open(const unsigned char* handle, void** ptr);
 cudaError_t peer_close(void* ptr);
 cudaError_t launch_ccn_chain(const s3_graph& g, const s3_batch& b, int64_t num_records, const OutPtrs& out, int64_t ldo,
-                             int64_t row_base, cudaStream_t st);
+                             int64_t row_base, cudaStream_t st, float* pool = nullptr, int* pool_busy = nullptr,
+                             int64_t slot_floats = 0, int pool_slots = 0, int pool_cw = 0);
 cudaError_t launch_plan_full(const s3_batch& b, cudaStream_t st);
 cudaError_t launch_sign_full(const s3_graph& g, const s3_batch& b, int64_t num_records, int label, const OutPtrs& out,
                              int64_t ldo, int64_t row_base, int64_t* node_out, cudaStream_t st);

@@ -21,6 +21,10 @@ import torch
 from . import _lib as L
 
 _NVTX = bool(os.environ.get('S3GRL_NVTX'))      # read once at import: NVTX ranges around every kernel launch
+# union chain: records whose shared-memory placement would run at a sub-chunk width <= this (n > ~1 700) take their two
+# operator buffers from a global pool at width 32 instead (s3_ccn_chain_pooled; read through L2).  Measured on the PubMed
+# union step, chain ms: 0 (all in shared memory) 356, 8: 322, 16: 338, 32: 446 (profiles/README.md).  0 switches it off.
+_CHAIN_POOL_CW = int(os.environ.get('S3GRL_CHAIN_POOL_CW', '8') or 0)
 _STRATEGY = {None: L.STRATEGY_NONE, '': L.STRATEGY_NONE, 'intersection': L.STRATEGY_INTERSECTION,
              'union': L.STRATEGY_UNION}
 _FLOW = {'PoS': L.FLOW_POS, 'SoP': L.FLOW_SOP}
@@ -170,6 +174,17 @@ class DeviceGraph:
             cur = torch.empty(int(words), dtype=torch.int32, device=self.device)
             setattr(self, name, cur)
         return cur
+
+    # pool of the union chain's large records (s3_ccn_chain_pooled): two slots per SM, each for two [n][32] buffers of
+    # the largest record the chain serves (n <= 5 200); allocated on first use, kept across calls
+    CHAIN_SLOT_FLOATS = 64 * 5216
+
+    def chain_pool(self):
+        if getattr(self, '_chain_pool', None) is None:
+            slots = 2 * torch.cuda.get_device_properties(self.device).multi_processor_count
+            self._chain_pool = (torch.empty(slots * self.CHAIN_SLOT_FLOATS, dtype=torch.float32, device=self.device),
+                                torch.zeros(slots, dtype=torch.int32, device=self.device), slots)
+        return self._chain_pool
 
     def streams(self):
         if self._streams is None:
@@ -694,7 +709,12 @@ class _Call:
         if self.ccn_chain and rows > 2 * nrec:
             # union: hop-limited SpMM chain over the stored CSR, one CTA per record; records too large for its
             # shared-memory placement were counted as work items by s3_plan and take the path below
-            self.launch('ccn_chain', bi, 's3_ccn_chain', g, C.byref(batch), nrec, ptrs, self.F1, 0, st)
+            if _CHAIN_POOL_CW:
+                pool, busy, slots = self.graph.chain_pool()
+                self.launch('ccn_chain', bi, 's3_ccn_chain_pooled', g, C.byref(batch), nrec, ptrs, self.F1, 0, _ptr(pool), _ptr(busy),
+                            DeviceGraph.CHAIN_SLOT_FLOATS, slots, _CHAIN_POOL_CW, st)
+            else:
+                self.launch('ccn_chain', bi, 's3_ccn_chain', g, C.byref(batch), nrec, ptrs, self.F1, 0, st)
             self.stats['launches'] += 1
         if items:       # CCN rows: extra work items of 2 (intersection) or 8 (union) selected rows each
             L.check(self.lib.s3_plan_items(C.byref(batch), st), 's3_plan_items')

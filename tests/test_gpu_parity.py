@@ -532,6 +532,34 @@ def test_union_chain_matches_work_item_path(N, E, F, h, K, L):
     print(f"N={N}: max_n={a.stats['max_n']} rows={a.stats['rows']}")
 
 
+@pytest.mark.parametrize('pool_cw,split', [(4, 0), (8, 1), (16, 2), (32, 0), (32, 2), (0, 0)])
+@pytest.mark.parametrize('N,E,F,h,K,L', [(2500, 9000, 70, 3, 3, 12), (5000, 40000, 33, 3, 2, 6), (600, 2400, 500, 3, 5, 16),
+                                         (3600, 12000, 9, 4, 3, 5)])
+def test_union_chain_pooled_route(monkeypatch, pool_cw, split, N, E, F, h, K, L):
+    """s3_ccn_chain_pooled: records that would run at a sub-chunk width <= pool_cw in shared memory take two [n][32]
+    buffers from the global pool instead.  Same sums in a different lane-group split for the warp-wide rows: within fp32
+    rounding of the shared-memory route, 1e-5 against the oracle, and independent of the batch composition."""
+    from s3grl_b200 import engine
+    rng = np.random.default_rng(N)
+    A = _random_graph(rng, N, E)
+    X = rng.random((N, F), dtype=np.float32)
+    links = rng.integers(0, N, (2, L))
+    links = links[:, links[0] != links[1]]
+    g = DeviceGraph(A, X)
+    a = precompute(g, links, h, K, 'PoS', 'union')                     # the default threshold
+    monkeypatch.setattr(engine, '_CHAIN_POOL_CW', pool_cw)             # 0: every record in shared memory
+    monkeypatch.setenv('S3GRL_CHAIN_POOL_SPLIT', str(split))           # pooled launches by the shared memory the CSR needs
+    b = precompute(g, links, h, K, 'PoS', 'union')
+    c = precompute(g, links, h, K, 'PoS', 'union', batch_records=5)
+    assert int(g.chain_pool()[1].sum()) == 0                           # every slot released
+    assert torch.equal(b.row_ptr, c.row_ptr) and all(torch.equal(x, y) for x, y in zip(b.xs, c.xs))
+    assert torch.equal(a.row_ptr, b.row_ptr) and torch.equal(a.xs[0], b.xs[0])
+    ref = orc.pos_precompute(links, h, A, X, K, 'union')
+    for k in range(1, K + 1):
+        assert_features_close(b.xs[k].cpu().numpy(), a.xs[k].cpu().numpy(), tol=2e-6, what=f'pooled vs shared x{k}')
+        assert_features_close(b.xs[k].cpu().numpy(), ref['xs'][k], what=f'pooled vs oracle x{k}')
+
+
 @pytest.mark.parametrize('strategy', ['intersection', 'union'])
 def test_pos_plus_pairing_places_both_directions(strategy):
     """PoS Plus with link pairing (csrc/expand.cu): a list holding (u,v), (v,u) and exact repeats runs the path once per
