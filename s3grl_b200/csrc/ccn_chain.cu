@@ -37,6 +37,11 @@
 //    shared memory the CSR needs (54 / 110 / 222 KB) so that what is left of the SM's 256 KB serves the pool as L1.
 //    Measured on the PubMed union step (chain ms): all in shared memory 356, pool_cw 8: 322 (319 with the split),
 //    16: 338, 32: 447 (398 with the split) — profiles/README.md.
+//  * level 1 from the feature matrix (chain_columns_x, default for the records with global-memory buffers): y_0 is not
+//    stored; level 1 forms D^-1/2 [X | label] per neighbour from the graph's X, which is L2-resident and shared by all
+//    CTAs, where a stored y_0 is private to its CTA (148 x 0.3-0.6 MB next to X's 39 MB in a 126 MB L2). No fill phase,
+//    one barrier less per sub-chunk, same bits (the product is rounded before the sum). pool_cw 8: 319 -> 285,
+//    16: 321 -> 280 (default), every record pooled: 330; the same for the shared-memory classes: slower (280 -> 321).
 //
 // Sums run in a fixed order per record (slot order inside a lane group, fixed shuffle tree for warp-wide rows):
 // results do not depend on scheduling, batch composition or slab count. Rows 0 and 1 of every record still
@@ -72,6 +77,8 @@ struct ChainParams {
     int* pool_busy;  // [pool_slots] 0 = free
     int64_t slot_floats;
     int pool_slots, pool_cw;
+    int pool_x;      // 1: the records with buffers in global memory form y_0 from the feature matrix instead of storing it (chain_columns_x)
+    int smem_x;      // 1: so do the records with buffers in shared memory
     int pool_split;  // pooled records run in the smallest of 1: {110, 222} KB / 2: {54, 110, 222} KB launches that holds their CSR
 };
 
@@ -232,25 +239,53 @@ struct ChainRec {
 #endif
 constexpr int kGrabSteps = S3_CHAIN_GRAB;  // warp steps a warp takes from the hand-out counter at once (0: static round robin)
 
+// The previous level's row of local node c, this lane's four columns. FROM_X (level 1 of the pooled route, S3GRL_CHAIN_POOL_X):
+// y_0[c] = D^-1/2 [X | label] is not stored at all but formed from the graph's feature matrix — L2-resident and shared by
+// every record, where a stored y_0 is private to its CTA — with the two roundings the stored value has (the product is
+// rounded before it is added: __fmul_rn is never contracted into an FMA), so both routes give the same bits.
+template <int LPR, bool FROM_X>
+struct PrevRows {
+    const float4* prev;
+    const float* x;
+    const int32_t* nodes;
+    const float* cdis;
+    int64_t ldx;
+    int f0, l, labpos;  // labpos: position of the label column among this lane's four columns, or -1
+    __device__ __forceinline__ float4 operator()(int c) const {
+        if (!FROM_X) return prev[c * LPR + l];
+        float4 v = f4_zero();
+        if (f0 < ldx) v = __ldg(reinterpret_cast<const float4*>(x + (int64_t)__ldg(nodes + c) * ldx + f0));
+        if (labpos >= 0) {
+            const float lab = c < 2 ? 1.0f : 0.0f;  // zero-one label, tuned_SIGN.py:234
+            if (labpos == 0) v.x = lab;
+            else if (labpos == 1) v.y = lab;
+            else if (labpos == 2) v.z = lab;
+            else v.w = lab;
+        }
+        const float dc = cdis[c];
+        return make_float4(__fmul_rn(v.x, dc), __fmul_rn(v.y, dc), __fmul_rn(v.z, dc), __fmul_rn(v.w, dc));
+    }
+};
+
 // D neighbours of one row, D a compile-time bound shared by the rows of the warp step (they are sorted by degree)
-template <int D, int LPR>
-__device__ __forceinline__ float4 row_sum(const float4* prev, const uint16_t* cc, int d, int l) {
+template <int D, class Prev>
+__device__ __forceinline__ float4 row_sum(const Prev& prev, const uint16_t* cc, int d) {
     int c[D];
 #pragma unroll
     for (int t = 0; t < D; ++t) c[t] = t < d ? (int)cc[t] : -1;
     float4 acc = f4_zero();
 #pragma unroll
     for (int t = 0; t < D; ++t)
-        if (c[t] >= 0) acc = f4_add(acc, prev[c[t] * LPR + l]);
+        if (c[t] >= 0) acc = f4_add(acc, prev(c[t]));
     return acc;
 }
 
 // One level for the chain columns [cs, cs + CW): x_k = D^-1/2 (sum over neighbours of y_{k-1}), y_k = D^-1/2 x_k.
 // `next` is null for the last level (k == K), which only writes the output rows.
-template <int CW, int T>
+template <int CW, int T, bool FROM_X = false>
 // (prev / next are NOT __restrict__: in the spill class they are global memory written earlier in the same kernel, which the
 // non-coherent load path a const __restrict__ pointer invites must not serve)
-__device__ __forceinline__ void chain_level(const ChainParams& p, const ChainRec& r, int k, const float4* prev, float4* next, int cs,
+__device__ __forceinline__ void chain_level(const ChainParams& p, const ChainRec& r, int k, const float4* prev_buf, float4* next, int cs,
                                             int* ctr) {
     constexpr int LPR = CW / 4, RPW = 32 / LPR, NWARP = T / 32;
     const unsigned full = 0xffffffffu;
@@ -262,6 +297,15 @@ __device__ __forceinline__ void chain_level(const ChainParams& p, const ChainRec
     const int Rk = r.hop_end[top];
     const bool last = next == nullptr;
     float* outk = p.out.p[k];
+    PrevRows<LPR, FROM_X> prev;
+    prev.prev = prev_buf;
+    prev.x = p.x;
+    prev.nodes = r.nodes;
+    prev.cdis = r.cdis;
+    prev.ldx = p.ldx;
+    prev.f0 = f0;
+    prev.l = l;
+    prev.labpos = (f0 + 3 >= F && f0 <= F) ? F - f0 : -1;
 
     // warp-wide rows: the heavy rows of every hop in range — and every row of the last level (hop <= 1: a few
     // rows whose dependent chains would otherwise leave the SM idle). Edges split over the lane groups.
@@ -276,7 +320,7 @@ __device__ __forceinline__ void chain_level(const ChainParams& p, const ChainRec
             const uint16_t* cc = r.ccol + mt.x;
             float4 acc = f4_zero();
 #pragma unroll 2
-            for (int e = sub; e < d; e += RPW) acc = f4_add(acc, prev[(int)cc[e] * LPR + l]);
+            for (int e = sub; e < d; e += RPW) acc = f4_add(acc, prev((int)cc[e]));
 #pragma unroll
             for (int sft = LPR; sft < 32; sft <<= 1) acc = f4_add(acc, f4_shfl_xor(acc, sft));
             if (sub == 0) {
@@ -318,17 +362,17 @@ __device__ __forceinline__ void chain_level(const ChainParams& p, const ChainRec
             float4 acc;
             switch (dmax) {
                 case 0: acc = f4_zero(); break;
-                case 1: acc = row_sum<1, LPR>(prev, cc, d, l); break;
-                case 2: acc = row_sum<2, LPR>(prev, cc, d, l); break;
-                case 3: acc = row_sum<3, LPR>(prev, cc, d, l); break;
-                case 4: acc = row_sum<4, LPR>(prev, cc, d, l); break;
-                case 5: acc = row_sum<5, LPR>(prev, cc, d, l); break;
-                case 6: acc = row_sum<6, LPR>(prev, cc, d, l); break;
-                case 7: acc = row_sum<7, LPR>(prev, cc, d, l); break;
-                case 8: acc = row_sum<8, LPR>(prev, cc, d, l); break;
+                case 1: acc = row_sum<1>(prev, cc, d); break;
+                case 2: acc = row_sum<2>(prev, cc, d); break;
+                case 3: acc = row_sum<3>(prev, cc, d); break;
+                case 4: acc = row_sum<4>(prev, cc, d); break;
+                case 5: acc = row_sum<5>(prev, cc, d); break;
+                case 6: acc = row_sum<6>(prev, cc, d); break;
+                case 7: acc = row_sum<7>(prev, cc, d); break;
+                case 8: acc = row_sum<8>(prev, cc, d); break;
                 default: {
                     acc = f4_zero();
-                    for (int t0 = 0; t0 < dmax; t0 += 4) acc = f4_add(acc, row_sum<4, LPR>(prev, cc + t0, d - t0, l));
+                    for (int t0 = 0; t0 < dmax; t0 += 4) acc = f4_add(acc, row_sum<4>(prev, cc + t0, d - t0));
                 }
             }
             if (act) {
@@ -416,8 +460,59 @@ __device__ __forceinline__ void chain_columns(const ChainParams& p, const ChainR
     }
 }
 
+// The pooled route without a stored y_0 (S3GRL_CHAIN_POOL_X; CW = 32, sign_k >= 2): level 1 forms y_0 on the fly from the
+// graph's feature matrix (PrevRows<.., true>), so a sub-chunk has no fill phase, one barrier less, and the CTA's private
+// footprint in L2 is the two buffers of levels 1.. only. The last level of a sub-chunk still shares a barrier interval
+// with the next sub-chunk's first phase: level 1 writes the buffer that last level does not read.
+template <int CW, int T>
+__device__ __forceinline__ void chain_columns_x(const ChainParams& p, const ChainRec& r, float4* buf0, int c0, int c1) {
+    constexpr int LPR = CW / 4, RPW = 32 / LPR, G = T / LPR;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / LPR, l = lane - sub * LPR;
+    const int g = warp * RPW + sub;
+    const int K = p.sign_k, F = p.F;
+    const int bstride = r.n * LPR;  // float4 per buffer
+    auto buf = [&](int i) -> float4* { return buf0 + (i & 1) * bstride; };
+    if (c0 >= c1) return;
+    int w = 0;   // buffer level 1 of the current sub-chunk writes
+    int lr = 0;  // buffer the last level of the previous sub-chunk reads
+    for (int ci = c0; ci <= c1; ++ci) {
+        const int cs = ci * CW;
+        int* ctr = r.ctr + (ci & 1) * (S3_MAX_K + 1);
+        if (ci < c1) {
+            if (threadIdx.x < S3_MAX_K + 1) r.ctr[((ci + 1) & 1) * (S3_MAX_K + 1) + threadIdx.x] = 0;
+            // operator 0 of the CCN rows: the row itself, [label = 0 | X[node]]
+            const int f0 = cs + 4 * l;
+            for (int j = 2 + g; j < r.n1; j += G) {
+                const int pos = r.cpos[j];
+                if (pos < 0) continue;
+                float4 v = f4_zero();
+                if (f0 < p.ldx) v = __ldg(reinterpret_cast<const float4*>(p.x + (int64_t)r.nodes[j] * p.ldx + f0));
+                if (f0 + 3 >= F && f0 <= F) {
+                    if (f0 == F) v.x = 0.0f;
+                    else if (f0 + 1 == F) v.y = 0.0f;
+                    else if (f0 + 2 == F) v.z = 0.0f;
+                    else v.w = 0.0f;
+                }
+                store_row(p.out.p[0] + (r.orow0 + pos) * p.ldo, f0, F, v);
+            }
+        }
+        if (ci > c0) chain_level<CW, T>(p, r, K, buf(lr), nullptr, cs - CW, nullptr);  // last level of the previous sub-chunk
+        if (ci == c1) break;
+        chain_level<CW, T, true>(p, r, 1, nullptr, buf(w), cs, ctr + 1);
+        __syncthreads();
+        for (int k = 2; k < K; ++k) {
+            chain_level<CW, T>(p, r, k, buf(w ^ (k & 1)), buf(w ^ ((k - 1) & 1)), cs, ctr + k);
+            __syncthreads();
+        }
+        lr = w ^ (K & 1);  // level K reads what level K - 1 wrote: buf(w ^ ((K - 2) & 1))
+        w = lr ^ 1;
+    }
+}
+
 // SPILL: the records of class 3 — operator buffers in the record's global float scratch instead of shared memory
-template <int T, bool SPILL>
+// XR: level 1 from the feature matrix (chain_columns_x) — a separate instantiation, so the code of the other route is untouched
+template <int T, bool SPILL, bool XR>
 __global__ void __launch_bounds__(T, 1024 / T) chain_kernel(ChainParams p) {
     extern __shared__ __align__(16) int s_dyn[];
     __shared__ int s_hop_end[S3_MAX_HOPS + 2];
@@ -537,10 +632,17 @@ __global__ void __launch_bounds__(T, 1024 / T) chain_kernel(ChainParams p) {
     r.nheavy = s_nheavy;
     r.dtab = s_dtab;
     r.ctr = s_ctr;
-    if (cw == 32) chain_columns<32, T>(p, r, buf0, c0, c1);
-    else if (cw == 16) chain_columns<16, T>(p, r, buf0, c0, c1);
-    else if (cw == 8) chain_columns<8, T>(p, r, buf0, c0, c1);
-    else chain_columns<4, T>(p, r, buf0, c0, c1);
+    if (XR) {  // level 1 from the feature matrix, no stored y_0
+        if (cw == 32) chain_columns_x<32, T>(p, r, buf0, c0, c1);
+        else if (cw == 16) chain_columns_x<16, T>(p, r, buf0, c0, c1);
+        else if (cw == 8) chain_columns_x<8, T>(p, r, buf0, c0, c1);
+        else chain_columns_x<4, T>(p, r, buf0, c0, c1);
+    } else {
+        if (cw == 32) chain_columns<32, T>(p, r, buf0, c0, c1);
+        else if (cw == 16) chain_columns<16, T>(p, r, buf0, c0, c1);
+        else if (cw == 8) chain_columns<8, T>(p, r, buf0, c0, c1);
+        else chain_columns<4, T>(p, r, buf0, c0, c1);
+    }
     if (SPILL && pooled) {
         __syncthreads();  // every thread's last reads of the slot
         if (tid == 0) atomicExch(&p.pool_busy[s_slot], 0);
@@ -554,16 +656,22 @@ int env_int(const char* name, int dflt, int lo, int hi) {
     return x < lo ? lo : (x > hi ? hi : x);
 }
 
-template <int T, bool SPILL>
-cudaError_t launch_class(const ChainParams& p, int cls, int slabs, cudaStream_t st) {
+template <int T, bool SPILL, bool XR>
+cudaError_t launch_class_x(const ChainParams& p, int cls, int slabs, cudaStream_t st) {
     static LaunchCache cache;  // the shared-memory opt-in is per device
     const size_t smem = (size_t)chain_class_bytes(cls == 4 ? 1 : (cls == 5 ? 0 : cls));  // 4 / 5: pooled launches with less shared memory
-    cudaError_t e = cache.get(reinterpret_cast<const void*>(chain_kernel<T, SPILL>), T, smem, nullptr, nullptr);
+    cudaError_t e = cache.get(reinterpret_cast<const void*>(chain_kernel<T, SPILL, XR>), T, smem, nullptr, nullptr);
     if (e != cudaSuccess) return e;
     ChainParams q = p;
     q.cls = cls;
-    chain_kernel<T, SPILL><<<dim3((unsigned)p.num_records, (unsigned)slabs), T, smem, st>>>(q);
+    chain_kernel<T, SPILL, XR><<<dim3((unsigned)p.num_records, (unsigned)slabs), T, smem, st>>>(q);
     return cudaGetLastError();
+}
+
+template <int T, bool SPILL>
+cudaError_t launch_class(const ChainParams& p, int cls, int slabs, cudaStream_t st) {
+    const bool xr = p.sign_k >= 2 && (SPILL ? p.pool_x : p.smem_x);
+    return xr ? launch_class_x<T, SPILL, true>(p, cls, slabs, st) : launch_class_x<T, SPILL, false>(p, cls, slabs, st);
 }
 
 }  // namespace
@@ -597,6 +705,8 @@ cudaError_t launch_ccn_chain(const s3_graph& g, const s3_batch& b, int64_t num_r
     p.pool_slots = pool_slots;
     p.pool_cw = pool_cw;
     p.pool_split = 0;
+    p.pool_x = p.pool ? env_int("S3GRL_CHAIN_POOL_X", 1, 0, 1) : 0;
+    p.smem_x = env_int("S3GRL_CHAIN_SMEM_X", 0, 0, 1);
     p.out = out;
     p.ldo = ldo;
     p.row_base = row_base;

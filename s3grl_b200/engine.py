@@ -21,10 +21,11 @@ import torch
 from . import _lib as L
 
 _NVTX = bool(os.environ.get('S3GRL_NVTX'))      # read once at import: NVTX ranges around every kernel launch
-# union chain: records whose shared-memory placement would run at a sub-chunk width <= this (n > ~1 700) take their two
-# operator buffers from a global pool at width 32 instead (s3_ccn_chain_pooled; read through L2).  Measured on the PubMed
-# union step, chain ms: 0 (all in shared memory) 356, 8: 322, 16: 338, 32: 446 (profiles/README.md).  0 switches it off.
-_CHAIN_POOL_CW = int(os.environ.get('S3GRL_CHAIN_POOL_CW', '8') or 0)
+# union chain: records whose shared-memory placement would run at a sub-chunk width <= this (16: n > ~860) take their two
+# operator buffers from a global pool at width 32 instead (s3_ccn_chain_pooled; read through L2) and form y_0 from the
+# feature matrix on the fly.  Measured on the PubMed union step, chain ms: 0 (all in shared memory) 356, 8: 285, 16: 280,
+# 32: 330 (profiles/README.md).  0 switches it off.
+_CHAIN_POOL_CW = int(os.environ.get('S3GRL_CHAIN_POOL_CW', '16') or 0)
 _STRATEGY = {None: L.STRATEGY_NONE, '': L.STRATEGY_NONE, 'intersection': L.STRATEGY_INTERSECTION,
              'union': L.STRATEGY_UNION}
 _FLOW = {'PoS': L.FLOW_POS, 'SoP': L.FLOW_SOP}

@@ -553,6 +553,14 @@ def test_union_chain_pooled_route(monkeypatch, pool_cw, split, N, E, F, h, K, L)
     c = precompute(g, links, h, K, 'PoS', 'union', batch_records=5)
     assert int(g.chain_pool()[1].sum()) == 0                           # every slot released
     assert torch.equal(b.row_ptr, c.row_ptr) and all(torch.equal(x, y) for x, y in zip(b.xs, c.xs))
+    # level 1 straight from the feature matrix instead of a stored y_0: the same bits (the product is rounded before the sum)
+    monkeypatch.setenv('S3GRL_CHAIN_POOL_X', '1')
+    d = precompute(g, links, h, K, 'PoS', 'union', batch_records=7)
+    monkeypatch.setenv('S3GRL_CHAIN_SMEM_X', '1')                      # ... and for the records with shared-memory buffers
+    d = precompute(g, links, h, K, 'PoS', 'union', batch_records=7)
+    monkeypatch.setenv('S3GRL_CHAIN_POOL_X', '0')
+    monkeypatch.setenv('S3GRL_CHAIN_SMEM_X', '0')
+    assert torch.equal(b.row_ptr, d.row_ptr) and all(torch.equal(x, y) for x, y in zip(b.xs, d.xs))
     assert torch.equal(a.row_ptr, b.row_ptr) and torch.equal(a.xs[0], b.xs[0])
     ref = orc.pos_precompute(links, h, A, X, K, 'union')
     for k in range(1, K + 1):
