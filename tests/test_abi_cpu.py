@@ -95,6 +95,20 @@ def test_argument_validation_of_the_wider_entry_points(lib):
     assert lib.s3_plan_full(ctypes.byref(b), None) == L.S3_ERR_INVALID_ARG                      # no row_ptr
     # s3_ccn_chain serves the union strategy only
     assert lib.s3_ccn_chain(ctypes.byref(g), ctypes.byref(b), 0, out, 5, 0, None) == L.S3_ERR_NOT_IMPLEMENTED
+    # s3_ccn_chain_pooled: the same rules, then the pool (slots of a multiple of 32 floats, flags, threshold 4..32)
+    pooled = lambda *pool: lib.s3_ccn_chain_pooled(ctypes.byref(g), ctypes.byref(b), 0, out, 5, 0, *pool, None)      # noqa: E731
+    assert pooled(P(128), P(16), 64 * 100, 4, 8) == L.S3_ERR_NOT_IMPLEMENTED
+    b.strategy, b.row_ptr = L.STRATEGY_UNION, 16
+    assert pooled(None, None, 0, 0, 0) == L.S3_OK                                   # no pool, no records: s3_ccn_chain
+    assert pooled(P(128), P(16), 64 * 100, 4, 8) == L.S3_OK
+    assert pooled(None, P(16), 64 * 100, 4, 8) == L.S3_ERR_INVALID_ARG              # slots without a pool
+    assert pooled(P(128), None, 64 * 100, 4, 8) == L.S3_ERR_INVALID_ARG             # ... without flags
+    assert pooled(P(128), P(16), 6401, 4, 8) == L.S3_ERR_INVALID_ARG                # slot size not a multiple of 32 floats
+    assert pooled(P(128), P(16), 32, 4, 8) == L.S3_ERR_INVALID_ARG                  # no record fits a slot of 32 floats
+    assert pooled(P(128), P(16), 64 * 100, 4, 2) == L.S3_ERR_INVALID_ARG            # threshold below the narrowest sub-chunk
+    assert pooled(P(128), P(16), 64 * 100, 4, 64) == L.S3_ERR_INVALID_ARG
+    assert pooled(P(128), P(16), 64 * 100, -1, 8) == L.S3_ERR_INVALID_ARG
+    b.strategy, b.row_ptr = L.STRATEGY_NONE, None
     # s3_joint_rows: operator count, leading dimensions
     assert lib.s3_joint_rows(out, 0, 5, 5, P(16), P(16), 1, None, 2, P(16), 20, None, None) == L.S3_ERR_INVALID_ARG
     assert lib.s3_joint_rows(out, 4, 5, 4, P(16), P(16), 1, None, 2, P(16), 20, None, None) == L.S3_ERR_INVALID_ARG   # ld_src < cols
@@ -190,6 +204,15 @@ def test_chain_placement_by_record_size(lib):
         bytes_needed = 4 * (2 * n * cw + 3 * n + min(n, 40) + (5 * n + 2) // 2 + 8)
         assert bytes_needed <= (54, 110, 222)[cls] * 1024
         last = (cw, cls)
+
+
+def test_chain_pool_slot_holds_every_record_the_chain_serves(lib):
+    """engine.DeviceGraph.CHAIN_SLOT_FLOATS: a pool slot takes two [n][32] buffers of the largest record s3_chain_shape
+    places in shared memory (those are the records the pooled route can take over)."""
+    from s3grl_b200.engine import DeviceGraph
+    assert DeviceGraph.CHAIN_SLOT_FLOATS % 32 == 0
+    largest = max(n for n in range(2, 7000) if lib.s3_chain_shape(n, 0, 2) >= 0)     # no edges, two hop-<=1 nodes: the largest n
+    assert 64 * largest <= DeviceGraph.CHAIN_SLOT_FLOATS, largest
 
 
 def test_per_hop_cap_counts_match_the_reference_formula():
