@@ -8,13 +8,13 @@
 // as ONE kernel: pooled[i, :] = bn(elu(X[2i] W^T + b)) * bn(elu(X[2i+1] W^T + b)).  The remaining
 // link_pred_mlp works on [L, 256] and stays with the caller.
 //
-// Persistent CTAs (one per SM) over 128-row tiles of X, N = 256 output channels, TF32 inputs straight from the fp32 joint matrix
+// Persistent CTAs (one per SM) over 256-row tiles of X, N = 256 output channels, TF32 inputs straight from the fp32 joint matrix
 // (no conversion pass), fp32 accumulation in TMEM:
-//   warp 0    TMA producer: cp.async.bulk.tensor 2-D boxes [128 x 32] of X and [256 x 32] of W (128-byte
-//             swizzle), 4-stage mbarrier ring (48 KB per stage); the K tail is zero-filled by TMA
+//   warp 0    TMA producer: cp.async.bulk.tensor 2-D boxes, two [128 x 32] of X and one [256 x 32] of W (128-byte
+//             swizzle), 3-stage mbarrier ring (64 KB per stage); the K tail is zero-filled by TMA
 //   warp 1    allocates all 512 TMEM columns (two accumulators), one lane issues tcgen05.mma.kind::tf32 (M128 N256 K8,
-//             4 per stage), tcgen05.commit releases the stage / signals the accumulator
-//   warps 2-9 epilogue of the PREVIOUS tile while the next one accumulates: tcgen05.ld 32x32b (one accumulator row
+//             2 x 4 per stage: both row halves share the weight stage), tcgen05.commit releases the stage / signals the accumulator
+//   warps 2-9 epilogue (the TMA loads of the next tile run ahead meanwhile; its MMAs wait for acc_empty): tcgen05.ld 32x32b (one accumulator row
 //             per thread), bias + ELU + BN affine in registers, the two rows of a link meet by one shuffle,
 //             128-byte vector stores of the product
 // The GEMM is HBM-bound on X (4*(K+1)F' bytes per row against 2*256*(K+1)F' flops): tensor cores are what
