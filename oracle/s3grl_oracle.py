@@ -149,12 +149,14 @@ def _induced_masked(nodes, A):
     return lrowptr, lcol
 
 
-def select_rows(lrowptr, lcol, strategy):
+def select_rows(lrowptr, lcol, strategy, compat_explicit_zero=False):
     """Row selection, tuned_SIGN.py:173 (PoS) and :228-238 (PoS Plus).
     strategy None -> [0,1]; 'intersection' -> [0,1] + common neighbours of local 0 and 1 in
     the masked subgraph; 'union' -> [0,1] + (N(0) ∪ N(1)) − {0,1} (paper semantics; the
     reference code raises for union, SURVEY.md A.4, and with its literal repaired additionally repeats
-    rows 0 and 1 — module docstring).  Extra rows ascending local id."""
+    rows 0 and 1 — module docstring; compat_explicit_zero=True restates that literal selection,
+    [0,1] + sorted({0,1} ∪ N(0) ∪ N(1)): utils.py:78-79 leave explicit zeros at [0,1] and [1,0], which
+    `neighbors` reports).  Extra rows ascending local id."""
     if strategy is None:
         return np.array([0, 1], dtype=np.int32)
     n0 = lcol[lrowptr[0]:lrowptr[1]]
@@ -166,6 +168,8 @@ def select_rows(lrowptr, lcol, strategy):
     else:
         raise NotImplementedError(f"check strat {strategy}")
     extra = extra[extra > 1]
+    if compat_explicit_zero and strategy == 'union':
+        extra = np.concatenate([[0, 1], extra])
     return np.concatenate([[0, 1], extra]).astype(np.int32)
 
 
@@ -181,7 +185,7 @@ def normalized_subgraph(lrowptr, lcol, dtype=np.float32):
     return ssp.csr_matrix((vals, lcol, lrowptr), shape=(n, n)), dis
 
 
-def pos_link(src, dst, num_hops, A, X, K, strategy=None, dtype=np.float32, caps=None):
+def pos_link(src, dst, num_hops, A, X, K, strategy=None, dtype=np.float32, caps=None, compat_explicit_zero=False):
     """One link through the optimised PoS / PoS-Plus flow (tuned_SIGN.py:147-187, :202-260).
     caps: None or dict(ratio_per_hop=, max_nodes_per_hop=, cap_seed=) for k_hop_subgraph.
 
@@ -189,7 +193,7 @@ def pos_link(src, dst, num_hops, A, X, K, strategy=None, dtype=np.float32, caps=
     nodes, hops, lrowptr, lcol = k_hop_subgraph(src, dst, num_hops, A, **(caps or {}))
     n = nodes.size
     S, _ = normalized_subgraph(lrowptr, lcol, dtype)
-    sel = select_rows(lrowptr, lcol, strategy)
+    sel = select_rows(lrowptr, lcol, strategy, compat_explicit_zero)
     label = np.zeros((n, 1), dtype=dtype)
     label[:2] = 1                                   # zero-one label, tuned_SIGN.py:177
     subg_x = np.hstack([label, np.asarray(X[nodes], dtype=dtype)])
@@ -255,13 +259,14 @@ def scaled_pos_precompute(links, sets, A, X, K, dtype=np.float32, keep_graphs=Fa
     return out
 
 
-def pos_precompute(links, num_hops, A, X, K, strategy=None, dtype=np.float32, keep_graphs=False, caps=None):
+def pos_precompute(links, num_hops, A, X, K, strategy=None, dtype=np.float32, keep_graphs=False, caps=None,
+                   compat_explicit_zero=False):
     """Whole call of get_PoS_prepped_ds / get_PoS_Plus_prepped_ds over `links` [2, L], in the
     collated layout PyG's InMemoryDataset.collate produces:
     K+1 row-stacked [R, F+1] arrays and row_ptr [L+1]."""
     links = np.asarray(links)
     L = links.shape[1]
-    per = [pos_link(int(links[0, i]), int(links[1, i]), num_hops, A, X, K, strategy, dtype, caps)
+    per = [pos_link(int(links[0, i]), int(links[1, i]), num_hops, A, X, K, strategy, dtype, caps, compat_explicit_zero)
            for i in range(L)]
     row_ptr = np.zeros(L + 1, dtype=np.int64)
     row_ptr[1:] = np.cumsum([p['sel'].size for p in per])

@@ -46,6 +46,24 @@ def test_hybrid_matches_reference(name):
         assert_features_close(out['xs'][k], c.xs[k], what=f'{name} x{k}')
 
 
+@pytest.mark.parametrize('name', [n for n in case_names('pos') if 'union' in n])
+def test_union_literal_rows_of_the_repaired_reference(name):
+    """The `union` fixtures hold the reference's LITERAL rows (its label-column literal repaired): src and dst selected a
+    second time.  The oracle's compat_explicit_zero restates that selection as [0, 1, 0, 1, CCN rows]; the fixtures list the
+    rows beyond the first two in ascending global id."""
+    c = Case(name)
+    assert c.reference_repair.startswith('tuned_SIGN.py:243')
+    out = orc.pos_precompute(c.links, c.num_hops, c.A, c.X, c.K, 'union', keep_graphs=True, compat_explicit_zero=True)
+    assert np.array_equal(out['row_ptr'], c.literal_row_ptr)
+    for i, g in enumerate(out['graphs']):
+        a, b = int(c.literal_row_ptr[i]), int(c.literal_row_ptr[i + 1])
+        gid = g['nodes'][g['sel']]
+        order = np.concatenate([[0, 1], 2 + np.argsort(gid[2:], kind='stable')])
+        assert np.array_equal(gid[order], c.literal_row_gid[a:b])
+        for k in range(c.K + 1):
+            assert_features_close(g['xs'][k][order], c.literal_xs[k][a:b], what=f'{name} link {i} x{k}')
+
+
 def test_union_rule_is_superset_of_intersection():
     c = Case('usair_posplus')
     inter = orc.pos_precompute(c.links[:, :20], c.num_hops, c.A, c.X, c.K, 'intersection', keep_graphs=True)
