@@ -716,7 +716,9 @@ class _Call:
                             DeviceGraph.CHAIN_SLOT_FLOATS, slots, _CHAIN_POOL_CW, st)
             else:
                 self.launch('ccn_chain', bi, 's3_ccn_chain', g, C.byref(batch), nrec, ptrs, self.F1, 0, st)
-            self.stats['launches'] += 1
+            # kernels of one call: prep, the global-memory class (+ its launches by CSR size with a pool), three CTA sizes
+            split = min(2, max(0, int(os.environ.get('S3GRL_CHAIN_POOL_SPLIT', '2') or 0))) if _CHAIN_POOL_CW else 0
+            self.stats['launches'] += 5 + split
         if items:       # CCN rows: extra work items of 2 (intersection) or 8 (union) selected rows each
             L.check(self.lib.s3_plan_items(C.byref(batch), st), 's3_plan_items')
             self.launch('diffuse', bi, 's3_diffuse', g, C.byref(batch), items, st)
