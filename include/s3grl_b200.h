@@ -284,7 +284,11 @@ int s3_ccn_chain(const s3_graph* g, const s3_batch* b, int64_t num_records, floa
  * sub-chunk width CW <= pool_cw (4, 8, 16 or 32: s3_chain_shape & 255) keeps its CSR in shared memory and takes its two
  * [n][32] operator buffers from one of pool_slots slots of slot_floats floats each (a slot serves records with
  * 64 * n <= slot_floats; slot_floats a multiple of 32; pool 128-byte aligned), read and written through L2. pool_busy
- * [pool_slots] int32 must be zero on entry and is zero again when the kernels have finished. pool_slots == 0: s3_ccn_chain. */
+ * [pool_slots] int32 must be zero on entry and is zero again when the kernels have finished. pool_slots == 0: s3_ccn_chain.
+ * Records with buffers in global memory (pooled or in their own arena scratch) form level 1's input D^-1/2 [X | label] from
+ * the feature matrix instead of storing it (same bits). A/B knobs read from the environment at every call, defaults in
+ * brackets: S3GRL_CHAIN_POOL_SPLIT [2] pooled launches by CSR size, S3GRL_CHAIN_POOL_X [1] / S3GRL_CHAIN_SMEM_X [0] level 1
+ * from the feature matrix for global- / shared-memory buffers, S3GRL_CHAIN_POLICY [0], S3GRL_CHAIN_SLABS [1]. */
 int s3_ccn_chain_pooled(const s3_graph* g, const s3_batch* b, int64_t num_records, float* const* out, int64_t ldo,
                         int64_t row_base, float* pool, int32_t* pool_busy, int64_t slot_floats, int32_t pool_slots,
                         int32_t pool_cw, void* stream);
