@@ -48,14 +48,55 @@ def _quiet():
         yield
 
 
-def ref_k_hop(src, dst, num_hops, A):
+class _RandomWithRankRule:
+    """Stand-in for the name `random` inside the reference's utils module while its per-hop caps are exercised.
+    utils.py:66-70 draws the nodes a hop keeps with `random.sample(fringe, k)` on a SET — no reproducible semantics, and a
+    TypeError on Python >= 3.11.  This proxy forwards everything to `random` and makes `sample` return the k elements of
+    the population with the smallest fmix32(node XOR seed): the framework's deterministic rule (include/s3grl_b200.h,
+    oracle.hash_rank).  Everything else of the capped BFS — the counts int(ratio * len) and max_nodes_per_hop, their
+    order, that dropped nodes stay visited, the early exit — is the reference's own code."""
+
+    def __init__(self, real, seed):
+        self._real, self._seed = real, int(seed)
+        self.calls = 0
+
+    def __getattr__(self, name):
+        return getattr(self._real, name)
+
+    def sample(self, population, k):
+        from oracle import s3grl_oracle as orc
+        self.calls += 1
+        pop = np.asarray(sorted(int(v) for v in population), dtype=np.int64)
+        if k > pop.size:
+            raise ValueError("Sample larger than population or is negative")
+        keep = np.argsort(orc.hash_rank(pop, self._seed), kind='stable')[:k]
+        return [int(v) for v in pop[keep]]
+
+
+@contextlib.contextmanager
+def cap_sampler_ranked(seed=0):
+    """Within the block the reference's `random.sample` follows the rank rule (see _RandomWithRankRule)."""
+    utils, _ = load_reference()
+    real = utils.random
+    proxy = _RandomWithRankRule(real, seed)
+    utils.random = proxy
+    try:
+        yield proxy
+    finally:
+        utils.random = real
+
+
+def ref_k_hop(src, dst, num_hops, A, ratio_per_hop=1.0, max_nodes_per_hop=None, cap_seed=0):
     """Reference k_hop_subgraph (utils.py:47-85) -> canonical
     (nodes int64 [n], hops int32 [n], edges int64 [m,2] of GLOBAL ids sorted by canonical
     (local row, local col)).  Edges are the non-zero entries `ssp.find` returns
-    (tuned_SIGN.py:153), i.e. after the target-link mask."""
+    (tuned_SIGN.py:153), i.e. after the target-link mask.  With caps the reference's sampler is the rank rule
+    (cap_sampler_ranked); without, the unmodified code runs."""
     import scipy.sparse as ssp
     utils, _ = load_reference()
-    nodes, sub, dists, _, _ = utils.k_hop_subgraph(src, dst, num_hops, A)
+    capped = (ratio_per_hop is not None and ratio_per_hop < 1.0) or max_nodes_per_hop is not None
+    with (cap_sampler_ranked(cap_seed) if capped else contextlib.nullcontext()):
+        nodes, sub, dists, _, _ = utils.k_hop_subgraph(src, dst, num_hops, A, ratio_per_hop, max_nodes_per_hop)
     nodes = np.asarray(nodes, dtype=np.int64)
     dists = np.asarray(dists, dtype=np.int32)
     order = np.concatenate([[0, 1], 2 + np.lexsort((nodes[2:], dists[2:]))]).astype(np.int64)
@@ -112,20 +153,27 @@ def _sign_kwargs(K, strategy):
             'k_heuristic': 0 if strategy is None else 1, 'k_node_set_strategy': strategy}
 
 
-def ref_pos(links, num_hops, A, X, K, strategy=None, repair_union_typo=False):
+def ref_pos(links, num_hops, A, X, K, strategy=None, repair_union_typo=False, caps=None):
     """get_PoS_prepped_ds / get_PoS_Plus_prepped_ds (tuned_SIGN.py:137-262) through
     extract_enclosing_subgraphs (utils.py:446-496) -> dict(xs, row_ptr, row_gid) with the rows
     of every link put in canonical order: row 0 = src, row 1 = dst, extra rows by ascending
     global id (== ascending canonical local id, all extra rows being hop-1 nodes).
     strategy='union' runs the UNMODIFIED reference unless repair_union_typo=True (union_typo_repaired above): unmodified,
-    it raises ValueError at tuned_SIGN.py:243 for every link whose subgraph does not have exactly 3 nodes."""
+    it raises ValueError at tuned_SIGN.py:243 for every link whose subgraph does not have exactly 3 nodes.
+    caps = dict(ratio_per_hop=, max_nodes_per_hop=, cap_seed=): the reference's per-hop caps with its sampler replaced by
+    the rank rule (cap_sampler_ranked); PoS only (the row recovery of PoS Plus below re-runs an uncapped BFS)."""
     utils, tuned = load_reference()
+    caps = dict(caps or {})
+    ratio, max_nodes = caps.get('ratio_per_hop', 1.0), caps.get('max_nodes_per_hop')
+    if caps and strategy is not None:
+        raise NotImplementedError("caps with PoS Plus are not wired through ref_pos")
     link_index = torch.as_tensor(np.asarray(links), dtype=torch.long)
     x = torch.as_tensor(np.asarray(X), dtype=torch.float32)
     ctx = union_typo_repaired() if (repair_union_typo and strategy == 'union') else contextlib.nullcontext()
-    with _quiet(), ctx:
+    ctx2 = cap_sampler_ranked(caps.get('cap_seed', 0)) if caps else contextlib.nullcontext()
+    with _quiet(), ctx, ctx2:
         data_list = utils.extract_enclosing_subgraphs(
-            link_index, A, x, 1, num_hops, 'zo', 1.0, None, False, None, None,
+            link_index, A, x, 1, num_hops, 'zo', ratio, max_nodes, False, None, None,
             _sign_kwargs(K, strategy), powers_of_A=[], data=None)
     xs = [[] for _ in range(K + 1)]
     row_ptr, row_gid = [0], []

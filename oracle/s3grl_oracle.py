@@ -83,7 +83,9 @@ def hash_rank(nodes, seed=0):
 def cap_fringe(fringe, ratio_per_hop, max_nodes_per_hop, seed=0):
     """utils.py:66-70 with a DETERMINISTIC rule in place of random.sample (which has no reproducible semantics and
     raises on Python >= 3.11): the hop keeps k = min(int(ratio * len), max) nodes — the reference's
-    counts — and they are the k nodes of the fringe with the smallest hash_rank.  Returned ascending."""
+    counts — and they are the k nodes of the fringe with the smallest hash_rank.  Returned ascending.
+    Pinned by tests/test_oracle_vs_reference.py against the reference's own capped BFS with its `random.sample` replaced
+    by this rule (oracle/ref_runner.cap_sampler_ranked)."""
     k = fringe.size
     if ratio_per_hop is not None and ratio_per_hop < 1.0:
         k = int(ratio_per_hop * fringe.size)

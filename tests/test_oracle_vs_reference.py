@@ -3,7 +3,8 @@ by oracle/ref_runner.py) on generated graphs — SURVEY.md §4 / §8c.  The comm
 draws new graphs and links every run (hypothesis, derandomised so that CI is reproducible) and compares node sets,
 hop labels, induced + masked edge sets (bit-exact) and operators (1e-5 of max|ref|) for PoS, PoS Plus intersection,
 PoS Plus union (the reference's ragged label-column literal at tuned_SIGN.py:243 repaired at run time, and — unmodified —
-on the 3-node subgraphs it happens to accept), SoP, hybrid and the non-optimised flow.  Build-container only: skipped where the reference checkout is absent
+on the 3-node subgraphs it happens to accept), the per-hop caps (the reference's `random.sample` replaced by the rank rule),
+SoP, hybrid and the non-optimised flow.  Build-container only: skipped where the reference checkout is absent
 (the GPU box), and never imported by the product."""
 import numpy as np
 import pytest
@@ -54,6 +55,29 @@ def test_k_hop_subgraph_sets(gl, num_hops, _k):
         rows = np.repeat(np.arange(gn.size), np.diff(lrowptr))
         e = np.stack([gn[rows], gn[lcol]], 1) if lcol.size else np.zeros((0, 2), np.int64)
         assert np.array_equal(e, edges)
+
+
+@settings(**SETTINGS)
+@given(graph_and_links(), st.integers(1, 3), st.sampled_from([(0.5, None), (1.0, 3), (0.7, 4), (0.34, 1), (1.0, 1)]), st.integers(0, 5))
+def test_per_hop_caps_with_the_reference_sampler_ranked(gl, num_hops, cap, seed):
+    """ratio_per_hop / max_nodes_per_hop (utils.py:66-70).  The reference's `random.sample` on a set cannot be reproduced
+    (and raises on Python >= 3.11); with ONLY that call replaced by the framework's rank rule (ref_runner.cap_sampler_ranked)
+    the reference's capped BFS — its counts, their order, dropped nodes staying visited, the early exit — and the oracle's
+    agree bit for bit on node sets, hop labels, edges, and within 1e-5 on the PoS operators."""
+    A, X, links = gl
+    ratio, max_nodes = cap
+    caps = dict(ratio_per_hop=ratio, max_nodes_per_hop=max_nodes, cap_seed=seed)
+    for u, v in links.T.tolist():
+        nodes, hops, edges = rr.ref_k_hop(u, v, num_hops, A, ratio, max_nodes, seed)
+        gn, gh, lrowptr, lcol = orc.k_hop_subgraph(u, v, num_hops, A, **caps)
+        assert np.array_equal(gn, nodes) and np.array_equal(gh, hops)
+        rows = np.repeat(np.arange(gn.size), np.diff(lrowptr))
+        e = np.stack([gn[rows], gn[lcol]], 1) if lcol.size else np.zeros((0, 2), np.int64)
+        assert np.array_equal(e, edges)
+    ref = rr.ref_pos(links, num_hops, A, X, 3, None, caps=caps)
+    out = orc.pos_precompute(links, num_hops, A, X, 3, None, caps=caps)
+    for k in range(4):
+        assert_features_close(out['xs'][k], ref['xs'][k], what=f'x{k}')
 
 
 @settings(**SETTINGS)
