@@ -217,6 +217,43 @@ def round2_cases():
     make_case('router_pos_k5', A, sample_links(splits, 60, 13), 'pos', 5, 2, None, x_spec='synthetic:32:0.5:8')
 
 
+def caps_case():
+    """Per-hop caps (utils.py:66-70): the reference's capped BFS + PoS with ONLY its `random.sample` replaced by the
+    framework's rank rule (oracle/ref_runner.cap_sampler_ranked).  flow = 'pos_caps', so the uncapped PoS tests skip it."""
+    edges, N, _ = ds.load_graph('usair')
+    A, splits = ds.split_links(edges, N, seed=1)
+    A = A.tocsr()
+    A.sort_indices()
+    links = np.ascontiguousarray(sample_links(splits, 40, 31), dtype=np.int64)
+    caps = dict(ratio_per_hop=0.6, max_nodes_per_hop=12, cap_seed=5)
+    h, K, x_spec = 2, 3, 'synthetic:16:0.5:6'
+    feats = features_from_spec(x_spec, A, N)
+    r = rr.ref_pos(links, h, A, feats, K, None, caps=caps)
+    node_ptr, edge_ptr, nodes, hops, edge_list = [0], [0], [], [], []
+    for i in range(links.shape[1]):
+        cn, hp, ed = rr.ref_k_hop(int(links[0, i]), int(links[1, i]), h, A, caps['ratio_per_hop'], caps['max_nodes_per_hop'],
+                                  caps['cap_seed'])
+        nodes.append(cn)
+        hops.append(hp)
+        edge_list.append(ed)
+        node_ptr.append(node_ptr[-1] + cn.size)
+        edge_ptr.append(edge_ptr[-1] + ed.shape[0])
+    out = dict(indptr=A.indptr.astype(np.int64), indices=A.indices.astype(np.int32), adata=A.data.astype(np.int64),
+               num_nodes=np.int64(N), links=links, num_hops=np.int64(h), K=np.int64(K), flow=np.str_('pos_caps'),
+               strategy=np.str_(''), row_ptr=r['row_ptr'], row_gid=r['row_gid'], x_spec=np.str_(x_spec),
+               node_ptr=np.asarray(node_ptr, np.int64), edge_ptr=np.asarray(edge_ptr, np.int64),
+               nodes=np.concatenate(nodes).astype(np.int32), hops=np.concatenate(hops).astype(np.int8),
+               edges=np.concatenate(edge_list, 0).astype(np.int32), ratio_per_hop=np.float64(caps['ratio_per_hop']),
+               max_nodes_per_hop=np.int64(caps['max_nodes_per_hop']), cap_seed=np.int64(caps['cap_seed']),
+               reference_repair=np.str_("utils.py:67,70 `random.sample` replaced by the rank rule (smallest fmix32(node ^ seed)) by "
+                                        "oracle/ref_runner.cap_sampler_ranked at run time; /root/reference unmodified on disk"))
+    for k, x in enumerate(r['xs']):
+        out[f'x{k}'] = x.astype(np.float32)
+    path = os.path.join(OUT, 'ref_usair_pos_caps.npz')
+    np.savez_compressed(path, **out)
+    print(f"usair_pos_caps: L={links.shape[1]} nodes={node_ptr[-1]} -> {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 def union_cases():
     """PoS Plus `union` (BASELINE config 3) against the reference with its label-column literal repaired: hand graphs,
     USAir, Cora and the PubMed graph with the bench's F = 500 feature spec."""
@@ -241,6 +278,9 @@ def main():
         return
     if '--union' in sys.argv:           # only the union fixtures (round 2, third session)
         union_cases()
+        return
+    if '--caps' in sys.argv:
+        caps_case()
         return
     make_posneg_case()
     A, links, X = tiny_graphs()
@@ -279,6 +319,7 @@ def main():
     make_case('power_pos_k5', A, sample_links(splits, 100, 4), 'pos', 5, 2, None, x_spec='synthetic:8:1.0:9')
     round2_cases()
     union_cases()
+    caps_case()
 
 
 if __name__ == '__main__':

@@ -52,7 +52,10 @@ class Case:
             self.rw_m, self.rw_M = int(d['rw_m']), int(d['rw_M'])
         if self.flow == 'full':
             self.node_label, self.node_id = str(d['node_label']), d['node_id']
-        if self.flow == 'pos':
+        if self.flow == 'pos_caps':
+            self.caps = dict(ratio_per_hop=float(d['ratio_per_hop']), max_nodes_per_hop=int(d['max_nodes_per_hop']),
+                             cap_seed=int(d['cap_seed']))
+        if self.flow in ('pos', 'pos_caps'):
             self.row_gid = d['row_gid']
             self.node_ptr, self.edge_ptr = d['node_ptr'], d['edge_ptr']
             self.nodes, self.hops, self.edges = d['nodes'], d['hops'], d['edges']

@@ -25,6 +25,27 @@ def test_pos_flows_match_reference(name):
         assert np.array_equal(g['nodes'][g['sel']], c.row_gid[c.row_ptr[i]:c.row_ptr[i + 1]])
 
 
+@pytest.mark.parametrize('name', case_names('pos_caps'))
+def test_per_hop_caps_match_the_reference_with_its_sampler_ranked(name):
+    """ratio_per_hop / max_nodes_per_hop: the fixture is the reference's own capped BFS + PoS with only `random.sample`
+    replaced by the rank rule (oracle/make_goldens.caps_case); node lists, hop labels, edges bit-exact, operators 1e-5."""
+    c = Case(name)
+    assert 'random.sample' in c.reference_repair
+    out = orc.pos_precompute(c.links, c.num_hops, c.A, c.X, c.K, None, keep_graphs=True, caps=c.caps)
+    assert np.array_equal(out['row_ptr'], c.row_ptr)
+    uncapped = 0
+    for i, g in enumerate(out['graphs']):
+        a, b = c.node_ptr[i], c.node_ptr[i + 1]
+        assert np.array_equal(g['nodes'], c.nodes[a:b]) and np.array_equal(g['hops'], c.hops[a:b]), f'{name} link {i}'
+        rows = np.repeat(np.arange(g['nodes'].size), np.diff(g['lrowptr']))
+        e = np.stack([g['nodes'][rows], g['nodes'][g['lcol']]], 1)
+        assert np.array_equal(e, c.edges[c.edge_ptr[i]:c.edge_ptr[i + 1]]), f'{name} link {i} edges'
+        uncapped += orc.k_hop_subgraph(int(c.links[0, i]), int(c.links[1, i]), c.num_hops, c.A)[0].size
+    assert uncapped > 2 * int(c.node_ptr[-1]), "the caps must bite on this fixture"
+    for k in range(c.K + 1):
+        assert_features_close(out['xs'][k], c.xs[k], what=f'{name} x{k}')
+
+
 @pytest.mark.parametrize('name', case_names('sop'))
 def test_sop_matches_reference(name):
     c = Case(name)
