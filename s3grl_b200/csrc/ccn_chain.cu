@@ -644,6 +644,7 @@ __global__ void __launch_bounds__(T, 1024 / T) chain_kernel(ChainParams p) {
         else chain_columns<4, T>(p, r, buf0, c0, c1);
     }
     if (SPILL && pooled) {
+        __threadfence();  // this thread's stores to the slot are performed before the slot is handed to another CTA
         __syncthreads();  // every thread's last reads of the slot
         if (tid == 0) atomicExch(&p.pool_busy[s_slot], 0);
     }
